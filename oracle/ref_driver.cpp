@@ -94,6 +94,15 @@ static void dump_pairs(wfc::File & out, const char * name, Array<Array<std::pair
     out.put_l(name, flat.data(), flat.size());
 }
 
+static void zero_uninitialised(SPH::Particle * P)
+{
+    // Scalars the reference's Particle constructor leaves uninitialised (Source/Particle.cpp:28-158 never assigns
+    // them) but reads before writing, e.g. T += dt*dTdt in the first ThermalCalcs (Source/Thermal.cpp:728). Give them
+    // the value a fresh zero page would, so runs are reproducible.
+    P->dTdt = 0.0; P->delta_cont = 0.0; P->q_fric_work = 0.0; P->dkin_energy_dt = 0.0; P->dint_energy_dt = 0.0;
+    P->Et = 0.0; P->Et_m = 0.0; P->T = 0.0; P->k_T = 0.0; P->cp_T = 0.0; P->h_conv = 0.0; P->T_inf = 0.0;
+}
+
 int main(int argc, char ** argv) try
 {
     if (argc < 3) { std::fprintf(stderr, "usage: wf_ref <case.wfc> <out.wfc>\n"); return 2; }
@@ -135,6 +144,8 @@ int main(int argc, char ** argv) try
         dom.solid_part_count = (int)n;
     }
     const size_t nsph = dom.Particles.Size();
+    for (size_t i = 0; i < nsph; ++i) zero_uninitialised(dom.Particles[i]);
+    dom.contact_force_sum = 0.0; dom.contact_reaction_sum = 0.0; dom.max_disp = Vec3_t(0., 0., 0.);   // uninitialised in Domain::Domain (Source/Domain.cpp:78-175)
 
     // materials table: [model, E, nu, p0..p12] per row of 16
     std::vector<Material_ *> mats; std::vector<Elastic_ *> els;
@@ -183,6 +194,7 @@ int main(int argc, char ** argv) try
         if (in.has(key)) { const std::vector<double> & a_ = in.f(key); mv.v[0] = a_[0]; mv.v[1] = a_[1]; mv.v[2] = a_[2]; mv.tau = a_[3]; }
         g_meshvel.push_back(mv);
     }
+    for (size_t i = nsph; i < dom.Particles.Size(); ++i) zero_uninitialised(dom.Particles[i]);
     dom.contact = in.scalar("contact", mesh_count > 0 ? 1 : 0) != 0.0;
     dom.friction_sta = in.scalar("friction_sta", 0.0);
     dom.friction_dyn = in.scalar("friction_dyn", 0.0);

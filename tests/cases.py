@@ -1,0 +1,126 @@
+"""Case builders shared by the tests, the golden-fixture generator and bench.py.
+
+A "case" is a flat dict of WFC1 records (see tests/wfc.py, oracle/ref_driver.cpp): lattice generator arguments taken
+from the reference's example drivers plus per-particle property arrays, exactly what those drivers assign in their
+`for (a < dom.Particles.Size())` loops.
+"""
+import numpy as np
+
+BILINEAR, HOLLOMON, JOHNSON_COOK = 0, 1, 2
+
+
+def cylinder_points(V, Rxy, Lz, r):
+    """numpy restatement of the lattice of Domain::AddCylinderLength (Source/Domain.cpp:708-792); used only to size
+    per-particle arrays in case dicts -- positions themselves always come from the implementation under test."""
+    def half(r, R, xinc):
+        yp, xp, c = r, r + (xinc - 1) * 2.0 * r, 1
+        while np.sqrt(yp * yp + xp * xp) <= R - r:
+            yp += 2.0 * r
+            c += 1
+        return c - 1
+    npxy = half(r, Rxy, 1)
+    pts = []
+    zp = V[2] + r
+    while zp <= V[2] + Lz - r:
+        yp = V[1] - r - 2.0 * r * (npxy - 1)
+        yinc, sign = npxy, -1
+        for _ in range(2 * npxy):
+            nx = half(r, Rxy, yinc)
+            xp = V[0] - r - 2.0 * r * (nx - 1)
+            for _ in range(2 * nx):
+                pts.append((xp, yp, zp))
+                xp += 2.0 * r
+            yp += 2.0 * r
+            yinc += sign
+            if yinc < 1:
+                yinc, sign = 1, 1
+        zp += 2.0 * r
+    return np.array(pts, dtype=np.float64)
+
+
+def compression(dx=0.03, nsteps=1, thermal=True, pl_heating=True, alpha=1.0, beta=0.0, ti=0.3, gradient_type=0,
+                vmax=10.0, tau=0.005, cfl=0.2, fy=300.0e6, model=BILINEAR, t_field=True, ts_nb_inc=5):
+    """examples/Compression_thermal.cpp:71-169 scaled by dx (shipped dx = 0.015 -> 12 144 particles)."""
+    rho, K, G = 2700.0, 6.7549e10, 2.5902e10
+    R, L = 0.15, 0.56
+    h = 1.2 * dx
+    Cs = np.sqrt(K / rho)
+    V = (0.0, 0.0, -L / 10.0)
+    pts = cylinder_points(V, R, L + 2.0 * L / 10.0, dx / 2.0)
+    n = len(pts)
+    z = pts[:, 2]
+    ID = np.full(n, 1, np.int32)
+    ID[z < 0] = 2
+    ID[z > L] = 3
+    ones = np.ones(n)
+    case = dict(
+        gen_kind=1.0, gen_args=np.array([1, V[0], V[1], V[2], R, L + 2.0 * L / 10.0, dx / 2.0, rho, h, 0, 0], float),
+        Dimension=3.0, KernelType=0.0, GradientType=float(gradient_type), DomMax=np.array([L, -1e11, -1e11]), DomMin=np.array([-L, 1e11, 1e11]),
+        ID=ID, G=G * ones, Cs=Cs * ones, PresEq=np.zeros(n, np.int32), Material=np.full(n, 2, np.int32), Fail=np.ones(n, np.int32),
+        Sigmay=fy * ones, Alpha=alpha * ones, Beta=beta * ones, TI=ti * ones, TIInitDist=dx * ones,
+        k_T=150.0 * ones, cp_T=960.0 * ones, th_exp=0.0 * ones,
+        thermal_solver=float(thermal), pl_heating=float(pl_heating), pl_work_heat_frac=0.9, ts_nb_inc=float(ts_nb_inc),
+        dt=cfl * h / Cs, nsteps=float(nsteps), mode=0.0,
+        bc=np.array([3, 0, 0, -vmax, tau, 1, 0, 0, 2, 0, 0, 0, 0, 1, 0, 0], float),
+    )
+    # non-uniform initial temperature so that conduction is exercised (last bullet)
+    case["T"] = 20.0 + (15.0 * np.sin(7.0 * pts[:, 0]) * np.cos(5.0 * z) if t_field else 0.0) * ones
+    if model == HOLLOMON:
+        case["Material_model"] = np.full(n, HOLLOMON, np.int32)
+        case["mat_id"] = np.zeros(n, np.int32)
+        case["materials"] = np.array([HOLLOMON, 70.0e9, 0.3, fy, 6.79e8, 0.15] + [0.0] * 10)
+    elif model == JOHNSON_COOK:
+        case["Material_model"] = np.full(n, JOHNSON_COOK, np.int32)
+        case["mat_id"] = np.zeros(n, np.int32)
+        # A, B, n, C, eps_0, m, T_m, T_t  (6061-T6-like numbers as in examples/FSW.cpp:113-115 semantics)
+        case["materials"] = np.array([JOHNSON_COOK, 70.0e9, 0.3, fy, 114.0e6, 0.42, 0.002, 1.0, 1.34, 925.0, 0.0] + [0.0] * 5)
+    return case
+
+
+def perturbed(case, amp=5.0, seed=1):
+    """Give every particle a smooth non-zero initial velocity so that one step exercises every pair term."""
+    c = dict(case)
+    g = c["gen_args"]
+    pts = cylinder_points((g[1], g[2], g[3]), g[4], g[5], g[6])
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    v = np.stack([amp * np.sin(9.0 * y + seed) * np.cos(4.0 * z), amp * np.cos(8.0 * x - seed) * np.sin(3.0 * z), -amp * z * (1.0 + 0.3 * np.sin(11.0 * x * y))], axis=1)
+    c["v"] = v.reshape(-1)
+    return c
+
+
+def contact_compression(dx=0.0024, nsteps=1, friction=0.2, model=HOLLOMON, vmax=1.0, tau=0.0005, cfl=0.7, dens=20, ts_nb_inc=5):
+    """examples/Contact_Compression_1010.cpp:91-268 scaled by dx (shipped dx = 0.0012), gradKernelCorr off."""
+    rho, E, nu = 7850.0, 200.0e9, 0.3
+    K = E / (3.0 * (1.0 - 2 * nu))
+    G = E / (2.0 * (1.0 + nu))
+    R, L = 0.0127, 0.030
+    h = 1.2 * dx
+    Cs = np.sqrt(K / rho)
+    fy = 260.0e6
+    pts = cylinder_points((0.0, 0.0, 0.0), R, L, dx / 2.0)
+    n = len(pts)
+    ones = np.ones(n)
+    zmax = pts[-1, 2] + h
+    zmin = pts[0, 2] - h
+    case = dict(
+        gen_kind=1.0, gen_args=np.array([0, 0, 0, 0, R, L, dx / 2.0, rho, h, 0, 0], float),
+        Dimension=3.0, KernelType=0.0, GradientType=0.0, DomMax=np.array([L, -1e11, -1e11]), DomMin=np.array([-L, 1e11, 1e11]),
+        G=G * ones, Cs=Cs * ones, PresEq=np.zeros(n, np.int32), Fail=np.ones(n, np.int32), Sigmay=fy * ones,
+        Alpha=2.5 * ones, Beta=2.5 * ones, TI=0.3 * ones, TIInitDist=dx * ones,
+        Material_model=np.full(n, model, np.int32), mat_id=np.zeros(n, np.int32),
+        materials=np.array([HOLLOMON, E, nu, fy, 7.1568e8, 0.22] + [0.0] * 10),
+        contact=1.0, friction_sta=friction, friction_dyn=friction, PFAC=0.4, DFAC=0.0, ts_nb_inc=float(ts_nb_inc),
+        mesh_count=2.0,
+        mesh0_plane=np.array([2, 0, -1.5 * R, -1.5 * R, zmax, 1.5 * R, 1.5 * R, zmax, dens], float), mesh0_hfac=1.1, mesh0_id=10.0,
+        mesh0_vel=np.array([0, 0, -vmax, tau], float),
+        mesh1_plane=np.array([2, 1, -1.5 * R, -1.5 * R, zmin, 1.5 * R, 1.5 * R, zmin, dens], float), mesh1_hfac=1.1, mesh1_id=11.0,
+        mesh1_vel=np.array([0, 0, 0, 0], float),
+        dt=cfl * h / (Cs + vmax), nsteps=float(nsteps), mode=0.0,
+    )
+    return case
+
+
+FIELDS_F64 = ["x", "v", "a", "Displacement", "Density", "dDensity", "Pressure", "Sigma", "ShearStress", "StrainRate", "RotationRate",
+              "Strain", "Strain_pl", "TIR", "pl_strain", "Sigmay", "eff_strain_rate", "T", "dTdt", "q_plheat", "q_conv",
+              "contforce", "delta_cont", "normal", "dint_energy_dt", "dkin_energy_dt"]
+SCALARS = ["Time", "int_energy_sum", "plastic_work", "contact_force_sum", "contact_reaction_sum", "ext_forces_work", "max_disp"]

@@ -1,0 +1,182 @@
+/* weldform_b200 -- C ABI of the B200-native SPH hot path (libweldform_b200.so).
+ *
+ * The reference (luchete80/WeldForm) has no FFI boundary: it is a header-only unity build whose hot path is a set of
+ * SPH::Domain member functions called from Domain::SolveDiffUpdateFraser (Source/SolverFraser.cpp:133-505). This
+ * header is the boundary a maintainer would bind instead; each entry point names the reference member(s) it replaces.
+ * The host-side mirror of the reference's source API (weldform_b200/host/Domain.h ...) and the Python harness
+ * (weldform_b200/api.py, ctypes) both sit on top of exactly these symbols.
+ *
+ * Conventions: every function returns 0 on success or a negative wf_status; wf_last_error() gives the message.
+ * No function throws or calls back into the host. One wf_ctx per GPU; calls on a ctx come from one host thread at a
+ * time and are asynchronous on the ctx-owned stream unless stated; the caller owns host buffers, the ctx owns device
+ * buffers. Host arrays are always in PARTICLE CREATION ORDER (SPH particles first, rigid-mesh particles after, as
+ * Source/Contact.cpp:12 requires); the cell-sorted device order is internal. There is no CPU fallback.
+ */
+#ifndef WELDFORM_B200_H
+#define WELDFORM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wf_ctx wf_ctx;
+
+typedef enum wf_status {
+    WF_OK = 0,
+    WF_ERR_CUDA = -1,          /* a CUDA runtime call or kernel failed */
+    WF_ERR_ARG = -2,           /* bad argument / call order */
+    WF_ERR_UNSUPPORTED = -3,   /* feature of the reference outside the implemented scope (fails loudly) */
+    WF_ERR_NOMEM = -4
+} wf_status;
+
+/* Domain-level switches; defaults are those of Domain::Domain (Source/Domain.cpp:78-175). */
+typedef struct wf_params {
+    int    dimension;          /* Domain::Dimension; only 3 is implemented */
+    int    kernel_type;        /* Domain::KernelType 0 Qubic_Spline, 1 Quintic, 2 Quintic_Spline, 3 Hyperbolic (Functions.cpp:25) */
+    int    gradient_type;      /* Domain::GradientType 0/1/2 (InteractionAlt.cpp:138-143) */
+    int    ts_nb_inc;          /* Domain::ts_nb_inc: neighbour rebuild cadence once yielding (SolverFraser.cpp:397-404) */
+    double dom_min[3];         /* Domain::DomMin / DomMax grid overrides (Neighbour.cpp:36-42) */
+    double dom_max[3];
+    int    thermal_solver;     /* Domain::thermal_solver */
+    int    pl_heating;         /* Domain::pl_heating */
+    double pl_work_heat_frac;  /* Domain::pl_work_heat_frac */
+    int    contact;            /* Domain::contact (Wang algorithm, Contact_Wang.cpp) */
+    double friction_sta, friction_dyn;
+    double pfac, dfac;         /* Domain::PFAC / DFAC */
+    double contact_force_factor;
+    int    cont_heat_fric, cont_heat_cond;
+    double contact_hc;
+    int    nb_order_reference; /* 1: neighbour lists in the reference's Nproc=1 summation order (default) */
+} wf_params;
+
+/* Material_ subclasses (Source/Material.h:96-224). model: 0 bilinear (no object), 1 Hollomon, 2 Johnson-Cook. */
+typedef struct wf_material {
+    int    model;
+    double E, nu;
+    double p[13];              /* Hollomon: sy0, K, m.  Johnson-Cook: A, B, n, C, eps_0, m, T_m, T_t */
+} wf_material;
+
+/* Initial particle set, creation order, n = n_sph + total mesh particles. NULL pointers take the value the reference's
+ * Particle constructor assigns (Source/Particle.cpp:28-158). */
+typedef struct wf_particles {
+    int64_t n_sph;
+    const double *x;           /* 3*n_sph */
+    const double *v;           /* 3*n_sph or NULL */
+    const double *mass, *density, *h;   /* n_sph */
+    const double *ref_density; /* NULL: = density */
+    const int32_t *id;         /* Particle::ID or NULL (0) */
+    const int32_t *is_free;    /* NULL: all free. Fixed particles are WF_ERR_UNSUPPORTED for now */
+    const int32_t *not_write_surf_id;
+    /* per-particle "class" properties; few distinct tuples are expected (they are deduplicated into a table) */
+    const double *G, *Cs, *P0, *alpha, *beta, *TI, *TIn, *TIInitDist, *Ep, *k_T, *cp_T, *h_conv, *T_inf, *th_exp, *q_source;
+    const int32_t *pres_eq, *fail, *material, *material_model, *mat_id, *thermal_bc;
+    /* per-particle state */
+    const double *sigmay, *T;
+} wf_particles;
+
+/* Rigid tool mesh, replaces TriMesh (Source/Mesh.h:44-75) + Domain::AddTrimeshParticles (Source/Contact.cpp:10-38).
+ * Element particles are appended after all SPH particles in call order. */
+typedef struct wf_mesh {
+    int32_t n_nodes, n_elems;
+    const double *nodes;       /* 3*n_nodes */
+    const int32_t *elems;      /* 3*n_elems node ids */
+    const double *normals;     /* 3*n_elems initial normals (AxisPlaneMesh may have flipped them) */
+    const int32_t *nfar;       /* n_elems, node slot used for pplane (Mesh.cpp:206-228) */
+    const double *radius;      /* n_elems */
+    double hfac;               /* h = (float)hfac * radius */
+    int32_t id;                /* contact_surf_id */
+} wf_mesh;
+
+/* Scalars the solver loop and user callbacks read (SolverFraser.cpp:139-159,437-467; Domain.h). */
+typedef struct wf_scalars {
+    double time;
+    double max_pl_strain;
+    double max_disp[3];
+    double kin_energy_sum, int_energy_sum, plastic_work;
+    double contact_force_sum, contact_reaction_sum, ext_forces_work, contact_friction_work, accum_cont_heat_cond;
+    double max_T, min_T;
+    int64_t steps, nb_rebuilds;
+    int32_t is_yielding;
+} wf_scalars;
+
+/* Field selectors for wf_download / wf_upload. Tensor fields use 9 doubles (row-major 3x3) per particle on the host side. */
+typedef enum wf_field {
+    WF_F_X = 0, WF_F_V, WF_F_A, WF_F_DISPLACEMENT, WF_F_NORMAL, WF_F_CONTFORCE,            /* 3 doubles */
+    WF_F_DENSITY, WF_F_DDENSITY, WF_F_PRESSURE, WF_F_MASS, WF_F_H, WF_F_PL_STRAIN, WF_F_SIGMAY, WF_F_EFF_STRAIN_RATE,
+    WF_F_T, WF_F_DTDT, WF_F_Q_PLHEAT, WF_F_Q_CONV, WF_F_DELTA_CONT, WF_F_DKIN_ENERGY_DT, WF_F_DINT_ENERGY_DT, /* 1 double */
+    WF_F_SIGMA, WF_F_SHEARSTRESS, WF_F_STRAINRATE, WF_F_ROTATIONRATE, WF_F_STRAIN, WF_F_STRAIN_PL, WF_F_TIR,   /* 9 doubles */
+    WF_F_ID, WF_F_NB,                                                                                           /* 1 int32 */
+    WF_F_COUNT
+} wf_field;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------ */
+int  wf_create(int device, wf_ctx **out);
+void wf_destroy(wf_ctx *ctx);
+const char *wf_last_error(const wf_ctx *ctx);      /* ctx may be NULL: last error of wf_create */
+int  wf_sync(wf_ctx *ctx);
+void wf_default_params(wf_params *p);               /* Domain::Domain defaults */
+
+/* ---- setup (replaces the driver-side loops over dom.Particles[a]-> and the Domain data members) --------------- */
+int wf_set_params(wf_ctx *ctx, const wf_params *p);
+int wf_set_materials(wf_ctx *ctx, const wf_material *m, int n);
+int wf_set_particles(wf_ctx *ctx, const wf_particles *p);
+int wf_add_mesh(wf_ctx *ctx, const wf_mesh *m);                       /* AddTrimeshParticles */
+int wf_mesh_set_motion(wf_ctx *ctx, int mesh, const double v[3], const double w[3]);   /* TriMesh::SetVel / SetRotAxisVel */
+int wf_mesh_set_ramp(wf_ctx *ctx, int mesh, const double vmax[3], double tau);         /* v(t) = vmax*min(t/tau,1), evaluated on device */
+/* Device-side restatement of the usual GeneralAfter callback (examples/Compression_thermal.cpp:30-66): particles whose
+ * ID == id get a = 0 (if set_a) and v = vmax*min(t/tau,1), at both callback points of the step. */
+int wf_add_velocity_bc(wf_ctx *ctx, int id, const double vmax[3], double tau, int set_a);
+int wf_clear_bcs(wf_ctx *ctx);
+
+/* ---- data movement -------------------------------------------------------------------------------------------- */
+int64_t wf_num_particles(const wf_ctx *ctx);        /* SPH + mesh particles */
+int64_t wf_num_sph(const wf_ctx *ctx);
+int wf_download(wf_ctx *ctx, wf_field f, void *host);                 /* blocking; creation order; all particles */
+int wf_upload(wf_ctx *ctx, wf_field f, const void *host);             /* blocking; X,V,A,DENSITY,T,SIGMAY,ID only */
+int wf_download_subset(wf_ctx *ctx, wf_field f, const int32_t *idx, int64_t n, void *host);   /* callback bridge */
+int wf_upload_subset(wf_ctx *ctx, wf_field f, const int32_t *idx, int64_t n, const void *host);
+int wf_mesh_download(wf_ctx *ctx, int mesh, double *nodes, double *normals, double *pplane);
+
+/* ---- hot path, one call per phase of the Fraser step (SolverFraser.cpp:133-505) -------------------------------- */
+int wf_solver_init(wf_ctx *ctx, double dt);         /* InitialChecks, CellInitiate, ListGenerate, contact prologue (:41-94) */
+int wf_nb_build(wf_ctx *ctx);                       /* ClearNbData+MainNeighbourSearch+CalcPairPosList+SaveNeighbourData(+ContactNbUpdate) */
+int wf_nb_export_pairs(wf_ctx *ctx, int64_t *ij, int64_t cap, int64_t *n_pairs);      /* sorted (i<j), creation numbering */
+int wf_cont_export_pairs(wf_ctx *ctx, int64_t *ij, int64_t cap, int64_t *n_pairs);
+int wf_step_begin(wf_ctx *ctx);                     /* StartAcceleration: resets + TIR (Domain.cpp:1519-1597) */
+int wf_density(wf_ctx *ctx);                        /* CalcDensInc + DensReduction + rho += dt*drho (:243-252) */
+int wf_rate_stress(wf_ctx *ctx);                    /* CalcRateTensors + RateTensorsReduction + CalcStressStrain (:261-271) */
+int wf_accel(wf_ctx *ctx);                          /* CalcAccel + AccelReduction (:280-289) */
+int wf_contact(wf_ctx *ctx);                        /* CalcContactForcesWang (:307-312) */
+int wf_apply_bcs(wf_ctx *ctx);                      /* device-side GeneralAfter (:332,:360) */
+int wf_integrate_pos(wf_ctx *ctx);                  /* x_prev, Displacement, x update (:337-343) */
+int wf_integrate_vel(wf_ctx *ctx);                  /* v += a*dt (:352-355) */
+int wf_thermal(wf_ctx *ctx);                        /* CalcPlasticWorkHeat + ThermalCalcs (:369-370) */
+int wf_energy(wf_ctx *ctx);                         /* CalcKinEnergyEqn + CalcIntEnergyEqn (:375-376) */
+int wf_step_end(wf_ctx *ctx);                       /* Time += dt, TriMesh::Update, UpdateContactParticles, cadence (:384-412) */
+int wf_reduce(wf_ctx *ctx, wf_scalars *out);        /* blocking: scalars */
+
+/* Whole steps. stage_a = begin .. contact; [GeneralAfter]; stage_b = move x, v; [GeneralAfter]; stage_c = thermal .. end. */
+int wf_fraser_stage_a(wf_ctx *ctx);
+int wf_fraser_stage_b1(wf_ctx *ctx);
+int wf_fraser_stage_b2(wf_ctx *ctx);
+int wf_fraser_stage_c(wf_ctx *ctx);
+int wf_fraser_run(wf_ctx *ctx, int64_t nsteps);     /* nsteps full steps with device-side BCs, no host callback */
+
+/* ---- host-side lattice generators (Domain::AddCylinderLength / AddBoxLength, Domain.cpp:708,326); 3-D, cubic packing.
+ * Call with pts = NULL to get the count. Returns particle count or a negative wf_status. ------------------------ */
+int64_t wf_gen_cylinder(const double V[3], double Rxy, double Lz, double r, double *pts, int64_t cap);
+int64_t wf_gen_box(const double V[3], double Lx, double Ly, double Lz, double r, double *pts, int64_t cap, double box_dims[3]);
+
+/* timing helper for bench.py: CUDA-event time (ms) of each kernel family accumulated since the last reset */
+int wf_prof_enable(wf_ctx *ctx, int on);
+int wf_prof_get(wf_ctx *ctx, double *ms, int64_t *launches, int cap, int *n_used);
+const char *wf_prof_name(int k);
+int wf_launch_count(wf_ctx *ctx, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,606 @@
+// Context, setup and data movement of libweldform_b200.so (see include/weldform_b200.h).
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <map>
+
+#include "wf_internal.cuh"
+
+using namespace wf;
+
+static std::string g_create_err;
+
+namespace wf {
+
+int fail(wf_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+int ensure_stage(wf_ctx *c, size_t bytes)
+{
+    if (bytes <= c->stage_bytes) return 0;
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr; c->stage_bytes = 0;
+    WF_CUDA(c, cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return 0;
+}
+
+} // namespace wf
+
+extern "C" void wf_default_params(wf_params *p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->dimension = 3; p->kernel_type = 0; p->gradient_type = 0; p->ts_nb_inc = 5;
+    for (int k = 0; k < 3; ++k) { p->dom_min[k] = 100000000000.0; p->dom_max[k] = -100000000000.0; }
+    p->pl_work_heat_frac = 0.9; p->pfac = 0.4; p->dfac = 0.0; p->contact_force_factor = 1.0;
+    p->nb_order_reference = 1;
+}
+
+extern "C" int wf_create(int device, wf_ctx **out)
+{
+    if (!out) return fail(nullptr, WF_ERR_ARG, "wf_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, WF_ERR_CUDA, "wf_create: no CUDA device (%s); weldform_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, WF_ERR_ARG, "wf_create: device %d out of range (%d devices)", device, ndev);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, WF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    wf_ctx *c = new wf_ctx();
+    c->device = device;
+    wf_default_params(&c->prm);
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete c; return fail(nullptr, WF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    cudaMalloc(&c->d_sc, sizeof(DevScalars)); cudaMemset(c->d_sc, 0, sizeof(DevScalars));
+    cudaMallocHost(&c->h_sc, sizeof(DevScalars)); std::memset(c->h_sc, 0, sizeof(DevScalars));
+    cudaMalloc(&c->d_maxcnt, 4 * sizeof(int));
+    std::memset(c->prof_ms, 0, sizeof(c->prof_ms)); std::memset(c->prof_n, 0, sizeof(c->prof_n));
+    *out = c;
+    return 0;
+}
+
+extern "C" void wf_destroy(wf_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(c->Q0[b]); cudaFree(c->Q1[b]); cudaFree(c->Q2[b]); cudaFree(c->S0[b]); cudaFree(c->S1[b]); cudaFree(c->S2[b]);
+        cudaFree(c->F[b]); cudaFree(c->I[b]); cudaFree(c->keys[b]); cudaFree(c->vals[b]);
+    }
+    cudaFree(c->slot_of); cudaFree(c->d_classes); cudaFree(c->d_mats); cudaFree(c->cell_start); cudaFree(c->cell_end);
+    cudaFree(c->cub_tmp); cudaFree(c->nbr); cudaFree(c->nb_cnt); cudaFree(c->nb_hi); cudaFree(c->d_maxcnt);
+    cudaFree(c->cont); cudaFree(c->cont_cnt); cudaFree(c->d_mesh_ids); cudaFree(c->d_bcs); cudaFree(c->d_sc); cudaFree(c->d_partial);
+    cudaFree(c->dm.node); cudaFree(c->dm.node_v); cudaFree(c->dm.en); cudaFree(c->dm.nfar); cudaFree(c->dm.emesh);
+    cudaFree(c->dm.enormal); cudaFree(c->dm.ev); cudaFree(c->dm.pplane); cudaFree(c->dm.motion);
+    cudaFree(c->stage); if (c->h_stage) cudaFreeHost(c->h_stage); if (c->h_sc) cudaFreeHost(c->h_sc);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" const char *wf_last_error(const wf_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int wf_sync(wf_ctx *c)
+{
+    if (!c) return WF_ERR_ARG;
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int wf_set_params(wf_ctx *c, const wf_params *p)
+{
+    if (!c || !p) return WF_ERR_ARG;
+    if (p->dimension != 3) return fail(c, WF_ERR_UNSUPPORTED, "wf_set_params: Dimension=%d; only the 3-D path is implemented", p->dimension);
+    if (p->kernel_type < 0 || p->kernel_type > 3) return fail(c, WF_ERR_ARG, "wf_set_params: kernel_type %d out of range", p->kernel_type);
+    if (p->gradient_type < 0 || p->gradient_type > 2) return fail(c, WF_ERR_ARG, "wf_set_params: gradient_type %d out of range", p->gradient_type);
+    if (p->ts_nb_inc < 1) return fail(c, WF_ERR_ARG, "wf_set_params: ts_nb_inc must be >= 1");
+    c->prm = *p;
+    c->Cellfac = (p->kernel_type == 2) ? 3.0 : 2.0;      // Domain::Kernel_Set (Domain.cpp:191-195)
+    return 0;
+}
+
+extern "C" int wf_set_materials(wf_ctx *c, const wf_material *m, int n)
+{
+    if (!c || (n > 0 && !m)) return WF_ERR_ARG;
+    c->h_mats.clear();
+    for (int k = 0; k < n; ++k) {
+        MatProps mp; std::memset(&mp, 0, sizeof(mp));
+        mp.model = m[k].model; mp.E = m[k].E; mp.nu = m[k].nu; for (int q = 0; q < 13; ++q) mp.p[q] = m[k].p[q];
+        if (mp.model == 1) {       // Hollomon ctor (Source/Material.cpp:48-57)
+            mp.eps0 = mp.p[0] / mp.E; mp.eps1 = std::pow(mp.p[0] / mp.p[1], 1. / mp.p[2]);
+            if (mp.eps0 > mp.eps1) return fail(c, WF_ERR_ARG, "Hollomon material bad definition (eps0 > eps1), Material.cpp:54");
+        } else if (mp.model != 2 && mp.model != 0) return fail(c, WF_ERR_UNSUPPORTED, "material model %d not implemented (0 bilinear, 1 Hollomon, 2 Johnson-Cook)", mp.model);
+        c->h_mats.push_back(mp);
+    }
+    cudaFree(c->d_mats); c->d_mats = nullptr;
+    if (n > 0) {
+        WF_CUDA(c, cudaMalloc(&c->d_mats, n * sizeof(MatProps)));
+        WF_CUDA(c, cudaMemcpy(c->d_mats, c->h_mats.data(), n * sizeof(MatProps), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+extern "C" int wf_add_mesh(wf_ctx *c, const wf_mesh *m)
+{
+    if (!c || !m) return WF_ERR_ARG;
+    if (c->have_particles) return fail(c, WF_ERR_ARG, "wf_add_mesh: add rigid meshes before wf_set_particles (mesh particles are appended after the SPH particles at upload)");
+    if (c->pending_meshes.size() >= 4) return fail(c, WF_ERR_UNSUPPORTED, "at most 4 rigid meshes");
+    wf_ctx::PendingMesh pm;
+    pm.nodes.assign(m->nodes, m->nodes + 3 * (size_t)m->n_nodes);
+    pm.elems.assign(m->elems, m->elems + 3 * (size_t)m->n_elems);
+    pm.normals.assign(m->normals, m->normals + 3 * (size_t)m->n_elems);
+    pm.nfar.assign(m->nfar, m->nfar + m->n_elems);
+    pm.radius.assign(m->radius, m->radius + m->n_elems);
+    pm.hfac = m->hfac; pm.id = m->id;
+    c->pending_meshes.push_back(pm);
+    return 0;
+}
+
+static int alloc_particles(wf_ctx *c, int64_t n)
+{
+    c->cap = n;
+    for (int b = 0; b < 2; ++b) {
+        WF_CUDA(c, cudaMalloc(&c->Q0[b], n * sizeof(double4))); WF_CUDA(c, cudaMalloc(&c->Q1[b], n * sizeof(double4)));
+        WF_CUDA(c, cudaMalloc(&c->Q2[b], n * sizeof(double4))); WF_CUDA(c, cudaMalloc(&c->S0[b], n * sizeof(double4)));
+        WF_CUDA(c, cudaMalloc(&c->S1[b], n * sizeof(double4))); WF_CUDA(c, cudaMalloc(&c->S2[b], n * sizeof(double4)));
+        WF_CUDA(c, cudaMalloc(&c->F[b], (size_t)F_COUNT * n * sizeof(double)));
+        WF_CUDA(c, cudaMalloc(&c->I[b], (size_t)I_COUNT * n * sizeof(int)));
+        WF_CUDA(c, cudaMalloc(&c->keys[b], n * sizeof(unsigned long long)));
+        WF_CUDA(c, cudaMalloc(&c->vals[b], n * sizeof(int)));
+        WF_CUDA(c, cudaMemset(c->S0[b], 0, n * sizeof(double4))); WF_CUDA(c, cudaMemset(c->S1[b], 0, n * sizeof(double4)));
+        WF_CUDA(c, cudaMemset(c->S2[b], 0, n * sizeof(double4)));
+        WF_CUDA(c, cudaMemset(c->F[b], 0, (size_t)F_COUNT * n * sizeof(double)));
+        WF_CUDA(c, cudaMemset(c->I[b], 0, (size_t)I_COUNT * n * sizeof(int)));
+    }
+    WF_CUDA(c, cudaMalloc(&c->slot_of, n * sizeof(int)));
+    WF_CUDA(c, cudaMalloc(&c->nb_cnt, n * sizeof(int))); WF_CUDA(c, cudaMalloc(&c->nb_hi, n * sizeof(int)));
+    WF_CUDA(c, cudaMalloc(&c->cont_cnt, n * sizeof(int)));
+    WF_CUDA(c, cudaMemset(c->nb_cnt, 0, n * sizeof(int))); WF_CUDA(c, cudaMemset(c->nb_hi, 0, n * sizeof(int)));
+    WF_CUDA(c, cudaMemset(c->cont_cnt, 0, n * sizeof(int)));
+    c->partial_blocks = 1024;
+    WF_CUDA(c, cudaMalloc(&c->d_partial, (size_t)c->partial_blocks * 32 * sizeof(double)));
+    return 0;
+}
+
+struct ClassKey {
+    double d[16]; int i[7];
+    bool operator<(const ClassKey &o) const { int r = std::memcmp(d, o.d, sizeof(d)); if (r) return r < 0; return std::memcmp(i, o.i, sizeof(i)) < 0; }
+    bool operator==(const ClassKey &o) const { return !std::memcmp(d, o.d, sizeof(d)) && !std::memcmp(i, o.i, sizeof(i)); }
+};
+
+extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
+{
+    if (!c || !p) return WF_ERR_ARG;
+    if (c->have_particles) return fail(c, WF_ERR_ARG, "wf_set_particles: particles already set for this context");
+    if (p->n_sph <= 0 || !p->x || !p->mass || !p->density || !p->h) return fail(c, WF_ERR_ARG, "wf_set_particles: n_sph, x, mass, density, h are required");
+    cudaSetDevice(c->device);
+    const int64_t nsph = p->n_sph;
+    int64_t nmeshp = 0; for (auto &pm : c->pending_meshes) nmeshp += (int64_t)pm.nfar.size();
+    const int64_t n = nsph + nmeshp;
+    if (n >= (int64_t)1 << 31) return fail(c, WF_ERR_UNSUPPORTED, "more than 2^31-1 particles per context");
+    if (p->is_free) for (int64_t i = 0; i < nsph; ++i) if (!p->is_free[i])
+        return fail(c, WF_ERR_UNSUPPORTED, "fixed particles (IsFree=false, FSMPairs / PrimaryComputeAcceleration) are not implemented; particle %lld", (long long)i);
+    c->n = n; c->nsph = nsph;
+    WF_CHECK(alloc_particles(c, n));
+
+    // ---- property classes -------------------------------------------------------------------------------------
+    std::vector<double> cls_of(n);
+    std::map<ClassKey, int> table; ClassKey last; int last_id = -1;
+    auto gd = [&](const double *a, int64_t i, double dflt) { return a ? a[i] : dflt; };
+    auto gi = [&](const int32_t *a, int64_t i, int dflt) { return a ? a[i] : dflt; };
+    c->h_classes.clear(); c->any_ti = false;
+    for (int64_t i = 0; i < nsph; ++i) {
+        ClassKey k; std::memset(&k, 0, sizeof(k));
+        k.d[0] = gd(p->G, i, 0.0); k.d[1] = gd(p->Cs, i, 0.0); k.d[2] = gd(p->P0, i, 0.0);
+        k.d[3] = p->ref_density ? p->ref_density[i] : p->density[i];
+        k.d[4] = gd(p->alpha, i, 0.0); k.d[5] = gd(p->beta, i, 0.0); k.d[6] = gd(p->TI, i, 0.0); k.d[7] = gd(p->TIn, i, 4.0);
+        k.d[8] = gd(p->TIInitDist, i, 0.0); k.d[9] = gd(p->Ep, i, 0.0); k.d[10] = gd(p->k_T, i, 0.0); k.d[11] = gd(p->cp_T, i, 0.0);
+        k.d[12] = gd(p->h_conv, i, 0.0); k.d[13] = gd(p->T_inf, i, 0.0); k.d[14] = gd(p->th_exp, i, 0.0); k.d[15] = gd(p->q_source, i, 0.0);
+        k.i[0] = gi(p->pres_eq, i, 0); k.i[1] = gi(p->fail, i, 0); k.i[2] = gi(p->material, i, 0); k.i[3] = gi(p->material_model, i, 0);
+        k.i[4] = gi(p->mat_id, i, -1); k.i[5] = gi(p->thermal_bc, i, 0); k.i[6] = 0;
+        int id;
+        if (last_id >= 0 && k == last) id = last_id;
+        else {
+            auto it = table.find(k);
+            if (it == table.end()) {
+                id = (int)c->h_classes.size();
+                if (id >= 65536) return fail(c, WF_ERR_UNSUPPORTED, "more than 65536 distinct per-particle property tuples");
+                ClassProps cp; std::memset(&cp, 0, sizeof(cp));
+                cp.G = k.d[0]; cp.Cs = k.d[1]; cp.P0 = k.d[2]; cp.RefDensity = k.d[3]; cp.Alpha = k.d[4]; cp.Beta = k.d[5]; cp.TI = k.d[6]; cp.TIn = k.d[7];
+                cp.TIInitDist = k.d[8]; cp.Ep = k.d[9]; cp.k_T = k.d[10]; cp.cp_T = k.d[11]; cp.h_conv = k.d[12]; cp.T_inf = k.d[13]; cp.th_exp = k.d[14]; cp.q_source = k.d[15];
+                cp.PresEq = k.i[0]; cp.Fail = k.i[1]; cp.Material = k.i[2]; cp.Material_model = k.i[3]; cp.mat_id = k.i[4]; cp.Thermal_BC = k.i[5]; cp.IsMesh = 0;
+                if (cp.Fail > 1) return fail(c, WF_ERR_ARG, "Undefined failure criteria for solids (Fail=%d), Particle.cpp:1062", cp.Fail);
+                if (cp.Fail == 1 && (cp.Material_model == 1 || cp.Material_model == 2) && (cp.mat_id < 0 || cp.mat_id >= (int)c->h_mats.size()))
+                    return fail(c, WF_ERR_ARG, "particle %lld uses Material_model %d but mat_id %d is not in the material table", (long long)i, cp.Material_model, cp.mat_id);
+                if (cp.Material_model > 2 || cp.Material_model < 0) return fail(c, WF_ERR_UNSUPPORTED, "Material_model %d not implemented", cp.Material_model);
+                if (cp.TI > 0.0) c->any_ti = true;
+                c->h_classes.push_back(cp); table[k] = id;
+            } else id = it->second;
+            last = k; last_id = id;
+        }
+        cls_of[i] = (double)id;
+    }
+    int mesh_class = -1;
+    if (nmeshp > 0) {     // rigid-mesh particles: Particle ctor defaults with Density = 0 (Contact.cpp:15-27)
+        ClassProps cp; std::memset(&cp, 0, sizeof(cp)); cp.TIn = 4.0; cp.mat_id = -1; cp.IsMesh = 1;
+        mesh_class = (int)c->h_classes.size(); c->h_classes.push_back(cp);
+        for (int64_t i = nsph; i < n; ++i) cls_of[i] = (double)mesh_class;
+    }
+    c->n_classes = (int)c->h_classes.size();
+    WF_CUDA(c, cudaMalloc(&c->d_classes, c->n_classes * sizeof(ClassProps)));
+    WF_CUDA(c, cudaMemcpy(c->d_classes, c->h_classes.data(), c->n_classes * sizeof(ClassProps), cudaMemcpyHostToDevice));
+
+    // ---- meshes -------------------------------------------------------------------------------------------------
+    std::vector<double> mx(3 * nmeshp), mh(nmeshp); std::vector<int> mids(nmeshp);
+    if (!c->pending_meshes.empty()) {
+        int tn = 0, te = 0; for (auto &pm : c->pending_meshes) { tn += (int)pm.nodes.size() / 3; te += (int)pm.nfar.size(); }
+        std::vector<double> nodes(3 * tn), enormal(3 * te), ev(3 * te, 0.0), pplane(te), nodev(3 * tn, 0.0);
+        std::vector<int> en(3 * te), nfar(te), emesh(te);
+        int n0 = 0, e0 = 0; int64_t fp = nsph;
+        for (size_t m = 0; m < c->pending_meshes.size(); ++m) {
+            auto &pm = c->pending_meshes[m]; int nn = (int)pm.nodes.size() / 3, ne = (int)pm.nfar.size();
+            HostMesh hm; hm.node0 = n0; hm.elem0 = e0; hm.n_nodes = nn; hm.n_elems = ne; hm.id = pm.id; hm.first_particle = fp;
+            c->meshes.push_back(hm); c->mesh_ids.push_back(pm.id);
+            std::copy(pm.nodes.begin(), pm.nodes.end(), nodes.begin() + 3 * n0);
+            for (int e = 0; e < ne; ++e) {
+                for (int k = 0; k < 3; ++k) { en[3 * (e0 + e) + k] = pm.elems[3 * e + k] + n0; enormal[3 * (e0 + e) + k] = pm.normals[3 * e + k]; }
+                nfar[e0 + e] = pm.nfar[e]; emesh[e0 + e] = (int)m;
+                V3 nf = v3(pm.nodes[3 * pm.elems[3 * e + pm.nfar[e]]], pm.nodes[3 * pm.elems[3 * e + pm.nfar[e]] + 1], pm.nodes[3 * pm.elems[3 * e + pm.nfar[e]] + 2]);
+                V3 nr = v3(pm.normals[3 * e], pm.normals[3 * e + 1], pm.normals[3 * e + 2]);
+                pplane[e0 + e] = dot(nf, nr);                       // TriMesh::UpdatePlaneCoeff (Mesh.cpp:222-228)
+                // element particle: centroid = (n0+n1+n2)/3 (Mesh.cpp:151-152), h = hfac*radius (Contact.cpp:25-26)
+                V3 a = v3(pm.nodes[3 * pm.elems[3 * e]], pm.nodes[3 * pm.elems[3 * e] + 1], pm.nodes[3 * pm.elems[3 * e] + 2]);
+                V3 b = v3(pm.nodes[3 * pm.elems[3 * e + 1]], pm.nodes[3 * pm.elems[3 * e + 1] + 1], pm.nodes[3 * pm.elems[3 * e + 1] + 2]);
+                V3 d = v3(pm.nodes[3 * pm.elems[3 * e + 2]], pm.nodes[3 * pm.elems[3 * e + 2] + 1], pm.nodes[3 * pm.elems[3 * e + 2] + 2]);
+                V3 cen = ((a + b) + d) / 3.;
+                int64_t q = (fp - nsph) + e;
+                mx[3 * q] = cen.x; mx[3 * q + 1] = cen.y; mx[3 * q + 2] = cen.z;
+                mh[q] = (double)(float)pm.hfac * pm.radius[e]; mids[q] = pm.id;
+            }
+            n0 += nn; e0 += ne; fp += ne;
+        }
+        c->dm.n_nodes = tn; c->dm.n_elems = te;
+        WF_CUDA(c, cudaMalloc(&c->dm.node, 3 * tn * sizeof(double))); WF_CUDA(c, cudaMalloc(&c->dm.node_v, 3 * tn * sizeof(double)));
+        WF_CUDA(c, cudaMalloc(&c->dm.en, 3 * te * sizeof(int))); WF_CUDA(c, cudaMalloc(&c->dm.nfar, te * sizeof(int))); WF_CUDA(c, cudaMalloc(&c->dm.emesh, te * sizeof(int)));
+        WF_CUDA(c, cudaMalloc(&c->dm.enormal, 3 * te * sizeof(double))); WF_CUDA(c, cudaMalloc(&c->dm.ev, 3 * te * sizeof(double))); WF_CUDA(c, cudaMalloc(&c->dm.pplane, te * sizeof(double)));
+        WF_CUDA(c, cudaMalloc(&c->dm.motion, 16 * c->meshes.size() * sizeof(double)));
+        c->h_motion.assign(16 * c->meshes.size(), 0.0);
+        WF_CUDA(c, cudaMemcpy(c->dm.node, nodes.data(), 3 * tn * sizeof(double), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->dm.node_v, nodev.data(), 3 * tn * sizeof(double), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->dm.en, en.data(), 3 * te * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->dm.nfar, nfar.data(), te * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->dm.emesh, emesh.data(), te * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->dm.enormal, enormal.data(), 3 * te * sizeof(double), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->dm.ev, ev.data(), 3 * te * sizeof(double), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->dm.pplane, pplane.data(), te * sizeof(double), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->dm.motion, c->h_motion.data(), c->h_motion.size() * sizeof(double), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMalloc(&c->d_mesh_ids, 4 * sizeof(int)));
+        int ids4[4] = { -2147483647, -2147483647, -2147483647, -2147483647 };
+        for (size_t m = 0; m < c->mesh_ids.size(); ++m) ids4[m] = c->mesh_ids[m];
+        WF_CUDA(c, cudaMemcpy(c->d_mesh_ids, ids4, sizeof(ids4), cudaMemcpyHostToDevice));
+        c->pending_meshes.clear();
+    }
+
+    // ---- particle arrays (initial slot order = creation order) ----------------------------------------------------
+    std::vector<double4> q(n);
+    bool uni_h = true;
+    for (int64_t i = 0; i < n; ++i) {
+        if (i < nsph) q[i] = make_double4(p->x[3 * i], p->x[3 * i + 1], p->x[3 * i + 2], p->h[i]);
+        else { int64_t k = i - nsph; q[i] = make_double4(mx[3 * k], mx[3 * k + 1], mx[3 * k + 2], mh[k]); }
+        if (i < nsph && p->h[i] != p->h[0]) uni_h = false;
+    }
+    c->uniform_h = uni_h && nmeshp == 0;
+    WF_CUDA(c, cudaMemcpy(c->Q0[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+    for (int64_t i = 0; i < n; ++i) {
+        if (i < nsph) q[i] = make_double4(p->v ? p->v[3 * i] : 0.0, p->v ? p->v[3 * i + 1] : 0.0, p->v ? p->v[3 * i + 2] : 0.0, p->density[i]);
+        else q[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+    WF_CUDA(c, cudaMemcpy(c->Q1[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+    double tot = 0.;
+    for (int64_t i = 0; i < n; ++i) {
+        double m = i < nsph ? p->mass[i] : 0.0;
+        tot += m;                                   // serial, creation order (Domain.cpp:1421-1423)
+        q[i] = make_double4(m, (i < nsph && p->T) ? p->T[i] : 0.0, cls_of[i], 0.0);
+    }
+    c->totmass_mean = tot / (double)n;
+    WF_CUDA(c, cudaMemcpy(c->Q2[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> sy(n, 0.0);
+        if (p->sigmay) for (int64_t i = 0; i < nsph; ++i) sy[i] = p->sigmay[i];
+        WF_CUDA(c, cudaMemcpy(c->F[0] + (int64_t)F_SIGY * n, sy.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+        if (nmeshp > 0) {   // mesh particles carry the element normal (Contact.cpp:28)
+            std::vector<double> nx(n, 0.0);
+            // normals are refreshed from the mesh at every step end; the particle copy is only a download mirror
+            (void)nx;
+        }
+    }
+    {
+        std::vector<int> iv(n);
+        for (int64_t i = 0; i < n; ++i) iv[i] = i < nsph ? gi(p->id, i, 0) : mids[i - nsph];
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_ID * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_IDORIG * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        for (int64_t i = 0; i < n; ++i) iv[i] = i < nsph ? gi(p->not_write_surf_id, i, 0) : 0;
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_NOWRITE * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        for (int64_t i = 0; i < n; ++i) iv[i] = (int)i;
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_ORIG * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->slot_of, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    c->cur = 0;
+    c->have_particles = true;
+    return 0;
+}
+
+extern "C" int64_t wf_num_particles(const wf_ctx *c) { return c ? c->n : 0; }
+extern "C" int64_t wf_num_sph(const wf_ctx *c) { return c ? c->nsph : 0; }
+
+extern "C" int wf_mesh_set_motion(wf_ctx *c, int mesh, const double v[3], const double w[3])
+{
+    if (!c || mesh < 0 || mesh >= (int)c->meshes.size()) return fail(c, WF_ERR_ARG, "wf_mesh_set_motion: bad mesh index %d", mesh);
+    double *m = &c->h_motion[16 * mesh];
+    if (v) for (int k = 0; k < 3; ++k) m[k] = v[k];
+    if (w) for (int k = 0; k < 3; ++k) m[3 + k] = w[k];
+    WF_CUDA(c, cudaMemcpyAsync(c->dm.motion + 16 * mesh, m, 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int wf_mesh_set_ramp(wf_ctx *c, int mesh, const double vmax[3], double tau)
+{
+    if (!c || mesh < 0 || mesh >= (int)c->meshes.size()) return fail(c, WF_ERR_ARG, "wf_mesh_set_ramp: bad mesh index %d", mesh);
+    double *m = &c->h_motion[16 * mesh];
+    for (int k = 0; k < 3; ++k) m[6 + k] = vmax[k];
+    m[9] = tau; m[10] = 1.0;
+    WF_CUDA(c, cudaMemcpy(c->dm.motion + 16 * mesh, m, 16 * sizeof(double), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int wf_add_velocity_bc(wf_ctx *c, int id, const double vmax[3], double tau, int set_a)
+{
+    if (!c || !vmax) return WF_ERR_ARG;
+    BCEntry b; b.id = id; b.set_a = set_a; for (int k = 0; k < 3; ++k) b.v[k] = vmax[k]; b.tau = tau;
+    c->h_bcs.push_back(b);
+    cudaFree(c->d_bcs); c->d_bcs = nullptr;
+    WF_CUDA(c, cudaMalloc(&c->d_bcs, c->h_bcs.size() * sizeof(BCEntry)));
+    WF_CUDA(c, cudaMemcpy(c->d_bcs, c->h_bcs.data(), c->h_bcs.size() * sizeof(BCEntry), cudaMemcpyHostToDevice));
+    c->n_bcs = (int)c->h_bcs.size();
+    return 0;
+}
+extern "C" int wf_clear_bcs(wf_ctx *c) { if (!c) return WF_ERR_ARG; c->h_bcs.clear(); c->n_bcs = 0; return 0; }
+
+// ---- field gather / scatter between slot order (device) and creation order (host) ------------------------------------
+struct FieldView {
+    const double4 *Q0, *Q1, *Q2, *S0, *S1, *S2; const double *F; const int *I; int64_t cap;
+};
+
+__device__ inline void field_get(const FieldView &v, int f, int64_t s, double out[9], int &iout)
+{
+    const double *F = v.F; const int64_t cap = v.cap;
+    auto own = [&](int fld) { return F[(int64_t)fld * cap + s]; };
+    auto sym = [&](int base) { double xx = own(base), yy = own(base + 1), zz = own(base + 2), xy = own(base + 3), yz = own(base + 4), xz = own(base + 5);
+                               out[0] = xx; out[1] = xy; out[2] = xz; out[3] = xy; out[4] = yy; out[5] = yz; out[6] = xz; out[7] = yz; out[8] = zz; };
+    switch (f) {
+    case WF_F_X: { double4 q = v.Q0[s]; out[0] = q.x; out[1] = q.y; out[2] = q.z; } break;
+    case WF_F_V: { double4 q = v.Q1[s]; out[0] = q.x; out[1] = q.y; out[2] = q.z; } break;
+    case WF_F_A: out[0] = own(F_AX); out[1] = own(F_AY); out[2] = own(F_AZ); break;
+    case WF_F_DISPLACEMENT: out[0] = own(F_DX); out[1] = own(F_DY); out[2] = own(F_DZ); break;
+    case WF_F_NORMAL: out[0] = own(F_NX); out[1] = own(F_NY); out[2] = own(F_NZ); break;
+    case WF_F_CONTFORCE: out[0] = own(F_CFX); out[1] = own(F_CFY); out[2] = own(F_CFZ); break;
+    case WF_F_DENSITY: out[0] = v.Q1[s].w; break;
+    case WF_F_DDENSITY: out[0] = own(F_DDENS); break;
+    case WF_F_PRESSURE: out[0] = v.Q2[s].w; break;
+    case WF_F_MASS: out[0] = v.Q2[s].x; break;
+    case WF_F_H: out[0] = v.Q0[s].w; break;
+    case WF_F_PL_STRAIN: out[0] = own(F_PLS); break;
+    case WF_F_SIGMAY: out[0] = own(F_SIGY); break;
+    case WF_F_EFF_STRAIN_RATE: out[0] = own(F_EFFSR); break;
+    case WF_F_T: out[0] = v.Q2[s].y; break;
+    case WF_F_DTDT: out[0] = own(F_DTDT); break;
+    case WF_F_Q_PLHEAT: out[0] = own(F_QPL); break;
+    case WF_F_Q_CONV: out[0] = own(F_QCONV); break;
+    case WF_F_DELTA_CONT: out[0] = own(F_DCONT); break;
+    case WF_F_DKIN_ENERGY_DT: out[0] = own(F_DKIN); break;
+    case WF_F_DINT_ENERGY_DT: out[0] = own(F_DINT); break;
+    case WF_F_SIGMA: { double4 a = v.S0[s], b = v.S1[s]; out[0] = a.x; out[1] = a.w; out[2] = b.y; out[3] = a.w; out[4] = a.y; out[5] = b.x; out[6] = b.y; out[7] = b.x; out[8] = a.z; } break;
+    case WF_F_TIR: { double4 b = v.S1[s], t = v.S2[s]; out[0] = b.z; out[1] = t.y; out[2] = t.w; out[3] = t.y; out[4] = b.w; out[5] = t.z; out[6] = t.w; out[7] = t.z; out[8] = t.x; } break;
+    case WF_F_SHEARSTRESS: sym(F_SH); break;
+    case WF_F_STRAINRATE: sym(F_SR); break;
+    case WF_F_STRAIN: sym(F_ST); break;
+    case WF_F_STRAIN_PL: sym(F_SP); break;
+    case WF_F_ROTATIONRATE: { double r01 = own(F_RR), r02 = own(F_RR + 1), r12 = own(F_RR + 2);
+        out[0] = 0.0; out[1] = r01; out[2] = r02; out[3] = -r01; out[4] = 0.0; out[5] = r12; out[6] = -r02; out[7] = -r12; out[8] = 0.0; } break;
+    case WF_F_ID: iout = v.I[(int64_t)I_ID * cap + s]; break;
+    case WF_F_NB: iout = v.I[(int64_t)I_NB * cap + s]; break;
+    default: break;
+    }
+}
+
+static int field_ncomp(int f)
+{
+    if (f <= WF_F_CONTFORCE) return 3;
+    if (f <= WF_F_DINT_ENERGY_DT) return 1;
+    if (f <= WF_F_TIR) return 9;
+    return 1;
+}
+static bool field_is_int(int f) { return f == WF_F_ID || f == WF_F_NB; }
+
+__global__ void k_download(FieldView v, int f, int ncomp, int is_int, int64_t n, const int *orig, const int *slot_of, const int *idx, int64_t nidx, void *out)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t cnt = idx ? nidx : n;
+    if (t >= cnt) return;
+    int64_t s, o;
+    if (idx) { s = slot_of[idx[t]]; o = t; } else { s = t; o = orig[t]; }
+    double val[9]; int iv = 0;
+    field_get(v, f, s, val, iv);
+    if (is_int) ((int *)out)[o] = iv;
+    else for (int k = 0; k < ncomp; ++k) ((double *)out)[o * ncomp + k] = val[k];
+}
+
+static FieldView view_of(wf_ctx *c)
+{
+    FieldView v; v.Q0 = c->Q0[c->cur]; v.Q1 = c->Q1[c->cur]; v.Q2 = c->Q2[c->cur]; v.S0 = c->S0[c->cur]; v.S1 = c->S1[c->cur]; v.S2 = c->S2[c->cur];
+    v.F = c->F[c->cur]; v.I = c->I[c->cur]; v.cap = c->cap; return v;
+}
+
+static int download_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, void *host)
+{
+    if (!c || !host) return WF_ERR_ARG;
+    if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_download: no particles");
+    if (f < 0 || f >= WF_F_COUNT) return fail(c, WF_ERR_ARG, "wf_download: bad field %d", (int)f);
+    cudaSetDevice(c->device);
+    const int nc = field_ncomp(f); const bool isint = field_is_int(f);
+    const int64_t cnt = idx ? nidx : c->n;
+    if (cnt == 0) return 0;
+    const size_t bytes = (size_t)cnt * nc * (isint ? 4 : 8);
+    const size_t idx_bytes = idx ? (((size_t)nidx * 4 + 255) / 256) * 256 : 0;
+    WF_CHECK(ensure_stage(c, bytes + idx_bytes));
+    int *d_idx = nullptr;
+    if (idx) { d_idx = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(d_idx, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); }
+    k_download<<<grid_for(cnt, 256), 256, 0, c->stream>>>(view_of(c), (int)f, nc, isint ? 1 : 0, c->n, c->Ip(I_ORIG), c->slot_of, d_idx, nidx, c->stage);
+    WF_LAUNCH_CHECK(c);
+    WF_CUDA(c, cudaMemcpyAsync(host, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int wf_download(wf_ctx *c, wf_field f, void *host) { return download_impl(c, f, nullptr, 0, host); }
+extern "C" int wf_download_subset(wf_ctx *c, wf_field f, const int32_t *idx, int64_t n, void *host)
+{ if (n > 0 && !idx) return WF_ERR_ARG; return download_impl(c, f, idx, n, host); }
+
+__global__ void k_upload(double4 *Q0, double4 *Q1, double4 *Q2, double *F, int *I, int64_t cap, int f, int64_t n, const int *slot_of, const int *idx, int64_t nidx, const void *in)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t cnt = idx ? nidx : n;
+    if (t >= cnt) return;
+    int64_t s = slot_of[idx ? idx[t] : t];
+    const double *d = (const double *)in;
+    switch (f) {
+    case WF_F_X: { double4 q = Q0[s]; q.x = d[3 * t]; q.y = d[3 * t + 1]; q.z = d[3 * t + 2]; Q0[s] = q; } break;
+    case WF_F_V: { double4 q = Q1[s]; q.x = d[3 * t]; q.y = d[3 * t + 1]; q.z = d[3 * t + 2]; Q1[s] = q; } break;
+    case WF_F_A: F[(int64_t)F_AX * cap + s] = d[3 * t]; F[(int64_t)F_AY * cap + s] = d[3 * t + 1]; F[(int64_t)F_AZ * cap + s] = d[3 * t + 2]; break;
+    case WF_F_DENSITY: { double4 q = Q1[s]; q.w = d[t]; Q1[s] = q; } break;
+    case WF_F_T: { double4 q = Q2[s]; q.y = d[t]; Q2[s] = q; } break;
+    case WF_F_SIGMAY: F[(int64_t)F_SIGY * cap + s] = d[t]; break;
+    case WF_F_ID: I[(int64_t)I_ID * cap + s] = ((const int *)in)[t]; break;
+    default: break;
+    }
+}
+static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, const void *host)
+{
+    if (!c || !host) return WF_ERR_ARG;
+    if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_upload: no particles");
+    switch (f) { case WF_F_X: case WF_F_V: case WF_F_A: case WF_F_DENSITY: case WF_F_T: case WF_F_SIGMAY: case WF_F_ID: break;
+        default: return fail(c, WF_ERR_UNSUPPORTED, "wf_upload: field %d is not uploadable", (int)f); }
+    cudaSetDevice(c->device);
+    const int nc = field_ncomp(f); const bool isint = field_is_int(f);
+    const int64_t cnt = idx ? nidx : c->n;
+    if (cnt == 0) return 0;
+    const size_t bytes = (((size_t)cnt * nc * (isint ? 4 : 8) + 255) / 256) * 256;
+    WF_CHECK(ensure_stage(c, bytes + (idx ? (size_t)nidx * 4 : 0)));
+    WF_CUDA(c, cudaMemcpyAsync(c->stage, host, (size_t)cnt * nc * (isint ? 4 : 8), cudaMemcpyHostToDevice, c->stream));
+    int *d_idx = nullptr;
+    if (idx) { d_idx = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(d_idx, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); }
+    k_upload<<<grid_for(cnt, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->F[c->cur], c->I[c->cur], c->cap, (int)f, c->n, c->slot_of, d_idx, nidx, c->stage);
+    WF_LAUNCH_CHECK(c);
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" int wf_upload(wf_ctx *c, wf_field f, const void *host) { return upload_impl(c, f, nullptr, 0, host); }
+extern "C" int wf_upload_subset(wf_ctx *c, wf_field f, const int32_t *idx, int64_t n, const void *host)
+{ if (n > 0 && !idx) return WF_ERR_ARG; return upload_impl(c, f, idx, n, host); }
+
+extern "C" int wf_mesh_download(wf_ctx *c, int mesh, double *nodes, double *normals, double *pplane)
+{
+    if (!c || mesh < 0 || mesh >= (int)c->meshes.size()) return fail(c, WF_ERR_ARG, "wf_mesh_download: bad mesh index %d", mesh);
+    const HostMesh &hm = c->meshes[mesh];
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (nodes) WF_CUDA(c, cudaMemcpy(nodes, c->dm.node + 3 * hm.node0, 3 * hm.n_nodes * sizeof(double), cudaMemcpyDeviceToHost));
+    if (normals) WF_CUDA(c, cudaMemcpy(normals, c->dm.enormal + 3 * hm.elem0, 3 * hm.n_elems * sizeof(double), cudaMemcpyDeviceToHost));
+    if (pplane) WF_CUDA(c, cudaMemcpy(pplane, c->dm.pplane + hm.elem0, hm.n_elems * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- profiling ---------------------------------------------------------------------------------------------------------
+static const char *k_prof_names[PK_COUNT] = { "nb_keys", "nb_sort", "nb_permute", "nb_cells", "nb_list", "nb_surface", "nb_contact",
+    "step_begin", "density", "rate_stress", "accel", "contact", "bc", "move", "thermal", "energy", "reduce", "step_end" };
+extern "C" const char *wf_prof_name(int k) { return (k >= 0 && k < PK_COUNT) ? k_prof_names[k] : ""; }
+extern "C" int wf_prof_enable(wf_ctx *c, int on)
+{
+    if (!c) return WF_ERR_ARG;
+    c->prof = on != 0; std::memset(c->prof_ms, 0, sizeof(c->prof_ms)); std::memset(c->prof_n, 0, sizeof(c->prof_n));
+    return 0;
+}
+extern "C" int wf_prof_get(wf_ctx *c, double *ms, int64_t *launches, int cap, int *n_used)
+{
+    if (!c) return WF_ERR_ARG;
+    int k = 0; for (; k < PK_COUNT && k < cap; ++k) { if (ms) ms[k] = c->prof_ms[k]; if (launches) launches[k] = c->prof_n[k]; }
+    if (n_used) *n_used = k;
+    return 0;
+}
+extern "C" int wf_launch_count(wf_ctx *c, int64_t *launches) { if (!c || !launches) return WF_ERR_ARG; *launches = c->launches; return 0; }
+
+// ---- host-side lattice generators ---------------------------------------------------------------------------------------
+// Source/Domain.cpp:674-689 calcHalfPartCount
+static int half_part_count(double r, double R, int xinc)
+{
+    int ypartcount = -1;
+    if (xinc > 0) {
+        ypartcount = 1;
+        double yp = r, xp = r + (double)(xinc - 1) * 2. * r;
+        double rad = std::sqrt(yp * yp + xp * xp);
+        while (rad <= R - r) { yp += 2. * r; rad = std::sqrt(yp * yp + xp * xp); ypartcount++; }
+        ypartcount -= 1;
+    }
+    return ypartcount;
+}
+// Source/Domain.cpp:708-792 AddCylinderLength, 3-D lattice (no ghost rows): fills SoA points directly instead of
+// `new Particle` per point; point order is the reference's (z rows, then y, then x).
+extern "C" int64_t wf_gen_cylinder(const double V[3], double Rxy, double Lz, double r, double *pts, int64_t cap)
+{
+    if (!V || r <= 0.0) return WF_ERR_ARG;
+    const int numpartxy = half_part_count(r, Rxy, 1);
+    int64_t n = 0;
+    double zp = V[2] + r;
+    while (zp <= (V[2] + Lz - r)) {
+        double yp = V[1] - r - (2. * r * (numpartxy - 1));
+        int numypart = 2 * numpartxy, yinc = numpartxy, yinc_sign = -1;
+        for (int j = 0; j < numypart; ++j) {
+            int numxpart = half_part_count(r, Rxy, yinc);
+            double xp = V[0] - r - (2. * r * (numxpart - 1));
+            for (int i = 0; i < 2 * numxpart; ++i) {
+                if (pts) { if (n >= cap) return WF_ERR_ARG; pts[3 * n] = xp; pts[3 * n + 1] = yp; pts[3 * n + 2] = zp; }
+                ++n; xp += 2. * r;
+            }
+            yp += 2. * r; yinc += yinc_sign;
+            if (yinc < 1) { yinc = 1; yinc_sign = 1; }
+        }
+        zp += 2. * r;
+    }
+    return n;
+}
+// Source/Domain.cpp:326-455 AddBoxLength, 3-D cubic packing (type 1, random = false); box_dims = Max + r - V (mass rule :447-455)
+extern "C" int64_t wf_gen_box(const double V[3], double Lx, double Ly, double Lz, double r, double *pts, int64_t cap, double box_dims[3])
+{
+    if (!V || r <= 0.0) return WF_ERR_ARG;
+    int64_t n = 0; double Max[3] = { V[0], V[1], V[2] };
+    size_t k = 0; double zp = V[2];
+    while (zp <= (V[2] + Lz - r)) {
+        size_t j = 0; double yp = V[1];
+        while (yp <= (V[1] + Ly - r)) {
+            size_t i = 0; double xp = V[0];
+            while (xp <= (V[0] + Lx - r)) {
+                double x = V[0] + (2.0 * i + 1) * r, y = V[1] + (2.0 * j + 1) * r, z = V[2] + (2.0 * k + 1) * r;
+                if (pts) { if (n >= cap) return WF_ERR_ARG; pts[3 * n] = x; pts[3 * n + 1] = y; pts[3 * n + 2] = z; }
+                if (x > Max[0]) Max[0] = x; if (y > Max[1]) Max[1] = y; if (z > Max[2]) Max[2] = z;
+                ++n; i++; xp = V[0] + (2 * i + 1) * r;
+            }
+            j++; yp = V[1] + (2.0 * j + 1) * r;
+        }
+        k++; zp = V[2] + (2.0 * k + 1) * r;
+    }
+    if (box_dims) for (int q = 0; q < 3; ++q) { Max[q] += r; box_dims[q] = Max[q] - V[q]; }
+    return n;
+}

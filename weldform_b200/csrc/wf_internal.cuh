@@ -1,0 +1,154 @@
+// Internal declarations shared by the translation units of libweldform_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/weldform_b200.h"
+#include "wf_math.cuh"
+
+namespace wf {
+
+// ---- property classes: distinct tuples of the per-particle constants the drivers assign (Particle.h:53-231) ------
+struct ClassProps {
+    double G, Cs, P0, RefDensity, Alpha, Beta, TI, TIn, TIInitDist, Ep, k_T, cp_T, h_conv, T_inf, th_exp, q_source;
+    int PresEq, Fail, Material, Material_model, mat_id, Thermal_BC, IsMesh, pad;
+};
+struct MatProps { int model, pad; double E, nu, p[13], eps0, eps1; };
+
+// ---- own (non-gathered) per-particle doubles, structure of arrays: field f of slot s is F[f*cap + s] -------------
+enum OwnField {
+    F_AX = 0, F_AY, F_AZ, F_DX, F_DY, F_DZ, F_DDENS,
+    F_SH,                 // ShearStress xx,yy,zz,xy,yz,xz
+    F_SR = F_SH + 6,      // StrainRate 6
+    F_RR = F_SR + 6,      // RotationRate 01,02,12
+    F_ST = F_RR + 3,      // Strain 6
+    F_SP = F_ST + 6,      // Strain_pl 6
+    F_SI = F_SP + 6,      // Strain_pl_incr 6
+    F_PLS = F_SI + 6, F_DPLS, F_SIGY, F_EFFSR, F_DTDT, F_QCONV, F_QPL, F_QFRIC, F_QCONT,
+    F_CFX, F_CFY, F_CFZ, F_DCONT, F_NX, F_NY, F_NZ, F_DKIN, F_DINT,
+    F_CSUM, F_CREAC, F_CEXT,          // per-particle partial sums of the Wang contact loop
+    F_COUNT
+};
+enum OwnInt { I_ID = 0, I_IDORIG, I_NB, I_NOWRITE, I_ORIG, I_OLDSURF, I_COUNT };
+
+struct DevMesh {      // concatenated over meshes
+    int n_nodes = 0, n_elems = 0;
+    double *node = nullptr, *node_v = nullptr;       // 3*n_nodes
+    int *en = nullptr;                               // 3*n_elems (global node ids)
+    int *nfar = nullptr, *emesh = nullptr;           // per element
+    double *enormal = nullptr, *ev = nullptr, *pplane = nullptr;   // 3*,3*,1* n_elems
+    double *motion = nullptr;                        // per mesh: m_v(3), m_w(3), vmax(3), tau, has_ramp  (11 doubles)
+};
+struct HostMesh { int node0, elem0, n_nodes, n_elems, id; int64_t first_particle; };
+
+struct BCEntry { int id, set_a; double v[3]; double tau; };
+
+// device-resident step scalars (advanced by kernels so that whole steps can be replayed without host involvement)
+struct DevScalars {
+    double time, dt;
+    double kin_energy_sum, int_energy_sum, plastic_work, contact_force_sum, contact_reaction_sum, ext_forces_work,
+           contact_friction_work, accum_cont_heat_cond;
+    double max_pl_strain, max_disp2[3], max_T, min_T;
+    double mcf[4][3];
+};
+
+enum ProfKernel { PK_NB_KEYS = 0, PK_NB_SORT, PK_NB_PERMUTE, PK_NB_CELLS, PK_NB_LIST, PK_NB_SURFACE, PK_NB_CONTACT,
+                  PK_BEGIN, PK_DENSITY, PK_RATE_STRESS, PK_ACCEL, PK_CONTACT, PK_BC, PK_MOVE, PK_THERMAL, PK_ENERGY,
+                  PK_REDUCE, PK_END, PK_COUNT };
+
+} // namespace wf
+
+struct wf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    wf_params prm;
+    bool have_particles = false, solver_ready = false;
+
+    int64_t n = 0, nsph = 0, cap = 0;            // particles (SPH + mesh), SPH count, allocated slots
+    // gathered arrays, double-buffered (index cur / 1-cur)
+    double4 *Q0[2] = { nullptr, nullptr }, *Q1[2] = { nullptr, nullptr }, *Q2[2] = { nullptr, nullptr },
+            *S0[2] = { nullptr, nullptr }, *S1[2] = { nullptr, nullptr }, *S2[2] = { nullptr, nullptr };
+    double *F[2] = { nullptr, nullptr };
+    int *I[2] = { nullptr, nullptr };
+    int cur = 0;
+    int *slot_of = nullptr;                      // creation index -> slot
+    // classes / materials
+    std::vector<wf::ClassProps> h_classes; wf::ClassProps *d_classes = nullptr; int n_classes = 0;
+    std::vector<wf::MatProps> h_mats; wf::MatProps *d_mats = nullptr;
+    bool any_ti = false, uniform_h = false;
+    double totmass_mean = 0.0;                   // CalculateSurface's serial mean mass (Domain.cpp:1421-1425)
+    // cell grid (Neighbour.cpp:10-139)
+    double BLPF[3], TRPR[3], CellSize[3], hmax = 0.0, Cellfac = 2.0; int CellNo[3] = { 0, 0, 0 }; int64_t ncells = 0;
+    int ax_fast = 0, ax_mid = 1, ax_slow = 2;
+    unsigned long long *keys[2] = { nullptr, nullptr }; int *vals[2] = { nullptr, nullptr };
+    int *cell_start = nullptr, *cell_end = nullptr; int64_t cell_cap = 0;
+    void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
+    // neighbour lists (ELL, transposed): nbr[k*cap + slot]; bit31 = "slot is temp1 (first) of the reference pair"
+    uint32_t *nbr = nullptr; int nbr_k = 0; int64_t nbr_alloc = 0;
+    int *nb_cnt = nullptr, *nb_hi = nullptr, *d_maxcnt = nullptr;
+    // contact candidate lists: cont[k*cap + slot] = global element index
+    int *cont = nullptr; int cont_k = 0; int64_t cont_alloc = 0; int *cont_cnt = nullptr;
+    // meshes
+    wf::DevMesh dm; std::vector<wf::HostMesh> meshes; std::vector<int> mesh_ids; int *d_mesh_ids = nullptr;
+    std::vector<double> h_motion;
+    struct PendingMesh { std::vector<double> nodes, normals, radius; std::vector<int> elems, nfar; double hfac; int id; };
+    std::vector<PendingMesh> pending_meshes;
+    // boundary conditions
+    std::vector<wf::BCEntry> h_bcs; wf::BCEntry *d_bcs = nullptr; int n_bcs = 0;
+    // scalars
+    wf::DevScalars *d_sc = nullptr; wf::DevScalars *h_sc = nullptr;   // h_sc pinned
+    double *d_partial = nullptr; int partial_blocks = 0;
+    // solver state (SolverFraser.cpp:62-68)
+    double dt = 0.0, time = 0.0; int ts_i = 0; bool isfirst = true, isyielding = false, nb_cleared = true;
+    int64_t steps = 0, nb_rebuilds = 0, launches = 0;
+    double step_max_pl = 0.0;                    // `max` of SolverFraser.cpp:139-149 for the step in flight
+    // staging
+    void *stage = nullptr; size_t stage_bytes = 0; void *h_stage = nullptr; size_t h_stage_bytes = 0;
+    // profiling
+    bool prof = false; double prof_ms[wf::PK_COUNT]; int64_t prof_n[wf::PK_COUNT]; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    double *Fp(int f) { return F[cur] + (int64_t)f * cap; }
+    int *Ip(int f) { return I[cur] + (int64_t)f * cap; }
+};
+
+namespace wf {
+
+int fail(wf_ctx *c, int code, const char *fmt, ...);
+#define WF_CUDA(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return wf::fail((c), WF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define WF_CHECK(expr) do { int r_ = (expr); if (r_ != 0) return r_; } while (0)
+#define WF_LAUNCH_CHECK(c) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return wf::fail((c), WF_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct ProfScope {
+    wf_ctx *c; int k;
+    ProfScope(wf_ctx *c_, int k_) : c(c_), k(k_) { if (c->prof) cudaEventRecord(c->ev0, c->stream); }
+    ~ProfScope() {
+        if (c->prof) { cudaEventRecord(c->ev1, c->stream); cudaEventSynchronize(c->ev1); float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->prof_ms[k] += ms; c->prof_n[k] += 1; }
+    }
+};
+
+inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+int ensure_stage(wf_ctx *c, size_t bytes);
+
+// wf_neighbour.cu
+int nb_cell_initiate(wf_ctx *c);
+int nb_build_impl(wf_ctx *c);
+// wf_pair.cu
+int pair_density(wf_ctx *c);
+int pair_rate_stress(wf_ctx *c);
+int pair_accel(wf_ctx *c);
+int pair_thermal(wf_ctx *c);
+int pair_energy(wf_ctx *c);
+// wf_step.cu
+int step_begin_impl(wf_ctx *c);
+int contact_impl(wf_ctx *c);
+int apply_bcs_impl(wf_ctx *c);
+int move_pos_impl(wf_ctx *c);
+int move_vel_impl(wf_ctx *c);
+int step_end_impl(wf_ctx *c);
+int reduce_impl(wf_ctx *c, bool to_host);
+
+} // namespace wf

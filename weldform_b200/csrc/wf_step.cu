@@ -1,0 +1,460 @@
+// Per-particle phases of the Fraser step, contact, rigid-mesh update, reductions and the step orchestration
+// (Source/SolverFraser.cpp:21-513). See include/weldform_b200.h for the reference member each entry point replaces.
+#include <cub/cub.cuh>
+#include <cstring>
+#include <cmath>
+
+#include "wf_internal.cuh"
+
+using namespace wf;
+
+namespace {
+
+__device__ inline double ramp(double t, double tau) { if (tau <= 0.0) return 1.0; return t < tau ? t / tau : 1.0; }
+
+struct StepArgs {
+    int64_t n, cap; int nsph; double dt;
+    double4 *Q0, *Q1, *Q2, *S0, *S1, *S2; double *F; int *I; const ClassProps *cls;
+    const BCEntry *bcs; int n_bcs; DevScalars *sc;
+};
+#define OWN(f) a.F[(int64_t)(f) * a.cap + s]
+#define OWNI(f) a.I[(int64_t)(f) * a.cap + s]
+
+// device-side GeneralAfter (examples/Compression_thermal.cpp:30-66 pattern; oracle/ref_driver.cpp UserBC)
+__device__ inline void apply_bc(const StepArgs &a, int64_t s, int id, double t, double &vx, double &vy, double &vz, double &ax, double &ay, double &az)
+{
+    for (int b = 0; b < a.n_bcs; ++b) {
+        if (id == a.bcs[b].id) {
+            const double f = ramp(t, a.bcs[b].tau);
+            if (a.bcs[b].set_a) { ax = 0.0; ay = 0.0; az = 0.0; }
+            vx = a.bcs[b].v[0] * f; vy = a.bcs[b].v[1] * f; vz = a.bcs[b].v[2] * f;
+        }
+    }
+}
+
+// mode bit 0: GeneralAfter before the move (SolverFraser.cpp:332); bit 1: position update (:337-343);
+// bit 2: velocity update (:352-355); bit 3: GeneralAfter after the move (:360)
+__global__ void k_bc_move(StepArgs a, int mode)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    const double t = a.sc->time, dt = a.dt;
+    double4 q = a.Q0[s], w = a.Q1[s];
+    double ax = OWN(F_AX), ay = OWN(F_AY), az = OWN(F_AZ);
+    const int id = OWNI(I_ID);
+    if ((mode & 1) && a.n_bcs) apply_bc(a, s, id, t, w.x, w.y, w.z, ax, ay, az);
+    if (mode & 2) {
+        // du = (v + VXSPH)*deltat + 0.5*a*deltat*deltat with VXSPH == 0 (never computed by the new solvers)
+        const double dux = (w.x + 0.0) * dt + 0.5 * ax * dt * dt, duy = (w.y + 0.0) * dt + 0.5 * ay * dt * dt, duz = (w.z + 0.0) * dt + 0.5 * az * dt * dt;
+        OWN(F_DX) += dux; OWN(F_DY) += duy; OWN(F_DZ) += duz;
+        q.x += dux; q.y += duy; q.z += duz;
+        a.Q0[s] = q;
+    }
+    if (mode & 4) { w.x += ax * dt; w.y += ay * dt; w.z += az * dt; }
+    if ((mode & 8) && a.n_bcs) apply_bc(a, s, id, t, w.x, w.y, w.z, ax, ay, az);
+    a.Q1[s] = w;
+    OWN(F_AX) = ax; OWN(F_AY) = ay; OWN(F_AZ) = az;
+}
+
+// mesh velocity ramps set from the callback in the oracle driver (trimesh[m]->SetVel)
+__global__ void k_mesh_ramp(double *motion, int n_mesh, const DevScalars *sc)
+{
+    int m = threadIdx.x; if (m >= n_mesh) return;
+    double *mo = motion + 16 * m;
+    if (mo[10] != 0.0) { const double f = ramp(sc->time, mo[9]); mo[0] = mo[6] * f; mo[1] = mo[7] * f; mo[2] = mo[8] * f; }
+}
+
+// ---- CalcContactForcesWang (Source/Contact_Wang.cpp:15-348), one thread per SPH particle with contact candidates ----
+struct ContactArgs {
+    int K; const int *cont, *cont_cnt; const double *node, *enormal, *ev, *pplane; const int *en, *emesh;
+    double friction_sta, friction_dyn, dfac, contact_hc; int cont_heat_fric, cont_heat_cond;
+};
+__global__ void k_contact(StepArgs a, ContactArgs k)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    // resets (Contact_Wang.cpp:27-42)
+    double cfx = 0., cfy = 0., cfz = 0., dcont = 0., qfric = 0., qcont = 0., csum = 0., creac = 0., cext = 0.;
+    const int cnt = k.cont_cnt[s];
+    if (cnt > 0) {
+        const double4 q = a.Q0[s], w = a.Q1[s], q2 = a.Q2[s];
+        const V3 x = v3(q.x, q.y, q.z), v = v3(w.x, w.y, w.z);
+        const double h = q.w, Mass = q2.x, dens = w.w, dt = a.dt;
+        V3 acc = v3(OWN(F_AX), OWN(F_AY), OWN(F_AZ));
+        for (int c = 0; c < cnt; ++c) {
+            const int e = k.cont[(int64_t)c * a.cap + s];
+            const V3 n2 = v3(k.enormal[3 * e], k.enormal[3 * e + 1], k.enormal[3 * e + 2]);
+            const V3 v2 = v3(k.ev[3 * e], k.ev[3 * e + 1], k.ev[3 * e + 2]);
+            const V3 vr = v - v2;
+            const double delta_ = -dot(n2, vr);
+            const V3 x_pred = (x + dt * v) + (dt * (dt * acc)) / 2.0;
+            const double dist = dot(n2, x_pred) - k.pplane[e];
+            if (dist < h) {
+                const V3 qj = x - dist * n2;
+                bool inside = true; int i = 0;
+                while (i < 3 && inside) {
+                    int j = i + 1; if (j > 2) j = 0;
+                    const int ni = k.en[3 * e + i], nj = k.en[3 * e + j];
+                    const V3 Ni = v3(k.node[3 * ni], k.node[3 * ni + 1], k.node[3 * ni + 2]), Nj = v3(k.node[3 * nj], k.node[3 * nj + 1], k.node[3 * nj + 2]);
+                    const double crit = dot(cross(Nj - Ni, qj - Ni), n2);
+                    if (crit < 0.0) inside = false;
+                    i++;
+                }
+                if (inside) {
+                    const double delta = h - dist;
+                    const double kij = 2.0 * Mass / (dt * dt);
+                    const double omega = sqrt(kij / Mass);
+                    const double psi_cont = 2. * Mass * omega * k.dfac;
+                    V3 cf = (kij * delta - psi_cont * delta_) * n2;
+                    dcont = delta;
+                    acc = acc + cf / Mass;
+                    const double dS2 = pow(Mass / dens, 2.0 / 3.0);
+                    if (k.friction_sta > 0.) {
+                        const V3 du = (x_pred - x) - dt * v2;
+                        const V3 delta_tg = du - dot(du, n2) * n2;
+                        const V3 tgforce = kij * delta_tg;
+                        if (norm(tgforce) < k.friction_sta * norm(cf)) {
+                            cf = cf - tgforce / Mass;          // unit quirk kept (Contact_Wang.cpp:279)
+                            acc = acc - tgforce / Mass;
+                        } else {
+                            const V3 tgforce_dyn = ((k.friction_dyn * norm(cf)) * tgforce) / norm(tgforce);
+                            cf = cf - tgforce_dyn;
+                            acc = acc - tgforce_dyn / Mass;
+                            if (k.cont_heat_fric) { const double abs_fv = fabs(dot(tgforce_dyn, vr)); qfric = abs_fv * dens / Mass; }
+                        }
+                    }
+                    cfx = cf.x; cfy = cf.y; cfz = cf.z;
+                    csum += norm(cf);
+                    creac += dot(acc, n2) * Mass;
+                    cext += dot(cf, v2);
+                    if (k.cont_heat_cond) qcont = dens * k.contact_hc * dS2 * (0.0 - q2.y) / Mass;   // mesh particle T stays 0 unless conduction to the tool is modelled
+                }
+            }
+        }
+        OWN(F_AX) = acc.x; OWN(F_AY) = acc.y; OWN(F_AZ) = acc.z;
+    }
+    OWN(F_CFX) = cfx; OWN(F_CFY) = cfy; OWN(F_CFZ) = cfz; OWN(F_DCONT) = dcont; OWN(F_QFRIC) = qfric; OWN(F_QCONT) = qcont;
+    OWN(F_CSUM) = csum; OWN(F_CREAC) = creac; OWN(F_CEXT) = cext;
+}
+
+// ---- TriMesh::Update (Source/Mesh.cpp:273-293) + Domain::UpdateContactParticles (Source/Contact.cpp:41-55) ----------
+__global__ void k_mesh_nodes_one(int n_nodes, double *node, double *node_v, const double *mo, double dt)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x; if (n >= n_nodes) return;
+    const V3 m_v = v3(mo[0], mo[1], mo[2]), m_w = v3(mo[3], mo[4], mo[5]);
+    V3 p = v3(node[3 * n], node[3 * n + 1], node[3 * n + 2]);
+    const V3 vr = cross(m_w, p);
+    const V3 nv = m_v + vr;
+    p = p + dt * nv;
+    node_v[3 * n] = nv.x; node_v[3 * n + 1] = nv.y; node_v[3 * n + 2] = nv.z;
+    node[3 * n] = p.x; node[3 * n + 1] = p.y; node[3 * n + 2] = p.z;
+}
+__global__ void k_mesh_elems(int n_elems, int nsph, const double *node, const double *node_v, const int *en, const int *nfar, double *enormal, double *ev, double *pplane,
+                             const int *slot_of, double4 *Q1, double *F, int64_t cap)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x; if (e >= n_elems) return;
+    const int n0 = en[3 * e], n1 = en[3 * e + 1], n2 = en[3 * e + 2];
+    const V3 A = v3(node[3 * n0], node[3 * n0 + 1], node[3 * n0 + 2]), B = v3(node[3 * n1], node[3 * n1 + 1], node[3 * n1 + 2]), C = v3(node[3 * n2], node[3 * n2 + 1], node[3 * n2 + 2]);
+    const V3 u = B - A, v = C - A, w = cross(u, v);
+    const V3 nr = w / norm(w);                                        // CalcNormals (Mesh.cpp:235-243)
+    const int nf = en[3 * e + nfar[e]];
+    pplane[e] = dot(v3(node[3 * nf], node[3 * nf + 1], node[3 * nf + 2]), nr);   // UpdatePlaneCoeff
+    enormal[3 * e] = nr.x; enormal[3 * e + 1] = nr.y; enormal[3 * e + 2] = nr.z;
+    V3 vv = v3(0., 0., 0.);
+    vv = vv + v3(node_v[3 * n0], node_v[3 * n0 + 1], node_v[3 * n0 + 2]); vv = vv + v3(node_v[3 * n1], node_v[3 * n1 + 1], node_v[3 * n1 + 2]); vv = vv + v3(node_v[3 * n2], node_v[3 * n2 + 1], node_v[3 * n2 + 2]);
+    vv = vv / 3;
+    ev[3 * e] = vv.x; ev[3 * e + 1] = vv.y; ev[3 * e + 2] = vv.z;
+    // element particle: v = mean node velocity, a = 0, normal = element normal
+    const int s = slot_of[nsph + e];
+    double4 q1 = Q1[s]; q1.x = vv.x; q1.y = vv.y; q1.z = vv.z; Q1[s] = q1;
+    F[(int64_t)F_AX * cap + s] = 0.; F[(int64_t)F_AY * cap + s] = 0.; F[(int64_t)F_AZ * cap + s] = 0.;
+    F[(int64_t)F_NX * cap + s] = nr.x; F[(int64_t)F_NY * cap + s] = nr.y; F[(int64_t)F_NZ * cap + s] = nr.z;
+}
+
+// ---- reductions ---------------------------------------------------------------------------------------------------------
+enum { R_DKIN = 0, R_DINT, R_PLW, R_FRIC, R_COND, R_CSUM, R_CREAC, R_CEXT, R_NSUM, R_MAXPL = R_NSUM, R_MD0, R_MD1, R_MD2, R_TMAX, R_TMIN, R_NTOT };
+
+__global__ void __launch_bounds__(256) k_reduce_partial(StepArgs a, int first_fem, double *partial)
+{
+    double acc[R_NTOT];
+    for (int k = 0; k < R_NSUM; ++k) acc[k] = 0.;
+    acc[R_MAXPL] = 0.; acc[R_MD0] = acc[R_MD1] = acc[R_MD2] = 0.; acc[R_TMAX] = 0.; acc[R_TMIN] = 1000.;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < a.n; s += (int64_t)gridDim.x * blockDim.x) {
+        const int o = OWNI(I_ORIG);
+        acc[R_DKIN] += OWN(F_DKIN);
+        acc[R_MAXPL] = fmax(acc[R_MAXPL], OWN(F_PLS));
+        if (o < a.nsph) {
+            const double m = a.Q2[s].x, d = a.Q1[s].w;
+            acc[R_PLW] += m / d * OWN(F_QPL);
+            acc[R_FRIC] += OWN(F_QFRIC) * m / d;
+            acc[R_COND] += OWN(F_QCONT) * m / d;
+            acc[R_CSUM] += OWN(F_CSUM); acc[R_CREAC] += OWN(F_CREAC); acc[R_CEXT] += OWN(F_CEXT);
+            const double dx = OWN(F_DX), dy = OWN(F_DY), dz = OWN(F_DZ);
+            acc[R_MD0] = fmax(acc[R_MD0], dx * dx); acc[R_MD1] = fmax(acc[R_MD1], dy * dy); acc[R_MD2] = fmax(acc[R_MD2], dz * dz);
+            const double T = a.Q2[s].y; acc[R_TMAX] = fmax(acc[R_TMAX], T); acc[R_TMIN] = fmin(acc[R_TMIN], T);
+        }
+        if (o < first_fem) acc[R_DINT] += OWN(F_DINT);
+    }
+    typedef cub::BlockReduce<double, 256> BR; __shared__ typename BR::TempStorage tmp;
+    for (int k = 0; k < R_NTOT; ++k) {
+        double r;
+        if (k < R_NSUM) r = BR(tmp).Sum(acc[k]);
+        else if (k == R_TMIN) r = BR(tmp).Reduce(acc[k], cub::Min());
+        else r = BR(tmp).Reduce(acc[k], cub::Max());
+        __syncthreads();
+        if (threadIdx.x == 0) partial[(int64_t)blockIdx.x * 32 + k] = r;
+    }
+}
+// accumulate = 1: end-of-step bookkeeping (energy sums += inc*dt etc.); 0: refresh maxima only
+__global__ void __launch_bounds__(256) k_reduce_final(const double *partial, int nblocks, DevScalars *sc, double dt, int accumulate)
+{
+    typedef cub::BlockReduce<double, 256> BR; __shared__ typename BR::TempStorage tmp;
+    __shared__ double res[R_NTOT];
+    for (int k = 0; k < R_NTOT; ++k) {
+        double v = (k < R_NSUM) ? 0. : (k == R_TMIN ? 1000. : 0.);
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+            const double p = partial[(int64_t)b * 32 + k];
+            if (k < R_NSUM) v += p; else if (k == R_TMIN) v = fmin(v, p); else v = fmax(v, p);
+        }
+        double r;
+        if (k < R_NSUM) r = BR(tmp).Sum(v); else if (k == R_TMIN) r = BR(tmp).Reduce(v, cub::Min()); else r = BR(tmp).Reduce(v, cub::Max());
+        __syncthreads();
+        if (threadIdx.x == 0) res[k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sc->max_pl_strain = res[R_MAXPL];
+        sc->max_disp2[0] = res[R_MD0]; sc->max_disp2[1] = res[R_MD1]; sc->max_disp2[2] = res[R_MD2];
+        sc->max_T = res[R_TMAX]; sc->min_T = res[R_TMIN];
+        if (accumulate) {
+            sc->kin_energy_sum += res[R_DKIN] * dt;             // Domain.cpp:1807
+            sc->int_energy_sum += res[R_DINT] * dt;             // Domain.cpp:1828
+            sc->plastic_work += res[R_PLW] * dt;                // ThermalStuct.cpp:36
+            sc->contact_friction_work += res[R_FRIC] * dt;      // Thermal.cpp:208
+            sc->accum_cont_heat_cond += res[R_COND] * dt;       // Thermal.cpp:209
+            sc->contact_force_sum = res[R_CSUM]; sc->contact_reaction_sum = res[R_CREAC];
+            sc->ext_forces_work += res[R_CEXT] * dt;            // Contact_Wang.cpp:344
+            sc->time += dt;                                     // SolverFraser.cpp:384
+        }
+    }
+}
+__global__ void k_set_time(DevScalars *sc, double t, double dt) { sc->time = t; sc->dt = dt; }
+
+// InitialChecks (Domain.cpp:2097-2113): Pressure = EOS(...) for every particle
+__global__ void k_init_pressure(StepArgs a)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    const double4 q2 = a.Q2[s]; const ClassProps cp = a.cls[(int)q2.z];
+    ((double *)&a.Q2[s])[3] = eos(cp.PresEq, cp.Cs, cp.P0, a.Q1[s].w, cp.RefDensity);
+}
+
+StepArgs make_step_args(wf_ctx *c)
+{
+    StepArgs a; a.n = c->n; a.cap = c->cap; a.nsph = (int)c->nsph; a.dt = c->dt;
+    a.Q0 = c->Q0[c->cur]; a.Q1 = c->Q1[c->cur]; a.Q2 = c->Q2[c->cur]; a.S0 = c->S0[c->cur]; a.S1 = c->S1[c->cur]; a.S2 = c->S2[c->cur];
+    a.F = c->F[c->cur]; a.I = c->I[c->cur]; a.cls = c->d_classes; a.bcs = c->d_bcs; a.n_bcs = c->n_bcs; a.sc = c->d_sc;
+    return a;
+}
+
+} // namespace
+
+namespace wf {
+
+int contact_impl(wf_ctx *c)
+{
+    if (!c->prm.contact) return 0;
+    if (!c->cont) return fail(c, WF_ERR_ARG, "wf_contact before the first neighbour build");
+    ProfScope ps(c, PK_CONTACT);
+    StepArgs a = make_step_args(c);
+    ContactArgs k; k.K = c->cont_k; k.cont = c->cont; k.cont_cnt = c->cont_cnt; k.node = c->dm.node; k.enormal = c->dm.enormal; k.ev = c->dm.ev; k.pplane = c->dm.pplane;
+    k.en = c->dm.en; k.emesh = c->dm.emesh; k.friction_sta = c->prm.friction_sta; k.friction_dyn = c->prm.friction_dyn; k.dfac = c->prm.dfac; k.contact_hc = c->prm.contact_hc;
+    k.cont_heat_fric = c->prm.cont_heat_fric; k.cont_heat_cond = c->prm.cont_heat_cond;
+    k_contact<<<grid_for(c->n, 128), 128, 0, c->stream>>>(a, k); WF_LAUNCH_CHECK(c); c->launches++;
+    return 0;
+}
+
+static int bc_move(wf_ctx *c, int mode, int pk)
+{
+    ProfScope ps(c, pk);
+    StepArgs a = make_step_args(c);
+    if ((mode & 9) && !c->meshes.empty()) { k_mesh_ramp<<<1, 32, 0, c->stream>>>(c->dm.motion, (int)c->meshes.size(), c->d_sc); WF_LAUNCH_CHECK(c); c->launches++; }
+    k_bc_move<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a, mode); WF_LAUNCH_CHECK(c); c->launches++;
+    return 0;
+}
+int apply_bcs_impl(wf_ctx *c) { if (c->n_bcs == 0 && c->meshes.empty()) return 0; return bc_move(c, 1, PK_BC); }
+int move_pos_impl(wf_ctx *c) { return bc_move(c, 2, PK_MOVE); }
+int move_vel_impl(wf_ctx *c) { return bc_move(c, 4, PK_MOVE); }
+
+int reduce_impl(wf_ctx *c, bool accumulate)
+{
+    ProfScope ps(c, PK_REDUCE);
+    StepArgs a = make_step_args(c);
+    int nb = std::min<int64_t>(c->partial_blocks, (c->n + 255) / 256); if (nb < 1) nb = 1;
+    const int first_fem = c->meshes.empty() ? (int)c->n : (int)c->meshes[0].first_particle;
+    k_reduce_partial<<<nb, 256, 0, c->stream>>>(a, c->prm.contact ? first_fem : (int)c->n, c->d_partial); WF_LAUNCH_CHECK(c);
+    k_reduce_final<<<1, 256, 0, c->stream>>>(c->d_partial, nb, c->d_sc, c->dt, accumulate ? 1 : 0); WF_LAUNCH_CHECK(c);
+    c->launches += 2;
+    return 0;
+}
+
+int step_end_impl(wf_ctx *c)
+{
+    // end-of-step reductions + Time += dt on the device
+    WF_CHECK(reduce_impl(c, true));
+    c->time += c->dt;
+    if (c->prm.contact && !c->meshes.empty()) {
+        ProfScope ps(c, PK_END);
+        // meshes are concatenated in the device arrays: one small launch per mesh for the nodes, one for all elements
+        for (size_t m = 0; m < c->meshes.size(); ++m) {
+            const HostMesh &hm = c->meshes[m];
+            k_mesh_nodes_one<<<grid_for(hm.n_nodes, 128), 128, 0, c->stream>>>(hm.n_nodes, c->dm.node + 3 * hm.node0, c->dm.node_v + 3 * hm.node0, c->dm.motion + 16 * m, c->dt);
+            WF_LAUNCH_CHECK(c); c->launches++;
+        }
+        k_mesh_elems<<<grid_for(c->dm.n_elems, 128), 128, 0, c->stream>>>(c->dm.n_elems, (int)c->nsph, c->dm.node, c->dm.node_v, c->dm.en, c->dm.nfar, c->dm.enormal, c->dm.ev, c->dm.pplane,
+            c->slot_of, c->Q1[c->cur], c->F[c->cur], c->cap);
+        WF_LAUNCH_CHECK(c); c->launches++;
+    }
+    return 0;
+}
+
+} // namespace wf
+
+// ================================================================================================================
+// C ABI: phases and whole steps
+// ================================================================================================================
+#define WF_NEED_READY(c) do { if (!(c)) return WF_ERR_ARG; if (!(c)->solver_ready) return wf::fail((c), WF_ERR_ARG, "%s: call wf_solver_init first", __func__); cudaSetDevice((c)->device); } while (0)
+
+extern "C" int wf_solver_init(wf_ctx *c, double dt)
+{
+    if (!c) return WF_ERR_ARG;
+    if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_solver_init: no particles");
+    if (!(dt > 0.0)) return fail(c, WF_ERR_ARG, "wf_solver_init: dt must be > 0");
+    cudaSetDevice(c->device);
+    c->dt = dt; c->time = 0.0; c->ts_i = 0; c->isfirst = true; c->isyielding = false; c->steps = 0;
+    k_set_time<<<1, 1, 0, c->stream>>>(c->d_sc, 0.0, dt); WF_LAUNCH_CHECK(c);
+    StepArgs a = make_step_args(c);
+    k_init_pressure<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c);       // InitialChecks
+    WF_CHECK(nb_cell_initiate(c));                                                               // CellInitiate (+ListGenerate: part of the build)
+    if (c->prm.contact) {
+        // SolverFraser.cpp:71-92: ID_orig = ID, MainNeighbourSearch, SaveNeighbourData, CalculateSurface(1)
+        WF_CHECK(nb_build_impl(c));
+    }
+    c->nb_cleared = true;                                                                        // ClearNbData (:94)
+    c->solver_ready = true;
+    WF_CHECK(reduce_impl(c, false));
+    return 0;
+}
+
+extern "C" int wf_nb_build(wf_ctx *c) { WF_NEED_READY(c); return nb_build_impl(c); }
+extern "C" int wf_density(wf_ctx *c) { WF_NEED_READY(c); return pair_density(c); }
+extern "C" int wf_rate_stress(wf_ctx *c) { WF_NEED_READY(c); return pair_rate_stress(c); }
+extern "C" int wf_accel(wf_ctx *c) { WF_NEED_READY(c); return pair_accel(c); }
+extern "C" int wf_contact(wf_ctx *c) { WF_NEED_READY(c); return contact_impl(c); }
+extern "C" int wf_apply_bcs(wf_ctx *c) { WF_NEED_READY(c); return apply_bcs_impl(c); }
+extern "C" int wf_integrate_pos(wf_ctx *c) { WF_NEED_READY(c); return move_pos_impl(c); }
+extern "C" int wf_integrate_vel(wf_ctx *c) { WF_NEED_READY(c); return move_vel_impl(c); }
+extern "C" int wf_thermal(wf_ctx *c) { WF_NEED_READY(c); return pair_thermal(c); }
+extern "C" int wf_energy(wf_ctx *c) { WF_NEED_READY(c); return pair_energy(c); }
+
+static int fetch_scalars(wf_ctx *c)
+{
+    WF_CUDA(c, cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int wf_reduce(wf_ctx *c, wf_scalars *out)
+{
+    WF_NEED_READY(c);
+    if (!out) return WF_ERR_ARG;
+    WF_CHECK(reduce_impl(c, false));
+    WF_CHECK(fetch_scalars(c));
+    const DevScalars &d = *c->h_sc;
+    std::memset(out, 0, sizeof(*out));
+    out->time = d.time; out->max_pl_strain = d.max_pl_strain;
+    for (int k = 0; k < 3; ++k) out->max_disp[k] = std::sqrt(d.max_disp2[k]);      // SolverFraser.cpp:159
+    out->kin_energy_sum = d.kin_energy_sum; out->int_energy_sum = d.int_energy_sum; out->plastic_work = d.plastic_work;
+    out->contact_force_sum = d.contact_force_sum; out->contact_reaction_sum = d.contact_reaction_sum; out->ext_forces_work = d.ext_forces_work;
+    out->contact_friction_work = d.contact_friction_work; out->accum_cont_heat_cond = d.accum_cont_heat_cond;
+    out->max_T = d.max_T; out->min_T = d.min_T; out->steps = c->steps; out->nb_rebuilds = c->nb_rebuilds; out->is_yielding = c->isyielding ? 1 : 0;
+    return 0;
+}
+
+// SolverFraser.cpp:139-219: max pl_strain / max_disp and the neighbour-rebuild policy
+static int nb_policy(wf_ctx *c)
+{
+    const double MIN_PS_FOR_NBSEARCH = 1.e-6;     // Domain.cpp:28
+    // max pl_strain / max_disp as of the end of the previous step (device scalars are refreshed by every step end).
+    // Once the body is yielding the cadence is fixed (pl_strain never decreases), so no host round trip is needed.
+    double mx = MIN_PS_FOR_NBSEARCH * 2.0; bool check_every = false;
+    if (!c->isyielding) {
+        WF_CHECK(fetch_scalars(c));
+        mx = c->h_sc->max_pl_strain;
+        const V3 md = v3(std::sqrt(c->h_sc->max_disp2[0]), std::sqrt(c->h_sc->max_disp2[1]), std::sqrt(c->h_sc->max_disp2[2]));
+        check_every = norm(md) > 0.1 * c->hmax;
+    }
+    c->step_max_pl = mx;
+    if (mx > MIN_PS_FOR_NBSEARCH && !c->isyielding) {          // first time yielding (:172-179)
+        WF_CHECK(nb_build_impl(c));
+        c->isyielding = true;
+    }
+    if (mx > MIN_PS_FOR_NBSEARCH || c->isfirst || check_every) {
+        if (c->ts_i == 0 && c->nb_cleared) WF_CHECK(nb_build_impl(c));
+    }
+    return 0;
+}
+// SolverFraser.cpp:384-412: Time += dt, mesh update, neighbour cadence bookkeeping
+static int finish_step(wf_ctx *c)
+{
+    const double MIN_PS_FOR_NBSEARCH = 1.e-6;
+    WF_CHECK(step_end_impl(c));
+    if (c->step_max_pl > MIN_PS_FOR_NBSEARCH) {                // :397-406
+        if (c->ts_i == (c->prm.ts_nb_inc - 1)) c->nb_cleared = true;      // ClearNbData
+        c->ts_i++;
+        if (c->ts_i > (c->prm.ts_nb_inc - 1)) c->ts_i = 0;
+    }
+    c->isfirst = false;
+    c->steps++;
+    return 0;
+}
+extern "C" int wf_step_begin(wf_ctx *c) { WF_NEED_READY(c); return nb_policy(c); }   // StartAcceleration's TIR is fused into wf_density; its resets are implicit
+extern "C" int wf_step_end(wf_ctx *c) { WF_NEED_READY(c); return finish_step(c); }
+
+extern "C" int wf_fraser_stage_a(wf_ctx *c)
+{
+    WF_NEED_READY(c);
+    WF_CHECK(nb_policy(c));
+    WF_CHECK(pair_density(c));
+    WF_CHECK(pair_rate_stress(c));
+    WF_CHECK(pair_accel(c));
+    WF_CHECK(contact_impl(c));
+    return 0;
+}
+extern "C" int wf_fraser_stage_b1(wf_ctx *c) { WF_NEED_READY(c); return move_pos_impl(c); }
+extern "C" int wf_fraser_stage_b2(wf_ctx *c) { WF_NEED_READY(c); return move_vel_impl(c); }
+extern "C" int wf_fraser_stage_c(wf_ctx *c)
+{
+    WF_NEED_READY(c);
+    WF_CHECK(pair_thermal(c));
+    WF_CHECK(pair_energy(c));
+    return finish_step(c);
+}
+
+// nsteps whole steps with the device-side boundary conditions at both GeneralAfter points; no host callback.
+extern "C" int wf_fraser_run(wf_ctx *c, int64_t nsteps)
+{
+    WF_NEED_READY(c);
+    for (int64_t k = 0; k < nsteps; ++k) {
+        WF_CHECK(wf_fraser_stage_a(c));
+        // GeneralAfter, x update, v update, GeneralAfter fused in one pass (per-particle, order preserved)
+        {
+            ProfScope ps(c, PK_MOVE);
+            StepArgs a = make_step_args(c);
+            if (!c->meshes.empty()) { k_mesh_ramp<<<1, 32, 0, c->stream>>>(c->dm.motion, (int)c->meshes.size(), c->d_sc); WF_LAUNCH_CHECK(c); c->launches++; }
+            k_bc_move<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a, 15); WF_LAUNCH_CHECK(c); c->launches++;
+        }
+        WF_CHECK(wf_fraser_stage_c(c));
+    }
+    return 0;
+}

@@ -1,0 +1,167 @@
+"""Builds a Context from a "case" dict (the same WFC1 records the oracle programs take, tests/cases.py) and returns the
+state as a dict of numpy arrays. Host-side setup only: lattice generation through the library's generators, rigid-mesh
+construction (TriMesh::AxisPlaneMesh / CalcSpheres, Source/Mesh.cpp:82-220), property arrays. No oracle code is used.
+"""
+import numpy as np
+
+from . import api
+
+_PART_D = {"G": "G", "Cs": "Cs", "P0": "P0", "Alpha": "alpha", "Beta": "beta", "TI": "TI", "TIn": "TIn", "TIInitDist": "TIInitDist", "Ep": "Ep",
+           "k_T": "k_T", "cp_T": "cp_T", "h_conv": "h_conv", "T_inf": "T_inf", "th_exp": "th_exp", "q_source": "q_source",
+           "Sigmay": "sigmay", "T": "T", "RefDensity": "ref_density"}
+_PART_I = {"PresEq": "pres_eq", "Fail": "fail", "Material": "material", "Material_model": "material_model", "mat_id": "mat_id",
+           "Thermal_BC": "thermal_bc", "ID": "id", "IsFree": "is_free", "not_write_surf_ID": "not_write_surf_id"}
+
+
+def _dotb(a, b):
+    """Blitz dot order a0*b0 + (a1*b1 + a2*b2)."""
+    return a[..., 0] * b[..., 0] + (a[..., 1] * b[..., 1] + a[..., 2] * b[..., 2])
+
+
+def axis_plane_mesh(axis, posit, p1, p2, dens):
+    """TriMesh::AxisPlaneMesh + CalcSpheres for dimension 3 (Source/Mesh.cpp:82-220): nodes, elements, normals, nfar, radius."""
+    p1 = np.asarray(p1, float); p2 = np.asarray(p2, float)
+    p = p2 - p1
+    dirs = {0: (1, 2), 1: (0, 2)}.get(axis, (0, 1))
+    x3 = p1[axis]; x2 = p1[dirs[1]]
+    dl = p[dirs[0]] / dens
+    nodes = []
+    for _ in range(dens + 1):
+        x1 = p1[dirs[0]]
+        for _ in range(dens + 1):
+            v = np.zeros(3); v[dirs[0]] = x1; v[dirs[1]] = x2; v[axis] = x3
+            nodes.append(v)
+            x1 += dl
+        x2 += dl
+    nodes = np.array(nodes)
+    elems = []
+    for j in range(dens):
+        for i in range(dens):
+            n0 = (dens + 1) * j + i; n1 = n0 + 1; n2 = (dens + 1) * (j + 1) + i; n3 = n2 + 1
+            if posit:
+                elems += [(n0, n1, n2), (n1, n3, n2)]
+            else:
+                elems += [(n0, n2, n1), (n1, n2, n3)]
+    elems = np.array(elems, np.int32)
+    A, B, Cn = nodes[elems[:, 0]], nodes[elems[:, 1]], nodes[elems[:, 2]]
+    centroid = ((A + B) + Cn) / 3.0
+    u, v = B - A, Cn - A
+    w = np.stack([u[:, 1] * v[:, 2] - u[:, 2] * v[:, 1], u[:, 2] * v[:, 0] - u[:, 0] * v[:, 2], u[:, 0] * v[:, 1] - u[:, 1] * v[:, 0]], axis=1)
+    normals = w / np.sqrt(_dotb(w, w))[:, None]
+    if posit:
+        normals = -normals
+    radius = np.zeros(len(elems))
+    for k in range(3):
+        rv = nodes[elems[:, k]] - centroid
+        radius = np.maximum(radius, np.sqrt(_dotb(rv, rv)))
+    nfar = np.full(len(elems), 2, np.int32)      # Mesh.cpp:211-214: nfar ends as the last node
+    return nodes, elems, normals, nfar, radius
+
+
+def context_from_case(case, device=0):
+    """Create and fully set up a Context; returns (ctx, info)."""
+    ctx = api.Context(device)
+    p = ctx.default_params()
+    p.dimension = int(case.get("Dimension", 3)); p.kernel_type = int(case.get("KernelType", 0)); p.gradient_type = int(case.get("GradientType", 0))
+    p.ts_nb_inc = int(case.get("ts_nb_inc", 5))
+    if "DomMin" in case:
+        for k in range(3):
+            p.dom_min[k] = float(case["DomMin"][k]); p.dom_max[k] = float(case["DomMax"][k])
+    p.thermal_solver = int(case.get("thermal_solver", 0)); p.pl_heating = int(case.get("pl_heating", 0)); p.pl_work_heat_frac = float(case.get("pl_work_heat_frac", 0.9))
+    mesh_count = int(case.get("mesh_count", 0))
+    p.contact = int(case.get("contact", 1 if mesh_count else 0))
+    p.friction_sta = float(case.get("friction_sta", 0.0)); p.friction_dyn = float(case.get("friction_dyn", 0.0))
+    p.pfac = float(case.get("PFAC", 0.4)); p.dfac = float(case.get("DFAC", 0.0))
+    p.cont_heat_fric = int(case.get("cont_heat_fric", 0)); p.cont_heat_cond = int(case.get("cont_heat_cond", 0))
+    if int(case.get("gradKernelCorr", 0)):
+        raise api.WeldformError("gradKernelCorr is not implemented (SURVEY.md section 8f item 2)")
+    ctx.set_params(p)
+    if "materials" in case:
+        mt = np.asarray(case["materials"], float).reshape(-1, 16)
+        ctx.set_materials([tuple(r) for r in mt])
+    # lattice
+    kind = int(case.get("gen_kind", 0))
+    arrays = {}
+    if kind == 1:
+        g = case["gen_args"]
+        pts = api.gen_cylinder((g[1], g[2], g[3]), g[4], g[5], g[6])
+        n = len(pts)
+        mass = np.pi * g[4] * g[4] * g[5] * g[7] / n       # Domain.cpp:839-841
+        arrays.update(x=pts, mass=np.full(n, mass), density=np.full(n, g[7]), h=np.full(n, g[8]), id=np.full(n, int(g[0]), np.int32))
+    elif kind == 2:
+        g = case["gen_args"]
+        pts, dims = api.gen_box((g[1], g[2], g[3]), g[4], g[5], g[6], g[7])
+        n = len(pts)
+        mass = dims[0] * dims[1] * dims[2] * g[8] / n     # Domain.cpp:447-455
+        arrays.update(x=pts, mass=np.full(n, mass), density=np.full(n, g[8]), h=np.full(n, g[9]), id=np.full(n, int(g[0]), np.int32))
+    else:
+        pts = np.asarray(case["x"], float).reshape(-1, 3)
+        n = len(pts)
+        arrays.update(x=pts, mass=case["Mass"], density=case["Density"], h=case["h"])
+    if kind != 0:
+        for key, name in (("Mass", "mass"), ("Density", "density"), ("h", "h")):
+            if key in case:
+                arrays[name] = case[key]
+        if "x" in case:
+            arrays["x"] = np.asarray(case["x"], float).reshape(-1, 3)
+    if "v" in case:
+        arrays["v"] = np.asarray(case["v"], float).reshape(-1, 3)
+    for key, name in _PART_D.items():
+        if key in case:
+            arrays[name] = case[key]
+    for key, name in _PART_I.items():
+        if key in case:
+            arrays[name] = case[key]
+    meshes = []
+    for m in range(mesh_count):
+        pl = case["mesh%d_plane" % m]
+        nodes, elems, normals, nfar, radius = axis_plane_mesh(int(pl[0]), pl[1] != 0, pl[2:5], pl[5:8], int(pl[8]))
+        ctx.add_mesh(nodes, elems, normals, nfar, radius, float(case.get("mesh%d_hfac" % m, 1.1)), int(case.get("mesh%d_id" % m, 10 + m)))
+        meshes.append((len(nodes), len(elems)))
+    ctx.set_particles(n, **arrays)
+    for m in range(mesh_count):
+        key = "mesh%d_vel" % m
+        if key in case:
+            ctx.mesh_set_ramp(m, case[key][:3], float(case[key][3]))
+    if "bc" in case:
+        for r in np.asarray(case["bc"], float).reshape(-1, 8):
+            ctx.add_velocity_bc(int(r[0]), r[1:4], r[4], int(r[5]))
+    return ctx, dict(n_sph=n, meshes=meshes)
+
+
+_DUMP = ["x", "v", "a", "Displacement", "normal", "contforce", "Mass", "h", "Density", "dDensity", "Pressure", "Sigma", "ShearStress", "StrainRate",
+         "RotationRate", "Strain", "Strain_pl", "TIR", "pl_strain", "Sigmay", "eff_strain_rate", "T", "dTdt", "q_plheat", "q_conv", "delta_cont",
+         "dkin_energy_dt", "dint_energy_dt", "ID", "Nb"]
+
+
+def dump(ctx, info, with_pairs=True):
+    out = {}
+    for name in _DUMP:
+        out[name] = ctx.download(name).reshape(-1)
+    s = ctx.reduce()
+    out.update(n_particles=np.array([float(ctx.n)]), solid_part_count=np.array([float(ctx.n_sph)]), Time=np.array([s.time]),
+               kin_energy_sum=np.array([s.kin_energy_sum]), int_energy_sum=np.array([s.int_energy_sum]), plastic_work=np.array([s.plastic_work]),
+               contact_force_sum=np.array([s.contact_force_sum]), contact_reaction_sum=np.array([s.contact_reaction_sum]),
+               ext_forces_work=np.array([s.ext_forces_work]), contact_friction_work=np.array([s.contact_friction_work]),
+               max_disp=np.array(s.max_disp[:]), nb_rebuilds=np.array([float(s.nb_rebuilds)]))
+    if with_pairs:
+        out["pairs"] = ctx.export_pairs().reshape(-1)
+        out["cont_pairs"] = ctx.export_contact_pairs().reshape(-1)
+    for m, (nn, ne) in enumerate(info["meshes"]):
+        nodes, normals, pp = ctx.mesh_download(m, nn, ne)
+        out["mesh%d_nodes" % m] = nodes.reshape(-1); out["mesh%d_normals" % m] = normals.reshape(-1); out["mesh%d_pplane" % m] = pp
+    return out
+
+
+def run_case(case, device=0, with_pairs=True):
+    """Same contract as the oracle programs: case in, state dump out (mode 0: nsteps Fraser steps; mode 1: neighbour build only)."""
+    ctx, info = context_from_case(case, device)
+    try:
+        ctx.solver_init(float(case.get("dt", 1.0e-7)))
+        if int(case.get("mode", 0)) == 1:
+            ctx.nb_build()
+        else:
+            ctx.run(int(case.get("nsteps", 1)))
+        return dump(ctx, info, with_pairs)
+    finally:
+        ctx.close()

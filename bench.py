@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the Fraser SPH step (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--particles P] [--impl ours|reference]
+
+Workload (config.workload): the reference's cylinder-compression lattice (examples/Compression_thermal.cpp:116,
+Domain::AddCylinderLength, R = 0.15, L = 0.56, h = 1.2 dx) scaled by dx to P particles (default 1.0e7, the configuration
+BASELINE.json's metric is quoted on; it fits one GPU), elastoplastic (bilinear J2), thermal solver + plastic heating on,
+artificial viscosity alpha = 1, tensile-instability TI = 0.3, velocity boundary conditions on the top/bottom rows.
+All fields start from the reference's uniform state plus a smooth synthetic velocity field (so that every pair term
+and the yield branch are populated); the run is spun up (untimed) until the body yields so that the timed steps
+include the reference's neighbour-rebuild cadence (every ts_nb_inc = 5 steps).
+
+One "step" = one full Fraser step (SolverFraser.cpp:133-505) over all particles. `value` is device-resident
+(wf_fraser_run, boundary conditions applied on the device); `e2e` drives the step phase by phase through the C ABI
+with a HOST GeneralAfter callback: every step the tagged particles' v and a are copied device->host into pinned
+buffers, the callback runs on the host, the result is copied host->device (twice per step, SolverFraser.cpp:332,360),
+and the step scalars are read back.
+
+`--impl reference` times the reference's own CPU solver (oracle/_ref/wf_ref: /root/reference compiled unmodified, or
+the oracle port if that binary is absent) on the host cores on a bounded sample of the same lattice.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec"
+UNIT = "particle-steps/s"
+R_CYL, L_CYL = 0.15, 0.56
+PERTURB_AMP = 30.0
+
+
+def dx_for(n_particles):
+    vol = np.pi * R_CYL * R_CYL * (L_CYL + 2.0 * L_CYL / 10.0)
+    return float((vol / n_particles) ** (1.0 / 3.0))
+
+
+def workload_config(n_sph, extra=None):
+    cfg = {"workload": "Compression_thermal cylinder lattice (AddCylinderLength R=0.15 L=0.56 h=1.2dx), elastoplastic + thermal + plastic heating, "
+                       "alpha=1 TI=0.3, yielding state, neighbour rebuild every 5 steps",
+           "particles": int(n_sph), "neighbours_per_particle": 56, "solver": "SolveDiffUpdateFraser", "ts_nb_inc": 5,
+           "l2": "inputs larger than L2 (>= 1 kB of fp64 state per particle)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# algorithmic bytes per particle per launch of each kernel family: every own array read or written
+# once + the neighbour-index list (4 B per neighbour) -- the unique-byte HBM lower bound of the gather formulation.
+# ---------------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(nb_avg, ti=True, thermal=True):
+    lst = 4.0 * nb_avg + 8.0
+    b = {
+        "density": 96.0 + (64.0 + 48.0 if ti else 0.0) + lst + 8.0 + (8.0 + 32.0 + 32.0),        # Q0,Q1,Q2 (+Sigma in, TIR out) + list + dDensity; rho update pass
+        "rate_stress": 96.0 + lst + 20 * 8.0 + (32.0 + 16.0 + 8.0 + 37 * 8.0),
+        "accel": 192.0 + lst + 24.0,
+        "thermal": (96.0 + lst + 24.0 + 48.0 + 8.0 + (64.0 + 56.0 + 16.0)) if thermal else 0.0,  # pair pass + per-particle pre pass
+        "energy": 96.0 + lst + 96.0 + 16.0,
+        "move": 64.0 + 24.0 + 24.0 + 4.0 + 64.0 + 24.0 + 24.0,
+    }
+    return b
+
+
+FLOPS_PER_PAIR = {"density": 45.0, "rate_stress": 80.0, "accel": 250.0, "thermal": 45.0, "energy": 40.0}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [t.strip() for t in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference CPU solver (test infrastructure; executed only here as the baseline, never on the product path)
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_throughput(n_sample, steps, warmup, max_threads=None, log=None):
+    """particle-steps/s of the reference's own OpenMP solver on a sample lattice of ~n_sample particles.
+    Time of `steps` steps = T(warmup + steps) - T(warmup) of two whole runs, so setup and the first neighbour build drop out."""
+    from tests import cases, oracle_tools as ot
+    dx = dx_for(n_sample)
+    cores = host_cores()
+    if ot.have_ref():
+        kind = "reference"
+        cand = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores and (max_threads is None or c <= max_threads)}, reverse=True) or [1]
+
+        def run(nsteps, nproc):
+            case = cases.compression_fast(dx=dx, nsteps=nsteps, perturb_amp=PERTURB_AMP)
+            out = ot.run_ref(case, nproc=nproc, timeout=3000)
+            return float(out["solve_seconds"][0]), int(out["solid_part_count"][0])
+        # the reference scales poorly with threads: pick the best thread count on a 2-step probe
+        best = None
+        for c in cand[:4]:
+            t, n = run(2, c)
+            if log:
+                log("reference probe: Nproc=%d  2 steps + setup %.2f s" % (c, t))
+            if best is None or t < best[0]:
+                best = (t, c)
+        nproc = best[1]
+    else:
+        kind = "port"
+        nproc = 1
+        if not ot.have_port():
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"], stdout=subprocess.DEVNULL)
+
+        def run(nsteps, nproc):
+            case = cases.compression_fast(dx=dx, nsteps=nsteps, perturb_amp=PERTURB_AMP)
+            t0 = time.time()
+            out = ot.run_port(case)
+            return time.time() - t0, int(out["solid_part_count"][0])
+    t_a, n = run(max(warmup, 1), nproc)
+    t_b, n = run(max(warmup, 1) + steps, nproc)
+    dt = max(t_b - t_a, 1e-9)
+    return {"value": n * steps / dt, "unit": UNIT, "cores": nproc, "kind": kind, "seconds": dt, "steps": steps, "particles": n,
+            "sample": "%d-particle cylinder of the same lattice (dx=%.4g), %d Fraser steps after %d warm-up steps, Nproc=%d of %d host cores"
+                      % (n, dx, steps, max(warmup, 1), nproc, cores)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = 4.0e6          # particle-steps over both runs: a few minutes of host time at ~1e5 p-steps/s
+    n_sample = int(min(100000, max(20000, budget / (args.steps + 2 * max(args.warmup, 1)))))
+    r = reference_throughput(n_sample, args.steps, args.warmup, log=lambda m: print(m, file=sys.stderr, flush=True))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args.particles, {"reference_sample_particles": r["particles"]}),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; weldform_b200 has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from weldform_b200 import build as wfbuild, harness, api
+    from tests import cases
+    wfbuild.build()
+
+    log = (lambda m: print("[bench r%d] %s" % (rank, m), file=sys.stderr, flush=True))
+    # ---- setup (untimed): lattice, upload, solver init, spin-up to the yielding state
+    n_target = args.particles
+    dx = dx_for(n_target)
+    t0 = time.time()
+    case = cases.compression_fast(dx=dx, nsteps=1, perturb_amp=PERTURB_AMP)
+    ctx, info = harness.context_from_case(case, device=local)
+    n_sph = ctx.n_sph
+    ctx.solver_init(float(case["dt"]))
+    log("setup: %d particles, dx=%.5g, dt=%.3g, %.1f s" % (n_sph, dx, case["dt"], time.time() - t0))
+    spin = 0
+    t0 = time.time()
+    while spin < args.max_spinup:
+        ctx.run(10); spin += 10
+        s = ctx.reduce()
+        if s.is_yielding and spin >= 20:
+            break
+    log("spin-up: %d steps, %.1f s, max pl_strain %.3g, yielding=%d, rebuilds=%d" % (spin, time.time() - t0, s.max_pl_strain, s.is_yielding, s.nb_rebuilds))
+    nb_avg = float(ctx.download("Nb")[:n_sph].mean())
+
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region
+    ctx.run(args.warmup)
+    ctx.sync()
+    ctx.prof_enable(True)
+    l0 = ctx.launch_count()
+    clocks = ClockSampler(local); clocks.start()
+    barrier()
+    ev0.record(ext)
+    ctx.run(args.steps)
+    ev1.record(ext)
+    ev1.synchronize()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    launches = ctx.launch_count() - l0
+    prof = ctx.prof_get()
+    ctx.prof_enable(False)
+    s_after = ctx.reduce()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_sph * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: phase API + host GeneralAfter callback bridge with pinned host buffers
+    ids = np.asarray(case["ID"])
+    tagged = np.nonzero(ids != 1)[0].astype(np.int32)
+    nt = len(tagged)
+    is3 = ids[tagged] == 3
+    v_host = torch.empty((nt, 3), dtype=torch.float64).pin_memory().numpy()
+    a_host = torch.empty((nt, 3), dtype=torch.float64).pin_memory().numpy()
+    bc = np.asarray(case["bc"]).reshape(-1, 8)
+    vtop, tau = bc[0, 1:4].copy(), float(bc[0, 4])
+
+    def general_after(t_now):
+        # examples/Compression_thermal.cpp:30-66: ID 3 rows pushed with a ramped velocity, ID 2 rows held, a = 0 for both
+        ctx.download("v", tagged, out=v_host); ctx.download("a", tagged, out=a_host)
+        f = min(t_now / tau, 1.0) if tau > 0 else 1.0
+        a_host[:] = 0.0
+        v_host[is3] = vtop * f
+        v_host[~is3] = 0.0
+        ctx.upload("v", v_host, tagged); ctx.upload("a", a_host, tagged)
+
+    def e2e_step():
+        sc = ctx.reduce()                       # scalars the solver loop reads each step (max pl_strain, max_disp): D2H
+        ctx.phase("fraser_stage_a")
+        general_after(sc.time)
+        ctx.phase("fraser_stage_b1"); ctx.phase("fraser_stage_b2")
+        general_after(sc.time)
+        ctx.phase("fraser_stage_c")
+
+    for _ in range(max(args.warmup, 1)):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        e2e_step()
+    sc = ctx.reduce()
+    e1.record(ext)
+    e1.synchronize()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    scal_bytes = 200
+    h2d = 2 * (2 * nt * 24 + 2 * nt * 4)            # v and a up, plus the index list with each call
+    d2h = 2 * (2 * nt * 24) + scal_bytes
+    e2e = {"value": n_sph * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": ms_e2e / args.steps, "path": "wf_fraser_stage_a/b1/b2/c + wf_download_subset/wf_upload_subset (host GeneralAfter on %d tagged particles, pinned buffers) + wf_reduce" % nt}
+
+    # ---- roofline of the dominant kernel, from the CUDA-event pairs recorded on the ctx stream inside the timed region
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak_hbm = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_hbm = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    alg = algorithmic_bytes(nb_avg)
+    total_prof = sum(v[0] for v in prof.values()) or 1.0
+    kernels = {}
+    for name, (kms, kn) in prof.items():
+        if kn == 0:
+            continue
+        ent = {"ms_per_launch": kms / kn, "launches": int(kn), "share_of_step": kms / total_prof}
+        if name in alg and alg[name] > 0:
+            ent["alg_bytes_per_particle"] = alg[name]
+            ent["hbm_gbs"] = alg[name] * n_sph / (kms / kn * 1e-3) / 1e9
+            ent["hbm_frac"] = ent["hbm_gbs"] / peak_hbm
+        if name in FLOPS_PER_PAIR:
+            ent["fp64_tflops_est"] = FLOPS_PER_PAIR[name] * nb_avg * n_sph / (kms / kn * 1e-3) / 1e12
+        kernels[name] = ent
+    pair_names = [k for k in ("accel", "rate_stress", "density", "thermal", "energy") if k in kernels]
+    dom = max(pair_names, key=lambda k: kernels[k]["share_of_step"]) if pair_names else None
+    roofline = None
+    if dom:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp)).get(dom)
+            if tj and abs(tj.get("particles", 0) - n_sph) <= 0.01 * n_sph:
+                traffic = tj["dram_bytes_per_launch"]
+        k = kernels[dom]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s", "frac": k["hbm_frac"], "traffic": traffic,
+                    "peak_source": peak_src, "alg_bytes_per_launch": k["alg_bytes_per_particle"] * n_sph, "ms_per_launch": k["ms_per_launch"],
+                    "share_of_step": k["share_of_step"],
+                    "note": "fp64 gather pair loop: the FP64 pipe, not HBM, is the binding roof (see fp64); HBM fraction is on unique algorithmic bytes"}
+        try:
+            fp64_peak = ctx.measure_fp64_peak()
+            roofline["fp64"] = {"achieved_tflops_est": k.get("fp64_tflops_est"), "peak_tflops_measured_dfma": fp64_peak,
+                                "frac": (k.get("fp64_tflops_est") or 0.0) / fp64_peak if fp64_peak else None,
+                                "flops_per_pair_visit": FLOPS_PER_PAIR.get(dom)}
+        except Exception as exc:       # noqa: BLE001
+            roofline["fp64"] = {"error": str(exc)}
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference solver on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = reference_throughput(args.cpu_sample, args.cpu_steps, 2, log=log)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as exc:       # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % exc}
+
+    ctx.close()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(n_sph, {"neighbours_avg": nb_avg, "spinup_steps": spin, "nb_rebuilds_in_timed_region": int(prof.get("nb_list", (0, 0))[1]),
+                                                  "max_pl_strain": s_after.max_pl_strain}),
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=float, default=1.0e7)
+    ap.add_argument("--max-spinup", type=int, default=400)
+    ap.add_argument("--cpu-sample", type=int, default=50000, help="particles of the CPU-baseline sample lattice")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.particles = int(args.particles)
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -175,6 +175,8 @@ int wf_prof_enable(wf_ctx *ctx, int on);
 int wf_prof_get(wf_ctx *ctx, double *ms, int64_t *launches, int cap, int *n_used);
 const char *wf_prof_name(int k);
 int wf_launch_count(wf_ctx *ctx, int64_t *launches);
+void *wf_get_stream(wf_ctx *ctx);                   /* the ctx-owned cudaStream_t every kernel is launched on (for external event timing) */
+int wf_measure_fp64_peak(wf_ctx *ctx, double *tflops);   /* DFMA microbenchmark: the FP64-pipe roofline denominator (2 flop per DFMA) */
 
 #ifdef __cplusplus
 }

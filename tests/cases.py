@@ -124,3 +124,79 @@ FIELDS_F64 = ["x", "v", "a", "Displacement", "Density", "dDensity", "Pressure", 
               "Strain", "Strain_pl", "TIR", "pl_strain", "Sigmay", "eff_strain_rate", "T", "dTdt", "q_plheat", "q_conv",
               "contforce", "delta_cont", "normal", "dint_energy_dt", "dkin_energy_dt"]
 SCALARS = ["Time", "int_energy_sum", "plastic_work", "contact_force_sum", "contact_reaction_sum", "ext_forces_work", "max_disp"]
+
+
+def compression_fast(dx, nsteps=1, **kw):
+    """compression() for large lattices: sizes the per-particle arrays from a vectorised point count instead of the
+    Python point loop (positions always come from the library's own generator; only the z of each row is needed here)."""
+    rho, K, G = 2700.0, 6.7549e10, 2.5902e10
+    R, L = 0.15, 0.56
+    r = dx / 2.0
+    V = (0.0, 0.0, -L / 10.0)
+    Lz = L + 2.0 * L / 10.0
+
+    def half(xinc):
+        yp, xp, c = r, r + (xinc - 1) * 2.0 * r, 1
+        while np.sqrt(yp * yp + xp * xp) <= R - r:
+            yp += 2.0 * r
+            c += 1
+        return c - 1
+    npxy = half(1)
+    per_layer = 0
+    xs, ys = [], []
+    yp = V[1] - r - 2.0 * r * (npxy - 1)
+    yinc, sign = npxy, -1
+    for _ in range(2 * npxy):
+        nx = half(yinc)
+        x0 = V[0] - r - 2.0 * r * (nx - 1)
+        row = np.empty(2 * nx)
+        xp = x0
+        for i in range(2 * nx):
+            row[i] = xp
+            xp += 2.0 * r
+        xs.append(row); ys.append(np.full(2 * nx, yp))
+        per_layer += 2 * nx
+        yp += 2.0 * r
+        yinc += sign
+        if yinc < 1:
+            yinc, sign = 1, 1
+    zs = []
+    zp = V[2] + r
+    while zp <= V[2] + Lz - r:
+        zs.append(zp)
+        zp += 2.0 * r
+    xl, yl = np.concatenate(xs), np.concatenate(ys)
+    pts = np.empty((len(zs) * per_layer, 3))
+    pts[:, 0] = np.tile(xl, len(zs)); pts[:, 1] = np.tile(yl, len(zs)); pts[:, 2] = np.repeat(np.array(zs), per_layer)
+    return _compression_from_points(pts, dx, nsteps, **kw)
+
+
+def _compression_from_points(pts, dx, nsteps, thermal=True, pl_heating=True, alpha=1.0, beta=0.0, ti=0.3, gradient_type=0,
+                             vmax=10.0, tau=0.005, cfl=0.2, fy=300.0e6, ts_nb_inc=5, perturb_amp=0.0, seed=1):
+    rho, K, G = 2700.0, 6.7549e10, 2.5902e10
+    R, L = 0.15, 0.56
+    h = 1.2 * dx
+    Cs = np.sqrt(K / rho)
+    V = (0.0, 0.0, -L / 10.0)
+    n = len(pts)
+    z = pts[:, 2]
+    ID = np.full(n, 1, np.int32)
+    ID[z < 0] = 2
+    ID[z > L] = 3
+    ones = np.ones(n)
+    case = dict(
+        gen_kind=1.0, gen_args=np.array([1, V[0], V[1], V[2], R, L + 2.0 * L / 10.0, dx / 2.0, rho, h, 0, 0], float),
+        Dimension=3.0, KernelType=0.0, GradientType=float(gradient_type), DomMax=np.array([L, -1e11, -1e11]), DomMin=np.array([-L, 1e11, 1e11]),
+        ID=ID, G=G * ones, Cs=Cs * ones, PresEq=np.zeros(n, np.int32), Material=np.full(n, 2, np.int32), Fail=np.ones(n, np.int32),
+        Sigmay=fy * ones, Alpha=alpha * ones, Beta=beta * ones, TI=ti * ones, TIInitDist=dx * ones,
+        k_T=150.0 * ones, cp_T=960.0 * ones, th_exp=0.0 * ones,
+        thermal_solver=float(thermal), pl_heating=float(pl_heating), pl_work_heat_frac=0.9, ts_nb_inc=float(ts_nb_inc),
+        dt=cfl * h / Cs, nsteps=float(nsteps), mode=0.0,
+        bc=np.array([3, 0, 0, -vmax, tau, 1, 0, 0, 2, 0, 0, 0, 0, 1, 0, 0], float),
+        T=20.0 + 15.0 * np.sin(7.0 * pts[:, 0]) * np.cos(5.0 * z),
+    )
+    if perturb_amp:      # same smooth field as perturbed()
+        x, y, amp = pts[:, 0], pts[:, 1], perturb_amp
+        case["v"] = np.stack([amp * np.sin(9.0 * y + seed) * np.cos(4.0 * z), amp * np.cos(8.0 * x - seed) * np.sin(3.0 * z),
+                              -amp * z * (1.0 + 0.3 * np.sin(11.0 * x * y))], axis=1).reshape(-1)
+    return case

@@ -1,0 +1,51 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference solver (oracle/_ref/wf_ref, built from /root/reference by
+oracle/Makefile). Run in the build container only:   python tests/golden/make_golden.py
+
+Each fixture holds the case records (prefix "case/") and the reference's state dump (prefix "ref/") of one small run
+with Nproc = 1. The reference ships no golden vectors of its own; these are the pin for the
+oracle port (tests/test_oracle.py) and, through it and directly, for the CUDA path (tests/test_parity_gpu.py).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from tests import cases, oracle_tools as ot  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def golden_cases():
+    """name -> case. Small lattices (hundreds of particles) so that the fixtures stay a few hundred kB each."""
+    out = {}
+    c = cases.perturbed(cases.compression(dx=0.04, nsteps=1)); c["mode"] = 1.0
+    out["nb_only"] = c                                                                       # neighbour build: pairs in discovery order
+    out["comp_1step"] = cases.perturbed(cases.compression(dx=0.04, nsteps=1), amp=60.0)     # one full Fraser step, every pair term active
+    out["comp_yield_40"] = cases.perturbed(cases.compression(dx=0.04, nsteps=40), amp=60.0)  # yields -> rebuild cadence, plastic heat, conduction
+    out["comp_noTI_g2_8"] = cases.perturbed(cases.compression(dx=0.04, nsteps=8, ti=0.0, gradient_type=2), amp=20.0)
+    out["comp_g1_beta_8"] = cases.perturbed(cases.compression(dx=0.04, nsteps=8, gradient_type=1, beta=1.0), amp=20.0)
+    out["comp_hollomon_30"] = cases.perturbed(cases.compression(dx=0.04, nsteps=30, model=cases.HOLLOMON), amp=60.0)
+    out["comp_jc_30"] = cases.perturbed(cases.compression(dx=0.04, nsteps=30, model=cases.JOHNSON_COOK), amp=60.0)
+    out["contact_1step"] = cases.contact_compression(dx=0.0032, nsteps=1, vmax=5.0, tau=1e-5, dens=8, cfl=0.3)
+    out["contact_100"] = cases.contact_compression(dx=0.0032, nsteps=100, vmax=5.0, tau=1e-5, dens=8, cfl=0.3)   # friction stick+slide, yields
+    return out
+
+
+def main():
+    if not ot.have_ref():
+        raise SystemExit("oracle/_ref/wf_ref missing: run `make -C oracle ref` in the container that has /root/reference")
+    for name, case in golden_cases().items():
+        ref = ot.run_ref(case, nproc=1)
+        ref.pop("solve_seconds", None)
+        rec = {"case/" + k: np.asarray(v) for k, v in case.items()}
+        rec.update({"ref/" + k: v for k, v in ref.items()})
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print("%-18s N=%d pairs=%d maxpl=%.3g  %.0f kB" % (name, int(ref["n_particles"][0]), ref["pairs"].size // 2, ref["pl_strain"].max(),
+                                                        os.path.getsize(path) / 1e3))
+
+
+if __name__ == "__main__":
+    main()

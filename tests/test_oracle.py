@@ -1,0 +1,63 @@
+"""CPU tests of the oracle (no GPU): the restatement oracle/wf_oracle.cpp must reproduce the reference solver's own
+output BIT FOR BIT -- on the committed golden fixtures (generated from oracle/_ref/wf_ref, i.e. /root/reference compiled
+unmodified) everywhere, and against a live run of oracle/_ref/wf_ref where that binary exists (the build container)."""
+import numpy as np
+import pytest
+
+from tests import cases, golden_tools, oracle_tools as ot
+
+SKIP_KEYS = {"solve_seconds"}
+
+
+def _assert_same(port, ref, what):
+    bad = []
+    for k, v in ref.items():
+        if k in SKIP_KEYS:
+            continue
+        assert k in port, "%s: port dump lacks %s" % (what, k)
+        if not np.array_equal(np.asarray(port[k]).reshape(-1), np.asarray(v).reshape(-1)):
+            bad.append(k)
+    assert not bad, "%s: oracle port differs from the reference in %s" % (what, bad)
+
+
+@pytest.mark.parametrize("name", golden_tools.names())
+def test_port_matches_golden_bit_exact(oracle_port, name):
+    case, ref = golden_tools.load(name)
+    port = ot.run_port(case)
+    _assert_same(port, ref, name)
+
+
+def test_golden_set_is_complete():
+    names = golden_tools.names()
+    for need in ("nb_only", "comp_1step", "comp_yield_40", "comp_hollomon_30", "comp_jc_30", "contact_1step", "contact_100"):
+        assert need in names
+
+
+def test_golden_fixtures_are_nontrivial():
+    _, ref = golden_tools.load("comp_yield_40")
+    assert ref["pl_strain"].max() > 1e-3                      # the body yields: radial return + rebuild cadence exercised
+    assert np.ptp(ref["T"][: int(ref["solid_part_count"][0])]) > 1.0 and np.abs(ref["dTdt"]).max() > 0.0
+    assert np.abs(ref["TIR"]).max() > 0.0                     # tensile-instability tensor populated
+    _, ref = golden_tools.load("contact_100")
+    assert (ref["delta_cont"] > 0).sum() > 10 and ref["contact_force_sum"][0] > 0.0 and ref["cont_pairs"].size > 0
+    _, ref = golden_tools.load("nb_only")
+    nb = ref["Nb"]
+    assert nb.max() == 56                                      # interior particle of the cubic lattice, h = 1.2 dx
+
+
+@pytest.mark.skipif(not ot.have_ref(), reason="oracle/_ref/wf_ref not built here (needs /root/reference)")
+@pytest.mark.parametrize("maker", [
+    lambda: cases.perturbed(cases.compression(dx=0.03, nsteps=25), amp=60.0),
+    lambda: cases.contact_compression(dx=0.0024, nsteps=12, vmax=5.0, tau=1e-5, dens=10),
+])
+def test_port_matches_live_reference(oracle_port, maker):
+    case = maker()
+    _assert_same(ot.run_port(case), ot.run_ref(case, nproc=1), "live")
+
+
+@pytest.mark.skipif(not ot.have_ref(), reason="oracle/_ref/wf_ref not built here (needs /root/reference)")
+def test_reference_pair_set_is_thread_count_independent():
+    """pair ORDER depends on Nproc, the sorted pair SET does not."""
+    c = cases.perturbed(cases.compression(dx=0.03, nsteps=1)); c["mode"] = 1.0
+    a, b = ot.run_ref(c, nproc=1), ot.run_ref(c, nproc=4)
+    assert np.array_equal(a["pairs"], b["pairs"])

@@ -96,6 +96,7 @@ def load_library():
         "wf_gen_cylinder": ([_PD, C.c_double, C.c_double, C.c_double, _PD, C.c_int64], C.c_int64),
         "wf_gen_box": ([_PD, C.c_double, C.c_double, C.c_double, C.c_double, _PD, C.c_int64, _PD], C.c_int64),
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
+        "wf_get_stream": ([vp], vp), "wf_measure_fp64_peak": ([vp, _PD], C.c_int),
         "wf_prof_name": ([C.c_int], C.c_char_p), "wf_launch_count": ([vp, C.POINTER(C.c_int64)], C.c_int),
     }
     for name in ["wf_step_begin", "wf_density", "wf_rate_stress", "wf_accel", "wf_contact", "wf_apply_bcs", "wf_integrate_pos", "wf_integrate_vel",
@@ -218,10 +219,13 @@ class Context:
     def n_sph(self):
         return self.L.wf_num_sph(self.h)
 
-    def download(self, name, idx=None):
+    def download(self, name, idx=None, out=None):
         fid, nc, dt = FIELDS[name]
         cnt = self.n if idx is None else len(idx)
-        out = np.empty((cnt, nc) if nc > 1 else (cnt,), dt)
+        if out is None:
+            out = np.empty((cnt, nc) if nc > 1 else (cnt,), dt)
+        elif out.dtype != dt or out.size != cnt * nc or not out.flags.c_contiguous:
+            raise WeldformError("download(%s): out buffer has the wrong dtype/size/layout" % name)
         if idx is None:
             self._ck(self.L.wf_download(self.h, fid, out.ctypes.data_as(C.c_void_p)), "wf_download(%s)" % name)
         else:
@@ -285,6 +289,15 @@ class Context:
         ms = (C.c_double * 64)(); nl = (C.c_int64 * 64)(); used = C.c_int()
         self._ck(self.L.wf_prof_get(self.h, ms, nl, 64, C.byref(used)), "wf_prof_get")
         return {self.L.wf_prof_name(k).decode(): (ms[k], nl[k]) for k in range(used.value)}
+
+    def stream(self):
+        """cudaStream_t (as int) every kernel of this context is launched on."""
+        return int(self.L.wf_get_stream(self.h) or 0)
+
+    def measure_fp64_peak(self):
+        t = C.c_double()
+        self._ck(self.L.wf_measure_fp64_peak(self.h, C.byref(t)), "wf_measure_fp64_peak")
+        return t.value
 
     def launch_count(self):
         n = C.c_int64()

@@ -46,7 +46,7 @@ def build(force=False, verbose=False, extra_flags=()):
             failed = True
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 

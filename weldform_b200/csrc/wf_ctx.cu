@@ -20,6 +20,15 @@ int fail(wf_ctx *c, int code, const char *fmt, ...)
     return code;
 }
 
+void prof_resolve(wf_ctx *c)
+{
+    for (auto &r : c->prof_pending) {
+        cudaEventSynchronize(r.b); float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+        c->prof_ms[r.k] += ms; c->prof_n[r.k] += 1; c->prof_free.push_back(std::make_pair(r.a, r.b));
+    }
+    c->prof_pending.clear();
+}
+
 int ensure_stage(wf_ctx *c, size_t bytes)
 {
     if (bytes <= c->stage_bytes) return 0;
@@ -78,12 +87,48 @@ extern "C" void wf_destroy(wf_ctx *c)
     cudaFree(c->dm.node); cudaFree(c->dm.node_v); cudaFree(c->dm.en); cudaFree(c->dm.nfar); cudaFree(c->dm.emesh);
     cudaFree(c->dm.enormal); cudaFree(c->dm.ev); cudaFree(c->dm.pplane); cudaFree(c->dm.motion);
     cudaFree(c->stage); if (c->h_stage) cudaFreeHost(c->h_stage); if (c->h_sc) cudaFreeHost(c->h_sc);
+    prof_resolve(c); for (auto &e : c->prof_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
 }
 
 extern "C" const char *wf_last_error(const wf_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+extern "C" void *wf_get_stream(wf_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+// FP64 pipe peak: 8 independent DFMA chains per thread, persistent grid; flops = 2 per DFMA.
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double m = 1.0000001, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b);
+        a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) out[0] = r;
+}
+extern "C" int wf_measure_fp64_peak(wf_ctx *c, double *tflops)
+{
+    if (!c || !tflops) return WF_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaDeviceProp prop; WF_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    WF_CHECK(ensure_stage(c, 256));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(c->ev0, c->stream);
+        k_fp64_peak<<<blocks, 256, 0, c->stream>>>((double *)c->stage, iters, 1.0 + rep);
+        cudaEventRecord(c->ev1, c->stream);
+        WF_CUDA(c, cudaEventSynchronize(c->ev1));
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        const double tf = 2.0 * 8.0 * (double)iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    *tflops = best;
+    return 0;
+}
 
 extern "C" int wf_sync(wf_ctx *c)
 {
@@ -530,12 +575,14 @@ extern "C" const char *wf_prof_name(int k) { return (k >= 0 && k < PK_COUNT) ? k
 extern "C" int wf_prof_enable(wf_ctx *c, int on)
 {
     if (!c) return WF_ERR_ARG;
+    prof_resolve(c);
     c->prof = on != 0; std::memset(c->prof_ms, 0, sizeof(c->prof_ms)); std::memset(c->prof_n, 0, sizeof(c->prof_n));
     return 0;
 }
 extern "C" int wf_prof_get(wf_ctx *c, double *ms, int64_t *launches, int cap, int *n_used)
 {
     if (!c) return WF_ERR_ARG;
+    prof_resolve(c);
     int k = 0; for (; k < PK_COUNT && k < cap; ++k) { if (ms) ms[k] = c->prof_ms[k]; if (launches) launches[k] = c->prof_n[k]; }
     if (n_used) *n_used = k;
     return 0;

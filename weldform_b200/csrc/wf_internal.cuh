@@ -51,7 +51,7 @@ struct DevScalars {
     double time, dt;
     double kin_energy_sum, int_energy_sum, plastic_work, contact_force_sum, contact_reaction_sum, ext_forces_work,
            contact_friction_work, accum_cont_heat_cond;
-    double max_pl_strain, max_disp2[3], max_T, min_T;
+    double max_pl_strain, max_disp2[3], max_disp2_prev[3], max_T, min_T;
     double mcf[4][3];
 };
 
@@ -104,12 +104,15 @@ struct wf_ctx {
     double *d_partial = nullptr; int partial_blocks = 0;
     // solver state (SolverFraser.cpp:62-68)
     double dt = 0.0, time = 0.0; int ts_i = 0; bool isfirst = true, isyielding = false, nb_cleared = true;
-    int64_t steps = 0, nb_rebuilds = 0, launches = 0;
+    int64_t steps = 0, nb_rebuilds = 0, launches = 0; bool in_step = false;
     double step_max_pl = 0.0;                    // `max` of SolverFraser.cpp:139-149 for the step in flight
     // staging
     void *stage = nullptr; size_t stage_bytes = 0; void *h_stage = nullptr; size_t h_stage_bytes = 0;
     // profiling
+    // profiling: event pairs are recorded on the ctx stream without synchronising and resolved in wf_prof_get
     bool prof = false; double prof_ms[wf::PK_COUNT]; int64_t prof_n[wf::PK_COUNT]; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct ProfRec { cudaEvent_t a, b; int k; };
+    std::vector<ProfRec> prof_pending; std::vector<std::pair<cudaEvent_t, cudaEvent_t> > prof_free;
 
     double *Fp(int f) { return F[cur] + (int64_t)f * cap; }
     int *Ip(int f) { return I[cur] + (int64_t)f * cap; }
@@ -122,12 +125,16 @@ int fail(wf_ctx *c, int code, const char *fmt, ...);
 #define WF_CHECK(expr) do { int r_ = (expr); if (r_ != 0) return r_; } while (0)
 #define WF_LAUNCH_CHECK(c) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return wf::fail((c), WF_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+void prof_resolve(wf_ctx *c);
 struct ProfScope {
-    wf_ctx *c; int k;
-    ProfScope(wf_ctx *c_, int k_) : c(c_), k(k_) { if (c->prof) cudaEventRecord(c->ev0, c->stream); }
-    ~ProfScope() {
-        if (c->prof) { cudaEventRecord(c->ev1, c->stream); cudaEventSynchronize(c->ev1); float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->prof_ms[k] += ms; c->prof_n[k] += 1; }
+    wf_ctx *c; int k; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(wf_ctx *c_, int k_) : c(c_), k(k_) {
+        if (!c->prof) return;
+        if (c->prof_free.empty()) { if (c->prof_pending.size() >= 8192) prof_resolve(c); }
+        if (c->prof_free.empty()) { cudaEventCreate(&a); cudaEventCreate(&b); } else { a = c->prof_free.back().first; b = c->prof_free.back().second; c->prof_free.pop_back(); }
+        cudaEventRecord(a, c->stream);
     }
+    ~ProfScope() { if (a) { cudaEventRecord(b, c->stream); wf_ctx::ProfRec r; r.a = a; r.b = b; r.k = k; c->prof_pending.push_back(r); } }
 };
 
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }

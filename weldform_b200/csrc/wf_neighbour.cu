@@ -354,6 +354,8 @@ static int export_common(wf_ctx *c, bool contact_pairs, int64_t *ij, int64_t cap
     if (!c || !n_pairs) return WF_ERR_ARG;
     if (!c->nbr) return fail(c, WF_ERR_ARG, "export pairs: no neighbour list built yet");
     if (contact_pairs && !c->cont) { *n_pairs = 0; return 0; }
+    // ClearNbData (Neighbour.cpp:479-497) empties SMPairs/ContPairs at the end of a cadence window; mirror that state
+    if (c->nb_cleared) { *n_pairs = 0; return 0; }
     cudaSetDevice(c->device);
     const int64_t n = c->n; cudaStream_t st = c->stream;
     int64_t *d_cnt = nullptr, *d_off = nullptr;

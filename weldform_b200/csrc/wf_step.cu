@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double *partial, int
     __syncthreads();
     if (threadIdx.x == 0) {
         sc->max_pl_strain = res[R_MAXPL];
+        // Domain::max_disp is evaluated at the START of a step (SolverFraser.cpp:151-159): keep the previous end-of-step
+        // value so that wf_reduce can report what the reference holds once the step has completed
+        if (accumulate) { sc->max_disp2_prev[0] = sc->max_disp2[0]; sc->max_disp2_prev[1] = sc->max_disp2[1]; sc->max_disp2_prev[2] = sc->max_disp2[2]; }
         sc->max_disp2[0] = res[R_MD0]; sc->max_disp2[1] = res[R_MD1]; sc->max_disp2[2] = res[R_MD2];
         sc->max_T = res[R_TMAX]; sc->min_T = res[R_TMIN];
         if (accumulate) {
@@ -368,12 +371,13 @@ extern "C" int wf_reduce(wf_ctx *c, wf_scalars *out)
 {
     WF_NEED_READY(c);
     if (!out) return WF_ERR_ARG;
-    WF_CHECK(reduce_impl(c, false));
+    // the device scalars are refreshed by every step end (and by wf_solver_init); this is a read-back only
     WF_CHECK(fetch_scalars(c));
     const DevScalars &d = *c->h_sc;
     std::memset(out, 0, sizeof(*out));
     out->time = d.time; out->max_pl_strain = d.max_pl_strain;
-    for (int k = 0; k < 3; ++k) out->max_disp[k] = std::sqrt(d.max_disp2[k]);      // SolverFraser.cpp:159
+    // Domain::max_disp as the reference holds it at this point: computed at the start of the step in flight / last completed
+    for (int k = 0; k < 3; ++k) out->max_disp[k] = std::sqrt((c->in_step || c->steps == 0) ? d.max_disp2[k] : d.max_disp2_prev[k]);      // SolverFraser.cpp:159
     out->kin_energy_sum = d.kin_energy_sum; out->int_energy_sum = d.int_energy_sum; out->plastic_work = d.plastic_work;
     out->contact_force_sum = d.contact_force_sum; out->contact_reaction_sum = d.contact_reaction_sum; out->ext_forces_work = d.ext_forces_work;
     out->contact_friction_work = d.contact_friction_work; out->accum_cont_heat_cond = d.accum_cont_heat_cond;
@@ -394,7 +398,7 @@ static int nb_policy(wf_ctx *c)
         const V3 md = v3(std::sqrt(c->h_sc->max_disp2[0]), std::sqrt(c->h_sc->max_disp2[1]), std::sqrt(c->h_sc->max_disp2[2]));
         check_every = norm(md) > 0.1 * c->hmax;
     }
-    c->step_max_pl = mx;
+    c->step_max_pl = mx; c->in_step = true;
     if (mx > MIN_PS_FOR_NBSEARCH && !c->isyielding) {          // first time yielding (:172-179)
         WF_CHECK(nb_build_impl(c));
         c->isyielding = true;
@@ -414,7 +418,7 @@ static int finish_step(wf_ctx *c)
         c->ts_i++;
         if (c->ts_i > (c->prm.ts_nb_inc - 1)) c->ts_i = 0;
     }
-    c->isfirst = false;
+    c->isfirst = false; c->in_step = false;
     c->steps++;
     return 0;
 }

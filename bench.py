@@ -63,17 +63,20 @@ def workload_config(n_sph, extra=None):
 def algorithmic_bytes(nb_avg, ti=True, thermal=True):
     lst = 4.0 * nb_avg + 8.0
     b = {
-        "density": 96.0 + (64.0 + 48.0 if ti else 0.0) + lst + 8.0 + (8.0 + 32.0 + 32.0),        # Q0,Q1,Q2 (+Sigma in, TIR out) + list + dDensity; rho update pass
-        "rate_stress": 96.0 + lst + 20 * 8.0 + (32.0 + 16.0 + 8.0 + 37 * 8.0),
-        "accel": 192.0 + lst + 24.0,
-        "thermal": (96.0 + lst + 24.0 + 48.0 + 8.0 + (64.0 + 56.0 + 16.0)) if thermal else 0.0,  # pair pass + per-particle pre pass
+        # per-particle prologue when the previous step's k_post prepared the density rate (the usual case)
+        "density": 8.0 + 32.0 + 48.0 + 8.0 + 32.0 + 32.0 + 32.0 + 32.0,
+        # Q0,Q1,Q2 + list; ShearStress, Sigmay, pl_strain, Strain, Strain_pl in; everything the constitutive update writes out
+        "rate_stress": 96.0 + lst + 20 * 8.0 + (32.0 + 32.0 + 8.0 + 44 * 8.0),
+        "accel": 192.0 + 4.0 + lst + 24.0,
+        # k_thermal_pre + k_post (conduction + kinetic/internal energy + next density rate + next TIR)
+        "post": (8.0 + 48.0 + 48.0 + 8.0 + 64.0 + 8.0) + (96.0 + lst + 24.0 + 48.0 + 8.0 + 96.0 + 16.0 + 8.0 + 48.0 + 48.0),
         "energy": 96.0 + lst + 96.0 + 16.0,
         "move": 64.0 + 24.0 + 24.0 + 4.0 + 64.0 + 24.0 + 24.0,
     }
     return b
 
 
-FLOPS_PER_PAIR = {"density": 45.0, "rate_stress": 80.0, "accel": 250.0, "thermal": 45.0, "energy": 40.0}
+FLOPS_PER_PAIR = {"rate_stress": 80.0, "accel": 250.0, "post": 45.0 + 40.0 + 45.0, "energy": 40.0}   # thermal + energy + density share k_post
 
 
 class ClockSampler:
@@ -214,6 +217,7 @@ def run_ours(args):
     dx = dx_for(n_target)
     t0 = time.time()
     case = cases.compression_fast(dx=dx, nsteps=1, perturb_amp=PERTURB_AMP)
+    case["tuning"] = float(args.tuning)
     ctx, info = harness.context_from_case(case, device=local)
     n_sph = ctx.n_sph
     ctx.solver_init(float(case["dt"]))
@@ -329,7 +333,7 @@ def run_ours(args):
         if name in FLOPS_PER_PAIR:
             ent["fp64_tflops_est"] = FLOPS_PER_PAIR[name] * nb_avg * n_sph / (kms / kn * 1e-3) / 1e12
         kernels[name] = ent
-    pair_names = [k for k in ("accel", "rate_stress", "density", "thermal", "energy") if k in kernels]
+    pair_names = [k for k in ("accel", "rate_stress", "post", "energy") if k in kernels]
     dom = max(pair_names, key=lambda k: kernels[k]["share_of_step"]) if pair_names else None
     roofline = None
     if dom:
@@ -384,6 +388,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=50000, help="particles of the CPU-baseline sample lattice")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tuning", type=int, default=0, help="wf_params::tuning bit mask (kernel A/B switches)")
     args = ap.parse_args()
     args.particles = int(args.particles)
     if args.warmup < 3:

@@ -50,6 +50,7 @@ typedef struct wf_params {
     int    cont_heat_fric, cont_heat_cond;
     double contact_hc;
     int    nb_order_reference; /* 1: neighbour lists in the reference's Nproc=1 summation order (default) */
+    int    tuning;             /* bit 0: disable the software-pipelined gathers of the pair kernels (A/B measurements); default 0 */
 } wf_params;
 
 /* Material_ subclasses (Source/Material.h:96-224). model: 0 bilinear (no object), 1 Hollomon, 2 Johnson-Cook. */

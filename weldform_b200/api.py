@@ -22,7 +22,7 @@ class wf_params(C.Structure):
                 ("contact", C.c_int), ("friction_sta", C.c_double), ("friction_dyn", C.c_double),
                 ("pfac", C.c_double), ("dfac", C.c_double), ("contact_force_factor", C.c_double),
                 ("cont_heat_fric", C.c_int), ("cont_heat_cond", C.c_int), ("contact_hc", C.c_double),
-                ("nb_order_reference", C.c_int)]
+                ("nb_order_reference", C.c_int), ("tuning", C.c_int)]
 
 
 class wf_material(C.Structure):

@@ -234,7 +234,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     WF_CHECK(alloc_particles(c, n));
 
     // ---- property classes -------------------------------------------------------------------------------------
-    std::vector<double> cls_of(n);
+    std::vector<int> cls_of(n);
     std::map<ClassKey, int> table; ClassKey last; int last_id = -1;
     auto gd = [&](const double *a, int64_t i, double dflt) { return a ? a[i] : dflt; };
     auto gi = [&](const int32_t *a, int64_t i, int dflt) { return a ? a[i] : dflt; };
@@ -268,15 +268,16 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
             } else id = it->second;
             last = k; last_id = id;
         }
-        cls_of[i] = (double)id;
+        cls_of[i] = id;
     }
     int mesh_class = -1;
     if (nmeshp > 0) {     // rigid-mesh particles: Particle ctor defaults with Density = 0 (Contact.cpp:15-27)
         ClassProps cp; std::memset(&cp, 0, sizeof(cp)); cp.TIn = 4.0; cp.mat_id = -1; cp.IsMesh = 1;
         mesh_class = (int)c->h_classes.size(); c->h_classes.push_back(cp);
-        for (int64_t i = nsph; i < n; ++i) cls_of[i] = (double)mesh_class;
+        for (int64_t i = nsph; i < n; ++i) cls_of[i] = mesh_class;
     }
     c->n_classes = (int)c->h_classes.size();
+    c->single_class = (c->n_classes - (nmeshp > 0 ? 1 : 0)) == 1;
     WF_CUDA(c, cudaMalloc(&c->d_classes, c->n_classes * sizeof(ClassProps)));
     WF_CUDA(c, cudaMemcpy(c->d_classes, c->h_classes.data(), c->n_classes * sizeof(ClassProps), cudaMemcpyHostToDevice));
 
@@ -339,10 +340,10 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         else { int64_t k = i - nsph; q[i] = make_double4(mx[3 * k], mx[3 * k + 1], mx[3 * k + 2], mh[k]); }
         if (i < nsph && p->h[i] != p->h[0]) uni_h = false;
     }
-    c->uniform_h = uni_h && nmeshp == 0;
+    c->uniform_h = uni_h;                        // over the SPH particles; rigid-mesh particles never enter an SM pair
     WF_CUDA(c, cudaMemcpy(c->Q0[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
     for (int64_t i = 0; i < n; ++i) {
-        if (i < nsph) q[i] = make_double4(p->v ? p->v[3 * i] : 0.0, p->v ? p->v[3 * i + 1] : 0.0, p->v ? p->v[3 * i + 2] : 0.0, p->density[i]);
+        if (i < nsph) q[i] = make_double4(p->v ? p->v[3 * i] : 0.0, p->v ? p->v[3 * i + 1] : 0.0, p->v ? p->v[3 * i + 2] : 0.0, p->mass[i] / p->density[i]);
         else q[i] = make_double4(0.0, 0.0, 0.0, 0.0);
     }
     WF_CUDA(c, cudaMemcpy(c->Q1[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
@@ -350,7 +351,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     for (int64_t i = 0; i < n; ++i) {
         double m = i < nsph ? p->mass[i] : 0.0;
         tot += m;                                   // serial, creation order (Domain.cpp:1421-1423)
-        q[i] = make_double4(m, (i < nsph && p->T) ? p->T[i] : 0.0, cls_of[i], 0.0);
+        q[i] = make_double4(m, i < nsph ? p->density[i] : 0.0, (i < nsph && p->T) ? p->T[i] : 0.0, 0.0);
     }
     c->totmass_mean = tot / (double)n;
     WF_CUDA(c, cudaMemcpy(c->Q2[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
@@ -371,6 +372,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_IDORIG * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         for (int64_t i = 0; i < n; ++i) iv[i] = i < nsph ? gi(p->not_write_surf_id, i, 0) : 0;
         WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_NOWRITE * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_CLS * n, cls_of.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         for (int64_t i = 0; i < n; ++i) iv[i] = (int)i;
         WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_ORIG * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         WF_CUDA(c, cudaMemcpy(c->slot_of, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
@@ -434,22 +436,22 @@ __device__ inline void field_get(const FieldView &v, int f, int64_t s, double ou
     case WF_F_DISPLACEMENT: out[0] = own(F_DX); out[1] = own(F_DY); out[2] = own(F_DZ); break;
     case WF_F_NORMAL: out[0] = own(F_NX); out[1] = own(F_NY); out[2] = own(F_NZ); break;
     case WF_F_CONTFORCE: out[0] = own(F_CFX); out[1] = own(F_CFY); out[2] = own(F_CFZ); break;
-    case WF_F_DENSITY: out[0] = v.Q1[s].w; break;
+    case WF_F_DENSITY: out[0] = v.Q2[s].y; break;
     case WF_F_DDENSITY: out[0] = own(F_DDENS); break;
-    case WF_F_PRESSURE: out[0] = v.Q2[s].w; break;
+    case WF_F_PRESSURE: out[0] = own(F_PRES); break;
     case WF_F_MASS: out[0] = v.Q2[s].x; break;
     case WF_F_H: out[0] = v.Q0[s].w; break;
     case WF_F_PL_STRAIN: out[0] = own(F_PLS); break;
     case WF_F_SIGMAY: out[0] = own(F_SIGY); break;
     case WF_F_EFF_STRAIN_RATE: out[0] = own(F_EFFSR); break;
-    case WF_F_T: out[0] = v.Q2[s].y; break;
+    case WF_F_T: out[0] = v.Q2[s].z; break;
     case WF_F_DTDT: out[0] = own(F_DTDT); break;
     case WF_F_Q_PLHEAT: out[0] = own(F_QPL); break;
     case WF_F_Q_CONV: out[0] = own(F_QCONV); break;
     case WF_F_DELTA_CONT: out[0] = own(F_DCONT); break;
     case WF_F_DKIN_ENERGY_DT: out[0] = own(F_DKIN); break;
     case WF_F_DINT_ENERGY_DT: out[0] = own(F_DINT); break;
-    case WF_F_SIGMA: { double4 a = v.S0[s], b = v.S1[s]; out[0] = a.x; out[1] = a.w; out[2] = b.y; out[3] = a.w; out[4] = a.y; out[5] = b.x; out[6] = b.y; out[7] = b.x; out[8] = a.z; } break;
+    case WF_F_SIGMA: sym(F_SG); break;
     case WF_F_TIR: { double4 b = v.S1[s], t = v.S2[s]; out[0] = b.z; out[1] = t.y; out[2] = t.w; out[3] = t.y; out[4] = b.w; out[5] = t.z; out[6] = t.w; out[7] = t.z; out[8] = t.x; } break;
     case WF_F_SHEARSTRESS: sym(F_SH); break;
     case WF_F_STRAINRATE: sym(F_SR); break;
@@ -526,8 +528,8 @@ __global__ void k_upload(double4 *Q0, double4 *Q1, double4 *Q2, double *F, int *
     case WF_F_X: { double4 q = Q0[s]; q.x = d[3 * t]; q.y = d[3 * t + 1]; q.z = d[3 * t + 2]; Q0[s] = q; } break;
     case WF_F_V: { double4 q = Q1[s]; q.x = d[3 * t]; q.y = d[3 * t + 1]; q.z = d[3 * t + 2]; Q1[s] = q; } break;
     case WF_F_A: F[(int64_t)F_AX * cap + s] = d[3 * t]; F[(int64_t)F_AY * cap + s] = d[3 * t + 1]; F[(int64_t)F_AZ * cap + s] = d[3 * t + 2]; break;
-    case WF_F_DENSITY: { double4 q = Q1[s]; q.w = d[t]; Q1[s] = q; } break;
-    case WF_F_T: { double4 q = Q2[s]; q.y = d[t]; Q2[s] = q; } break;
+    case WF_F_DENSITY: { double4 q = Q2[s]; q.y = d[t]; Q2[s] = q; double4 w = Q1[s]; w.w = q.x / d[t]; Q1[s] = w; } break;
+    case WF_F_T: { double4 q = Q2[s]; q.z = d[t]; Q2[s] = q; } break;
     case WF_F_SIGMAY: F[(int64_t)F_SIGY * cap + s] = d[t]; break;
     case WF_F_ID: I[(int64_t)I_ID * cap + s] = ((const int *)in)[t]; break;
     default: break;
@@ -551,6 +553,7 @@ static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, 
     k_upload<<<grid_for(cnt, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->F[c->cur], c->I[c->cur], c->cap, (int)f, c->n, c->slot_of, d_idx, nidx, c->stage);
     WF_LAUNCH_CHECK(c);
     WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (f == WF_F_X || f == WF_F_V || f == WF_F_DENSITY) c->dens_valid = false;   // the prepared density rate no longer matches the state
     return 0;
 }
 extern "C" int wf_upload(wf_ctx *c, wf_field f, const void *host) { return upload_impl(c, f, nullptr, 0, host); }
@@ -570,7 +573,7 @@ extern "C" int wf_mesh_download(wf_ctx *c, int mesh, double *nodes, double *norm
 
 // ---- profiling ---------------------------------------------------------------------------------------------------------
 static const char *k_prof_names[PK_COUNT] = { "nb_keys", "nb_sort", "nb_permute", "nb_cells", "nb_list", "nb_surface", "nb_contact",
-    "step_begin", "density", "rate_stress", "accel", "contact", "bc", "move", "thermal", "energy", "reduce", "step_end" };
+    "step_begin", "density", "rate_stress", "accel", "contact", "bc", "move", "post", "energy", "reduce", "step_end" };
 extern "C" const char *wf_prof_name(int k) { return (k >= 0 && k < PK_COUNT) ? k_prof_names[k] : ""; }
 extern "C" int wf_prof_enable(wf_ctx *c, int on)
 {

@@ -30,9 +30,13 @@ enum OwnField {
     F_PLS = F_SI + 6, F_DPLS, F_SIGY, F_EFFSR, F_DTDT, F_QCONV, F_QPL, F_QFRIC, F_QCONT,
     F_CFX, F_CFY, F_CFZ, F_DCONT, F_NX, F_NY, F_NZ, F_DKIN, F_DINT,
     F_CSUM, F_CREAC, F_CEXT,          // per-particle partial sums of the Wang contact loop
-    F_COUNT
+    F_SG,                 // Sigma xx,yy,zz,xy,yz,xz (own copy; the gathered S arrays hold Sigma/rho^2 for GradientType 0)
+    F_PRES = F_SG + 6,    // Pressure
+    F_DDN,                // density rate prepared for the NEXT step by k_post (or by the stand-alone density pass)
+    F_TN,                 // TIR prepared for the next step, 6
+    F_COUNT = F_TN + 6
 };
-enum OwnInt { I_ID = 0, I_IDORIG, I_NB, I_NOWRITE, I_ORIG, I_OLDSURF, I_COUNT };
+enum OwnInt { I_ID = 0, I_IDORIG, I_NB, I_NOWRITE, I_ORIG, I_OLDSURF, I_CLS, I_COUNT };
 
 struct DevMesh {      // concatenated over meshes
     int n_nodes = 0, n_elems = 0;
@@ -69,7 +73,8 @@ struct wf_ctx {
     bool have_particles = false, solver_ready = false;
 
     int64_t n = 0, nsph = 0, cap = 0;            // particles (SPH + mesh), SPH count, allocated slots
-    // gathered arrays, double-buffered (index cur / 1-cur)
+    // gathered arrays, double-buffered (index cur / 1-cur): Q0 (x,y,z,h) Q1 (vx,vy,vz,m/rho) Q2 (m,rho,T,P/rho^2)
+    // S0 (pxx,pyy,pzz,pxy) S1 (pyz,pxz,Rxx,Ryy) S2 (Rzz,Rxy,Ryz,Rxz), p = Sigma/rho^2 (GradientType 0) or Sigma, R = TIR
     double4 *Q0[2] = { nullptr, nullptr }, *Q1[2] = { nullptr, nullptr }, *Q2[2] = { nullptr, nullptr },
             *S0[2] = { nullptr, nullptr }, *S1[2] = { nullptr, nullptr }, *S2[2] = { nullptr, nullptr };
     double *F[2] = { nullptr, nullptr };
@@ -79,7 +84,8 @@ struct wf_ctx {
     // classes / materials
     std::vector<wf::ClassProps> h_classes; wf::ClassProps *d_classes = nullptr; int n_classes = 0;
     std::vector<wf::MatProps> h_mats; wf::MatProps *d_mats = nullptr;
-    bool any_ti = false, uniform_h = false;
+    bool any_ti = false, uniform_h = false, single_class = false;
+    bool dens_valid = false;                     // F_DDN / F_TN hold the coming step's density rate and TIR (set by k_post)
     double totmass_mean = 0.0;                   // CalculateSurface's serial mean mass (Domain.cpp:1421-1425)
     // cell grid (Neighbour.cpp:10-139)
     double BLPF[3], TRPR[3], CellSize[3], hmax = 0.0, Cellfac = 2.0; int CellNo[3] = { 0, 0, 0 }; int64_t ncells = 0;
@@ -149,6 +155,7 @@ int pair_rate_stress(wf_ctx *c);
 int pair_accel(wf_ctx *c);
 int pair_thermal(wf_ctx *c);
 int pair_energy(wf_ctx *c);
+int pair_post(wf_ctx *c);
 // wf_step.cu
 int step_begin_impl(wf_ctx *c);
 int contact_impl(wf_ctx *c);

@@ -97,7 +97,7 @@ __device__ inline bool is_mesh_id(int id, int4 mids) { return id == mids.x || id
 __global__ void __launch_bounds__(128)
 k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long long *keys, const int *cell_start, const int *cell_end,
           const double4 *__restrict__ Q0, const double4 *__restrict__ Q2, const int *__restrict__ orig, const int *__restrict__ ID,
-          const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material,
+          const int *__restrict__ cls_of, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material,
           uint32_t *nbr, int *nb_cnt, int *nb_hi, int *nbI, double *normal_x, double *normal_y, double *normal_z, int *d_maxcnt)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,7 +111,7 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
         if (active) {
             const double4 qi = Q0[s];
             const V3 xi = v3(qi.x, qi.y, qi.z);
-            const int mat_i = check_material ? classes[(int)Q2[s].z].Material : 0;
+            const int mat_i = check_material ? classes[cls_of[s]].Material : 0;
             int c[3]; g.unlin((int)(keys[s] >> 32), c);
             for (int e = 0; e < 27; ++e) {
                 int d[3] = { c[0] + c_walk[e][0], c[1] + c_walk[e][1], c[2] + c_walk[e][2] };
@@ -119,28 +119,41 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
                 const int l = g.lin(d);
                 int js = cell_start[l], je = cell_end[l];
                 const int role = c_walk[e][3];
-                for (int j = js; j < je; ++j) {
-                    if (j == (int)s) continue;
-                    const int oj = orig[j];
-                    if (oj >= nsph) continue;                               // rigid-mesh particle: never an SM pair
-                    if (contact && is_mesh_id(ID[j], mids)) continue;
-                    const double4 qj = Q0[j];
-                    // own cell: particles stored before s have a larger creation index and act as temp1
-                    const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
-                    const double hh = (qi.w + qj.w) / 2;
-                    const V3 xj = v3(qj.x, qj.y, qj.z);
-                    const V3 xij = ifirst ? (xi - xj) : (xj - xi);
-                    const double rij = norm(xij);
-                    if (!((rij / hh) <= g.Cellfac)) continue;
-                    if (check_material && classes[(int)Q2[j].z].Material != mat_i) continue;
-                    uint32_t entry = (uint32_t)j | (ifirst ? 0x80000000u : 0u);
-                    if (oj > oi) { if (nhi + nlo < K) nbr[(int64_t)nhi * cap + s] = entry; ++nhi; }
-                    else         { if (nhi + nlo < K) nbr[(int64_t)(K - 1 - nlo) * cap + s] = entry; ++nlo; }
-                    if (contact) {
-                        // Domain.cpp:1446-1463: P1->normal += mj*xij ; P2->normal -= mi*xij, in discovery order
-                        const double mj = Q2[j].x;
-                        if (ifirst) { nx += mj * xij.x; ny += mj * xij.y; nz += mj * xij.z; }
-                        else        { nx -= mj * xij.x; ny -= mj * xij.y; nz -= mj * xij.z; }
+                // candidates of a cell are contiguous slots: fetch them four at a time (independent loads in flight), then
+                // test / append strictly in slot order so that the list keeps the reference's discovery order
+                for (int j0 = js; j0 < je; j0 += 4) {
+                    double4 qb[4]; int ob[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int jj = (j0 + u < je) ? j0 + u : je - 1; qb[u] = Q0[jj]; ob[u] = orig[jj]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = j0 + u;
+                        if (j >= je || j == (int)s) continue;
+                        const int oj = ob[u];
+                        if (oj >= nsph) continue;                               // rigid-mesh particle: never an SM pair
+                        if (contact && is_mesh_id(ID[j], mids)) continue;
+                        const double4 qj = qb[u];
+                        // own cell: particles stored before s have a larger creation index and act as temp1
+                        const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
+                        const double hh = (qi.w + qj.w) / 2;
+                        const V3 xj = v3(qj.x, qj.y, qj.z);
+                        const V3 xij = ifirst ? (xi - xj) : (xj - xi);
+                        // CheckRadius (Neighbour.cpp:361-372): sqrt(|xij|^2)/hh <= Cellfac. The squared form decides every candidate
+                        // that is not within a few ulp of the cutoff (sqrt and the division each round within 2^-53 relative);
+                        // only those borderline ones take the exact expression.
+                        const double d2 = dot(xij, xij), lim = g.Cellfac * hh, lim2 = lim * lim;
+                        if (d2 > lim2 * (1.0 + 8e-15)) continue;
+                        if (!(d2 < lim2 * (1.0 - 8e-15))) { const double rij = sqrt(d2); if (!((rij / hh) <= g.Cellfac)) continue; }
+                        if (check_material && classes[cls_of[j]].Material != mat_i) continue;
+                        uint32_t entry = (uint32_t)j | (ifirst ? 0x80000000u : 0u);
+                        if (oj > oi) { if (nhi + nlo < K) nbr[(int64_t)nhi * cap + s] = entry; ++nhi; }
+                        else         { if (nhi + nlo < K) nbr[(int64_t)(K - 1 - nlo) * cap + s] = entry; ++nlo; }
+                        if (contact) {
+                            // Domain.cpp:1446-1463: P1->normal += mj*xij ; P2->normal -= mi*xij, in discovery order
+                            const double mj = Q2[j].x;
+                            if (ifirst) { nx += mj * xij.x; ny += mj * xij.y; nz += mj * xij.z; }
+                            else        { nx -= mj * xij.x; ny -= mj * xij.y; nz -= mj * xij.z; }
+                        }
                     }
                 }
             }
@@ -312,7 +325,7 @@ int nb_build_impl(wf_ctx *c)
         if ((int64_t)K * cap > c->nbr_alloc) { cudaFree(c->nbr); c->nbr = nullptr; WF_CUDA(c, cudaMalloc(&c->nbr, (size_t)K * cap * sizeof(uint32_t))); c->nbr_alloc = (int64_t)K * cap; }
         WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt, 0, 4 * sizeof(int), st));
         k_nb_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->cell_start, c->cell_end, c->Q0[c->cur], c->Q2[c->cur], c->Ip(I_ORIG), c->Ip(I_ID),
-            c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
+            c->Ip(I_CLS), c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
         WF_LAUNCH_CHECK(c); c->launches++;
         int mx = 0; WF_CUDA(c, cudaMemcpyAsync(&mx, c->d_maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));
         if (mx <= K) break;
@@ -343,6 +356,7 @@ int nb_build_impl(wf_ctx *c)
         }
     }
     c->nb_cleared = false;
+    c->dens_valid = false;           // a density rate summed over the old list is not what the reference would compute now
     c->nb_rebuilds++;
     return 0;
 }

@@ -5,13 +5,32 @@
 //   CalcAccel + AccelReduction               Source/InteractionAlt.cpp:12-260
 //   CalcTempInc                              Source/Thermal.cpp:53-217
 //   CalcKinEnergyEqn                         Source/Domain.cpp:1752-1808
-// and Domain::StartAcceleration (Source/Domain.cpp:1519-1597), which is fused into the density kernel.
+// and Domain::StartAcceleration (Source/Domain.cpp:1519-1597).
+//
+// Three pair passes per step instead of the reference's five:
+//   k_rate_stress   strain/rotation-rate sums + the whole constitutive update
+//   k_accel         momentum
+//   k_post          heat conduction + kinetic-energy rate + (for the NEXT step) density rate and tensile-instability tensor:
+//                   between the end of step n and the density pass of step n+1 neither x, v nor rho change, so the
+//                   three loops share one walk (x_ij, r, q, grad-W evaluated once). When the neighbour list is rebuilt
+//                   or the host uploads state in between, the prologue falls back to the stand-alone pass (k_post<DENS only>).
+//
+// Gathered arrays (one 32-byte sector per neighbour and array):
+//   Q0 = (x, y, z, h)   Q1 = (vx, vy, vz, m/rho)   Q2 = (m, rho, T, P/rho^2)
+//   S0 = (pxx, pyy, pzz, pxy)  S1 = (pyz, pxz, Rxx, Ryy)  S2 = (Rzz, Rxy, Ryz, Rxz)
+//   with p = Sigma/rho^2 for GradientType 0 (the reference's 1/(rho*rho)*Sigma factor, evaluated once per particle
+//   instead of once per pair -- same expression, same bits) or Sigma itself for GradientType 1/2, and R = TIR.
 //
 // Each pair term is evaluated with the reference's operand order. The reference evaluates a pair once with
 // P1 = min(i,j), P2 = max(i,j) and adds +m_j*t to P1, -m_i*t to P2; every term used here is exactly symmetric or
 // antisymmetric under i<->j in IEEE arithmetic (x_ij, v_ij flip sign exactly; h, rho sums commute), so evaluating it
 // from particle i's side gives the same bits. GradientType 2 (sigma_i - sigma_j) is the exception and is evaluated in
 // min/max order explicitly. Sums run in the reference's order (see wf_neighbour.cu).
+//
+// Divisions by a quantity that is constant for the thread (h, W(dx0/h), k_i + k_j) use div_c(): a correctly rounded
+// quotient from the correctly rounded reciprocal and two FMA residual corrections (Markstein), bit-identical to an IEEE
+// division, cheaper than the generic division sequence. Guarded against the one divisor pattern (all-ones significand)
+// for which the theorem does not hold.
 #include "wf_internal.cuh"
 
 using namespace wf;
@@ -20,7 +39,7 @@ namespace {
 
 struct PairArgs {
     int64_t n, cap; int nsph, K, dim, kt, gt;
-    const uint32_t *nbr; const int *nb_cnt, *nb_hi; const int *orig;
+    const uint32_t *nbr; const int *nb_cnt, *nb_hi; const int *orig; const int *cls_of;
     double4 *Q0, *Q1, *Q2, *S0, *S1, *S2; double *F; const ClassProps *cls; const MatProps *mats;
     double dt; int any_ti, thermal, pl_heating, contact, cont_heat_fric; double pl_work_heat_frac;
 };
@@ -33,10 +52,33 @@ __device__ inline int nb_row(int n, int nhi, int K) { return n < nhi ? n : (K - 
 __device__ inline double c3_of(double h) { return 1.0 / (h * h * h * WF_PI); }
 __device__ inline double c4_of(double h) { return 1.0 / (h * h * h * h * WF_PI); }
 
-template <int KT> __device__ inline double GK_of(int dim, int kt, double q, double hh, double C4)
-{ if (KT == 0) return cubicGW_c(C4, q, hh); else return gradW(dim, kt, q, hh); }
-template <int KT> __device__ inline double W_of(int dim, int kt, double q, double hh, double C3)
-{ if (KT == 0) return cubicW_c(C3, q); else return kernelW(dim, kt, q, hh); }
+// ---- division by a per-thread constant -------------------------------------------------------------------------------
+struct DivC { double b, y; int fast; };
+__device__ inline DivC divc_make(double b)
+{
+    DivC d; d.b = b; d.y = 1.0 / b;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(b);
+    const unsigned ex = (unsigned)((bits >> 52) & 0x7ff);
+    // exclusions: all-ones significand (Markstein's theorem needs RN(1/b) with |b*y - 1| < 2^-53), and extreme exponents
+    d.fast = ((bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull) && ex > 200 && ex < 1800;
+    return d;
+}
+__device__ inline double div_c(double a, const DivC &d)
+{
+    if (!d.fast) return a / d.b;
+    const unsigned ea = (unsigned)(((unsigned long long)__double_as_longlong(a) >> 52) & 0x7ff);
+    if (ea < 200 || ea > 1800) return a / d.b;                 // zero / subnormal / huge numerators: generic path
+    const double q0 = a * d.y;
+    const double r0 = __fma_rn(-q0, d.b, a);
+    const double q1 = __fma_rn(r0, d.y, q0);                   // faithful
+    const double r1 = __fma_rn(-q1, d.b, a);                   // exact
+    return __fma_rn(r1, d.y, q1);                              // RN(a/b)
+}
+
+template <bool FAST> __device__ inline double GK_of(int dim, int kt, double q, double hh, double C4)
+{ if (FAST) return cubicGW_c(C4, q, hh); else return gradW(dim, kt, q, hh); }
+template <bool FAST> __device__ inline double W_of(int dim, int kt, double q, double hh, double C3)
+{ if (FAST) return cubicW_c(C3, q); else return kernelW(dim, kt, q, hh); }
 
 // x^4 rounded from a double-double product: reproduces a correctly rounded pow(x, 4.0) (InteractionAlt.cpp:108 with
 // the default TIn = 4) without the cost of a general fp64 pow.
@@ -47,59 +89,36 @@ __device__ inline double pow4_cr(double r)
     return r4h + (e1 + 2.0 * r2h * r2l);
 }
 
-// ---- StartAcceleration (TIR) + CalcDensInc + DensReduction ------------------------------------------------------------
-template <int KT> __global__ void __launch_bounds__(128) k_density(PairArgs a)
+// Domain.cpp:1528-1570: tensile-instability tensor from Sigma and rho
+__device__ inline void tir_of(const S6 &sg, double rho, double TI, double out[6])
+{
+    const double rho2 = rho * rho;
+    const double pc = TI / (rho2);
+    double d[3]; M3 Vec; sym_eig3(m3sym(sg), d, Vec);
+    M3 VecT = mtrans(Vec), Val = m3zero();
+    for (int k = 0; k < 3; ++k) { if (d[k] > 0) Val(k, k) = -pc * d[k]; else Val(k, k) = 0.0; }
+    M3 T = mmul(mmul(Vec, Val), VecT);
+    // stored symmetric (upper triangle); the reference's TIR differs from its transpose by round-off only
+    out[0] = T(0, 0); out[1] = T(1, 1); out[2] = T(2, 2); out[3] = T(0, 1); out[4] = T(1, 2); out[5] = T(0, 2);
+}
+
+// ---- step prologue per particle: rho += dt*drho (SolverFraser.cpp:248-252), m/rho, TIR <- the tensor prepared for this step
+__global__ void k_prologue(PairArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
-    const double4 qi = a.Q0[s], wi = a.Q1[s];
-    const int ci = (int)a.Q2[s].z;
-    // Domain.cpp:1528-1570: tensile-instability tensor from the stress and density the step starts with
-    if (a.any_ti) {
-        const double TI = a.cls[ci].TI;
-        if (TI > 0.0) {
-            const double rho2 = wi.w * wi.w;
-            const double pc = TI / (rho2);
-            double4 s0 = a.S0[s]; double2 s1 = *(const double2 *)&a.S1[s];
-            S6 sg; sg.xx = s0.x; sg.yy = s0.y; sg.zz = s0.z; sg.xy = s0.w; sg.yz = s1.x; sg.xz = s1.y;
-            double d[3]; M3 Vec; sym_eig3(m3sym(sg), d, Vec);
-            M3 VecT = mtrans(Vec), Val = m3zero();
-            for (int k = 0; k < 3; ++k) { if (d[k] > 0) Val(k, k) = -pc * d[k]; else Val(k, k) = 0.0; }
-            M3 T = mmul(mmul(Vec, Val), VecT);
-            // stored symmetric (upper triangle); the reference's TIR differs from its transpose by round-off only
-            ((double2 *)&a.S1[s])[1] = make_double2(T(0, 0), T(1, 1));
-            a.S2[s] = make_double4(T(2, 2), T(0, 1), T(1, 2), T(0, 2));
-        }
-    }
-    const V3 xi = v3(qi.x, qi.y, qi.z), vi = v3(wi.x, wi.y, wi.z);
-    const double hi = qi.w, C4i = c4_of(hi);
-    const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
-    double dd = 0.;
-    for (int n = 0; n < cnt; ++n) {
-        const int j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
-        const double4 qj = a.Q0[j], wj = a.Q1[j];
-        const double mj = a.Q2[j].x;
-        double hh, C4;
-        if (qj.w == hi) { hh = hi; C4 = C4i; } else { hh = (hi + qj.w) / 2; C4 = c4_of(hh); }
-        const V3 xij = xi - v3(qj.x, qj.y, qj.z);
-        const double rij = norm(xij);
-        const V3 vij = vi - v3(wj.x, wj.y, wj.z);
-        const double GK = GK_of<KT>(a.dim, a.kt, rij / hh, hh, C4);
-        const double t1 = dot(vij, GK * xij);
-        dd += mj / wj.w * t1;
-    }
-    dd *= wi.w;
+    const double dd = OWN(F_DDN);
     OWN(F_DDENS) = dd;
-}
-
-// rho += dt*drho (SolverFraser.cpp:248-252)
-__global__ void k_density_update(PairArgs a)
-{
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n) return;
-    double *rho = &((double *)&a.Q1[s])[3];
-    *rho = *rho + a.dt * OWN(F_DDENS);
+    double4 q2 = a.Q2[s];
+    const double rho = q2.y + a.dt * dd;
+    q2.y = rho;
+    a.Q2[s] = q2;
+    ((double *)&a.Q1[s])[3] = q2.x / rho;
+    if (a.any_ti) {
+        ((double2 *)&a.S1[s])[1] = make_double2(OWN(F_TN), OWN(F_TN + 1));
+        a.S2[s] = make_double4(OWN(F_TN + 2), OWN(F_TN + 3), OWN(F_TN + 4), OWN(F_TN + 5));
+    }
 }
 
 // Material.cpp:6-25,59-64
@@ -114,7 +133,7 @@ __device__ inline double yield_stress(const MatProps &m, double strain, double s
 }
 
 // ---- CalcRateTensors + RateTensorsReduction + CalcStressStrain -------------------------------------------------------
-template <int KT> __global__ void __launch_bounds__(128) k_rate_stress(PairArgs a)
+template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_stress(PairArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
@@ -122,18 +141,31 @@ template <int KT> __global__ void __launch_bounds__(128) k_rate_stress(PairArgs 
     const double4 qi = a.Q0[s], wi = a.Q1[s];
     const V3 xi = v3(qi.x, qi.y, qi.z), vi = v3(wi.x, wi.y, wi.z);
     const double hi = qi.w, C4i = c4_of(hi);
+    const DivC dh = divc_make(hi);
     const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
     double sxx = 0., syy = 0., szz = 0., sxy = 0., syz = 0., sxz = 0., r01 = 0., r02 = 0., r12 = 0.;
+    // software pipeline: the gathers of neighbour n+1 (and the list entry of n+2) are in flight while n is evaluated
+    double4 qn = qi, wn = wi; uint32_t e2 = 0;
+    if (PF && cnt > 0) { const int j0 = (int)(a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s] & 0x7fffffffu); qn = a.Q0[j0]; wn = a.Q1[j0];
+                         if (cnt > 1) e2 = a.nbr[(int64_t)nb_row(1, nhi, a.K) * a.cap + s]; }
     for (int n = 0; n < cnt; ++n) {
-        const int j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
-        const double4 qj = a.Q0[j], wj = a.Q1[j];
-        const double mjdj = a.Q2[j].x / wj.w;
-        double hh, C4;
-        if (qj.w == hi) { hh = hi; C4 = C4i; } else { hh = (hi + qj.w) / 2; C4 = c4_of(hh); }
+        double4 qj, wj;
+        if (PF) {
+            qj = qn; wj = wn;
+            if (n + 1 < cnt) { const int j1 = (int)(e2 & 0x7fffffffu); qn = a.Q0[j1]; wn = a.Q1[j1]; }
+            if (n + 2 < cnt) e2 = a.nbr[(int64_t)nb_row(n + 2, nhi, a.K) * a.cap + s];
+        } else {
+            const int j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
+            qj = a.Q0[j]; wj = a.Q1[j];
+        }
+        const double mjdj = wj.w;                                    // m_j / rho_j (InteractionAlt.cpp:455), kept per particle
         const V3 xij = xi - v3(qj.x, qj.y, qj.z);
         const double rij = norm(xij);
         const V3 vab = vi - v3(wj.x, wj.y, wj.z);
-        const double GK = GK_of<KT>(a.dim, a.kt, rij / hh, hh, C4);
+        double GK;
+        if (FAST) GK = cubicGW_c(C4i, div_c(rij, dh), hi);
+        else { double hh, C4; if (qj.w == hi) { hh = hi; C4 = C4i; } else { hh = (hi + qj.w) / 2; C4 = c4_of(hh); }
+               GK = (a.kt == 0 && a.dim == 3) ? cubicGW_c(C4, rij / hh, hh) : gradW(a.dim, a.kt, rij / hh, hh); }
         const double f = -0.5 * GK;
         // InteractionAlt.cpp:338-361, then :456-457 (StrainRate = StrainRate + mjdj * pair_StrainRate)
         sxx = sxx + ((2.0 * vab.x * xij.x) * f) * mjdj;
@@ -147,9 +179,10 @@ template <int KT> __global__ void __launch_bounds__(128) k_rate_stress(PairArgs 
         r12 = r12 + ((vab.y * xij.z - vab.z * xij.y) * f) * mjdj;
     }
     // ---------------- Particle::CalcStressStrain (Particle.cpp:960-1067) ----------------
-    const int ci = (int)a.Q2[s].z; const ClassProps cp = a.cls[ci];
+    const int ci = a.cls_of[s]; const ClassProps cp = a.cls[ci];
     const double dt = a.dt;
-    const double rho = wi.w;
+    double4 q2 = a.Q2[s];
+    const double rho = q2.y;
     const double Pressure = eos(cp.PresEq, cp.Cs, cp.P0, rho, cp.RefDensity);
     S6 srs; srs.xx = sxx; srs.yy = syy; srs.zz = szz; srs.xy = sxy; srs.yz = syz; srs.xz = sxz;
     const M3 SR = m3sym(srs);
@@ -173,7 +206,7 @@ template <int KT> __global__ void __launch_bounds__(128) k_rate_stress(PairArgs 
         SS = ((1.0 < rs) ? 1.0 : rs) * SS;            // std::min(Sigmay/sig_trial, 1.0), NaN-propagating like the reference
         double pl = OWN(F_PLS);
         if (cp.Material_model == 1) Sigmay = yield_stress(a.mats[cp.mat_id], pl, 0.0, 0.0);
-        else if (cp.Material_model == 2) Sigmay = yield_stress(a.mats[cp.mat_id], pl, effsr, a.Q2[s].y);
+        else if (cp.Material_model == 2) Sigmay = yield_stress(a.mats[cp.mat_id], pl, effsr, q2.z);
         if (sig_trial > Sigmay) {
             double Ep = cp.Ep;
             if (Ep < 0) Ep = 1. * a.mats[cp.mat_id].E;
@@ -186,9 +219,19 @@ template <int KT> __global__ void __launch_bounds__(128) k_rate_stress(PairArgs 
     }
     const M3 Sg = (-Pressure) * I + SS;
     OWN(F_SH) = SS(0, 0); OWN(F_SH + 1) = SS(1, 1); OWN(F_SH + 2) = SS(2, 2); OWN(F_SH + 3) = SS(0, 1); OWN(F_SH + 4) = SS(1, 2); OWN(F_SH + 5) = SS(0, 2);
-    a.S0[s] = make_double4(Sg(0, 0), Sg(1, 1), Sg(2, 2), Sg(0, 1));
-    ((double2 *)&a.S1[s])[0] = make_double2(Sg(1, 2), Sg(0, 2));
-    ((double *)&a.Q2[s])[3] = Pressure;
+    OWN(F_SG) = Sg(0, 0); OWN(F_SG + 1) = Sg(1, 1); OWN(F_SG + 2) = Sg(2, 2); OWN(F_SG + 3) = Sg(0, 1); OWN(F_SG + 4) = Sg(1, 2); OWN(F_SG + 5) = Sg(0, 2);
+    OWN(F_PRES) = Pressure;
+    // gathered copies for the momentum pass: 1.0/(rho*rho)*Sigma (InteractionAlt.cpp:139) or Sigma (GradientType 1, 2);
+    // and P/(rho*rho) for the kinetic-energy pass (Domain.cpp:1784)
+    const double inv_d2 = 1.0 / (rho * rho);
+    if (a.gt == 0) {
+        a.S0[s] = make_double4(Sg(0, 0) * inv_d2, Sg(1, 1) * inv_d2, Sg(2, 2) * inv_d2, Sg(0, 1) * inv_d2);
+        ((double2 *)&a.S1[s])[0] = make_double2(Sg(1, 2) * inv_d2, Sg(0, 2) * inv_d2);
+    } else {
+        a.S0[s] = make_double4(Sg(0, 0), Sg(1, 1), Sg(2, 2), Sg(0, 1));
+        ((double2 *)&a.S1[s])[0] = make_double2(Sg(1, 2), Sg(0, 2));
+    }
+    ((double *)&a.Q2[s])[3] = Pressure / (rho * rho);
     if (dep > 0.0) {
         const double f = dep / Sigmay;
         const double ixx = f * (Sg(0, 0) - 0.5 * (Sg(1, 1) + Sg(2, 2)));
@@ -207,56 +250,79 @@ template <int KT> __global__ void __launch_bounds__(128) k_rate_stress(PairArgs 
 }
 
 // ---- CalcAccel + AccelReduction ------------------------------------------------------------------------------------------
-template <int KT, int GT> __global__ void __launch_bounds__(128) k_accel(PairArgs a)
+template <bool FAST, int GT, int MB, bool PF> __global__ void __launch_bounds__(128, MB) k_accel(PairArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
-    const double4 qi = a.Q0[s], wi = a.Q1[s];
+    const double4 qi = a.Q0[s], wi = a.Q1[s], q2i = a.Q2[s];
     const V3 xi = v3(qi.x, qi.y, qi.z), vi = v3(wi.x, wi.y, wi.z);
-    const double hi = qi.w, C3i = c3_of(hi), C4i = c4_of(hi), di = wi.w;
-    const int ci = (int)a.Q2[s].z; const ClassProps cpi = a.cls[ci];
+    const double hi = qi.w, C3i = c3_of(hi), C4i = c4_of(hi), di = q2i.y;
+    const int ci = a.cls_of[s]; const ClassProps cpi = a.cls[ci];
     const double4 s0i = a.S0[s], s1i = a.S1[s], s2i = a.S2[s];
     const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
-    const double inv_di2 = 1.0 / (di * di);
     const double Ci = soundSpeed(cpi.PresEq, cpi.Cs, di, cpi.RefDensity);
     // W(dx0/h) of the tensile-instability term for the common same-class, same-h neighbour
-    const double W0i = W_of<KT>(a.dim, a.kt, (cpi.TIInitDist + cpi.TIInitDist) / (2.0 * hi), hi, C3i);
+    const double W0i = W_of<FAST>(a.dim, a.kt, (cpi.TIInitDist + cpi.TIInitDist) / (2.0 * hi), hi, C3i);
+    const DivC dh = divc_make(hi), dW0 = divc_make(W0i);
+    const bool ti_on = a.any_ti && (!FAST || cpi.TI > 0.0);
     double ax = 0., ay = 0., az = 0.;
+    double4 qn = qi, wn = wi, q2n = q2i, s0n = s0i, s1n = s1i; uint32_t e2 = 0; int jcur = 0;
+    if (PF && cnt > 0) { jcur = (int)(a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s] & 0x7fffffffu); qn = a.Q0[jcur]; wn = a.Q1[jcur]; q2n = a.Q2[jcur];
+                         if (MB == 2) { s0n = a.S0[jcur]; s1n = a.S1[jcur]; }
+                         if (cnt > 1) e2 = a.nbr[(int64_t)nb_row(1, nhi, a.K) * a.cap + s]; }
     for (int n = 0; n < cnt; ++n) {
-        const int j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
-        const double4 qj = a.Q0[j], wj = a.Q1[j], q2j = a.Q2[j];
-        const double4 s0j = a.S0[j]; const double2 s1j = *(const double2 *)&a.S1[j];
-        const double mj = q2j.x, dj = wj.w; const int cj = (int)q2j.z;
-        const bool same = (cj == ci);
-        const bool sameh = (qj.w == hi);
-        double hh, C3, C4;
-        if (sameh) { hh = hi; C3 = C3i; C4 = C4i; } else { hh = (hi + qj.w) / 2; C3 = c3_of(hh); C4 = c4_of(hh); }
-        // GradientType 2 is not symmetric under i<->j: evaluate it the way the reference does, P1 = smaller creation index
-        const bool swap = (GT == 2) && (n >= nhi);
+        int j; double4 qj, wj, q2j;
+        if (PF) {
+            j = jcur; qj = qn; wj = wn; q2j = q2n;
+        } else {
+            j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
+            qj = a.Q0[j]; wj = a.Q1[j]; q2j = a.Q2[j];
+        }
+        double4 s0j, s1j;
+        if (PF && MB == 2) { s0j = s0n; s1j = s1n; }
+        else { s0j = a.S0[j]; s1j = a.S1[j]; }            // consumed late in the iteration: their latency overlaps the kernel / viscosity math
+        if (PF) {
+            if (n + 1 < cnt) { jcur = (int)(e2 & 0x7fffffffu); qn = a.Q0[jcur]; wn = a.Q1[jcur]; q2n = a.Q2[jcur]; if (MB == 2) { s0n = a.S0[jcur]; s1n = a.S1[jcur]; } }
+            if (n + 2 < cnt) e2 = a.nbr[(int64_t)nb_row(n + 2, nhi, a.K) * a.cap + s];
+        }
+        const double mj = q2j.x, dj = q2j.y;
+        const bool swap = (GT == 2) && (n >= nhi);      // GradientType 2 is not symmetric under i<->j: P1 = smaller creation index
         V3 xij = xi - v3(qj.x, qj.y, qj.z), vij = vi - v3(wj.x, wj.y, wj.z);
         if (swap) { xij = v3(-xij.x, -xij.y, -xij.z); vij = v3(-vij.x, -vij.y, -vij.z); }
         const double rij = norm(xij);
-        const double q = rij / hh;
-        const double GK = GK_of<KT>(a.dim, a.kt, q, hh, C4);
-        double Alpha, Beta, TIj, TInj, TId_j, Cj;
-        if (same) { Alpha = (cpi.Alpha + cpi.Alpha) / 2.0; Beta = (cpi.Beta + cpi.Beta) / 2.0; TIj = cpi.TI; TInj = cpi.TIn; TId_j = cpi.TIInitDist; Cj = soundSpeed(cpi.PresEq, cpi.Cs, dj, cpi.RefDensity); }
-        else { const ClassProps cpj = a.cls[cj]; Alpha = (cpi.Alpha + cpj.Alpha) / 2.0; Beta = (cpi.Beta + cpj.Beta) / 2.0; TIj = cpj.TI; TInj = cpj.TIn; TId_j = cpj.TIInitDist;
-               Cj = soundSpeed(cpj.PresEq, cpj.Cs, dj, cpj.RefDensity); }
+        double hh, C3, C4, q, Alpha, Beta, TIj, TInj, TId_j, Cj; bool same_w0;
+        if (FAST) {
+            hh = hi; C3 = C3i; C4 = C4i; q = div_c(rij, dh);
+            Alpha = (cpi.Alpha + cpi.Alpha) / 2.0; Beta = (cpi.Beta + cpi.Beta) / 2.0; TIj = cpi.TI; TInj = cpi.TIn; TId_j = cpi.TIInitDist;
+            Cj = soundSpeed(cpi.PresEq, cpi.Cs, dj, cpi.RefDensity); same_w0 = true;
+        } else {
+            if (qj.w == hi) { hh = hi; C3 = C3i; C4 = C4i; } else { hh = (hi + qj.w) / 2; C3 = c3_of(hh); C4 = c4_of(hh); }
+            q = rij / hh;
+            const int cj = a.cls_of[j];
+            if (cj == ci) { Alpha = (cpi.Alpha + cpi.Alpha) / 2.0; Beta = (cpi.Beta + cpi.Beta) / 2.0; TIj = cpi.TI; TInj = cpi.TIn; TId_j = cpi.TIInitDist;
+                            Cj = soundSpeed(cpi.PresEq, cpi.Cs, dj, cpi.RefDensity); }
+            else { const ClassProps cpj = a.cls[cj]; Alpha = (cpi.Alpha + cpj.Alpha) / 2.0; Beta = (cpi.Beta + cpj.Beta) / 2.0; TIj = cpj.TI; TInj = cpj.TIn; TId_j = cpj.TIInitDist;
+                   Cj = soundSpeed(cpj.PresEq, cpj.Cs, dj, cpj.RefDensity); }
+            same_w0 = (cj == ci) && (qj.w == hi);
+        }
+        double GK;
+        if (FAST) GK = cubicGW_c(C4, q, hh); else GK = (a.kt == 0 && a.dim == 3) ? cubicGW_c(C4, q, hh) : gradW(a.dim, a.kt, q, hh);
         // artificial viscosity (InteractionAlt.cpp:72-94)
         double pi = 0.0; bool pi_on = false;
         if (Alpha != 0.0 || Beta != 0.0) {
             const double vx = dot(vij, xij);
-            const double MUij = hh * vx / (rij * rij + 0.01 * hh * hh);
-            const double Cij = 0.5 * (Ci + Cj);
-            if (vx < 0) { pi = (Alpha * Cij * MUij + Beta * MUij * MUij) / (0.5 * (di + dj)); pi_on = true; }
+            if (vx < 0) {
+                const double MUij = hh * vx / (rij * rij + 0.01 * hh * hh);
+                const double Cij = 0.5 * (Ci + Cj);
+                pi = (Alpha * Cij * MUij + Beta * MUij * MUij) / (0.5 * (di + dj)); pi_on = true;
+            }
         }
         // momentum tensor (InteractionAlt.cpp:138-143)
         double mxx, myy, mzz, mxy, myz, mxz;
-        if (GT == 0) {
-            const double inv_dj2 = 1.0 / (dj * dj);
-            mxx = s0i.x * inv_di2 + s0j.x * inv_dj2; myy = s0i.y * inv_di2 + s0j.y * inv_dj2; mzz = s0i.z * inv_di2 + s0j.z * inv_dj2;
-            mxy = s0i.w * inv_di2 + s0j.w * inv_dj2; myz = s1i.x * inv_di2 + s1j.x * inv_dj2; mxz = s1i.y * inv_di2 + s1j.y * inv_dj2;
+        if (GT == 0) {          // S holds 1.0/(rho*rho)*Sigma
+            mxx = s0i.x + s0j.x; myy = s0i.y + s0j.y; mzz = s0i.z + s0j.z;
+            mxy = s0i.w + s0j.w; myz = s1i.x + s1j.x; mxz = s1i.y + s1j.y;
         } else if (GT == 1) {
             const double f = 1.0 / (di * dj);
             mxx = (s0i.x + s0j.x) * f; myy = (s0i.y + s0j.y) * f; mzz = (s0i.z + s0j.z) * f;
@@ -269,14 +335,14 @@ template <int KT, int GT> __global__ void __launch_bounds__(128) k_accel(PairArg
         }
         if (pi_on) { mxx += pi; myy += pi; mzz += pi; }
         // tensile instability (InteractionAlt.cpp:103-110)
-        if (a.any_ti && (cpi.TI > 0.0 || TIj > 0.0)) {
-            const double K = W_of<KT>(a.dim, a.kt, q, hh, C3);
-            const double W0 = (same && sameh) ? W0i : W_of<KT>(a.dim, a.kt, (cpi.TIInitDist + TId_j) / (2.0 * hh), hh, C3);
+        if (ti_on && (cpi.TI > 0.0 || TIj > 0.0)) {
+            const double K = W_of<FAST>(a.dim, a.kt, q, hh, C3);
+            double r;
+            if (same_w0) r = div_c(K, dW0); else r = K / W_of<FAST>(a.dim, a.kt, (cpi.TIInitDist + TId_j) / (2.0 * hh), hh, C3);
             const double nbar = (cpi.TIn + TInj) / 2.0;
-            const double r = K / W0;
             const double fti = (nbar == 4.0) ? pow4_cr(r) : pow(r, nbar);
-            const double2 t1j = ((const double2 *)&a.S1[j])[1]; const double4 t2j = a.S2[j];
-            mxx += (s1i.z + t1j.x) * fti; myy += (s1i.w + t1j.y) * fti; mzz += (s2i.x + t2j.x) * fti;
+            const double4 t2j = a.S2[j];
+            mxx += (s1i.z + s1j.z) * fti; myy += (s1i.w + s1j.w) * fti; mzz += (s2i.x + t2j.x) * fti;
             mxy += (s2i.y + t2j.y) * fti; myz += (s2i.z + t2j.z) * fti; mxz += (s2i.w + t2j.w) * fti;
         }
         // temp = (GK*xij)^T M (matvec.h:829-834), a_i += m_j*temp (or -= when i is P2 of a GradientType-2 pair)
@@ -300,104 +366,126 @@ __global__ void k_thermal_pre(PairArgs a)
     const double dt = a.dt;
     if (a.pl_heating && OWN(F_DPLS) > 0.0) {
         const double f = 1. / dt;
-        const double4 s0 = a.S0[s]; const double2 s1 = *(const double2 *)&a.S1[s];
+        const double sxx = OWN(F_SG), syy = OWN(F_SG + 1), szz = OWN(F_SG + 2), sxy = OWN(F_SG + 3), syz = OWN(F_SG + 4), sxz = OWN(F_SG + 5);
         const double dxx = OWN(F_SI) * f, dyy = OWN(F_SI + 1) * f, dzz = OWN(F_SI + 2) * f, dxy = OWN(F_SI + 3) * f, dyz = OWN(F_SI + 4) * f, dxz = OWN(F_SI + 5) * f;
-        OWN(F_QPL) = s0.x * dxx + 2.0 * s0.w * dxy + 2.0 * s1.y * dxz + s0.y * dyy + 2.0 * s1.x * dyz + s0.z * dzz;
+        OWN(F_QPL) = sxx * dxx + 2.0 * sxy * dxy + 2.0 * sxz * dxz + syy * dyy + 2.0 * syz * dyz + szz * dzz;
     }
     if (a.thermal) {
         double4 q2 = a.Q2[s];
-        const double T = q2.y + dt * OWN(F_DTDT);
-        ((double *)&a.Q2[s])[1] = T;
-        const ClassProps cp = a.cls[(int)q2.z];
+        const double T = q2.z + dt * OWN(F_DTDT);
+        ((double *)&a.Q2[s])[2] = T;
+        const ClassProps cp = a.cls[a.cls_of[s]];
         if (cp.Thermal_BC == 1) {
-            const double dens = a.Q1[s].w;
+            const double dens = q2.y;
             const double dS2 = pow(q2.x / dens, 2.0 / 3.0);
             OWN(F_QCONV) = dens * cp.h_conv * dS2 * (cp.T_inf - T) / q2.x;
         }
     }
 }
 
-// ---- CalcTempInc (Thermal.cpp:53-217); sums run in list order (round-off level difference to the reference's
-// pair-discovery order); the m_j/rho_j factor is the SECOND particle's, as in the reference ---------------------------
-template <int KT> __global__ void __launch_bounds__(128) k_thermal(PairArgs a)
+// ---- k_post: CalcTempInc (Thermal.cpp:53-217) + CalcKinEnergyEqn / CalcIntEnergyEqn (Domain.cpp:1752-1829) + the
+// density rate (InteractionAlt.cpp:483-640) and TIR (Domain.cpp:1528-1570) of the step that follows. One neighbour
+// walk; each sum keeps its own reference order and operand order. Thermal: the m/rho factor is the SECOND particle's
+// of the reference pair, and the sums run in list order (round-off level difference to the reference's pair-discovery
+// order when several threads race in the reference; identical for Nproc = 1).
+template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF> __global__ void __launch_bounds__(128, 4) k_post(PairArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
-    if (a.orig[s] >= a.nsph) { OWN(F_DTDT) = 0.; return; }
-    const double4 qi = a.Q0[s], q2i = a.Q2[s];
-    const V3 xi = v3(qi.x, qi.y, qi.z);
-    const double hi = qi.w, C4i = c4_of(hi), di = a.Q1[s].w, Ti = q2i.y, mi = q2i.x;
-    const int ci = (int)q2i.z; const ClassProps cpi = a.cls[ci];
-    const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
-    double temp = 0.;
-    for (int n = 0; n < cnt; ++n) {
-        const uint32_t e = a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s];
-        const int j = (int)(e & 0x7fffffffu); const bool ifirst = (e >> 31) != 0;
-        const double4 qj = a.Q0[j], q2j = a.Q2[j];
-        const double dj = a.Q1[j].w;
-        const int cj = (int)q2j.z; const double kj = (cj == ci) ? cpi.k_T : a.cls[cj].k_T;
-        double hh, C4;
-        if (qj.w == hi) { hh = hi; C4 = C4i; } else { hh = (hi + qj.w) / 2.0; C4 = c4_of(hh); }
-        const V3 xj = v3(qj.x, qj.y, qj.z);
-        if (ifirst) {      // i is P1: temp[i] += m
-            const V3 xij = xi - xj; const double nr = norm(xij);
-            const double GK = GK_of<KT>(a.dim, a.kt, nr / hh, hh, C4);
-            const double m = q2j.x / dj * 4. * (cpi.k_T * kj) / (cpi.k_T + kj) * (Ti - q2j.y) * dot(xij, GK * xij) / (nr * nr);
-            temp += m;
-        } else {           // i is P2: temp[i] -= m, m built with P1 = j and m_i/rho_i
-            const V3 xij = xj - xi; const double nr = norm(xij);
-            const double GK = GK_of<KT>(a.dim, a.kt, nr / hh, hh, C4);
-            const double m = mi / di * 4. * (kj * cpi.k_T) / (kj + cpi.k_T) * (q2j.y - Ti) * dot(xij, GK * xij) / (nr * nr);
-            temp -= m;
-        }
-    }
-    const double f = 1. / (di * cpi.cp_T);
-    double dTdt = f * (temp + OWN(F_QCONV) + cpi.q_source + OWN(F_QPL) * a.pl_work_heat_frac + OWN(F_QCONT));
-    if (a.contact && a.cont_heat_fric) dTdt += f * OWN(F_QFRIC);
-    OWN(F_DTDT) = dTdt;
-    // CalcThermalExpStrainRate (Particle.cpp:953-957): StrainRate += th_exp*dTdt*I
-    const double te = cpi.th_exp * dTdt;
-    OWN(F_SR) = OWN(F_SR) + te; OWN(F_SR + 1) = OWN(F_SR + 1) + te; OWN(F_SR + 2) = OWN(F_SR + 2) + te;
-}
-
-// ---- CalcKinEnergyEqn pair loop + CalcIntEnergyEqn (Domain.cpp:1752-1829, Particle.cpp:941-950) ---------------------
-template <int KT> __global__ void __launch_bounds__(128) k_energy(PairArgs a)
-{
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n) return;
-    if (a.orig[s] >= a.nsph) { OWN(F_DKIN) = 0.; return; }
+    if (a.orig[s] >= a.nsph) { if (THERM) OWN(F_DTDT) = 0.; if (EKIN) OWN(F_DKIN) = 0.; return; }
     const double4 qi = a.Q0[s], wi = a.Q1[s], q2i = a.Q2[s];
     const V3 xi = v3(qi.x, qi.y, qi.z), vi = v3(wi.x, wi.y, wi.z);
-    const double hi = qi.w, C4i = c4_of(hi), di = wi.w, Pi = q2i.w, mi = q2i.x;
+    const double hi = qi.w, C4i = c4_of(hi), di = q2i.y, Ti = q2i.z, mi = q2i.x, Pi2 = q2i.w, midi = wi.w;
+    const int ci = a.cls_of[s]; const ClassProps cpi = a.cls[ci];
     const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
-    double dk = 0.;
+    const DivC dh = divc_make(hi), dkk = divc_make(cpi.k_T + cpi.k_T);
+    const double kk_same = cpi.k_T * cpi.k_T;
+    double temp = 0., dk = 0., dd = 0.;
+    double4 qn = qi, wn = wi, q2n = q2i; uint32_t e1 = 0, e2 = 0;
+    if (PF && cnt > 0) { e1 = a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s]; const int j0 = (int)(e1 & 0x7fffffffu); qn = a.Q0[j0]; wn = a.Q1[j0];
+                         if (THERM || EKIN) q2n = a.Q2[j0];
+                         if (cnt > 1) e2 = a.nbr[(int64_t)nb_row(1, nhi, a.K) * a.cap + s]; }
     for (int n = 0; n < cnt; ++n) {
-        const uint32_t e = a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s];
+        uint32_t e; double4 qj, wj;
+        if (PF) { e = e1; qj = qn; wj = wn; } else { e = a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s]; }
         const int j = (int)(e & 0x7fffffffu); const bool ifirst = (e >> 31) != 0;
-        const double4 qj = a.Q0[j], wj = a.Q1[j], q2j = a.Q2[j];
-        const double dj = wj.w;
-        double hh, C4;
-        if (qj.w == hi) { hh = hi; C4 = C4i; } else { hh = (hi + qj.w) / 2.0; C4 = c4_of(hh); }
+        if (!PF) { qj = a.Q0[j]; wj = a.Q1[j]; }
+        double4 q2j_pf = make_double4(0., 0., 0., 0.);
+        if (THERM || EKIN) { if (PF) q2j_pf = q2n; else q2j_pf = a.Q2[j]; }
+        if (PF) {
+            if (n + 1 < cnt) { e1 = e2; const int j1 = (int)(e1 & 0x7fffffffu); qn = a.Q0[j1]; wn = a.Q1[j1]; if (THERM || EKIN) q2n = a.Q2[j1]; }
+            if (n + 2 < cnt) e2 = a.nbr[(int64_t)nb_row(n + 2, nhi, a.K) * a.cap + s];
+        }
         const V3 xj = v3(qj.x, qj.y, qj.z), vj = v3(wj.x, wj.y, wj.z);
-        if (ifirst) {
-            const V3 xij = xi - xj, vij = vi - vj;
-            const double GK = GK_of<KT>(a.dim, a.kt, norm(xij) / hh, hh, C4);
-            dk += 0.5 * q2j.x * (Pi / (di * di) + q2j.w / (dj * dj)) * dot(vij, GK * xij);
-        } else {
-            const V3 xij = xj - xi, vij = vj - vi;
-            const double GK = GK_of<KT>(a.dim, a.kt, norm(xij) / hh, hh, C4);
-            dk -= 0.5 * mi * (q2j.w / (dj * dj) + Pi / (di * di)) * dot(vij, GK * xij);
+        // x_ij with the reference's sign for this pair (P1 - P2); r, q and grad-W are even in it
+        const V3 xp = ifirst ? (xi - xj) : (xj - xi);
+        const double nr = norm(xp);
+        double hh, C4, q;
+        if (FAST) { hh = hi; C4 = C4i; q = div_c(nr, dh); }
+        else { if (qj.w == hi) { hh = hi; C4 = C4i; } else { hh = (hi + qj.w) / 2.0; C4 = c4_of(hh); } q = nr / hh; }
+        double GK;
+        if (FAST) GK = cubicGW_c(C4, q, hh); else GK = (a.kt == 0 && a.dim == 3) ? cubicGW_c(C4, q, hh) : gradW(a.dim, a.kt, q, hh);
+        const V3 gx = GK * xp;
+        if (DENS) {
+            // CalcDensInc evaluates with x_i - x_j, v_i - v_j from particle i's side; dot() of two sign-flipped vectors is bit-identical
+            const V3 vij = vi - vj;
+            const V3 xij = xi - xj;
+            const double t1 = dot(vij, GK * xij);
+            dd += wj.w * t1;
+        }
+        if (THERM || EKIN) {
+            const double4 q2j = q2j_pf;
+            if (THERM) {
+                double kj, kki, num; bool same = true;
+                if (!FAST) { const int cj = a.cls_of[j]; same = (cj == ci); kj = same ? cpi.k_T : a.cls[cj].k_T; } else kj = cpi.k_T;
+                const double xgx = dot(xp, gx);
+                if (ifirst) {      // i is P1: temp[i] += m, with m_j/rho_j
+                    const double t0 = wj.w * 4. * (same ? kk_same : (cpi.k_T * kj));
+                    const double t1 = same ? div_c(t0, dkk) : t0 / (cpi.k_T + kj);
+                    temp += t1 * (Ti - q2j.z) * xgx / (nr * nr);
+                } else {           // i is P2: temp[i] -= m, m built with P1 = j and m_i/rho_i
+                    const double t0 = midi * 4. * (same ? kk_same : (kj * cpi.k_T));
+                    const double t1 = same ? div_c(t0, dkk) : t0 / (kj + cpi.k_T);
+                    temp -= t1 * (q2j.z - Ti) * xgx / (nr * nr);
+                }
+                (void)kki; (void)num;
+            }
+            if (EKIN) {
+                const V3 vp = ifirst ? (vi - vj) : (vj - vi);
+                if (ifirst) dk += 0.5 * q2j.x * (Pi2 + q2j.w) * dot(vp, gx);
+                else        dk -= 0.5 * mi * (q2j.w + Pi2) * dot(vp, gx);
+            }
         }
     }
-    OWN(F_DKIN) = dk;
-    OWN(F_DINT) = mi / di * (OWN(F_SH) * OWN(F_SR) + 2.0 * OWN(F_SH + 3) * OWN(F_SR + 3) + 2.0 * OWN(F_SH + 5) * OWN(F_SR + 5) +
-                             OWN(F_SH + 1) * OWN(F_SR + 1) + 2.0 * OWN(F_SH + 4) * OWN(F_SR + 4) + OWN(F_SH + 2) * OWN(F_SR + 2));
+    if (THERM) {
+        const double f = 1. / (di * cpi.cp_T);
+        double dTdt = f * (temp + OWN(F_QCONV) + cpi.q_source + OWN(F_QPL) * a.pl_work_heat_frac + OWN(F_QCONT));
+        if (a.contact && a.cont_heat_fric) dTdt += f * OWN(F_QFRIC);
+        OWN(F_DTDT) = dTdt;
+        // CalcThermalExpStrainRate (Particle.cpp:953-957): StrainRate += th_exp*dTdt*I
+        const double te = cpi.th_exp * dTdt;
+        OWN(F_SR) = OWN(F_SR) + te; OWN(F_SR + 1) = OWN(F_SR + 1) + te; OWN(F_SR + 2) = OWN(F_SR + 2) + te;
+    }
+    if (EKIN) {
+        OWN(F_DKIN) = dk;
+        OWN(F_DINT) = mi / di * (OWN(F_SH) * OWN(F_SR) + 2.0 * OWN(F_SH + 3) * OWN(F_SR + 3) + 2.0 * OWN(F_SH + 5) * OWN(F_SR + 5) +
+                                 OWN(F_SH + 1) * OWN(F_SR + 1) + 2.0 * OWN(F_SH + 4) * OWN(F_SR + 4) + OWN(F_SH + 2) * OWN(F_SR + 2));
+    }
+    if (DENS) {
+        dd *= di;
+        OWN(F_DDN) = dd;
+        if (a.any_ti && cpi.TI > 0.0) {
+            S6 sg; sg.xx = OWN(F_SG); sg.yy = OWN(F_SG + 1); sg.zz = OWN(F_SG + 2); sg.xy = OWN(F_SG + 3); sg.yz = OWN(F_SG + 4); sg.xz = OWN(F_SG + 5);
+            double t[6]; tir_of(sg, di, cpi.TI, t);
+            for (int k = 0; k < 6; ++k) OWN(F_TN + k) = t[k];
+        }
+    }
 }
 
 PairArgs make_args(wf_ctx *c)
 {
     PairArgs a; a.n = c->n; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
-    a.nbr = c->nbr; a.nb_cnt = c->nb_cnt; a.nb_hi = c->nb_hi; a.orig = c->Ip(I_ORIG);
+    a.nbr = c->nbr; a.nb_cnt = c->nb_cnt; a.nb_hi = c->nb_hi; a.orig = c->Ip(I_ORIG); a.cls_of = c->Ip(I_CLS);
     a.Q0 = c->Q0[c->cur]; a.Q1 = c->Q1[c->cur]; a.Q2 = c->Q2[c->cur]; a.S0 = c->S0[c->cur]; a.S1 = c->S1[c->cur]; a.S2 = c->S2[c->cur];
     a.F = c->F[c->cur]; a.cls = c->d_classes; a.mats = c->d_mats; a.dt = c->dt; a.any_ti = c->any_ti ? 1 : 0;
     a.thermal = c->prm.thermal_solver; a.pl_heating = c->prm.pl_heating; a.contact = c->prm.contact; a.cont_heat_fric = c->prm.cont_heat_fric;
@@ -405,56 +493,83 @@ PairArgs make_args(wf_ctx *c)
     return a;
 }
 
+inline bool use_pf(const wf_ctx *c) { return (c->prm.tuning & 1) == 0; }     // bit 0 of wf_params::tuning switches the software pipeline OFF
+inline bool fast_path(const wf_ctx *c) { return c->prm.kernel_type == 0 && c->prm.dimension == 3 && c->uniform_h && c->single_class; }
+
 } // namespace
 
 namespace wf {
 
 #define WF_PAIR_PRECHECK(c) if (!(c)->nbr) return fail((c), WF_ERR_ARG, "pair kernel called before the first neighbour build")
+// launch KERNEL<targs..., PF> with PF = software pipeline on/off; grid of one thread per slot, 128 threads per block
+#define WF_LAUNCH_PF(KERNEL, ...) do { if (pf) KERNEL<__VA_ARGS__, true><<<g, 128, 0, c->stream>>>(a); else KERNEL<__VA_ARGS__, false><<<g, 128, 0, c->stream>>>(a); } while (0)
 
+// CalcDensInc + DensReduction + rho update. If the previous step's k_post already holds this step's density rate and TIR
+// (nothing moved in between) only the per-particle prologue runs.
 int pair_density(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128);
-    {   ProfScope ps(c, PK_DENSITY);
-        if (a.kt == 0 && a.dim == 3) k_density<0><<<g, 128, 0, c->stream>>>(a); else k_density<1><<<g, 128, 0, c->stream>>>(a);
-        WF_LAUNCH_CHECK(c);
-        k_density_update<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); }
-    c->launches += 2;
+    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
+    ProfScope ps(c, PK_DENSITY);
+    if (!c->dens_valid) {
+        if (fast_path(c)) WF_LAUNCH_PF(k_post, true, false, false, true); else WF_LAUNCH_PF(k_post, false, false, false, true);
+        WF_LAUNCH_CHECK(c); c->launches++;
+    }
+    k_prologue<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    c->dens_valid = false;
     return 0;
 }
 int pair_rate_stress(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128);
+    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_RATE_STRESS);
-    if (a.kt == 0 && a.dim == 3) k_rate_stress<0><<<g, 128, 0, c->stream>>>(a); else k_rate_stress<1><<<g, 128, 0, c->stream>>>(a);
+    if (fast_path(c)) WF_LAUNCH_PF(k_rate_stress, true); else WF_LAUNCH_PF(k_rate_stress, false);
     WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
 int pair_accel(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128);
+    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_ACCEL);
-    const bool fast = (a.kt == 0 && a.dim == 3);
+    const bool fast = fast_path(c);
+    const bool mb3 = (c->prm.tuning & 2) == 0;        // 3 resident blocks per SM (168 registers) by default; bit 1 of wf_params::tuning selects 4 (128 registers, spills)
     switch (a.gt) {
-    case 0: if (fast) k_accel<0, 0><<<g, 128, 0, c->stream>>>(a); else k_accel<1, 0><<<g, 128, 0, c->stream>>>(a); break;
-    case 1: if (fast) k_accel<0, 1><<<g, 128, 0, c->stream>>>(a); else k_accel<1, 1><<<g, 128, 0, c->stream>>>(a); break;
-    default: if (fast) k_accel<0, 2><<<g, 128, 0, c->stream>>>(a); else k_accel<1, 2><<<g, 128, 0, c->stream>>>(a); break;
+    case 0: if (fast) { if (c->prm.tuning & 4) WF_LAUNCH_PF(k_accel, true, 0, 2); else if (mb3) WF_LAUNCH_PF(k_accel, true, 0, 3); else WF_LAUNCH_PF(k_accel, true, 0, 4); }
+            else WF_LAUNCH_PF(k_accel, false, 0, 4); break;
+    case 1: if (fast) WF_LAUNCH_PF(k_accel, true, 1, 4); else WF_LAUNCH_PF(k_accel, false, 1, 4); break;
+    default: if (fast) WF_LAUNCH_PF(k_accel, true, 2, 4); else WF_LAUNCH_PF(k_accel, false, 2, 4); break;
     }
     WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
+// CalcPlasticWorkHeat + ThermalCalcs, then CalcKinEnergyEqn + CalcIntEnergyEqn, then next step's density rate: one walk
+int pair_post(wf_ctx *c)
+{
+    WF_PAIR_PRECHECK(c);
+    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
+    ProfScope ps(c, PK_THERMAL);
+    const bool th = c->prm.thermal_solver != 0;
+    if (th || c->prm.pl_heating) { k_thermal_pre<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
+    const bool fast = fast_path(c);
+    if (th) { if (fast) WF_LAUNCH_PF(k_post, true, true, true, true); else WF_LAUNCH_PF(k_post, false, true, true, true); }
+    else    { if (fast) WF_LAUNCH_PF(k_post, true, false, true, true); else WF_LAUNCH_PF(k_post, false, false, true, true); }
+    WF_LAUNCH_CHECK(c); c->launches++;
+    c->dens_valid = true;
+    return 0;
+}
+// stand-alone phases of the C ABI (wf_thermal, wf_energy): same kernel, one family of sums each
 int pair_thermal(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
     if (!c->prm.thermal_solver && !c->prm.pl_heating) return 0;
-    PairArgs a = make_args(c);
+    PairArgs a = make_args(c); const bool pf = use_pf(c);
     ProfScope ps(c, PK_THERMAL);
     k_thermal_pre<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
     if (c->prm.thermal_solver) {
         const int g = grid_for(c->n, 128);
-        if (a.kt == 0 && a.dim == 3) k_thermal<0><<<g, 128, 0, c->stream>>>(a); else k_thermal<1><<<g, 128, 0, c->stream>>>(a);
+        if (fast_path(c)) WF_LAUNCH_PF(k_post, true, true, false, false); else WF_LAUNCH_PF(k_post, false, true, false, false);
         WF_LAUNCH_CHECK(c); c->launches++;
     }
     return 0;
@@ -462,9 +577,9 @@ int pair_thermal(wf_ctx *c)
 int pair_energy(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128);
+    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_ENERGY);
-    if (a.kt == 0 && a.dim == 3) k_energy<0><<<g, 128, 0, c->stream>>>(a); else k_energy<1><<<g, 128, 0, c->stream>>>(a);
+    if (fast_path(c)) WF_LAUNCH_PF(k_post, true, false, true, false); else WF_LAUNCH_PF(k_post, false, false, true, false);
     WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }

@@ -79,7 +79,7 @@ __global__ void k_contact(StepArgs a, ContactArgs k)
     if (cnt > 0) {
         const double4 q = a.Q0[s], w = a.Q1[s], q2 = a.Q2[s];
         const V3 x = v3(q.x, q.y, q.z), v = v3(w.x, w.y, w.z);
-        const double h = q.w, Mass = q2.x, dens = w.w, dt = a.dt;
+        const double h = q.w, Mass = q2.x, dens = q2.y, dt = a.dt;
         V3 acc = v3(OWN(F_AX), OWN(F_AY), OWN(F_AZ));
         for (int c = 0; c < cnt; ++c) {
             const int e = k.cont[(int64_t)c * a.cap + s];
@@ -127,7 +127,7 @@ __global__ void k_contact(StepArgs a, ContactArgs k)
                     csum += norm(cf);
                     creac += dot(acc, n2) * Mass;
                     cext += dot(cf, v2);
-                    if (k.cont_heat_cond) qcont = dens * k.contact_hc * dS2 * (0.0 - q2.y) / Mass;   // mesh particle T stays 0 unless conduction to the tool is modelled
+                    if (k.cont_heat_cond) qcont = dens * k.contact_hc * dS2 * (0.0 - q2.z) / Mass;   // mesh particle T stays 0 unless conduction to the tool is modelled
                 }
             }
         }
@@ -184,14 +184,14 @@ __global__ void __launch_bounds__(256) k_reduce_partial(StepArgs a, int first_fe
         acc[R_DKIN] += OWN(F_DKIN);
         acc[R_MAXPL] = fmax(acc[R_MAXPL], OWN(F_PLS));
         if (o < a.nsph) {
-            const double m = a.Q2[s].x, d = a.Q1[s].w;
+            const double m = a.Q2[s].x, d = a.Q2[s].y;
             acc[R_PLW] += m / d * OWN(F_QPL);
             acc[R_FRIC] += OWN(F_QFRIC) * m / d;
             acc[R_COND] += OWN(F_QCONT) * m / d;
             acc[R_CSUM] += OWN(F_CSUM); acc[R_CREAC] += OWN(F_CREAC); acc[R_CEXT] += OWN(F_CEXT);
             const double dx = OWN(F_DX), dy = OWN(F_DY), dz = OWN(F_DZ);
             acc[R_MD0] = fmax(acc[R_MD0], dx * dx); acc[R_MD1] = fmax(acc[R_MD1], dy * dy); acc[R_MD2] = fmax(acc[R_MD2], dz * dz);
-            const double T = a.Q2[s].y; acc[R_TMAX] = fmax(acc[R_TMAX], T); acc[R_TMIN] = fmin(acc[R_TMIN], T);
+            const double T = a.Q2[s].z; acc[R_TMAX] = fmax(acc[R_TMAX], T); acc[R_TMIN] = fmin(acc[R_TMIN], T);
         }
         if (o < first_fem) acc[R_DINT] += OWN(F_DINT);
     }
@@ -248,8 +248,11 @@ __global__ void k_init_pressure(StepArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
-    const double4 q2 = a.Q2[s]; const ClassProps cp = a.cls[(int)q2.z];
-    ((double *)&a.Q2[s])[3] = eos(cp.PresEq, cp.Cs, cp.P0, a.Q1[s].w, cp.RefDensity);
+    const double4 q2 = a.Q2[s]; const ClassProps cp = a.cls[OWNI(I_CLS)];
+    if (OWNI(I_ORIG) >= a.nsph) { OWN(F_PRES) = eos(cp.PresEq, cp.Cs, cp.P0, 0.0, cp.RefDensity); return; }
+    const double P = eos(cp.PresEq, cp.Cs, cp.P0, q2.y, cp.RefDensity);
+    OWN(F_PRES) = P;
+    ((double *)&a.Q2[s])[3] = P / (q2.y * q2.y);
 }
 
 StepArgs make_step_args(wf_ctx *c)
@@ -283,6 +286,7 @@ static int bc_move(wf_ctx *c, int mode, int pk)
     StepArgs a = make_step_args(c);
     if ((mode & 9) && !c->meshes.empty()) { k_mesh_ramp<<<1, 32, 0, c->stream>>>(c->dm.motion, (int)c->meshes.size(), c->d_sc); WF_LAUNCH_CHECK(c); c->launches++; }
     k_bc_move<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a, mode); WF_LAUNCH_CHECK(c); c->launches++;
+    c->dens_valid = false;       // x / v changed after the last k_post (if any): its prepared density rate is stale
     return 0;
 }
 int apply_bcs_impl(wf_ctx *c) { if (c->n_bcs == 0 && c->meshes.empty()) return 0; return bc_move(c, 1, PK_BC); }
@@ -334,7 +338,7 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_solver_init: no particles");
     if (!(dt > 0.0)) return fail(c, WF_ERR_ARG, "wf_solver_init: dt must be > 0");
     cudaSetDevice(c->device);
-    c->dt = dt; c->time = 0.0; c->ts_i = 0; c->isfirst = true; c->isyielding = false; c->steps = 0;
+    c->dt = dt; c->time = 0.0; c->ts_i = 0; c->isfirst = true; c->isyielding = false; c->steps = 0; c->dens_valid = false; c->in_step = false;
     k_set_time<<<1, 1, 0, c->stream>>>(c->d_sc, 0.0, dt); WF_LAUNCH_CHECK(c);
     StepArgs a = make_step_args(c);
     k_init_pressure<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c);       // InitialChecks
@@ -440,8 +444,7 @@ extern "C" int wf_fraser_stage_b2(wf_ctx *c) { WF_NEED_READY(c); return move_vel
 extern "C" int wf_fraser_stage_c(wf_ctx *c)
 {
     WF_NEED_READY(c);
-    WF_CHECK(pair_thermal(c));
-    WF_CHECK(pair_energy(c));
+    WF_CHECK(pair_post(c));            // CalcPlasticWorkHeat + ThermalCalcs + CalcKinEnergyEqn + CalcIntEnergyEqn (+ next density rate)
     return finish_step(c);
 }
 

@@ -73,6 +73,7 @@ def context_from_case(case, device=0):
     p.friction_sta = float(case.get("friction_sta", 0.0)); p.friction_dyn = float(case.get("friction_dyn", 0.0))
     p.pfac = float(case.get("PFAC", 0.4)); p.dfac = float(case.get("DFAC", 0.0))
     p.cont_heat_fric = int(case.get("cont_heat_fric", 0)); p.cont_heat_cond = int(case.get("cont_heat_cond", 0))
+    p.tuning = int(case.get("tuning", int(__import__("os").environ.get("WF_TUNING", "0"))))
     if int(case.get("gradKernelCorr", 0)):
         raise api.WeldformError("gradKernelCorr is not implemented (SURVEY.md section 8f item 2)")
     ctx.set_params(p)

@@ -1,0 +1,390 @@
+// Multi-GPU support: one process per GPU, 1-D slab decomposition of the reference's cell grid along its longest axis,
+// NCCL point-to-point halos over NVLink. The reference is single-process ("distributed
+// communication backend: none"); this is the B200-native scaling path of BASELINE.json's north_star.
+//
+//   * ownership: rank r owns the cell layers [layer_lo, layer_hi) of the slowest axis, balanced by particle count;
+//   * at every neighbour rebuild: particles that left the slab migrate to the adjacent rank (whole state, packed), the
+//     local region is re-sorted by cell, and the one-cell-thick boundary layers -- CONTIGUOUS slices of the cell-sorted
+//     arrays, because the slab axis is the most significant sort digit -- are sent to the neighbours' halo regions;
+//   * per step: three refreshes of those same slices, dictated by the data dependencies of the Fraser step
+//       m/rho            (after the density update, before the rate-tensor pass)
+//       m,rho,P/rho^2, sigma/rho^2, TIR   (after the constitutive update, before the momentum pass)
+//       x, v, T          (after the move / temperature update, before the conduction + energy + next-density pass)
+//     zero-copy: ncclSend/ncclRecv straight from/into the particle arrays, no pack/unpack kernels;
+//   * global scalars (max pl_strain, max_disp, energies ...): one 32-double all-gather per step, reduced in rank order
+//     on every rank (deterministic, identical on all ranks).
+// Neighbour lists keep the reference's discovery order (it depends only on global cell coordinates and creation
+// indices), so every per-particle result is bit-identical to the single-GPU run.
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- inside a torch process that is torch's own copy), so the library
+// has no link-time dependency on it and single-GPU users never touch it.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "wf_internal.cuh"
+
+using namespace wf;
+
+namespace {
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false; std::string err;
+};
+
+NcclApi *nccl_api()
+{
+    static NcclApi a; static bool tried = false;
+    if (tried) return &a;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { a.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return &a; }
+#define WF_SYM(name) do { *(void **)(&a.name) = dlsym(h, "nccl" #name); if (!a.name) { a.err = "libnccl.so.2 lacks nccl" #name; return &a; } } while (0)
+    WF_SYM(GetUniqueId); WF_SYM(CommInitRank); WF_SYM(CommDestroy); WF_SYM(Send); WF_SYM(Recv); WF_SYM(AllGather); WF_SYM(AllReduce);
+    WF_SYM(GroupStart); WF_SYM(GroupEnd); WF_SYM(GetErrorString);
+#undef WF_SYM
+    a.ok = true;
+    return &a;
+}
+
+#define WF_NCCL(c, expr) do { ncclResult_t r_ = (expr); if (r_ != ncclSuccess) return wf::fail((c), WF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, nccl_api()->GetErrorString(r_), __FILE__, __LINE__); } while (0)
+
+struct QPtrs { double4 *q[6]; };
+
+// whole-state pack / unpack of migrating particles: doubles [field][k]; fields = 24 gathered components, F_COUNT own
+// doubles, I_COUNT own ints (stored as doubles, exact)
+__global__ void k_pack(QPtrs Q, const double *F, const int *I, int64_t cap, const int *slots, int n, double *out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= n) return;
+    const int f = blockIdx.y; const int64_t s = slots[k];
+    double v;
+    if (f < 24) v = ((const double *)&Q.q[f >> 2][s])[f & 3];
+    else if (f < 24 + F_COUNT) v = F[(int64_t)(f - 24) * cap + s];
+    else v = (double)I[(int64_t)(f - 24 - F_COUNT) * cap + s];
+    out[(int64_t)f * n + k] = v;
+}
+__global__ void k_unpack(QPtrs Q, double *F, int *I, int64_t cap, int64_t base, int n, const double *in)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x; if (k >= n) return;
+    const int f = blockIdx.y; const int64_t s = base + k;
+    const double v = in[(int64_t)f * n + k];
+    if (f < 24) ((double *)&Q.q[f >> 2][s])[f & 3] = v;
+    else if (f < 24 + F_COUNT) F[(int64_t)(f - 24) * cap + s] = v;
+    else I[(int64_t)(f - 24 - F_COUNT) * cap + s] = (int)v;
+}
+// first slot whose sorted key has a cell index >= target (binary search, one thread per target)
+__global__ void k_lower_bound(const unsigned long long *keys, int64_t n, const long long *targets, int nt, long long *out)
+{
+    const int t = threadIdx.x; if (t >= nt) return;
+    const unsigned long long tk = (unsigned long long)targets[t] << 32;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (keys[mid] < tk) lo = mid + 1; else hi = mid; }
+    out[t] = lo;
+}
+__global__ void k_iota_orig(int64_t n, const int *orig, int *keys, int *vals)
+{ int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (s < n) { keys[s] = orig[s]; vals[s] = (int)s; } }
+__global__ void k_set_lid(int64_t n, const int *sorted_slots, int *slot_of, int *lid)
+{ int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (k < n) { const int s = sorted_slots[k]; slot_of[k] = s; lid[s] = (int)k; } }
+
+QPtrs qptrs(wf_ctx *c, int buf) { QPtrs q; q.q[0] = c->Q0[buf]; q.q[1] = c->Q1[buf]; q.q[2] = c->Q2[buf]; q.q[3] = c->S0[buf]; q.q[4] = c->S1[buf]; q.q[5] = c->S2[buf]; return q; }
+
+} // namespace
+
+namespace wf {
+
+// balanced contiguous split of the slow-axis layers by particle count (same code for the library and the host planner)
+static void balance_layers(const std::vector<long long> &hist, int nranks, std::vector<int> &bounds)
+{
+    const int L = (int)hist.size();
+    long long total = 0; for (long long h : hist) total += h;
+    bounds.assign(nranks + 1, 0); bounds[nranks] = L;
+    long long cum = 0; int r = 1;
+    for (int l = 0; l < L && r < nranks; ++l) {
+        cum += hist[l];
+        // close rank r-1 after layer l when its share is reached, keeping at least one layer for every remaining rank
+        while (r < nranks && (cum * nranks >= (long long)r * total) && (l + 1) <= L - (nranks - r)) { bounds[r] = std::max(l + 1, bounds[r - 1] + 1); ++r; }
+    }
+    for (; r < nranks; ++r) bounds[r] = std::max(bounds[r - 1] + 1, L - (nranks - r));
+}
+
+int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax)
+{
+    if (c->comm.nranks <= 1) return 0;
+    NcclApi *A = nccl_api();
+    double h[8] = { -BL[0], -BL[1], -BL[2], TR[0], TR[1], TR[2], *hmax, 0.0 };
+    WF_CHECK(ensure_stage(c, 256));
+    WF_CUDA(c, cudaMemcpyAsync(c->stage, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    WF_NCCL(c, A->AllReduce(c->stage, c->stage, 8, ncclDouble, ncclMax, (ncclComm_t)c->comm.nccl, c->stream));
+    WF_CUDA(c, cudaMemcpyAsync(h, c->stage, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 3; ++k) { BL[k] = -h[k]; TR[k] = h[3 + k]; }
+    *hmax = h[6];
+    return 0;
+}
+
+int comm_plan_layers(wf_ctx *c, const std::vector<long long> &hist_local)
+{
+    if (c->comm.nranks <= 1) return 0;
+    NcclApi *A = nccl_api();
+    const size_t L = hist_local.size();
+    if ((int)L < c->comm.nranks) return fail(c, WF_ERR_ARG, "slab decomposition: %d cell layers along the longest axis for %d ranks", (int)L, c->comm.nranks);
+    WF_CHECK(ensure_stage(c, L * sizeof(long long)));
+    std::vector<long long> hist(hist_local);
+    WF_CUDA(c, cudaMemcpyAsync(c->stage, hist.data(), L * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    WF_NCCL(c, A->AllReduce(c->stage, c->stage, L, ncclInt64, ncclSum, (ncclComm_t)c->comm.nccl, c->stream));
+    WF_CUDA(c, cudaMemcpyAsync(hist.data(), c->stage, L * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<int> b; balance_layers(hist, c->comm.nranks, b);
+    c->comm.layer_lo = b[c->comm.rank]; c->comm.layer_hi = b[c->comm.rank + 1];
+    return 0;
+}
+
+// sends/receives the boundary slices of the selected gathered arrays (zero-copy); halo regions were sized at the rebuild
+int comm_halo_refresh(wf_ctx *c, int sets)
+{
+    wf_ctx::Comm &m = c->comm;
+    if (m.nranks <= 1) return 0;
+    NcclApi *A = nccl_api();
+    ProfScope ps(c, PK_HALO);
+    double4 *arr[6]; int na = 0; const int b = c->cur;
+    if (sets & HALO_Q0) arr[na++] = c->Q0[b];
+    if (sets & HALO_Q1) arr[na++] = c->Q1[b];
+    if (sets & HALO_Q2) arr[na++] = c->Q2[b];
+    if (sets & HALO_S) { arr[na++] = c->S0[b]; arr[na++] = c->S1[b]; arr[na++] = c->S2[b]; }
+    ncclComm_t comm = (ncclComm_t)m.nccl;
+    WF_NCCL(c, A->GroupStart());
+    for (int k = 0; k < na; ++k) {
+        if (m.rank > 0) {
+            if (m.send_lo_n) WF_NCCL(c, A->Send(arr[k] + m.send_lo_start, 4 * m.send_lo_n, ncclDouble, m.rank - 1, comm, c->stream));
+            if (m.halo_lo_n) WF_NCCL(c, A->Recv(arr[k] + m.halo_lo_start, 4 * m.halo_lo_n, ncclDouble, m.rank - 1, comm, c->stream));
+        }
+        if (m.rank < m.nranks - 1) {
+            if (m.send_hi_n) WF_NCCL(c, A->Send(arr[k] + m.send_hi_start, 4 * m.send_hi_n, ncclDouble, m.rank + 1, comm, c->stream));
+            if (m.halo_hi_n) WF_NCCL(c, A->Recv(arr[k] + m.halo_hi_start, 4 * m.halo_hi_n, ncclDouble, m.rank + 1, comm, c->stream));
+        }
+    }
+    WF_NCCL(c, A->GroupEnd());
+    c->launches += 1;
+    return 0;
+}
+
+int comm_gather_scalars(wf_ctx *c, int nvals)
+{
+    wf_ctx::Comm &m = c->comm;
+    if (m.nranks <= 1) return 0;
+    NcclApi *A = nccl_api();
+    WF_NCCL(c, A->AllGather(m.d_rank, m.d_all, (size_t)nvals, ncclDouble, (ncclComm_t)m.nccl, c->stream));
+    return 0;
+}
+
+static int exchange_counts(wf_ctx *c, const int send[2], int recv[2])
+{
+    // send[0] -> rank-1, send[1] -> rank+1; recv[0] <- rank-1, recv[1] <- rank+1
+    wf_ctx::Comm &m = c->comm; NcclApi *A = nccl_api(); ncclComm_t comm = (ncclComm_t)m.nccl;
+    int h[4] = { send[0], send[1], 0, 0 };
+    WF_CUDA(c, cudaMemcpyAsync(m.d_cnt + 4, h, 4 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    WF_NCCL(c, A->GroupStart());
+    if (m.rank > 0) { WF_NCCL(c, A->Send(m.d_cnt + 4, 1, ncclInt32, m.rank - 1, comm, c->stream)); WF_NCCL(c, A->Recv(m.d_cnt + 6, 1, ncclInt32, m.rank - 1, comm, c->stream)); }
+    if (m.rank < m.nranks - 1) { WF_NCCL(c, A->Send(m.d_cnt + 5, 1, ncclInt32, m.rank + 1, comm, c->stream)); WF_NCCL(c, A->Recv(m.d_cnt + 7, 1, ncclInt32, m.rank + 1, comm, c->stream)); }
+    WF_NCCL(c, A->GroupEnd());
+    WF_CUDA(c, cudaMemcpyAsync(h, m.d_cnt + 4, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    recv[0] = m.rank > 0 ? h[2] : 0; recv[1] = m.rank < m.nranks - 1 ? h[3] : 0;
+    return 0;
+}
+
+// Phase 1 of the multi-GPU neighbour build (before the sort): emigrants were listed by k_cell_keys_mig in
+// d_emig[dir*emig_cap ..] with counts in d_cnt[0..1]; ship them, append the immigrants at [n_loc, n_loc + n_in).
+// Returns the number of slots to sort in *n_sort and the number of emigrants in *n_out.
+int comm_migrate(wf_ctx *c, int64_t *n_sort, int64_t *n_out)
+{
+    wf_ctx::Comm &m = c->comm; NcclApi *A = nccl_api(); ncclComm_t comm = (ncclComm_t)m.nccl;
+    int out[2] = { 0, 0 }, in[2] = { 0, 0 };
+    WF_CUDA(c, cudaMemcpyAsync(out, m.d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (out[0] > m.emig_cap || out[1] > m.emig_cap) return fail(c, WF_ERR_NOMEM, "migration: %d/%d particles leave the slab at once (capacity %lld)", out[0], out[1], (long long)m.emig_cap);
+    if (m.rank == 0 && out[0]) return fail(c, WF_ERR_ARG, "migration: %d particles left the cell grid below rank 0", out[0]);
+    if (m.rank == m.nranks - 1 && out[1]) return fail(c, WF_ERR_ARG, "migration: %d particles left the cell grid above the last rank", out[1]);
+    WF_CHECK(exchange_counts(c, out, in));
+    const int NF = 24 + F_COUNT + I_COUNT;
+    const int64_t total_in = (int64_t)in[0] + in[1];
+    if (c->n_loc + total_in > c->cap) return fail(c, WF_ERR_NOMEM, "migration: %lld local + %lld incoming particles exceed the %lld allocated slots", (long long)c->n_loc, (long long)total_in, (long long)c->cap);
+    const size_t need = (size_t)NF * std::max(std::max(out[0], out[1]), std::max(in[0], in[1])) * sizeof(double);
+    if (need > m.stage_cap) {
+        for (int d = 0; d < 2; ++d) { cudaFree(m.stage_send[d]); cudaFree(m.stage_recv[d]); m.stage_send[d] = m.stage_recv[d] = nullptr; }
+        const size_t cap2 = need * 2 + 4096;
+        for (int d = 0; d < 2; ++d) { WF_CUDA(c, cudaMalloc(&m.stage_send[d], cap2)); WF_CUDA(c, cudaMalloc(&m.stage_recv[d], cap2)); }
+        m.stage_cap = cap2;
+    }
+    const int b = c->cur;
+    for (int d = 0; d < 2; ++d) if (out[d]) {
+        dim3 g((out[d] + 127) / 128, NF);
+        k_pack<<<g, 128, 0, c->stream>>>(qptrs(c, b), c->F[b], c->I[b], c->cap, m.d_emig + (int64_t)d * m.emig_cap, out[d], m.stage_send[d]);
+        WF_LAUNCH_CHECK(c); c->launches++;
+    }
+    if (out[0] || out[1] || in[0] || in[1]) {
+        WF_NCCL(c, A->GroupStart());
+        if (out[0]) WF_NCCL(c, A->Send(m.stage_send[0], (size_t)NF * out[0], ncclDouble, m.rank - 1, comm, c->stream));
+        if (in[0]) WF_NCCL(c, A->Recv(m.stage_recv[0], (size_t)NF * in[0], ncclDouble, m.rank - 1, comm, c->stream));
+        if (out[1]) WF_NCCL(c, A->Send(m.stage_send[1], (size_t)NF * out[1], ncclDouble, m.rank + 1, comm, c->stream));
+        if (in[1]) WF_NCCL(c, A->Recv(m.stage_recv[1], (size_t)NF * in[1], ncclDouble, m.rank + 1, comm, c->stream));
+        WF_NCCL(c, A->GroupEnd());
+    }
+    int64_t base = c->n_loc;
+    for (int d = 0; d < 2; ++d) if (in[d]) {
+        dim3 g((in[d] + 127) / 128, NF);
+        k_unpack<<<g, 128, 0, c->stream>>>(qptrs(c, b), c->F[b], c->I[b], c->cap, base, in[d], m.stage_recv[d]);
+        WF_LAUNCH_CHECK(c); c->launches++;
+        base += in[d];
+    }
+    m.migrated_out += out[0] + out[1]; m.migrated_in += total_in;
+    *n_sort = c->n_loc + total_in; *n_out = (int64_t)out[0] + out[1];
+    return 0;
+}
+
+// Phase 2 (after sort + permutation of the local region, n_loc final): boundary slices, halo sizes, first halo fill
+// of all gathered arrays + creation index / ID / class of the halo particles.
+int comm_halo_setup(wf_ctx *c, const unsigned long long *sorted_keys)
+{
+    wf_ctx::Comm &m = c->comm; NcclApi *A = nccl_api(); ncclComm_t comm = (ncclComm_t)m.nccl;
+    const long long plane = (long long)c->CellNo[c->ax_mid] * c->CellNo[c->ax_fast];
+    long long tg[4] = { (long long)m.layer_lo * plane, (long long)(m.layer_lo + 1) * plane, (long long)(m.layer_hi - 1) * plane, (long long)m.layer_hi * plane };
+    long long *d_t = (long long *)(m.d_cnt + 8), res[4];
+    WF_CUDA(c, cudaMemcpyAsync(d_t, tg, sizeof(tg), cudaMemcpyHostToDevice, c->stream));
+    k_lower_bound<<<1, 32, 0, c->stream>>>(sorted_keys, c->n_loc, d_t, 4, d_t + 4); WF_LAUNCH_CHECK(c);
+    WF_CUDA(c, cudaMemcpyAsync(res, d_t + 4, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    m.send_lo_start = res[0]; m.send_lo_n = (m.rank > 0) ? res[1] - res[0] : 0;
+    m.send_hi_start = res[2]; m.send_hi_n = (m.rank < m.nranks - 1) ? res[3] - res[2] : 0;
+    int snd[2] = { (int)m.send_lo_n, (int)m.send_hi_n }, rcv[2];
+    WF_CHECK(exchange_counts(c, snd, rcv));
+    m.halo_lo_start = c->n_loc; m.halo_lo_n = rcv[0];
+    m.halo_hi_start = c->n_loc + rcv[0]; m.halo_hi_n = rcv[1];
+    c->n = c->n_loc + rcv[0] + rcv[1];
+    if (c->n > c->cap) return fail(c, WF_ERR_NOMEM, "halo: %lld local + %d + %d halo particles exceed the %lld allocated slots", (long long)c->n_loc, rcv[0], rcv[1], (long long)c->cap);
+    m.halo_bytes_step = 8LL * 32 * (m.send_lo_n + m.send_hi_n);
+    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2 | HALO_S));
+    const int ifields[3] = { I_ORIG, I_ID, I_CLS };
+    WF_NCCL(c, A->GroupStart());
+    for (int k = 0; k < 3; ++k) {
+        int *arr = c->Ip(ifields[k]);
+        if (m.rank > 0) { if (m.send_lo_n) WF_NCCL(c, A->Send(arr + m.send_lo_start, m.send_lo_n, ncclInt32, m.rank - 1, comm, c->stream));
+                          if (m.halo_lo_n) WF_NCCL(c, A->Recv(arr + m.halo_lo_start, m.halo_lo_n, ncclInt32, m.rank - 1, comm, c->stream)); }
+        if (m.rank < m.nranks - 1) { if (m.send_hi_n) WF_NCCL(c, A->Send(arr + m.send_hi_start, m.send_hi_n, ncclInt32, m.rank + 1, comm, c->stream));
+                                     if (m.halo_hi_n) WF_NCCL(c, A->Recv(arr + m.halo_hi_start, m.halo_hi_n, ncclInt32, m.rank + 1, comm, c->stream)); }
+    }
+    WF_NCCL(c, A->GroupEnd());
+    return 0;
+}
+
+// local index (position in ascending creation-index order of this rank's particles) <-> slot
+int comm_local_index(wf_ctx *c)
+{
+    const int64_t n = c->n_loc; cudaStream_t st = c->stream;
+    int *k_in = c->vals[0], *v_in = c->vals[0] + 0;   // reuse the sort buffers: keys need int buffers of their own
+    (void)k_in; (void)v_in;
+    int *buf = nullptr; const size_t bytes = 4 * (size_t)n * sizeof(int);
+    WF_CHECK(ensure_stage(c, bytes + 256));
+    buf = (int *)c->stage;
+    int *ko = buf, *vo = buf + n, *ks = buf + 2 * n, *vs = buf + 3 * n;
+    k_iota_orig<<<grid_for(n, 256), 256, 0, st>>>(n, c->Ip(I_ORIG), ko, vo); WF_LAUNCH_CHECK(c);
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, ko, ks, vo, vs, (int)n, 0, 32, st);
+    if (need > c->cub_tmp_bytes) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; WF_CUDA(c, cudaMalloc(&c->cub_tmp, need)); c->cub_tmp_bytes = need; }
+    WF_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, need, ko, ks, vo, vs, (int)n, 0, 32, st));
+    k_set_lid<<<grid_for(n, 256), 256, 0, st>>>(n, vs, c->slot_of, c->Ip(I_LID)); WF_LAUNCH_CHECK(c);
+    c->launches += 3;
+    return 0;
+}
+
+} // namespace wf
+
+// ================================================================================================================
+extern "C" int wf_comm_unique_id(void *out128)
+{
+    if (!out128) return WF_ERR_ARG;
+    NcclApi *A = nccl_api();
+    if (!A->ok) return wf::fail(nullptr, WF_ERR_UNSUPPORTED, "NCCL unavailable: %s", A->err.c_str());
+    ncclUniqueId id; ncclResult_t r = A->GetUniqueId(&id);
+    if (r != ncclSuccess) return wf::fail(nullptr, WF_ERR_CUDA, "ncclGetUniqueId: %s", A->GetErrorString(r));
+    std::memcpy(out128, id.internal, NCCL_UNIQUE_ID_BYTES);
+    return 0;
+}
+
+extern "C" int wf_comm_init(wf_ctx *c, int rank, int nranks, const void *id128)
+{
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return WF_ERR_ARG;
+    if (c->have_particles) return wf::fail(c, WF_ERR_ARG, "wf_comm_init: call before wf_set_particles");
+    c->comm.rank = rank; c->comm.nranks = nranks;
+    if (nranks == 1) return 0;
+    if (!id128) return WF_ERR_ARG;
+    NcclApi *A = nccl_api();
+    if (!A->ok) return wf::fail(c, WF_ERR_UNSUPPORTED, "NCCL unavailable: %s", A->err.c_str());
+    cudaSetDevice(c->device);
+    ncclUniqueId id; std::memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    ncclComm_t comm;
+    WF_NCCL(c, A->CommInitRank(&comm, nranks, id, rank));
+    c->comm.nccl = comm;
+    WF_CUDA(c, cudaMalloc(&c->comm.d_cnt, 64 * sizeof(int) + 16 * sizeof(long long)));
+    WF_CUDA(c, cudaMemset(c->comm.d_cnt, 0, 64 * sizeof(int) + 16 * sizeof(long long)));
+    WF_CUDA(c, cudaMalloc(&c->comm.d_all, (size_t)nranks * 32 * sizeof(double)));
+    return 0;
+}
+
+extern "C" int wf_comm_info(wf_ctx *c, int64_t out[8])
+{
+    if (!c || !out) return WF_ERR_ARG;
+    out[0] = c->n_loc; out[1] = c->n - c->n_loc; out[2] = c->comm.migrated_out; out[3] = c->comm.migrated_in;
+    out[4] = c->comm.layer_lo; out[5] = c->comm.layer_hi; out[6] = c->comm.halo_bytes_step; out[7] = c->CellNo[c->ax_slow];
+    return 0;
+}
+
+// Host-side planner (no GPU, no NCCL): the slab a particle set would be split into by `nranks` ranks -- the same grid
+// (Neighbour.cpp:10-139) and the same balancing code the library uses. rank_of[i] in [0, nranks), bounds[nranks+1] layers.
+extern "C" int wf_plan_slabs(const double *x, const double *h, int64_t n, int kernel_type, const double dom_min[3], const double dom_max[3],
+                             int nranks, int32_t *rank_of, int32_t *bounds)
+{
+    if (!x || !h || n <= 0 || nranks < 1) return WF_ERR_ARG;
+    const double Cellfac = (kernel_type == 2) ? 3.0 : 2.0;
+    double BL[3] = { x[0], x[1], x[2] }, TR[3] = { x[0], x[1], x[2] }, hmax = h[0];
+    for (int64_t i = 0; i < n; ++i) { for (int k = 0; k < 3; ++k) { if (x[3 * i + k] > TR[k]) TR[k] = x[3 * i + k]; if (x[3 * i + k] < BL[k]) BL[k] = x[3 * i + k]; } if (h[i] > hmax) hmax = h[i]; }
+    if (dom_max) for (int k = 0; k < 3; ++k) if (dom_max[k] > TR[k]) TR[k] = dom_max[k];
+    if (dom_min) for (int k = 0; k < 3; ++k) if (dom_min[k] < BL[k]) BL[k] = dom_min[k];
+    int CellNo[3]; double CellSize[3];
+    for (int k = 0; k < 3; ++k) { TR[k] += hmax / 2; BL[k] -= hmax / 2; }
+    for (int k = 0; k < 3; ++k) {
+        double qq = (TR[k] - BL[k]) / (Cellfac * hmax);
+        if ((double)(std::ceil(qq) - qq) < (hmax / 10.0)) CellNo[k] = (int)std::ceil(qq); else CellNo[k] = (int)std::floor(qq);
+        if (CellNo[k] <= 0) return WF_ERR_ARG;
+        CellSize[k] = (TR[k] - BL[k]) / CellNo[k];
+    }
+    int ax[3] = { 0, 1, 2 };
+    std::sort(ax, ax + 3, [&](int a, int b) { return CellNo[a] < CellNo[b] || (CellNo[a] == CellNo[b] && a < b); });
+    const int slow = ax[2], L = CellNo[slow];
+    if (L < nranks) return WF_ERR_ARG;
+    std::vector<long long> hist(L, 0); std::vector<int> layer(n);
+    for (int64_t i = 0; i < n; ++i) {
+        int ci = (int)std::floor((x[3 * i + slow] - BL[slow]) / CellSize[slow]);
+        if (ci < 0) ci = 0; if (ci >= L) ci = L - 1;
+        layer[i] = ci; hist[ci]++;
+    }
+    std::vector<int> b; wf::balance_layers(hist, nranks, b);
+    if (bounds) for (int r = 0; r <= nranks; ++r) bounds[r] = b[r];
+    if (rank_of) for (int64_t i = 0; i < n; ++i) { int r = (int)(std::upper_bound(b.begin(), b.end(), layer[i]) - b.begin()) - 1; rank_of[i] = std::min(std::max(r, 0), nranks - 1); }
+    return 0;
+}

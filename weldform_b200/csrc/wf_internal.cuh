@@ -72,7 +72,20 @@ struct wf_ctx {
     wf_params prm;
     bool have_particles = false, solver_ready = false;
 
-    int64_t n = 0, nsph = 0, cap = 0;            // particles (SPH + mesh), SPH count, allocated slots
+    int64_t n = 0, nsph = 0, cap = 0;            // active slots (local + halo), GLOBAL SPH count, allocated slots
+    int64_t n_loc = 0;                           // slots [0, n_loc) are this rank's own particles (== n on one GPU); halos follow
+    // ---- multi-GPU (wf_comm.cu): 1-D slab decomposition along the slowest cell axis, NCCL point-to-point halos
+    struct Comm {
+        void *nccl = nullptr;                    // ncclComm_t
+        int rank = 0, nranks = 1;
+        int layer_lo = 0, layer_hi = 0;          // owned slow-axis cell layers [layer_lo, layer_hi)
+        int64_t send_lo_start = 0, send_lo_n = 0, send_hi_start = 0, send_hi_n = 0;   // boundary-layer slices of the local region
+        int64_t halo_lo_start = 0, halo_lo_n = 0, halo_hi_start = 0, halo_hi_n = 0;   // halo regions (from rank-1 / rank+1)
+        double *stage_send[2] = { nullptr, nullptr }, *stage_recv[2] = { nullptr, nullptr }; size_t stage_cap = 0;   // migration staging
+        int *d_emig = nullptr; int *d_cnt = nullptr; int64_t emig_cap = 0;            // emigrant slot lists (2 x emig_cap), counters
+        double *d_rank = nullptr, *d_all = nullptr;                                     // scalar partials: this rank / all ranks
+        int64_t migrated_out = 0, migrated_in = 0, halo_bytes_step = 0;
+    } comm;
     // gathered arrays, double-buffered (index cur / 1-cur): Q0 (x,y,z,h) Q1 (vx,vy,vz,m/rho) Q2 (m,rho,T,P/rho^2)
     // S0 (pxx,pyy,pzz,pxy) S1 (pyz,pxz,Rxx,Ryy) S2 (Rzz,Rxy,Ryz,Rxz), p = Sigma/rho^2 (GradientType 0) or Sigma, R = TIR
     double4 *Q0[2] = { nullptr, nullptr }, *Q1[2] = { nullptr, nullptr }, *Q2[2] = { nullptr, nullptr },
@@ -156,6 +169,13 @@ int pair_accel(wf_ctx *c);
 int pair_thermal(wf_ctx *c);
 int pair_energy(wf_ctx *c);
 int pair_post(wf_ctx *c);
+// wf_comm.cu
+enum HaloSet { HALO_Q1 = 1, HALO_Q0 = 2, HALO_Q2 = 4, HALO_S = 8 };
+int comm_halo_refresh(wf_ctx *c, int sets);             // no-op on one GPU
+int comm_gather_scalars(wf_ctx *c, int nvals);          // d_rank -> d_all (all ranks), no-op on one GPU
+int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
+int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);
+int comm_plan_layers(wf_ctx *c, const std::vector<long long> &hist);
 // wf_step.cu
 int step_begin_impl(wf_ctx *c);
 int contact_impl(wf_ctx *c);

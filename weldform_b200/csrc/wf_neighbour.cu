@@ -119,41 +119,32 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
                 const int l = g.lin(d);
                 int js = cell_start[l], je = cell_end[l];
                 const int role = c_walk[e][3];
-                // candidates of a cell are contiguous slots: fetch them four at a time (independent loads in flight), then
-                // test / append strictly in slot order so that the list keeps the reference's discovery order
-                for (int j0 = js; j0 < je; j0 += 4) {
-                    double4 qb[4]; int ob[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int jj = (j0 + u < je) ? j0 + u : je - 1; qb[u] = Q0[jj]; ob[u] = orig[jj]; }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = j0 + u;
-                        if (j >= je || j == (int)s) continue;
-                        const int oj = ob[u];
-                        if (oj >= nsph) continue;                               // rigid-mesh particle: never an SM pair
-                        if (contact && is_mesh_id(ID[j], mids)) continue;
-                        const double4 qj = qb[u];
-                        // own cell: particles stored before s have a larger creation index and act as temp1
-                        const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
-                        const double hh = (qi.w + qj.w) / 2;
-                        const V3 xj = v3(qj.x, qj.y, qj.z);
-                        const V3 xij = ifirst ? (xi - xj) : (xj - xi);
-                        // CheckRadius (Neighbour.cpp:361-372): sqrt(|xij|^2)/hh <= Cellfac. The squared form decides every candidate
-                        // that is not within a few ulp of the cutoff (sqrt and the division each round within 2^-53 relative);
-                        // only those borderline ones take the exact expression.
-                        const double d2 = dot(xij, xij), lim = g.Cellfac * hh, lim2 = lim * lim;
-                        if (d2 > lim2 * (1.0 + 8e-15)) continue;
-                        if (!(d2 < lim2 * (1.0 - 8e-15))) { const double rij = sqrt(d2); if (!((rij / hh) <= g.Cellfac)) continue; }
-                        if (check_material && classes[cls_of[j]].Material != mat_i) continue;
-                        uint32_t entry = (uint32_t)j | (ifirst ? 0x80000000u : 0u);
-                        if (oj > oi) { if (nhi + nlo < K) nbr[(int64_t)nhi * cap + s] = entry; ++nhi; }
-                        else         { if (nhi + nlo < K) nbr[(int64_t)(K - 1 - nlo) * cap + s] = entry; ++nlo; }
-                        if (contact) {
-                            // Domain.cpp:1446-1463: P1->normal += mj*xij ; P2->normal -= mi*xij, in discovery order
-                            const double mj = Q2[j].x;
-                            if (ifirst) { nx += mj * xij.x; ny += mj * xij.y; nz += mj * xij.z; }
-                            else        { nx -= mj * xij.x; ny -= mj * xij.y; nz -= mj * xij.z; }
-                        }
+                for (int j = js; j < je; ++j) {
+                    if (j == (int)s) continue;
+                    const int oj = orig[j];
+                    if (oj >= nsph) continue;                               // rigid-mesh particle: never an SM pair
+                    if (contact && is_mesh_id(ID[j], mids)) continue;
+                    const double4 qj = Q0[j];
+                    // own cell: particles stored before s have a larger creation index and act as temp1
+                    const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
+                    const double hh = (qi.w + qj.w) / 2;
+                    const V3 xj = v3(qj.x, qj.y, qj.z);
+                    const V3 xij = ifirst ? (xi - xj) : (xj - xi);
+                    // CheckRadius (Neighbour.cpp:361-372): sqrt(|xij|^2)/hh <= Cellfac. The squared form decides every candidate
+                    // that is not within a few ulp of the cutoff (sqrt and the division each round within 2^-53 relative);
+                    // only those borderline ones take the exact expression.
+                    const double d2 = dot(xij, xij), lim = g.Cellfac * hh, lim2 = lim * lim;
+                    if (d2 > lim2 * (1.0 + 8e-15)) continue;
+                    if (!(d2 < lim2 * (1.0 - 8e-15))) { const double rij = sqrt(d2); if (!((rij / hh) <= g.Cellfac)) continue; }
+                    if (check_material && classes[cls_of[j]].Material != mat_i) continue;
+                    uint32_t entry = (uint32_t)j | (ifirst ? 0x80000000u : 0u);
+                    if (oj > oi) { if (nhi + nlo < K) nbr[(int64_t)nhi * cap + s] = entry; ++nhi; }
+                    else         { if (nhi + nlo < K) nbr[(int64_t)(K - 1 - nlo) * cap + s] = entry; ++nlo; }
+                    if (contact) {
+                        // Domain.cpp:1446-1463: P1->normal += mj*xij ; P2->normal -= mi*xij, in discovery order
+                        const double mj = Q2[j].x;
+                        if (ifirst) { nx += mj * xij.x; ny += mj * xij.y; nz += mj * xij.z; }
+                        else        { nx -= mj * xij.x; ny -= mj * xij.y; nz -= mj * xij.z; }
                     }
                 }
             }

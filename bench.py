@@ -218,10 +218,19 @@ def run_ours(args):
     t0 = time.time()
     case = cases.compression_fast(dx=dx, nsteps=1, perturb_amp=PERTURB_AMP)
     case["tuning"] = float(args.tuning)
-    ctx, info = harness.context_from_case(case, device=local)
-    n_sph = ctx.n_sph
+    comm = None
+    if world > 1:
+        # the library owns its NCCL communicator; torch.distributed only carries the 128-byte id, the barriers and the max-over-ranks
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        comm = (rank, world, bytes(uid.cpu().numpy().tobytes()))
+    ctx, info = harness.context_from_case(case, device=local, comm=comm)
+    n_sph = info["n_sph_global"]            # the whole domain: `value` is the whole-job throughput
+    n_local0 = ctx.n_sph
     ctx.solver_init(float(case["dt"]))
-    log("setup: %d particles, dx=%.5g, dt=%.3g, %.1f s" % (n_sph, dx, case["dt"], time.time() - t0))
+    log("setup: %d particles (%d on this rank), dx=%.5g, dt=%.3g, %.1f s" % (n_sph, n_local0, dx, case["dt"], time.time() - t0))
     spin = 0
     t0 = time.time()
     while spin < args.max_spinup:
@@ -230,7 +239,7 @@ def run_ours(args):
         if s.is_yielding and spin >= 20:
             break
     log("spin-up: %d steps, %.1f s, max pl_strain %.3g, yielding=%d, rebuilds=%d" % (spin, time.time() - t0, s.max_pl_strain, s.is_yielding, s.nb_rebuilds))
-    nb_avg = float(ctx.download("Nb")[:n_sph].mean())
+    nb_avg = float(ctx.download("Nb").mean())
 
     ext = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -262,20 +271,30 @@ def run_ours(args):
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = n_sph * world * args.steps / (ms * 1e-3)
+    value = n_sph * args.steps / (ms * 1e-3)
 
     # ---- e2e: phase API + host GeneralAfter callback bridge with pinned host buffers
-    ids = np.asarray(case["ID"])
-    tagged = np.nonzero(ids != 1)[0].astype(np.int32)
-    nt = len(tagged)
-    is3 = ids[tagged] == 3
-    v_host = torch.empty((nt, 3), dtype=torch.float64).pin_memory().numpy()
-    a_host = torch.empty((nt, 3), dtype=torch.float64).pin_memory().numpy()
     bc = np.asarray(case["bc"]).reshape(-1, 8)
     vtop, tau = bc[0, 1:4].copy(), float(bc[0, 4])
+    bridge = {"mig": None}
+
+    def refresh_tagged():
+        # local indices of the tagged particles (ID != bulk); re-derived when particles migrated between ranks at a rebuild
+        mig = (ctx.comm_info()["migrated_out"], ctx.comm_info()["migrated_in"]) if world > 1 else (0, 0)
+        if bridge["mig"] == mig:
+            return
+        ids = ctx.download("ID")
+        tg = np.nonzero(ids != 1)[0].astype(np.int32)
+        bridge.update(mig=mig, tagged=tg, is3=ids[tg] == 3,
+                      v=torch.empty((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)],
+                      a=torch.empty((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)])
 
     def general_after(t_now):
         # examples/Compression_thermal.cpp:30-66: ID 3 rows pushed with a ramped velocity, ID 2 rows held, a = 0 for both
+        refresh_tagged()
+        tagged, is3, v_host, a_host = bridge["tagged"], bridge["is3"], bridge["v"], bridge["a"]
+        if len(tagged) == 0:
+            return
         ctx.download("v", tagged, out=v_host); ctx.download("a", tagged, out=a_host)
         f = min(t_now / tau, 1.0) if tau > 0 else 1.0
         a_host[:] = 0.0
@@ -308,9 +327,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     scal_bytes = 200
-    h2d = 2 * (2 * nt * 24 + 2 * nt * 4)            # v and a up, plus the index list with each call
-    d2h = 2 * (2 * nt * 24) + scal_bytes
-    e2e = {"value": n_sph * world * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+    nt = len(bridge["tagged"])
+    if world > 1:
+        t = torch.tensor([nt], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        nt = int(t.item())
+    h2d = 2 * (2 * nt * 24 + 2 * nt * 4)            # v and a up, plus the index list with each call (all ranks)
+    d2h = 2 * (2 * nt * 24) + scal_bytes * world
+    e2e = {"value": n_sph * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": ms_e2e / args.steps, "path": "wf_fraser_stage_a/b1/b2/c + wf_download_subset/wf_upload_subset (host GeneralAfter on %d tagged particles, pinned buffers) + wf_reduce" % nt}
 
     # ---- roofline of the dominant kernel, from the CUDA-event pairs recorded on the ctx stream inside the timed region
@@ -320,6 +344,7 @@ def run_ours(args):
     else:
         peak_hbm = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
     alg = algorithmic_bytes(nb_avg)
+    n_loc_now = ctx.n_sph                    # particles this rank's kernels process (== the domain on one GPU)
     total_prof = sum(v[0] for v in prof.values()) or 1.0
     kernels = {}
     for name, (kms, kn) in prof.items():
@@ -328,10 +353,10 @@ def run_ours(args):
         ent = {"ms_per_launch": kms / kn, "launches": int(kn), "share_of_step": kms / total_prof}
         if name in alg and alg[name] > 0:
             ent["alg_bytes_per_particle"] = alg[name]
-            ent["hbm_gbs"] = alg[name] * n_sph / (kms / kn * 1e-3) / 1e9
+            ent["hbm_gbs"] = alg[name] * n_loc_now / (kms / kn * 1e-3) / 1e9
             ent["hbm_frac"] = ent["hbm_gbs"] / peak_hbm
         if name in FLOPS_PER_PAIR:
-            ent["fp64_tflops_est"] = FLOPS_PER_PAIR[name] * nb_avg * n_sph / (kms / kn * 1e-3) / 1e12
+            ent["fp64_tflops_est"] = FLOPS_PER_PAIR[name] * nb_avg * n_loc_now / (kms / kn * 1e-3) / 1e12
         kernels[name] = ent
     pair_names = [k for k in ("accel", "rate_stress", "post", "energy") if k in kernels]
     dom = max(pair_names, key=lambda k: kernels[k]["share_of_step"]) if pair_names else None
@@ -341,11 +366,11 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp)).get(dom)
-            if tj and abs(tj.get("particles", 0) - n_sph) <= 0.01 * n_sph:
+            if tj and abs(tj.get("particles", 0) - n_loc_now) <= 0.01 * n_loc_now:
                 traffic = tj["dram_bytes_per_launch"]
         k = kernels[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s", "frac": k["hbm_frac"], "traffic": traffic,
-                    "peak_source": peak_src, "alg_bytes_per_launch": k["alg_bytes_per_particle"] * n_sph, "ms_per_launch": k["ms_per_launch"],
+                    "peak_source": peak_src, "alg_bytes_per_launch": k["alg_bytes_per_particle"] * n_loc_now, "ms_per_launch": k["ms_per_launch"],
                     "share_of_step": k["share_of_step"],
                     "note": "fp64 gather pair loop: the FP64 pipe, not HBM, is the binding roof (see fp64); HBM fraction is on unique algorithmic bytes"}
         try:
@@ -365,11 +390,13 @@ def run_ours(args):
         except Exception as exc:       # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % exc}
 
+    comm_info = ctx.comm_info() if world > 1 else None
     ctx.close()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak" if world > 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(n_sph, {"neighbours_avg": nb_avg, "spinup_steps": spin, "nb_rebuilds_in_timed_region": int(prof.get("nb_list", (0, 0))[1]),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(n_sph, {"decomposition": ("1 GPU" if world == 1 else "%d slabs along z, NCCL halos (3 refreshes per step), rank 0: %s" % (world, comm_info)),
+                                                  "neighbours_avg": nb_avg, "spinup_steps": spin, "nb_rebuilds_in_timed_region": int(prof.get("nb_list", (0, 0))[1]),
                                                   "max_pl_strain": s_after.max_pl_strain}),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line), flush=True)

@@ -76,6 +76,10 @@ typedef struct wf_particles {
     const int32_t *pres_eq, *fail, *material, *material_model, *mat_id, *thermal_bc;
     /* per-particle state */
     const double *sigmay, *T;
+    /* multi-GPU (wf_comm_init with nranks > 1): the arrays above hold THIS RANK's particles; global_index gives their creation
+     * index in the whole domain (NULL: 0..n_sph-1) and n_sph_global the domain's SPH particle count (0: n_sph) */
+    const int64_t *global_index;
+    int64_t n_sph_global;
 } wf_particles;
 
 /* Rigid tool mesh, replaces TriMesh (Source/Mesh.h:44-75) + Domain::AddTrimeshParticles (Source/Contact.cpp:10-38).
@@ -109,7 +113,7 @@ typedef enum wf_field {
     WF_F_DENSITY, WF_F_DDENSITY, WF_F_PRESSURE, WF_F_MASS, WF_F_H, WF_F_PL_STRAIN, WF_F_SIGMAY, WF_F_EFF_STRAIN_RATE,
     WF_F_T, WF_F_DTDT, WF_F_Q_PLHEAT, WF_F_Q_CONV, WF_F_DELTA_CONT, WF_F_DKIN_ENERGY_DT, WF_F_DINT_ENERGY_DT, /* 1 double */
     WF_F_SIGMA, WF_F_SHEARSTRESS, WF_F_STRAINRATE, WF_F_ROTATIONRATE, WF_F_STRAIN, WF_F_STRAIN_PL, WF_F_TIR,   /* 9 doubles */
-    WF_F_ID, WF_F_NB,                                                                                           /* 1 int32 */
+    WF_F_ID, WF_F_NB, WF_F_GLOBAL_INDEX,                                                                        /* 1 int32 */
     WF_F_COUNT
 } wf_field;
 
@@ -170,6 +174,17 @@ int wf_fraser_run(wf_ctx *ctx, int64_t nsteps);     /* nsteps full steps with de
  * Call with pts = NULL to get the count. Returns particle count or a negative wf_status. ------------------------ */
 int64_t wf_gen_cylinder(const double V[3], double Rxy, double Lz, double r, double *pts, int64_t cap);
 int64_t wf_gen_box(const double V[3], double Lx, double Ly, double Lz, double r, double *pts, int64_t cap, double box_dims[3]);
+
+/* ---- multi-GPU: one process (and one wf_ctx) per GPU, 1-D slab decomposition of the cell grid along its longest axis, NCCL
+ * point-to-point halos; the reference is single-process (no counterpart). Rank 0 obtains an id with wf_comm_unique_id and
+ * hands it to the other ranks by any means (bench.py: torch.distributed broadcast); every rank calls wf_comm_init BEFORE
+ * wf_set_particles and uploads only the particles wf_plan_slabs assigns to it. All per-phase entry points are then collective.
+ * Host arrays of wf_download / wf_upload hold this rank's current particles in ascending creation index (WF_F_GLOBAL_INDEX). */
+int wf_comm_unique_id(void *out128);
+int wf_comm_init(wf_ctx *ctx, int rank, int nranks, const void *id128);
+int wf_comm_info(wf_ctx *ctx, int64_t out[8]);      /* n_local, n_halo, migrated_out, migrated_in, layer_lo, layer_hi, halo bytes sent per step, layers */
+int wf_plan_slabs(const double *x, const double *h, int64_t n, int kernel_type, const double dom_min[3], const double dom_max[3],
+                  int nranks, int32_t *rank_of, int32_t *bounds);   /* host-only planner: same grid + balancing code as the library */
 
 /* timing helper for bench.py: CUDA-event time (ms) of each kernel family accumulated since the last reset */
 int wf_prof_enable(wf_ctx *ctx, int on);

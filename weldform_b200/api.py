@@ -39,7 +39,7 @@ class wf_particles(C.Structure):
                 ("G", _PD), ("Cs", _PD), ("P0", _PD), ("alpha", _PD), ("beta", _PD), ("TI", _PD), ("TIn", _PD), ("TIInitDist", _PD),
                 ("Ep", _PD), ("k_T", _PD), ("cp_T", _PD), ("h_conv", _PD), ("T_inf", _PD), ("th_exp", _PD), ("q_source", _PD),
                 ("pres_eq", _PI), ("fail", _PI), ("material", _PI), ("material_model", _PI), ("mat_id", _PI), ("thermal_bc", _PI),
-                ("sigmay", _PD), ("T", _PD)]
+                ("sigmay", _PD), ("T", _PD), ("global_index", C.POINTER(C.c_int64)), ("n_sph_global", C.c_int64)]
 
 
 class wf_mesh(C.Structure):
@@ -60,7 +60,7 @@ _F3 = ["x", "v", "a", "Displacement", "normal", "contforce"]
 _F1 = ["Density", "dDensity", "Pressure", "Mass", "h", "pl_strain", "Sigmay", "eff_strain_rate", "T", "dTdt", "q_plheat", "q_conv",
        "delta_cont", "dkin_energy_dt", "dint_energy_dt"]
 _F9 = ["Sigma", "ShearStress", "StrainRate", "RotationRate", "Strain", "Strain_pl", "TIR"]
-_FI = ["ID", "Nb"]
+_FI = ["ID", "Nb", "global_index"]
 FIELDS = {}
 for _k, _n in enumerate(_F3 + _F1 + _F9 + _FI):
     FIELDS[_n] = (_k, 3 if _n in _F3 else 9 if _n in _F9 else 1, np.int32 if _n in _FI else np.float64)
@@ -96,6 +96,8 @@ def load_library():
         "wf_gen_cylinder": ([_PD, C.c_double, C.c_double, C.c_double, _PD, C.c_int64], C.c_int64),
         "wf_gen_box": ([_PD, C.c_double, C.c_double, C.c_double, C.c_double, _PD, C.c_int64, _PD], C.c_int64),
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
+        "wf_comm_unique_id": ([vp], C.c_int), "wf_comm_init": ([vp, C.c_int, C.c_int, vp], C.c_int), "wf_comm_info": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "wf_plan_slabs": ([_PD, _PD, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
         "wf_get_stream": ([vp], vp), "wf_measure_fp64_peak": ([vp, _PD], C.c_int),
         "wf_prof_name": ([C.c_int], C.c_char_p), "wf_launch_count": ([vp, C.POINTER(C.c_int64)], C.c_int),
     }
@@ -136,6 +138,30 @@ def gen_box(V, Lx, Ly, Lz, r):
     pts = np.empty((n, 3))
     L.wf_gen_box(Vc, Lx, Ly, Lz, r, _dp(pts), n, dims)
     return pts, np.array(dims[:])
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the other ranks receive it by any means)."""
+    L = load_library()
+    buf = (C.c_char * 128)()
+    rc = L.wf_comm_unique_id(buf)
+    if rc != 0:
+        raise WeldformError("wf_comm_unique_id: %s" % L.wf_last_error(None).decode())
+    return bytes(buf)
+
+
+def plan_slabs(x, h, nranks, kernel_type=0, dom_min=None, dom_max=None):
+    """Host-only planner (wf_plan_slabs): -> (rank_of[n], layer bounds[nranks+1]) of the slab decomposition."""
+    L = load_library()
+    x = np.ascontiguousarray(x, np.float64).reshape(-1, 3); h = np.ascontiguousarray(h, np.float64)
+    n = len(x)
+    rank_of = np.empty(n, np.int32); bounds = np.empty(nranks + 1, np.int32)
+    dmin = (C.c_double * 3)(*(dom_min if dom_min is not None else (1e11, 1e11, 1e11)))
+    dmax = (C.c_double * 3)(*(dom_max if dom_max is not None else (-1e11, -1e11, -1e11)))
+    rc = L.wf_plan_slabs(_dp(x), _dp(h), n, int(kernel_type), dmin, dmax, int(nranks), _ip(rank_of), _ip(bounds))
+    if rc != 0:
+        raise WeldformError("wf_plan_slabs failed (%d): fewer cell layers than ranks, or bad arguments" % rc)
+    return rank_of, bounds
 
 
 class Context:
@@ -187,12 +213,27 @@ class Context:
         m = wf_mesh(len(nodes), len(elems), _dp(nodes), _ip(elems), _dp(normals), _ip(nfar), _dp(radius), float(hfac), int(mesh_id))
         self._ck(self.L.wf_add_mesh(self.h, C.byref(m)), "wf_add_mesh")
 
-    def set_particles(self, n_sph, **arrays):
+    def comm_init(self, rank, nranks, uid):
+        self._ck(self.L.wf_comm_init(self.h, int(rank), int(nranks), C.c_char_p(uid) if uid is not None else None), "wf_comm_init")
+
+    def comm_info(self):
+        out = (C.c_int64 * 8)()
+        self._ck(self.L.wf_comm_info(self.h, out), "wf_comm_info")
+        keys = ["n_local", "n_halo", "migrated_out", "migrated_in", "layer_lo", "layer_hi", "halo_bytes_per_step", "layers"]
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def set_particles(self, n_sph, n_sph_global=0, **arrays):
         p = wf_particles()
         p.n_sph = n_sph
+        p.n_sph_global = int(n_sph_global)
         keep = []
         for name, typ in wf_particles._fields_:
-            if name == "n_sph" or name not in arrays or arrays[name] is None:
+            if name in ("n_sph", "n_sph_global") or name not in arrays or arrays[name] is None:
+                continue
+            if name == "global_index":
+                a = np.ascontiguousarray(arrays[name], np.int64)
+                keep.append(a)
+                p.global_index = a.ctypes.data_as(C.POINTER(C.c_int64))
                 continue
             a = np.ascontiguousarray(arrays[name], np.float64 if typ is _PD else np.int32)
             keep.append(a)

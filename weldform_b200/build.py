@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libweldform_b200.so")
-SOURCES = ["wf_ctx.cu", "wf_neighbour.cu", "wf_pair.cu", "wf_step.cu"]
+SOURCES = ["wf_ctx.cu", "wf_neighbour.cu", "wf_pair.cu", "wf_step.cu", "wf_comm.cu"]
 # -fmad=false: the pair terms must round exactly like the reference's x86-64 build (no FMA contraction); see DESIGN.md
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations", "-diag-suppress", "177,550"]
@@ -46,7 +46,7 @@ def build(force=False, verbose=False, extra_flags=()):
             failed = True
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -363,6 +363,7 @@ extern "C" int wf_plan_slabs(const double *x, const double *h, int64_t n, int ke
     const double Cellfac = (kernel_type == 2) ? 3.0 : 2.0;
     double BL[3] = { x[0], x[1], x[2] }, TR[3] = { x[0], x[1], x[2] }, hmax = h[0];
     for (int64_t i = 0; i < n; ++i) { for (int k = 0; k < 3; ++k) { if (x[3 * i + k] > TR[k]) TR[k] = x[3 * i + k]; if (x[3 * i + k] < BL[k]) BL[k] = x[3 * i + k]; } if (h[i] > hmax) hmax = h[i]; }
+    const double pBL[3] = { BL[0], BL[1], BL[2] }, pTR[3] = { TR[0], TR[1], TR[2] };
     if (dom_max) for (int k = 0; k < 3; ++k) if (dom_max[k] > TR[k]) TR[k] = dom_max[k];
     if (dom_min) for (int k = 0; k < 3; ++k) if (dom_min[k] < BL[k]) BL[k] = dom_min[k];
     int CellNo[3]; double CellSize[3];
@@ -373,8 +374,9 @@ extern "C" int wf_plan_slabs(const double *x, const double *h, int64_t n, int ke
         if (CellNo[k] <= 0) return WF_ERR_ARG;
         CellSize[k] = (TR[k] - BL[k]) / CellNo[k];
     }
-    int ax[3] = { 0, 1, 2 };
-    std::sort(ax, ax + 3, [&](int a, int b) { return CellNo[a] < CellNo[b] || (CellNo[a] == CellNo[b] && a < b); });
+    int ax[3] = { 0, 1, 2 }; double occ[3];
+    for (int k = 0; k < 3; ++k) occ[k] = (pTR[k] - pBL[k]) / CellSize[k];
+    std::sort(ax, ax + 3, [&](int a, int b) { return occ[a] < occ[b] || (occ[a] == occ[b] && a < b); });
     const int slow = ax[2], L = CellNo[slow];
     if (L < nranks) return WF_ERR_ARG;
     std::vector<long long> hist(L, 0); std::vector<int> layer(n);

@@ -67,6 +67,7 @@ extern "C" int wf_create(int device, wf_ctx **out)
     cudaMalloc(&c->d_sc, sizeof(DevScalars)); cudaMemset(c->d_sc, 0, sizeof(DevScalars));
     cudaMallocHost(&c->h_sc, sizeof(DevScalars)); std::memset(c->h_sc, 0, sizeof(DevScalars));
     cudaMalloc(&c->d_maxcnt, 4 * sizeof(int));
+    cudaMalloc(&c->comm.d_rank, 32 * sizeof(double));
     std::memset(c->prof_ms, 0, sizeof(c->prof_ms)); std::memset(c->prof_n, 0, sizeof(c->prof_n));
     *out = c;
     return 0;
@@ -86,6 +87,8 @@ extern "C" void wf_destroy(wf_ctx *c)
     cudaFree(c->cont); cudaFree(c->cont_cnt); cudaFree(c->d_mesh_ids); cudaFree(c->d_bcs); cudaFree(c->d_sc); cudaFree(c->d_partial);
     cudaFree(c->dm.node); cudaFree(c->dm.node_v); cudaFree(c->dm.en); cudaFree(c->dm.nfar); cudaFree(c->dm.emesh);
     cudaFree(c->dm.enormal); cudaFree(c->dm.ev); cudaFree(c->dm.pplane); cudaFree(c->dm.motion);
+    cudaFree(c->comm.d_emig); cudaFree(c->comm.d_cnt); cudaFree(c->comm.d_rank); cudaFree(c->comm.d_all);
+    for (int d = 0; d < 2; ++d) { cudaFree(c->comm.stage_send[d]); cudaFree(c->comm.stage_recv[d]); }
     cudaFree(c->stage); if (c->h_stage) cudaFreeHost(c->h_stage); if (c->h_sc) cudaFreeHost(c->h_sc);
     prof_resolve(c); for (auto &e : c->prof_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -188,7 +191,7 @@ extern "C" int wf_add_mesh(wf_ctx *c, const wf_mesh *m)
 
 static int alloc_particles(wf_ctx *c, int64_t n)
 {
-    c->cap = n;
+    c->cap = n;                                   // allocated slots (multi-GPU: local particles + migration slack + halos)
     for (int b = 0; b < 2; ++b) {
         WF_CUDA(c, cudaMalloc(&c->Q0[b], n * sizeof(double4))); WF_CUDA(c, cudaMalloc(&c->Q1[b], n * sizeof(double4)));
         WF_CUDA(c, cudaMalloc(&c->Q2[b], n * sizeof(double4))); WF_CUDA(c, cudaMalloc(&c->S0[b], n * sizeof(double4)));
@@ -227,11 +230,16 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     const int64_t nsph = p->n_sph;
     int64_t nmeshp = 0; for (auto &pm : c->pending_meshes) nmeshp += (int64_t)pm.nfar.size();
     const int64_t n = nsph + nmeshp;
-    if (n >= (int64_t)1 << 31) return fail(c, WF_ERR_UNSUPPORTED, "more than 2^31-1 particles per context");
+    const bool multi = c->comm.nranks > 1;
+    const int64_t nsph_global = (multi && p->n_sph_global > 0) ? p->n_sph_global : nsph;
+    if (nsph_global + nmeshp >= (int64_t)1 << 31) return fail(c, WF_ERR_UNSUPPORTED, "more than 2^31-1 particles per domain");
+    if (multi && nmeshp > 0) return fail(c, WF_ERR_UNSUPPORTED, "rigid-mesh contact is not implemented for the multi-GPU decomposition yet");
+    if (multi && !p->global_index) return fail(c, WF_ERR_ARG, "wf_set_particles: global_index is required when nranks > 1");
     if (p->is_free) for (int64_t i = 0; i < nsph; ++i) if (!p->is_free[i])
         return fail(c, WF_ERR_UNSUPPORTED, "fixed particles (IsFree=false, FSMPairs / PrimaryComputeAcceleration) are not implemented; particle %lld", (long long)i);
-    c->n = n; c->nsph = nsph;
-    WF_CHECK(alloc_particles(c, n));
+    c->n = n; c->n_loc = n; c->nsph = nsph_global;
+    WF_CHECK(alloc_particles(c, multi ? n + n / 4 + 262144 : n));
+    const int64_t cap = c->cap;
 
     // ---- property classes -------------------------------------------------------------------------------------
     std::vector<int> cls_of(n);
@@ -358,7 +366,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     {
         std::vector<double> sy(n, 0.0);
         if (p->sigmay) for (int64_t i = 0; i < nsph; ++i) sy[i] = p->sigmay[i];
-        WF_CUDA(c, cudaMemcpy(c->F[0] + (int64_t)F_SIGY * n, sy.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->F[0] + (int64_t)F_SIGY * cap, sy.data(), n * sizeof(double), cudaMemcpyHostToDevice));
         if (nmeshp > 0) {   // mesh particles carry the element normal (Contact.cpp:28)
             std::vector<double> nx(n, 0.0);
             // normals are refreshed from the mesh at every step end; the particle copy is only a download mirror
@@ -368,22 +376,30 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     {
         std::vector<int> iv(n);
         for (int64_t i = 0; i < n; ++i) iv[i] = i < nsph ? gi(p->id, i, 0) : mids[i - nsph];
-        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_ID * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_IDORIG * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_ID * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_IDORIG * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         for (int64_t i = 0; i < n; ++i) iv[i] = i < nsph ? gi(p->not_write_surf_id, i, 0) : 0;
-        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_NOWRITE * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
-        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_CLS * n, cls_of.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_NOWRITE * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_CLS * cap, cls_of.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         for (int64_t i = 0; i < n; ++i) iv[i] = (int)i;
-        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_ORIG * n, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_LID * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         WF_CUDA(c, cudaMemcpy(c->slot_of, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        if (multi) {
+            for (int64_t i = 0; i < n; ++i) {
+                if (p->global_index[i] < 0 || p->global_index[i] >= nsph_global) return fail(c, WF_ERR_ARG, "global_index[%lld] out of range", (long long)i);
+                if (i > 0 && p->global_index[i] <= p->global_index[i - 1]) return fail(c, WF_ERR_ARG, "global_index must be strictly ascending");
+                iv[i] = (int)p->global_index[i];
+            }
+        }
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_ORIG * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
     }
     c->cur = 0;
     c->have_particles = true;
     return 0;
 }
 
-extern "C" int64_t wf_num_particles(const wf_ctx *c) { return c ? c->n : 0; }
-extern "C" int64_t wf_num_sph(const wf_ctx *c) { return c ? c->nsph : 0; }
+extern "C" int64_t wf_num_particles(const wf_ctx *c) { return c ? c->n_loc : 0; }      /* this rank's particles (SPH + mesh), halos excluded */
+extern "C" int64_t wf_num_sph(const wf_ctx *c) { return c ? (c->comm.nranks > 1 ? c->n_loc : c->nsph) : 0; }
 
 extern "C" int wf_mesh_set_motion(wf_ctx *c, int mesh, const double v[3], const double w[3])
 {
@@ -461,6 +477,7 @@ __device__ inline void field_get(const FieldView &v, int f, int64_t s, double ou
         out[0] = 0.0; out[1] = r01; out[2] = r02; out[3] = -r01; out[4] = 0.0; out[5] = r12; out[6] = -r02; out[7] = -r12; out[8] = 0.0; } break;
     case WF_F_ID: iout = v.I[(int64_t)I_ID * cap + s]; break;
     case WF_F_NB: iout = v.I[(int64_t)I_NB * cap + s]; break;
+    case WF_F_GLOBAL_INDEX: iout = v.I[(int64_t)I_ORIG * cap + s]; break;
     default: break;
     }
 }
@@ -472,7 +489,7 @@ static int field_ncomp(int f)
     if (f <= WF_F_TIR) return 9;
     return 1;
 }
-static bool field_is_int(int f) { return f == WF_F_ID || f == WF_F_NB; }
+static bool field_is_int(int f) { return f == WF_F_ID || f == WF_F_NB || f == WF_F_GLOBAL_INDEX; }
 
 __global__ void k_download(FieldView v, int f, int ncomp, int is_int, int64_t n, const int *orig, const int *slot_of, const int *idx, int64_t nidx, void *out)
 {
@@ -500,14 +517,14 @@ static int download_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx
     if (f < 0 || f >= WF_F_COUNT) return fail(c, WF_ERR_ARG, "wf_download: bad field %d", (int)f);
     cudaSetDevice(c->device);
     const int nc = field_ncomp(f); const bool isint = field_is_int(f);
-    const int64_t cnt = idx ? nidx : c->n;
+    const int64_t cnt = idx ? nidx : c->n_loc;
     if (cnt == 0) return 0;
     const size_t bytes = (size_t)cnt * nc * (isint ? 4 : 8);
     const size_t idx_bytes = idx ? (((size_t)nidx * 4 + 255) / 256) * 256 : 0;
     WF_CHECK(ensure_stage(c, bytes + idx_bytes));
     int *d_idx = nullptr;
     if (idx) { d_idx = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(d_idx, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); }
-    k_download<<<grid_for(cnt, 256), 256, 0, c->stream>>>(view_of(c), (int)f, nc, isint ? 1 : 0, c->n, c->Ip(I_ORIG), c->slot_of, d_idx, nidx, c->stage);
+    k_download<<<grid_for(cnt, 256), 256, 0, c->stream>>>(view_of(c), (int)f, nc, isint ? 1 : 0, c->n_loc, c->Ip(I_LID), c->slot_of, d_idx, nidx, c->stage);
     WF_LAUNCH_CHECK(c);
     WF_CUDA(c, cudaMemcpyAsync(host, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
     WF_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -543,14 +560,14 @@ static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, 
         default: return fail(c, WF_ERR_UNSUPPORTED, "wf_upload: field %d is not uploadable", (int)f); }
     cudaSetDevice(c->device);
     const int nc = field_ncomp(f); const bool isint = field_is_int(f);
-    const int64_t cnt = idx ? nidx : c->n;
+    const int64_t cnt = idx ? nidx : c->n_loc;
     if (cnt == 0) return 0;
     const size_t bytes = (((size_t)cnt * nc * (isint ? 4 : 8) + 255) / 256) * 256;
     WF_CHECK(ensure_stage(c, bytes + (idx ? (size_t)nidx * 4 : 0)));
     WF_CUDA(c, cudaMemcpyAsync(c->stage, host, (size_t)cnt * nc * (isint ? 4 : 8), cudaMemcpyHostToDevice, c->stream));
     int *d_idx = nullptr;
     if (idx) { d_idx = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(d_idx, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); }
-    k_upload<<<grid_for(cnt, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->F[c->cur], c->I[c->cur], c->cap, (int)f, c->n, c->slot_of, d_idx, nidx, c->stage);
+    k_upload<<<grid_for(cnt, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->F[c->cur], c->I[c->cur], c->cap, (int)f, c->n_loc, c->slot_of, d_idx, nidx, c->stage);
     WF_LAUNCH_CHECK(c);
     WF_CUDA(c, cudaStreamSynchronize(c->stream));
     if (f == WF_F_X || f == WF_F_V || f == WF_F_DENSITY) c->dens_valid = false;   // the prepared density rate no longer matches the state
@@ -573,7 +590,7 @@ extern "C" int wf_mesh_download(wf_ctx *c, int mesh, double *nodes, double *norm
 
 // ---- profiling ---------------------------------------------------------------------------------------------------------
 static const char *k_prof_names[PK_COUNT] = { "nb_keys", "nb_sort", "nb_permute", "nb_cells", "nb_list", "nb_surface", "nb_contact",
-    "step_begin", "density", "rate_stress", "accel", "contact", "bc", "move", "post", "energy", "reduce", "step_end" };
+    "step_begin", "density", "rate_stress", "accel", "contact", "bc", "move", "post", "energy", "reduce", "step_end", "halo" };
 extern "C" const char *wf_prof_name(int k) { return (k >= 0 && k < PK_COUNT) ? k_prof_names[k] : ""; }
 extern "C" int wf_prof_enable(wf_ctx *c, int on)
 {

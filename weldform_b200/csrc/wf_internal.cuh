@@ -36,7 +36,7 @@ enum OwnField {
     F_TN,                 // TIR prepared for the next step, 6
     F_COUNT = F_TN + 6
 };
-enum OwnInt { I_ID = 0, I_IDORIG, I_NB, I_NOWRITE, I_ORIG, I_OLDSURF, I_CLS, I_COUNT };
+enum OwnInt { I_ID = 0, I_IDORIG, I_NB, I_NOWRITE, I_ORIG, I_OLDSURF, I_CLS, I_LID, I_COUNT };   // I_ORIG: global creation index; I_LID: local index (slot_of inverse)
 
 struct DevMesh {      // concatenated over meshes
     int n_nodes = 0, n_elems = 0;
@@ -61,7 +61,7 @@ struct DevScalars {
 
 enum ProfKernel { PK_NB_KEYS = 0, PK_NB_SORT, PK_NB_PERMUTE, PK_NB_CELLS, PK_NB_LIST, PK_NB_SURFACE, PK_NB_CONTACT,
                   PK_BEGIN, PK_DENSITY, PK_RATE_STRESS, PK_ACCEL, PK_CONTACT, PK_BC, PK_MOVE, PK_THERMAL, PK_ENERGY,
-                  PK_REDUCE, PK_END, PK_COUNT };
+                  PK_REDUCE, PK_END, PK_HALO, PK_COUNT };
 
 } // namespace wf
 
@@ -176,6 +176,9 @@ int comm_gather_scalars(wf_ctx *c, int nvals);          // d_rank -> d_all (all 
 int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);
 int comm_plan_layers(wf_ctx *c, const std::vector<long long> &hist);
+int comm_migrate(wf_ctx *c, int64_t *n_sort, int64_t *n_out);
+int comm_halo_setup(wf_ctx *c, const unsigned long long *sorted_keys);
+int comm_local_index(wf_ctx *c);
 // wf_step.cu
 int step_begin_impl(wf_ctx *c);
 int contact_impl(wf_ctx *c);

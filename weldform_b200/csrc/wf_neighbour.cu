@@ -28,10 +28,14 @@ struct Grid {
 };
 
 // Neighbour.cpp:185-225 ListGenerate: cell index with clamping
-__global__ void k_cell_keys(Grid g, const double4 *Q0, const int *orig, int64_t n, unsigned long long *keys, int *vals)
+// mig != 0 (multi-GPU): particles whose slow-axis cell layer left [layer_lo, layer_hi) get a sentinel key (they sort to
+// the tail and are dropped) and are listed for migration to the adjacent rank (emig[dir*emig_cap + k], cnt[dir])
+struct MigArgs { int on, layer_lo, layer_hi; long long plane; int *emig; int *cnt; long long emig_cap; };
+__global__ void k_cell_keys(Grid g, const double4 *Q0, const int *orig, int64_t n, int64_t s_off, unsigned long long *keys, int *vals, MigArgs mg)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
+    s += s_off;
     double4 q = Q0[s]; double x[3] = { q.x, q.y, q.z }; int c[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -41,7 +45,19 @@ __global__ void k_cell_keys(Grid g, const double4 *Q0, const int *orig, int64_t 
         c[k] = ci;
     }
     // descending creation index inside a cell == the order the reference's push-front linked list is walked in
-    keys[s] = ((unsigned long long)(unsigned)g.lin(c) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)orig[s]);
+    const int lin = g.lin(c);
+    if (mg.on) {
+        const int layer = (int)(lin / mg.plane);
+        if (layer < mg.layer_lo || layer >= mg.layer_hi) {
+            const int dir = layer < mg.layer_lo ? 0 : 1;
+            const int k = atomicAdd(&mg.cnt[dir], 1);
+            if (k < mg.emig_cap) mg.emig[(long long)dir * mg.emig_cap + k] = (int)s;
+            keys[s] = 0xFFFFFFFF00000000ull | (unsigned long long)(0xFFFFFFFFu - (unsigned)orig[s]);
+            vals[s] = (int)s;
+            return;
+        }
+    }
+    keys[s] = ((unsigned long long)(unsigned)lin << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)orig[s]);
     vals[s] = (int)s;
 }
 
@@ -67,13 +83,14 @@ __global__ void k_permute_i(int64_t n, int64_t cap, const int *perm, const int *
     int64_t off = (int64_t)blockIdx.y * cap;
     int v = a[off + perm[s]];
     b[off + s] = v;
-    if (blockIdx.y == I_ORIG) slot_of[v] = (int)s;
+    if (blockIdx.y == I_LID && slot_of) slot_of[v] = (int)s;     // one GPU: local index == creation index
 }
 __global__ void k_cell_bounds(int64_t n, const unsigned long long *keys, int *cell_start, int *cell_end)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int cell = (int)(keys[s] >> 32);
+    if (cell < 0) return;                      // migration sentinel
     if (s == 0 || (int)(keys[s - 1] >> 32) != cell) cell_start[cell] = (int)s;
     if (s == n - 1 || (int)(keys[s + 1] >> 32) != cell) cell_end[cell] = (int)s + 1;
 }
@@ -242,21 +259,21 @@ Grid make_grid(const wf_ctx *c)
 namespace wf {
 
 // Neighbour.cpp:10-139 CellInitiate (3-D, non-periodic). Done once per run, as in the reference; a one-off host pass
-// over a downloaded copy of the positions (setup, not hot path).
+// over a downloaded copy of the positions (setup, not hot path). Multi-GPU: bounding box and hmax are all-reduced, so
+// every rank builds the same global grid; the slab (cell layers of the slowest axis) each rank owns is balanced by count.
 int nb_cell_initiate(wf_ctx *c)
 {
-    const int64_t n = c->n;
+    const int64_t n = c->n_loc;
     std::vector<double4> q(n);
     WF_CUDA(c, cudaMemcpy(q.data(), c->Q0[c->cur], n * sizeof(double4), cudaMemcpyDeviceToHost));
-    std::vector<int> orig(n);
-    WF_CUDA(c, cudaMemcpy(orig.data(), c->Ip(I_ORIG), n * sizeof(int), cudaMemcpyDeviceToHost));
-    int64_t s0 = 0; for (int64_t s = 0; s < n; ++s) if (orig[s] == 0) { s0 = s; break; }
-    double BL[3] = { q[s0].x, q[s0].y, q[s0].z }, TR[3] = { q[s0].x, q[s0].y, q[s0].z }; double hmax = q[s0].w;
+    double BL[3] = { q[0].x, q[0].y, q[0].z }, TR[3] = { q[0].x, q[0].y, q[0].z }; double hmax = q[0].w;
     for (int64_t s = 0; s < n; ++s) {
         double x[3] = { q[s].x, q[s].y, q[s].z };
         for (int k = 0; k < 3; ++k) { if (x[k] > TR[k]) TR[k] = x[k]; if (x[k] < BL[k]) BL[k] = x[k]; }
         if (q[s].w > hmax) hmax = q[s].w;
     }
+    WF_CHECK(comm_global_grid(c, BL, TR, &hmax));
+    const double pBL[3] = { BL[0], BL[1], BL[2] }, pTR[3] = { TR[0], TR[1], TR[2] };      // extent the particles occupy
     for (int k = 0; k < 3; ++k) { if (c->prm.dom_max[k] > TR[k]) TR[k] = c->prm.dom_max[k]; if (c->prm.dom_min[k] < BL[k]) BL[k] = c->prm.dom_min[k]; }
     for (int k = 0; k < 3; ++k) { TR[k] += hmax / 2; BL[k] -= hmax / 2; }
     int64_t nc = 1;
@@ -268,42 +285,82 @@ int nb_cell_initiate(wf_ctx *c)
         c->BLPF[k] = BL[k]; c->TRPR[k] = TR[k];
         nc *= c->CellNo[k];
     }
-    if (nc >= ((int64_t)1 << 31)) return fail(c, WF_ERR_UNSUPPORTED, "cell grid too large (%lld cells)", (long long)nc);
+    if (nc >= ((int64_t)1 << 31) - 2) return fail(c, WF_ERR_UNSUPPORTED, "cell grid too large (%lld cells)", (long long)nc);
     c->hmax = hmax; c->ncells = nc;
-    // storage order of cells: longest axis slowest (slab decomposition splits along it), shortest fastest
-    int ax[3] = { 0, 1, 2 };
-    std::sort(ax, ax + 3, [&](int a, int b) { return c->CellNo[a] < c->CellNo[b] || (c->CellNo[a] == c->CellNo[b] && a < b); });
+    // storage order of cells: the axis along which the particles occupy most cell layers is the slowest (the slab
+    // decomposition splits along it), the one with the fewest the fastest
+    int ax[3] = { 0, 1, 2 }; double occ[3];
+    for (int k = 0; k < 3; ++k) occ[k] = (pTR[k] - pBL[k]) / c->CellSize[k];
+    std::sort(ax, ax + 3, [&](int a, int b) { return occ[a] < occ[b] || (occ[a] == occ[b] && a < b); });
     c->ax_fast = ax[0]; c->ax_mid = ax[1]; c->ax_slow = ax[2];
     cudaFree(c->cell_start); cudaFree(c->cell_end);
     WF_CUDA(c, cudaMalloc(&c->cell_start, nc * sizeof(int))); WF_CUDA(c, cudaMalloc(&c->cell_end, nc * sizeof(int)));
     c->cell_cap = nc;
+    if (c->comm.nranks > 1) {
+        const int slow = c->ax_slow, L = c->CellNo[slow];
+        std::vector<long long> hist(L, 0);
+        for (int64_t s = 0; s < n; ++s) {
+            const double xs = slow == 0 ? q[s].x : (slow == 1 ? q[s].y : q[s].z);
+            int ci = (int)std::floor((xs - c->BLPF[slow]) / c->CellSize[slow]);
+            if (ci < 0) ci = 0; if (ci >= L) ci = L - 1;
+            hist[ci]++;
+        }
+        WF_CHECK(comm_plan_layers(c, hist));
+        c->comm.emig_cap = std::max<int64_t>(4096, n / 16);
+        cudaFree(c->comm.d_emig); WF_CUDA(c, cudaMalloc(&c->comm.d_emig, 2 * c->comm.emig_cap * sizeof(int)));
+    }
     return 0;
 }
 
 int nb_build_impl(wf_ctx *c)
 {
-    const int64_t n = c->n, cap = c->cap; const int B = 256;
+    const int64_t cap = c->cap; const int B = 256;
     cudaStream_t st = c->stream;
     Grid g = make_grid(c);
+    const bool multi = c->comm.nranks > 1;
+    int64_t n = c->n_loc, n_out = 0;                  // slots to sort; emigrants among them
     const int a = c->cur, b = 1 - c->cur;
+    MigArgs mg; mg.on = multi ? 1 : 0; mg.layer_lo = c->comm.layer_lo; mg.layer_hi = c->comm.layer_hi;
+    mg.plane = (long long)c->CellNo[c->ax_mid] * c->CellNo[c->ax_fast]; mg.emig = c->comm.d_emig; mg.cnt = c->comm.d_cnt; mg.emig_cap = c->comm.emig_cap;
     {   ProfScope ps(c, PK_NB_KEYS);
-        k_cell_keys<<<grid_for(n, B), B, 0, st>>>(g, c->Q0[a], c->Ip(I_ORIG), n, c->keys[0], c->vals[0]); WF_LAUNCH_CHECK(c); c->launches++; }
+        if (multi) WF_CUDA(c, cudaMemsetAsync(c->comm.d_cnt, 0, 4 * sizeof(int), st));
+        k_cell_keys<<<grid_for(n, B), B, 0, st>>>(g, c->Q0[a], c->Ip(I_ORIG), n, 0, c->keys[0], c->vals[0], mg); WF_LAUNCH_CHECK(c); c->launches++;
+        if (multi) {
+            // migration: emigrants out, immigrants appended at [n_loc, n); their keys computed here (they are inside the slab by construction)
+            int64_t n_sort = n;
+            WF_CHECK(comm_migrate(c, &n_sort, &n_out));
+            if (n_sort > n) { MigArgs off = mg; off.on = 0;
+                k_cell_keys<<<grid_for(n_sort - n, B), B, 0, st>>>(g, c->Q0[a], c->Ip(I_ORIG), n_sort - n, n, c->keys[0], c->vals[0], off); WF_LAUNCH_CHECK(c); c->launches++; }
+            n = n_sort;
+        }
+    }
     {   ProfScope ps(c, PK_NB_SORT);
         int cellbits = 1; while (((int64_t)1 << cellbits) < c->ncells) ++cellbits;
+        const int end_bit = multi ? 64 : 32 + cellbits;
         size_t need = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, need, c->keys[0], c->keys[1], c->vals[0], c->vals[1], (int)n, 0, 32 + cellbits, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, need, c->keys[0], c->keys[1], c->vals[0], c->vals[1], (int)n, 0, end_bit, st);
         if (need > c->cub_tmp_bytes) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; WF_CUDA(c, cudaMalloc(&c->cub_tmp, need)); c->cub_tmp_bytes = need; }
-        WF_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, need, c->keys[0], c->keys[1], c->vals[0], c->vals[1], (int)n, 0, 32 + cellbits, st));
+        WF_CUDA(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, need, c->keys[0], c->keys[1], c->vals[0], c->vals[1], (int)n, 0, end_bit, st));
         c->launches += 4; }
     {   ProfScope ps(c, PK_NB_PERMUTE);
         const int *perm = c->vals[1];
-        k_permute_q<<<grid_for(n, B), B, 0, st>>>(n, perm, c->Q0[a], c->Q1[a], c->Q2[a], c->S0[a], c->S1[a], c->S2[a], c->Q0[b], c->Q1[b], c->Q2[b], c->S0[b], c->S1[b], c->S2[b]); WF_LAUNCH_CHECK(c);
-        dim3 gf(grid_for(n, B), F_COUNT); k_permute_f<<<gf, B, 0, st>>>(n, cap, perm, c->F[a], c->F[b]); WF_LAUNCH_CHECK(c);
-        dim3 gi(grid_for(n, B), I_COUNT); k_permute_i<<<gi, B, 0, st>>>(n, cap, perm, c->I[a], c->I[b], c->slot_of); WF_LAUNCH_CHECK(c);
-        c->cur = b; c->launches += 3; }
+        const int64_t keep = n - n_out;               // emigrants carry the sentinel key: they are the tail and are dropped
+        k_permute_q<<<grid_for(keep, B), B, 0, st>>>(keep, perm, c->Q0[a], c->Q1[a], c->Q2[a], c->S0[a], c->S1[a], c->S2[a], c->Q0[b], c->Q1[b], c->Q2[b], c->S0[b], c->S1[b], c->S2[b]); WF_LAUNCH_CHECK(c);
+        dim3 gf(grid_for(keep, B), F_COUNT); k_permute_f<<<gf, B, 0, st>>>(keep, cap, perm, c->F[a], c->F[b]); WF_LAUNCH_CHECK(c);
+        dim3 gi(grid_for(keep, B), I_COUNT); k_permute_i<<<gi, B, 0, st>>>(keep, cap, perm, c->I[a], c->I[b], multi ? nullptr : c->slot_of); WF_LAUNCH_CHECK(c);
+        c->cur = b; c->launches += 3;
+        c->n_loc = keep; c->n = keep; n = keep; }
+    if (multi) {
+        ProfScope ps(c, PK_HALO);
+        WF_CHECK(comm_halo_setup(c, c->keys[1]));     // boundary slices, halo regions filled: c->n = n_loc + halos
+        if (c->n > c->n_loc) { MigArgs off = mg; off.on = 0;
+            k_cell_keys<<<grid_for(c->n - c->n_loc, B), B, 0, st>>>(g, c->Q0[c->cur], c->Ip(I_ORIG), c->n - c->n_loc, c->n_loc, c->keys[1], c->vals[0], off); WF_LAUNCH_CHECK(c); c->launches++; }
+        WF_CHECK(comm_local_index(c));
+    }
     {   ProfScope ps(c, PK_NB_CELLS);
         WF_CUDA(c, cudaMemsetAsync(c->cell_start, 0, c->ncells * sizeof(int), st)); WF_CUDA(c, cudaMemsetAsync(c->cell_end, 0, c->ncells * sizeof(int), st));
-        k_cell_bounds<<<grid_for(n, B), B, 0, st>>>(n, c->keys[1], c->cell_start, c->cell_end); WF_LAUNCH_CHECK(c); c->launches++; }
+        k_cell_bounds<<<grid_for(c->n, B), B, 0, st>>>(c->n, c->keys[1], c->cell_start, c->cell_end); WF_LAUNCH_CHECK(c); c->launches++; }
+    n = c->n_loc;                                     // lists are built for this rank's own particles; candidates include the halos
     int4 mids = make_int4(-2147483647, -2147483647, -2147483647, -2147483647);
     if (c->mesh_ids.size() > 0) mids.x = c->mesh_ids[0]; if (c->mesh_ids.size() > 1) mids.y = c->mesh_ids[1];
     if (c->mesh_ids.size() > 2) mids.z = c->mesh_ids[2]; if (c->mesh_ids.size() > 3) mids.w = c->mesh_ids[3];
@@ -362,7 +419,7 @@ static int export_common(wf_ctx *c, bool contact_pairs, int64_t *ij, int64_t cap
     // ClearNbData (Neighbour.cpp:479-497) empties SMPairs/ContPairs at the end of a cadence window; mirror that state
     if (c->nb_cleared) { *n_pairs = 0; return 0; }
     cudaSetDevice(c->device);
-    const int64_t n = c->n; cudaStream_t st = c->stream;
+    const int64_t n = c->n_loc; cudaStream_t st = c->stream;
     int64_t *d_cnt = nullptr, *d_off = nullptr;
     WF_CUDA(c, cudaMalloc(&d_cnt, (n + 1) * sizeof(int64_t))); WF_CUDA(c, cudaMalloc(&d_off, (n + 1) * sizeof(int64_t)));
     WF_CUDA(c, cudaMemsetAsync(d_cnt, 0, (n + 1) * sizeof(int64_t), st));

@@ -484,7 +484,7 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF> __global__ void 
 
 PairArgs make_args(wf_ctx *c)
 {
-    PairArgs a; a.n = c->n; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
+    PairArgs a; a.n = c->n_loc; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
     a.nbr = c->nbr; a.nb_cnt = c->nb_cnt; a.nb_hi = c->nb_hi; a.orig = c->Ip(I_ORIG); a.cls_of = c->Ip(I_CLS);
     a.Q0 = c->Q0[c->cur]; a.Q1 = c->Q1[c->cur]; a.Q2 = c->Q2[c->cur]; a.S0 = c->S0[c->cur]; a.S1 = c->S1[c->cur]; a.S2 = c->S2[c->cur];
     a.F = c->F[c->cur]; a.cls = c->d_classes; a.mats = c->d_mats; a.dt = c->dt; a.any_ti = c->any_ti ? 1 : 0;
@@ -509,20 +509,20 @@ namespace wf {
 int pair_density(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
+    PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_DENSITY);
     if (!c->dens_valid) {
         if (fast_path(c)) WF_LAUNCH_PF(k_post, true, false, false, true); else WF_LAUNCH_PF(k_post, false, false, false, true);
         WF_LAUNCH_CHECK(c); c->launches++;
     }
-    k_prologue<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    k_prologue<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
     c->dens_valid = false;
     return 0;
 }
 int pair_rate_stress(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
+    PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_RATE_STRESS);
     if (fast_path(c)) WF_LAUNCH_PF(k_rate_stress, true); else WF_LAUNCH_PF(k_rate_stress, false);
     WF_LAUNCH_CHECK(c); c->launches++;
@@ -531,7 +531,7 @@ int pair_rate_stress(wf_ctx *c)
 int pair_accel(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
+    PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_ACCEL);
     const bool fast = fast_path(c);
     const bool mb3 = (c->prm.tuning & 2) == 0;        // 3 resident blocks per SM (168 registers) by default; bit 1 of wf_params::tuning selects 4 (128 registers, spills)
@@ -548,10 +548,11 @@ int pair_accel(wf_ctx *c)
 int pair_post(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
+    PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_THERMAL);
     const bool th = c->prm.thermal_solver != 0;
-    if (th || c->prm.pl_heating) { k_thermal_pre<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
+    if (th || c->prm.pl_heating) { k_thermal_pre<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
+    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2));   // x, v, T of the halos after the move / temperature update
     const bool fast = fast_path(c);
     if (th) { if (fast) WF_LAUNCH_PF(k_post, true, true, true, true); else WF_LAUNCH_PF(k_post, false, true, true, true); }
     else    { if (fast) WF_LAUNCH_PF(k_post, true, false, true, true); else WF_LAUNCH_PF(k_post, false, false, true, true); }
@@ -566,9 +567,10 @@ int pair_thermal(wf_ctx *c)
     if (!c->prm.thermal_solver && !c->prm.pl_heating) return 0;
     PairArgs a = make_args(c); const bool pf = use_pf(c);
     ProfScope ps(c, PK_THERMAL);
-    k_thermal_pre<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    k_thermal_pre<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2));
     if (c->prm.thermal_solver) {
-        const int g = grid_for(c->n, 128);
+        const int g = grid_for(c->n_loc, 128);
         if (fast_path(c)) WF_LAUNCH_PF(k_post, true, true, false, false); else WF_LAUNCH_PF(k_post, false, true, false, false);
         WF_LAUNCH_CHECK(c); c->launches++;
     }
@@ -577,7 +579,8 @@ int pair_thermal(wf_ctx *c)
 int pair_energy(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n, 128); const bool pf = use_pf(c);
+    PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
+    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2));
     ProfScope ps(c, PK_ENERGY);
     if (fast_path(c)) WF_LAUNCH_PF(k_post, true, false, true, false); else WF_LAUNCH_PF(k_post, false, false, true, false);
     WF_LAUNCH_CHECK(c); c->launches++;

@@ -205,11 +205,10 @@ __global__ void __launch_bounds__(256) k_reduce_partial(StepArgs a, int first_fe
         if (threadIdx.x == 0) partial[(int64_t)blockIdx.x * 32 + k] = r;
     }
 }
-// accumulate = 1: end-of-step bookkeeping (energy sums += inc*dt etc.); 0: refresh maxima only
-__global__ void __launch_bounds__(256) k_reduce_final(const double *partial, int nblocks, DevScalars *sc, double dt, int accumulate)
+// stage 2: block partials -> this rank's totals (32 doubles)
+__global__ void __launch_bounds__(256) k_reduce_rank(const double *partial, int nblocks, double *out)
 {
     typedef cub::BlockReduce<double, 256> BR; __shared__ typename BR::TempStorage tmp;
-    __shared__ double res[R_NTOT];
     for (int k = 0; k < R_NTOT; ++k) {
         double v = (k < R_NSUM) ? 0. : (k == R_TMIN ? 1000. : 0.);
         for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
@@ -219,10 +218,21 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double *partial, int
         double r;
         if (k < R_NSUM) r = BR(tmp).Sum(v); else if (k == R_TMIN) r = BR(tmp).Reduce(v, cub::Min()); else r = BR(tmp).Reduce(v, cub::Max());
         __syncthreads();
-        if (threadIdx.x == 0) res[k] = r;
+        if (threadIdx.x == 0) out[k] = r;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+}
+// stage 3: totals of all ranks (rank order, identical on every rank) -> device scalars.
+// accumulate = 1: end-of-step bookkeeping (energy sums += inc*dt etc.); 0: refresh maxima only
+__global__ void k_reduce_final(const double *all, int nranks, DevScalars *sc, double dt, int accumulate)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double res[R_NTOT];
+    for (int k = 0; k < R_NTOT; ++k) {
+        double v = (k < R_NSUM) ? 0. : (k == R_TMIN ? 1000. : 0.);
+        for (int r = 0; r < nranks; ++r) { const double p = all[r * 32 + k]; if (k < R_NSUM) v += p; else if (k == R_TMIN) v = fmin(v, p); else v = fmax(v, p); }
+        res[k] = v;
+    }
+    {
         sc->max_pl_strain = res[R_MAXPL];
         // Domain::max_disp is evaluated at the START of a step (SolverFraser.cpp:151-159): keep the previous end-of-step
         // value so that wf_reduce can report what the reference holds once the step has completed
@@ -257,7 +267,7 @@ __global__ void k_init_pressure(StepArgs a)
 
 StepArgs make_step_args(wf_ctx *c)
 {
-    StepArgs a; a.n = c->n; a.cap = c->cap; a.nsph = (int)c->nsph; a.dt = c->dt;
+    StepArgs a; a.n = c->n_loc; a.cap = c->cap; a.nsph = (int)c->nsph; a.dt = c->dt;
     a.Q0 = c->Q0[c->cur]; a.Q1 = c->Q1[c->cur]; a.Q2 = c->Q2[c->cur]; a.S0 = c->S0[c->cur]; a.S1 = c->S1[c->cur]; a.S2 = c->S2[c->cur];
     a.F = c->F[c->cur]; a.I = c->I[c->cur]; a.cls = c->d_classes; a.bcs = c->d_bcs; a.n_bcs = c->n_bcs; a.sc = c->d_sc;
     return a;
@@ -276,7 +286,7 @@ int contact_impl(wf_ctx *c)
     ContactArgs k; k.K = c->cont_k; k.cont = c->cont; k.cont_cnt = c->cont_cnt; k.node = c->dm.node; k.enormal = c->dm.enormal; k.ev = c->dm.ev; k.pplane = c->dm.pplane;
     k.en = c->dm.en; k.emesh = c->dm.emesh; k.friction_sta = c->prm.friction_sta; k.friction_dyn = c->prm.friction_dyn; k.dfac = c->prm.dfac; k.contact_hc = c->prm.contact_hc;
     k.cont_heat_fric = c->prm.cont_heat_fric; k.cont_heat_cond = c->prm.cont_heat_cond;
-    k_contact<<<grid_for(c->n, 128), 128, 0, c->stream>>>(a, k); WF_LAUNCH_CHECK(c); c->launches++;
+    k_contact<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a, k); WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
 
@@ -285,7 +295,7 @@ static int bc_move(wf_ctx *c, int mode, int pk)
     ProfScope ps(c, pk);
     StepArgs a = make_step_args(c);
     if ((mode & 9) && !c->meshes.empty()) { k_mesh_ramp<<<1, 32, 0, c->stream>>>(c->dm.motion, (int)c->meshes.size(), c->d_sc); WF_LAUNCH_CHECK(c); c->launches++; }
-    k_bc_move<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a, mode); WF_LAUNCH_CHECK(c); c->launches++;
+    k_bc_move<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a, mode); WF_LAUNCH_CHECK(c); c->launches++;
     c->dens_valid = false;       // x / v changed after the last k_post (if any): its prepared density rate is stale
     return 0;
 }
@@ -297,11 +307,14 @@ int reduce_impl(wf_ctx *c, bool accumulate)
 {
     ProfScope ps(c, PK_REDUCE);
     StepArgs a = make_step_args(c);
-    int nb = std::min<int64_t>(c->partial_blocks, (c->n + 255) / 256); if (nb < 1) nb = 1;
-    const int first_fem = c->meshes.empty() ? (int)c->n : (int)c->meshes[0].first_particle;
-    k_reduce_partial<<<nb, 256, 0, c->stream>>>(a, c->prm.contact ? first_fem : (int)c->n, c->d_partial); WF_LAUNCH_CHECK(c);
-    k_reduce_final<<<1, 256, 0, c->stream>>>(c->d_partial, nb, c->d_sc, c->dt, accumulate ? 1 : 0); WF_LAUNCH_CHECK(c);
-    c->launches += 2;
+    int nb = std::min<int64_t>(c->partial_blocks, (c->n_loc + 255) / 256); if (nb < 1) nb = 1;
+    const int first_fem = c->meshes.empty() ? 2147483647 : (int)c->meshes[0].first_particle;
+    k_reduce_partial<<<nb, 256, 0, c->stream>>>(a, first_fem, c->d_partial); WF_LAUNCH_CHECK(c);
+    k_reduce_rank<<<1, 256, 0, c->stream>>>(c->d_partial, nb, c->comm.d_rank); WF_LAUNCH_CHECK(c);
+    WF_CHECK(comm_gather_scalars(c, 32));
+    const bool multi = c->comm.nranks > 1;
+    k_reduce_final<<<1, 32, 0, c->stream>>>(multi ? c->comm.d_all : c->comm.d_rank, multi ? c->comm.nranks : 1, c->d_sc, c->dt, accumulate ? 1 : 0); WF_LAUNCH_CHECK(c);
+    c->launches += 3;
     return 0;
 }
 
@@ -341,7 +354,7 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     c->dt = dt; c->time = 0.0; c->ts_i = 0; c->isfirst = true; c->isyielding = false; c->steps = 0; c->dens_valid = false; c->in_step = false;
     k_set_time<<<1, 1, 0, c->stream>>>(c->d_sc, 0.0, dt); WF_LAUNCH_CHECK(c);
     StepArgs a = make_step_args(c);
-    k_init_pressure<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c);       // InitialChecks
+    k_init_pressure<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c);       // InitialChecks
     WF_CHECK(nb_cell_initiate(c));                                                               // CellInitiate (+ListGenerate: part of the build)
     if (c->prm.contact) {
         // SolverFraser.cpp:71-92: ID_orig = ID, MainNeighbourSearch, SaveNeighbourData, CalculateSurface(1)
@@ -354,9 +367,9 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
 }
 
 extern "C" int wf_nb_build(wf_ctx *c) { WF_NEED_READY(c); return nb_build_impl(c); }
-extern "C" int wf_density(wf_ctx *c) { WF_NEED_READY(c); return pair_density(c); }
-extern "C" int wf_rate_stress(wf_ctx *c) { WF_NEED_READY(c); return pair_rate_stress(c); }
-extern "C" int wf_accel(wf_ctx *c) { WF_NEED_READY(c); return pair_accel(c); }
+extern "C" int wf_density(wf_ctx *c) { WF_NEED_READY(c); if (!c->dens_valid) WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1)); return pair_density(c); }
+extern "C" int wf_rate_stress(wf_ctx *c) { WF_NEED_READY(c); WF_CHECK(comm_halo_refresh(c, HALO_Q1)); return pair_rate_stress(c); }
+extern "C" int wf_accel(wf_ctx *c) { WF_NEED_READY(c); WF_CHECK(comm_halo_refresh(c, HALO_Q2 | HALO_S)); return pair_accel(c); }
 extern "C" int wf_contact(wf_ctx *c) { WF_NEED_READY(c); return contact_impl(c); }
 extern "C" int wf_apply_bcs(wf_ctx *c) { WF_NEED_READY(c); return apply_bcs_impl(c); }
 extern "C" int wf_integrate_pos(wf_ctx *c) { WF_NEED_READY(c); return move_pos_impl(c); }
@@ -433,8 +446,11 @@ extern "C" int wf_fraser_stage_a(wf_ctx *c)
 {
     WF_NEED_READY(c);
     WF_CHECK(nb_policy(c));
+    if (!c->dens_valid) WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));   // stand-alone density pass gathers x, v, m/rho of the halos
     WF_CHECK(pair_density(c));
+    WF_CHECK(comm_halo_refresh(c, HALO_Q1));                     // m/rho of the halos (rho just advanced)
     WF_CHECK(pair_rate_stress(c));
+    WF_CHECK(comm_halo_refresh(c, HALO_Q2 | HALO_S));            // m, rho, sigma/rho^2, TIR of the halos
     WF_CHECK(pair_accel(c));
     WF_CHECK(contact_impl(c));
     return 0;
@@ -459,7 +475,7 @@ extern "C" int wf_fraser_run(wf_ctx *c, int64_t nsteps)
             ProfScope ps(c, PK_MOVE);
             StepArgs a = make_step_args(c);
             if (!c->meshes.empty()) { k_mesh_ramp<<<1, 32, 0, c->stream>>>(c->dm.motion, (int)c->meshes.size(), c->d_sc); WF_LAUNCH_CHECK(c); c->launches++; }
-            k_bc_move<<<grid_for(c->n, 256), 256, 0, c->stream>>>(a, 15); WF_LAUNCH_CHECK(c); c->launches++;
+            k_bc_move<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a, 15); WF_LAUNCH_CHECK(c); c->launches++;
         }
         WF_CHECK(wf_fraser_stage_c(c));
     }

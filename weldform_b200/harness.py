@@ -58,9 +58,12 @@ def axis_plane_mesh(axis, posit, p1, p2, dens):
     return nodes, elems, normals, nfar, radius
 
 
-def context_from_case(case, device=0):
-    """Create and fully set up a Context; returns (ctx, info)."""
+def context_from_case(case, device=0, comm=None):
+    """Create and fully set up a Context; returns (ctx, info). comm = (rank, nranks, uid) for the multi-GPU decomposition:
+    every rank builds the whole case on the host, asks the library's planner for the slab split and uploads only its part."""
     ctx = api.Context(device)
+    if comm is not None:
+        ctx.comm_init(comm[0], comm[1], comm[2])
     p = ctx.default_params()
     p.dimension = int(case.get("Dimension", 3)); p.kernel_type = int(case.get("KernelType", 0)); p.gradient_type = int(case.get("GradientType", 0))
     p.ts_nb_inc = int(case.get("ts_nb_inc", 5))
@@ -119,7 +122,27 @@ def context_from_case(case, device=0):
         nodes, elems, normals, nfar, radius = axis_plane_mesh(int(pl[0]), pl[1] != 0, pl[2:5], pl[5:8], int(pl[8]))
         ctx.add_mesh(nodes, elems, normals, nfar, radius, float(case.get("mesh%d_hfac" % m, 1.1)), int(case.get("mesh%d_id" % m, 10 + m)))
         meshes.append((len(nodes), len(elems)))
-    ctx.set_particles(n, **arrays)
+    n_global = n
+    if comm is not None and comm[1] > 1:
+        xg = np.asarray(arrays["x"], float).reshape(-1, 3)
+        hg = np.broadcast_to(np.asarray(arrays["h"], float), (n,))
+        rank_of, bounds = api.plan_slabs(xg, hg, comm[1], int(case.get("KernelType", 0)), case.get("DomMin"), case.get("DomMax"))
+        sel = np.nonzero(rank_of == comm[0])[0]
+        local = {}
+        for key, val in arrays.items():
+            v = np.asarray(val)
+            if v.ndim == 0:
+                v = np.full(n, v)
+            if v.size == 3 * n and key in ("x", "v"):
+                local[key] = v.reshape(-1, 3)[sel]
+            elif v.shape[0] == n:
+                local[key] = v[sel]
+            else:
+                raise api.WeldformError("multi-GPU split: array %s has unexpected size %d" % (key, v.size))
+        arrays = local
+        arrays["global_index"] = sel.astype(np.int64)
+        n = len(sel)
+    ctx.set_particles(n, n_sph_global=n_global, **arrays)
     for m in range(mesh_count):
         key = "mesh%d_vel" % m
         if key in case:
@@ -127,7 +150,7 @@ def context_from_case(case, device=0):
     if "bc" in case:
         for r in np.asarray(case["bc"], float).reshape(-1, 8):
             ctx.add_velocity_bc(int(r[0]), r[1:4], r[4], int(r[5]))
-    return ctx, dict(n_sph=n, meshes=meshes)
+    return ctx, dict(n_sph=n, n_sph_global=n_global, meshes=meshes)
 
 
 _DUMP = ["x", "v", "a", "Displacement", "normal", "contforce", "Mass", "h", "Density", "dDensity", "Pressure", "Sigma", "ShearStress", "StrainRate",
@@ -139,6 +162,7 @@ def dump(ctx, info, with_pairs=True):
     out = {}
     for name in _DUMP:
         out[name] = ctx.download(name).reshape(-1)
+    out["global_index"] = ctx.download("global_index").reshape(-1)
     s = ctx.reduce()
     out.update(n_particles=np.array([float(ctx.n)]), solid_part_count=np.array([float(ctx.n_sph)]), Time=np.array([s.time]),
                kin_energy_sum=np.array([s.kin_energy_sum]), int_energy_sum=np.array([s.int_energy_sum]), plastic_work=np.array([s.plastic_work]),
@@ -154,9 +178,32 @@ def dump(ctx, info, with_pairs=True):
     return out
 
 
-def run_case(case, device=0, with_pairs=True):
+def merge_rank_dumps(dumps):
+    """Per-rank dumps of a multi-GPU run -> one dump in global creation order (pairs merged and sorted)."""
+    n = int(sum(len(d["global_index"]) for d in dumps))
+    out = {}
+    for name in _DUMP + ["global_index"]:
+        first = dumps[0][name]
+        nc = first.size // max(len(dumps[0]["global_index"]), 1) if len(dumps[0]["global_index"]) else 1
+        full = np.empty((n, nc), first.dtype)
+        for d in dumps:
+            full[d["global_index"]] = d[name].reshape(len(d["global_index"]), nc)
+        out[name] = full.reshape(-1)
+    for k, v in dumps[0].items():
+        if k not in out and k not in ("pairs", "cont_pairs"):
+            out[k] = v                                     # scalars are identical on every rank
+    out["n_particles"] = np.array([float(n)]); out["solid_part_count"] = np.array([float(n)])
+    if "pairs" in dumps[0]:
+        pr = np.concatenate([d["pairs"].reshape(-1, 2) for d in dumps])
+        pr = pr[np.lexsort((pr[:, 1], pr[:, 0]))]
+        out["pairs"] = pr.reshape(-1)
+        out["cont_pairs"] = np.concatenate([d["cont_pairs"] for d in dumps])
+    return out
+
+
+def run_case(case, device=0, with_pairs=True, comm=None):
     """Same contract as the oracle programs: case in, state dump out (mode 0: nsteps Fraser steps; mode 1: neighbour build only)."""
-    ctx, info = context_from_case(case, device)
+    ctx, info = context_from_case(case, device, comm)
     try:
         ctx.solver_init(float(case.get("dt", 1.0e-7)))
         if int(case.get("mode", 0)) == 1:

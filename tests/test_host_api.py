@@ -1,0 +1,92 @@
+"""The drop-in boundary above the C ABI: the host-side mirror of the reference's SPH::Domain source API
+(weldform_b200/host/). CPU: the reference's own example drivers compile UNCHANGED against it (where /root/reference
+exists), the repo's example driver links against libweldform_b200.so and refuses to run without a GPU. GPU: a driver
+with a host GeneralAfter callback reproduces the device-side-BC run bit for bit and the oracle within tolerance, in both
+callback-bridge modes."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import cases, oracle_tools as ot
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "weldform_b200", "host")
+REF_EXAMPLES = "/root/reference/examples"
+DRIVERS = ["Compression.cpp", "Compression_thermal.cpp", "Contact_Compression_1010.cpp", "Plate-Yield_3d.cpp", "FSW.cpp"]
+
+
+@pytest.fixture(scope="module")
+def host_example(product_lib):
+    from weldform_b200 import build
+    exes = build.build_host_examples()
+    exe = [e for e in exes if e.endswith("compression_host_api")]
+    assert exe
+    return exe[0]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="/root/reference is only present in the build container")
+@pytest.mark.parametrize("driver", DRIVERS)
+def test_reference_drivers_compile_unchanged(driver):
+    """The five configurations of BASELINE.json, straight from the reference tree, against the host mirror headers."""
+    cmd = ["g++", "-std=c++14", "-fsyntax-only", "-fpermissive", "-w", "-fopenmp", "-D_USE_MATH_DEFINES", "-I" + HOST, "-I" + os.path.join(ROOT, "include"),
+           os.path.join(REF_EXAMPLES, driver)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_example_links_and_refuses_without_gpu(host_example):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([host_example, "0.05", "1", "0", os.path.join(d, "o.bin")], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+def test_unsupported_solvers_fail_loudly(product_lib):
+    src = r'''
+#include "Domain.h"
+int main() { SPH::Domain d; int hits = 0;
+  try { d.Solve(1, 1, 1, "x", 1); } catch (Fatal * f) { ++hits; delete f; }
+  try { d.SolveDiffUpdateKickDrift(1, 1, 1, "x", 1); } catch (Fatal * f) { ++hits; delete f; }
+  try { d.AddCylinderLength(1, Vec3_t(0, 0, 0), 0.1, 0.1, 0.01, 1000., 0.012, false, true); } catch (Fatal * f) { ++hits; delete f; }
+  d.AddCylinderLength(1, Vec3_t(0, 0, 0), 0.1, 0.1, 0.01, 1000., 0.012, false);
+  return (hits == 3 && d.Particles.Size() > 100 && d.solid_part_count == (int)d.Particles.Size()) ? 0 : 1; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.cpp"), "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.check_call(["g++", "-std=c++14", "-w", "-I" + HOST, "-I" + os.path.join(ROOT, "include"), os.path.join(d, "t.cpp"), "-o", exe,
+                               "-L" + os.path.join(ROOT, "weldform_b200"), "-lweldform_b200", "-Wl,-rpath," + os.path.join(ROOT, "weldform_b200")])
+        assert subprocess.run([exe], capture_output=True).returncode == 0
+
+
+def _read_bin(path):
+    raw = np.fromfile(path, dtype=np.uint8)
+    n = int(raw[:8].view(np.int64)[0])
+    rec = raw[8:].view(np.float64).reshape(n, 21)
+    return dict(x=rec[:, 0:3].reshape(-1), v=rec[:, 3:6].reshape(-1), Displacement=rec[:, 6:9].reshape(-1), pl_strain=rec[:, 9], T=rec[:, 10],
+                Density=rec[:, 11], Sigma=rec[:, 12:21].reshape(-1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sync", ["full", "tagged"])
+def test_host_domain_driver_matches_device_run_and_oracle(host_example, oracle_port, sync):
+    from weldform_b200 import harness
+    dx, nsteps, amp = 0.03, 40, 60.0
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.bin")
+        r = subprocess.run([host_example, str(dx), str(nsteps), str(amp), out], capture_output=True, text=True, timeout=600, env=dict(os.environ, WELDFORM_SYNC=sync))
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        got = _read_bin(out)
+    case = cases.perturbed(cases.compression(dx=dx, nsteps=nsteps), amp=amp)
+    dev = harness.run_case(case, with_pairs=False)
+    for k in got:
+        assert np.array_equal(got[k], dev[k]), "host-callback run differs from the device-BC run in %s (%.3e)" % (k, ot.max_rel(got[k], dev[k]))
+    ref = ot.run_port(case)
+    assert ref["pl_strain"].max() > 1e-3
+    worst = {k: ot.max_rel(got[k], ref[k]) for k in got}
+    assert max(worst.values()) < 1e-6, worst

@@ -51,6 +51,32 @@ def build(force=False, verbose=False, extra_flags=()):
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_BIN = os.path.join(HOST_DIR, "bin")
+EXAMPLES = os.path.join(os.path.dirname(HERE), "examples")
+
+
+def build_host_examples(force=False):
+    """Compile examples/*.cpp (drivers written against the reference-style Domain API in weldform_b200/host/) and link them
+    with libweldform_b200.so. Host C++ only -- g++, no nvcc."""
+    build()
+    os.makedirs(HOST_BIN, exist_ok=True)
+    out = []
+    for src in sorted(os.listdir(EXAMPLES)):
+        if not src.endswith(".cpp"):
+            continue
+        exe = os.path.join(HOST_BIN, src[:-4])
+        deps = [os.path.join(EXAMPLES, src), LIB] + [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith((".h", ".cpp"))]
+        if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+            cmd = ["g++", "-std=c++14", "-O2", "-fpermissive", "-w", "-I" + HOST_DIR, "-I" + os.path.join(os.path.dirname(HERE), "include"),
+                   os.path.join(EXAMPLES, src), "-o", exe, "-L" + HERE, "-lweldform_b200", "-Wl,-rpath,$ORIGIN/../.."]
+            subprocess.check_call(cmd)
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)
+    for exe in build_host_examples():
+        print(exe)

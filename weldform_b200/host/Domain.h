@@ -1,0 +1,465 @@
+// Host-side mirror of the reference's SPH::Domain source API (Source/Domain.h:96-470) on top of the weldform_b200 C ABI.
+//
+// The reference is a header-only unity build whose drivers (examples/*.cpp) construct an SPH::Domain, fill
+// dom.Particles[a]->field, install a GeneralAfter callback and call dom.SolveDiffUpdateFraser(...). This header keeps
+// that surface -- same class, member and file names, same argument meaning, errors as `throw new Fatal(...)` -- so those
+// drivers compile and run unchanged with   -I weldform_b200/host -I include -L weldform_b200 -lweldform_b200.
+// The per-timestep work (Source/SolverFraser.cpp:133-505) is NOT done here: every phase is a call into
+// libweldform_b200.so (include/weldform_b200.h), i.e. hand-written sm_100a CUDA kernels. There is no CPU fallback: without
+// the library or a CUDA device, Solve throws.
+//
+// What stays on the host: lattice generation (through the library's wf_gen_* helpers), packing the per-particle mirrors
+// into structure-of-arrays uploads, the solver loop's control flow, the GeneralAfter/GeneralBefore callback bridge, output.
+//
+// Callback bridge. GeneralAfter runs twice per step on host Particle objects (SolverFraser.cpp:332,360). Environment
+// variable WELDFORM_SYNC selects what is mirrored around each call:
+//   full    (default, always correct) x, v, a, Sigma, T, pl_strain, Displacement, Density, Pressure of ALL particles are
+//           downloaded before the callback; v and a of all particles are uploaded after it;
+//   tagged  only particles whose ID differs from the most common ID (the boundary-condition rows of the usual drivers,
+//           e.g. ID 2/3 in examples/Compression_thermal.cpp:30-66) are mirrored -- O(surface) traffic instead of O(N);
+//   none    the callback only sees scalars (time, max_disp, contact_force_sum) and trimesh[m]->SetVel.
+// Rigid-mesh velocities set from the callback (trimesh[m]->SetVel / SetRotAxisVel) are always forwarded.
+#ifndef WF_HOST_DOMAIN_H
+#define WF_HOST_DOMAIN_H
+
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "weldform_b200.h"
+#include "matvec.h"
+#include "Particle.h"
+#include "Mesh.h"
+
+using std::cout;
+using std::endl;
+using std::string;
+
+enum domain_bid_type { PlaneStress = 0, PlaneStrain = 1, AxiSymmetric = 2, AxiSymm_3D = 2 };
+enum Kernels_Type { Qubic_Spline = 0, Quintic = 1, Quintic_Spline = 2, Hyperbolic_Spline = 3 };
+enum Viscosity_Eq_Type { Morris = 0, Shao = 1, Incompressible_Full = 2, Takeda = 3 };
+enum Gradient_Type { Squared_density = 0, Multiplied_density = 1, Randles_Libersky = 2 };
+enum Damage_Model { None = 0, Rankine = 1 };
+enum Function_Type { Constant = 0, Linear = 1, Multilinear = 2 };
+enum Friction_Type { Fr_Sta = 0, Fr_Dyn, Fr_StaDyn, Fr_Bound };
+enum Contact_Alg { Fraser = 0, Wang, Seo, Zhan, LSDyna };
+
+namespace SPH {
+
+class Domain;
+typedef void (*PtDom)(Domain & dom);
+
+struct Boundary { int InOutFlow = 0; bool Periodic[3] = { false, false, false }; };
+struct iKernel { iKernel() {} iKernel(size_t, double) {} };     // the device evaluates the kernel; kept so that `dom.m_kernel = SPH::iKernel(dim, h)` compiles
+
+class Domain {
+public:
+    typedef void (*PtVel)(Vec3_t & position, Vec3_t & Vel, double & Den, Boundary & bdry);
+
+    Domain();
+    ~Domain();
+
+    // ---- geometry (Source/Domain.cpp:326-455, 708-860; Source/Contact.cpp:10-38)
+    void AddBoxLength(int tag, Vec3_t const & V, double Lx, double Ly, double Lz, double r, double Density, double h, int type, int rotation, bool random, bool Fixed);
+    void AddCylinderLength(int tag, Vec3_t const & V, double Rxy, double Lz, double r, double Density, double h, bool Fixed, bool ghost = false);
+    void AddTrimeshParticles(TriMesh * mesh, const float & hfac, const int & id);
+    void Kernel_Set(Kernels_Type const & KT) { KernelType = KT; Cellfac = (KT == Quintic_Spline) ? 3.0 : 2.0; }
+    void Gradient_Approach_Set(Gradient_Type const & GT) { GradientType = GT; }
+    void Viscosity_Eq_Set(Viscosity_Eq_Type const & VQ) { VisEq = VQ; }
+
+    // ---- solvers (Source/Domain.h:197-210). Only the Fraser loop -- the one all shipped configurations use -- is implemented.
+    void SolveDiffUpdateFraser(double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx);
+    void SolveDiffUpdateKickDrift(double, double, double, char const *, size_t) { not_implemented("SolveDiffUpdateKickDrift"); }
+    void SolveDiffUpdateLeapFrog(double, double, double, char const *, size_t) { not_implemented("SolveDiffUpdateLeapFrog"); }
+    void SolveDiffUpdateLeapfrog(double tf, double dt, double dtOut, char const * k, size_t m) { SolveDiffUpdateLeapFrog(tf, dt, dtOut, k, m); }
+    void SolveDiffUpdateVerlet(double, double, double, char const *, size_t) { not_implemented("SolveDiffUpdateVerlet"); }
+    void ThermalSolve(double, double, double, char const *, size_t) { not_implemented("ThermalSolve"); }
+    void ThermalStructSolve(double, double, double, char const *, size_t) { not_implemented("ThermalStructSolve"); }
+    void Solve(double, double, double, char const *, size_t) { throw new Fatal("Domain::Solve: DEPRECATED (the reference throws here too, Source/Domain.cpp:2130); use SolveDiffUpdateFraser"); }
+
+    // ---- output
+    void WriteXDMF(char const * FileKey);
+    void WriteCSV(char const * FileKey);
+    double getTime() { return Time; }
+
+    // ---- data members drivers set / read (defaults: Source/Domain.cpp:78-175)
+    int Dimension = 3;
+    size_t Nproc = 1;                          // host threads of the reference; unused (the step runs on the GPU)
+    size_t Scheme = 0;
+    double CFL = 0.4, XSPH = 0.0, deltat = 0.0, deltatmin = 0.0, Alpha = 0.0, Beta = 0.0;
+    bool auto_ts = false, auto_ts_acc = false;
+    int ts_nb_inc = 5;
+    Vec3_t DomMax, DomMin, Gravity;
+    PtDom GeneralBefore = nullptr, GeneralAfter = nullptr;
+    Boundary BC;
+    iKernel m_kernel;
+    size_t KernelType = 0, GradientType = 0, VisEq = 0;
+    double Cellfac = 2.0, hmax = 0.0;
+    bool thermal_solver = false, pl_heating = false, gradKernelCorr = false, nonlock_sum = true;
+    double pl_work_heat_frac = 0.9;
+    bool contact = false, update_contact_surface = true, cont_heat_gen = false, cont_heat_cond = false, cont_heat_fric = false, model_damage = false;
+    double PFAC = 0.4, DFAC = 0.0, friction_sta = 0.0, friction_dyn = 0.0, friction_m = 0.0, friction_b = 0.0, contact_hc = 0.0;
+    int friction_function = Constant, fric_type = Fr_Dyn, contact_alg = Wang;
+    int id_free_surf = 1;
+    std::vector<int> contact_surf_id;
+    std::vector<TriMesh *> trimesh;
+    std::vector<Vec3_t> m_contact_force;
+    int meshcount = 0, first_fem_particle_idx = -1, solid_part_count = 0;
+    Array<Particle *> Particles;
+    double m_scalar_prop = 0.0;
+    Vec3_t max_disp;
+    double contact_force_sum = 0.0, contact_reaction_sum = 0.0, ext_forces_work = 0.0, plastic_work = 0.0, accum_cont_heat_cond = 0.0,
+           contact_friction_work = 0.0, kin_energy_sum = 0.0, int_energy_sum = 0.0, max_contact_force = 0.0, m_maxT = 0.0, m_minT = 0.0;
+    size_t steps = 0;
+
+    // ---- weldform_b200 specifics
+    wf_ctx * backend = nullptr;                // live between the start and the end of a Solve call
+    int device = 0;                            // CUDA device (WELDFORM_DEVICE)
+    double wall_seconds = 0.0;                 // wall time of the last Solve's step loop
+
+private:
+    double Time = 0.0;
+    enum SyncMode { SYNC_FULL = 0, SYNC_TAGGED = 1, SYNC_NONE = 2 } sync_mode = SYNC_FULL;
+    std::vector<int32_t> sync_idx;             // creation indices mirrored around callbacks (empty + SYNC_FULL: everything)
+    std::vector<double> buf3, buf9, buf1;
+    std::vector<Vec3_t> sent_mv, sent_mw;
+    struct MeshRec { TriMesh * mesh; float hfac; int id; };
+    std::vector<MeshRec> mesh_recs;
+
+    void not_implemented(const char * what) { throw new Fatal("Domain::%s is not implemented in weldform_b200 (SURVEY.md section 8f, next rows); the shipped configurations use SolveDiffUpdateFraser", what); }
+    void ck(int rc, const char * what) { if (rc != 0) throw new Fatal("%s failed (%d): %s", what, rc, wf_last_error(backend)); }
+    void backend_begin(double dt);
+    void backend_end();
+    void choose_sync();
+    void get3(wf_field f, Vec3_t Particle::*mem, bool subset);
+    void get9(wf_field f, Mat3_t Particle::*mem, bool subset);
+    void get1(wf_field f, double Particle::*mem, bool subset);
+    void put3(wf_field f, Vec3_t Particle::*mem, bool subset);
+    void sync_down(bool everything);
+    void sync_up();
+    void forward_mesh_motion();
+    void refresh_scalars();
+    void run_callback(PtDom cb);
+};
+
+// =====================================================================================================================
+inline Domain::Domain()
+{
+    DomMax = Vec3_t(-100000000000.0); DomMin = Vec3_t(100000000000.0);       // Source/Domain.cpp:118-119
+    const char * dv = std::getenv("WELDFORM_DEVICE"); if (dv) device = std::atoi(dv);
+}
+inline Domain::~Domain()
+{
+    if (backend) { wf_destroy(backend); backend = nullptr; }
+    for (size_t i = 0; i < Particles.Size(); ++i) delete Particles[i];       // Domain owns its particles (Source/Domain.cpp:177-181)
+}
+
+// Source/Domain.cpp:708-860 (3-D, no ghost rows). Points come from the library's generator, mass rule :839-841.
+inline void Domain::AddCylinderLength(int tag, Vec3_t const & V, double Rxy, double Lz, double r, double Density, double h, bool Fixed, bool ghost)
+{
+    if (Dimension != 3) throw new Fatal("AddCylinderLength: only Dimension = 3 is implemented in weldform_b200");
+    if (ghost) throw new Fatal("AddCylinderLength: ghost/symmetry particles are not implemented in weldform_b200 (SURVEY.md section 2 row 11)");
+    const double Vd[3] = { V(0), V(1), V(2) };
+    const int64_t n = wf_gen_cylinder(Vd, Rxy, Lz, r, nullptr, 0);
+    if (n < 0) throw new Fatal("AddCylinderLength: bad arguments");
+    std::vector<double> pts(3 * (size_t)n);
+    wf_gen_cylinder(Vd, Rxy, Lz, r, pts.data(), n);
+    const size_t first = Particles.Size();
+    std::cout << "\n--------------Generating particles by AddCylinderLength with defined length of particles-----------" << std::endl;
+    for (int64_t i = 0; i < n; ++i) Particles.Push(new Particle(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
+    const double Vol = M_PI * Rxy * Rxy * Lz;
+    const double Mass = Vol * Density / (double)(Particles.Size() - first);
+    std::cout << "Total Particle count: " << Particles.Size() << std::endl;
+    std::cout << "Particle mass: " << Mass << std::endl;
+    for (size_t i = first; i < Particles.Size(); ++i) Particles[i]->Mass = Mass;
+    solid_part_count = (int)Particles.Size();
+}
+
+// Source/Domain.cpp:326-455 (3-D cubic packing, type 1, rotation 0, random = false); mass rule :447-455
+inline void Domain::AddBoxLength(int tag, Vec3_t const & V, double Lx, double Ly, double Lz, double r, double Density, double h, int type, int rotation, bool random, bool Fixed)
+{
+    if (Dimension != 3) throw new Fatal("AddBoxLength: only Dimension = 3 is implemented in weldform_b200");
+    if (type != 1 || random) throw new Fatal("AddBoxLength: only cubic packing (type 1, random = false) is implemented in weldform_b200");
+    (void)rotation;
+    const double Vd[3] = { V(0), V(1), V(2) }; double dims[3];
+    const int64_t n = wf_gen_box(Vd, Lx, Ly, Lz, r, nullptr, 0, dims);
+    if (n <= 0) throw new Fatal("AddBoxLength: empty lattice");
+    std::vector<double> pts(3 * (size_t)n);
+    wf_gen_box(Vd, Lx, Ly, Lz, r, pts.data(), n, dims);
+    const size_t first = Particles.Size();
+    std::cout << "\n--------------Generating particles by AddBoxLength with defined length of particles-----------" << std::endl;
+    for (int64_t i = 0; i < n; ++i) Particles.Push(new Particle(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
+    const double Vol = dims[0] * dims[1] * dims[2];
+    const double Mass = Vol * Density / (double)(Particles.Size() - first);
+    std::cout << "Total Particle count: " << Particles.Size() << std::endl;
+    for (size_t i = first; i < Particles.Size(); ++i) Particles[i]->Mass = Mass;
+    solid_part_count = (int)Particles.Size();
+}
+
+// Source/Contact.cpp:10-38: one massless particle per element at its centroid, h = hfac * radius, ID = id
+inline void Domain::AddTrimeshParticles(TriMesh * mesh, const float & hfac, const int & id)
+{
+    if (first_fem_particle_idx < 0) first_fem_particle_idx = (int)Particles.Size();
+    mesh->id = id;
+    for (size_t e = 0; e < mesh->element.Size(); ++e) {
+        Particle * p = new Particle(id, mesh->element[e]->centroid, Vec3_t(0, 0, 0), 0.0, 0.0, (double)hfac * mesh->element[e]->radius, false);
+        p->normal = mesh->element[e]->normal; p->element = (int)e; p->mesh = meshcount;
+        Particles.Push(p);
+    }
+    trimesh.push_back(mesh); contact_surf_id.push_back(id); m_contact_force.push_back(Vec3_t(0., 0., 0.));
+    MeshRec r; r.mesh = mesh; r.hfac = hfac; r.id = id; mesh_recs.push_back(r);
+    meshcount++;
+    std::cout << "Particle count " << Particles.Size() << std::endl;
+}
+
+inline void Domain::choose_sync()
+{
+    const char * m = std::getenv("WELDFORM_SYNC");
+    sync_mode = SYNC_FULL;
+    if (m && std::strcmp(m, "tagged") == 0) sync_mode = SYNC_TAGGED;
+    if (m && std::strcmp(m, "none") == 0) sync_mode = SYNC_NONE;
+    sync_idx.clear();
+    if (sync_mode == SYNC_TAGGED) {
+        std::map<int, size_t> hist;
+        for (int i = 0; i < solid_part_count; ++i) hist[Particles[i]->ID]++;
+        int bulk = 0; size_t best = 0;
+        for (auto & kv : hist) if (kv.second > best) { best = kv.second; bulk = kv.first; }
+        for (int i = 0; i < solid_part_count; ++i) if (Particles[i]->ID != bulk) sync_idx.push_back(i);
+    }
+}
+
+inline void Domain::backend_begin(double dt)
+{
+    if (backend) { wf_destroy(backend); backend = nullptr; }
+    if (wf_create(device, &backend) != 0) throw new Fatal("weldform_b200: %s", wf_last_error(nullptr));
+    const size_t ntot = Particles.Size();
+    const size_t nsph = first_fem_particle_idx >= 0 ? (size_t)first_fem_particle_idx : ntot;
+    if (nsph == 0) throw new Fatal("Domain: no particles");
+    // ---- parameters
+    wf_params p; wf_default_params(&p);
+    p.dimension = Dimension; p.kernel_type = (int)KernelType; p.gradient_type = (int)GradientType; p.ts_nb_inc = ts_nb_inc;
+    for (int k = 0; k < 3; ++k) { p.dom_min[k] = DomMin(k); p.dom_max[k] = DomMax(k); }
+    p.thermal_solver = thermal_solver; p.pl_heating = pl_heating; p.pl_work_heat_frac = pl_work_heat_frac;
+    p.contact = contact; p.friction_sta = friction_sta; p.friction_dyn = friction_dyn; p.pfac = PFAC; p.dfac = DFAC;
+    p.cont_heat_fric = cont_heat_fric; p.cont_heat_cond = cont_heat_cond; p.contact_hc = contact_hc;
+    if (gradKernelCorr) throw new Fatal("Domain::gradKernelCorr (kernel gradient correction, Source/Domain.cpp:1832-1940) is not implemented in weldform_b200 yet (SURVEY.md section 8f item 2)");
+    if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
+    if (friction_function != Constant && contact) throw new Fatal("Domain::friction_function != Constant is not implemented in weldform_b200");
+    ck(wf_set_params(backend, &p), "wf_set_params");
+    // ---- materials: distinct Material_ objects
+    std::map<Material_ *, int> mat_ids; std::vector<wf_material> mats;
+    for (size_t i = 0; i < nsph; ++i) {
+        Material_ * m = Particles[i]->mat;
+        if (m && !mat_ids.count(m)) {
+            wf_material wm; std::memset(&wm, 0, sizeof(wm));
+            wm.model = m->Material_model; wm.E = m->Elastic().E(); wm.nu = m->Elastic().Poisson();
+            for (int k = 0; k < 13; ++k) wm.p[k] = m->params[k];
+            mat_ids[m] = (int)mats.size(); mats.push_back(wm);
+        }
+    }
+    ck(wf_set_materials(backend, mats.empty() ? nullptr : mats.data(), (int)mats.size()), "wf_set_materials");
+    // ---- rigid meshes
+    for (auto & mr : mesh_recs) {
+        TriMesh * tm = mr.mesh; const int nn = (int)tm->node.Size(), ne = (int)tm->element.Size();
+        std::vector<double> nodes(3 * nn), normals(3 * ne), radius(ne); std::vector<int32_t> elems(3 * ne), nfar(ne);
+        for (int n = 0; n < nn; ++n) for (int k = 0; k < 3; ++k) nodes[3 * n + k] = (*tm->node[n])(k);
+        for (int e = 0; e < ne; ++e) { for (int k = 0; k < 3; ++k) { elems[3 * e + k] = tm->element[e]->node[k]; normals[3 * e + k] = tm->element[e]->normal(k); }
+                                       nfar[e] = tm->element[e]->nfar; radius[e] = tm->element[e]->radius; }
+        wf_mesh wm; wm.n_nodes = nn; wm.n_elems = ne; wm.nodes = nodes.data(); wm.elems = elems.data(); wm.normals = normals.data(); wm.nfar = nfar.data();
+        wm.radius = radius.data(); wm.hfac = (double)mr.hfac; wm.id = mr.id;
+        ck(wf_add_mesh(backend, &wm), "wf_add_mesh");
+    }
+    // ---- particles: AoS mirrors -> SoA upload
+    std::vector<double> x(3 * nsph), v(3 * nsph), mass(nsph), dens(nsph), hh(nsph), refd(nsph), G(nsph), Cs(nsph), P0(nsph), al(nsph), be(nsph), TI(nsph), TIn(nsph),
+        TId(nsph), Ep(nsph), kT(nsph), cp(nsph), hc(nsph), Tinf(nsph), thx(nsph), qs(nsph), sy(nsph), T(nsph);
+    std::vector<int32_t> id(nsph), isfree(nsph), nowr(nsph), preseq(nsph), fail(nsph), matl(nsph), mmodel(nsph), matid(nsph), thbc(nsph);
+    for (size_t i = 0; i < nsph; ++i) {
+        const Particle * P = Particles[i];
+        for (int k = 0; k < 3; ++k) { x[3 * i + k] = P->x(k); v[3 * i + k] = P->v(k); }
+        mass[i] = P->Mass; dens[i] = P->Density; hh[i] = P->h; refd[i] = P->RefDensity; G[i] = P->G; Cs[i] = P->Cs; P0[i] = P->P0; al[i] = P->Alpha; be[i] = P->Beta;
+        TI[i] = P->TI; TIn[i] = P->TIn; TId[i] = P->TIInitDist; Ep[i] = P->Ep; kT[i] = P->k_T; cp[i] = P->cp_T; hc[i] = P->h_conv; Tinf[i] = P->T_inf; thx[i] = P->th_exp;
+        qs[i] = P->q_source; sy[i] = P->Sigmay; T[i] = P->T;
+        id[i] = P->ID; isfree[i] = P->IsFree ? 1 : 0; nowr[i] = P->not_write_surf_ID ? 1 : 0; preseq[i] = (int)P->PresEq; fail[i] = (int)P->Fail; matl[i] = P->Material;
+        mmodel[i] = P->Material_model; matid[i] = P->mat ? mat_ids[P->mat] : -1; thbc[i] = P->Thermal_BC;
+    }
+    wf_particles wp; std::memset(&wp, 0, sizeof(wp));
+    wp.n_sph = (int64_t)nsph; wp.x = x.data(); wp.v = v.data(); wp.mass = mass.data(); wp.density = dens.data(); wp.h = hh.data(); wp.ref_density = refd.data();
+    wp.id = id.data(); wp.is_free = isfree.data(); wp.not_write_surf_id = nowr.data();
+    wp.G = G.data(); wp.Cs = Cs.data(); wp.P0 = P0.data(); wp.alpha = al.data(); wp.beta = be.data(); wp.TI = TI.data(); wp.TIn = TIn.data(); wp.TIInitDist = TId.data();
+    wp.Ep = Ep.data(); wp.k_T = kT.data(); wp.cp_T = cp.data(); wp.h_conv = hc.data(); wp.T_inf = Tinf.data(); wp.th_exp = thx.data(); wp.q_source = qs.data();
+    wp.pres_eq = preseq.data(); wp.fail = fail.data(); wp.material = matl.data(); wp.material_model = mmodel.data(); wp.mat_id = matid.data(); wp.thermal_bc = thbc.data();
+    wp.sigmay = sy.data(); wp.T = T.data();
+    ck(wf_set_particles(backend, &wp), "wf_set_particles");
+    sent_mv.assign(trimesh.size(), Vec3_t(0.)); sent_mw.assign(trimesh.size(), Vec3_t(0.));
+    forward_mesh_motion();
+    ck(wf_solver_init(backend, dt), "wf_solver_init");
+    choose_sync();
+}
+
+inline void Domain::backend_end() { if (backend) { wf_destroy(backend); backend = nullptr; } }
+
+// ---- field mirrors -------------------------------------------------------------------------------------------------
+inline void Domain::get3(wf_field f, Vec3_t Particle::*mem, bool subset)
+{
+    const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
+    buf3.resize(3 * n);
+    if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf3.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf3.data()), "wf_download");
+    for (size_t k = 0; k < n; ++k) { Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 3; ++d) (P->*mem)(d) = buf3[3 * k + d]; }
+}
+inline void Domain::get9(wf_field f, Mat3_t Particle::*mem, bool subset)
+{
+    const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
+    buf9.resize(9 * n);
+    if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf9.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf9.data()), "wf_download");
+    for (size_t k = 0; k < n; ++k) { Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 9; ++d) (P->*mem).d[d] = buf9[9 * k + d]; }
+}
+inline void Domain::get1(wf_field f, double Particle::*mem, bool subset)
+{
+    const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
+    buf1.resize(n);
+    if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf1.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf1.data()), "wf_download");
+    for (size_t k = 0; k < n; ++k) Particles[subset ? sync_idx[k] : k]->*mem = buf1[k];
+}
+inline void Domain::put3(wf_field f, Vec3_t Particle::*mem, bool subset)
+{
+    const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
+    buf3.resize(3 * n);
+    for (size_t k = 0; k < n; ++k) { const Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 3; ++d) buf3[3 * k + d] = (P->*mem)(d); }
+    if (subset) ck(wf_upload_subset(backend, f, sync_idx.data(), (int64_t)n, buf3.data()), "wf_upload_subset"); else ck(wf_upload(backend, f, buf3.data()), "wf_upload");
+}
+
+inline void Domain::sync_down(bool everything)
+{
+    const bool subset = !everything && sync_mode == SYNC_TAGGED;
+    if (!everything && sync_mode == SYNC_NONE) return;
+    get3(WF_F_X, &Particle::x, subset); get3(WF_F_V, &Particle::v, subset); get3(WF_F_A, &Particle::a, subset);
+    get3(WF_F_DISPLACEMENT, &Particle::Displacement, subset); get9(WF_F_SIGMA, &Particle::Sigma, subset);
+    get1(WF_F_T, &Particle::T, subset); get1(WF_F_PL_STRAIN, &Particle::pl_strain, subset); get1(WF_F_DENSITY, &Particle::Density, subset);
+    get1(WF_F_PRESSURE, &Particle::Pressure, subset);
+    if (everything) {
+        get3(WF_F_CONTFORCE, &Particle::contforce, false); get3(WF_F_NORMAL, &Particle::normal, false);
+        get9(WF_F_SHEARSTRESS, &Particle::ShearStress, false); get9(WF_F_STRAINRATE, &Particle::StrainRate, false); get9(WF_F_ROTATIONRATE, &Particle::RotationRate, false);
+        get9(WF_F_STRAIN, &Particle::Strain, false); get9(WF_F_STRAIN_PL, &Particle::Strain_pl, false); get9(WF_F_TIR, &Particle::TIR, false);
+        get1(WF_F_SIGMAY, &Particle::Sigmay, false); get1(WF_F_DDENSITY, &Particle::dDensity, false); get1(WF_F_DTDT, &Particle::dTdt, false);
+        get1(WF_F_EFF_STRAIN_RATE, &Particle::eff_strain_rate, false); get1(WF_F_Q_PLHEAT, &Particle::q_plheat, false); get1(WF_F_DELTA_CONT, &Particle::delta_cont, false);
+        const size_t n = Particles.Size(); std::vector<int32_t> ib(n);
+        ck(wf_download(backend, WF_F_ID, ib.data()), "wf_download(ID)"); for (size_t i = 0; i < n; ++i) Particles[i]->ID = ib[i];
+        ck(wf_download(backend, WF_F_NB, ib.data()), "wf_download(Nb)"); for (size_t i = 0; i < n; ++i) Particles[i]->Nb = ib[i];
+        // Particle::CalculateEquivalentStress (Source/Particle.cpp)
+        for (size_t i = 0; i < n; ++i) { const Mat3_t & S = Particles[i]->Sigma;
+            Particles[i]->Sigma_eq = std::sqrt(0.5 * ((S(0, 0) - S(1, 1)) * (S(0, 0) - S(1, 1)) + (S(1, 1) - S(2, 2)) * (S(1, 1) - S(2, 2)) + (S(2, 2) - S(0, 0)) * (S(2, 2) - S(0, 0))) +
+                                               3.0 * (S(0, 1) * S(0, 1) + S(1, 2) * S(1, 2) + S(2, 0) * S(2, 0))); }
+    }
+}
+inline void Domain::sync_up()
+{
+    if (sync_mode == SYNC_NONE) return;
+    const bool subset = sync_mode == SYNC_TAGGED;
+    put3(WF_F_V, &Particle::v, subset); put3(WF_F_A, &Particle::a, subset);
+}
+inline void Domain::forward_mesh_motion()
+{
+    for (size_t m = 0; m < trimesh.size(); ++m) {
+        const Vec3_t & mv = trimesh[m]->m_v, & mw = trimesh[m]->m_w;
+        bool ch = false; for (int k = 0; k < 3; ++k) if (mv(k) != sent_mv[m](k) || mw(k) != sent_mw[m](k)) ch = true;
+        if (ch) { ck(wf_mesh_set_motion(backend, (int)m, mv.d, mw.d), "wf_mesh_set_motion"); sent_mv[m] = mv; sent_mw[m] = mw; }
+    }
+}
+inline void Domain::refresh_scalars()
+{
+    wf_scalars s; ck(wf_reduce(backend, &s), "wf_reduce");
+    Time = s.time; for (int k = 0; k < 3; ++k) max_disp(k) = s.max_disp[k];
+    contact_force_sum = s.contact_force_sum; contact_reaction_sum = s.contact_reaction_sum; ext_forces_work = s.ext_forces_work; plastic_work = s.plastic_work;
+    accum_cont_heat_cond = s.accum_cont_heat_cond; contact_friction_work = s.contact_friction_work; kin_energy_sum = s.kin_energy_sum; int_energy_sum = s.int_energy_sum;
+    m_maxT = s.max_T; m_minT = s.min_T; steps = (size_t)s.steps;
+}
+inline void Domain::run_callback(PtDom cb)
+{
+    if (!cb) return;
+    sync_down(false);
+    cb(*this);
+    sync_up();
+    forward_mesh_motion();
+}
+
+// Source/SolverFraser.cpp:21-513: the loop's control flow; every phase is a C-ABI call into the CUDA library
+inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx)
+{
+    std::cout << "\n--------------Solving (weldform_b200, SolveDiffUpdateFraser on the GPU)----------------------------" << std::endl;
+    deltat = dt; deltatmin = dt;
+    backend_begin(dt);
+    size_t idx_out = 1; double tout = Time; double max_pl = 0.0;
+    auto t0 = std::chrono::steady_clock::now();
+    refresh_scalars();
+    while (Time <= tf && idx_out <= maxidx) {
+        if (GeneralBefore) run_callback(GeneralBefore);                          // :238
+        ck(wf_fraser_stage_a(backend), "wf_fraser_stage_a");                     // :137-312 rebuild policy, density, rates + stress, accel, contact
+        if (GeneralAfter) { refresh_scalars(); run_callback(GeneralAfter); }     // :332
+        ck(wf_fraser_stage_b1(backend), "wf_fraser_stage_b1");                   // :337-343 position update
+        ck(wf_fraser_stage_b2(backend), "wf_fraser_stage_b2");                   // :352-355 velocity update
+        if (GeneralAfter) run_callback(GeneralAfter);                            // :360
+        ck(wf_fraser_stage_c(backend), "wf_fraser_stage_c");                     // :367-412 heat, energies, time, mesh update, cadence
+        refresh_scalars();
+        if (Time >= tout) {                                                      // :420-499
+            wf_scalars s; ck(wf_reduce(backend, &s), "wf_reduce"); max_pl = s.max_pl_strain;
+            if (TheFileKey != NULL) { String fn; fn.Printf("%s_%04d", TheFileKey, (int)idx_out); sync_down(true); WriteCSV(fn.CStr()); }
+            idx_out++; tout += dtOut;
+            wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            std::ostringstream o;
+            o << "\n---------------------------------------\n Total time: " << wall_seconds << " s (GPU backend)\nstep number: " << steps << "\n";
+            o << "Output No. " << idx_out << " at " << Time << " has been generated\nCurrent Time Step = " << deltat << "\n";
+            o << "Max plastic strain: " << max_pl << "\n";
+            if (max_pl > 0.) o << "Plastic Work " << plastic_work << "\n";
+            o << "Max Displacements (No Cont Surf): " << max_disp << "\n";
+            if (contact) o << "Contact Force Sum " << contact_force_sum << ", Reaction Sum " << contact_reaction_sum << "\nContact Friction Work " << contact_friction_work
+                           << "\nExternal Forces Work " << ext_forces_work << "\n";
+            o << "Int Energy: " << int_energy_sum << ", Kin Energy: " << kin_energy_sum << "\n";
+            if (thermal_solver) o << "Max, Min, Avg temps: " << m_maxT << ", " << m_minT << ", " << (m_maxT + m_minT) / 2. << "\n";
+            o << "-----------------------------------------------------------------------------\n";
+            std::cout << o.str();
+        }
+    }
+    ck(wf_sync(backend), "wf_sync");
+    wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    sync_down(true);
+    for (size_t m = 0; m < trimesh.size(); ++m) {                                // rigid-mesh node positions / normals back into the driver's TriMesh
+        TriMesh * tm = trimesh[m]; const size_t nn = tm->node.Size(), ne = tm->element.Size();
+        std::vector<double> nodes(3 * nn), nrm(3 * ne), pp(ne);
+        ck(wf_mesh_download(backend, (int)m, nodes.data(), nrm.data(), pp.data()), "wf_mesh_download");
+        for (size_t n = 0; n < nn; ++n) for (int k = 0; k < 3; ++k) (*tm->node[n])(k) = nodes[3 * n + k];
+        for (size_t e = 0; e < ne; ++e) { for (int k = 0; k < 3; ++k) tm->element[e]->normal(k) = nrm[3 * e + k]; tm->element[e]->pplane = pp[e]; }
+    }
+    std::cout << "\n--------------Solving is finished: " << steps << " steps, " << wall_seconds << " s, "
+              << (double)solid_part_count * (double)steps / (wall_seconds > 0 ? wall_seconds : 1.0) << " particle-steps/s--------------" << std::endl;
+    backend_end();
+}
+
+// Source/Output.cpp:520-554 (same columns)
+inline void Domain::WriteCSV(char const * FileKey)
+{
+    std::ostringstream oss;
+    oss << "X, Y, Z, ID, Sigma_eq, Pl_Strain, vx, vy, vz, ax, ay, az, CFx, CFy, CZFz, p, Temp" << endl;
+    for (size_t i = 0; i < Particles.Size(); i++) {
+        const Particle * P = Particles[i];
+        for (int j = 0; j < 3; j++) oss << P->x(j) << ", ";
+        oss << P->ID << ", " << P->Sigma_eq << ", " << P->pl_strain << ", " << P->v(0) << ", " << P->v(1) << ", " << P->v(2) << ", "
+            << P->a(0) << ", " << P->a(1) << ", " << P->a(2) << ", " << P->contforce(0) << ", " << P->contforce(1) << ", " << P->contforce(2) << ", "
+            << P->Pressure << ", " << P->T << endl;
+    }
+    String fn(FileKey); fn.append(".csv");
+    std::ofstream of(fn.CStr(), std::ios::out); of << oss.str(); of.close();
+}
+// Source/Output.cpp:75-518 writes XDMF + HDF5 (float32). HDF5 is outside the hot path: the same
+// particle table is written as CSV next to the name the driver asked for.
+inline void Domain::WriteXDMF(char const * FileKey) { WriteCSV(FileKey); }
+
+} // namespace SPH
+#endif

@@ -284,22 +284,24 @@ def run_ours(args):
         if bridge["mig"] == mig:
             return
         ids = ctx.download("ID")
-        tg = np.nonzero(ids != 1)[0].astype(np.int32)
-        bridge.update(mig=mig, tagged=tg, is3=ids[tg] == 3,
+        # tagged rows grouped by ID so that the callback writes contiguous slices of the pinned buffers (ID 2 rows, then ID 3 rows)
+        i2 = np.nonzero(ids == 2)[0]; i3 = np.nonzero(ids == 3)[0]
+        tg = np.concatenate([i2, i3]).astype(np.int32)
+        bridge.update(mig=mig, tagged=tg, n2=len(i2),
                       v=torch.empty((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)],
                       a=torch.empty((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)])
 
     def general_after(t_now):
         # examples/Compression_thermal.cpp:30-66: ID 3 rows pushed with a ramped velocity, ID 2 rows held, a = 0 for both
         refresh_tagged()
-        tagged, is3, v_host, a_host = bridge["tagged"], bridge["is3"], bridge["v"], bridge["a"]
+        tagged, n2, v_host, a_host = bridge["tagged"], bridge["n2"], bridge["v"], bridge["a"]
         if len(tagged) == 0:
             return
         ctx.download("v", tagged, out=v_host); ctx.download("a", tagged, out=a_host)
         f = min(t_now / tau, 1.0) if tau > 0 else 1.0
         a_host[:] = 0.0
-        v_host[is3] = vtop * f
-        v_host[~is3] = 0.0
+        v_host[n2:] = vtop * f
+        v_host[:n2] = 0.0
         ctx.upload("v", v_host, tagged); ctx.upload("a", a_host, tagged)
 
     def e2e_step():

@@ -69,7 +69,7 @@ typedef struct wf_particles {
     const double *mass, *density, *h;   /* n_sph */
     const double *ref_density; /* NULL: = density */
     const int32_t *id;         /* Particle::ID or NULL (0) */
-    const int32_t *is_free;    /* NULL: all free. Fixed particles are WF_ERR_UNSUPPORTED for now */
+    const int32_t *is_free;    /* NULL: all free. Fixed particles get no SM pairs (Neighbour.cpp:400-411); their Shepard-smoothed TIR is not computed */
     const int32_t *not_write_surf_id;
     /* per-particle "class" properties; few distinct tuples are expected (they are deduplicated into a table) */
     const double *G, *Cs, *P0, *alpha, *beta, *TI, *TIn, *TIInitDist, *Ep, *k_T, *cp_T, *h_conv, *T_inf, *th_exp, *q_source;

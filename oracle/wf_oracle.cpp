@@ -16,8 +16,9 @@
 // Particle::CalcStressStrain (+Hollomon / Johnson-Cook), CalcAccel+AccelReduction, CalculateSurface,
 // ContactNbSearch, CalcContactForcesWang, TriMesh::Update, position/velocity update, CalcPlasticWorkHeat,
 // ThermalCalcs (CalcConvHeat, CalcTempInc), CalcKinEnergyEqn/CalcIntEnergyEqn, and the Fraser step order with its
-// neighbour-rebuild cadence (Source/SolverFraser.cpp:133-505). Not restated: gradKernelCorr, fixed particles /
-// FSMPairs, ghost particles, damage, 2-D axisymmetric branches (all "next" or out of scope in SURVEY.md section 8).
+// neighbour-rebuild cadence (Source/SolverFraser.cpp:133-505). Fixed particles (IsFree = false) are routed as the reference
+// does (no SM pairs); their Shepard-smoothed TIR (PrimaryComputeAcceleration, Domain.cpp:1599-1698, read by nothing) is not
+// restated. Not restated: gradKernelCorr, ghost particles, damage, 2-D axisymmetric branches (all "next" or out of scope in SURVEY.md section 8).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

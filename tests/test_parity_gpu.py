@@ -130,6 +130,24 @@ def test_variable_h_and_scattered_points(harness, oracle_port):
     _compare(got, ref, TOL_ONE_STEP * 10, what="variable h")
 
 
+def test_fixed_particles(harness, oracle_port):
+    """IsFree = false (the fixed side rows of examples/FSW.cpp:262-272): such particles only enter FSMPairs, which the new
+    solvers never read -- they get no SM neighbours and are invisible to the free particles (Neighbour.cpp:400-411).
+    Their own TIR (a Shepard-smoothed diagnostic written by PrimaryComputeAcceleration, read by nothing) is not restated."""
+    c = cases.contact_compression(dx=0.0032, nsteps=60, vmax=5.0, tau=1e-5, dens=8, cfl=0.3)
+    g = c["gen_args"]
+    pts = cases.cylinder_points((g[1], g[2], g[3]), g[4], g[5], g[6])
+    rr = np.hypot(pts[:, 0], pts[:, 1])
+    free = np.ones(len(pts), np.int32); free[rr > 0.9 * rr.max()] = 0
+    c["IsFree"] = free
+    got, ref = harness.run_case(c), ot.run_port(c)
+    assert (ref["Nb"][:len(pts)][free == 0] == 0).all() and ref["pl_strain"].max() > 0
+    keys = [k for k in cases.FIELDS_F64 + cases.SCALARS if k != "TIR"]
+    _compare(got, ref, 1e-7, keys=keys, what="fixed particles")
+    tir_g, tir_r = got["TIR"].reshape(-1, 9)[:len(pts)][free == 1], ref["TIR"].reshape(-1, 9)[:len(pts)][free == 1]
+    assert ot.max_rel(tir_g, tir_r) < 1e-7
+
+
 def test_tiny_inputs(harness, oracle_port):
     """1 particle (no neighbours) and 2 particles exactly at / just beyond the cutoff r = 2h (kept at equality: CheckRadius
     uses <=, Neighbour.cpp:368). DomMin/DomMax give the cell grid an extent, as the reference's drivers do."""
@@ -168,9 +186,9 @@ def test_api_errors(harness):
         p = ctx.default_params(); p.dimension = 2
         with pytest.raises(api.WeldformError, match="3-D"):
             ctx.set_params(p)
-        x = np.zeros((4, 3)); x[:, 0] = np.arange(4) * 0.01
-        with pytest.raises(api.WeldformError, match="fixed particles"):
-            ctx.set_particles(4, x=x, mass=np.ones(4), density=np.ones(4), h=np.full(4, 0.012), is_free=np.array([1, 0, 1, 1], np.int32))
+        p = ctx.default_params(); p.kernel_type = 7
+        with pytest.raises(api.WeldformError, match="kernel_type"):
+            ctx.set_params(p)
     finally:
         ctx.close()
 

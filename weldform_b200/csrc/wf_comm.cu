@@ -279,9 +279,9 @@ int comm_halo_setup(wf_ctx *c, const unsigned long long *sorted_keys)
     if (c->n > c->cap) return fail(c, WF_ERR_NOMEM, "halo: %lld local + %d + %d halo particles exceed the %lld allocated slots", (long long)c->n_loc, rcv[0], rcv[1], (long long)c->cap);
     m.halo_bytes_step = 8LL * 32 * (m.send_lo_n + m.send_hi_n);
     WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2 | HALO_S));
-    const int ifields[3] = { I_ORIG, I_ID, I_CLS };
+    const int ifields[4] = { I_ORIG, I_ID, I_CLS, I_FREE };
     WF_NCCL(c, A->GroupStart());
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 4; ++k) {
         int *arr = c->Ip(ifields[k]);
         if (m.rank > 0) { if (m.send_lo_n) WF_NCCL(c, A->Send(arr + m.send_lo_start, m.send_lo_n, ncclInt32, m.rank - 1, comm, c->stream));
                           if (m.halo_lo_n) WF_NCCL(c, A->Recv(arr + m.halo_lo_start, m.halo_lo_n, ncclInt32, m.rank - 1, comm, c->stream)); }

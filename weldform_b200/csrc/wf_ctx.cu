@@ -235,8 +235,8 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     if (nsph_global + nmeshp >= (int64_t)1 << 31) return fail(c, WF_ERR_UNSUPPORTED, "more than 2^31-1 particles per domain");
     if (multi && nmeshp > 0) return fail(c, WF_ERR_UNSUPPORTED, "rigid-mesh contact is not implemented for the multi-GPU decomposition yet");
     if (multi && !p->global_index) return fail(c, WF_ERR_ARG, "wf_set_particles: global_index is required when nranks > 1");
-    if (p->is_free) for (int64_t i = 0; i < nsph; ++i) if (!p->is_free[i])
-        return fail(c, WF_ERR_UNSUPPORTED, "fixed particles (IsFree=false, FSMPairs / PrimaryComputeAcceleration) are not implemented; particle %lld", (long long)i);
+    c->any_fixed = false;
+    if (p->is_free) for (int64_t i = 0; i < nsph; ++i) if (!p->is_free[i]) { c->any_fixed = true; break; }
     c->n = n; c->n_loc = n; c->nsph = nsph_global;
     WF_CHECK(alloc_particles(c, multi ? n + n / 4 + 262144 : n));
     const int64_t cap = c->cap;
@@ -348,6 +348,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         else { int64_t k = i - nsph; q[i] = make_double4(mx[3 * k], mx[3 * k + 1], mx[3 * k + 2], mh[k]); }
         if (i < nsph && p->h[i] != p->h[0]) uni_h = false;
     }
+    c->h_uniform = p->h[0];
     c->uniform_h = uni_h;                        // over the SPH particles; rigid-mesh particles never enter an SM pair
     WF_CUDA(c, cudaMemcpy(c->Q0[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
     for (int64_t i = 0; i < n; ++i) {
@@ -378,6 +379,8 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         for (int64_t i = 0; i < n; ++i) iv[i] = i < nsph ? gi(p->id, i, 0) : mids[i - nsph];
         WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_ID * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_IDORIG * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+        for (int64_t i = 0; i < n; ++i) iv[i] = i < nsph ? gi(p->is_free, i, 1) : 1;
+        WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_FREE * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         for (int64_t i = 0; i < n; ++i) iv[i] = i < nsph ? gi(p->not_write_surf_id, i, 0) : 0;
         WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_NOWRITE * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_CLS * cap, cls_of.data(), n * sizeof(int), cudaMemcpyHostToDevice));

@@ -36,7 +36,7 @@ enum OwnField {
     F_TN,                 // TIR prepared for the next step, 6
     F_COUNT = F_TN + 6
 };
-enum OwnInt { I_ID = 0, I_IDORIG, I_NB, I_NOWRITE, I_ORIG, I_OLDSURF, I_CLS, I_LID, I_COUNT };   // I_ORIG: global creation index; I_LID: local index (slot_of inverse)
+enum OwnInt { I_ID = 0, I_IDORIG, I_NB, I_NOWRITE, I_ORIG, I_OLDSURF, I_CLS, I_LID, I_FREE, I_COUNT };   // I_ORIG: global creation index; I_LID: local index (slot_of inverse)
 
 struct DevMesh {      // concatenated over meshes
     int n_nodes = 0, n_elems = 0;
@@ -97,7 +97,7 @@ struct wf_ctx {
     // classes / materials
     std::vector<wf::ClassProps> h_classes; wf::ClassProps *d_classes = nullptr; int n_classes = 0;
     std::vector<wf::MatProps> h_mats; wf::MatProps *d_mats = nullptr;
-    bool any_ti = false, uniform_h = false, single_class = false;
+    bool any_ti = false, uniform_h = false, single_class = false, any_fixed = false; double h_uniform = 0.0;
     bool dens_valid = false;                     // F_DDN / F_TN hold the coming step's density rate and TIR (set by k_post)
     double totmass_mean = 0.0;                   // CalculateSurface's serial mean mass (Domain.cpp:1421-1425)
     // cell grid (Neighbour.cpp:10-139)

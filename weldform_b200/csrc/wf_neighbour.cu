@@ -114,7 +114,7 @@ __device__ inline bool is_mesh_id(int id, int4 mids) { return id == mids.x || id
 __global__ void __launch_bounds__(128)
 k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long long *keys, const int *cell_start, const int *cell_end,
           const double4 *__restrict__ Q0, const double4 *__restrict__ Q2, const int *__restrict__ orig, const int *__restrict__ ID,
-          const int *__restrict__ cls_of, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material,
+          const int *__restrict__ cls_of, const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material,
           uint32_t *nbr, int *nb_cnt, int *nb_hi, int *nbI, double *normal_x, double *normal_y, double *normal_z, int *d_maxcnt)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,6 +125,9 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
         double nx = 0.0, ny = 0.0, nz = 0.0;
         bool active = oi < nsph;
         if (active && contact && is_mesh_id(ID[s], mids)) active = false;
+        // fixed particles (IsFree = false) only ever enter FSMPairs (Neighbour.cpp:400-411), which no pair loop of the new
+        // solvers reads: they keep an empty SM list and are invisible to their neighbours
+        if (active && is_free && !is_free[s]) active = false;
         if (active) {
             const double4 qi = Q0[s];
             const V3 xi = v3(qi.x, qi.y, qi.z);
@@ -141,6 +144,7 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
                     const int oj = orig[j];
                     if (oj >= nsph) continue;                               // rigid-mesh particle: never an SM pair
                     if (contact && is_mesh_id(ID[j], mids)) continue;
+                    if (is_free && !is_free[j]) continue;
                     const double4 qj = Q0[j];
                     // own cell: particles stored before s have a larger creation index and act as temp1
                     const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
@@ -373,7 +377,7 @@ int nb_build_impl(wf_ctx *c)
         if ((int64_t)K * cap > c->nbr_alloc) { cudaFree(c->nbr); c->nbr = nullptr; WF_CUDA(c, cudaMalloc(&c->nbr, (size_t)K * cap * sizeof(uint32_t))); c->nbr_alloc = (int64_t)K * cap; }
         WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt, 0, 4 * sizeof(int), st));
         k_nb_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->cell_start, c->cell_end, c->Q0[c->cur], c->Q2[c->cur], c->Ip(I_ORIG), c->Ip(I_ID),
-            c->Ip(I_CLS), c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
+            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
         WF_LAUNCH_CHECK(c); c->launches++;
         int mx = 0; WF_CUDA(c, cudaMemcpyAsync(&mx, c->d_maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));
         if (mx <= K) break;

@@ -31,15 +31,24 @@
 // quotient from the correctly rounded reciprocal and two FMA residual corrections (Markstein), bit-identical to an IEEE
 // division, cheaper than the generic division sequence. Guarded against the one divisor pattern (all-ones significand)
 // for which the theorem does not hold.
+#include <cstring>
 #include "wf_internal.cuh"
 
 using namespace wf;
 
 namespace {
 
+// FAST path (3-D cubic spline, uniform h, one property class): every per-thread constant is uniform over the launch.
+// They are evaluated once on the host with the same expressions (IEEE, no contraction) and travel as kernel parameters,
+// i.e. constant-bank operands: no registers, no per-thread divisions.
+struct FastConsts {
+    double h, C3, C4, inv_h, W0, inv_W0, Alpha, Beta, TI, TIn, TId, Cs, RefDensity, kT, kk, ksum, inv_ksum, cpT, th_exp, q_source;
+    int PresEq, fast_h, fast_W0, fast_k;
+};
 struct PairArgs {
+    FastConsts fc;
     int64_t n, cap; int nsph, K, dim, kt, gt;
-    const uint32_t *nbr; const int *nb_cnt, *nb_hi; const int *orig; const int *cls_of;
+    const uint32_t *nbr; const int *nb_cnt, *nb_hi; const int *orig; const int *cls_of; const int *is_free;   // is_free: NULL when every particle is free
     double4 *Q0, *Q1, *Q2, *S0, *S1, *S2; double *F; const ClassProps *cls; const MatProps *mats;
     double dt; int any_ti, thermal, pl_heating, contact, cont_heat_fric; double pl_work_heat_frac;
 };
@@ -63,6 +72,7 @@ __device__ inline DivC divc_make(double b)
     d.fast = ((bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull) && ex > 200 && ex < 1800;
     return d;
 }
+__device__ inline DivC divc_from(double b, double y, int fast) { DivC d; d.b = b; d.y = y; d.fast = fast; return d; }
 __device__ inline double div_c(double a, const DivC &d)
 {
     if (!d.fast) return a / d.b;
@@ -140,8 +150,8 @@ template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_s
     if (a.orig[s] >= a.nsph) return;
     const double4 qi = a.Q0[s], wi = a.Q1[s];
     const V3 xi = v3(qi.x, qi.y, qi.z), vi = v3(wi.x, wi.y, wi.z);
-    const double hi = qi.w, C4i = c4_of(hi);
-    const DivC dh = divc_make(hi);
+    const double hi = FAST ? a.fc.h : qi.w, C4i = FAST ? a.fc.C4 : c4_of(hi);
+    const DivC dh = FAST ? divc_from(a.fc.h, a.fc.inv_h, a.fc.fast_h) : divc_make(hi);
     const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
     double sxx = 0., syy = 0., szz = 0., sxy = 0., syz = 0., sxz = 0., r01 = 0., r02 = 0., r12 = 0.;
     // software pipeline: the gathers of neighbour n+1 (and the list entry of n+2) are in flight while n is evaluated
@@ -188,6 +198,8 @@ template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_s
     const M3 SR = m3sym(srs);
     M3 RR = m3zero(); RR(0, 1) = r01; RR(0, 2) = r02; RR(1, 2) = r12; RR(1, 0) = -r01; RR(2, 0) = -r02; RR(2, 1) = -r12;
     S6 shs; shs.xx = OWN(F_SH); shs.yy = OWN(F_SH + 1); shs.zz = OWN(F_SH + 2); shs.xy = OWN(F_SH + 3); shs.yz = OWN(F_SH + 4); shs.xz = OWN(F_SH + 5);
+    // StartAcceleration zeroes Sigma / ShearStress of fixed particles every step (Domain.cpp:1572-1578)
+    if (a.is_free && !a.is_free[s]) { shs.xx = shs.yy = shs.zz = shs.xy = shs.yz = shs.xz = 0.0; }
     M3 SS = m3sym(shs);
     const M3 RRT = mtrans(RR), SRT = mmul(SS, RRT), RS = mmul(RR, SS);
     M3 I = m3zero(); I(0, 0) = 1.0; I(1, 1) = 1.0; I(2, 2) = 1.0;
@@ -257,14 +269,18 @@ template <bool FAST, int GT, int MB, bool PF> __global__ void __launch_bounds__(
     if (a.orig[s] >= a.nsph) return;
     const double4 qi = a.Q0[s], wi = a.Q1[s], q2i = a.Q2[s];
     const V3 xi = v3(qi.x, qi.y, qi.z), vi = v3(wi.x, wi.y, wi.z);
-    const double hi = qi.w, C3i = c3_of(hi), C4i = c4_of(hi), di = q2i.y;
-    const int ci = a.cls_of[s]; const ClassProps cpi = a.cls[ci];
+    const double hi = FAST ? a.fc.h : qi.w, C3i = FAST ? a.fc.C3 : c3_of(hi), C4i = FAST ? a.fc.C4 : c4_of(hi), di = q2i.y;
+    const int ci = FAST ? 0 : a.cls_of[s];
+    // property record: constant-bank fields on the FAST path, a per-thread copy of the class otherwise
+    struct { double Alpha, Beta, TI, TIn, TIInitDist, Cs, RefDensity; int PresEq; } cpi;
+    if (FAST) { cpi.Alpha = a.fc.Alpha; cpi.Beta = a.fc.Beta; cpi.TI = a.fc.TI; cpi.TIn = a.fc.TIn; cpi.TIInitDist = a.fc.TId; cpi.Cs = a.fc.Cs; cpi.RefDensity = a.fc.RefDensity; cpi.PresEq = a.fc.PresEq; }
+    else { const ClassProps cp0 = a.cls[ci]; cpi.Alpha = cp0.Alpha; cpi.Beta = cp0.Beta; cpi.TI = cp0.TI; cpi.TIn = cp0.TIn; cpi.TIInitDist = cp0.TIInitDist; cpi.Cs = cp0.Cs; cpi.RefDensity = cp0.RefDensity; cpi.PresEq = cp0.PresEq; }
     const double4 s0i = a.S0[s], s1i = a.S1[s], s2i = a.S2[s];
     const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
     const double Ci = soundSpeed(cpi.PresEq, cpi.Cs, di, cpi.RefDensity);
     // W(dx0/h) of the tensile-instability term for the common same-class, same-h neighbour
-    const double W0i = W_of<FAST>(a.dim, a.kt, (cpi.TIInitDist + cpi.TIInitDist) / (2.0 * hi), hi, C3i);
-    const DivC dh = divc_make(hi), dW0 = divc_make(W0i);
+    const double W0i = FAST ? a.fc.W0 : W_of<FAST>(a.dim, a.kt, (cpi.TIInitDist + cpi.TIInitDist) / (2.0 * hi), hi, C3i);
+    const DivC dh = FAST ? divc_from(a.fc.h, a.fc.inv_h, a.fc.fast_h) : divc_make(hi), dW0 = FAST ? divc_from(a.fc.W0, a.fc.inv_W0, a.fc.fast_W0) : divc_make(W0i);
     const bool ti_on = a.any_ti && (!FAST || cpi.TI > 0.0);
     double ax = 0., ay = 0., az = 0.;
     double4 qn = qi, wn = wi, q2n = q2i, s0n = s0i, s1n = s1i; uint32_t e2 = 0; int jcur = 0;
@@ -395,11 +411,14 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF> __global__ void 
     if (a.orig[s] >= a.nsph) { if (THERM) OWN(F_DTDT) = 0.; if (EKIN) OWN(F_DKIN) = 0.; return; }
     const double4 qi = a.Q0[s], wi = a.Q1[s], q2i = a.Q2[s];
     const V3 xi = v3(qi.x, qi.y, qi.z), vi = v3(wi.x, wi.y, wi.z);
-    const double hi = qi.w, C4i = c4_of(hi), di = q2i.y, Ti = q2i.z, mi = q2i.x, Pi2 = q2i.w, midi = wi.w;
-    const int ci = a.cls_of[s]; const ClassProps cpi = a.cls[ci];
+    const double hi = FAST ? a.fc.h : qi.w, C4i = FAST ? a.fc.C4 : c4_of(hi), di = q2i.y, Ti = q2i.z, mi = q2i.x, Pi2 = q2i.w, midi = wi.w;
+    const int ci = FAST ? 0 : a.cls_of[s];
+    struct { double k_T, cp_T, th_exp, q_source, TI; } cpi;
+    if (FAST) { cpi.k_T = a.fc.kT; cpi.cp_T = a.fc.cpT; cpi.th_exp = a.fc.th_exp; cpi.q_source = a.fc.q_source; cpi.TI = a.fc.TI; }
+    else { const ClassProps cp0 = a.cls[ci]; cpi.k_T = cp0.k_T; cpi.cp_T = cp0.cp_T; cpi.th_exp = cp0.th_exp; cpi.q_source = cp0.q_source; cpi.TI = cp0.TI; }
     const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
-    const DivC dh = divc_make(hi), dkk = divc_make(cpi.k_T + cpi.k_T);
-    const double kk_same = cpi.k_T * cpi.k_T;
+    const DivC dh = FAST ? divc_from(a.fc.h, a.fc.inv_h, a.fc.fast_h) : divc_make(hi), dkk = FAST ? divc_from(a.fc.ksum, a.fc.inv_ksum, a.fc.fast_k) : divc_make(cpi.k_T + cpi.k_T);
+    const double kk_same = FAST ? a.fc.kk : cpi.k_T * cpi.k_T;
     double temp = 0., dk = 0., dd = 0.;
     double4 qn = qi, wn = wi, q2n = q2i; uint32_t e1 = 0, e2 = 0;
     if (PF && cnt > 0) { e1 = a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s]; const int j0 = (int)(e1 & 0x7fffffffu); qn = a.Q0[j0]; wn = a.Q1[j0];
@@ -474,7 +493,7 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF> __global__ void 
     if (DENS) {
         dd *= di;
         OWN(F_DDN) = dd;
-        if (a.any_ti && cpi.TI > 0.0) {
+        if (a.any_ti && cpi.TI > 0.0 && !(a.is_free && !a.is_free[s])) {      // StartAcceleration: TIR for free particles only
             S6 sg; sg.xx = OWN(F_SG); sg.yy = OWN(F_SG + 1); sg.zz = OWN(F_SG + 2); sg.xy = OWN(F_SG + 3); sg.yz = OWN(F_SG + 4); sg.xz = OWN(F_SG + 5);
             double t[6]; tir_of(sg, di, cpi.TI, t);
             for (int k = 0; k < 6; ++k) OWN(F_TN + k) = t[k];
@@ -482,10 +501,27 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF> __global__ void 
     }
 }
 
+inline int divc_ok(double b)
+{
+    unsigned long long bits; std::memcpy(&bits, &b, 8);
+    const unsigned ex = (unsigned)((bits >> 52) & 0x7ff);
+    return ((bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull) && ex > 200 && ex < 1800;
+}
+inline bool fast_path(const wf_ctx *c) { return c->prm.kernel_type == 0 && c->prm.dimension == 3 && c->uniform_h && c->single_class; }
+
 PairArgs make_args(wf_ctx *c)
 {
-    PairArgs a; a.n = c->n_loc; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
-    a.nbr = c->nbr; a.nb_cnt = c->nb_cnt; a.nb_hi = c->nb_hi; a.orig = c->Ip(I_ORIG); a.cls_of = c->Ip(I_CLS);
+    PairArgs a; std::memset(&a.fc, 0, sizeof(a.fc));
+    if (fast_path(c)) {
+        const ClassProps &cp = c->h_classes[0]; FastConsts &f = a.fc;
+        f.h = c->h_uniform; f.C3 = 1.0 / (f.h * f.h * f.h * WF_PI); f.C4 = 1.0 / (f.h * f.h * f.h * f.h * WF_PI); f.inv_h = 1.0 / f.h; f.fast_h = divc_ok(f.h);
+        f.W0 = cubicW_c(f.C3, (cp.TIInitDist + cp.TIInitDist) / (2.0 * f.h)); f.inv_W0 = 1.0 / f.W0; f.fast_W0 = divc_ok(f.W0);
+        f.Alpha = cp.Alpha; f.Beta = cp.Beta; f.TI = cp.TI; f.TIn = cp.TIn; f.TId = cp.TIInitDist; f.Cs = cp.Cs; f.RefDensity = cp.RefDensity; f.PresEq = cp.PresEq;
+        f.kT = cp.k_T; f.kk = cp.k_T * cp.k_T; f.ksum = cp.k_T + cp.k_T; f.inv_ksum = 1.0 / f.ksum; f.fast_k = divc_ok(f.ksum);
+        f.cpT = cp.cp_T; f.th_exp = cp.th_exp; f.q_source = cp.q_source;
+    }
+    a.n = c->n_loc; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
+    a.nbr = c->nbr; a.nb_cnt = c->nb_cnt; a.nb_hi = c->nb_hi; a.orig = c->Ip(I_ORIG); a.cls_of = c->Ip(I_CLS); a.is_free = c->any_fixed ? c->Ip(I_FREE) : nullptr;
     a.Q0 = c->Q0[c->cur]; a.Q1 = c->Q1[c->cur]; a.Q2 = c->Q2[c->cur]; a.S0 = c->S0[c->cur]; a.S1 = c->S1[c->cur]; a.S2 = c->S2[c->cur];
     a.F = c->F[c->cur]; a.cls = c->d_classes; a.mats = c->d_mats; a.dt = c->dt; a.any_ti = c->any_ti ? 1 : 0;
     a.thermal = c->prm.thermal_solver; a.pl_heating = c->prm.pl_heating; a.contact = c->prm.contact; a.cont_heat_fric = c->prm.cont_heat_fric;
@@ -494,7 +530,6 @@ PairArgs make_args(wf_ctx *c)
 }
 
 inline bool use_pf(const wf_ctx *c) { return (c->prm.tuning & 1) == 0; }     // bit 0 of wf_params::tuning switches the software pipeline OFF
-inline bool fast_path(const wf_ctx *c) { return c->prm.kernel_type == 0 && c->prm.dimension == 3 && c->uniform_h && c->single_class; }
 
 } // namespace
 

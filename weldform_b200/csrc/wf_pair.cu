@@ -43,6 +43,7 @@ namespace {
 // i.e. constant-bank operands: no registers, no per-thread divisions.
 struct FastConsts {
     double h, C3, C4, inv_h, W0, inv_W0, Alpha, Beta, TI, TIn, TId, Cs, RefDensity, kT, kk, ksum, inv_ksum, cpT, th_exp, q_source;
+    double AlphaAvg, BetaAvg, AlphaCij, h2_001;    // lean momentum kernel: (Alpha+Alpha)/2, (Beta+Beta)/2, AlphaAvg*(0.5*(Cs+Cs)), 0.01*h*h
     int PresEq, fast_h, fast_W0, fast_k;
 };
 struct PairArgs {
@@ -54,6 +55,19 @@ struct PairArgs {
 };
 
 #define OWN(f) a.F[(int64_t)(f) * a.cap + s]
+
+// One 256-bit load per 32-byte record (LDG.E.256, sm_100): a gathered double4 costs one L1 request instead of the two
+// LDG.E.128 the compiler emits for a double4 (which is only 16-byte aligned by type). All gathered arrays are cudaMalloc'ed
+// (256-byte aligned) arrays of 32-byte records.
+template <bool W256> __device__ __forceinline__ double4 ldrec(const double4 *p)
+{
+    if (W256) {
+        double4 r;
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+        return r;
+    }
+    return *p;
+}
 
 __device__ inline int nb_row(int n, int nhi, int K) { return n < nhi ? n : (K - 1 - (n - nhi)); }
 
@@ -373,6 +387,83 @@ template <bool FAST, int GT, int MB, bool PF> __global__ void __launch_bounds__(
     OWN(F_AX) = ax; OWN(F_AY) = ay; OWN(F_AZ) = az;
 }
 
+
+// ---- CalcAccel + AccelReduction, lean form of the common case --------------------------------------------------------
+// FAST path (3-D cubic spline, uniform h, one property class) with GradientType 0, TIn = 4, PresEq = 0 (constant sound
+// speed) and Markstein-safe divisors h and W0: every loop invariant is a kernel parameter (constant bank, no registers),
+// no generic pow / sound-speed code in the loop, and the neighbour pipeline is unrolled by two with named buffers so that
+// the prefetched sectors are consumed where they landed (no register rotation). Same expressions, same operand order
+// and same summation order as k_accel<true, 0, ...>: bit-identical results.
+struct NbBuf { double4 q, w; int j; };
+template <bool TI_ON, bool W256> __device__ __forceinline__ void accel_term(const PairArgs &a, const NbBuf &nb, const V3 &xi, const V3 &vi, double di,
+                                                              const double4 &s0i, const double4 &s1i, const double4 &s2i,
+                                                              double &ax, double &ay, double &az)
+{
+    const int j = nb.j;
+    const double4 q2j = ldrec<W256>(a.Q2 + j), s0j = ldrec<W256>(a.S0 + j), s1j = ldrec<W256>(a.S1 + j);      // consumed late: their latency overlaps the kernel / viscosity math
+    double4 t2j = make_double4(0., 0., 0., 0.);
+    if (TI_ON) t2j = ldrec<W256>(a.S2 + j);
+    const V3 xij = xi - v3(nb.q.x, nb.q.y, nb.q.z), vij = vi - v3(nb.w.x, nb.w.y, nb.w.z);
+    const double rij = norm(xij);
+    const double h = a.fc.h;
+    const double q = div_c(rij, divc_from(h, a.fc.inv_h, 1));
+    const double GK = cubicGW_c(a.fc.C4, q, h);
+    const double mj = q2j.x, dj = q2j.y;
+    // artificial viscosity (InteractionAlt.cpp:72-94)
+    double pi = 0.0; bool pi_on = false;
+    if (a.fc.AlphaAvg != 0.0 || a.fc.BetaAvg != 0.0) {
+        const double vx = dot(vij, xij);
+        if (vx < 0) {
+            const double MUij = h * vx / (rij * rij + a.fc.h2_001);
+            pi = (a.fc.AlphaCij * MUij + a.fc.BetaAvg * MUij * MUij) / (0.5 * (di + dj)); pi_on = true;
+        }
+    }
+    // momentum tensor, GradientType 0 (InteractionAlt.cpp:139): S holds 1.0/(rho*rho)*Sigma
+    double mxx = s0i.x + s0j.x, myy = s0i.y + s0j.y, mzz = s0i.z + s0j.z;
+    double mxy = s0i.w + s0j.w, myz = s1i.x + s1j.x, mxz = s1i.y + s1j.y;
+    if (pi_on) { mxx += pi; myy += pi; mzz += pi; }
+    // tensile instability (InteractionAlt.cpp:103-110), TIn = 4
+    if (TI_ON) {
+        const double K = cubicW_c(a.fc.C3, q);
+        const double r = div_c(K, divc_from(a.fc.W0, a.fc.inv_W0, 1));
+        const double fti = pow4_cr(r);
+        mxx += (s1i.z + s1j.z) * fti; myy += (s1i.w + s1j.w) * fti; mzz += (s2i.x + t2j.x) * fti;
+        mxy += (s2i.y + t2j.y) * fti; myz += (s2i.z + t2j.z) * fti; mxz += (s2i.w + t2j.w) * fti;
+    }
+    const V3 g = GK * xij;
+    const double tx = g.x * mxx + g.y * mxy + g.z * mxz;
+    const double ty = g.x * mxy + g.y * myy + g.z * myz;
+    const double tz = g.x * mxz + g.y * myz + g.z * mzz;
+    ax += mj * tx; ay += mj * ty; az += mj * tz;
+}
+template <bool TI_ON, int MB, bool W256> __global__ void __launch_bounds__(128, MB) k_accel_lean(PairArgs a)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    if (a.orig[s] >= a.nsph) return;
+    const double4 qi = a.Q0[s], wi = a.Q1[s];
+    const V3 xi = v3(qi.x, qi.y, qi.z), vi = v3(wi.x, wi.y, wi.z);
+    const double di = a.Q2[s].y;
+    const double4 s0i = a.S0[s], s1i = a.S1[s], s2i = TI_ON ? a.S2[s] : make_double4(0., 0., 0., 0.);
+    const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
+    double ax = 0., ay = 0., az = 0.;
+    const uint32_t *row = a.nbr + s;
+    NbBuf A, B; uint32_t e = 0;
+    A.q = qi; A.w = wi; A.j = 0; B = A;
+    if (cnt > 0) { A.j = (int)(row[(int64_t)nb_row(0, nhi, a.K) * a.cap] & 0x7fffffffu); A.q = ldrec<W256>(a.Q0 + A.j); A.w = ldrec<W256>(a.Q1 + A.j);
+                   if (cnt > 1) e = row[(int64_t)nb_row(1, nhi, a.K) * a.cap]; }
+    for (int n = 0; n < cnt; n += 2) {
+        if (n + 1 < cnt) { B.j = (int)(e & 0x7fffffffu); B.q = ldrec<W256>(a.Q0 + B.j); B.w = ldrec<W256>(a.Q1 + B.j); }
+        if (n + 2 < cnt) e = row[(int64_t)nb_row(n + 2, nhi, a.K) * a.cap];
+        accel_term<TI_ON, W256>(a, A, xi, vi, di, s0i, s1i, s2i, ax, ay, az);
+        if (n + 1 >= cnt) break;
+        if (n + 2 < cnt) { A.j = (int)(e & 0x7fffffffu); A.q = ldrec<W256>(a.Q0 + A.j); A.w = ldrec<W256>(a.Q1 + A.j); }
+        if (n + 3 < cnt) e = row[(int64_t)nb_row(n + 3, nhi, a.K) * a.cap];
+        accel_term<TI_ON, W256>(a, B, xi, vi, di, s0i, s1i, s2i, ax, ay, az);
+    }
+    OWN(F_AX) = ax; OWN(F_AY) = ay; OWN(F_AZ) = az;
+}
+
 // ---- CalcPlasticWorkHeat, T += dt*dTdt, CalcConvHeat (ThermalStuct.cpp:14-39, Thermal.cpp:721-732,339-389) ------------
 __global__ void k_thermal_pre(PairArgs a)
 {
@@ -519,6 +610,8 @@ PairArgs make_args(wf_ctx *c)
         f.Alpha = cp.Alpha; f.Beta = cp.Beta; f.TI = cp.TI; f.TIn = cp.TIn; f.TId = cp.TIInitDist; f.Cs = cp.Cs; f.RefDensity = cp.RefDensity; f.PresEq = cp.PresEq;
         f.kT = cp.k_T; f.kk = cp.k_T * cp.k_T; f.ksum = cp.k_T + cp.k_T; f.inv_ksum = 1.0 / f.ksum; f.fast_k = divc_ok(f.ksum);
         f.cpT = cp.cp_T; f.th_exp = cp.th_exp; f.q_source = cp.q_source;
+        f.AlphaAvg = (cp.Alpha + cp.Alpha) / 2.0; f.BetaAvg = (cp.Beta + cp.Beta) / 2.0;
+        f.AlphaCij = f.AlphaAvg * (0.5 * (cp.Cs + cp.Cs)); f.h2_001 = 0.01 * f.h * f.h;
     }
     a.n = c->n_loc; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
     a.nbr = c->nbr; a.nb_cnt = c->nb_cnt; a.nb_hi = c->nb_hi; a.orig = c->Ip(I_ORIG); a.cls_of = c->Ip(I_CLS); a.is_free = c->any_fixed ? c->Ip(I_FREE) : nullptr;
@@ -529,6 +622,12 @@ PairArgs make_args(wf_ctx *c)
     return a;
 }
 
+// lean momentum kernel: uniform class with PresEq 0 (constant sound speed), TIn = 4, Markstein-safe h and W0, 3-D
+inline bool lean_ok(const wf_ctx *c, const PairArgs &a)
+{
+    const FastConsts &f = a.fc;
+    return a.dim == 3 && f.PresEq == 0 && f.fast_h && (!c->any_ti || (f.TI > 0.0 && f.TIn == 4.0 && f.fast_W0)) && !c->any_fixed;
+}
 inline bool use_pf(const wf_ctx *c) { return (c->prm.tuning & 1) == 0; }     // bit 0 of wf_params::tuning switches the software pipeline OFF
 
 } // namespace
@@ -571,7 +670,15 @@ int pair_accel(wf_ctx *c)
     const bool fast = fast_path(c);
     const bool mb3 = (c->prm.tuning & 2) == 0;        // 3 resident blocks per SM (168 registers) by default; bit 1 of wf_params::tuning selects 4 (128 registers, spills)
     switch (a.gt) {
-    case 0: if (fast) { if (c->prm.tuning & 4) WF_LAUNCH_PF(k_accel, true, 0, 2); else if (mb3) WF_LAUNCH_PF(k_accel, true, 0, 3); else WF_LAUNCH_PF(k_accel, true, 0, 4); }
+    case 0: if (fast && lean_ok(c, a) && !(c->prm.tuning & 8)) {        // bit 3 of wf_params::tuning: the general FAST kernel instead of the lean one
+                const bool w256 = (c->prm.tuning & 32) == 0;           // bit 5: 2 x LDG.128 per gathered record instead of one LDG.256
+                if (c->any_ti) {
+                    if (c->prm.tuning & 16) { if (w256) k_accel_lean<true, 4, true><<<g, 128, 0, c->stream>>>(a); else k_accel_lean<true, 4, false><<<g, 128, 0, c->stream>>>(a); }
+                    else { if (w256) k_accel_lean<true, 3, true><<<g, 128, 0, c->stream>>>(a); else k_accel_lean<true, 3, false><<<g, 128, 0, c->stream>>>(a); }
+                }
+                else { if (w256) k_accel_lean<false, 4, true><<<g, 128, 0, c->stream>>>(a); else k_accel_lean<false, 4, false><<<g, 128, 0, c->stream>>>(a); }
+            }
+            else if (fast) { if (c->prm.tuning & 4) WF_LAUNCH_PF(k_accel, true, 0, 2); else if (mb3) WF_LAUNCH_PF(k_accel, true, 0, 3); else WF_LAUNCH_PF(k_accel, true, 0, 4); }
             else WF_LAUNCH_PF(k_accel, false, 0, 4); break;
     case 1: if (fast) WF_LAUNCH_PF(k_accel, true, 1, 4); else WF_LAUNCH_PF(k_accel, false, 1, 4); break;
     default: if (fast) WF_LAUNCH_PF(k_accel, true, 2, 4); else WF_LAUNCH_PF(k_accel, false, 2, 4); break;

@@ -114,7 +114,7 @@ __device__ inline bool is_mesh_id(int id, int4 mids) { return id == mids.x || id
 __global__ void __launch_bounds__(128)
 k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long long *keys, const int *cell_start, const int *cell_end,
           const double4 *__restrict__ Q0, const double4 *__restrict__ Q2, const int *__restrict__ orig, const int *__restrict__ ID,
-          const int *__restrict__ cls_of, const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material,
+          const int *__restrict__ cls_of, const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material, int uniform_h,
           uint32_t *nbr, int *nb_cnt, int *nb_hi, int *nbI, double *normal_x, double *normal_y, double *normal_z, int *d_maxcnt)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,40 +132,58 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
             const double4 qi = Q0[s];
             const V3 xi = v3(qi.x, qi.y, qi.z);
             const int mat_i = check_material ? classes[cls_of[s]].Material : 0;
+            const double lim_u = g.Cellfac * ((qi.w + qi.w) / 2), thr_u = (lim_u * lim_u) * (1.0 + 8e-15);     // uniform h: (h+h)/2 == h
             int c[3]; g.unlin((int)(keys[s] >> 32), c);
             for (int e = 0; e < 27; ++e) {
                 int d[3] = { c[0] + c_walk[e][0], c[1] + c_walk[e][1], c[2] + c_walk[e][2] };
                 if (d[0] < 0 || d[0] >= g.CellNo[0] || d[1] < 0 || d[1] >= g.CellNo[1] || d[2] < 0 || d[2] >= g.CellNo[2]) continue;
                 const int l = g.lin(d);
-                int js = cell_start[l], je = cell_end[l];
+                const int js = cell_start[l], je = cell_end[l];
                 const int role = c_walk[e][3];
-                for (int j = js; j < je; ++j) {
-                    if (j == (int)s) continue;
-                    const int oj = orig[j];
-                    if (oj >= nsph) continue;                               // rigid-mesh particle: never an SM pair
-                    if (contact && is_mesh_id(ID[j], mids)) continue;
-                    if (is_free && !is_free[j]) continue;
-                    const double4 qj = Q0[j];
-                    // own cell: particles stored before s have a larger creation index and act as temp1
-                    const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
-                    const double hh = (qi.w + qj.w) / 2;
-                    const V3 xj = v3(qj.x, qj.y, qj.z);
-                    const V3 xij = ifirst ? (xi - xj) : (xj - xi);
-                    // CheckRadius (Neighbour.cpp:361-372): sqrt(|xij|^2)/hh <= Cellfac. The squared form decides every candidate
-                    // that is not within a few ulp of the cutoff (sqrt and the division each round within 2^-53 relative);
-                    // only those borderline ones take the exact expression.
-                    const double d2 = dot(xij, xij), lim = g.Cellfac * hh, lim2 = lim * lim;
-                    if (d2 > lim2 * (1.0 + 8e-15)) continue;
-                    if (!(d2 < lim2 * (1.0 - 8e-15))) { const double rij = sqrt(d2); if (!((rij / hh) <= g.Cellfac)) continue; }
-                    if (check_material && classes[cls_of[j]].Material != mat_i) continue;
-                    uint32_t entry = (uint32_t)j | (ifirst ? 0x80000000u : 0u);
-                    if (oj > oi) { if (nhi + nlo < K) nbr[(int64_t)nhi * cap + s] = entry; ++nhi; }
-                    else         { if (nhi + nlo < K) nbr[(int64_t)(K - 1 - nlo) * cap + s] = entry; ++nlo; }
-                    if (contact) {
-                        // Domain.cpp:1446-1463: P1->normal += mj*xij ; P2->normal -= mi*xij, in discovery order
-                        const double mj = Q2[j].x;
-                        if (ifirst) { nx += mj * xij.x; ny += mj * xij.y; nz += mj * xij.z; }
-                        else        { nx -= mj * xij.x; ny -= mj * xij.y; nz -= mj * xij.z; }
+                // two phases per cell: (1) a store-free squared-distance sweep over the cell's candidates, 32 at a time, whose
+                // loads the compiler can batch (lanes of one cell read the same record: one L1 wavefront); (2) the reference's
+                // exact test and the list update, in candidate order, for the few that passed.
+                for (int base = js; base < je; base += 32) {
+                    const int m = min(32, je - base);
+                    unsigned mask = 0u;
+#pragma unroll 4
+                    for (int k = 0; k < m; ++k) {
+                        const double4 qj = Q0[base + k];
+                        const double ex = xi.x - qj.x, ey = xi.y - qj.y, ez = xi.z - qj.z;
+                        const double d2 = ex * ex + (ey * ey + ez * ez);          // == dot(xij, xij) for either sign of xij
+                        double thr = thr_u;
+                        if (!uniform_h) { const double hh = (qi.w + qj.w) / 2, lim = g.Cellfac * hh; thr = (lim * lim) * (1.0 + 8e-15); }
+                        if (!(d2 > thr)) mask |= 1u << k;
+                    }
+                    while (mask) {
+                        const int j = base + (__ffs(mask) - 1); mask &= mask - 1u;
+                        if (j == (int)s) continue;
+                        const int oj = orig[j];
+                        if (oj >= nsph) continue;                               // rigid-mesh particle: never an SM pair
+                        if (contact && is_mesh_id(ID[j], mids)) continue;
+                        if (is_free && !is_free[j]) continue;
+                        const double4 qj = Q0[j];
+                        // own cell: particles stored before s have a larger creation index and act as temp1
+                        const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
+                        const double hh = (qi.w + qj.w) / 2;
+                        const V3 xj = v3(qj.x, qj.y, qj.z);
+                        const V3 xij = ifirst ? (xi - xj) : (xj - xi);
+                        // CheckRadius (Neighbour.cpp:361-372): sqrt(|xij|^2)/hh <= Cellfac. The squared form decides every candidate
+                        // that is not within a few ulp of the cutoff (sqrt and the division each round within 2^-53 relative);
+                        // only those borderline ones take the exact expression.
+                        const double d2 = dot(xij, xij), lim = g.Cellfac * hh, lim2 = lim * lim;
+                        if (d2 > lim2 * (1.0 + 8e-15)) continue;
+                        if (!(d2 < lim2 * (1.0 - 8e-15))) { const double rij = sqrt(d2); if (!((rij / hh) <= g.Cellfac)) continue; }
+                        if (check_material && classes[cls_of[j]].Material != mat_i) continue;
+                        uint32_t entry = (uint32_t)j | (ifirst ? 0x80000000u : 0u);
+                        if (oj > oi) { if (nhi + nlo < K) nbr[(int64_t)nhi * cap + s] = entry; ++nhi; }
+                        else         { if (nhi + nlo < K) nbr[(int64_t)(K - 1 - nlo) * cap + s] = entry; ++nlo; }
+                        if (contact) {
+                            // Domain.cpp:1446-1463: P1->normal += mj*xij ; P2->normal -= mi*xij, in discovery order
+                            const double mj = Q2[j].x;
+                            if (ifirst) { nx += mj * xij.x; ny += mj * xij.y; nz += mj * xij.z; }
+                            else        { nx -= mj * xij.x; ny -= mj * xij.y; nz -= mj * xij.z; }
+                        }
                     }
                 }
             }
@@ -377,7 +395,7 @@ int nb_build_impl(wf_ctx *c)
         if ((int64_t)K * cap > c->nbr_alloc) { cudaFree(c->nbr); c->nbr = nullptr; WF_CUDA(c, cudaMalloc(&c->nbr, (size_t)K * cap * sizeof(uint32_t))); c->nbr_alloc = (int64_t)K * cap; }
         WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt, 0, 4 * sizeof(int), st));
         k_nb_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->cell_start, c->cell_end, c->Q0[c->cur], c->Q2[c->cur], c->Ip(I_ORIG), c->Ip(I_ID),
-            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
+            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->uniform_h ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
         WF_LAUNCH_CHECK(c); c->launches++;
         int mx = 0; WF_CUDA(c, cudaMemcpyAsync(&mx, c->d_maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));
         if (mx <= K) break;

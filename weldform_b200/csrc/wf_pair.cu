@@ -495,7 +495,7 @@ __global__ void k_thermal_pre(PairArgs a)
 // walk; each sum keeps its own reference order and operand order. Thermal: the m/rho factor is the SECOND particle's
 // of the reference pair, and the sums run in list order (round-off level difference to the reference's pair-discovery
 // order when several threads race in the reference; identical for Nproc = 1).
-template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF> __global__ void __launch_bounds__(128, 4) k_post(PairArgs a)
+template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __global__ void __launch_bounds__(128, MB) k_post(PairArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n) return;
@@ -696,7 +696,10 @@ int pair_post(wf_ctx *c)
     if (th || c->prm.pl_heating) { k_thermal_pre<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
     WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2));   // x, v, T of the halos after the move / temperature update
     const bool fast = fast_path(c);
-    if (th) { if (fast) WF_LAUNCH_PF(k_post, true, true, true, true); else WF_LAUNCH_PF(k_post, false, true, true, true); }
+    if (th && fast && pf && (c->prm.tuning & (64 | 128))) {      // bits 6 / 7 of wf_params::tuning: 5 / 3 resident blocks per SM for the fused pass (A/B measurements)
+        if (c->prm.tuning & 64) k_post<true, true, true, true, true, 5><<<g, 128, 0, c->stream>>>(a); else k_post<true, true, true, true, true, 3><<<g, 128, 0, c->stream>>>(a);
+    }
+    else if (th) { if (fast) WF_LAUNCH_PF(k_post, true, true, true, true); else WF_LAUNCH_PF(k_post, false, true, true, true); }
     else    { if (fast) WF_LAUNCH_PF(k_post, true, false, true, true); else WF_LAUNCH_PF(k_post, false, false, true, true); }
     WF_LAUNCH_CHECK(c); c->launches++;
     c->dens_valid = true;

@@ -50,7 +50,7 @@ typedef struct wf_params {
     int    cont_heat_fric, cont_heat_cond;
     double contact_hc;
     int    nb_order_reference; /* 1: neighbour lists in the reference's Nproc=1 summation order (default) */
-    int    tuning;             /* bit 0: disable the software-pipelined gathers of the pair kernels (A/B measurements); default 0 */
+    int    tuning;             /* bit 0: disable the software-pipelined gathers of the pair kernels (A/B measurements), bit 8: multi-GPU mesh-particle layout on one GPU; default 0 */
 } wf_params;
 
 /* Material_ subclasses (Source/Material.h:96-224). model: 0 bilinear (no object), 1 Hollomon, 2 Johnson-Cook. */
@@ -185,6 +185,11 @@ int wf_comm_init(wf_ctx *ctx, int rank, int nranks, const void *id128);
 int wf_comm_info(wf_ctx *ctx, int64_t out[8]);      /* n_local, n_halo, migrated_out, migrated_in, layer_lo, layer_hi, halo bytes sent per step, layers */
 int wf_plan_slabs(const double *x, const double *h, int64_t n, int kernel_type, const double dom_min[3], const double dom_max[3],
                   int nranks, int32_t *rank_of, int32_t *bounds);   /* host-only planner: same grid + balancing code as the library */
+/* Same with rigid meshes: x, h = the n_sph SPH particles followed by the element particles (centroid, (float)hfac*radius), which
+ * shape the cell grid like every particle does (Neighbour.cpp:10-139) but are not distributed: each rank is given ALL meshes
+ * (wf_add_mesh) and keeps a replica of their element particles; rank_of = -1 for them. */
+int wf_plan_slabs_ex(const double *x, const double *h, int64_t n, int64_t n_sph, int kernel_type, const double dom_min[3], const double dom_max[3],
+                     int nranks, int32_t *rank_of, int32_t *bounds);
 
 /* timing helper for bench.py: CUDA-event time (ms) of each kernel family accumulated since the last reset */
 int wf_prof_enable(wf_ctx *ctx, int on);

@@ -124,3 +124,28 @@ def test_multi_gpu_bit_identical_to_single(product_lib, oracle_port, nranks, amp
     ref = ot.run_port(case)
     worst = {k: ot.max_rel(multi[k], ref[k]) for k in ("x", "v", "Displacement", "pl_strain", "T", "Density", "Sigma")}
     assert max(worst.values()) < 1e-6, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs (gpurun --gpus 2)")
+def test_multi_gpu_contact_bit_identical_to_single(product_lib, oracle_port):
+    """Rigid-mesh contact on the slab decomposition: every rank keeps a replica of the meshes and of their element
+    particles (outside the cell table), contact candidates and forces are computed by the owner of the SPH particle."""
+    from weldform_b200 import harness
+    case = cases.contact_compression(dx=0.0024, nsteps=150, vmax=5.0, tau=1e-5, dens=10, cfl=0.3)
+    multi, info = _run_multi(case, 2)
+    single = harness.run_case(case)
+    assert all(i[1] > 0 for i in info), "every rank must hold halo particles"
+    assert single["cont_pairs"].size > 0 and np.array_equal(multi["cont_pairs"], single["cont_pairs"])
+    assert np.array_equal(multi["pairs"], single["pairs"])
+    bad = {k: ot.max_rel(multi[k], single[k]) for k in cases.FIELDS_F64 + ["ID", "Nb"] if not np.array_equal(multi[k], single[k])}
+    assert not bad, "multi-GPU contact differs from single GPU per particle: %s" % bad
+    assert (single["delta_cont"] > 0).sum() > 20
+    for k in ("Time", "max_disp", "mesh0_nodes", "mesh1_nodes"):
+        if k in single:
+            assert np.array_equal(multi[k], single[k]), k
+    for k in ("contact_force_sum", "ext_forces_work", "plastic_work"):
+        assert ot.max_rel(multi[k], single[k]) < 1e-12, k
+    ref = ot.run_port(case)
+    worst = {k: ot.max_rel(multi[k], ref[k]) for k in ("x", "v", "Displacement", "pl_strain", "Density", "Sigma", "contforce", "delta_cont")}
+    assert max(worst.values()) < 1e-6, worst

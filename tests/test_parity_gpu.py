@@ -71,6 +71,23 @@ def test_golden_multi_step_tight(harness, name):
     _compare(harness.run_case(case), ref, 1e-7, what=name)
 
 
+@pytest.mark.parametrize("name", ["contact_1step", "contact_100"])
+def test_mesh_tail_layout_equals_cell_layout(harness, name):
+    """wf_params::tuning bit 8 runs the multi-GPU layout of the rigid-mesh element particles (kept out of the cell table,
+    matched by k_cont_list_tail) on one GPU: same contact candidate lists in the same order, hence the same bits."""
+    case, ref = golden_tools.load(name)
+    base = harness.run_case(case)
+    case = dict(case); case["tuning"] = 256.0
+    tail = harness.run_case(case)
+    assert tail["cont_pairs"].size > 0 and np.array_equal(tail["cont_pairs"], base["cont_pairs"])
+    bad = [k for k in cases.FIELDS_F64 + ["ID", "Nb", "pairs"] if k in base and not np.array_equal(tail[k], base[k])]
+    assert not bad, "mesh-tail layout differs from the cell layout: %s" % bad
+    for k in cases.SCALARS:                                  # domain totals: the slot order, hence the reduction tree, differs
+        if k in base:
+            assert ot.max_rel(tail[k], base[k]) < 1e-12, k
+    _compare(tail, ref, TOL_ONE_STEP if name.endswith("1step") else 1e-7, what=name + " (mesh tail)")
+
+
 def test_pairs_bit_exact_12k(harness, oracle_port):
     c = cases.perturbed(cases.compression(dx=0.015, nsteps=1)); c["mode"] = 1.0
     got, ref = harness.run_case(c), ot.run_port(c)

@@ -98,6 +98,7 @@ def load_library():
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
         "wf_comm_unique_id": ([vp], C.c_int), "wf_comm_init": ([vp, C.c_int, C.c_int, vp], C.c_int), "wf_comm_info": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "wf_plan_slabs": ([_PD, _PD, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
+        "wf_plan_slabs_ex": ([_PD, _PD, C.c_int64, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
         "wf_get_stream": ([vp], vp), "wf_measure_fp64_peak": ([vp, _PD], C.c_int),
         "wf_prof_name": ([C.c_int], C.c_char_p), "wf_launch_count": ([vp, C.POINTER(C.c_int64)], C.c_int),
     }
@@ -150,15 +151,16 @@ def comm_unique_id():
     return bytes(buf)
 
 
-def plan_slabs(x, h, nranks, kernel_type=0, dom_min=None, dom_max=None):
-    """Host-only planner (wf_plan_slabs): -> (rank_of[n], layer bounds[nranks+1]) of the slab decomposition."""
+def plan_slabs(x, h, nranks, kernel_type=0, dom_min=None, dom_max=None, n_sph=None):
+    """Host-only planner (wf_plan_slabs_ex): -> (rank_of[n], layer bounds[nranks+1]) of the slab decomposition. With rigid
+    meshes x, h hold the n_sph SPH particles followed by the element particles (rank_of = -1: replicated)."""
     L = load_library()
     x = np.ascontiguousarray(x, np.float64).reshape(-1, 3); h = np.ascontiguousarray(h, np.float64)
     n = len(x)
     rank_of = np.empty(n, np.int32); bounds = np.empty(nranks + 1, np.int32)
     dmin = (C.c_double * 3)(*(dom_min if dom_min is not None else (1e11, 1e11, 1e11)))
     dmax = (C.c_double * 3)(*(dom_max if dom_max is not None else (-1e11, -1e11, -1e11)))
-    rc = L.wf_plan_slabs(_dp(x), _dp(h), n, int(kernel_type), dmin, dmax, int(nranks), _ip(rank_of), _ip(bounds))
+    rc = L.wf_plan_slabs_ex(_dp(x), _dp(h), n, int(n if n_sph is None else n_sph), int(kernel_type), dmin, dmax, int(nranks), _ip(rank_of), _ip(bounds))
     if rc != 0:
         raise WeldformError("wf_plan_slabs failed (%d): fewer cell layers than ranks, or bad arguments" % rc)
     return rank_of, bounds

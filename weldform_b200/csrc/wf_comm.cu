@@ -137,6 +137,30 @@ int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax)
     return 0;
 }
 
+// CalculateSurface (Domain.cpp:1421-1425) sums the particle masses serially in creation order; with the particles spread over
+// ranks every rank scatters its masses into a zeroed creation-ordered array, the arrays are summed (exact: one non-zero
+// contributor per entry) and each rank repeats the reference's serial sum over the result.
+static __global__ void k_scatter_mass(const double *m, const long long *gidx, long long n, double *all)
+{ long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) all[gidx[i]] = m[i]; }
+int comm_serial_mass_sum(wf_ctx *c, const double *mass, const int64_t *gidx, int64_t n_local, int64_t n_global, double *tot)
+{
+    NcclApi *A = nccl_api();
+    double *d_all = nullptr, *d_m = nullptr; long long *d_g = nullptr;
+    WF_CUDA(c, cudaMalloc(&d_all, n_global * sizeof(double))); WF_CUDA(c, cudaMalloc(&d_m, n_local * sizeof(double))); WF_CUDA(c, cudaMalloc(&d_g, n_local * sizeof(long long)));
+    WF_CUDA(c, cudaMemsetAsync(d_all, 0, n_global * sizeof(double), c->stream));
+    WF_CUDA(c, cudaMemcpyAsync(d_m, mass, n_local * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    WF_CUDA(c, cudaMemcpyAsync(d_g, gidx, n_local * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    k_scatter_mass<<<grid_for(n_local, 256), 256, 0, c->stream>>>(d_m, d_g, n_local, d_all); WF_LAUNCH_CHECK(c);
+    WF_NCCL(c, A->AllReduce(d_all, d_all, (size_t)n_global, ncclDouble, ncclSum, (ncclComm_t)c->comm.nccl, c->stream));
+    std::vector<double> h(n_global);
+    WF_CUDA(c, cudaMemcpyAsync(h.data(), d_all, n_global * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_all); cudaFree(d_m); cudaFree(d_g);
+    double t = 0.; for (int64_t i = 0; i < n_global; ++i) t += h[i];
+    *tot = t;
+    return 0;
+}
+
 int comm_plan_layers(wf_ctx *c, const std::vector<long long> &hist_local)
 {
     if (c->comm.nranks <= 1) return 0;
@@ -358,8 +382,15 @@ extern "C" int wf_comm_info(wf_ctx *c, int64_t out[8])
 // (Neighbour.cpp:10-139) and the same balancing code the library uses. rank_of[i] in [0, nranks), bounds[nranks+1] layers.
 extern "C" int wf_plan_slabs(const double *x, const double *h, int64_t n, int kernel_type, const double dom_min[3], const double dom_max[3],
                              int nranks, int32_t *rank_of, int32_t *bounds)
+{ return wf_plan_slabs_ex(x, h, n, n, kernel_type, dom_min, dom_max, nranks, rank_of, bounds); }
+
+// With rigid meshes: x, h hold the n_sph SPH particles followed by the element particles (centroid, hfac*radius). All of
+// them shape the cell grid (bounding box, hmax -- Neighbour.cpp:10-139 runs over every particle), only the SPH particles are
+// distributed (rank_of = -1 for the element particles: every rank keeps a replica of the meshes).
+extern "C" int wf_plan_slabs_ex(const double *x, const double *h, int64_t n, int64_t n_sph, int kernel_type, const double dom_min[3], const double dom_max[3],
+                                int nranks, int32_t *rank_of, int32_t *bounds)
 {
-    if (!x || !h || n <= 0 || nranks < 1) return WF_ERR_ARG;
+    if (!x || !h || n <= 0 || n_sph <= 0 || n_sph > n || nranks < 1) return WF_ERR_ARG;
     const double Cellfac = (kernel_type == 2) ? 3.0 : 2.0;
     double BL[3] = { x[0], x[1], x[2] }, TR[3] = { x[0], x[1], x[2] }, hmax = h[0];
     for (int64_t i = 0; i < n; ++i) { for (int k = 0; k < 3; ++k) { if (x[3 * i + k] > TR[k]) TR[k] = x[3 * i + k]; if (x[3 * i + k] < BL[k]) BL[k] = x[3 * i + k]; } if (h[i] > hmax) hmax = h[i]; }
@@ -383,10 +414,10 @@ extern "C" int wf_plan_slabs(const double *x, const double *h, int64_t n, int ke
     for (int64_t i = 0; i < n; ++i) {
         int ci = (int)std::floor((x[3 * i + slow] - BL[slow]) / CellSize[slow]);
         if (ci < 0) ci = 0; if (ci >= L) ci = L - 1;
-        layer[i] = ci; hist[ci]++;
+        layer[i] = ci; if (i < n_sph) hist[ci]++;
     }
     std::vector<int> b; wf::balance_layers(hist, nranks, b);
     if (bounds) for (int r = 0; r <= nranks; ++r) bounds[r] = b[r];
-    if (rank_of) for (int64_t i = 0; i < n; ++i) { int r = (int)(std::upper_bound(b.begin(), b.end(), layer[i]) - b.begin()) - 1; rank_of[i] = std::min(std::max(r, 0), nranks - 1); }
+    if (rank_of) for (int64_t i = 0; i < n; ++i) { int r = (int)(std::upper_bound(b.begin(), b.end(), layer[i]) - b.begin()) - 1; rank_of[i] = i < n_sph ? std::min(std::max(r, 0), nranks - 1) : -1; }
     return 0;
 }

@@ -233,11 +233,11 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     const bool multi = c->comm.nranks > 1;
     const int64_t nsph_global = (multi && p->n_sph_global > 0) ? p->n_sph_global : nsph;
     if (nsph_global + nmeshp >= (int64_t)1 << 31) return fail(c, WF_ERR_UNSUPPORTED, "more than 2^31-1 particles per domain");
-    if (multi && nmeshp > 0) return fail(c, WF_ERR_UNSUPPORTED, "rigid-mesh contact is not implemented for the multi-GPU decomposition yet");
     if (multi && !p->global_index) return fail(c, WF_ERR_ARG, "wf_set_particles: global_index is required when nranks > 1");
     c->any_fixed = false;
     if (p->is_free) for (int64_t i = 0; i < nsph; ++i) if (!p->is_free[i]) { c->any_fixed = true; break; }
-    c->n = n; c->n_loc = n; c->nsph = nsph_global;
+    c->n = n; c->n_loc = n; c->nsph = nsph_global; c->nmeshp = nmeshp;
+    c->mesh_tail = nmeshp > 0 && (multi || (c->prm.tuning & 256));   // bit 8 of wf_params::tuning: the multi-GPU mesh-particle layout on one GPU (tests)
     WF_CHECK(alloc_particles(c, multi ? n + n / 4 + 262144 : n));
     const int64_t cap = c->cap;
 
@@ -295,7 +295,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         int tn = 0, te = 0; for (auto &pm : c->pending_meshes) { tn += (int)pm.nodes.size() / 3; te += (int)pm.nfar.size(); }
         std::vector<double> nodes(3 * tn), enormal(3 * te), ev(3 * te, 0.0), pplane(te), nodev(3 * tn, 0.0);
         std::vector<int> en(3 * te), nfar(te), emesh(te);
-        int n0 = 0, e0 = 0; int64_t fp = nsph;
+        int n0 = 0, e0 = 0; int64_t fp = nsph_global;      // creation index of the first element particle: after ALL SPH particles (Contact.cpp:12)
         for (size_t m = 0; m < c->pending_meshes.size(); ++m) {
             auto &pm = c->pending_meshes[m]; int nn = (int)pm.nodes.size() / 3, ne = (int)pm.nfar.size();
             HostMesh hm; hm.node0 = n0; hm.elem0 = e0; hm.n_nodes = nn; hm.n_elems = ne; hm.id = pm.id; hm.first_particle = fp;
@@ -312,7 +312,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
                 V3 b = v3(pm.nodes[3 * pm.elems[3 * e + 1]], pm.nodes[3 * pm.elems[3 * e + 1] + 1], pm.nodes[3 * pm.elems[3 * e + 1] + 2]);
                 V3 d = v3(pm.nodes[3 * pm.elems[3 * e + 2]], pm.nodes[3 * pm.elems[3 * e + 2] + 1], pm.nodes[3 * pm.elems[3 * e + 2] + 2]);
                 V3 cen = ((a + b) + d) / 3.;
-                int64_t q = (fp - nsph) + e;
+                int64_t q = (fp - nsph_global) + e;
                 mx[3 * q] = cen.x; mx[3 * q + 1] = cen.y; mx[3 * q + 2] = cen.z;
                 mh[q] = (double)(float)pm.hfac * pm.radius[e]; mids[q] = pm.id;
             }
@@ -362,7 +362,8 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         tot += m;                                   // serial, creation order (Domain.cpp:1421-1423)
         q[i] = make_double4(m, i < nsph ? p->density[i] : 0.0, (i < nsph && p->T) ? p->T[i] : 0.0, 0.0);
     }
-    c->totmass_mean = tot / (double)n;
+    if (multi && nmeshp > 0) WF_CHECK(comm_serial_mass_sum(c, p->mass, p->global_index, nsph, nsph_global, &tot));
+    c->totmass_mean = tot / (double)(nsph_global + nmeshp);
     WF_CUDA(c, cudaMemcpy(c->Q2[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
     {
         std::vector<double> sy(n, 0.0);
@@ -388,7 +389,8 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         WF_CUDA(c, cudaMemcpy(c->I[0] + (int64_t)I_LID * cap, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         WF_CUDA(c, cudaMemcpy(c->slot_of, iv.data(), n * sizeof(int), cudaMemcpyHostToDevice));
         if (multi) {
-            for (int64_t i = 0; i < n; ++i) {
+            for (int64_t i = nsph; i < n; ++i) iv[i] = (int)(nsph_global + (i - nsph));
+            for (int64_t i = 0; i < nsph; ++i) {
                 if (p->global_index[i] < 0 || p->global_index[i] >= nsph_global) return fail(c, WF_ERR_ARG, "global_index[%lld] out of range", (long long)i);
                 if (i > 0 && p->global_index[i] <= p->global_index[i - 1]) return fail(c, WF_ERR_ARG, "global_index must be strictly ascending");
                 iv[i] = (int)p->global_index[i];
@@ -402,7 +404,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
 }
 
 extern "C" int64_t wf_num_particles(const wf_ctx *c) { return c ? c->n_loc : 0; }      /* this rank's particles (SPH + mesh), halos excluded */
-extern "C" int64_t wf_num_sph(const wf_ctx *c) { return c ? (c->comm.nranks > 1 ? c->n_loc : c->nsph) : 0; }
+extern "C" int64_t wf_num_sph(const wf_ctx *c) { return c ? (c->comm.nranks > 1 ? c->n_loc - c->nmeshp : c->nsph) : 0; }
 
 extern "C" int wf_mesh_set_motion(wf_ctx *c, int mesh, const double v[3], const double w[3])
 {

@@ -74,6 +74,8 @@ struct wf_ctx {
 
     int64_t n = 0, nsph = 0, cap = 0;            // active slots (local + halo), GLOBAL SPH count, allocated slots
     int64_t n_loc = 0;                           // slots [0, n_loc) are this rank's own particles (== n on one GPU); halos follow
+    int64_t nmeshp = 0;                          // rigid-mesh element particles (replicated on every rank of a multi-GPU run)
+    bool mesh_tail = false;                      // mesh particles are kept out of the cell table (sorted to the tail of the local region, see wf_neighbour.cu)
     // ---- multi-GPU (wf_comm.cu): 1-D slab decomposition along the slowest cell axis, NCCL point-to-point halos
     struct Comm {
         void *nccl = nullptr;                    // ncclComm_t
@@ -175,6 +177,7 @@ int comm_halo_refresh(wf_ctx *c, int sets);             // no-op on one GPU
 int comm_gather_scalars(wf_ctx *c, int nvals);          // d_rank -> d_all (all ranks), no-op on one GPU
 int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);
+int comm_serial_mass_sum(wf_ctx *c, const double *mass, const int64_t *gidx, int64_t n_local, int64_t n_global, double *tot);
 int comm_plan_layers(wf_ctx *c, const std::vector<long long> &hist);
 int comm_migrate(wf_ctx *c, int64_t *n_sort, int64_t *n_out);
 int comm_halo_setup(wf_ctx *c, const unsigned long long *sorted_keys);

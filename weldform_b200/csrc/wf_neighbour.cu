@@ -30,7 +30,12 @@ struct Grid {
 // Neighbour.cpp:185-225 ListGenerate: cell index with clamping
 // mig != 0 (multi-GPU): particles whose slow-axis cell layer left [layer_lo, layer_hi) get a sentinel key (they sort to
 // the tail and are dropped) and are listed for migration to the adjacent rank (emig[dir*emig_cap + k], cnt[dir])
-struct MigArgs { int on, layer_lo, layer_hi; long long plane; int *emig; int *cnt; long long emig_cap; };
+// mesh_tail != 0: rigid-mesh element particles (creation index >= nsph) get the virtual cell WF_VCELL: they sort behind every
+// real cell (a contiguous tail of the local region, descending creation index), stay out of the cell table, the halo slices
+// and the migration, and are matched against the free-surface particles by k_cont_list_tail. Every rank of a multi-GPU run
+// keeps a replica of all of them.
+#define WF_VCELL 0x7FFFFFFEu
+struct MigArgs { int on, layer_lo, layer_hi; long long plane; int *emig; int *cnt; long long emig_cap; int mesh_tail, nsph; };
 __global__ void k_cell_keys(Grid g, const double4 *Q0, const int *orig, int64_t n, int64_t s_off, unsigned long long *keys, int *vals, MigArgs mg)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,6 +48,11 @@ __global__ void k_cell_keys(Grid g, const double4 *Q0, const int *orig, int64_t 
         if (ci < 0) ci = 0;
         if (ci >= g.CellNo[k]) ci = g.CellNo[k] - 1;
         c[k] = ci;
+    }
+    if (mg.mesh_tail && orig[s] >= mg.nsph) {
+        keys[s] = ((unsigned long long)WF_VCELL << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)orig[s]);
+        vals[s] = (int)s;
+        return;
     }
     // descending creation index inside a cell == the order the reference's push-front linked list is walked in
     const int lin = g.lin(c);
@@ -90,7 +100,7 @@ __global__ void k_cell_bounds(int64_t n, const unsigned long long *keys, int *ce
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int cell = (int)(keys[s] >> 32);
-    if (cell < 0) return;                      // migration sentinel
+    if (cell < 0 || cell == (int)WF_VCELL) return;   // migration sentinel / mesh-particle tail
     if (s == 0 || (int)(keys[s - 1] >> 32) != cell) cell_start[cell] = (int)s;
     if (s == n - 1 || (int)(keys[s + 1] >> 32) != cell) cell_end[cell] = (int)s + 1;
 }
@@ -254,6 +264,57 @@ k_cont_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long
     if (threadIdx.x == 0 && m > 0) atomicMax(d_maxcnt, m);
 }
 
+// Same lists as k_cont_list when the mesh particles live in the tail [tail0, tail0 + ntail) instead of the cell table
+// (mesh_tail layout): every free-surface particle scans the tail, keeps the element particles of its 27 cells within
+// h_i + h_j and orders them as the cell walk would have met them -- walk position of the element particle's cell first,
+// descending creation index (the tail's own order) inside a cell.
+__global__ void __launch_bounds__(128)
+k_cont_list_tail(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long long *keys, const double4 *__restrict__ Q0, const int *__restrict__ orig,
+                 const int *__restrict__ ID, const int *__restrict__ oldsurf, int surf_id, int require_old, int64_t tail0, int ntail, int *cont, int *cont_cnt, int *d_maxcnt)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (s < n) {
+        const int oi = orig[s];
+        if (oi < nsph && ID[s] == surf_id && (!require_old || oldsurf[s])) {
+            const double4 qi = Q0[s]; const V3 xi = v3(qi.x, qi.y, qi.z);
+            int c[3]; g.unlin((int)(keys[s] >> 32), c);
+            for (int t = 0; t < ntail; ++t) {
+                const int64_t j = tail0 + t;
+                const double4 qj = Q0[j]; const double xj3[3] = { qj.x, qj.y, qj.z };
+                int d[3]; bool near = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {            // the element particle's cell, as k_cell_keys computes it
+                    int ci = (int)(floor((xj3[k] - g.BLPF[k]) / g.CellSize[k]));
+                    if (ci < 0) ci = 0;
+                    if (ci >= g.CellNo[k]) ci = g.CellNo[k] - 1;
+                    d[k] = ci - c[k];
+                    if (d[k] < -1 || d[k] > 1) near = false;
+                }
+                if (!near) continue;
+                int e = 0;
+                for (; e < 27; ++e) if (c_walk[e][0] == d[0] && c_walk[e][1] == d[1] && c_walk[e][2] == d[2]) break;
+                // own cell: element particles have the largest creation indices, i.e. they precede s in the cell: s is temp2
+                const int ifirst = (c_walk[e][3] == 2) ? 0 : c_walk[e][3];
+                const V3 xj = v3(qj.x, qj.y, qj.z);
+                const V3 xij = ifirst ? (xi - xj) : (xj - xi);
+                if (!(norm(xij) < (ifirst ? (qi.w + qj.w) : (qj.w + qi.w)))) continue;
+                if (cnt < K) {                          // stable insertion by walk position (entries carry it in bits 24..30 until the end)
+                    int pos = cnt;
+                    while (pos > 0 && (cont[(int64_t)(pos - 1) * cap + s] >> 24) > e) { cont[(int64_t)pos * cap + s] = cont[(int64_t)(pos - 1) * cap + s]; --pos; }
+                    cont[(int64_t)pos * cap + s] = (e << 24) | (orig[j] - nsph);
+                }
+                ++cnt;
+            }
+            for (int k = 0; k < cnt && k < K; ++k) cont[(int64_t)k * cap + s] &= 0xFFFFFF;
+        }
+        cont_cnt[s] = cnt;
+    }
+    typedef cub::BlockReduce<int, 128> BR; __shared__ typename BR::TempStorage tmp;
+    int m = BR(tmp).Reduce(cnt, cub::Max());
+    if (threadIdx.x == 0 && m > 0) atomicMax(d_maxcnt, m);
+}
+
 __global__ void k_export_pairs(int64_t n, int64_t cap, int K, const uint32_t *nbr, const int *nb_hi, const int *orig, const int64_t *offs, int64_t *out)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,7 +382,7 @@ int nb_cell_initiate(wf_ctx *c)
     if (c->comm.nranks > 1) {
         const int slow = c->ax_slow, L = c->CellNo[slow];
         std::vector<long long> hist(L, 0);
-        for (int64_t s = 0; s < n; ++s) {
+        for (int64_t s = 0; s < n - c->nmeshp; ++s) {          // SPH particles only: element particles are replicated, not owned
             const double xs = slow == 0 ? q[s].x : (slow == 1 ? q[s].y : q[s].z);
             int ci = (int)std::floor((xs - c->BLPF[slow]) / c->CellSize[slow]);
             if (ci < 0) ci = 0; if (ci >= L) ci = L - 1;
@@ -344,6 +405,7 @@ int nb_build_impl(wf_ctx *c)
     const int a = c->cur, b = 1 - c->cur;
     MigArgs mg; mg.on = multi ? 1 : 0; mg.layer_lo = c->comm.layer_lo; mg.layer_hi = c->comm.layer_hi;
     mg.plane = (long long)c->CellNo[c->ax_mid] * c->CellNo[c->ax_fast]; mg.emig = c->comm.d_emig; mg.cnt = c->comm.d_cnt; mg.emig_cap = c->comm.emig_cap;
+    mg.mesh_tail = c->mesh_tail ? 1 : 0; mg.nsph = (int)c->nsph;
     {   ProfScope ps(c, PK_NB_KEYS);
         if (multi) WF_CUDA(c, cudaMemsetAsync(c->comm.d_cnt, 0, 4 * sizeof(int), st));
         k_cell_keys<<<grid_for(n, B), B, 0, st>>>(g, c->Q0[a], c->Ip(I_ORIG), n, 0, c->keys[0], c->vals[0], mg); WF_LAUNCH_CHECK(c); c->launches++;
@@ -351,14 +413,14 @@ int nb_build_impl(wf_ctx *c)
             // migration: emigrants out, immigrants appended at [n_loc, n); their keys computed here (they are inside the slab by construction)
             int64_t n_sort = n;
             WF_CHECK(comm_migrate(c, &n_sort, &n_out));
-            if (n_sort > n) { MigArgs off = mg; off.on = 0;
+            if (n_sort > n) { MigArgs off = mg; off.on = 0; off.mesh_tail = 0;
                 k_cell_keys<<<grid_for(n_sort - n, B), B, 0, st>>>(g, c->Q0[a], c->Ip(I_ORIG), n_sort - n, n, c->keys[0], c->vals[0], off); WF_LAUNCH_CHECK(c); c->launches++; }
             n = n_sort;
         }
     }
     {   ProfScope ps(c, PK_NB_SORT);
         int cellbits = 1; while (((int64_t)1 << cellbits) < c->ncells) ++cellbits;
-        const int end_bit = multi ? 64 : 32 + cellbits;
+        const int end_bit = (multi || c->mesh_tail) ? 64 : 32 + cellbits;
         size_t need = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, need, c->keys[0], c->keys[1], c->vals[0], c->vals[1], (int)n, 0, end_bit, st);
         if (need > c->cub_tmp_bytes) { cudaFree(c->cub_tmp); c->cub_tmp = nullptr; WF_CUDA(c, cudaMalloc(&c->cub_tmp, need)); c->cub_tmp_bytes = need; }
@@ -375,7 +437,7 @@ int nb_build_impl(wf_ctx *c)
     if (multi) {
         ProfScope ps(c, PK_HALO);
         WF_CHECK(comm_halo_setup(c, c->keys[1]));     // boundary slices, halo regions filled: c->n = n_loc + halos
-        if (c->n > c->n_loc) { MigArgs off = mg; off.on = 0;
+        if (c->n > c->n_loc) { MigArgs off = mg; off.on = 0; off.mesh_tail = 0;
             k_cell_keys<<<grid_for(c->n - c->n_loc, B), B, 0, st>>>(g, c->Q0[c->cur], c->Ip(I_ORIG), c->n - c->n_loc, c->n_loc, c->keys[1], c->vals[0], off); WF_LAUNCH_CHECK(c); c->launches++; }
         WF_CHECK(comm_local_index(c));
     }
@@ -415,6 +477,10 @@ int nb_build_impl(wf_ctx *c)
             const int K = c->cont_k;
             if ((int64_t)K * cap > c->cont_alloc) { cudaFree(c->cont); c->cont = nullptr; WF_CUDA(c, cudaMalloc(&c->cont, (size_t)K * cap * sizeof(int))); c->cont_alloc = (int64_t)K * cap; }
             WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt + 2, 0, sizeof(int), st));
+            if (c->mesh_tail)
+                k_cont_list_tail<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->Q0[c->cur], c->Ip(I_ORIG), c->Ip(I_ID), c->Ip(I_OLDSURF),
+                    1, c->solver_ready ? 1 : 0, c->n_loc - c->nmeshp, (int)c->nmeshp, c->cont, c->cont_cnt, c->d_maxcnt + 2);
+            else
             k_cont_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->cell_start, c->cell_end, c->Q0[c->cur], c->Ip(I_ORIG), c->Ip(I_ID), c->Ip(I_OLDSURF),
                 1, c->solver_ready ? 1 : 0, c->cont, c->cont_cnt, c->d_maxcnt + 2);
             WF_LAUNCH_CHECK(c); c->launches++;

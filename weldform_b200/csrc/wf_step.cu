@@ -165,7 +165,7 @@ __global__ void k_mesh_elems(int n_elems, int nsph, const double *node, const do
     vv = vv / 3;
     ev[3 * e] = vv.x; ev[3 * e + 1] = vv.y; ev[3 * e + 2] = vv.z;
     // element particle: v = mean node velocity, a = 0, normal = element normal
-    const int s = slot_of[nsph + e];
+    const int s = slot_of[nsph + e];            // nsph = local index of the first element particle
     double4 q1 = Q1[s]; q1.x = vv.x; q1.y = vv.y; q1.z = vv.z; Q1[s] = q1;
     F[(int64_t)F_AX * cap + s] = 0.; F[(int64_t)F_AY * cap + s] = 0.; F[(int64_t)F_AZ * cap + s] = 0.;
     F[(int64_t)F_NX * cap + s] = nr.x; F[(int64_t)F_NY * cap + s] = nr.y; F[(int64_t)F_NZ * cap + s] = nr.z;
@@ -331,7 +331,7 @@ int step_end_impl(wf_ctx *c)
             k_mesh_nodes_one<<<grid_for(hm.n_nodes, 128), 128, 0, c->stream>>>(hm.n_nodes, c->dm.node + 3 * hm.node0, c->dm.node_v + 3 * hm.node0, c->dm.motion + 16 * m, c->dt);
             WF_LAUNCH_CHECK(c); c->launches++;
         }
-        k_mesh_elems<<<grid_for(c->dm.n_elems, 128), 128, 0, c->stream>>>(c->dm.n_elems, (int)c->nsph, c->dm.node, c->dm.node_v, c->dm.en, c->dm.nfar, c->dm.enormal, c->dm.ev, c->dm.pplane,
+        k_mesh_elems<<<grid_for(c->dm.n_elems, 128), 128, 0, c->stream>>>(c->dm.n_elems, (int)(c->n_loc - c->nmeshp), c->dm.node, c->dm.node_v, c->dm.en, c->dm.nfar, c->dm.enormal, c->dm.ev, c->dm.pplane,
             c->slot_of, c->Q1[c->cur], c->F[c->cur], c->cap);
         WF_LAUNCH_CHECK(c); c->launches++;
     }

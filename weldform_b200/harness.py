@@ -117,17 +117,23 @@ def context_from_case(case, device=0, comm=None):
         if key in case:
             arrays[name] = case[key]
     meshes = []
+    mesh_x, mesh_h = [], []                      # element particles (centroid, (float)hfac*radius; Contact.cpp:10-38): they shape the cell grid
     for m in range(mesh_count):
         pl = case["mesh%d_plane" % m]
         nodes, elems, normals, nfar, radius = axis_plane_mesh(int(pl[0]), pl[1] != 0, pl[2:5], pl[5:8], int(pl[8]))
-        ctx.add_mesh(nodes, elems, normals, nfar, radius, float(case.get("mesh%d_hfac" % m, 1.1)), int(case.get("mesh%d_id" % m, 10 + m)))
+        hfac = float(case.get("mesh%d_hfac" % m, 1.1))
+        ctx.add_mesh(nodes, elems, normals, nfar, radius, hfac, int(case.get("mesh%d_id" % m, 10 + m)))
         meshes.append((len(nodes), len(elems)))
+        mesh_x.append(((nodes[elems[:, 0]] + nodes[elems[:, 1]]) + nodes[elems[:, 2]]) / 3.0)
+        mesh_h.append(float(np.float32(hfac)) * radius)
     n_global = n
     if comm is not None and comm[1] > 1:
         xg = np.asarray(arrays["x"], float).reshape(-1, 3)
         hg = np.broadcast_to(np.asarray(arrays["h"], float), (n,))
-        rank_of, bounds = api.plan_slabs(xg, hg, comm[1], int(case.get("KernelType", 0)), case.get("DomMin"), case.get("DomMax"))
-        sel = np.nonzero(rank_of == comm[0])[0]
+        if mesh_x:
+            xg = np.concatenate([xg] + mesh_x); hg = np.concatenate([hg] + mesh_h)
+        rank_of, bounds = api.plan_slabs(xg, hg, comm[1], int(case.get("KernelType", 0)), case.get("DomMin"), case.get("DomMax"), n_sph=n)
+        sel = np.nonzero(rank_of[:n] == comm[0])[0]
         local = {}
         for key, val in arrays.items():
             v = np.asarray(val)
@@ -180,7 +186,7 @@ def dump(ctx, info, with_pairs=True):
 
 def merge_rank_dumps(dumps):
     """Per-rank dumps of a multi-GPU run -> one dump in global creation order (pairs merged and sorted)."""
-    n = int(sum(len(d["global_index"]) for d in dumps))
+    n = int(max(int(d["global_index"].max()) for d in dumps)) + 1       # rigid-mesh element particles are replicated on every rank
     out = {}
     for name in _DUMP + ["global_index"]:
         first = dumps[0][name]
@@ -192,12 +198,14 @@ def merge_rank_dumps(dumps):
     for k, v in dumps[0].items():
         if k not in out and k not in ("pairs", "cont_pairs"):
             out[k] = v                                     # scalars are identical on every rank
-    out["n_particles"] = np.array([float(n)]); out["solid_part_count"] = np.array([float(n)])
+    out["n_particles"] = np.array([float(n)])
+    out["solid_part_count"] = np.array([float(sum(float(d["solid_part_count"][0]) for d in dumps))])
     if "pairs" in dumps[0]:
         pr = np.concatenate([d["pairs"].reshape(-1, 2) for d in dumps])
         pr = pr[np.lexsort((pr[:, 1], pr[:, 0]))]
         out["pairs"] = pr.reshape(-1)
-        out["cont_pairs"] = np.concatenate([d["cont_pairs"] for d in dumps])
+        cp = np.concatenate([d["cont_pairs"].reshape(-1, 2) for d in dumps])
+        out["cont_pairs"] = cp[np.lexsort((cp[:, 1], cp[:, 0]))].reshape(-1)
     return out
 
 

@@ -47,7 +47,7 @@ def dx_for(n_particles):
 
 
 def workload_config(n_sph, extra=None):
-    cfg = {"workload": "Compression_thermal cylinder lattice (AddCylinderLength R=0.15 L=0.56 h=1.2dx), elastoplastic + thermal + plastic heating, "
+    cfg = {"workload": ("Compression_thermal cylinder between two rigid planes (penalty contact), lattice" if extra and extra.get("contact") else "Compression_thermal cylinder lattice") + " (AddCylinderLength R=0.15 L=0.56 h=1.2dx), elastoplastic + thermal + plastic heating, "
                        "alpha=1 TI=0.3, yielding state, neighbour rebuild every 5 steps",
            "particles": int(n_sph), "neighbours_per_particle": 56, "solver": "SolveDiffUpdateFraser", "ts_nb_inc": 5,
            "l2": "inputs larger than L2 (>= 1 kB of fp64 state per particle)"}
@@ -216,7 +216,8 @@ def run_ours(args):
     n_target = args.particles
     dx = dx_for(n_target)
     t0 = time.time()
-    case = cases.compression_fast(dx=dx, nsteps=1, perturb_amp=PERTURB_AMP)
+    contact = args.workload == "contact"
+    case = cases.compression_fast(dx=dx, nsteps=1, perturb_amp=PERTURB_AMP, contact_planes=contact)
     case["tuning"] = float(args.tuning)
     comm = None
     if world > 1:
@@ -274,8 +275,11 @@ def run_ours(args):
     value = n_sph * args.steps / (ms * 1e-3)
 
     # ---- e2e: phase API + host GeneralAfter callback bridge with pinned host buffers
-    bc = np.asarray(case["bc"]).reshape(-1, 8)
-    vtop, tau = bc[0, 1:4].copy(), float(bc[0, 4])
+    if contact:
+        vtop, tau = np.asarray(case["mesh0_vel"][:3], float).copy(), float(case["mesh0_vel"][3])
+    else:
+        bc = np.asarray(case["bc"]).reshape(-1, 8)
+        vtop, tau = bc[0, 1:4].copy(), float(bc[0, 4])
     bridge = {"mig": None}
 
     def refresh_tagged():
@@ -291,8 +295,26 @@ def run_ours(args):
                       v=torch.empty((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)],
                       a=torch.empty((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)])
 
+    def general_after_contact(t_now):
+        # examples/Contact_Compression_1010.cpp:18-47: the tool velocity is set from the host (TriMesh::SetVel) and the callback
+        # integrates Sigma(2,2) and a(2)*Mass over the first particle row (read back from the device)
+        if bridge["mig"] is None:
+            zs = np.asarray(ctx.download("x")).reshape(-1, 3)[:ctx.n_sph, 2] if world == 1 else np.zeros(1)
+            nrow = int(np.count_nonzero(zs <= zs.min() + 1e-9)) if world == 1 else 0
+            row = np.arange(max(nrow, 1), dtype=np.int32)
+            bridge.update(mig=(0, 0), tagged=row, n2=0,
+                          v=torch.empty((len(row), 9), dtype=torch.float64).pin_memory().numpy(),
+                          a=torch.empty((len(row), 3), dtype=torch.float64).pin_memory().numpy())
+        f = min(t_now / tau, 1.0) if tau > 0 else 1.0
+        ctx.mesh_set_motion(0, vtop * f)
+        if world == 1:
+            ctx.download("Sigma", bridge["tagged"], out=bridge["v"]); ctx.download("a", bridge["tagged"], out=bridge["a"])
+            bridge["force"] = float(bridge["v"][:, 8].sum())
+
     def general_after(t_now):
         # examples/Compression_thermal.cpp:30-66: ID 3 rows pushed with a ramped velocity, ID 2 rows held, a = 0 for both
+        if contact:
+            return general_after_contact(t_now)
         refresh_tagged()
         tagged, n2, v_host, a_host = bridge["tagged"], bridge["n2"], bridge["v"], bridge["a"]
         if len(tagged) == 0:
@@ -336,8 +358,12 @@ def run_ours(args):
         nt = int(t.item())
     h2d = 2 * (2 * nt * 24 + 2 * nt * 4)            # v and a up, plus the index list with each call (all ranks)
     d2h = 2 * (2 * nt * 24) + scal_bytes * world
+    path = "wf_fraser_stage_a/b1/b2/c + wf_download_subset/wf_upload_subset (host GeneralAfter on %d tagged particles, pinned buffers) + wf_reduce" % nt
+    if contact:
+        h2d = 2 * (48 + nt * 4 * 2) * world; d2h = 2 * (nt * 96) + scal_bytes * world
+        path = "wf_fraser_stage_a/b1/b2/c + wf_mesh_set_motion + wf_download_subset (host callback of Contact_Compression_1010: tool velocity, Sigma and a of the first row of %d particles) + wf_reduce" % nt
     e2e = {"value": n_sph * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "ms_per_step": ms_e2e / args.steps, "path": "wf_fraser_stage_a/b1/b2/c + wf_download_subset/wf_upload_subset (host GeneralAfter on %d tagged particles, pinned buffers) + wf_reduce" % nt}
+           "ms_per_step": ms_e2e / args.steps, "path": path}
 
     # ---- roofline of the dominant kernel, from the CUDA-event pairs recorded on the ctx stream inside the timed region
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -399,7 +425,8 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(n_sph, {"decomposition": ("1 GPU" if world == 1 else "%d slabs along z, NCCL halos (3 refreshes per step), rank 0: %s" % (world, comm_info)),
                                                   "neighbours_avg": nb_avg, "spinup_steps": spin, "nb_rebuilds_in_timed_region": int(prof.get("nb_list", (0, 0))[1]),
-                                                  "max_pl_strain": s_after.max_pl_strain}),
+                                                  "max_pl_strain": s_after.max_pl_strain,
+                                                  **({"contact": "two rigid AxisPlaneMesh planes (%d elements each), Wang penalty contact, friction 0.2; contact force sum %.4g N" % (info["meshes"][0][1], s_after.contact_force_sum)} if contact else {})}),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -417,6 +444,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=50000, help="particles of the CPU-baseline sample lattice")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["compression", "contact"], default="compression",
+                    help="compression: Compression_thermal (velocity-prescribed end rows, BASELINE configs[1] scaled); contact: the same cylinder between two rigid planes (penalty contact)")
     ap.add_argument("--tuning", type=int, default=0, help="wf_params::tuning bit mask (kernel A/B switches)")
     args = ap.parse_args()
     args.particles = int(args.particles)

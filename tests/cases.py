@@ -180,7 +180,7 @@ def compression_fast(dx, nsteps=1, **kw):
 
 
 def _compression_from_points(pts, dx, nsteps, thermal=True, pl_heating=True, alpha=1.0, beta=0.0, ti=0.3, gradient_type=0,
-                             vmax=10.0, tau=0.005, cfl=0.2, fy=300.0e6, ts_nb_inc=5, perturb_amp=0.0, seed=1):
+                             vmax=10.0, tau=0.005, cfl=0.2, fy=300.0e6, ts_nb_inc=5, perturb_amp=0.0, seed=1, contact_planes=False, friction=0.2):
     rho, K, G = 2700.0, 6.7549e10, 2.5902e10
     R, L = 0.15, 0.56
     h = 1.2 * dx
@@ -207,4 +207,19 @@ def _compression_from_points(pts, dx, nsteps, thermal=True, pl_heating=True, alp
         x, y, amp = pts[:, 0], pts[:, 1], perturb_amp
         case["v"] = np.stack([amp * np.sin(9.0 * y + seed) * np.cos(4.0 * z), amp * np.cos(8.0 * x - seed) * np.sin(3.0 * z),
                               -amp * z * (1.0 + 0.3 * np.sin(11.0 * x * y))], axis=1).reshape(-1)
+    if contact_planes:
+        # the cylinder between two rigid planes as in examples/Contact_Compression_1010.cpp:148-156,249-250 (AxisPlaneMesh above
+        # and below, the upper one pushed down with a ramped velocity) instead of velocity-prescribed end rows; the mesh density
+        # keeps the element particles' h = 1.1*radius at the SPH h, as the shipped example does, so that the cell grid stays tight
+        del case["bc"]
+        case["ID"] = np.full(n, 1, np.int32)
+        side = 2.4 * R
+        dens = int(np.ceil(side / (1.45 * dx)))
+        zmax, zmin = z.max() + h, z.min() - h
+        sx, sy = 0.37 * dx, -0.21 * dx           # keeps lattice points off the mesh edges (see contact_compression)
+        case.update(contact=1.0, friction_sta=friction, friction_dyn=friction, PFAC=0.4, DFAC=0.0, mesh_count=2.0,
+                    mesh0_plane=np.array([2, 0, -side / 2 + sx, -side / 2 + sy, zmax, side / 2 + sx, side / 2 + sy, zmax, dens], float), mesh0_hfac=1.1, mesh0_id=10.0,
+                    mesh0_vel=np.array([0, 0, -vmax, tau], float),
+                    mesh1_plane=np.array([2, 1, -side / 2 + sx, -side / 2 + sy, zmin, side / 2 + sx, side / 2 + sy, zmin, dens], float), mesh1_hfac=1.1, mesh1_id=11.0,
+                    mesh1_vel=np.array([0, 0, 0, 0], float))
     return case

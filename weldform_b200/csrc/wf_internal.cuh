@@ -75,7 +75,7 @@ struct wf_ctx {
     int64_t n = 0, nsph = 0, cap = 0;            // active slots (local + halo), GLOBAL SPH count, allocated slots
     int64_t n_loc = 0;                           // slots [0, n_loc) are this rank's own particles (== n on one GPU); halos follow
     int64_t nmeshp = 0;                          // rigid-mesh element particles (replicated on every rank of a multi-GPU run)
-    bool mesh_tail = false;                      // mesh particles are kept out of the cell table (sorted to the tail of the local region, see wf_neighbour.cu)
+    bool mesh_tail = false;                      // mesh particles are kept out of the SPH cell table (tail of the local region with a cell table of their own, see wf_neighbour.cu)
     // ---- multi-GPU (wf_comm.cu): 1-D slab decomposition along the slowest cell axis, NCCL point-to-point halos
     struct Comm {
         void *nccl = nullptr;                    // ncclComm_t
@@ -107,6 +107,7 @@ struct wf_ctx {
     int ax_fast = 0, ax_mid = 1, ax_slow = 2;
     unsigned long long *keys[2] = { nullptr, nullptr }; int *vals[2] = { nullptr, nullptr };
     int *cell_start = nullptr, *cell_end = nullptr; int64_t cell_cap = 0;
+    int *mcell_start = nullptr, *mcell_end = nullptr;   // cell table of the rigid-mesh element particles (mesh_tail layout)
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     // neighbour lists (ELL, transposed): nbr[k*cap + slot]; bit31 = "slot is temp1 (first) of the reference pair"
     uint32_t *nbr = nullptr; int nbr_k = 0; int64_t nbr_alloc = 0;

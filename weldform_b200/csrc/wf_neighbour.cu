@@ -30,11 +30,11 @@ struct Grid {
 // Neighbour.cpp:185-225 ListGenerate: cell index with clamping
 // mig != 0 (multi-GPU): particles whose slow-axis cell layer left [layer_lo, layer_hi) get a sentinel key (they sort to
 // the tail and are dropped) and are listed for migration to the adjacent rank (emig[dir*emig_cap + k], cnt[dir])
-// mesh_tail != 0: rigid-mesh element particles (creation index >= nsph) get the virtual cell WF_VCELL: they sort behind every
-// real cell (a contiguous tail of the local region, descending creation index), stay out of the cell table, the halo slices
-// and the migration, and are matched against the free-surface particles by k_cont_list_tail. Every rank of a multi-GPU run
-// keeps a replica of all of them.
-#define WF_VCELL 0x7FFFFFFEu
+// mesh_tail != 0: rigid-mesh element particles (creation index >= nsph) are keyed in a cell space of their own (bit 30 set):
+// they sort behind every SPH particle -- a contiguous tail of the local region, by cell, descending creation index inside a
+// cell -- stay out of the SPH cell table, the halo slices and the migration, and get a cell table of their own, which
+// k_cont_list walks. Every rank of a multi-GPU run keeps a replica of all of them.
+#define WF_MESH_CELL_BIT 0x40000000u
 struct MigArgs { int on, layer_lo, layer_hi; long long plane; int *emig; int *cnt; long long emig_cap; int mesh_tail, nsph; };
 __global__ void k_cell_keys(Grid g, const double4 *Q0, const int *orig, int64_t n, int64_t s_off, unsigned long long *keys, int *vals, MigArgs mg)
 {
@@ -49,13 +49,13 @@ __global__ void k_cell_keys(Grid g, const double4 *Q0, const int *orig, int64_t 
         if (ci >= g.CellNo[k]) ci = g.CellNo[k] - 1;
         c[k] = ci;
     }
+    // descending creation index inside a cell == the order the reference's push-front linked list is walked in
+    const int lin = g.lin(c);
     if (mg.mesh_tail && orig[s] >= mg.nsph) {
-        keys[s] = ((unsigned long long)WF_VCELL << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)orig[s]);
+        keys[s] = ((unsigned long long)((unsigned)lin | WF_MESH_CELL_BIT) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)orig[s]);
         vals[s] = (int)s;
         return;
     }
-    // descending creation index inside a cell == the order the reference's push-front linked list is walked in
-    const int lin = g.lin(c);
     if (mg.on) {
         const int layer = (int)(lin / mg.plane);
         if (layer < mg.layer_lo || layer >= mg.layer_hi) {
@@ -95,14 +95,16 @@ __global__ void k_permute_i(int64_t n, int64_t cap, const int *perm, const int *
     b[off + s] = v;
     if (blockIdx.y == I_LID && slot_of) slot_of[v] = (int)s;     // one GPU: local index == creation index
 }
-__global__ void k_cell_bounds(int64_t n, const unsigned long long *keys, int *cell_start, int *cell_end)
+__global__ void k_cell_bounds(int64_t n, const unsigned long long *keys, int *cell_start, int *cell_end, int *mcell_start, int *mcell_end)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     int cell = (int)(keys[s] >> 32);
-    if (cell < 0 || cell == (int)WF_VCELL) return;   // migration sentinel / mesh-particle tail
-    if (s == 0 || (int)(keys[s - 1] >> 32) != cell) cell_start[cell] = (int)s;
-    if (s == n - 1 || (int)(keys[s + 1] >> 32) != cell) cell_end[cell] = (int)s + 1;
+    if (cell < 0) return;                      // migration sentinel
+    int *cs = cell_start, *ce = cell_end; int idx = cell;
+    if ((unsigned)cell & WF_MESH_CELL_BIT) { cs = mcell_start; ce = mcell_end; idx = (int)((unsigned)cell & ~WF_MESH_CELL_BIT); }
+    if (s == 0 || (int)(keys[s - 1] >> 32) != cell) cs[idx] = (int)s;
+    if (s == n - 1 || (int)(keys[s + 1] >> 32) != cell) ce[idx] = (int)s + 1;
 }
 
 // The 27 cells around (q1,q2,q3) in the order in which the reference's sweep (q1 outer, q3, q2 inner;
@@ -264,57 +266,6 @@ k_cont_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long
     if (threadIdx.x == 0 && m > 0) atomicMax(d_maxcnt, m);
 }
 
-// Same lists as k_cont_list when the mesh particles live in the tail [tail0, tail0 + ntail) instead of the cell table
-// (mesh_tail layout): every free-surface particle scans the tail, keeps the element particles of its 27 cells within
-// h_i + h_j and orders them as the cell walk would have met them -- walk position of the element particle's cell first,
-// descending creation index (the tail's own order) inside a cell.
-__global__ void __launch_bounds__(128)
-k_cont_list_tail(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long long *keys, const double4 *__restrict__ Q0, const int *__restrict__ orig,
-                 const int *__restrict__ ID, const int *__restrict__ oldsurf, int surf_id, int require_old, int64_t tail0, int ntail, int *cont, int *cont_cnt, int *d_maxcnt)
-{
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int cnt = 0;
-    if (s < n) {
-        const int oi = orig[s];
-        if (oi < nsph && ID[s] == surf_id && (!require_old || oldsurf[s])) {
-            const double4 qi = Q0[s]; const V3 xi = v3(qi.x, qi.y, qi.z);
-            int c[3]; g.unlin((int)(keys[s] >> 32), c);
-            for (int t = 0; t < ntail; ++t) {
-                const int64_t j = tail0 + t;
-                const double4 qj = Q0[j]; const double xj3[3] = { qj.x, qj.y, qj.z };
-                int d[3]; bool near = true;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {            // the element particle's cell, as k_cell_keys computes it
-                    int ci = (int)(floor((xj3[k] - g.BLPF[k]) / g.CellSize[k]));
-                    if (ci < 0) ci = 0;
-                    if (ci >= g.CellNo[k]) ci = g.CellNo[k] - 1;
-                    d[k] = ci - c[k];
-                    if (d[k] < -1 || d[k] > 1) near = false;
-                }
-                if (!near) continue;
-                int e = 0;
-                for (; e < 27; ++e) if (c_walk[e][0] == d[0] && c_walk[e][1] == d[1] && c_walk[e][2] == d[2]) break;
-                // own cell: element particles have the largest creation indices, i.e. they precede s in the cell: s is temp2
-                const int ifirst = (c_walk[e][3] == 2) ? 0 : c_walk[e][3];
-                const V3 xj = v3(qj.x, qj.y, qj.z);
-                const V3 xij = ifirst ? (xi - xj) : (xj - xi);
-                if (!(norm(xij) < (ifirst ? (qi.w + qj.w) : (qj.w + qi.w)))) continue;
-                if (cnt < K) {                          // stable insertion by walk position (entries carry it in bits 24..30 until the end)
-                    int pos = cnt;
-                    while (pos > 0 && (cont[(int64_t)(pos - 1) * cap + s] >> 24) > e) { cont[(int64_t)pos * cap + s] = cont[(int64_t)(pos - 1) * cap + s]; --pos; }
-                    cont[(int64_t)pos * cap + s] = (e << 24) | (orig[j] - nsph);
-                }
-                ++cnt;
-            }
-            for (int k = 0; k < cnt && k < K; ++k) cont[(int64_t)k * cap + s] &= 0xFFFFFF;
-        }
-        cont_cnt[s] = cnt;
-    }
-    typedef cub::BlockReduce<int, 128> BR; __shared__ typename BR::TempStorage tmp;
-    int m = BR(tmp).Reduce(cnt, cub::Max());
-    if (threadIdx.x == 0 && m > 0) atomicMax(d_maxcnt, m);
-}
-
 __global__ void k_export_pairs(int64_t n, int64_t cap, int K, const uint32_t *nbr, const int *nb_hi, const int *orig, const int64_t *offs, int64_t *out)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,6 +330,11 @@ int nb_cell_initiate(wf_ctx *c)
     cudaFree(c->cell_start); cudaFree(c->cell_end);
     WF_CUDA(c, cudaMalloc(&c->cell_start, nc * sizeof(int))); WF_CUDA(c, cudaMalloc(&c->cell_end, nc * sizeof(int)));
     c->cell_cap = nc;
+    if (c->mesh_tail) {
+        if (nc >= (int64_t)WF_MESH_CELL_BIT) return fail(c, WF_ERR_UNSUPPORTED, "cell grid too large for the mesh cell table (%lld cells)", (long long)nc);
+        cudaFree(c->mcell_start); cudaFree(c->mcell_end);
+        WF_CUDA(c, cudaMalloc(&c->mcell_start, nc * sizeof(int))); WF_CUDA(c, cudaMalloc(&c->mcell_end, nc * sizeof(int)));
+    }
     if (c->comm.nranks > 1) {
         const int slow = c->ax_slow, L = c->CellNo[slow];
         std::vector<long long> hist(L, 0);
@@ -443,7 +399,8 @@ int nb_build_impl(wf_ctx *c)
     }
     {   ProfScope ps(c, PK_NB_CELLS);
         WF_CUDA(c, cudaMemsetAsync(c->cell_start, 0, c->ncells * sizeof(int), st)); WF_CUDA(c, cudaMemsetAsync(c->cell_end, 0, c->ncells * sizeof(int), st));
-        k_cell_bounds<<<grid_for(c->n, B), B, 0, st>>>(c->n, c->keys[1], c->cell_start, c->cell_end); WF_LAUNCH_CHECK(c); c->launches++; }
+        if (c->mesh_tail) { WF_CUDA(c, cudaMemsetAsync(c->mcell_start, 0, c->ncells * sizeof(int), st)); WF_CUDA(c, cudaMemsetAsync(c->mcell_end, 0, c->ncells * sizeof(int), st)); }
+        k_cell_bounds<<<grid_for(c->n, B), B, 0, st>>>(c->n, c->keys[1], c->cell_start, c->cell_end, c->mcell_start, c->mcell_end); WF_LAUNCH_CHECK(c); c->launches++; }
     n = c->n_loc;                                     // lists are built for this rank's own particles; candidates include the halos
     int4 mids = make_int4(-2147483647, -2147483647, -2147483647, -2147483647);
     if (c->mesh_ids.size() > 0) mids.x = c->mesh_ids[0]; if (c->mesh_ids.size() > 1) mids.y = c->mesh_ids[1];
@@ -477,11 +434,8 @@ int nb_build_impl(wf_ctx *c)
             const int K = c->cont_k;
             if ((int64_t)K * cap > c->cont_alloc) { cudaFree(c->cont); c->cont = nullptr; WF_CUDA(c, cudaMalloc(&c->cont, (size_t)K * cap * sizeof(int))); c->cont_alloc = (int64_t)K * cap; }
             WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt + 2, 0, sizeof(int), st));
-            if (c->mesh_tail)
-                k_cont_list_tail<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->Q0[c->cur], c->Ip(I_ORIG), c->Ip(I_ID), c->Ip(I_OLDSURF),
-                    1, c->solver_ready ? 1 : 0, c->n_loc - c->nmeshp, (int)c->nmeshp, c->cont, c->cont_cnt, c->d_maxcnt + 2);
-            else
-            k_cont_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->cell_start, c->cell_end, c->Q0[c->cur], c->Ip(I_ORIG), c->Ip(I_ID), c->Ip(I_OLDSURF),
+            // mesh_tail layout: the element particles have a cell table of their own (same walk, same order inside a cell)
+            k_cont_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->mesh_tail ? c->mcell_start : c->cell_start, c->mesh_tail ? c->mcell_end : c->cell_end, c->Q0[c->cur], c->Ip(I_ORIG), c->Ip(I_ID), c->Ip(I_OLDSURF),
                 1, c->solver_ready ? 1 : 0, c->cont, c->cont_cnt, c->d_maxcnt + 2);
             WF_LAUNCH_CHECK(c); c->launches++;
             int mx[2] = { 0, 0 }; WF_CUDA(c, cudaMemcpyAsync(mx, c->d_maxcnt + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));

@@ -266,6 +266,7 @@ int main(int argc, char ** argv) try
     put_mat3(out, "StrainRate", dom, &SPH::Particle::StrainRate); put_mat3(out, "RotationRate", dom, &SPH::Particle::RotationRate);
     put_mat3(out, "Strain", dom, &SPH::Particle::Strain); put_mat3(out, "Strain_pl", dom, &SPH::Particle::Strain_pl);
     put_mat3(out, "TIR", dom, &SPH::Particle::TIR);
+    if (dom.gradKernelCorr) put_mat3(out, "gradCorrM", dom, &SPH::Particle::gradCorrM);
     put_dbl(out, "pl_strain", dom, &SPH::Particle::pl_strain); put_dbl(out, "Sigmay", dom, &SPH::Particle::Sigmay);
     put_dbl(out, "eff_strain_rate", dom, &SPH::Particle::eff_strain_rate);
     put_dbl(out, "T", dom, &SPH::Particle::T); put_dbl(out, "dTdt", dom, &SPH::Particle::dTdt);

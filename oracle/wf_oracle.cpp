@@ -18,7 +18,7 @@
 // ThermalCalcs (CalcConvHeat, CalcTempInc), CalcKinEnergyEqn/CalcIntEnergyEqn, and the Fraser step order with its
 // neighbour-rebuild cadence (Source/SolverFraser.cpp:133-505). Fixed particles (IsFree = false) are routed as the reference
 // does (no SM pairs); their Shepard-smoothed TIR (PrimaryComputeAcceleration, Domain.cpp:1599-1698, read by nothing) is not
-// restated. Not restated: gradKernelCorr, ghost particles, damage, 2-D axisymmetric branches (all "next" or out of scope in SURVEY.md section 8).
+// restated. gradKernelCorr (Domain.cpp:1832-1940 + the locking branches of InteractionAlt.cpp) is restated for all-free particle sets. Not restated: ghost particles, damage, 2-D axisymmetric branches (all "next" or out of scope in SURVEY.md section 8).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -286,6 +286,7 @@ struct Dom {
     int Dimension = 3, KernelType = 0, GradientType = 0, ts_nb_inc = 5;
     double Cellfac = 2.0, deltat = 0.0, Time = 0.0;
     bool thermal_solver = false, pl_heating = false, contact = false, cont_heat_fric = false, cont_heat_cond = false;
+    bool gradKernelCorr = false;             // Domain::gradKernelCorr: Bonet-Lok corrected gradient; the Fraser solver then sums with locks, in pair order (SolverFraser.cpp:112-115)
     double pl_work_heat_frac = 0.9, friction_sta = 0.0, friction_dyn = 0.0, PFAC = 0.4, DFAC = 0.0, contact_force_factor = 1.0, contact_hc = 0.0;
     double DomMax[3] = { -100000000000.0, -100000000000.0, -100000000000.0 }, DomMin[3] = { 100000000000.0, 100000000000.0, 100000000000.0 };
     int solid_part_count = 0; int id_free_surf = 1;
@@ -295,7 +296,7 @@ struct Dom {
     dvec Mass, Density, dDensity, RefDensity, h, Pressure, G, Cs, P0, Alpha, Beta, TI, TIn, TIInitDist, Sigmay, Ep;
     dvec pl_strain, delta_pl_strain, eff_strain_rate, T, dTdt, k_T, cp_T, h_conv, T_inf, th_exp, q_source, q_conv, q_plheat, q_fric_work, q_cont_conv;
     dvec delta_cont, dkin, dint;
-    dvec Sigma, Shear, SRate, RRate, Strain, Strain_pl, Strain_pl_incr, TIR;   // 9N
+    dvec Sigma, Shear, SRate, RRate, Strain, Strain_pl, Strain_pl_incr, TIR, gradCorrM;   // 9N
     ivec ID, ID_orig, IsFree, PresEq, Fail, Material, Material_model, mat_id, Thermal_BC, nowrite, Nb, pmesh, pelem;
     std::vector<Mat> mats; std::vector<Mesh> meshes; std::vector<BC> bcs;
     // cell grid
@@ -325,7 +326,7 @@ struct Dom {
                         &pl_strain, &delta_pl_strain, &eff_strain_rate, &T, &dTdt, &k_T, &cp_T, &h_conv, &T_inf, &th_exp, &q_source, &q_conv, &q_plheat,
                         &q_fric_work, &q_cont_conv, &delta_cont, &dkin, &dint };
         for (auto p : v1) p->assign(n, 0.0);
-        dvec * v9[] = { &Sigma, &Shear, &SRate, &RRate, &Strain, &Strain_pl, &Strain_pl_incr, &TIR };
+        dvec * v9[] = { &Sigma, &Shear, &SRate, &RRate, &Strain, &Strain_pl, &Strain_pl_incr, &TIR, &gradCorrM };
         for (auto p : v9) p->assign(9 * n, 0.0);
         ivec * vi[] = { &ID, &ID_orig, &IsFree, &PresEq, &Fail, &Material, &Material_model, &mat_id, &Thermal_BC, &nowrite, &Nb, &pmesh, &pelem };
         for (auto p : vi) p->assign(n, 0);
@@ -537,6 +538,110 @@ struct Dom {
             setM(SRate, i, S); setM(RRate, i, R);
         }
     }
+    // ================= gradKernelCorr = true: locking summation, pairs as stored (first, second), pair order =================
+    // External/matvec.h:836-841 Mult(Mat3,Vec3,Vec3): B = M A
+    static V3 mvmul(const M3 & M, const V3 & A) { V3 b; for (int i = 0; i < 3; ++i) b(i) = A(0) * M(i, 0) + A(1) * M(i, 1) + A(2) * M(i, 2); return b; }
+    // ---- Source/Domain.cpp:1832-1940 CalcGradCorrMatrix (SM pairs; this restatement has no FSM pairs: fixed particles unsupported with it)
+    void CalcGradCorrMatrix() {
+        std::vector<M3> temp(N, zero3());
+        for (size_t p = 0; p < SM.size(); ++p) {
+            int P1 = SM[p].first, P2 = SM[p].second;
+            V3 xij = vsub(X(P1), X(P2));
+            double hh = (h[P1] + h[P2]) / 2.0;
+            double GK = GradKernel(Dimension, KernelType, norm3(xij) / hh, hh);
+            double di = Density[P1], mi = Mass[P1], dj = Density[P2], mj = Mass[P2];
+            V3 gx = vscale(GK, xij);
+            M3 m;                                     // Dyad(GK*xij, xij), matvec.h:813-818
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) m(r, c) = gx(r) * xij(c);
+            temp[P1] = msub(temp[P1], smul(mj / dj, m));
+            temp[P2] = msub(temp[P2], smul(mi / di, m));
+        }
+        int max_id = contact ? first_fem() : (int)N;
+        M3 I = zero3(); I(0, 0) = I(1, 1) = I(2, 2) = 1.0;
+        for (int i = 0; i < max_id; ++i) {
+            if (IsFree[i]) {
+                const M3 & M = temp[i]; M3 Mi;       // InvLog, matvec.h:673-693
+                double det = M(0, 0) * (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) - M(0, 1) * (M(1, 0) * M(2, 2) - M(1, 2) * M(2, 0)) + M(0, 2) * (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0));
+                bool ok = !(std::fabs(det) < 1.0e-10);
+                Mi(0, 0) = (M(1, 1) * M(2, 2) - M(1, 2) * M(2, 1)) / det; Mi(0, 1) = (M(0, 2) * M(2, 1) - M(0, 1) * M(2, 2)) / det; Mi(0, 2) = (M(0, 1) * M(1, 2) - M(0, 2) * M(1, 1)) / det;
+                Mi(1, 0) = (M(1, 2) * M(2, 0) - M(1, 0) * M(2, 2)) / det; Mi(1, 1) = (M(0, 0) * M(2, 2) - M(0, 2) * M(2, 0)) / det; Mi(1, 2) = (M(0, 2) * M(1, 0) - M(0, 0) * M(1, 2)) / det;
+                Mi(2, 0) = (M(1, 0) * M(2, 1) - M(1, 1) * M(2, 0)) / det; Mi(2, 1) = (M(0, 1) * M(2, 0) - M(0, 0) * M(2, 1)) / det; Mi(2, 2) = (M(0, 0) * M(1, 1) - M(0, 1) * M(1, 0)) / det;
+                setM(gradCorrM, i, ok ? Mi : I);
+            } else setM(gradCorrM, i, I);
+        }
+    }
+    // ---- InteractionAlt.cpp:483-611 CalcDensInc, !nonlock_sum && gradKernelCorr branch ----------------------------
+    void Density_lock() {
+        for (size_t p = 0; p < SM.size(); ++p) {
+            int P1 = SM[p].first, P2 = SM[p].second;
+            double hh = (h[P1] + h[P2]) / 2;
+            V3 xij = vsub(X(P1), X(P2)); double rij = norm3(xij);
+            double di = Density[P1], mi = Mass[P1], dj = Density[P2], mj = Mass[P2];
+            V3 vij = vsub(Vv(P1), Vv(P2));
+            double GK = GradKernel(Dimension, KernelType, rij / hh, hh);
+            V3 vc0 = mvmul(smul(GK, getM(gradCorrM, P1)), xij), vc1 = mvmul(smul(GK, getM(gradCorrM, P2)), xij);
+            double t0 = dot3(vij, vc0), t1 = dot3(vij, vc1);
+            dDensity[P1] += 1.0 * mj * (di / dj) * t0;
+            dDensity[P2] += 1.0 * mi * (dj / di) * t1;
+        }
+    }
+    // ---- InteractionAlt.cpp:263-446 CalcRateTensors, locking branch with corrected gradients (float m/rho, :416,432) ---
+    void RateTensors_lock() {
+        for (size_t p = 0; p < SM.size(); ++p) {
+            int P1 = SM[p].first, P2 = SM[p].second;
+            double hh = (h[P1] + h[P2]) / 2;
+            V3 xij = vsub(X(P1), X(P2)); double rij = norm3(xij);
+            double di = Density[P1], mi = Mass[P1], dj = Density[P2], mj = Mass[P2];
+            V3 vab = vsub(Vv(P1), Vv(P2));
+            double GK = GradKernel(Dimension, KernelType, rij / hh, hh);
+            M3 Sc[2], Rc[2];
+            for (int k = 0; k < 2; ++k) {
+                V3 gradK = mvmul(smul(GK, getM(gradCorrM, k == 0 ? P1 : P2)), xij);
+                M3 gv, gvT;                           // Dyad(vab, gradK)
+                for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) gv(r, c) = vab(r) * gradK(c);
+                gvT = trans(gv);
+                Sc[k] = smul(-0.5, madd(gv, gvT)); Rc[k] = smul(-0.5, msub(gv, gvT));
+            }
+            float mj_dj = mj / dj;
+            setM(SRate, P1, madd(getM(SRate, P1), smul(mj_dj, Sc[0]))); setM(RRate, P1, madd(getM(RRate, P1), smul(mj_dj, Rc[0])));
+            float mi_di = mi / di;
+            setM(SRate, P2, madd(getM(SRate, P2), smul(mi_di, Sc[1]))); setM(RRate, P2, madd(getM(RRate, P2), smul(mi_di, Rc[1])));
+        }
+    }
+    // ---- InteractionAlt.cpp:12-235 CalcAccel, locking branch with corrected gradients -------------------------------
+    void Accel_lock() {
+        M3 I = zero3(); I(0, 0) = I(1, 1) = I(2, 2) = 1.0;
+        for (size_t p = 0; p < SM.size(); ++p) {
+            int P1 = SM[p].first, P2 = SM[p].second;
+            double hh = (h[P1] + h[P2]) / 2;
+            V3 xij = vsub(X(P1), X(P2)); double rij = norm3(xij);
+            double Alpha_ = (Alpha[P1] + Alpha[P2]) / 2.0, Beta_ = (Beta[P1] + Beta[P2]) / 2.0;
+            double di = Density[P1], mi = Mass[P1], dj = Density[P2], mj = Mass[P2];
+            V3 vij = vsub(Vv(P1), Vv(P2));
+            double GK = GradKernel(Dimension, KernelType, rij / hh, hh);
+            double K = Kernel(Dimension, KernelType, rij / hh, hh);
+            M3 PIij = zero3();
+            if (Alpha_ != 0.0 || Beta_ != 0.0) {
+                double MUij = hh * dot3(vij, xij) / (rij * rij + 0.01 * hh * hh);
+                double Ci = SoundSpeed(PresEq[P1], Cs[P1], di, RefDensity[P1]);
+                double Cj = SoundSpeed(PresEq[P2], Cs[P2], dj, RefDensity[P2]);
+                double Cij = 0.5 * (Ci + Cj);
+                if (dot3(vij, xij) < 0) PIij = smul((Alpha_ * Cij * MUij + Beta_ * MUij * MUij) / (0.5 * (di + dj)), I);
+            }
+            M3 Sigmai = getM(Sigma, P1), Sigmaj = getM(Sigma, P2);
+            M3 TIij = zero3();
+            if (TI[P1] > 0.0 || TI[P2] > 0.0)
+                TIij = smul(std::pow((K / Kernel(Dimension, KernelType, (TIInitDist[P1] + TIInitDist[P2]) / (2.0 * hh), hh)), (TIn[P1] + TIn[P2]) / 2.0),
+                            madd(getM(TIR, P1), getM(TIR, P2)));
+            M3 Msum;
+            if (GradientType == 0) Msum = madd(madd(madd(smul(1.0 / (di * di), Sigmai), smul(1.0 / (dj * dj), Sigmaj)), PIij), TIij);
+            else if (GradientType == 1) Msum = madd(madd(smul(1.0 / (di * dj), madd(Sigmai, Sigmaj)), PIij), TIij);
+            else Msum = madd(madd(smul(1.0 / (di * dj), msub(Sigmai, Sigmaj)), PIij), TIij);
+            V3 vc0 = mvmul(smul(GK, getM(gradCorrM, P1)), xij), vc1 = mvmul(smul(GK, getM(gradCorrM, P2)), xij);
+            V3 t0 = vmul(vc0, Msum), t1 = vmul(vc1, Msum);
+            for (int k = 0; k < 3; ++k) { a[3 * P1 + k] += (1.0 * mj) * t0(k); a[3 * P2 + k] -= (1.0 * mi) * t1(k); }
+        }
+    }
     // ---- Source/Particle.cpp:960-1067 CalcStressStrain --------------------------------------------------------
     void CalcStressStrain(size_t i, double dt) {
         double rho = Density[i];
@@ -732,6 +837,15 @@ struct Dom {
             double hh = (h[P1] + h[P2]) / 2.0;
             double GK = GradKernel(Dimension, KernelType, norm3(xij) / hh, hh);
             double dj = Density[P2], mj = Mass[P2];
+            if (gradKernelCorr) {      // Thermal.cpp:90-111: v = gradCorrM_i (GK xij); both halves carry m_j/rho_j
+                double mc[2];
+                for (int k = 0; k < 2; ++k) {
+                    V3 vv = mvmul(getM(gradCorrM, k == 0 ? P1 : P2), vscale(GK, xij));
+                    mc[k] = mj / dj * 4. * (k_T[P1] * k_T[P2]) / (k_T[P1] + k_T[P2]) * (T[P1] - T[P2]) * dot3(xij, vv) / (norm3(xij) * norm3(xij));
+                }
+                temp[P1] += mc[0]; temp[P2] -= mc[1];
+                continue;
+            }
             double m = mj / dj * 4. * (k_T[P1] * k_T[P2]) / (k_T[P1] + k_T[P2]) * (T[P1] - T[P2]) * dot3(xij, vscale(GK, xij)) / (norm3(xij) * norm3(xij));
             temp[P1] += m; temp[P2] -= m;
         }
@@ -820,13 +934,17 @@ struct Dom {
             if (mx > MIN_PS_FOR_NBSEARCH || isfirst || check_nb_every_time) {
                 if (ts_i == 0 && nb_cleared) {
                     MainNeighbourSearch(); CalcPairPosList(); SaveNeighbourData();
+                    if (gradKernelCorr) CalcGradCorrMatrix();          // SolverFraser.cpp:203-204: at cadence rebuilds only, not at the first-yield search
                     if (contact) ContactNbUpdate();
                 }
             }
+            if (gradKernelCorr) Density_lock(); else
             Density_pass();
             for (size_t i = 0; i < N; ++i) Density[i] += deltat * dDensity[i];
+            if (gradKernelCorr) RateTensors_lock(); else
             RateTensors_pass();
             for (size_t i = 0; i < N; ++i) CalcStressStrain(i, deltat);
+            if (gradKernelCorr) Accel_lock(); else
             Accel_pass();
             if (contact) ContactWang();
             UserBC();
@@ -973,6 +1091,7 @@ void load_case(const wfc::File & in, Dom & d)
     d.PFAC = in.scalar("PFAC", 0.4); d.DFAC = in.scalar("DFAC", 0.0);
     d.cont_heat_fric = in.scalar("cont_heat_fric", 0) != 0.0; d.cont_heat_cond = in.scalar("cont_heat_cond", 0) != 0.0;
     d.ts_nb_inc = (int)in.scalar("ts_nb_inc", 5);
+    d.gradKernelCorr = in.scalar("gradKernelCorr", 0) != 0.0;
     d.thermal_solver = in.scalar("thermal_solver", 0) != 0.0; d.pl_heating = in.scalar("pl_heating", 0) != 0.0;
     d.pl_work_heat_frac = in.scalar("pl_work_heat_frac", 0.9);
     if (in.has("bc")) { const dvec & b = in.f("bc"); for (size_t r = 0; r + 8 <= b.size(); r += 8) { BC s; s.id = (int)b[r]; s.v[0] = b[r + 1]; s.v[1] = b[r + 2]; s.v[2] = b[r + 3]; s.tau = b[r + 4]; s.set_a = (int)b[r + 5]; d.bcs.push_back(s); } }
@@ -1021,6 +1140,7 @@ extern "C" int wfo_run_file(const char * case_path, const char * out_path)
     put9(out, "Mass", d.Mass); put9(out, "h", d.h); put9(out, "Density", d.Density); put9(out, "dDensity", d.dDensity); put9(out, "Pressure", d.Pressure);
     put9(out, "Sigma", d.Sigma); put9(out, "ShearStress", d.Shear); put9(out, "StrainRate", d.SRate); put9(out, "RotationRate", d.RRate);
     put9(out, "Strain", d.Strain); put9(out, "Strain_pl", d.Strain_pl); put9(out, "TIR", d.TIR);
+    if (d.gradKernelCorr) put9(out, "gradCorrM", d.gradCorrM);
     put9(out, "pl_strain", d.pl_strain); put9(out, "Sigmay", d.Sigmay); put9(out, "eff_strain_rate", d.eff_strain_rate);
     put9(out, "T", d.T); put9(out, "dTdt", d.dTdt); put9(out, "q_plheat", d.q_plheat); put9(out, "q_conv", d.q_conv); put9(out, "delta_cont", d.delta_cont);
     put9(out, "dkin_energy_dt", d.dkin); put9(out, "dint_energy_dt", d.dint);

@@ -50,6 +50,8 @@ typedef struct wf_params {
     int    cont_heat_fric, cont_heat_cond;
     double contact_hc;
     int    nb_order_reference; /* 1: neighbour lists in the reference's Nproc=1 summation order (default) */
+    int    grad_kernel_corr;   /* Domain::gradKernelCorr: Bonet-Lok corrected kernel gradient (Domain.cpp:1832-1940). As in the reference the Fraser
+                                * solver then sums per pair with locks, in pair-discovery order (SolverFraser.cpp:112-115) */
     int    tuning;             /* bit 0: disable the software-pipelined gathers of the pair kernels (A/B measurements), bit 8: multi-GPU mesh-particle layout on one GPU; default 0 */
 } wf_params;
 
@@ -112,7 +114,7 @@ typedef enum wf_field {
     WF_F_X = 0, WF_F_V, WF_F_A, WF_F_DISPLACEMENT, WF_F_NORMAL, WF_F_CONTFORCE,            /* 3 doubles */
     WF_F_DENSITY, WF_F_DDENSITY, WF_F_PRESSURE, WF_F_MASS, WF_F_H, WF_F_PL_STRAIN, WF_F_SIGMAY, WF_F_EFF_STRAIN_RATE,
     WF_F_T, WF_F_DTDT, WF_F_Q_PLHEAT, WF_F_Q_CONV, WF_F_DELTA_CONT, WF_F_DKIN_ENERGY_DT, WF_F_DINT_ENERGY_DT, /* 1 double */
-    WF_F_SIGMA, WF_F_SHEARSTRESS, WF_F_STRAINRATE, WF_F_ROTATIONRATE, WF_F_STRAIN, WF_F_STRAIN_PL, WF_F_TIR,   /* 9 doubles */
+    WF_F_SIGMA, WF_F_SHEARSTRESS, WF_F_STRAINRATE, WF_F_ROTATIONRATE, WF_F_STRAIN, WF_F_STRAIN_PL, WF_F_TIR, WF_F_GRADCORRM,   /* 9 doubles */
     WF_F_ID, WF_F_NB, WF_F_GLOBAL_INDEX,                                                                        /* 1 int32 */
     WF_F_COUNT
 } wf_field;
@@ -150,6 +152,7 @@ int wf_solver_init(wf_ctx *ctx, double dt);         /* InitialChecks, CellInitia
 int wf_nb_build(wf_ctx *ctx);                       /* ClearNbData+MainNeighbourSearch+CalcPairPosList+SaveNeighbourData(+ContactNbUpdate) */
 int wf_nb_export_pairs(wf_ctx *ctx, int64_t *ij, int64_t cap, int64_t *n_pairs);      /* sorted (i<j), creation numbering */
 int wf_cont_export_pairs(wf_ctx *ctx, int64_t *ij, int64_t cap, int64_t *n_pairs);
+int wf_grad_corr(wf_ctx *ctx);                      /* CalcGradCorrMatrix (Domain.cpp:1832-1940) on the current lists; no-op unless grad_kernel_corr */
 int wf_step_begin(wf_ctx *ctx);                     /* StartAcceleration: resets + TIR (Domain.cpp:1519-1597) */
 int wf_density(wf_ctx *ctx);                        /* CalcDensInc + DensReduction + rho += dt*drho (:243-252) */
 int wf_rate_stress(wf_ctx *ctx);                    /* CalcRateTensors + RateTensorsReduction + CalcStressStrain (:261-271) */

@@ -30,13 +30,24 @@ def golden_cases():
     out["comp_jc_30"] = cases.perturbed(cases.compression(dx=0.04, nsteps=30, model=cases.JOHNSON_COOK), amp=60.0)
     out["contact_1step"] = cases.contact_compression(dx=0.0032, nsteps=1, vmax=5.0, tau=1e-5, dens=8, cfl=0.3)
     out["contact_100"] = cases.contact_compression(dx=0.0032, nsteps=100, vmax=5.0, tau=1e-5, dens=8, cfl=0.3)   # friction stick+slide, yields
+    # Domain::gradKernelCorr = true (examples/Contact_Compression_1010.cpp:125 as shipped): corrected gradients + locking summation
+    def gc(c):
+        c = dict(c); c["gradKernelCorr"] = 1.0
+        return c
+    out["gc_comp_1step"] = gc(cases.perturbed(cases.compression(dx=0.04, nsteps=1), amp=60.0))
+    out["gc_comp_yield_40"] = gc(cases.perturbed(cases.compression(dx=0.04, nsteps=40), amp=60.0))      # first-yield search keeps the stale matrices
+    out["gc_g2_jc_12"] = gc(cases.perturbed(cases.compression(dx=0.04, nsteps=12, gradient_type=2, model=cases.JOHNSON_COOK), amp=40.0))
+    out["gc_contact_60"] = gc(cases.contact_compression(dx=0.0032, nsteps=60, vmax=5.0, tau=1e-5, dens=8, cfl=0.3))
     return out
 
 
 def main():
     if not ot.have_ref():
         raise SystemExit("oracle/_ref/wf_ref missing: run `make -C oracle ref` in the container that has /root/reference")
+    only = set(sys.argv[1:])            # optional: names to (re)generate; default all
     for name, case in golden_cases().items():
+        if only and name not in only:
+            continue
         ref = ot.run_ref(case, nproc=1)
         ref.pop("solve_seconds", None)
         rec = {"case/" + k: np.asarray(v) for k, v in case.items()}

@@ -30,7 +30,7 @@ def _compare(got, ref, tol, keys=None, what=""):
         if k in ref:
             assert np.array_equal(got[k].reshape(-1), ref[k].reshape(-1)), "%s: %s differs (sizes %d vs %d)" % (what, k, got[k].size, ref[k].size)
     worst = {}
-    for k in (keys or cases.FIELDS_F64 + cases.SCALARS):
+    for k in (keys or cases.FIELDS_F64 + cases.SCALARS + ["gradCorrM"]):
         if k in ref and k in got:
             e = ot.max_rel(got[k], ref[k])
             if not (e <= tol):
@@ -53,17 +53,19 @@ def test_golden_reference_dumps(harness, name):
 ORDER_DEPENDENT = {"dTdt", "dkin_energy_dt", "TIR"}
 
 
-@pytest.mark.parametrize("name", ["comp_1step", "contact_1step"])
+@pytest.mark.parametrize("name", ["comp_1step", "contact_1step", "gc_comp_1step"])
 def test_golden_one_step_bit_exact_fields(harness, name):
     """Stronger than the bar: after one step every per-particle field except the order-dependent sums is bit-identical
     to the reference (same operand order, FMA contraction off, reference summation order in the neighbour lists)."""
     case, ref = golden_tools.load(name)
     got = harness.run_case(case)
-    bad = {k: ot.max_rel(got[k], ref[k]) for k in cases.FIELDS_F64 if k in ref and k not in ORDER_DEPENDENT and not np.array_equal(got[k], ref[k])}
+    bad = {k: ot.max_rel(got[k], ref[k]) for k in cases.FIELDS_F64 + ["gradCorrM"] if k in ref and k not in ORDER_DEPENDENT and not np.array_equal(got[k], ref[k])}
     assert not bad, "%s: not bit-identical: %s" % (name, bad)
+    if name.startswith("gc_"):
+        assert "gradCorrM" in got and np.abs(got["gradCorrM"].reshape(-1, 9)[:, [0, 4, 8]] - 1.0).max() > 1e-3, "correction matrices must be non-trivial"
 
 
-@pytest.mark.parametrize("name", ["comp_yield_40", "contact_100", "comp_hollomon_30", "comp_jc_30"])
+@pytest.mark.parametrize("name", ["comp_yield_40", "contact_100", "comp_hollomon_30", "comp_jc_30", "gc_comp_yield_40", "gc_g2_jc_12", "gc_contact_60"])
 def test_golden_multi_step_tight(harness, name):
     """Tens of steps through yield, rebuilds and contact stay within 1e-7 of the reference on every field (state fields
     x, v, rho, sigma sit at 1e-10 or better; a and d(rho)/dt, differences of large terms, are the noisiest)."""
@@ -107,6 +109,14 @@ def test_1000_steps(harness, oracle_port, model):
     got, ref = harness.run_case(c), ot.run_port(c)
     assert ref["pl_strain"].max() > 5e-3 and np.isfinite(ref["x"]).all()
     _compare(got, ref, TOL_LONG, keys=LONG_KEYS + ["Time", "plastic_work", "int_energy_sum", "max_disp"], what="1000 steps model %d" % model)
+
+
+def test_grad_kernel_corr_1000_steps(harness, oracle_port):
+    """Domain::gradKernelCorr through yield, rebuilds (matrices recomputed at the cadence rebuilds only) and conduction."""
+    c = cases.perturbed(cases.compression(dx=0.03, nsteps=1000, model=cases.HOLLOMON), amp=30.0); c["gradKernelCorr"] = 1.0
+    got, ref = harness.run_case(c), ot.run_port(c)
+    assert ref["pl_strain"].max() > 5e-3 and np.isfinite(ref["x"]).all()
+    _compare(got, ref, TOL_LONG, keys=LONG_KEYS + ["Time", "plastic_work", "int_energy_sum", "max_disp", "gradCorrM"], what="gradKernelCorr 1000 steps")
 
 
 def test_contact_500_steps(harness, oracle_port):

@@ -22,7 +22,7 @@ class wf_params(C.Structure):
                 ("contact", C.c_int), ("friction_sta", C.c_double), ("friction_dyn", C.c_double),
                 ("pfac", C.c_double), ("dfac", C.c_double), ("contact_force_factor", C.c_double),
                 ("cont_heat_fric", C.c_int), ("cont_heat_cond", C.c_int), ("contact_hc", C.c_double),
-                ("nb_order_reference", C.c_int), ("tuning", C.c_int)]
+                ("nb_order_reference", C.c_int), ("grad_kernel_corr", C.c_int), ("tuning", C.c_int)]
 
 
 class wf_material(C.Structure):
@@ -59,7 +59,7 @@ class wf_scalars(C.Structure):
 _F3 = ["x", "v", "a", "Displacement", "normal", "contforce"]
 _F1 = ["Density", "dDensity", "Pressure", "Mass", "h", "pl_strain", "Sigmay", "eff_strain_rate", "T", "dTdt", "q_plheat", "q_conv",
        "delta_cont", "dkin_energy_dt", "dint_energy_dt"]
-_F9 = ["Sigma", "ShearStress", "StrainRate", "RotationRate", "Strain", "Strain_pl", "TIR"]
+_F9 = ["Sigma", "ShearStress", "StrainRate", "RotationRate", "Strain", "Strain_pl", "TIR", "gradCorrM"]
 _FI = ["ID", "Nb", "global_index"]
 FIELDS = {}
 for _k, _n in enumerate(_F3 + _F1 + _F9 + _FI):
@@ -89,7 +89,7 @@ def load_library():
         "wf_download": ([vp, C.c_int, vp], C.c_int), "wf_upload": ([vp, C.c_int, vp], C.c_int),
         "wf_download_subset": ([vp, C.c_int, _PI, C.c_int64, vp], C.c_int), "wf_upload_subset": ([vp, C.c_int, _PI, C.c_int64, vp], C.c_int),
         "wf_mesh_download": ([vp, C.c_int, _PD, _PD, _PD], C.c_int),
-        "wf_solver_init": ([vp, C.c_double], C.c_int), "wf_nb_build": ([vp], C.c_int),
+        "wf_solver_init": ([vp, C.c_double], C.c_int), "wf_nb_build": ([vp], C.c_int), "wf_grad_corr": ([vp], C.c_int),
         "wf_nb_export_pairs": ([vp, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)], C.c_int),
         "wf_cont_export_pairs": ([vp, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)], C.c_int),
         "wf_reduce": ([vp, C.POINTER(wf_scalars)], C.c_int), "wf_fraser_run": ([vp, C.c_int64], C.c_int),
@@ -176,6 +176,7 @@ class Context:
         if rc != 0:
             raise WeldformError("wf_create: %s" % self.L.wf_last_error(None).decode())
         self.h = h
+        self.grad_kernel_corr = 0
         self._keep = []
 
     def close(self):
@@ -200,6 +201,7 @@ class Context:
 
     def set_params(self, p):
         self._ck(self.L.wf_set_params(self.h, C.byref(p)), "wf_set_params")
+        self.grad_kernel_corr = int(p.grad_kernel_corr)
 
     def set_materials(self, mats):
         arr = (wf_material * max(len(mats), 1))()
@@ -295,6 +297,9 @@ class Context:
 
     def nb_build(self):
         self._ck(self.L.wf_nb_build(self.h), "wf_nb_build")
+
+    def grad_corr(self):
+        self._ck(self.L.wf_grad_corr(self.h), "wf_grad_corr")
 
     def _pairs(self, fn, what):
         n = C.c_int64()

@@ -236,6 +236,7 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     if (multi && !p->global_index) return fail(c, WF_ERR_ARG, "wf_set_particles: global_index is required when nranks > 1");
     c->any_fixed = false;
     if (p->is_free) for (int64_t i = 0; i < nsph; ++i) if (!p->is_free[i]) { c->any_fixed = true; break; }
+    if (c->any_fixed && c->prm.grad_kernel_corr) return fail(c, WF_ERR_UNSUPPORTED, "gradKernelCorr with fixed particles (FSM pairs of CalcGradCorrMatrix, Domain.cpp:1870-1898) is not implemented");
     c->n = n; c->n_loc = n; c->nsph = nsph_global; c->nmeshp = nmeshp;
     c->mesh_tail = nmeshp > 0 && (multi || (c->prm.tuning & 256));   // bit 8 of wf_params::tuning: the multi-GPU mesh-particle layout on one GPU (tests)
     WF_CHECK(alloc_particles(c, multi ? n + n / 4 + 262144 : n));
@@ -474,6 +475,7 @@ __device__ inline void field_get(const FieldView &v, int f, int64_t s, double ou
     case WF_F_DINT_ENERGY_DT: out[0] = own(F_DINT); break;
     case WF_F_SIGMA: sym(F_SG); break;
     case WF_F_TIR: { double4 b = v.S1[s], t = v.S2[s]; out[0] = b.z; out[1] = t.y; out[2] = t.w; out[3] = t.y; out[4] = b.w; out[5] = t.z; out[6] = t.w; out[7] = t.z; out[8] = t.x; } break;
+    case WF_F_GRADCORRM: for (int k = 0; k < 9; ++k) out[k] = own(F_GC + k); break;
     case WF_F_SHEARSTRESS: sym(F_SH); break;
     case WF_F_STRAINRATE: sym(F_SR); break;
     case WF_F_STRAIN: sym(F_ST); break;
@@ -491,7 +493,7 @@ static int field_ncomp(int f)
 {
     if (f <= WF_F_CONTFORCE) return 3;
     if (f <= WF_F_DINT_ENERGY_DT) return 1;
-    if (f <= WF_F_TIR) return 9;
+    if (f <= WF_F_GRADCORRM) return 9;
     return 1;
 }
 static bool field_is_int(int f) { return f == WF_F_ID || f == WF_F_NB || f == WF_F_GLOBAL_INDEX; }

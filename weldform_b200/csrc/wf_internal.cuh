@@ -34,7 +34,8 @@ enum OwnField {
     F_PRES = F_SG + 6,    // Pressure
     F_DDN,                // density rate prepared for the NEXT step by k_post (or by the stand-alone density pass)
     F_TN,                 // TIR prepared for the next step, 6
-    F_COUNT = F_TN + 6
+    F_GC = F_TN + 6,      // gradCorrM (Domain.cpp:1832-1940), full 3x3 row-major: the reference's matrix is not exactly symmetric
+    F_COUNT = F_GC + 9
 };
 enum OwnInt { I_ID = 0, I_IDORIG, I_NB, I_NOWRITE, I_ORIG, I_OLDSURF, I_CLS, I_LID, I_FREE, I_COUNT };   // I_ORIG: global creation index; I_LID: local index (slot_of inverse)
 
@@ -166,6 +167,7 @@ int ensure_stage(wf_ctx *c, size_t bytes);
 int nb_cell_initiate(wf_ctx *c);
 int nb_build_impl(wf_ctx *c);
 // wf_pair.cu
+int pair_gradcorr(wf_ctx *c);
 int pair_density(wf_ctx *c);
 int pair_rate_stress(wf_ctx *c);
 int pair_accel(wf_ctx *c);

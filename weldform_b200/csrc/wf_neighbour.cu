@@ -126,7 +126,7 @@ __device__ inline bool is_mesh_id(int id, int4 mids) { return id == mids.x || id
 __global__ void __launch_bounds__(128)
 k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long long *keys, const int *cell_start, const int *cell_end,
           const double4 *__restrict__ Q0, const double4 *__restrict__ Q2, const int *__restrict__ orig, const int *__restrict__ ID,
-          const int *__restrict__ cls_of, const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material, int uniform_h,
+          const int *__restrict__ cls_of, const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material, int uniform_h, int walk_order,
           uint32_t *nbr, int *nb_cnt, int *nb_hi, int *nbI, double *normal_x, double *normal_y, double *normal_z, int *d_maxcnt)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,7 +188,9 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
                         if (!(d2 < lim2 * (1.0 - 8e-15))) { const double rij = sqrt(d2); if (!((rij / hh) <= g.Cellfac)) continue; }
                         if (check_material && classes[cls_of[j]].Material != mat_i) continue;
                         uint32_t entry = (uint32_t)j | (ifirst ? 0x80000000u : 0u);
-                        if (oj > oi) { if (nhi + nlo < K) nbr[(int64_t)nhi * cap + s] = entry; ++nhi; }
+                        // walk_order (gradKernelCorr: the reference then sums per pair with locks, SolverFraser.cpp:112-115): one list in
+                        // plain discovery order, which is the order the pair loop adds into this particle
+                        if (oj > oi || walk_order) { if (nhi + nlo < K) nbr[(int64_t)nhi * cap + s] = entry; ++nhi; }
                         else         { if (nhi + nlo < K) nbr[(int64_t)(K - 1 - nlo) * cap + s] = entry; ++nlo; }
                         if (contact) {
                             // Domain.cpp:1446-1463: P1->normal += mj*xij ; P2->normal -= mi*xij, in discovery order
@@ -266,12 +268,18 @@ k_cont_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long
     if (threadIdx.x == 0 && m > 0) atomicMax(d_maxcnt, m);
 }
 
-__global__ void k_export_pairs(int64_t n, int64_t cap, int K, const uint32_t *nbr, const int *nb_hi, const int *orig, const int64_t *offs, int64_t *out)
+// pairs (i, j > i) of slot s: rows [0, nb_hi) hold them unless the list is in plain discovery order (walk_order), where
+// every front row is tested
+__global__ void k_export_pairs(int64_t n, int64_t cap, int K, const uint32_t *nbr, const int *nb_hi, const int *orig, const int64_t *offs, int64_t *out, int64_t *count)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    int64_t o = offs[s]; int oi = orig[s];
-    for (int k = 0; k < nb_hi[s]; ++k) { int j = (int)(nbr[(int64_t)k * cap + s] & 0x7fffffffu); out[2 * (o + k)] = oi; out[2 * (o + k) + 1] = orig[j]; }
+    int64_t o = out ? offs[s] : 0; int oi = orig[s]; int m = 0;
+    for (int k = 0; k < nb_hi[s]; ++k) {
+        int j = (int)(nbr[(int64_t)k * cap + s] & 0x7fffffffu);
+        if (orig[j] > oi) { if (out) { out[2 * (o + m)] = oi; out[2 * (o + m) + 1] = orig[j]; } ++m; }
+    }
+    if (count) count[s] = m;
 }
 __global__ void k_export_cont(int64_t n, int64_t cap, int nsph, const int *cont, const int *cont_cnt, const int *orig, const int64_t *offs, int64_t *out)
 {
@@ -414,7 +422,7 @@ int nb_build_impl(wf_ctx *c)
         if ((int64_t)K * cap > c->nbr_alloc) { cudaFree(c->nbr); c->nbr = nullptr; WF_CUDA(c, cudaMalloc(&c->nbr, (size_t)K * cap * sizeof(uint32_t))); c->nbr_alloc = (int64_t)K * cap; }
         WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt, 0, 4 * sizeof(int), st));
         k_nb_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->cell_start, c->cell_end, c->Q0[c->cur], c->Q2[c->cur], c->Ip(I_ORIG), c->Ip(I_ID),
-            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->uniform_h ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
+            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->uniform_h ? 1 : 0, c->prm.grad_kernel_corr ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
         WF_LAUNCH_CHECK(c); c->launches++;
         int mx = 0; WF_CUDA(c, cudaMemcpyAsync(&mx, c->d_maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));
         if (mx <= K) break;
@@ -465,7 +473,8 @@ static int export_common(wf_ctx *c, bool contact_pairs, int64_t *ij, int64_t cap
     int64_t *d_cnt = nullptr, *d_off = nullptr;
     WF_CUDA(c, cudaMalloc(&d_cnt, (n + 1) * sizeof(int64_t))); WF_CUDA(c, cudaMalloc(&d_off, (n + 1) * sizeof(int64_t)));
     WF_CUDA(c, cudaMemsetAsync(d_cnt, 0, (n + 1) * sizeof(int64_t), st));
-    k_cnt_to_i64<<<grid_for(n, 256), 256, 0, st>>>(n, contact_pairs ? c->cont_cnt : c->nb_hi, d_cnt);
+    if (contact_pairs) k_cnt_to_i64<<<grid_for(n, 256), 256, 0, st>>>(n, c->cont_cnt, d_cnt);
+    else k_export_pairs<<<grid_for(n, 256), 256, 0, st>>>(n, c->cap, c->nbr_k, c->nbr, c->nb_hi, c->Ip(I_ORIG), nullptr, nullptr, d_cnt);
     size_t need = 0; cub::DeviceScan::ExclusiveSum(nullptr, need, d_cnt, d_off, (int)(n + 1), st);
     void *tmp = nullptr; WF_CUDA(c, cudaMalloc(&tmp, need));
     cub::DeviceScan::ExclusiveSum(tmp, need, d_cnt, d_off, (int)(n + 1), st);
@@ -477,7 +486,7 @@ static int export_common(wf_ctx *c, bool contact_pairs, int64_t *ij, int64_t cap
         else {
             int64_t *d_out = nullptr; WF_CUDA(c, cudaMalloc(&d_out, 2 * total * sizeof(int64_t)));
             if (contact_pairs) k_export_cont<<<grid_for(n, 256), 256, 0, st>>>(n, c->cap, (int)c->nsph, c->cont, c->cont_cnt, c->Ip(I_ORIG), d_off, d_out);
-            else k_export_pairs<<<grid_for(n, 256), 256, 0, st>>>(n, c->cap, c->nbr_k, c->nbr, c->nb_hi, c->Ip(I_ORIG), d_off, d_out);
+            else k_export_pairs<<<grid_for(n, 256), 256, 0, st>>>(n, c->cap, c->nbr_k, c->nbr, c->nb_hi, c->Ip(I_ORIG), d_off, d_out, nullptr);
             std::vector<int64_t> h(2 * total);
             WF_CUDA(c, cudaMemcpyAsync(h.data(), d_out, 2 * total * sizeof(int64_t), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));
             cudaFree(d_out);

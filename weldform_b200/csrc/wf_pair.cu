@@ -52,6 +52,7 @@ struct PairArgs {
     const uint32_t *nbr; const int *nb_cnt, *nb_hi; const int *orig; const int *cls_of; const int *is_free;   // is_free: NULL when every particle is free
     double4 *Q0, *Q1, *Q2, *S0, *S1, *S2; double *F; const ClassProps *cls; const MatProps *mats;
     double dt; int any_ti, thermal, pl_heating, contact, cont_heat_fric; double pl_work_heat_frac;
+    int gc;                       // Domain::gradKernelCorr: corrected gradients, pairs in stored (first, second) roles, lists in plain discovery order
 };
 
 #define OWN(f) a.F[(int64_t)(f) * a.cap + s]
@@ -126,6 +127,62 @@ __device__ inline void tir_of(const S6 &sg, double rho, double TI, double out[6]
     out[0] = T(0, 0); out[1] = T(1, 1); out[2] = T(2, 2); out[3] = T(0, 1); out[4] = T(1, 2); out[5] = T(0, 2);
 }
 
+// ---- Bonet-Lok gradient correction (Domain::gradKernelCorr) -------------------------------------------------------------
+// Mult(GK * gradCorrM, xij) as InteractionAlt.cpp:118-131 evaluates it: the matrix is scaled first (matvec.h:547, element*GK),
+// then B(r) = x0*M(r,0) + x1*M(r,1) + x2*M(r,2) (matvec.h:836-841)
+__device__ inline V3 gc_scaled_mat_vec(const double M[9], double GK, const V3 &x)
+{
+    double g[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] = M[k] * GK;
+    return v3(x.x * g[0] + x.y * g[1] + x.z * g[2], x.x * g[3] + x.y * g[4] + x.z * g[5], x.x * g[6] + x.y * g[7] + x.z * g[8]);
+}
+// Mult(gradCorrM, GK*xij) as Thermal.cpp:101 evaluates it (matrix unscaled, vector scaled)
+__device__ inline V3 gc_mat_vec(const double M[9], const V3 &g)
+{ return v3(g.x * M[0] + g.y * M[1] + g.z * M[2], g.x * M[3] + g.y * M[4] + g.z * M[5], g.x * M[6] + g.y * M[7] + g.z * M[8]); }
+
+// Domain::CalcGradCorrMatrix (Domain.cpp:1832-1940), gather form: M_i = - sum_j (m_j/rho_j) (GK xij) (x) xij over the list in
+// discovery order, then InvLog (matvec.h:673-693); identity when the determinant is below 1e-10. All-free particle sets only.
+__global__ void __launch_bounds__(128) k_gradcorr(PairArgs a)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    if (a.orig[s] >= a.nsph) return;
+    const double4 qi = a.Q0[s];
+    const V3 xi = v3(qi.x, qi.y, qi.z);
+    const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
+    double T[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) T[k] = 0.0;
+    for (int n = 0; n < cnt; ++n) {
+        const uint32_t e = a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s];
+        const int j = (int)(e & 0x7fffffffu); const bool ifirst = (e >> 31) != 0;
+        const double4 qj = a.Q0[j], q2j = a.Q2[j];
+        const V3 xj = v3(qj.x, qj.y, qj.z);
+        const V3 xij = ifirst ? (xi - xj) : (xj - xi);
+        const double hh = (qi.w + qj.w) / 2.0;
+        const double q = norm(xij) / hh;
+        const double GK = (a.kt == 0 && a.dim == 3) ? cubicGW_c(c4_of(hh), q, hh) : gradW(a.dim, a.kt, q, hh);
+        const double f = q2j.x / q2j.y;                 // m/rho of the other particle of the pair (Domain.cpp:1859-1860)
+        const V3 g = GK * xij;
+        const double gx[3] = { g.x, g.y, g.z }, xx[3] = { xij.x, xij.y, xij.z };
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) T[3 * r + c] = T[3 * r + c] - (gx[r] * xx[c]) * f;
+    }
+    const double det = T[0] * (T[4] * T[8] - T[5] * T[7]) - T[1] * (T[3] * T[8] - T[5] * T[6]) + T[2] * (T[3] * T[7] - T[4] * T[6]);
+    double Mi[9];
+    if (fabs(det) < 1.0e-10) { for (int k = 0; k < 9; ++k) Mi[k] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0; }
+    else {
+        Mi[0] = (T[4] * T[8] - T[5] * T[7]) / det; Mi[1] = (T[2] * T[7] - T[1] * T[8]) / det; Mi[2] = (T[1] * T[5] - T[2] * T[4]) / det;
+        Mi[3] = (T[5] * T[6] - T[3] * T[8]) / det; Mi[4] = (T[0] * T[8] - T[2] * T[6]) / det; Mi[5] = (T[2] * T[3] - T[0] * T[5]) / det;
+        Mi[6] = (T[3] * T[7] - T[4] * T[6]) / det; Mi[7] = (T[1] * T[6] - T[0] * T[7]) / det; Mi[8] = (T[0] * T[4] - T[1] * T[3]) / det;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) OWN(F_GC + k) = Mi[k];
+}
+
 // ---- step prologue per particle: rho += dt*drho (SolverFraser.cpp:248-252), m/rho, TIR <- the tensor prepared for this step
 __global__ void k_prologue(PairArgs a)
 {
@@ -170,9 +227,33 @@ template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_s
     double sxx = 0., syy = 0., szz = 0., sxy = 0., syz = 0., sxz = 0., r01 = 0., r02 = 0., r12 = 0.;
     // software pipeline: the gathers of neighbour n+1 (and the list entry of n+2) are in flight while n is evaluated
     double4 qn = qi, wn = wi; uint32_t e2 = 0;
-    if (PF && cnt > 0) { const int j0 = (int)(a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s] & 0x7fffffffu); qn = a.Q0[j0]; wn = a.Q1[j0];
+    const bool gc = !FAST && a.gc;
+    double Mg[9];
+    if (!FAST) { for (int k = 0; k < 9; ++k) Mg[k] = gc ? OWN(F_GC + k) : 0.0; }
+    if (gc) {
+        // CalcRateTensors, locking branch with corrected gradients (InteractionAlt.cpp:362-441): per pair, in discovery order,
+        // StrainRate_i += (float)(m_j/rho_j) * (-0.5)(L + L^T), L = v_ab (x) (GK*gradCorrM_i) x_ij, roles as stored in the pair
+        for (int n = 0; n < cnt; ++n) {
+            const uint32_t e = a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s];
+            const int j = (int)(e & 0x7fffffffu); const bool ifirst = (e >> 31) != 0;
+            const double4 qj = a.Q0[j], wj = a.Q1[j];
+            const V3 xj = v3(qj.x, qj.y, qj.z), vj = v3(wj.x, wj.y, wj.z);
+            const V3 xij = ifirst ? (xi - xj) : (xj - xi), vab = ifirst ? (vi - vj) : (vj - vi);
+            const double hh = (hi + qj.w) / 2;
+            const double q = norm(xij) / hh;
+            const double GK = (a.kt == 0 && a.dim == 3) ? cubicGW_c(c4_of(hh), q, hh) : gradW(a.dim, a.kt, q, hh);
+            const V3 gk = gc_scaled_mat_vec(Mg, GK, xij);
+            const double mf = (double)(float)wj.w;        // float mj_dj = mj/dj (InteractionAlt.cpp:416,432)
+            const double L00 = vab.x * gk.x, L01 = vab.x * gk.y, L02 = vab.x * gk.z, L10 = vab.y * gk.x, L11 = vab.y * gk.y, L12 = vab.y * gk.z,
+                         L20 = vab.z * gk.x, L21 = vab.z * gk.y, L22 = vab.z * gk.z;
+            sxx = sxx + ((L00 + L00) * -0.5) * mf; syy = syy + ((L11 + L11) * -0.5) * mf; szz = szz + ((L22 + L22) * -0.5) * mf;
+            sxy = sxy + ((L01 + L10) * -0.5) * mf; syz = syz + ((L12 + L21) * -0.5) * mf; sxz = sxz + ((L02 + L20) * -0.5) * mf;
+            r01 = r01 + ((L01 - L10) * -0.5) * mf; r02 = r02 + ((L02 - L20) * -0.5) * mf; r12 = r12 + ((L12 - L21) * -0.5) * mf;
+        }
+    }
+    if (PF && cnt > 0 && !gc) { const int j0 = (int)(a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s] & 0x7fffffffu); qn = a.Q0[j0]; wn = a.Q1[j0];
                          if (cnt > 1) e2 = a.nbr[(int64_t)nb_row(1, nhi, a.K) * a.cap + s]; }
-    for (int n = 0; n < cnt; ++n) {
+    for (int n = 0; n < (gc ? 0 : cnt); ++n) {
         double4 qj, wj;
         if (PF) {
             qj = qn; wj = wn;
@@ -297,27 +378,33 @@ template <bool FAST, int GT, int MB, bool PF> __global__ void __launch_bounds__(
     const DivC dh = FAST ? divc_from(a.fc.h, a.fc.inv_h, a.fc.fast_h) : divc_make(hi), dW0 = FAST ? divc_from(a.fc.W0, a.fc.inv_W0, a.fc.fast_W0) : divc_make(W0i);
     const bool ti_on = a.any_ti && (!FAST || cpi.TI > 0.0);
     double ax = 0., ay = 0., az = 0.;
-    double4 qn = qi, wn = wi, q2n = q2i, s0n = s0i, s1n = s1i; uint32_t e2 = 0; int jcur = 0;
-    if (PF && cnt > 0) { jcur = (int)(a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s] & 0x7fffffffu); qn = a.Q0[jcur]; wn = a.Q1[jcur]; q2n = a.Q2[jcur];
+    double4 qn = qi, wn = wi, q2n = q2i, s0n = s0i, s1n = s1i; uint32_t e2 = 0; int jcur = 0; bool ifirst_cur = true;
+    const bool gc = !FAST && a.gc;
+    double Mg[9];
+    if (!FAST) { for (int k = 0; k < 9; ++k) Mg[k] = gc ? OWN(F_GC + k) : 0.0; }
+    if (PF && cnt > 0) { const uint32_t e0 = a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s]; jcur = (int)(e0 & 0x7fffffffu); ifirst_cur = (e0 >> 31) != 0; qn = a.Q0[jcur]; wn = a.Q1[jcur]; q2n = a.Q2[jcur];
                          if (MB == 2) { s0n = a.S0[jcur]; s1n = a.S1[jcur]; }
                          if (cnt > 1) e2 = a.nbr[(int64_t)nb_row(1, nhi, a.K) * a.cap + s]; }
     for (int n = 0; n < cnt; ++n) {
-        int j; double4 qj, wj, q2j;
+        int j; double4 qj, wj, q2j; bool ifirst_n = true;
         if (PF) {
-            j = jcur; qj = qn; wj = wn; q2j = q2n;
+            j = jcur; qj = qn; wj = wn; q2j = q2n; ifirst_n = ifirst_cur;
         } else {
-            j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
+            const uint32_t en = a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s];
+            j = (int)(en & 0x7fffffffu); ifirst_n = (en >> 31) != 0;
             qj = a.Q0[j]; wj = a.Q1[j]; q2j = a.Q2[j];
         }
         double4 s0j, s1j;
         if (PF && MB == 2) { s0j = s0n; s1j = s1n; }
         else { s0j = a.S0[j]; s1j = a.S1[j]; }            // consumed late in the iteration: their latency overlaps the kernel / viscosity math
         if (PF) {
-            if (n + 1 < cnt) { jcur = (int)(e2 & 0x7fffffffu); qn = a.Q0[jcur]; wn = a.Q1[jcur]; q2n = a.Q2[jcur]; if (MB == 2) { s0n = a.S0[jcur]; s1n = a.S1[jcur]; } }
+            if (n + 1 < cnt) { jcur = (int)(e2 & 0x7fffffffu); ifirst_cur = (e2 >> 31) != 0; qn = a.Q0[jcur]; wn = a.Q1[jcur]; q2n = a.Q2[jcur]; if (MB == 2) { s0n = a.S0[jcur]; s1n = a.S1[jcur]; } }
             if (n + 2 < cnt) e2 = a.nbr[(int64_t)nb_row(n + 2, nhi, a.K) * a.cap + s];
         }
         const double mj = q2j.x, dj = q2j.y;
-        const bool swap = (GT == 2) && (n >= nhi);      // GradientType 2 is not symmetric under i<->j: P1 = smaller creation index
+        // GradientType 2 is not symmetric under i<->j: P1 = smaller creation index. With gradKernelCorr the reference evaluates the
+        // pair in its stored roles (P1 = first) and subtracts from P2 (InteractionAlt.cpp:26-28,216-225)
+        const bool swap = gc ? !ifirst_n : ((GT == 2) && (n >= nhi));
         V3 xij = xi - v3(qj.x, qj.y, qj.z), vij = vi - v3(wj.x, wj.y, wj.z);
         if (swap) { xij = v3(-xij.x, -xij.y, -xij.z); vij = v3(-vij.x, -vij.y, -vij.z); }
         const double rij = norm(xij);
@@ -375,8 +462,10 @@ template <bool FAST, int GT, int MB, bool PF> __global__ void __launch_bounds__(
             mxx += (s1i.z + s1j.z) * fti; myy += (s1i.w + s1j.w) * fti; mzz += (s2i.x + t2j.x) * fti;
             mxy += (s2i.y + t2j.y) * fti; myz += (s2i.z + t2j.z) * fti; mxz += (s2i.w + t2j.w) * fti;
         }
-        // temp = (GK*xij)^T M (matvec.h:829-834), a_i += m_j*temp (or -= when i is P2 of a GradientType-2 pair)
-        const V3 g = GK * xij;
+        // temp = (GK*xij)^T M (matvec.h:829-834), a_i += m_j*temp (or -= when i is P2 of a GradientType-2 pair);
+        // gradKernelCorr: the corrected vector (GK*gradCorrM_i) xij takes the place of GK*xij (InteractionAlt.cpp:129-133,170-183)
+        V3 g = GK * xij;
+        if (gc) g = gc_scaled_mat_vec(Mg, GK, xij);
         double tx = g.x * mxx + g.y * mxy + g.z * mxz;
         double ty = g.x * mxy + g.y * myy + g.z * myz;
         double tz = g.x * mxz + g.y * myz + g.z * mzz;
@@ -511,6 +600,9 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __gl
     const DivC dh = FAST ? divc_from(a.fc.h, a.fc.inv_h, a.fc.fast_h) : divc_make(hi), dkk = FAST ? divc_from(a.fc.ksum, a.fc.inv_ksum, a.fc.fast_k) : divc_make(cpi.k_T + cpi.k_T);
     const double kk_same = FAST ? a.fc.kk : cpi.k_T * cpi.k_T;
     double temp = 0., dk = 0., dd = 0.;
+    const bool gc = !FAST && a.gc;
+    double Mg[9];
+    if (!FAST) { for (int k = 0; k < 9; ++k) Mg[k] = gc ? OWN(F_GC + k) : 0.0; }
     double4 qn = qi, wn = wi, q2n = q2i; uint32_t e1 = 0, e2 = 0;
     if (PF && cnt > 0) { e1 = a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s]; const int j0 = (int)(e1 & 0x7fffffffu); qn = a.Q0[j0]; wn = a.Q1[j0];
                          if (THERM || EKIN) q2n = a.Q2[j0];
@@ -540,15 +632,23 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __gl
             // CalcDensInc evaluates with x_i - x_j, v_i - v_j from particle i's side; dot() of two sign-flipped vectors is bit-identical
             const V3 vij = vi - vj;
             const V3 xij = xi - xj;
+            if (gc) {
+                // locking branch (InteractionAlt.cpp:569-582): dDensity_i += m_j * (rho_i/rho_j) * dot(v_ij, (GK*gradCorrM_i) x_ij), pair roles
+                const double4 qd = (THERM || EKIN) ? q2j_pf : a.Q2[j];
+                const V3 vp = ifirst ? vij : (vj - vi);
+                dd += (1.0 * qd.x) * (di / qd.y) * dot(vp, gc_scaled_mat_vec(Mg, GK, xp));
+            } else {
             const double t1 = dot(vij, GK * xij);
             dd += wj.w * t1;
+            }
         }
         if (THERM || EKIN) {
             const double4 q2j = q2j_pf;
             if (THERM) {
                 double kj, kki, num; bool same = true;
                 if (!FAST) { const int cj = a.cls_of[j]; same = (cj == ci); kj = same ? cpi.k_T : a.cls[cj].k_T; } else kj = cpi.k_T;
-                const double xgx = dot(xp, gx);
+                // gradKernelCorr (Thermal.cpp:90-111): dot(xij, gradCorrM_i (GK xij)) replaces dot(xij, GK xij)
+                const double xgx = gc ? dot(xp, gc_mat_vec(Mg, gx)) : dot(xp, gx);
                 if (ifirst) {      // i is P1: temp[i] += m, with m_j/rho_j
                     const double t0 = wj.w * 4. * (same ? kk_same : (cpi.k_T * kj));
                     const double t1 = same ? div_c(t0, dkk) : t0 / (cpi.k_T + kj);
@@ -582,7 +682,7 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __gl
                                  OWN(F_SH + 1) * OWN(F_SR + 1) + 2.0 * OWN(F_SH + 4) * OWN(F_SR + 4) + OWN(F_SH + 2) * OWN(F_SR + 2));
     }
     if (DENS) {
-        dd *= di;
+        if (!gc) dd *= di;
         OWN(F_DDN) = dd;
         if (a.any_ti && cpi.TI > 0.0 && !(a.is_free && !a.is_free[s])) {      // StartAcceleration: TIR for free particles only
             S6 sg; sg.xx = OWN(F_SG); sg.yy = OWN(F_SG + 1); sg.zz = OWN(F_SG + 2); sg.xy = OWN(F_SG + 3); sg.yz = OWN(F_SG + 4); sg.xz = OWN(F_SG + 5);
@@ -598,7 +698,7 @@ inline int divc_ok(double b)
     const unsigned ex = (unsigned)((bits >> 52) & 0x7ff);
     return ((bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull) && ex > 200 && ex < 1800;
 }
-inline bool fast_path(const wf_ctx *c) { return c->prm.kernel_type == 0 && c->prm.dimension == 3 && c->uniform_h && c->single_class; }
+inline bool fast_path(const wf_ctx *c) { return c->prm.kernel_type == 0 && c->prm.dimension == 3 && c->uniform_h && c->single_class && !c->prm.grad_kernel_corr; }
 
 PairArgs make_args(wf_ctx *c)
 {
@@ -618,7 +718,7 @@ PairArgs make_args(wf_ctx *c)
     a.Q0 = c->Q0[c->cur]; a.Q1 = c->Q1[c->cur]; a.Q2 = c->Q2[c->cur]; a.S0 = c->S0[c->cur]; a.S1 = c->S1[c->cur]; a.S2 = c->S2[c->cur];
     a.F = c->F[c->cur]; a.cls = c->d_classes; a.mats = c->d_mats; a.dt = c->dt; a.any_ti = c->any_ti ? 1 : 0;
     a.thermal = c->prm.thermal_solver; a.pl_heating = c->prm.pl_heating; a.contact = c->prm.contact; a.cont_heat_fric = c->prm.cont_heat_fric;
-    a.pl_work_heat_frac = c->prm.pl_work_heat_frac;
+    a.pl_work_heat_frac = c->prm.pl_work_heat_frac; a.gc = c->prm.grad_kernel_corr ? 1 : 0;
     return a;
 }
 
@@ -638,6 +738,17 @@ namespace wf {
 // launch KERNEL<targs..., PF> with PF = software pipeline on/off; grid of one thread per slot, 128 threads per block
 #define WF_LAUNCH_PF(KERNEL, ...) do { if (pf) KERNEL<__VA_ARGS__, true><<<g, 128, 0, c->stream>>>(a); else KERNEL<__VA_ARGS__, false><<<g, 128, 0, c->stream>>>(a); } while (0)
 
+// CalcGradCorrMatrix (Domain.cpp:1832-1940) on the current neighbour lists
+int pair_gradcorr(wf_ctx *c)
+{
+    WF_PAIR_PRECHECK(c);
+    if (!c->prm.grad_kernel_corr) return 0;
+    PairArgs a = make_args(c);
+    ProfScope ps(c, PK_NB_LIST);
+    k_gradcorr<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    c->dens_valid = false;
+    return 0;
+}
 // CalcDensInc + DensReduction + rho update. If the previous step's k_post already holds this step's density rate and TIR
 // (nothing moved in between) only the per-particle prologue runs.
 int pair_density(wf_ctx *c)

@@ -367,6 +367,7 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
 }
 
 extern "C" int wf_nb_build(wf_ctx *c) { WF_NEED_READY(c); return nb_build_impl(c); }
+extern "C" int wf_grad_corr(wf_ctx *c) { WF_NEED_READY(c); return pair_gradcorr(c); }
 extern "C" int wf_density(wf_ctx *c) { WF_NEED_READY(c); if (!c->dens_valid) WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1)); return pair_density(c); }
 extern "C" int wf_rate_stress(wf_ctx *c) { WF_NEED_READY(c); WF_CHECK(comm_halo_refresh(c, HALO_Q1)); return pair_rate_stress(c); }
 extern "C" int wf_accel(wf_ctx *c) { WF_NEED_READY(c); WF_CHECK(comm_halo_refresh(c, HALO_Q2 | HALO_S)); return pair_accel(c); }
@@ -421,7 +422,10 @@ static int nb_policy(wf_ctx *c)
         c->isyielding = true;
     }
     if (mx > MIN_PS_FOR_NBSEARCH || c->isfirst || check_every) {
-        if (c->ts_i == 0 && c->nb_cleared) WF_CHECK(nb_build_impl(c));
+        if (c->ts_i == 0 && c->nb_cleared) {
+            WF_CHECK(nb_build_impl(c));
+            WF_CHECK(pair_gradcorr(c));        // SolverFraser.cpp:203-204: at the cadence rebuilds only, not at the first-yield search above
+        }
     }
     return 0;
 }

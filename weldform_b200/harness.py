@@ -77,8 +77,7 @@ def context_from_case(case, device=0, comm=None):
     p.pfac = float(case.get("PFAC", 0.4)); p.dfac = float(case.get("DFAC", 0.0))
     p.cont_heat_fric = int(case.get("cont_heat_fric", 0)); p.cont_heat_cond = int(case.get("cont_heat_cond", 0))
     p.tuning = int(case.get("tuning", int(__import__("os").environ.get("WF_TUNING", "0"))))
-    if int(case.get("gradKernelCorr", 0)):
-        raise api.WeldformError("gradKernelCorr is not implemented (SURVEY.md section 8f item 2)")
+    p.grad_kernel_corr = int(case.get("gradKernelCorr", 0))
     ctx.set_params(p)
     if "materials" in case:
         mt = np.asarray(case["materials"], float).reshape(-1, 16)
@@ -169,6 +168,8 @@ def dump(ctx, info, with_pairs=True):
     for name in _DUMP:
         out[name] = ctx.download(name).reshape(-1)
     out["global_index"] = ctx.download("global_index").reshape(-1)
+    if ctx.grad_kernel_corr:
+        out["gradCorrM"] = ctx.download("gradCorrM").reshape(-1)
     s = ctx.reduce()
     out.update(n_particles=np.array([float(ctx.n)]), solid_part_count=np.array([float(ctx.n_sph)]), Time=np.array([s.time]),
                kin_energy_sum=np.array([s.kin_energy_sum]), int_energy_sum=np.array([s.int_energy_sum]), plastic_work=np.array([s.plastic_work]),

@@ -250,7 +250,7 @@ inline void Domain::backend_begin(double dt)
     p.thermal_solver = thermal_solver; p.pl_heating = pl_heating; p.pl_work_heat_frac = pl_work_heat_frac;
     p.contact = contact; p.friction_sta = friction_sta; p.friction_dyn = friction_dyn; p.pfac = PFAC; p.dfac = DFAC;
     p.cont_heat_fric = cont_heat_fric; p.cont_heat_cond = cont_heat_cond; p.contact_hc = contact_hc;
-    if (gradKernelCorr) throw new Fatal("Domain::gradKernelCorr (kernel gradient correction, Source/Domain.cpp:1832-1940) is not implemented in weldform_b200 yet (SURVEY.md section 8f item 2)");
+    p.grad_kernel_corr = gradKernelCorr ? 1 : 0;     // CalcGradCorrMatrix + the locking summation the reference switches to (SolverFraser.cpp:112-115)
     if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
     if (friction_function != Constant && contact) throw new Fatal("Domain::friction_function != Constant is not implemented in weldform_b200");
     ck(wf_set_params(backend, &p), "wf_set_params");

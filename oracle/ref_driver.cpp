@@ -25,6 +25,7 @@
 #include "InteractionAlt.cpp"
 #include "SolverKickDrift.cpp"
 #include "SolverFraser.cpp"
+#include "SolverLeapfrog.cpp"
 
 #include "wfc_io.h"
 
@@ -208,7 +209,8 @@ int main(int argc, char ** argv) try
     dom.pl_heating = in.scalar("pl_heating", 0) != 0.0;
     dom.pl_work_heat_frac = in.scalar("pl_work_heat_frac", 0.9);
     dom.BC.InOutFlow = 0;
-    dom.auto_ts = false;
+    dom.auto_ts = in.scalar("auto_ts", 0) != 0.0;      // honoured by the KickDrift / LeapFrog solvers only (SolverFraser.cpp:500-502 is commented out)
+    dom.CFL = in.scalar("CFL", 0.7);
 
     if (in.has("bc")) {
         const std::vector<double> & b = in.f("bc");
@@ -236,9 +238,13 @@ int main(int argc, char ** argv) try
         dump_pairs(out, "pairs_discovery", dom.SMPairs, false);
     } else {
         // run exactly nsteps iterations of while (Time <= tf) (Source/SolverFraser.cpp:133)
-        const double tf = (nsteps - 0.5) * dt;
+        double tf = (nsteps - 0.5) * dt;
+        if (in.scalar("tf", 0.0) > 0.0) tf = in.scalar("tf", 0.0);     // adaptive time step: the loop ends on Time, not on a step count
+        const int solver = (int)in.scalar("solver", 0);
         auto t0 = std::chrono::steady_clock::now();
-        dom.SolveDiffUpdateFraser(tf, dt, 1.0e30, "wfref", 1000000);
+        if (solver == 1) dom.SolveDiffUpdateKickDrift(tf, dt, 1.0e30, "wfref", 1000000);
+        else if (solver == 2) dom.SolveDiffUpdateLeapFrog(tf, dt, 1.0e30, "wfref", 1000000);
+        else dom.SolveDiffUpdateFraser(tf, dt, 1.0e30, "wfref", 1000000);
         solve_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     std::cout.rdbuf(cout_buf);
@@ -248,6 +254,7 @@ int main(int argc, char ** argv) try
     out.put_scalar("solid_part_count", (double)dom.solid_part_count);
     out.put_scalar("Time", dom.getTime());
     out.put_scalar("solve_seconds", solve_seconds);
+    out.put_scalar("deltat", dom.getStepSize());
     out.put_scalar("kin_energy_sum", dom.kin_energy_sum);
     out.put_scalar("int_energy_sum", dom.int_energy_sum);
     out.put_scalar("plastic_work", dom.plastic_work);

@@ -286,6 +286,9 @@ struct Dom {
     int Dimension = 3, KernelType = 0, GradientType = 0, ts_nb_inc = 5;
     double Cellfac = 2.0, deltat = 0.0, Time = 0.0;
     bool thermal_solver = false, pl_heating = false, contact = false, cont_heat_fric = false, cont_heat_cond = false;
+    int solver = 0;                          // 0 SolveDiffUpdateFraser, 1 SolveDiffUpdateKickDrift, 2 SolveDiffUpdateLeapFrog
+    bool auto_ts = false; double CFL = 0.7, deltatint = 0.0, deltatmin = 0.0, manual_min_ts = 1.e-10;   // Domain.cpp:126,153,170
+    long steps_done = 0;
     bool gradKernelCorr = false;             // Domain::gradKernelCorr: Bonet-Lok corrected gradient; the Fraser solver then sums with locks, in pair order (SolverFraser.cpp:112-115)
     double pl_work_heat_frac = 0.9, friction_sta = 0.0, friction_dyn = 0.0, PFAC = 0.4, DFAC = 0.0, contact_force_factor = 1.0, contact_hc = 0.0;
     double DomMax[3] = { -100000000000.0, -100000000000.0, -100000000000.0 }, DomMin[3] = { 100000000000.0, 100000000000.0, 100000000000.0 };
@@ -904,9 +907,34 @@ struct Dom {
         for (size_t m = 0; m < meshes.size(); ++m) { double f = ramp(Time, meshes[m].tau); for (int k = 0; k < 3; ++k) meshes[m].m_v(k) = meshes[m].vel[k] * f; }
     }
 
-    // ---- Source/SolverFraser.cpp:21-513 SolveDiffUpdateFraser ----------------------------------------------------
-    void Solve(int nsteps, double dt) {
-        deltat = dt;
+    // ---- Domain.cpp:267-297 CheckMinTSVel (over the Nishiura lists: pairs as min first, then as max) + :205-239 AdaptiveTimeStep
+    void CheckMinTSVel() {
+        deltatmin = deltatint;
+        for (size_t i = 0; i < N; ++i) {
+            double mn = 1000.;
+            if (i < ipairs.size()) {
+                for (size_t n = 0; n < ipairs[i].size(); ++n) { int p = ipairs[i][n]; int j = std::max(SM[p].first, SM[p].second); double d = norm3(vsub(X(j), X(i))); if (d < mn) mn = d; }
+                for (size_t n = 0; n < jpairs[i].size(); ++n) { int p = jpairs[i][n]; int j = std::min(SM[p].first, SM[p].second); double d = norm3(vsub(X(j), X(i))); if (d < mn) mn = d; }
+            }
+            double test = CFL * mn / (Cs[i] + norm3(Vv(i)));
+            if (deltatmin > test) deltatmin = test;
+        }
+    }
+    void AdaptiveTimeStep() {
+        if (deltatint > deltatmin) {
+            if (deltat < deltatmin) deltat = 2.0 * deltat * deltatmin / (deltat + deltatmin);
+            else deltat = deltatmin;
+        } else {
+            if (deltatint != deltat) deltat = 2.0 * deltat * deltatint / (deltat + deltatint);
+            else deltat = deltatint;
+        }
+        if (deltat < manual_min_ts) deltat = manual_min_ts;
+    }
+    // ---- Source/SolverFraser.cpp:21-513 SolveDiffUpdateFraser, SolverKickDrift.cpp:21-400 SolveDiffUpdateKickDrift,
+    //      SolverLeapfrog.cpp:24-450 SolveDiffUpdateLeapFrog: one neighbour policy, three step orders.
+    //      nsteps > 0: that many iterations; else while (Time <= tf) as the reference loops.
+    void Solve(int nsteps, double dt, double tf = 0.0) {
+        deltat = deltatint = deltatmin = dt;
         for (size_t i = 0; i < N; ++i) Pressure[i] = EOS(PresEq[i], Cs[i], P0[i], Density[i], RefDensity[i]);   // InitialChecks, Domain.cpp:2097-2113
         CellInitiate(); ListGenerate();
         int ts_i = 0; bool isfirst = true, isyielding = false;
@@ -916,15 +944,19 @@ struct Dom {
         }
         ClearNbData();
         const double MIN_PS_FOR_NBSEARCH = 1.e-6;   // Domain.cpp:28
-        for (int step = 0; step < nsteps; ++step) {
+        double prev_deltat = deltat;
+        for (int step = 0; nsteps > 0 ? step < nsteps : Time <= tf; ++step) {
             StartAcceleration();
             double mx = 0;
             for (size_t i = 0; i < N; ++i) if (pl_strain[i] > mx) mx = pl_strain[i];
-            max_disp[0] = max_disp[1] = max_disp[2] = 0.;
+            double mdl[3] = { 0., 0., 0. };
             for (int i = 0; i < solid_part_count; ++i) for (int j = 0; j < 3; ++j)
-                if (Disp[3 * i + j] * Disp[3 * i + j] > max_disp[j]) max_disp[j] = Disp[3 * i + j] * Disp[3 * i + j];
-            for (int j = 0; j < 3; ++j) max_disp[j] = std::sqrt(max_disp[j]);
-            V3 md; md(0) = max_disp[0]; md(1) = max_disp[1]; md(2) = max_disp[2];
+                if (Disp[3 * i + j] * Disp[3 * i + j] > mdl[j]) mdl[j] = Disp[3 * i + j] * Disp[3 * i + j];
+            for (int j = 0; j < 3; ++j) mdl[j] = std::sqrt(mdl[j]);
+            // the KickDrift / LeapFrog loops keep max_disp in a LOCAL that shadows Domain::max_disp (SolverKickDrift.cpp:122,
+            // SolverLeapfrog.cpp:138): the member a driver reads stays at its constructor value there
+            if (solver == 0) for (int j = 0; j < 3; ++j) max_disp[j] = mdl[j];
+            V3 md; md(0) = mdl[0]; md(1) = mdl[1]; md(2) = mdl[2];
             bool check_nb_every_time = norm3(md) > 0.1 * hmax;
             if (mx > MIN_PS_FOR_NBSEARCH && !isyielding) {
                 ClearNbData(); MainNeighbourSearch(); CalcPairPosList(); SaveNeighbourData();
@@ -934,26 +966,51 @@ struct Dom {
             if (mx > MIN_PS_FOR_NBSEARCH || isfirst || check_nb_every_time) {
                 if (ts_i == 0 && nb_cleared) {
                     MainNeighbourSearch(); CalcPairPosList(); SaveNeighbourData();
-                    if (gradKernelCorr) CalcGradCorrMatrix();          // SolverFraser.cpp:203-204: at cadence rebuilds only, not at the first-yield search
+                    // SolverFraser.cpp:203-204, SolverLeapfrog.cpp:196-197: at cadence rebuilds, not at the first-yield search; KickDrift: never here
+                    if (gradKernelCorr && solver != 1) CalcGradCorrMatrix();
                     if (contact) ContactNbUpdate();
                 }
             }
-            if (gradKernelCorr) Density_lock(); else
-            Density_pass();
-            for (size_t i = 0; i < N; ++i) Density[i] += deltat * dDensity[i];
-            if (gradKernelCorr) RateTensors_lock(); else
-            RateTensors_pass();
-            for (size_t i = 0; i < N; ++i) CalcStressStrain(i, deltat);
-            if (gradKernelCorr) Accel_lock(); else
-            Accel_pass();
-            if (contact) ContactWang();
-            UserBC();
-            for (size_t i = 0; i < N; ++i) for (int k = 0; k < 3; ++k) {
-                double du = (v[3 * i + k] + 0.0) * deltat + 0.5 * a[3 * i + k] * deltat * deltat;
-                Disp[3 * i + k] += du; x[3 * i + k] += du;
+            if (isfirst && gradKernelCorr) CalcGradCorrMatrix();     // SolverFraser.cpp:228-231, SolverKickDrift.cpp:187-190, SolverLeapfrog.cpp:208-211
+            if (solver == 0) {
+                if (gradKernelCorr) Density_lock(); else Density_pass();
+                for (size_t i = 0; i < N; ++i) Density[i] += deltat * dDensity[i];
+                if (gradKernelCorr) RateTensors_lock(); else RateTensors_pass();
+                for (size_t i = 0; i < N; ++i) CalcStressStrain(i, deltat);
+                if (gradKernelCorr) Accel_lock(); else Accel_pass();
+                if (contact) ContactWang();
+                UserBC();
+                for (size_t i = 0; i < N; ++i) for (int k = 0; k < 3; ++k) {
+                    double du = (v[3 * i + k] + 0.0) * deltat + 0.5 * a[3 * i + k] * deltat * deltat;
+                    Disp[3 * i + k] += du; x[3 * i + k] += du;
+                }
+                for (size_t i = 0; i < N; ++i) for (int k = 0; k < 3; ++k) v[3 * i + k] += a[3 * i + k] * deltat;
+                UserBC();
+            } else {
+                // SolverKickDrift.cpp:195-271 / SolverLeapfrog.cpp:213-290
+                if (gradKernelCorr) Accel_lock(); else Accel_pass();
+                UserBC();
+                if (contact) ContactWang();
+                if (solver == 2) {
+                    if (isfirst) for (size_t i = 0; i < 3 * N; ++i) v[i] -= a[i] * 0.5 * deltat;
+                    UserBC();
+                }
+                prev_deltat = deltat;
+                if (auto_ts) { CheckMinTSVel(); AdaptiveTimeStep(); }
+                if (solver == 1) for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * 0.5 * prev_deltat * 1.;
+                else for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * 0.5 * (prev_deltat + deltat);
+                UserBC();
+                if (gradKernelCorr) Density_lock(); else Density_pass();
+                if (solver == 1) for (size_t i = 0; i < N; ++i) Density[i] += deltat * dDensity[i] * 1.;
+                else for (size_t i = 0; i < N; ++i) Density[i] += deltat * dDensity[i];
+                for (size_t i = 0; i < 3 * N; ++i) {
+                    double du = solver == 1 ? (v[i] + 0.0) * deltat * 1. : (v[i] + 0.0) * deltat;
+                    Disp[i] += du; x[i] += du;
+                }
+                if (solver == 1) { for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * deltat / 2. * 1.; UserBC(); }
+                if (gradKernelCorr) RateTensors_lock(); else RateTensors_pass();
+                for (size_t i = 0; i < N; ++i) CalcStressStrain(i, deltat);
             }
-            for (size_t i = 0; i < N; ++i) for (int k = 0; k < 3; ++k) v[3 * i + k] += a[3 * i + k] * deltat;
-            UserBC();
             CalcPlasticWorkHeat(deltat);
             ThermalCalcs(deltat);
             Energies();
@@ -965,6 +1022,7 @@ struct Dom {
                 if (ts_i > (ts_nb_inc - 1)) ts_i = 0;
             }
             if (isfirst) isfirst = false;
+            steps_done++;
         }
     }
 };
@@ -1092,6 +1150,7 @@ void load_case(const wfc::File & in, Dom & d)
     d.cont_heat_fric = in.scalar("cont_heat_fric", 0) != 0.0; d.cont_heat_cond = in.scalar("cont_heat_cond", 0) != 0.0;
     d.ts_nb_inc = (int)in.scalar("ts_nb_inc", 5);
     d.gradKernelCorr = in.scalar("gradKernelCorr", 0) != 0.0;
+    d.solver = (int)in.scalar("solver", 0); d.auto_ts = in.scalar("auto_ts", 0) != 0.0; d.CFL = in.scalar("CFL", 0.7);
     d.thermal_solver = in.scalar("thermal_solver", 0) != 0.0; d.pl_heating = in.scalar("pl_heating", 0) != 0.0;
     d.pl_work_heat_frac = in.scalar("pl_work_heat_frac", 0.9);
     if (in.has("bc")) { const dvec & b = in.f("bc"); for (size_t r = 0; r + 8 <= b.size(); r += 8) { BC s; s.id = (int)b[r]; s.v[0] = b[r + 1]; s.v[1] = b[r + 2]; s.v[2] = b[r + 3]; s.tau = b[r + 4]; s.set_a = (int)b[r + 5]; d.bcs.push_back(s); } }
@@ -1126,11 +1185,12 @@ extern "C" int wfo_run_file(const char * case_path, const char * out_path)
         dump_pairs(out, "pairs_discovery", d.SM, false);
     } else {
         auto t0 = std::chrono::steady_clock::now();
-        d.Solve(nsteps, dt);
+        const double tf = in.scalar("tf", 0.0);          // > 0: loop while (Time <= tf) as the reference does (needed with auto_ts)
+        if (tf > 0.0) d.Solve(0, dt, tf); else d.Solve(nsteps, dt);
         solve_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     out.put_scalar("n_particles", (double)d.N); out.put_scalar("solid_part_count", (double)d.solid_part_count);
-    out.put_scalar("Time", d.Time); out.put_scalar("solve_seconds", solve_seconds);
+    out.put_scalar("Time", d.Time); out.put_scalar("solve_seconds", solve_seconds); out.put_scalar("deltat", d.deltat);
     out.put_scalar("kin_energy_sum", d.kin_energy_sum); out.put_scalar("int_energy_sum", d.int_energy_sum);
     out.put_scalar("plastic_work", d.plastic_work); out.put_scalar("contact_force_sum", d.contact_force_sum);
     out.put_scalar("contact_reaction_sum", d.contact_reaction_sum); out.put_scalar("ext_forces_work", d.ext_forces_work);

@@ -1,5 +1,5 @@
 # usage: bash scripts/gpu_v5.sh <tag>   -- GPU tests, 10M bench, ncu launch list, full ncu capture of the pair kernels
-tag=${1:-v5}
+tag=${1:-v7}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 > gpurun_out/pytest_$tag.log
 tail -3 gpurun_out/pytest_$tag.log

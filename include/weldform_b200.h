@@ -52,6 +52,10 @@ typedef struct wf_params {
     int    nb_order_reference; /* 1: neighbour lists in the reference's Nproc=1 summation order (default) */
     int    grad_kernel_corr;   /* Domain::gradKernelCorr: Bonet-Lok corrected kernel gradient (Domain.cpp:1832-1940). As in the reference the Fraser
                                 * solver then sums per pair with locks, in pair-discovery order (SolverFraser.cpp:112-115) */
+    int    solver;             /* step order run by wf_run: 0 SolveDiffUpdateFraser (SolverFraser.cpp), 1 SolveDiffUpdateKickDrift
+                                * (SolverKickDrift.cpp:21-400), 2 SolveDiffUpdateLeapFrog (SolverLeapfrog.cpp:24-450) */
+    int    auto_ts;            /* Domain::auto_ts: CheckMinTSVel + AdaptiveTimeStep (Domain.cpp:205-297); honoured by solvers 1 and 2 only, like the reference */
+    double cfl;                /* Domain::CFL (0.7) */
     int    tuning;             /* bit 0: disable the software-pipelined gathers of the pair kernels (A/B measurements), bit 8: multi-GPU mesh-particle layout on one GPU; default 0 */
 } wf_params;
 
@@ -107,6 +111,7 @@ typedef struct wf_scalars {
     double max_T, min_T;
     int64_t steps, nb_rebuilds;
     int32_t is_yielding;
+    double deltat;             /* current time step (changes under auto_ts) */
 } wf_scalars;
 
 /* Field selectors for wf_download / wf_upload. Tensor fields use 9 doubles (row-major 3x3) per particle on the host side. */
@@ -172,6 +177,11 @@ int wf_fraser_stage_b1(wf_ctx *ctx);
 int wf_fraser_stage_b2(wf_ctx *ctx);
 int wf_fraser_stage_c(wf_ctx *ctx);
 int wf_fraser_run(wf_ctx *ctx, int64_t nsteps);     /* nsteps full steps with device-side BCs, no host callback */
+/* Whole steps of the solver wf_params::solver selects (Fraser / KickDrift / LeapFrog step order), device-side BCs.
+ * wf_run: nsteps steps. wf_run_until: while (Time <= tf) as the reference's loops do (the only stop rule that makes sense
+ * with auto_ts); *steps_done receives the number of steps taken. */
+int wf_run(wf_ctx *ctx, int64_t nsteps);
+int wf_run_until(wf_ctx *ctx, double tf, int64_t *steps_done);
 
 /* ---- host-side lattice generators (Domain::AddCylinderLength / AddBoxLength, Domain.cpp:708,326); 3-D, cubic packing.
  * Call with pts = NULL to get the count. Returns particle count or a negative wf_status. ------------------------ */

@@ -131,7 +131,7 @@ def contact_compression(dx=0.0024, nsteps=1, friction=0.2, model=HOLLOMON, vmax=
 FIELDS_F64 = ["x", "v", "a", "Displacement", "Density", "dDensity", "Pressure", "Sigma", "ShearStress", "StrainRate", "RotationRate",
               "Strain", "Strain_pl", "TIR", "pl_strain", "Sigmay", "eff_strain_rate", "T", "dTdt", "q_plheat", "q_conv",
               "contforce", "delta_cont", "normal", "dint_energy_dt", "dkin_energy_dt"]
-SCALARS = ["Time", "int_energy_sum", "plastic_work", "contact_force_sum", "contact_reaction_sum", "ext_forces_work", "max_disp"]
+SCALARS = ["Time", "int_energy_sum", "plastic_work", "contact_force_sum", "contact_reaction_sum", "ext_forces_work", "max_disp", "deltat"]
 
 
 def compression_fast(dx, nsteps=1, **kw):

@@ -38,6 +38,17 @@ def golden_cases():
     out["gc_comp_yield_40"] = gc(cases.perturbed(cases.compression(dx=0.04, nsteps=40), amp=60.0))      # first-yield search keeps the stale matrices
     out["gc_g2_jc_12"] = gc(cases.perturbed(cases.compression(dx=0.04, nsteps=12, gradient_type=2, model=cases.JOHNSON_COOK), amp=40.0))
     out["gc_contact_60"] = gc(cases.contact_compression(dx=0.0032, nsteps=60, vmax=5.0, tau=1e-5, dens=8, cfl=0.3))
+    # SolveDiffUpdateKickDrift / SolveDiffUpdateLeapFrog, fixed and adaptive time step
+    def sv(c, solver, **kw):
+        c = dict(c); c["solver"] = float(solver); c.update(kw)
+        return c
+    base = cases.perturbed(cases.compression(dx=0.04, nsteps=30), amp=60.0)
+    out["kd_comp_30"] = sv(base, 1)
+    out["lf_comp_30"] = sv(base, 2)
+    out["kd_auto_ts"] = sv(base, 1, auto_ts=1.0, CFL=0.1, tf=25 * base["dt"])        # CFL 0.1: the velocity criterion shortens the step
+    out["lf_auto_ts"] = sv(base, 2, auto_ts=1.0, CFL=0.1, tf=25 * base["dt"])
+    out["lf_contact_60"] = sv(cases.contact_compression(dx=0.0032, nsteps=60, vmax=5.0, tau=1e-5, dens=8, cfl=0.3), 2)
+    out["kd_gc_20"] = sv(gc(cases.perturbed(cases.compression(dx=0.04, nsteps=20), amp=60.0)), 1)
     return out
 
 

@@ -27,6 +27,8 @@ def main():
         ctx.solver_init(float(case.get("dt", 1.0e-7)))
         if int(case.get("mode", 0)) == 1:
             ctx.nb_build()
+        elif float(case.get("tf", 0.0)) > 0.0:
+            ctx.run_until(float(case["tf"]))
         else:
             ctx.run(int(case.get("nsteps", 1)))
         out = harness.dump(ctx, info, True)

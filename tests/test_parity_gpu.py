@@ -65,7 +65,8 @@ def test_golden_one_step_bit_exact_fields(harness, name):
         assert "gradCorrM" in got and np.abs(got["gradCorrM"].reshape(-1, 9)[:, [0, 4, 8]] - 1.0).max() > 1e-3, "correction matrices must be non-trivial"
 
 
-@pytest.mark.parametrize("name", ["comp_yield_40", "contact_100", "comp_hollomon_30", "comp_jc_30", "gc_comp_yield_40", "gc_g2_jc_12", "gc_contact_60"])
+@pytest.mark.parametrize("name", ["comp_yield_40", "contact_100", "comp_hollomon_30", "comp_jc_30", "gc_comp_yield_40", "gc_g2_jc_12", "gc_contact_60",
+                                  "kd_comp_30", "lf_comp_30", "kd_auto_ts", "lf_auto_ts", "lf_contact_60", "kd_gc_20"])
 def test_golden_multi_step_tight(harness, name):
     """Tens of steps through yield, rebuilds and contact stay within 1e-7 of the reference on every field (state fields
     x, v, rho, sigma sit at 1e-10 or better; a and d(rho)/dt, differences of large terms, are the noisiest)."""
@@ -117,6 +118,21 @@ def test_grad_kernel_corr_1000_steps(harness, oracle_port):
     got, ref = harness.run_case(c), ot.run_port(c)
     assert ref["pl_strain"].max() > 5e-3 and np.isfinite(ref["x"]).all()
     _compare(got, ref, TOL_LONG, keys=LONG_KEYS + ["Time", "plastic_work", "int_energy_sum", "max_disp", "gradCorrM"], what="gradKernelCorr 1000 steps")
+
+
+@pytest.mark.parametrize("solver,auto_ts", [(1, 0), (2, 1)])
+def test_kickdrift_leapfrog_long(harness, oracle_port, solver, auto_ts):
+    """SolveDiffUpdateKickDrift / SolveDiffUpdateLeapFrog step orders (SURVEY.md section 8f item 1) through yield and rebuilds;
+    with auto_ts the run ends on Time like the reference's loop and the step count must agree."""
+    c = cases.perturbed(cases.compression(dx=0.03, nsteps=600, model=cases.HOLLOMON), amp=30.0)
+    c["solver"] = float(solver)
+    if auto_ts:
+        c.update(auto_ts=1.0, CFL=0.2, tf=400 * c["dt"])
+    got, ref = harness.run_case(c), ot.run_port(c)
+    assert ref["pl_strain"].max() > 5e-3 and np.isfinite(ref["x"]).all()
+    if auto_ts:
+        assert float(ref["deltat"][0]) < 0.9 * c["dt"], "the velocity criterion is meant to shorten the step in this case"
+    _compare(got, ref, TOL_LONG, keys=LONG_KEYS + ["Time", "deltat", "plastic_work", "int_energy_sum"], what="solver %d" % solver)
 
 
 def test_contact_500_steps(harness, oracle_port):

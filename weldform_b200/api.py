@@ -22,7 +22,7 @@ class wf_params(C.Structure):
                 ("contact", C.c_int), ("friction_sta", C.c_double), ("friction_dyn", C.c_double),
                 ("pfac", C.c_double), ("dfac", C.c_double), ("contact_force_factor", C.c_double),
                 ("cont_heat_fric", C.c_int), ("cont_heat_cond", C.c_int), ("contact_hc", C.c_double),
-                ("nb_order_reference", C.c_int), ("grad_kernel_corr", C.c_int), ("tuning", C.c_int)]
+                ("nb_order_reference", C.c_int), ("grad_kernel_corr", C.c_int), ("solver", C.c_int), ("auto_ts", C.c_int), ("cfl", C.c_double), ("tuning", C.c_int)]
 
 
 class wf_material(C.Structure):
@@ -52,7 +52,7 @@ class wf_scalars(C.Structure):
                 ("kin_energy_sum", C.c_double), ("int_energy_sum", C.c_double), ("plastic_work", C.c_double),
                 ("contact_force_sum", C.c_double), ("contact_reaction_sum", C.c_double), ("ext_forces_work", C.c_double),
                 ("contact_friction_work", C.c_double), ("accum_cont_heat_cond", C.c_double), ("max_T", C.c_double), ("min_T", C.c_double),
-                ("steps", C.c_int64), ("nb_rebuilds", C.c_int64), ("is_yielding", C.c_int32)]
+                ("steps", C.c_int64), ("nb_rebuilds", C.c_int64), ("is_yielding", C.c_int32), ("deltat", C.c_double)]
 
 
 # wf_field enum: name -> (id, components, dtype)
@@ -93,6 +93,7 @@ def load_library():
         "wf_nb_export_pairs": ([vp, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)], C.c_int),
         "wf_cont_export_pairs": ([vp, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)], C.c_int),
         "wf_reduce": ([vp, C.POINTER(wf_scalars)], C.c_int), "wf_fraser_run": ([vp, C.c_int64], C.c_int),
+        "wf_run": ([vp, C.c_int64], C.c_int), "wf_run_until": ([vp, C.c_double, C.POINTER(C.c_int64)], C.c_int),
         "wf_gen_cylinder": ([_PD, C.c_double, C.c_double, C.c_double, _PD, C.c_int64], C.c_int64),
         "wf_gen_box": ([_PD, C.c_double, C.c_double, C.c_double, C.c_double, _PD, C.c_int64, _PD], C.c_int64),
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
@@ -320,7 +321,14 @@ class Context:
         self._ck(getattr(self.L, "wf_" + name)(self.h), "wf_" + name)
 
     def run(self, nsteps):
-        self._ck(self.L.wf_fraser_run(self.h, nsteps), "wf_fraser_run")
+        """nsteps whole steps of the configured solver (wf_params::solver), device-side BCs"""
+        self._ck(self.L.wf_run(self.h, nsteps), "wf_run")
+
+    def run_until(self, tf):
+        """while (Time <= tf) step; returns the number of steps taken"""
+        n = C.c_int64()
+        self._ck(self.L.wf_run_until(self.h, float(tf), C.byref(n)), "wf_run_until")
+        return int(n.value)
 
     def sync(self):
         self._ck(self.L.wf_sync(self.h), "wf_sync")

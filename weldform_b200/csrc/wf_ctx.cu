@@ -47,7 +47,7 @@ extern "C" void wf_default_params(wf_params *p)
     p->dimension = 3; p->kernel_type = 0; p->gradient_type = 0; p->ts_nb_inc = 5;
     for (int k = 0; k < 3; ++k) { p->dom_min[k] = 100000000000.0; p->dom_max[k] = -100000000000.0; }
     p->pl_work_heat_frac = 0.9; p->pfac = 0.4; p->dfac = 0.0; p->contact_force_factor = 1.0;
-    p->nb_order_reference = 1;
+    p->nb_order_reference = 1; p->cfl = 0.7;
 }
 
 extern "C" int wf_create(int device, wf_ctx **out)
@@ -144,6 +144,7 @@ extern "C" int wf_set_params(wf_ctx *c, const wf_params *p)
 {
     if (!c || !p) return WF_ERR_ARG;
     if (p->dimension != 3) return fail(c, WF_ERR_UNSUPPORTED, "wf_set_params: Dimension=%d; only the 3-D path is implemented", p->dimension);
+    if (p->solver < 0 || p->solver > 2) return fail(c, WF_ERR_UNSUPPORTED, "wf_set_params: solver=%d; 0 Fraser, 1 KickDrift, 2 LeapFrog are implemented (Verlet is not)", p->solver);
     if (p->kernel_type < 0 || p->kernel_type > 3) return fail(c, WF_ERR_ARG, "wf_set_params: kernel_type %d out of range", p->kernel_type);
     if (p->gradient_type < 0 || p->gradient_type > 2) return fail(c, WF_ERR_ARG, "wf_set_params: gradient_type %d out of range", p->gradient_type);
     if (p->ts_nb_inc < 1) return fail(c, WF_ERR_ARG, "wf_set_params: ts_nb_inc must be >= 1");
@@ -210,7 +211,7 @@ static int alloc_particles(wf_ctx *c, int64_t n)
     WF_CUDA(c, cudaMalloc(&c->cont_cnt, n * sizeof(int)));
     WF_CUDA(c, cudaMemset(c->nb_cnt, 0, n * sizeof(int))); WF_CUDA(c, cudaMemset(c->nb_hi, 0, n * sizeof(int)));
     WF_CUDA(c, cudaMemset(c->cont_cnt, 0, n * sizeof(int)));
-    c->partial_blocks = 1024;
+    c->partial_blocks = 148 * 4;              // grid-stride reduction: few blocks, so that the 20 block-wide reductions per block stay negligible
     WF_CUDA(c, cudaMalloc(&c->d_partial, (size_t)c->partial_blocks * 32 * sizeof(double)));
     return 0;
 }

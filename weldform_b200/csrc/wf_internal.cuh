@@ -126,6 +126,7 @@ struct wf_ctx {
     wf::DevScalars *d_sc = nullptr; wf::DevScalars *h_sc = nullptr;   // h_sc pinned
     double *d_partial = nullptr; int partial_blocks = 0;
     // solver state (SolverFraser.cpp:62-68)
+    double dt_init = 0.0, dt_min = 0.0;          // Domain::deltatint / deltatmin (adaptive time step, Domain.cpp:205-297)
     double dt = 0.0, time = 0.0; int ts_i = 0; bool isfirst = true, isyielding = false, nb_cleared = true;
     int64_t steps = 0, nb_rebuilds = 0, launches = 0; bool in_step = false;
     double step_max_pl = 0.0;                    // `max` of SolverFraser.cpp:139-149 for the step in flight
@@ -168,12 +169,14 @@ int nb_cell_initiate(wf_ctx *c);
 int nb_build_impl(wf_ctx *c);
 // wf_pair.cu
 int pair_gradcorr(wf_ctx *c);
+int pair_tir(wf_ctx *c);
+int pair_min_ts(wf_ctx *c, double *test_min);
 int pair_density(wf_ctx *c);
 int pair_rate_stress(wf_ctx *c);
 int pair_accel(wf_ctx *c);
 int pair_thermal(wf_ctx *c);
 int pair_energy(wf_ctx *c);
-int pair_post(wf_ctx *c);
+int pair_post(wf_ctx *c, bool skip_dens = false);
 // wf_comm.cu
 enum HaloSet { HALO_Q1 = 1, HALO_Q0 = 2, HALO_Q2 = 4, HALO_S = 8 };
 int comm_halo_refresh(wf_ctx *c, int sets);             // no-op on one GPU

@@ -394,7 +394,8 @@ int nb_build_impl(wf_ctx *c)
         const int *perm = c->vals[1];
         const int64_t keep = n - n_out;               // emigrants carry the sentinel key: they are the tail and are dropped
         k_permute_q<<<grid_for(keep, B), B, 0, st>>>(keep, perm, c->Q0[a], c->Q1[a], c->Q2[a], c->S0[a], c->S1[a], c->S2[a], c->Q0[b], c->Q1[b], c->Q2[b], c->S0[b], c->S1[b], c->S2[b]); WF_LAUNCH_CHECK(c);
-        dim3 gf(grid_for(keep, B), F_COUNT); k_permute_f<<<gf, B, 0, st>>>(keep, cap, perm, c->F[a], c->F[b]); WF_LAUNCH_CHECK(c);
+        // gradCorrM (the last 9 own fields) lives only with gradKernelCorr
+        dim3 gf(grid_for(keep, B), c->prm.grad_kernel_corr ? F_COUNT : F_GC); k_permute_f<<<gf, B, 0, st>>>(keep, cap, perm, c->F[a], c->F[b]); WF_LAUNCH_CHECK(c);
         dim3 gi(grid_for(keep, B), I_COUNT); k_permute_i<<<gi, B, 0, st>>>(keep, cap, perm, c->I[a], c->I[b], multi ? nullptr : c->slot_of); WF_LAUNCH_CHECK(c);
         c->cur = b; c->launches += 3;
         c->n_loc = keep; c->n = keep; n = keep; }

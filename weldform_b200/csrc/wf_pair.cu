@@ -32,6 +32,7 @@
 // division, cheaper than the generic division sequence. Guarded against the one divisor pattern (all-ones significand)
 // for which the theorem does not hold.
 #include <cstring>
+#include <cub/cub.cuh>
 #include "wf_internal.cuh"
 
 using namespace wf;
@@ -181,6 +182,56 @@ __global__ void __launch_bounds__(128) k_gradcorr(PairArgs a)
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) OWN(F_GC + k) = Mi[k];
+}
+
+// ---- StartAcceleration's tensile-instability tensor (Domain.cpp:1528-1570) as a stand-alone pass: the KickDrift / LeapFrog step
+// orders evaluate the momentum sums first, with the TIR of the stresses and densities the previous step left behind
+__global__ void k_tir(PairArgs a)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    if (a.orig[s] >= a.nsph) return;
+    const double TI = a.cls[a.cls_of[s]].TI;
+    if (!(TI > 0.0) || (a.is_free && !a.is_free[s])) return;
+    S6 sg; sg.xx = OWN(F_SG); sg.yy = OWN(F_SG + 1); sg.zz = OWN(F_SG + 2); sg.xy = OWN(F_SG + 3); sg.yz = OWN(F_SG + 4); sg.xz = OWN(F_SG + 5);
+    double t[6]; tir_of(sg, a.Q2[s].y, TI, t);
+    ((double2 *)&a.S1[s])[1] = make_double2(t[0], t[1]);
+    a.S2[s] = make_double4(t[2], t[3], t[4], t[5]);
+    for (int k = 0; k < 6; ++k) OWN(F_TN + k) = t[k];
+}
+
+// ---- Domain::CheckMinTSVel (Domain.cpp:267-297): min over all particles of CFL * (nearest listed neighbour) / (Cs + |v|);
+// the CFL factor and the comparison with deltatint are applied by the caller
+__global__ void __launch_bounds__(128) k_min_ts(PairArgs a, double cfl, double *partial)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double test = 1.0e300;
+    if (s < a.n) {
+        const double4 qi = a.Q0[s], wi = a.Q1[s];
+        const V3 xi = v3(qi.x, qi.y, qi.z);
+        double mn = 1000.;
+        if (a.orig[s] < a.nsph) {
+            const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
+            for (int n = 0; n < cnt; ++n) {
+                const int j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
+                const double4 qj = a.Q0[j];
+                const double d = norm(v3(qj.x, qj.y, qj.z) - xi);
+                if (d < mn) mn = d;
+            }
+        }
+        test = cfl * mn / (a.cls[a.cls_of[s]].Cs + norm(v3(wi.x, wi.y, wi.z)));
+    }
+    typedef cub::BlockReduce<double, 128> BR; __shared__ typename BR::TempStorage tmp;
+    const double r = BR(tmp).Reduce(test, cub::Min());
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(256) k_min_final(const double *partial, int n, double *out)
+{
+    double v = 1.0e300;
+    for (int b = threadIdx.x; b < n; b += blockDim.x) v = fmin(v, partial[b]);
+    typedef cub::BlockReduce<double, 256> BR; __shared__ typename BR::TempStorage tmp;
+    const double r = BR(tmp).Reduce(v, cub::Min());
+    if (threadIdx.x == 0) out[0] = r;
 }
 
 // ---- step prologue per particle: rho += dt*drho (SolverFraser.cpp:248-252), m/rho, TIR <- the tensor prepared for this step
@@ -749,6 +800,30 @@ int pair_gradcorr(wf_ctx *c)
     c->dens_valid = false;
     return 0;
 }
+// StartAcceleration's TIR, stand-alone (KickDrift / LeapFrog step orders)
+int pair_tir(wf_ctx *c)
+{
+    if (!c->any_ti) return 0;
+    PairArgs a = make_args(c);
+    ProfScope ps(c, PK_BEGIN);
+    k_tir<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    return 0;
+}
+// CheckMinTSVel: this rank's min of CFL*dmin/(Cs+|v|) (blocking read-back)
+int pair_min_ts(wf_ctx *c, double *test_min)
+{
+    WF_PAIR_PRECHECK(c);
+    PairArgs a = make_args(c);
+    const int g = grid_for(c->n_loc, 128);
+    WF_CHECK(ensure_stage(c, (size_t)(g + 8) * sizeof(double)));
+    double *partial = (double *)c->stage;
+    {   ProfScope ps(c, PK_REDUCE);
+        k_min_ts<<<g, 128, 0, c->stream>>>(a, c->prm.cfl, partial + 8); WF_LAUNCH_CHECK(c);
+        k_min_final<<<1, 256, 0, c->stream>>>(partial + 8, g, partial); WF_LAUNCH_CHECK(c); c->launches += 2; }
+    WF_CUDA(c, cudaMemcpyAsync(test_min, partial, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
 // CalcDensInc + DensReduction + rho update. If the previous step's k_post already holds this step's density rate and TIR
 // (nothing moved in between) only the per-particle prologue runs.
 int pair_density(wf_ctx *c)
@@ -798,7 +873,7 @@ int pair_accel(wf_ctx *c)
     return 0;
 }
 // CalcPlasticWorkHeat + ThermalCalcs, then CalcKinEnergyEqn + CalcIntEnergyEqn, then next step's density rate: one walk
-int pair_post(wf_ctx *c)
+int pair_post(wf_ctx *c, bool skip_dens)
 {
     WF_PAIR_PRECHECK(c);
     PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
@@ -807,6 +882,15 @@ int pair_post(wf_ctx *c)
     if (th || c->prm.pl_heating) { k_thermal_pre<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
     WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2));   // x, v, T of the halos after the move / temperature update
     const bool fast = fast_path(c);
+    if (skip_dens) {
+        // the coming step rebuilds its neighbour lists first (known from the cadence): a density rate and TIR summed over the
+        // current lists would be discarded, so only the conduction and energy sums of this step are evaluated
+        if (th) { if (fast) WF_LAUNCH_PF(k_post, true, true, true, false); else WF_LAUNCH_PF(k_post, false, true, true, false); }
+        else    { if (fast) WF_LAUNCH_PF(k_post, true, false, true, false); else WF_LAUNCH_PF(k_post, false, false, true, false); }
+        WF_LAUNCH_CHECK(c); c->launches++;
+        c->dens_valid = false;
+        return 0;
+    }
     if (th && fast && pf && (c->prm.tuning & (64 | 128))) {      // bits 6 / 7 of wf_params::tuning: 5 / 3 resident blocks per SM for the fused pass (A/B measurements)
         if (c->prm.tuning & 64) k_post<true, true, true, true, true, 5><<<g, 128, 0, c->stream>>>(a); else k_post<true, true, true, true, true, 3><<<g, 128, 0, c->stream>>>(a);
     }

@@ -56,6 +56,31 @@ __global__ void k_bc_move(StepArgs a, int mode)
     OWN(F_AX) = ax; OWN(F_AY) = ay; OWN(F_AZ) = az;
 }
 
+// Velocity kicks and the drift of the KickDrift / LeapFrog step orders, every particle (SolverKickDrift.cpp:225-259, SolverLeapfrog.cpp:241-286):
+//   kind 0  v -= a*0.5*dt             (LeapFrog, first step only)      kind 1  v += a*0.5*prev_dt*factor   (KickDrift, factor = 1.)
+//   kind 2  v += a*0.5*(prev_dt+dt)   (LeapFrog)                       kind 3  v += a*dt/2.*factor          (KickDrift)
+//   kind 4  x_prev = x; du = (v + VXSPH)*dt*factor; Displacement += du; x += du   (both; VXSPH == 0, factor == 1.)
+__global__ void k_kick(StepArgs a, int kind, double prev_dt, double dt)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n) return;
+    double4 w = a.Q1[s];
+    if (kind == 4) {
+        double4 q = a.Q0[s];
+        const double dux = (w.x + 0.0) * dt * 1., duy = (w.y + 0.0) * dt * 1., duz = (w.z + 0.0) * dt * 1.;
+        OWN(F_DX) += dux; OWN(F_DY) += duy; OWN(F_DZ) += duz;
+        q.x += dux; q.y += duy; q.z += duz;
+        a.Q0[s] = q;
+        return;
+    }
+    const double ax = OWN(F_AX), ay = OWN(F_AY), az = OWN(F_AZ);
+    if (kind == 0)      { w.x -= ax * 0.5 * dt; w.y -= ay * 0.5 * dt; w.z -= az * 0.5 * dt; }
+    else if (kind == 1) { w.x += ax * 0.5 * prev_dt * 1.; w.y += ay * 0.5 * prev_dt * 1.; w.z += az * 0.5 * prev_dt * 1.; }
+    else if (kind == 2) { const double f = prev_dt + dt; w.x += ax * 0.5 * f; w.y += ay * 0.5 * f; w.z += az * 0.5 * f; }
+    else                { w.x += ax * dt / 2. * 1.; w.y += ay * dt / 2. * 1.; w.z += az * dt / 2. * 1.; }
+    a.Q1[s] = w;
+}
+
 // mesh velocity ramps set from the callback in the oracle driver (trimesh[m]->SetVel)
 __global__ void k_mesh_ramp(double *motion, int n_mesh, const DevScalars *sc)
 {
@@ -179,6 +204,7 @@ __global__ void __launch_bounds__(256) k_reduce_partial(StepArgs a, int first_fe
     double acc[R_NTOT];
     for (int k = 0; k < R_NSUM; ++k) acc[k] = 0.;
     acc[R_MAXPL] = 0.; acc[R_MD0] = acc[R_MD1] = acc[R_MD2] = 0.; acc[R_TMAX] = 0.; acc[R_TMIN] = 1000.;
+#pragma unroll 2
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < a.n; s += (int64_t)gridDim.x * blockDim.x) {
         const int o = OWNI(I_ORIG);
         acc[R_DKIN] += OWN(F_DKIN);
@@ -290,6 +316,7 @@ int contact_impl(wf_ctx *c)
     return 0;
 }
 
+extern "C" int wf_fraser_run(wf_ctx *c, int64_t nsteps);
 static int bc_move(wf_ctx *c, int mode, int pk)
 {
     ProfScope ps(c, pk);
@@ -351,6 +378,7 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_solver_init: no particles");
     if (!(dt > 0.0)) return fail(c, WF_ERR_ARG, "wf_solver_init: dt must be > 0");
     cudaSetDevice(c->device);
+    c->dt_init = c->dt_min = dt;
     c->dt = dt; c->time = 0.0; c->ts_i = 0; c->isfirst = true; c->isyielding = false; c->steps = 0; c->dens_valid = false; c->in_step = false;
     k_set_time<<<1, 1, 0, c->stream>>>(c->d_sc, 0.0, dt); WF_LAUNCH_CHECK(c);
     StepArgs a = make_step_args(c);
@@ -396,10 +424,14 @@ extern "C" int wf_reduce(wf_ctx *c, wf_scalars *out)
     out->time = d.time; out->max_pl_strain = d.max_pl_strain;
     // Domain::max_disp as the reference holds it at this point: computed at the start of the step in flight / last completed
     for (int k = 0; k < 3; ++k) out->max_disp[k] = std::sqrt((c->in_step || c->steps == 0) ? d.max_disp2[k] : d.max_disp2_prev[k]);      // SolverFraser.cpp:159
+    // the KickDrift / LeapFrog loops keep max_disp in a local that shadows Domain::max_disp (SolverKickDrift.cpp:122, SolverLeapfrog.cpp:138):
+    // the member a driver reads is never written by them
+    if (c->prm.solver != 0) for (int k = 0; k < 3; ++k) out->max_disp[k] = 0.0;
     out->kin_energy_sum = d.kin_energy_sum; out->int_energy_sum = d.int_energy_sum; out->plastic_work = d.plastic_work;
     out->contact_force_sum = d.contact_force_sum; out->contact_reaction_sum = d.contact_reaction_sum; out->ext_forces_work = d.ext_forces_work;
     out->contact_friction_work = d.contact_friction_work; out->accum_cont_heat_cond = d.accum_cont_heat_cond;
     out->max_T = d.max_T; out->min_T = d.min_T; out->steps = c->steps; out->nb_rebuilds = c->nb_rebuilds; out->is_yielding = c->isyielding ? 1 : 0;
+    out->deltat = c->dt;
     return 0;
 }
 
@@ -424,7 +456,9 @@ static int nb_policy(wf_ctx *c)
     if (mx > MIN_PS_FOR_NBSEARCH || c->isfirst || check_every) {
         if (c->ts_i == 0 && c->nb_cleared) {
             WF_CHECK(nb_build_impl(c));
-            WF_CHECK(pair_gradcorr(c));        // SolverFraser.cpp:203-204: at the cadence rebuilds only, not at the first-yield search above
+            // SolverFraser.cpp:203-204, SolverLeapfrog.cpp:196-197: at the cadence rebuilds only, not at the first-yield search above;
+            // the KickDrift loop computes the matrices once, at the first step (SolverKickDrift.cpp:187-190)
+            if (c->prm.solver != 1 || c->isfirst) WF_CHECK(pair_gradcorr(c));
         }
     }
     return 0;
@@ -464,8 +498,102 @@ extern "C" int wf_fraser_stage_b2(wf_ctx *c) { WF_NEED_READY(c); return move_vel
 extern "C" int wf_fraser_stage_c(wf_ctx *c)
 {
     WF_NEED_READY(c);
-    WF_CHECK(pair_post(c));            // CalcPlasticWorkHeat + ThermalCalcs + CalcKinEnergyEqn + CalcIntEnergyEqn (+ next density rate)
+    // CalcPlasticWorkHeat + ThermalCalcs + CalcKinEnergyEqn + CalcIntEnergyEqn (+ next density rate, unless the cadence
+    // (finish_step / nb_policy) says the next step starts with a neighbour rebuild, which would invalidate it)
+    const bool next_rebuilds = c->step_max_pl > 1.e-6 && c->ts_i == (c->prm.ts_nb_inc - 1);
+    WF_CHECK(pair_post(c, next_rebuilds));
     return finish_step(c);
+}
+
+// Domain::AdaptiveTimeStep (Domain.cpp:205-239), host scalars; auto_ts_cont is off in every driver and not modelled
+static void adaptive_time_step(wf_ctx *c)
+{
+    const double manual_min_ts = 1.e-10;       // Domain.cpp:170
+    double &deltat = c->dt; const double deltatint = c->dt_init, deltatmin = c->dt_min;
+    if (deltatint > deltatmin) {
+        if (deltat < deltatmin) deltat = 2.0 * deltat * deltatmin / (deltat + deltatmin);
+        else deltat = deltatmin;
+    } else {
+        if (deltatint != deltat) deltat = 2.0 * deltat * deltatint / (deltat + deltatint);
+        else deltat = deltatint;
+    }
+    if (deltat < manual_min_ts) deltat = manual_min_ts;
+}
+
+static int kick(wf_ctx *c, int kind, double prev_dt)
+{
+    ProfScope ps(c, PK_MOVE);
+    StepArgs a = make_step_args(c);
+    k_kick<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a, kind, prev_dt, c->dt); WF_LAUNCH_CHECK(c); c->launches++;
+    c->dens_valid = false;
+    return 0;
+}
+
+// One step of SolveDiffUpdateKickDrift (SolverKickDrift.cpp:98-335) or SolveDiffUpdateLeapFrog (SolverLeapfrog.cpp:124-443) with the
+// device-side GeneralAfter: same kernels as the Fraser step in the order those loops run them; momentum first (with the TIR of the
+// state the previous step left), density after the first kick, rate tensors and stresses after the drift.
+static int kdlf_step(wf_ctx *c)
+{
+    const int solver = c->prm.solver;
+    WF_CHECK(nb_policy(c));
+    WF_CHECK(pair_tir(c));                                       // StartAcceleration
+    WF_CHECK(comm_halo_refresh(c, HALO_Q2 | HALO_S));
+    WF_CHECK(pair_accel(c));
+    WF_CHECK(apply_bcs_impl(c));                                 // GeneralAfter: fix free accel
+    WF_CHECK(contact_impl(c));
+    if (solver == 2) {
+        if (c->isfirst) WF_CHECK(kick(c, 0, c->dt));
+        WF_CHECK(apply_bcs_impl(c));
+    }
+    const double prev_dt = c->dt;
+    if (c->prm.auto_ts) {
+        double t = 0.0;
+        WF_CHECK(pair_min_ts(c, &t));
+        if (c->comm.nranks > 1) {                                // min over the ranks
+            WF_CUDA(c, cudaMemcpyAsync(c->comm.d_rank, &t, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            WF_CHECK(comm_gather_scalars(c, 1));
+            std::vector<double> all(c->comm.nranks);
+            WF_CUDA(c, cudaMemcpyAsync(all.data(), c->comm.d_all, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            WF_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (double v : all) if (v < t) t = v;
+        }
+        c->dt_min = c->dt_init;                                  // CheckMinTSVel: deltatmin = deltatint; if (deltatmin > test) deltatmin = test
+        if (c->dt_min > t) c->dt_min = t;
+        adaptive_time_step(c);
+    }
+    WF_CHECK(kick(c, solver == 1 ? 1 : 2, prev_dt));
+    WF_CHECK(apply_bcs_impl(c));
+    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));
+    c->dens_valid = false;
+    WF_CHECK(pair_density(c));                                   // CalcDensInc + DensReduction, rho += dt*drho
+    WF_CHECK(kick(c, 4, prev_dt));                               // drift
+    if (solver == 1) { WF_CHECK(kick(c, 3, prev_dt)); WF_CHECK(apply_bcs_impl(c)); }
+    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));
+    WF_CHECK(pair_rate_stress(c));
+    WF_CHECK(pair_post(c, true));                                // CalcPlasticWorkHeat, ThermalCalcs, energies (no density hand-over in this step order)
+    c->dens_valid = false;                                       // the next density pass runs after a kick: nothing to hand over
+    return finish_step(c);
+}
+
+static int one_step(wf_ctx *c)
+{
+    if (c->prm.solver != 0) return kdlf_step(c);
+    return wf_fraser_run(c, 1);
+}
+extern "C" int wf_run(wf_ctx *c, int64_t nsteps)
+{
+    WF_NEED_READY(c);
+    if (c->prm.solver == 0) return wf_fraser_run(c, nsteps);
+    for (int64_t k = 0; k < nsteps; ++k) WF_CHECK(kdlf_step(c));
+    return 0;
+}
+extern "C" int wf_run_until(wf_ctx *c, double tf, int64_t *steps_done)
+{
+    WF_NEED_READY(c);
+    int64_t n = 0;
+    while (c->time <= tf) { WF_CHECK(one_step(c)); ++n; }        // while (Time <= tf), SolverFraser.cpp:133
+    if (steps_done) *steps_done = n;
+    return 0;
 }
 
 // nsteps whole steps with the device-side boundary conditions at both GeneralAfter points; no host callback.

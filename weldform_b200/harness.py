@@ -78,6 +78,7 @@ def context_from_case(case, device=0, comm=None):
     p.cont_heat_fric = int(case.get("cont_heat_fric", 0)); p.cont_heat_cond = int(case.get("cont_heat_cond", 0))
     p.tuning = int(case.get("tuning", int(__import__("os").environ.get("WF_TUNING", "0"))))
     p.grad_kernel_corr = int(case.get("gradKernelCorr", 0))
+    p.solver = int(case.get("solver", 0)); p.auto_ts = int(case.get("auto_ts", 0)); p.cfl = float(case.get("CFL", 0.7))
     ctx.set_params(p)
     if "materials" in case:
         mt = np.asarray(case["materials"], float).reshape(-1, 16)
@@ -171,7 +172,7 @@ def dump(ctx, info, with_pairs=True):
     if ctx.grad_kernel_corr:
         out["gradCorrM"] = ctx.download("gradCorrM").reshape(-1)
     s = ctx.reduce()
-    out.update(n_particles=np.array([float(ctx.n)]), solid_part_count=np.array([float(ctx.n_sph)]), Time=np.array([s.time]),
+    out.update(n_particles=np.array([float(ctx.n)]), solid_part_count=np.array([float(ctx.n_sph)]), Time=np.array([s.time]), deltat=np.array([s.deltat]),
                kin_energy_sum=np.array([s.kin_energy_sum]), int_energy_sum=np.array([s.int_energy_sum]), plastic_work=np.array([s.plastic_work]),
                contact_force_sum=np.array([s.contact_force_sum]), contact_reaction_sum=np.array([s.contact_reaction_sum]),
                ext_forces_work=np.array([s.ext_forces_work]), contact_friction_work=np.array([s.contact_friction_work]),
@@ -217,6 +218,8 @@ def run_case(case, device=0, with_pairs=True, comm=None):
         ctx.solver_init(float(case.get("dt", 1.0e-7)))
         if int(case.get("mode", 0)) == 1:
             ctx.nb_build()
+        elif float(case.get("tf", 0.0)) > 0.0:
+            ctx.run_until(float(case["tf"]))               # while (Time <= tf): the stop rule of the reference's loops (adaptive time step)
         else:
             ctx.run(int(case.get("nsteps", 1)))
         return dump(ctx, info, with_pairs)

@@ -4,12 +4,14 @@
 // a cylinder with AddCylinderLength, assign per-particle material fields, install a GeneralAfter callback that drives
 // the top rows and holds the bottom rows, call SolveDiffUpdateFraser. Everything under Solve runs on the GPU.
 //
-//   usage: compression_host_api <dx> <nsteps> <perturb_amp> <out.bin>
+//   usage: compression_host_api <dx> <nsteps> <perturb_amp> <out.bin> [solver: 0 Fraser (default), 1 KickDrift, 2 LeapFrog]
 // out.bin: int64 n, then n*(x[3], v[3], Displacement[3], pl_strain, T, Density, Sigma[9]) as float64 (creation order).
 #include <cstdio>
 #include "Domain.h"
 #include "InteractionAlt.cpp"
 #include "SolverFraser.cpp"
+#include "SolverKickDrift.cpp"
+#include "SolverLeapfrog.cpp"
 
 #define TAU  0.005
 #define VMAX 10.0
@@ -49,7 +51,10 @@ int main(int argc, char ** argv) try
     dom.BC.InOutFlow = 0;
     dom.thermal_solver = true; dom.pl_heating = true; dom.pl_work_heat_frac = 0.9; dom.auto_ts = false;
     const double timestep = 0.2 * h / Cs;
-    dom.SolveDiffUpdateFraser((nsteps - 0.5) * timestep, timestep, 1.e30, NULL, 1000000);
+    const int solver = argc > 5 ? std::atoi(argv[5]) : 0;
+    if (solver == 1) dom.SolveDiffUpdateKickDrift((nsteps - 0.5) * timestep, timestep, 1.e30, NULL, 1000000);
+    else if (solver == 2) dom.SolveDiffUpdateLeapFrog((nsteps - 0.5) * timestep, timestep, 1.e30, NULL, 1000000);
+    else dom.SolveDiffUpdateFraser((nsteps - 0.5) * timestep, timestep, 1.e30, NULL, 1000000);
     FILE * fp = std::fopen(argv[4], "wb");
     const long long n = (long long)dom.Particles.Size();
     std::fwrite(&n, sizeof(n), 1, fp);

@@ -181,6 +181,10 @@ int wf_fraser_run(wf_ctx *ctx, int64_t nsteps);     /* nsteps full steps with de
  * wf_run: nsteps steps. wf_run_until: while (Time <= tf) as the reference's loops do (the only stop rule that makes sense
  * with auto_ts); *steps_done receives the number of steps taken. */
 int wf_run(wf_ctx *ctx, int64_t nsteps);
+/* One KickDrift / LeapFrog step in five stages split at the reference loops' GeneralAfter calls (host-callback bridge): 0 rebuild
+ * policy + TIR + CalcAccel | 1 contact (+ LeapFrog's first-step half kick) | 2 adaptive time step + velocity kick | 3 density + drift
+ * (+ KickDrift's second half kick) | 4 rate tensors + stresses + heat + energies + end of step. No device-side BCs are applied. */
+int wf_solver_stage(wf_ctx *ctx, int stage);
 int wf_run_until(wf_ctx *ctx, double tf, int64_t *steps_done);
 
 /* ---- host-side lattice generators (Domain::AddCylinderLength / AddBoxLength, Domain.cpp:708,326); 3-D, cubic packing.

@@ -51,7 +51,7 @@ def test_unsupported_solvers_fail_loudly(product_lib):
 #include "Domain.h"
 int main() { SPH::Domain d; int hits = 0;
   try { d.Solve(1, 1, 1, "x", 1); } catch (Fatal * f) { ++hits; delete f; }
-  try { d.SolveDiffUpdateKickDrift(1, 1, 1, "x", 1); } catch (Fatal * f) { ++hits; delete f; }
+  try { d.SolveDiffUpdateVerlet(1, 1, 1, "x", 1); } catch (Fatal * f) { ++hits; delete f; }
   try { d.AddCylinderLength(1, Vec3_t(0, 0, 0), 0.1, 0.1, 0.01, 1000., 0.012, false, true); } catch (Fatal * f) { ++hits; delete f; }
   d.AddCylinderLength(1, Vec3_t(0, 0, 0), 0.1, 0.1, 0.01, 1000., 0.012, false);
   return (hits == 3 && d.Particles.Size() > 100 && d.solid_part_count == (int)d.Particles.Size()) ? 0 : 1; }
@@ -73,16 +73,19 @@ def _read_bin(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sync", ["full", "tagged"])
-def test_host_domain_driver_matches_device_run_and_oracle(host_example, oracle_port, sync):
+@pytest.mark.parametrize("sync,solver", [("full", 0), ("tagged", 0), ("tagged", 1), ("tagged", 2)])
+def test_host_domain_driver_matches_device_run_and_oracle(host_example, oracle_port, sync, solver):
+    """The C++ driver (host GeneralAfter callback between the stages of SolveDiffUpdateFraser / KickDrift / LeapFrog) against the
+    device-BC run of the same case and against the oracle."""
     from weldform_b200 import harness
     dx, nsteps, amp = 0.03, 40, 60.0
     with tempfile.TemporaryDirectory() as d:
         out = os.path.join(d, "o.bin")
-        r = subprocess.run([host_example, str(dx), str(nsteps), str(amp), out], capture_output=True, text=True, timeout=600, env=dict(os.environ, WELDFORM_SYNC=sync))
+        r = subprocess.run([host_example, str(dx), str(nsteps), str(amp), out, str(solver)], capture_output=True, text=True, timeout=600, env=dict(os.environ, WELDFORM_SYNC=sync))
         assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
         got = _read_bin(out)
     case = cases.perturbed(cases.compression(dx=dx, nsteps=nsteps), amp=amp)
+    case["solver"] = float(solver)
     dev = harness.run_case(case, with_pairs=False)
     for k in got:
         assert np.array_equal(got[k], dev[k]), "host-callback run differs from the device-BC run in %s (%.3e)" % (k, ot.max_rel(got[k], dev[k]))

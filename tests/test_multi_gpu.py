@@ -149,3 +149,28 @@ def test_multi_gpu_contact_bit_identical_to_single(product_lib, oracle_port):
     ref = ot.run_port(case)
     worst = {k: ot.max_rel(multi[k], ref[k]) for k in ("x", "v", "Displacement", "pl_strain", "Density", "Sigma", "contforce", "delta_cont")}
     assert max(worst.values()) < 1e-6, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("solver,auto_ts", [(1, 1), (2, 0)])
+def test_multi_gpu_kickdrift_leapfrog_bit_identical_to_single(product_lib, oracle_port, solver, auto_ts):
+    """KickDrift / LeapFrog step orders on the slab decomposition (their own halo refresh points; the adaptive time step takes
+    the minimum over the ranks)."""
+    from weldform_b200 import harness
+    case = cases.perturbed(cases.compression(dx=0.02, nsteps=60), amp=200.0)
+    case["solver"] = float(solver)
+    if auto_ts:
+        case.update(auto_ts=1.0, CFL=0.15, tf=50 * case["dt"])
+    multi, info = _run_multi(case, 2)
+    single = harness.run_case(case)
+    assert np.array_equal(multi["pairs"], single["pairs"])
+    bad = {k: ot.max_rel(multi[k], single[k]) for k in cases.FIELDS_F64 + ["ID", "Nb"] if not np.array_equal(multi[k], single[k])}
+    assert not bad, "multi-GPU differs from single GPU per particle: %s" % bad
+    for k in ("Time", "deltat"):
+        assert np.array_equal(multi[k], single[k]), k
+    if auto_ts:
+        assert float(single["deltat"][0]) < 0.9 * case["dt"]
+    ref = ot.run_port(case)
+    worst = {k: ot.max_rel(multi[k], ref[k]) for k in ("x", "v", "Displacement", "pl_strain", "T", "Density", "Sigma")}
+    assert max(worst.values()) < 1e-6, worst

@@ -93,7 +93,7 @@ def load_library():
         "wf_nb_export_pairs": ([vp, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)], C.c_int),
         "wf_cont_export_pairs": ([vp, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)], C.c_int),
         "wf_reduce": ([vp, C.POINTER(wf_scalars)], C.c_int), "wf_fraser_run": ([vp, C.c_int64], C.c_int),
-        "wf_run": ([vp, C.c_int64], C.c_int), "wf_run_until": ([vp, C.c_double, C.POINTER(C.c_int64)], C.c_int),
+        "wf_run": ([vp, C.c_int64], C.c_int), "wf_solver_stage": ([vp, C.c_int], C.c_int), "wf_run_until": ([vp, C.c_double, C.POINTER(C.c_int64)], C.c_int),
         "wf_gen_cylinder": ([_PD, C.c_double, C.c_double, C.c_double, _PD, C.c_int64], C.c_int64),
         "wf_gen_box": ([_PD, C.c_double, C.c_double, C.c_double, C.c_double, _PD, C.c_int64, _PD], C.c_int64),
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
@@ -323,6 +323,9 @@ class Context:
     def run(self, nsteps):
         """nsteps whole steps of the configured solver (wf_params::solver), device-side BCs"""
         self._ck(self.L.wf_run(self.h, nsteps), "wf_run")
+
+    def solver_stage(self, stage):
+        self._ck(self.L.wf_solver_stage(self.h, int(stage)), "wf_solver_stage")
 
     def run_until(self, tf):
         """while (Time <= tf) step; returns the number of steps taken"""

@@ -126,6 +126,7 @@ struct wf_ctx {
     wf::DevScalars *d_sc = nullptr; wf::DevScalars *h_sc = nullptr;   // h_sc pinned
     double *d_partial = nullptr; int partial_blocks = 0;
     // solver state (SolverFraser.cpp:62-68)
+    double prev_dt = 0.0;                        // deltat of the previous step (the kicks of the KickDrift / LeapFrog orders use both)
     double dt_init = 0.0, dt_min = 0.0;          // Domain::deltatint / deltatmin (adaptive time step, Domain.cpp:205-297)
     double dt = 0.0, time = 0.0; int ts_i = 0; bool isfirst = true, isyielding = false, nb_cleared = true;
     int64_t steps = 0, nb_rebuilds = 0, launches = 0; bool in_step = false;

@@ -529,50 +529,80 @@ static int kick(wf_ctx *c, int kind, double prev_dt)
     return 0;
 }
 
-// One step of SolveDiffUpdateKickDrift (SolverKickDrift.cpp:98-335) or SolveDiffUpdateLeapFrog (SolverLeapfrog.cpp:124-443) with the
-// device-side GeneralAfter: same kernels as the Fraser step in the order those loops run them; momentum first (with the TIR of the
-// state the previous step left), density after the first kick, rate tensors and stresses after the drift.
-static int kdlf_step(wf_ctx *c)
+// One step of SolveDiffUpdateKickDrift (SolverKickDrift.cpp:98-335) or SolveDiffUpdateLeapFrog (SolverLeapfrog.cpp:124-443), in five
+// stages split at the loops' GeneralAfter calls: same kernels as the Fraser step in the order those loops run them -- momentum
+// first (with the TIR of the state the previous step left), density after the first kick, rate tensors and stresses after the drift.
+//   0  rebuild policy, StartAcceleration (TIR), CalcAccel                       [GeneralAfter]
+//   1  contact; LeapFrog, first step: v -= a*dt/2                               [GeneralAfter, LeapFrog only]
+//   2  CheckMinTSVel + AdaptiveTimeStep, velocity kick                          [GeneralAfter]
+//   3  density, drift; KickDrift: second half kick                              [GeneralAfter, KickDrift only]
+//   4  rate tensors + stresses, heat, energies, end of step
+// device_bcs: apply the device-side GeneralAfter at those points (wf_run); the host mirror calls the driver's callback instead.
+static int kdlf_stage(wf_ctx *c, int stage, bool device_bcs)
 {
     const int solver = c->prm.solver;
-    WF_CHECK(nb_policy(c));
-    WF_CHECK(pair_tir(c));                                       // StartAcceleration
-    WF_CHECK(comm_halo_refresh(c, HALO_Q2 | HALO_S));
-    WF_CHECK(pair_accel(c));
-    WF_CHECK(apply_bcs_impl(c));                                 // GeneralAfter: fix free accel
-    WF_CHECK(contact_impl(c));
-    if (solver == 2) {
-        if (c->isfirst) WF_CHECK(kick(c, 0, c->dt));
-        WF_CHECK(apply_bcs_impl(c));
-    }
-    const double prev_dt = c->dt;
-    if (c->prm.auto_ts) {
-        double t = 0.0;
-        WF_CHECK(pair_min_ts(c, &t));
-        if (c->comm.nranks > 1) {                                // min over the ranks
-            WF_CUDA(c, cudaMemcpyAsync(c->comm.d_rank, &t, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            WF_CHECK(comm_gather_scalars(c, 1));
-            std::vector<double> all(c->comm.nranks);
-            WF_CUDA(c, cudaMemcpyAsync(all.data(), c->comm.d_all, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            WF_CUDA(c, cudaStreamSynchronize(c->stream));
-            for (double v : all) if (v < t) t = v;
+    switch (stage) {
+    case 0:
+        WF_CHECK(nb_policy(c));
+        WF_CHECK(pair_tir(c));
+        WF_CHECK(comm_halo_refresh(c, HALO_Q2 | HALO_S));
+        WF_CHECK(pair_accel(c));
+        if (device_bcs) WF_CHECK(apply_bcs_impl(c));
+        return 0;
+    case 1:
+        WF_CHECK(contact_impl(c));
+        if (solver == 2) {
+            if (c->isfirst) WF_CHECK(kick(c, 0, c->dt));
+            if (device_bcs) WF_CHECK(apply_bcs_impl(c));
         }
-        c->dt_min = c->dt_init;                                  // CheckMinTSVel: deltatmin = deltatint; if (deltatmin > test) deltatmin = test
-        if (c->dt_min > t) c->dt_min = t;
-        adaptive_time_step(c);
+        return 0;
+    case 2:
+        c->prev_dt = c->dt;
+        if (c->prm.auto_ts) {
+            double t = 0.0;
+            WF_CHECK(pair_min_ts(c, &t));
+            if (c->comm.nranks > 1) {                                // min over the ranks
+                WF_CUDA(c, cudaMemcpyAsync(c->comm.d_rank, &t, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+                WF_CHECK(comm_gather_scalars(c, 1));
+                std::vector<double> all(c->comm.nranks);
+                WF_CUDA(c, cudaMemcpyAsync(all.data(), c->comm.d_all, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                WF_CUDA(c, cudaStreamSynchronize(c->stream));
+                for (double v : all) if (v < t) t = v;
+            }
+            c->dt_min = c->dt_init;                                  // CheckMinTSVel: deltatmin = deltatint; if (deltatmin > test) deltatmin = test
+            if (c->dt_min > t) c->dt_min = t;
+            adaptive_time_step(c);
+        }
+        WF_CHECK(kick(c, solver == 1 ? 1 : 2, c->prev_dt));
+        if (device_bcs) WF_CHECK(apply_bcs_impl(c));
+        return 0;
+    case 3:
+        WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));
+        c->dens_valid = false;
+        WF_CHECK(pair_density(c));                                   // CalcDensInc + DensReduction, rho += dt*drho
+        WF_CHECK(kick(c, 4, c->prev_dt));                            // drift
+        if (solver == 1) { WF_CHECK(kick(c, 3, c->prev_dt)); if (device_bcs) WF_CHECK(apply_bcs_impl(c)); }
+        return 0;
+    case 4:
+        WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));
+        WF_CHECK(pair_rate_stress(c));
+        WF_CHECK(pair_post(c, true));                                // CalcPlasticWorkHeat, ThermalCalcs, energies (no density hand-over in this step order)
+        c->dens_valid = false;
+        return finish_step(c);
+    default:
+        return fail(c, WF_ERR_ARG, "wf_solver_stage: stage %d (0..4)", stage);
     }
-    WF_CHECK(kick(c, solver == 1 ? 1 : 2, prev_dt));
-    WF_CHECK(apply_bcs_impl(c));
-    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));
-    c->dens_valid = false;
-    WF_CHECK(pair_density(c));                                   // CalcDensInc + DensReduction, rho += dt*drho
-    WF_CHECK(kick(c, 4, prev_dt));                               // drift
-    if (solver == 1) { WF_CHECK(kick(c, 3, prev_dt)); WF_CHECK(apply_bcs_impl(c)); }
-    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));
-    WF_CHECK(pair_rate_stress(c));
-    WF_CHECK(pair_post(c, true));                                // CalcPlasticWorkHeat, ThermalCalcs, energies (no density hand-over in this step order)
-    c->dens_valid = false;                                       // the next density pass runs after a kick: nothing to hand over
-    return finish_step(c);
+}
+static int kdlf_step(wf_ctx *c)
+{
+    for (int st = 0; st < 5; ++st) WF_CHECK(kdlf_stage(c, st, true));
+    return 0;
+}
+extern "C" int wf_solver_stage(wf_ctx *c, int stage)
+{
+    WF_NEED_READY(c);
+    if (c->prm.solver == 0) return fail(c, WF_ERR_ARG, "wf_solver_stage: the Fraser step has its own stages (wf_fraser_stage_a/b1/b2/c)");
+    return kdlf_stage(c, stage, false);
 }
 
 static int one_step(wf_ctx *c)

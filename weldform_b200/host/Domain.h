@@ -77,9 +77,12 @@ public:
 
     // ---- solvers (Source/Domain.h:197-210). Only the Fraser loop -- the one all shipped configurations use -- is implemented.
     void SolveDiffUpdateFraser(double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx);
-    void SolveDiffUpdateKickDrift(double, double, double, char const *, size_t) { not_implemented("SolveDiffUpdateKickDrift"); }
-    void SolveDiffUpdateLeapFrog(double, double, double, char const *, size_t) { not_implemented("SolveDiffUpdateLeapFrog"); }
+    void SolveDiffUpdateKickDrift(double tf, double dt, double dtOut, char const * k, size_t m) { solve_kick_drift_leap_frog(1, tf, dt, dtOut, k, m); }
+    void SolveDiffUpdateLeapFrog(double tf, double dt, double dtOut, char const * k, size_t m) { solve_kick_drift_leap_frog(2, tf, dt, dtOut, k, m); }
+    void solve_kick_drift_leap_frog(int solver, double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx);
     void SolveDiffUpdateLeapfrog(double tf, double dt, double dtOut, char const * k, size_t m) { SolveDiffUpdateLeapFrog(tf, dt, dtOut, k, m); }
+    // the reference's Verlet loop calls its reductions under `#ifdef NONLOCK_SUM`, a macro nothing defines (SolverVerlet.cpp:176-178,
+    // 206-208): with the default nonlock_sum = true no pair sum ever reaches the particles there. Not restated.
     void SolveDiffUpdateVerlet(double, double, double, char const *, size_t) { not_implemented("SolveDiffUpdateVerlet"); }
     void ThermalSolve(double, double, double, char const *, size_t) { not_implemented("ThermalSolve"); }
     void ThermalStructSolve(double, double, double, char const *, size_t) { not_implemented("ThermalStructSolve"); }
@@ -94,8 +97,8 @@ public:
     int Dimension = 3;
     size_t Nproc = 1;                          // host threads of the reference; unused (the step runs on the GPU)
     size_t Scheme = 0;
-    double CFL = 0.4, XSPH = 0.0, deltat = 0.0, deltatmin = 0.0, Alpha = 0.0, Beta = 0.0;
-    bool auto_ts = false, auto_ts_acc = false;
+    double CFL = 0.7, XSPH = 0.0, deltat = 0.0, deltatmin = 0.0, Alpha = 0.0, Beta = 0.0;
+    bool auto_ts = false, auto_ts_acc = false; int solver_kind = 0;
     int ts_nb_inc = 5;
     Vec3_t DomMax, DomMin, Gravity;
     PtDom GeneralBefore = nullptr, GeneralAfter = nullptr;
@@ -250,6 +253,7 @@ inline void Domain::backend_begin(double dt)
     p.thermal_solver = thermal_solver; p.pl_heating = pl_heating; p.pl_work_heat_frac = pl_work_heat_frac;
     p.contact = contact; p.friction_sta = friction_sta; p.friction_dyn = friction_dyn; p.pfac = PFAC; p.dfac = DFAC;
     p.cont_heat_fric = cont_heat_fric; p.cont_heat_cond = cont_heat_cond; p.contact_hc = contact_hc;
+    p.solver = solver_kind; p.auto_ts = (solver_kind != 0 && auto_ts) ? 1 : 0; p.cfl = CFL;   // auto_ts is dead code in the Fraser loop (SolverFraser.cpp:500-502)
     p.grad_kernel_corr = gradKernelCorr ? 1 : 0;     // CalcGradCorrMatrix + the locking summation the reference switches to (SolverFraser.cpp:112-115)
     if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
     if (friction_function != Constant && contact) throw new Fatal("Domain::friction_function != Constant is not implemented in weldform_b200");
@@ -390,10 +394,49 @@ inline void Domain::run_callback(PtDom cb)
     forward_mesh_motion();
 }
 
+// Source/SolverKickDrift.cpp:21-400 / Source/SolverLeapfrog.cpp:24-450: the loops' control flow with the GeneralAfter calls at the
+// reference's points; every stage is a C-ABI call (wf_solver_stage) into the CUDA library
+inline void Domain::solve_kick_drift_leap_frog(int solver, double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx)
+{
+    std::cout << "\n--------------Solving (weldform_b200, " << (solver == 1 ? "SolveDiffUpdateKickDrift" : "SolveDiffUpdateLeapFrog") << " on the GPU)----------------------------" << std::endl;
+    if (auto_ts_acc) throw new Fatal("Domain::auto_ts_acc (CheckMinTSAccel) is not implemented in weldform_b200");
+    solver_kind = solver;
+    deltat = dt; deltatmin = dt;
+    backend_begin(dt);
+    size_t idx_out = 1; double tout = Time;
+    auto t0 = std::chrono::steady_clock::now();
+    refresh_scalars();
+    while (Time <= tf && idx_out <= maxidx) {
+        if (GeneralBefore) run_callback(GeneralBefore);
+        ck(wf_solver_stage(backend, 0), "wf_solver_stage 0");
+        if (GeneralAfter) { refresh_scalars(); run_callback(GeneralAfter); }     // fix free accel
+        ck(wf_solver_stage(backend, 1), "wf_solver_stage 1");
+        if (GeneralAfter && solver == 2) run_callback(GeneralAfter);            // SolverLeapfrog.cpp:254
+        ck(wf_solver_stage(backend, 2), "wf_solver_stage 2");
+        if (GeneralAfter) run_callback(GeneralAfter);                            // reinforce BC vel
+        ck(wf_solver_stage(backend, 3), "wf_solver_stage 3");
+        if (GeneralAfter && solver == 1) run_callback(GeneralAfter);            // SolverKickDrift.cpp:260
+        ck(wf_solver_stage(backend, 4), "wf_solver_stage 4");
+        refresh_scalars();
+        { wf_scalars s; ck(wf_reduce(backend, &s), "wf_reduce"); deltat = s.deltat; }
+        if (Time >= tout) {
+            if (TheFileKey != NULL) { String fn; fn.Printf("%s_%04d", TheFileKey, (int)idx_out); sync_down(true); WriteCSV(fn.CStr()); }
+            idx_out++; tout += dtOut;
+            std::cout << "Output No. " << idx_out << " at " << Time << " has been generated\nCurrent Time Step = " << deltat << "\n";
+        }
+    }
+    ck(wf_sync(backend), "wf_sync");
+    wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    sync_down(true);
+    for (int k = 0; k < 3; ++k) max_disp(k) = 0.0;       // those loops shadow Domain::max_disp with a local (SolverKickDrift.cpp:122)
+    std::cout << "\n--------------Solving is finished: " << steps << " steps, " << wall_seconds << " s" << std::endl;
+}
+
 // Source/SolverFraser.cpp:21-513: the loop's control flow; every phase is a C-ABI call into the CUDA library
 inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx)
 {
     std::cout << "\n--------------Solving (weldform_b200, SolveDiffUpdateFraser on the GPU)----------------------------" << std::endl;
+    solver_kind = 0;
     deltat = dt; deltatmin = dt;
     backend_begin(dt);
     size_t idx_out = 1; double tout = Time; double max_pl = 0.0;

@@ -45,6 +45,8 @@ typedef struct wf_params {
     double pl_work_heat_frac;  /* Domain::pl_work_heat_frac */
     int    contact;            /* Domain::contact (Wang algorithm, Contact_Wang.cpp) */
     double friction_sta, friction_dyn;
+    int    friction_function;  /* Domain::friction_function: 0 Constant, 1 Linear: mu = friction_m*T + friction_b (Contact_Wang.cpp:243-244) */
+    double friction_m, friction_b;
     double pfac, dfac;         /* Domain::PFAC / DFAC */
     double contact_force_factor;
     int    cont_heat_fric, cont_heat_cond;

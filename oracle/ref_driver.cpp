@@ -194,11 +194,14 @@ int main(int argc, char ** argv) try
         std::snprintf(key, 64, "mesh%d_vel", m);
         if (in.has(key)) { const std::vector<double> & a_ = in.f(key); mv.v[0] = a_[0]; mv.v[1] = a_[1]; mv.v[2] = a_[2]; mv.tau = a_[3]; }
         g_meshvel.push_back(mv);
+        std::snprintf(key, 64, "mesh%d_w", m);
+        if (in.has(key)) { const std::vector<double> & w_ = in.f(key); tm->SetRotAxisVel(Vec3_t(w_[0], w_[1], w_[2])); }
     }
     for (size_t i = nsph; i < dom.Particles.Size(); ++i) zero_uninitialised(dom.Particles[i]);
     dom.contact = in.scalar("contact", mesh_count > 0 ? 1 : 0) != 0.0;
     dom.friction_sta = in.scalar("friction_sta", 0.0);
     dom.friction_dyn = in.scalar("friction_dyn", 0.0);
+    if ((int)in.scalar("friction_function", 0) == 1) { dom.friction_function = Linear; dom.friction_m = in.scalar("friction_m", 0.0); dom.friction_b = in.scalar("friction_b", 0.0); }
     dom.PFAC = in.scalar("PFAC", 0.4);
     dom.DFAC = in.scalar("DFAC", 0.0);
     dom.cont_heat_fric = in.scalar("cont_heat_fric", 0) != 0.0;

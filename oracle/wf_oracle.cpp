@@ -290,6 +290,7 @@ struct Dom {
     bool auto_ts = false; double CFL = 0.7, deltatint = 0.0, deltatmin = 0.0, manual_min_ts = 1.e-10;   // Domain.cpp:126,153,170
     long steps_done = 0;
     bool gradKernelCorr = false;             // Domain::gradKernelCorr: Bonet-Lok corrected gradient; the Fraser solver then sums with locks, in pair order (SolverFraser.cpp:112-115)
+    int friction_function = 0; double friction_m = 0.0, friction_b = 0.0;   // Domain::friction_function (0 Constant, 1 Linear in T), Contact_Wang.cpp:243-244
     double pl_work_heat_frac = 0.9, friction_sta = 0.0, friction_dyn = 0.0, PFAC = 0.4, DFAC = 0.0, contact_force_factor = 1.0, contact_hc = 0.0;
     double DomMax[3] = { -100000000000.0, -100000000000.0, -100000000000.0 }, DomMin[3] = { 100000000000.0, 100000000000.0, 100000000000.0 };
     int solid_part_count = 0; int id_free_surf = 1;
@@ -772,6 +773,7 @@ struct Dom {
                     set3(contforce, P1, cf); delta_cont[P1] = delta;
                     V3 aP = vadd(A(P1), vdiv(cf, Mass[P1])); set3(a, P1, aP);
                     double fr_sta = friction_sta, fr_dyn = friction_dyn;
+                    if (friction_function == 1) fr_sta = fr_dyn = friction_m * T[P1] + friction_b;
                     double dens = Density[P1];
                     double dS2 = std::pow(Mass[P1] / dens, 2.0 / 3.0);
                     if (fr_sta > 0.) {
@@ -1108,6 +1110,7 @@ void load_case(const wfc::File & in, Dom & d)
         ms.axis_plane((int)pl[0], pl[1] != 0.0, p1, p2, (int)pl[8]); ms.calc_spheres();
         std::snprintf(key, 64, "mesh%d_hfac", m); ms.hfac = (float)in.scalar(key, 1.1);
         std::snprintf(key, 64, "mesh%d_id", m); ms.id = (int)in.scalar(key, 10 + m);
+        std::snprintf(key, 64, "mesh%d_w", m); if (in.has(key)) { const dvec & w_ = in.f(key); for (int k = 0; k < 3; ++k) ms.m_w(k) = w_[k]; }   // TriMesh::SetRotAxisVel
         std::snprintf(key, 64, "mesh%d_vel", m); if (in.has(key)) { const dvec & a_ = in.f(key); for (int k = 0; k < 3; ++k) ms.vel[k] = a_[k]; ms.tau = a_[3]; }
         ms.first_particle = (int)ntot; ntot += ms.nelem();
         d.meshes.push_back(ms);
@@ -1146,6 +1149,7 @@ void load_case(const wfc::File & in, Dom & d)
     }
     d.contact = in.scalar("contact", mesh_count > 0 ? 1 : 0) != 0.0;
     d.friction_sta = in.scalar("friction_sta", 0.0); d.friction_dyn = in.scalar("friction_dyn", 0.0);
+    d.friction_function = (int)in.scalar("friction_function", 0); d.friction_m = in.scalar("friction_m", 0.0); d.friction_b = in.scalar("friction_b", 0.0);
     d.PFAC = in.scalar("PFAC", 0.4); d.DFAC = in.scalar("DFAC", 0.0);
     d.cont_heat_fric = in.scalar("cont_heat_fric", 0) != 0.0; d.cont_heat_cond = in.scalar("cont_heat_cond", 0) != 0.0;
     d.ts_nb_inc = (int)in.scalar("ts_nb_inc", 5);

@@ -38,6 +38,103 @@ def cylinder_points(V, Rxy, Lz, r):
     return np.array(pts, dtype=np.float64)
 
 
+def box_points(V, Lx, Ly, Lz, r):
+    """numpy restatement of the cubic lattice of Domain::AddBoxLength (Source/Domain.cpp:326-470, type 1, no random); used only
+    to size per-particle arrays and to tag particles by position -- positions themselves come from the implementation under test."""
+    def axis(v0, L):
+        out, i, p = [], 0, v0
+        while p <= (v0 + L - r):
+            out.append(v0 + (2.0 * i + 1) * r)
+            i += 1
+            p = v0 + (2 * i + 1) * r
+        return np.array(out)
+    xs, ys, zs = axis(V[0], Lx), axis(V[1], Ly), axis(V[2], Lz)
+    pts = np.empty((len(zs) * len(ys) * len(xs), 3))
+    pts[:, 0] = np.tile(xs, len(ys) * len(zs)); pts[:, 1] = np.tile(np.repeat(ys, len(xs)), len(zs)); pts[:, 2] = np.repeat(zs, len(xs) * len(ys))
+    return pts
+
+
+def plate_yield(dx=0.0005, nsteps=1, kernel=0, hfac=1.2, vpull=0.01, amp=0.0):
+    """examples/Plate-Yield_3d.cpp:60-119 scaled by dx: AddBoxLength plate, bilinear yield, ends ID 2 / 3 pulled apart. The shipped
+    driver's Quintic_Spline with h = 1.3 dx gives 250 neighbours per particle, beyond the reference's MAX_NB_PER_PART (SURVEY.md
+    section 8c); kernel / hfac select what the reference itself can run. `amp` adds a smooth velocity field so that a short run yields."""
+    H, L = 0.01, 0.03
+    rho, K, G, Fy = 1000.0, 3.25e6, 7.15e5, 4000.0
+    h = hfac * dx
+    Cs = np.sqrt(K / rho)
+    V = (-L / 2.0 - L / 20.0, -H / 2.0, -H / 2.0)
+    dims = (L + L / 10.0 + dx / 10.0, H + dx / 10.0, H + dx / 10.0)
+    pts = box_points(V, dims[0], dims[1], dims[2], dx / 2.0)
+    n = len(pts)
+    x = pts[:, 0]
+    ID = np.full(n, 1, np.int32)
+    ID[x < -L / 2.0] = 2
+    ID[x > L / 2.0] = 3
+    ones = np.ones(n)
+    case = dict(
+        gen_kind=2.0, gen_args=np.array([1, V[0], V[1], V[2], dims[0], dims[1], dims[2], dx / 2.0, rho, h, 1, 0, 0, 0], float),
+        Dimension=3.0, KernelType=float(kernel), GradientType=0.0, DomMax=np.array([L, -1e11, -1e11]), DomMin=np.array([-L, 1e11, 1e11]),
+        ID=ID, G=G * ones, Cs=Cs * ones, PresEq=np.zeros(n, np.int32), Material=np.full(n, 2, np.int32), Fail=np.ones(n, np.int32),
+        Sigmay=Fy * ones, Alpha=1.0 * ones, Beta=1.0 * ones, TI=0.3 * ones, TIInitDist=dx * ones,
+        ts_nb_inc=5.0, dt=0.2 * h / Cs, nsteps=float(nsteps), mode=0.0,
+        bc=np.array([3, vpull, 0, 0, 0.0, 1, 0, 0, 2, -vpull, 0, 0, 0.0, 1, 0, 0], float),
+    )
+    if amp:
+        y, z = pts[:, 1], pts[:, 2]
+        case["v"] = np.stack([amp * np.sin(300.0 * y) * np.cos(200.0 * z) + amp * 40.0 * x, amp * np.cos(250.0 * x) * np.sin(300.0 * z), amp * np.sin(400.0 * x * 1.0) * np.cos(150.0 * y)], axis=1).reshape(-1)
+    return case
+
+
+def fsw_like(dx=0.0012, nsteps=1, wrot=10000.0, vplunge=10.0, vfac=1.0, L=0.05, rt=0.0065):
+    """examples/FSW.cpp:60-305 scaled by dx, with the NASTRAN tool replaced by a rotating, plunging AxisPlaneMesh disc-sized plane
+    (the mesh file reader is out of scope): AddBoxLength plate, Johnson-Cook with the driver's argument order (FSW.cpp:100-107 passes
+    C, m, n, eps_0 where the constructor takes n, c, eps0, m), thermal solver, convection on the bottom row, fixed side walls
+    (IsFree = false), friction linear in temperature, contact heat from friction."""
+    H = 0.003
+    rho, E, nu, Fy = 2700.0, 70.0e9, 0.3, 350.0e6
+    K = E / (3.0 * (1.0 - 2 * nu)); G = E / (2.0 * (1.0 + nu))
+    h = 1.2 * dx
+    Cs = np.sqrt(K / rho)
+    ybottom = -H - dx / 1.45
+    ytop = ybottom + H
+    V = (-L / 2.0 - L / 20.0, ybottom, -L / 2.0 - L / 20.0)
+    dims = (L + L / 10.0 + dx / 10.0, H, L + L / 10.0)
+    pts = box_points(V, dims[0], dims[1], dims[2], dx / 2.0)
+    n = len(pts)
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    r = np.sqrt(x * x + z * z)
+    ID = np.zeros(n, np.int32); nowrite = np.zeros(n, np.int32); free = np.ones(n, np.int32)
+    thbc = np.zeros(n, np.int32); hconv = np.zeros(n); tinf = np.zeros(n)
+    bottom = y < (ybottom + dx)
+    ID[bottom] = 2; nowrite[bottom] = 1; thbc[bottom] = 1; hconv[bottom] = 200.0 * vfac; tinf[bottom] = 20.0
+    top = (r > 1.85 * rt) & (y > (ytop - dx))
+    ID[top] = 2; nowrite[top] = 1
+    side = (z < -L / 2.0 + dx) | (z > L / 2.0 - dx) | (x < -L / 2.0 + 2.0 * dx) | (x > L / 2.0 - 2.0 * dx)
+    ID[side] = 3; nowrite[side] = 1; free[side] = 0
+    ones = np.ones(n)
+    A, B, C, m, n_, eps_0, T_m, T_t = 276.0e6, 255.0e6, 0.0015, 1.0, 0.3, 1.0, 775.0, 273.0
+    yplane = y.max() + h                          # the tool starts exactly one h above the top row: contact begins as soon as it moves
+    dens = max(4, int(np.ceil(2 * rt / (1.45 * dx))))
+    sx, sz = 0.37 * dx, -0.21 * dx
+    case = dict(
+        gen_kind=2.0, gen_args=np.array([0, V[0], V[1], V[2], dims[0], dims[1], dims[2], dx / 2.0, rho, h, 1, 0, 0, 0], float),
+        Dimension=3.0, KernelType=0.0, GradientType=0.0, DomMax=np.array([L, -1e11, -1e11]), DomMin=np.array([-L, 1e11, 1e11]),
+        ID=ID, IsFree=free, not_write_surf_ID=nowrite, G=G * ones, Cs=Cs * ones, PresEq=np.zeros(n, np.int32), Material=np.full(n, 2, np.int32),
+        Fail=np.ones(n, np.int32), Sigmay=Fy * ones, Alpha=1.0 * ones, TI=0.3 * ones, TIInitDist=dx * ones,
+        Material_model=np.full(n, JOHNSON_COOK, np.int32), mat_id=np.zeros(n, np.int32),
+        materials=np.array([JOHNSON_COOK, E, nu, A, B, C, m, n_, eps_0, T_m, T_t] + [0.0] * 5),     # constructor order: a, b, n, c, eps0, m, Tm, Tt
+        k_T=130.0 * vfac * ones, cp_T=960.0 * ones, T=20.0 * ones, Thermal_BC=thbc, h_conv=hconv, T_inf=tinf,
+        thermal_solver=1.0, pl_heating=1.0, cont_heat_fric=1.0, ts_nb_inc=5.0,
+        contact=1.0, friction_function=1.0, friction_b=0.3, friction_m=(0.1 - 0.3) / 500.0, friction_sta=0.3, friction_dyn=0.3, PFAC=0.6, DFAC=0.0,
+        mesh_count=1.0,
+        mesh0_plane=np.array([1, 1, -rt + sx, yplane, -rt + sz, rt + sx, yplane, rt + sz, dens], float), mesh0_hfac=1.1, mesh0_id=10.0,
+        mesh0_vel=np.array([0, -vplunge * vfac, 0, 0.0], float), mesh0_w=np.array([0.0, wrot * np.pi / 30.0 * vfac, 0.0]),
+        bc=np.array([2, 0, 0, 0, 0.0, 1, 0, 0, 3, 0, 0, 0, 0.0, 1, 0, 0], float),
+        dt=0.7 * h / Cs, nsteps=float(nsteps), mode=0.0,
+    )
+    return case
+
+
 def compression(dx=0.03, nsteps=1, thermal=True, pl_heating=True, alpha=1.0, beta=0.0, ti=0.3, gradient_type=0,
                 vmax=10.0, tau=0.005, cfl=0.2, fy=300.0e6, model=BILINEAR, t_field=True, ts_nb_inc=5):
     """examples/Compression_thermal.cpp:71-169 scaled by dx (shipped dx = 0.015 -> 12 144 particles)."""

@@ -49,6 +49,11 @@ def golden_cases():
     out["lf_auto_ts"] = sv(base, 2, auto_ts=1.0, CFL=0.1, tf=25 * base["dt"])
     out["lf_contact_60"] = sv(cases.contact_compression(dx=0.0032, nsteps=60, vmax=5.0, tau=1e-5, dens=8, cfl=0.3), 2)
     out["kd_gc_20"] = sv(gc(cases.perturbed(cases.compression(dx=0.04, nsteps=20), amp=60.0)), 1)
+    # AddBoxLength lattices: examples/Plate-Yield_3d.cpp (cubic and quintic spline kernels) and an examples/FSW.cpp-like set-up
+    # (Johnson-Cook, thermal, convection BC, fixed side walls, rotating + plunging tool plane, friction linear in T, friction heat)
+    out["plate_cubic_40"] = cases.plate_yield(dx=0.0012, nsteps=40, amp=0.3)
+    out["plate_quintic_10"] = cases.plate_yield(dx=0.0012, nsteps=10, kernel=2, hfac=0.8, amp=0.3)
+    out["fsw_like_80"] = cases.fsw_like(dx=0.0009, nsteps=80, L=0.02, rt=0.004)
     return out
 
 

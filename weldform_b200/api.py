@@ -20,6 +20,7 @@ class wf_params(C.Structure):
                 ("dom_min", C.c_double * 3), ("dom_max", C.c_double * 3),
                 ("thermal_solver", C.c_int), ("pl_heating", C.c_int), ("pl_work_heat_frac", C.c_double),
                 ("contact", C.c_int), ("friction_sta", C.c_double), ("friction_dyn", C.c_double),
+                ("friction_function", C.c_int), ("friction_m", C.c_double), ("friction_b", C.c_double),
                 ("pfac", C.c_double), ("dfac", C.c_double), ("contact_force_factor", C.c_double),
                 ("cont_heat_fric", C.c_int), ("cont_heat_cond", C.c_int), ("contact_hc", C.c_double),
                 ("nb_order_reference", C.c_int), ("grad_kernel_corr", C.c_int), ("solver", C.c_int), ("auto_ts", C.c_int), ("cfl", C.c_double), ("tuning", C.c_int)]

@@ -93,6 +93,7 @@ __global__ void k_mesh_ramp(double *motion, int n_mesh, const DevScalars *sc)
 struct ContactArgs {
     int K; const int *cont, *cont_cnt; const double *node, *enormal, *ev, *pplane; const int *en, *emesh;
     double friction_sta, friction_dyn, dfac, contact_hc; int cont_heat_fric, cont_heat_cond;
+    int friction_function; double friction_m, friction_b;
 };
 __global__ void k_contact(StepArgs a, ContactArgs k)
 {
@@ -134,15 +135,17 @@ __global__ void k_contact(StepArgs a, ContactArgs k)
                     dcont = delta;
                     acc = acc + cf / Mass;
                     const double dS2 = pow(Mass / dens, 2.0 / 3.0);
-                    if (k.friction_sta > 0.) {
+                    double fr_sta = k.friction_sta, fr_dyn = k.friction_dyn;
+                    if (k.friction_function == 1) fr_sta = fr_dyn = k.friction_m * q2.z + k.friction_b;      // Linear in T (Contact_Wang.cpp:243-244)
+                    if (fr_sta > 0.) {
                         const V3 du = (x_pred - x) - dt * v2;
                         const V3 delta_tg = du - dot(du, n2) * n2;
                         const V3 tgforce = kij * delta_tg;
-                        if (norm(tgforce) < k.friction_sta * norm(cf)) {
+                        if (norm(tgforce) < fr_sta * norm(cf)) {
                             cf = cf - tgforce / Mass;          // unit quirk kept (Contact_Wang.cpp:279)
                             acc = acc - tgforce / Mass;
                         } else {
-                            const V3 tgforce_dyn = ((k.friction_dyn * norm(cf)) * tgforce) / norm(tgforce);
+                            const V3 tgforce_dyn = ((fr_dyn * norm(cf)) * tgforce) / norm(tgforce);
                             cf = cf - tgforce_dyn;
                             acc = acc - tgforce_dyn / Mass;
                             if (k.cont_heat_fric) { const double abs_fv = fabs(dot(tgforce_dyn, vr)); qfric = abs_fv * dens / Mass; }
@@ -310,7 +313,7 @@ int contact_impl(wf_ctx *c)
     ProfScope ps(c, PK_CONTACT);
     StepArgs a = make_step_args(c);
     ContactArgs k; k.K = c->cont_k; k.cont = c->cont; k.cont_cnt = c->cont_cnt; k.node = c->dm.node; k.enormal = c->dm.enormal; k.ev = c->dm.ev; k.pplane = c->dm.pplane;
-    k.en = c->dm.en; k.emesh = c->dm.emesh; k.friction_sta = c->prm.friction_sta; k.friction_dyn = c->prm.friction_dyn; k.dfac = c->prm.dfac; k.contact_hc = c->prm.contact_hc;
+    k.en = c->dm.en; k.emesh = c->dm.emesh; k.friction_sta = c->prm.friction_sta; k.friction_dyn = c->prm.friction_dyn; k.friction_function = c->prm.friction_function; k.friction_m = c->prm.friction_m; k.friction_b = c->prm.friction_b; k.dfac = c->prm.dfac; k.contact_hc = c->prm.contact_hc;
     k.cont_heat_fric = c->prm.cont_heat_fric; k.cont_heat_cond = c->prm.cont_heat_cond;
     k_contact<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a, k); WF_LAUNCH_CHECK(c); c->launches++;
     return 0;

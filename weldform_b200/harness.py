@@ -74,6 +74,7 @@ def context_from_case(case, device=0, comm=None):
     mesh_count = int(case.get("mesh_count", 0))
     p.contact = int(case.get("contact", 1 if mesh_count else 0))
     p.friction_sta = float(case.get("friction_sta", 0.0)); p.friction_dyn = float(case.get("friction_dyn", 0.0))
+    p.friction_function = int(case.get("friction_function", 0)); p.friction_m = float(case.get("friction_m", 0.0)); p.friction_b = float(case.get("friction_b", 0.0))
     p.pfac = float(case.get("PFAC", 0.4)); p.dfac = float(case.get("DFAC", 0.0))
     p.cont_heat_fric = int(case.get("cont_heat_fric", 0)); p.cont_heat_cond = int(case.get("cont_heat_cond", 0))
     p.tuning = int(case.get("tuning", int(__import__("os").environ.get("WF_TUNING", "0"))))
@@ -150,6 +151,8 @@ def context_from_case(case, device=0, comm=None):
         n = len(sel)
     ctx.set_particles(n, n_sph_global=n_global, **arrays)
     for m in range(mesh_count):
+        if "mesh%d_w" % m in case:                         # TriMesh::SetRotAxisVel
+            ctx.mesh_set_motion(m, (0.0, 0.0, 0.0), tuple(float(w) for w in case["mesh%d_w" % m][:3]))
         key = "mesh%d_vel" % m
         if key in case:
             ctx.mesh_set_ramp(m, case[key][:3], float(case[key][3]))

@@ -256,7 +256,7 @@ inline void Domain::backend_begin(double dt)
     p.solver = solver_kind; p.auto_ts = (solver_kind != 0 && auto_ts) ? 1 : 0; p.cfl = CFL;   // auto_ts is dead code in the Fraser loop (SolverFraser.cpp:500-502)
     p.grad_kernel_corr = gradKernelCorr ? 1 : 0;     // CalcGradCorrMatrix + the locking summation the reference switches to (SolverFraser.cpp:112-115)
     if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
-    if (friction_function != Constant && contact) throw new Fatal("Domain::friction_function != Constant is not implemented in weldform_b200");
+    p.friction_function = (friction_function == Linear) ? 1 : 0; p.friction_m = friction_m; p.friction_b = friction_b;
     ck(wf_set_params(backend, &p), "wf_set_params");
     // ---- materials: distinct Material_ objects
     std::map<Material_ *, int> mat_ids; std::vector<wf_material> mats;

@@ -79,12 +79,19 @@ __global__ void k_permute_q(int64_t n, const int *perm, const double4 *a0, const
     int p = perm[s];
     b0[s] = a0[p]; b1[s] = a1[p]; b2[s] = a2[p]; b3[s] = a3[p]; b4[s] = a4[p]; b5[s] = a5[p];
 }
-__global__ void k_permute_f(int64_t n, int64_t cap, const int *perm, const double *a, double *b)
+// WF_PERM_FIELDS own fields per thread: one read of perm[s] and that many independent 8-byte gathers in flight
+#define WF_PERM_FIELDS 8
+__global__ void k_permute_f(int64_t n, int64_t cap, int nf, const int *perm, const double *a, double *b)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    int64_t off = (int64_t)blockIdx.y * cap;
-    b[off + s] = a[off + perm[s]];
+    const int p = perm[s];
+    const int f0 = blockIdx.y * WF_PERM_FIELDS;
+    double v[WF_PERM_FIELDS];
+#pragma unroll
+    for (int k = 0; k < WF_PERM_FIELDS; ++k) if (f0 + k < nf) v[k] = a[(int64_t)(f0 + k) * cap + p];
+#pragma unroll
+    for (int k = 0; k < WF_PERM_FIELDS; ++k) if (f0 + k < nf) b[(int64_t)(f0 + k) * cap + s] = v[k];
 }
 __global__ void k_permute_i(int64_t n, int64_t cap, const int *perm, const int *a, int *b, int *slot_of)
 {
@@ -160,7 +167,7 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
                     unsigned mask = 0u;
 #pragma unroll 4
                     for (int k = 0; k < m; ++k) {
-                        const double4 qj = Q0[base + k];
+                        const double4 qj = Q0[base + k];        // two LDG.128: measured faster here than one LDG.256 (lanes of a cell read the same record)
                         const double ex = xi.x - qj.x, ey = xi.y - qj.y, ez = xi.z - qj.z;
                         const double d2 = ex * ex + (ey * ey + ez * ez);          // == dot(xij, xij) for either sign of xij
                         double thr = thr_u;
@@ -395,7 +402,8 @@ int nb_build_impl(wf_ctx *c)
         const int64_t keep = n - n_out;               // emigrants carry the sentinel key: they are the tail and are dropped
         k_permute_q<<<grid_for(keep, B), B, 0, st>>>(keep, perm, c->Q0[a], c->Q1[a], c->Q2[a], c->S0[a], c->S1[a], c->S2[a], c->Q0[b], c->Q1[b], c->Q2[b], c->S0[b], c->S1[b], c->S2[b]); WF_LAUNCH_CHECK(c);
         // gradCorrM (the last 9 own fields) lives only with gradKernelCorr
-        dim3 gf(grid_for(keep, B), c->prm.grad_kernel_corr ? F_COUNT : F_GC); k_permute_f<<<gf, B, 0, st>>>(keep, cap, perm, c->F[a], c->F[b]); WF_LAUNCH_CHECK(c);
+        const int nf = c->prm.grad_kernel_corr ? F_COUNT : F_GC;
+        dim3 gf(grid_for(keep, B), (nf + WF_PERM_FIELDS - 1) / WF_PERM_FIELDS); k_permute_f<<<gf, B, 0, st>>>(keep, cap, nf, perm, c->F[a], c->F[b]); WF_LAUNCH_CHECK(c);
         dim3 gi(grid_for(keep, B), I_COUNT); k_permute_i<<<gi, B, 0, st>>>(keep, cap, perm, c->I[a], c->I[b], multi ? nullptr : c->slot_of); WF_LAUNCH_CHECK(c);
         c->cur = b; c->launches += 3;
         c->n_loc = keep; c->n = keep; n = keep; }

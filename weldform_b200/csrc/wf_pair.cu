@@ -302,13 +302,13 @@ template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_s
             r01 = r01 + ((L01 - L10) * -0.5) * mf; r02 = r02 + ((L02 - L20) * -0.5) * mf; r12 = r12 + ((L12 - L21) * -0.5) * mf;
         }
     }
-    if (PF && cnt > 0 && !gc) { const int j0 = (int)(a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s] & 0x7fffffffu); qn = a.Q0[j0]; wn = a.Q1[j0];
+    if (PF && cnt > 0 && !gc) { const int j0 = (int)(a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s] & 0x7fffffffu); qn = ldrec<true>(a.Q0 + j0); wn = ldrec<true>(a.Q1 + j0);
                          if (cnt > 1) e2 = a.nbr[(int64_t)nb_row(1, nhi, a.K) * a.cap + s]; }
     for (int n = 0; n < (gc ? 0 : cnt); ++n) {
         double4 qj, wj;
         if (PF) {
             qj = qn; wj = wn;
-            if (n + 1 < cnt) { const int j1 = (int)(e2 & 0x7fffffffu); qn = a.Q0[j1]; wn = a.Q1[j1]; }
+            if (n + 1 < cnt) { const int j1 = (int)(e2 & 0x7fffffffu); qn = ldrec<true>(a.Q0 + j1); wn = ldrec<true>(a.Q1 + j1); }
             if (n + 2 < cnt) e2 = a.nbr[(int64_t)nb_row(n + 2, nhi, a.K) * a.cap + s];
         } else {
             const int j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
@@ -655,8 +655,8 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __gl
     double Mg[9];
     if (!FAST) { for (int k = 0; k < 9; ++k) Mg[k] = gc ? OWN(F_GC + k) : 0.0; }
     double4 qn = qi, wn = wi, q2n = q2i; uint32_t e1 = 0, e2 = 0;
-    if (PF && cnt > 0) { e1 = a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s]; const int j0 = (int)(e1 & 0x7fffffffu); qn = a.Q0[j0]; wn = a.Q1[j0];
-                         if (THERM || EKIN) q2n = a.Q2[j0];
+    if (PF && cnt > 0) { e1 = a.nbr[(int64_t)nb_row(0, nhi, a.K) * a.cap + s]; const int j0 = (int)(e1 & 0x7fffffffu); qn = ldrec<true>(a.Q0 + j0); wn = ldrec<true>(a.Q1 + j0);
+                         if (THERM || EKIN) q2n = ldrec<true>(a.Q2 + j0);
                          if (cnt > 1) e2 = a.nbr[(int64_t)nb_row(1, nhi, a.K) * a.cap + s]; }
     for (int n = 0; n < cnt; ++n) {
         uint32_t e; double4 qj, wj;
@@ -666,7 +666,7 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __gl
         double4 q2j_pf = make_double4(0., 0., 0., 0.);
         if (THERM || EKIN) { if (PF) q2j_pf = q2n; else q2j_pf = a.Q2[j]; }
         if (PF) {
-            if (n + 1 < cnt) { e1 = e2; const int j1 = (int)(e1 & 0x7fffffffu); qn = a.Q0[j1]; wn = a.Q1[j1]; if (THERM || EKIN) q2n = a.Q2[j1]; }
+            if (n + 1 < cnt) { e1 = e2; const int j1 = (int)(e1 & 0x7fffffffu); qn = ldrec<true>(a.Q0 + j1); wn = ldrec<true>(a.Q1 + j1); if (THERM || EKIN) q2n = ldrec<true>(a.Q2 + j1); }
             if (n + 2 < cnt) e2 = a.nbr[(int64_t)nb_row(n + 2, nhi, a.K) * a.cap + s];
         }
         const V3 xj = v3(qj.x, qj.y, qj.z), vj = v3(wj.x, wj.y, wj.z);

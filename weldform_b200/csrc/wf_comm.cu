@@ -111,15 +111,21 @@ namespace wf {
 static void balance_layers(const std::vector<long long> &hist, int nranks, std::vector<int> &bounds)
 {
     const int L = (int)hist.size();
-    long long total = 0; for (long long h : hist) total += h;
+    std::vector<long long> cum(L + 1, 0);
+    for (int l = 0; l < L; ++l) cum[l + 1] = cum[l] + hist[l];
+    const long long total = cum[L];
     bounds.assign(nranks + 1, 0); bounds[nranks] = L;
-    long long cum = 0; int r = 1;
-    for (int l = 0; l < L && r < nranks; ++l) {
-        cum += hist[l];
-        // close rank r-1 after layer l when its share is reached, keeping at least one layer for every remaining rank
-        while (r < nranks && (cum * nranks >= (long long)r * total) && (l + 1) <= L - (nranks - r)) { bounds[r] = std::max(l + 1, bounds[r - 1] + 1); ++r; }
+    for (int r = 1; r < nranks; ++r) {
+        // the layer boundary whose cumulative count is NEAREST to r/nranks of the particles (the step time is set by the fullest
+        // rank), keeping at least one layer for every rank before and after
+        const int lo = bounds[r - 1] + 1, hi = L - (nranks - r);
+        int best = lo; long long bestd = -1;
+        for (int b = lo; b <= hi; ++b) {
+            long long d = cum[b] * nranks - (long long)r * total; if (d < 0) d = -d;
+            if (bestd < 0 || d < bestd) { bestd = d; best = b; }
+        }
+        bounds[r] = best;
     }
-    for (; r < nranks; ++r) bounds[r] = std::max(bounds[r - 1] + 1, L - (nranks - r));
 }
 
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax)
@@ -179,12 +185,10 @@ int comm_plan_layers(wf_ctx *c, const std::vector<long long> &hist_local)
 }
 
 // sends/receives the boundary slices of the selected gathered arrays (zero-copy); halo regions were sized at the rebuild
-int comm_halo_refresh(wf_ctx *c, int sets)
+static int halo_exchange(wf_ctx *c, int sets, cudaStream_t st)
 {
     wf_ctx::Comm &m = c->comm;
-    if (m.nranks <= 1) return 0;
     NcclApi *A = nccl_api();
-    ProfScope ps(c, PK_HALO);
     double4 *arr[6]; int na = 0; const int b = c->cur;
     if (sets & HALO_Q0) arr[na++] = c->Q0[b];
     if (sets & HALO_Q1) arr[na++] = c->Q1[b];
@@ -194,16 +198,54 @@ int comm_halo_refresh(wf_ctx *c, int sets)
     WF_NCCL(c, A->GroupStart());
     for (int k = 0; k < na; ++k) {
         if (m.rank > 0) {
-            if (m.send_lo_n) WF_NCCL(c, A->Send(arr[k] + m.send_lo_start, 4 * m.send_lo_n, ncclDouble, m.rank - 1, comm, c->stream));
-            if (m.halo_lo_n) WF_NCCL(c, A->Recv(arr[k] + m.halo_lo_start, 4 * m.halo_lo_n, ncclDouble, m.rank - 1, comm, c->stream));
+            if (m.send_lo_n) WF_NCCL(c, A->Send(arr[k] + m.send_lo_start, 4 * m.send_lo_n, ncclDouble, m.rank - 1, comm, st));
+            if (m.halo_lo_n) WF_NCCL(c, A->Recv(arr[k] + m.halo_lo_start, 4 * m.halo_lo_n, ncclDouble, m.rank - 1, comm, st));
         }
         if (m.rank < m.nranks - 1) {
-            if (m.send_hi_n) WF_NCCL(c, A->Send(arr[k] + m.send_hi_start, 4 * m.send_hi_n, ncclDouble, m.rank + 1, comm, c->stream));
-            if (m.halo_hi_n) WF_NCCL(c, A->Recv(arr[k] + m.halo_hi_start, 4 * m.halo_hi_n, ncclDouble, m.rank + 1, comm, c->stream));
+            if (m.send_hi_n) WF_NCCL(c, A->Send(arr[k] + m.send_hi_start, 4 * m.send_hi_n, ncclDouble, m.rank + 1, comm, st));
+            if (m.halo_hi_n) WF_NCCL(c, A->Recv(arr[k] + m.halo_hi_start, 4 * m.halo_hi_n, ncclDouble, m.rank + 1, comm, st));
         }
     }
     WF_NCCL(c, A->GroupEnd());
     c->launches += 1;
+    return 0;
+}
+int comm_halo_refresh(wf_ctx *c, int sets)
+{
+    if (c->comm.nranks <= 1) return 0;
+    ProfScope ps(c, PK_HALO);
+    return halo_exchange(c, sets, c->stream);
+}
+// Overlap of the halo exchange with interior pair work: the exchange is issued on the communication stream once everything
+// queued on the compute stream so far (the producers of the slices) has finished; the caller evaluates the interior range
+// meanwhile and calls comm_halo_end before touching the boundary layers. Only the one-cell-thick boundary layers -- the send
+// slices themselves -- can hold a particle with a halo neighbour, and they are contiguous in the cell-sorted order.
+int comm_halo_begin(wf_ctx *c, int sets, int64_t *i0, int64_t *i1)
+{
+    wf_ctx::Comm &m = c->comm;
+    *i0 = 0; *i1 = c->n_loc;
+    if (m.nranks <= 1) return 0;
+    if (c->prm.tuning & 512) {                        // bit 9 of wf_params::tuning: blocking refresh (A/B measurement)
+        WF_CHECK(comm_halo_refresh(c, sets));
+        return 0;
+    }
+    if (m.rank > 0) *i0 = m.send_lo_start + m.send_lo_n;
+    if (m.rank < m.nranks - 1) *i1 = m.send_hi_start;
+    if (*i1 < *i0) *i1 = *i0;
+    WF_CUDA(c, cudaEventRecord(m.ev_ready, c->stream));
+    WF_CUDA(c, cudaStreamWaitEvent(m.stream, m.ev_ready, 0));
+    WF_CHECK(halo_exchange(c, sets, m.stream));
+    WF_CUDA(c, cudaEventRecord(m.ev_done, m.stream));
+    m.pending = true;
+    return 0;
+}
+int comm_halo_end(wf_ctx *c)
+{
+    wf_ctx::Comm &m = c->comm;
+    if (!m.pending) return 0;
+    ProfScope ps(c, PK_HALO);
+    WF_CUDA(c, cudaStreamWaitEvent(c->stream, m.ev_done, 0));
+    m.pending = false;
     return 0;
 }
 
@@ -364,6 +406,8 @@ extern "C" int wf_comm_init(wf_ctx *c, int rank, int nranks, const void *id128)
     ncclComm_t comm;
     WF_NCCL(c, A->CommInitRank(&comm, nranks, id, rank));
     c->comm.nccl = comm;
+    WF_CUDA(c, cudaStreamCreateWithFlags(&c->comm.stream, cudaStreamNonBlocking));
+    WF_CUDA(c, cudaEventCreateWithFlags(&c->comm.ev_ready, cudaEventDisableTiming)); WF_CUDA(c, cudaEventCreateWithFlags(&c->comm.ev_done, cudaEventDisableTiming));
     WF_CUDA(c, cudaMalloc(&c->comm.d_cnt, 64 * sizeof(int) + 16 * sizeof(long long)));
     WF_CUDA(c, cudaMemset(c->comm.d_cnt, 0, 64 * sizeof(int) + 16 * sizeof(long long)));
     WF_CUDA(c, cudaMalloc(&c->comm.d_all, (size_t)nranks * 32 * sizeof(double)));

@@ -86,6 +86,7 @@ struct wf_ctx {
         int64_t halo_lo_start = 0, halo_lo_n = 0, halo_hi_start = 0, halo_hi_n = 0;   // halo regions (from rank-1 / rank+1)
         double *stage_send[2] = { nullptr, nullptr }, *stage_recv[2] = { nullptr, nullptr }; size_t stage_cap = 0;   // migration staging
         int *d_emig = nullptr; int *d_cnt = nullptr; int64_t emig_cap = 0;            // emigrant slot lists (2 x emig_cap), counters
+        cudaStream_t stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool pending = false;   // halo exchange overlapped with interior work
         double *d_rank = nullptr, *d_all = nullptr;                                     // scalar partials: this rank / all ranks
         int64_t migrated_out = 0, migrated_in = 0, halo_bytes_step = 0;
     } comm;
@@ -173,14 +174,18 @@ int pair_gradcorr(wf_ctx *c);
 int pair_tir(wf_ctx *c);
 int pair_min_ts(wf_ctx *c, double *test_min);
 int pair_density(wf_ctx *c);
-int pair_rate_stress(wf_ctx *c);
-int pair_accel(wf_ctx *c);
+int pair_rate_stress(wf_ctx *c, int64_t lo = 0, int64_t hi = -1);   // slots [lo, hi); hi < 0: n_loc
+int pair_accel(wf_ctx *c, int64_t lo = 0, int64_t hi = -1);
 int pair_thermal(wf_ctx *c);
 int pair_energy(wf_ctx *c);
 int pair_post(wf_ctx *c, bool skip_dens = false);
 // wf_comm.cu
 enum HaloSet { HALO_Q1 = 1, HALO_Q0 = 2, HALO_Q2 = 4, HALO_S = 8 };
 int comm_halo_refresh(wf_ctx *c, int sets);             // no-op on one GPU
+// asynchronous form: the exchange runs on the communication stream; [*i0, *i1) receives the interior slot range (particles whose
+// neighbour lists cannot reach a halo slot) that may be evaluated meanwhile; comm_halo_end makes the compute stream wait for it
+int comm_halo_begin(wf_ctx *c, int sets, int64_t *i0, int64_t *i1);
+int comm_halo_end(wf_ctx *c);
 int comm_gather_scalars(wf_ctx *c, int nvals);          // d_rank -> d_all (all ranks), no-op on one GPU
 int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);

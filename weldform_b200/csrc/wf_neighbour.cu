@@ -22,7 +22,7 @@ using namespace wf;
 namespace {
 
 struct Grid {
-    double BLPF[3], CellSize[3], Cellfac; int CellNo[3]; int ax[3];   // ax[0] fastest .. ax[2] slowest storage axis
+    double BLPF[3], CellSize[3], Cellfac, hmax; int CellNo[3]; int ax[3];   // ax[0] fastest .. ax[2] slowest storage axis
     __host__ __device__ int lin(const int c[3]) const { return (c[ax[2]] * CellNo[ax[1]] + c[ax[1]]) * CellNo[ax[0]] + c[ax[0]]; }
     __host__ __device__ void unlin(int l, int c[3]) const { c[ax[0]] = l % CellNo[ax[0]]; l /= CellNo[ax[0]]; c[ax[1]] = l % CellNo[ax[1]]; c[ax[2]] = l / CellNo[ax[1]]; }
 };
@@ -153,9 +153,24 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
             const int mat_i = check_material ? classes[cls_of[s]].Material : 0;
             const double lim_u = g.Cellfac * ((qi.w + qi.w) / 2), thr_u = (lim_u * lim_u) * (1.0 + 8e-15);     // uniform h: (h+h)/2 == h
             int c[3]; g.unlin((int)(keys[s] >> 32), c);
+            // distance from x_i to the lower / upper face of its own cell along each axis: a neighbour cell none of whose points can
+            // lie within the largest possible cutoff Cellfac*(h_i + hmax)/2 is skipped (about a quarter of the 27 for a lattice).
+            // Conservative: faces nudged by 1e-9 cell sizes (floor((x - BLPF)/CellSize) rounds), clamped particles count as on the face.
+            const double xi3[3] = { qi.x, qi.y, qi.z };
+            double glo[3], ghi[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double lo = g.BLPF[k] + c[k] * g.CellSize[k], eps = 1e-9 * g.CellSize[k];
+                glo[k] = fmax(xi3[k] - lo - eps, 0.0); ghi[k] = fmax(lo + g.CellSize[k] - xi3[k] - eps, 0.0);
+            }
+            const double lim_c = g.Cellfac * ((qi.w + g.hmax) / 2), thr_c = (lim_c * lim_c) * (1.0 + 1e-9);
             for (int e = 0; e < 27; ++e) {
                 int d[3] = { c[0] + c_walk[e][0], c[1] + c_walk[e][1], c[2] + c_walk[e][2] };
                 if (d[0] < 0 || d[0] >= g.CellNo[0] || d[1] < 0 || d[1] >= g.CellNo[1] || d[2] < 0 || d[2] >= g.CellNo[2]) continue;
+                double gap2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const double gk = c_walk[e][k] < 0 ? glo[k] : (c_walk[e][k] > 0 ? ghi[k] : 0.0); gap2 += gk * gk; }
+                if (gap2 > thr_c) continue;
                 const int l = g.lin(d);
                 const int js = cell_start[l], je = cell_end[l];
                 const int role = c_walk[e][3];
@@ -300,7 +315,7 @@ __global__ void k_cnt_to_i64(int64_t n, const int *a, int64_t *b) { int64_t s = 
 Grid make_grid(const wf_ctx *c)
 {
     Grid g; for (int k = 0; k < 3; ++k) { g.BLPF[k] = c->BLPF[k]; g.CellSize[k] = c->CellSize[k]; g.CellNo[k] = c->CellNo[k]; }
-    g.Cellfac = c->Cellfac; g.ax[0] = c->ax_fast; g.ax[1] = c->ax_mid; g.ax[2] = c->ax_slow; return g;
+    g.Cellfac = c->Cellfac; g.hmax = c->hmax; g.ax[0] = c->ax_fast; g.ax[1] = c->ax_mid; g.ax[2] = c->ax_slow; return g;
 }
 
 } // namespace

@@ -49,7 +49,8 @@ struct FastConsts {
 };
 struct PairArgs {
     FastConsts fc;
-    int64_t n, cap; int nsph, K, dim, kt, gt;
+    int64_t n, cap, s0;           // slots [s0, n) of this launch (s0 = 0, n = n_loc unless the launch covers a sub-range)
+    int nsph, K, dim, kt, gt;
     const uint32_t *nbr; const int *nb_cnt, *nb_hi; const int *orig; const int *cls_of; const int *is_free;   // is_free: NULL when every particle is free
     double4 *Q0, *Q1, *Q2, *S0, *S1, *S2; double *F; const ClassProps *cls; const MatProps *mats;
     double dt; int any_ti, thermal, pl_heating, contact, cont_heat_fric; double pl_work_heat_frac;
@@ -146,7 +147,7 @@ __device__ inline V3 gc_mat_vec(const double M[9], const V3 &g)
 // discovery order, then InvLog (matvec.h:673-693); identity when the determinant is below 1e-10. All-free particle sets only.
 __global__ void __launch_bounds__(128) k_gradcorr(PairArgs a)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
     const double4 qi = a.Q0[s];
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(128) k_gradcorr(PairArgs a)
 // orders evaluate the momentum sums first, with the TIR of the stresses and densities the previous step left behind
 __global__ void k_tir(PairArgs a)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
     const double TI = a.cls[a.cls_of[s]].TI;
@@ -204,7 +205,7 @@ __global__ void k_tir(PairArgs a)
 // the CFL factor and the comparison with deltatint are applied by the caller
 __global__ void __launch_bounds__(128) k_min_ts(PairArgs a, double cfl, double *partial)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     double test = 1.0e300;
     if (s < a.n) {
         const double4 qi = a.Q0[s], wi = a.Q1[s];
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(256) k_min_final(const double *partial, int n,
 // ---- step prologue per particle: rho += dt*drho (SolverFraser.cpp:248-252), m/rho, TIR <- the tensor prepared for this step
 __global__ void k_prologue(PairArgs a)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
     const double dd = OWN(F_DDN);
@@ -267,7 +268,7 @@ __device__ inline double yield_stress(const MatProps &m, double strain, double s
 // ---- CalcRateTensors + RateTensorsReduction + CalcStressStrain -------------------------------------------------------
 template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_stress(PairArgs a)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
     const double4 qi = a.Q0[s], wi = a.Q1[s];
@@ -410,7 +411,7 @@ template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_s
 // ---- CalcAccel + AccelReduction ------------------------------------------------------------------------------------------
 template <bool FAST, int GT, int MB, bool PF> __global__ void __launch_bounds__(128, MB) k_accel(PairArgs a)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
     const double4 qi = a.Q0[s], wi = a.Q1[s], q2i = a.Q2[s];
@@ -578,7 +579,7 @@ template <bool TI_ON, bool W256> __device__ __forceinline__ void accel_term(cons
 }
 template <bool TI_ON, int MB, bool W256> __global__ void __launch_bounds__(128, MB) k_accel_lean(PairArgs a)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
     const double4 qi = a.Q0[s], wi = a.Q1[s];
@@ -607,7 +608,7 @@ template <bool TI_ON, int MB, bool W256> __global__ void __launch_bounds__(128, 
 // ---- CalcPlasticWorkHeat, T += dt*dTdt, CalcConvHeat (ThermalStuct.cpp:14-39, Thermal.cpp:721-732,339-389) ------------
 __global__ void k_thermal_pre(PairArgs a)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) return;
     const double dt = a.dt;
@@ -637,7 +638,7 @@ __global__ void k_thermal_pre(PairArgs a)
 // order when several threads race in the reference; identical for Nproc = 1).
 template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __global__ void __launch_bounds__(128, MB) k_post(PairArgs a)
 {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
     if (a.orig[s] >= a.nsph) { if (THERM) OWN(F_DTDT) = 0.; if (EKIN) OWN(F_DKIN) = 0.; return; }
     const double4 qi = a.Q0[s], wi = a.Q1[s], q2i = a.Q2[s];
@@ -764,7 +765,7 @@ PairArgs make_args(wf_ctx *c)
         f.AlphaAvg = (cp.Alpha + cp.Alpha) / 2.0; f.BetaAvg = (cp.Beta + cp.Beta) / 2.0;
         f.AlphaCij = f.AlphaAvg * (0.5 * (cp.Cs + cp.Cs)); f.h2_001 = 0.01 * f.h * f.h;
     }
-    a.n = c->n_loc; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
+    a.n = c->n_loc; a.s0 = 0; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
     a.nbr = c->nbr; a.nb_cnt = c->nb_cnt; a.nb_hi = c->nb_hi; a.orig = c->Ip(I_ORIG); a.cls_of = c->Ip(I_CLS); a.is_free = c->any_fixed ? c->Ip(I_FREE) : nullptr;
     a.Q0 = c->Q0[c->cur]; a.Q1 = c->Q1[c->cur]; a.Q2 = c->Q2[c->cur]; a.S0 = c->S0[c->cur]; a.S1 = c->S1[c->cur]; a.S2 = c->S2[c->cur];
     a.F = c->F[c->cur]; a.cls = c->d_classes; a.mats = c->d_mats; a.dt = c->dt; a.any_ti = c->any_ti ? 1 : 0;
@@ -839,19 +840,23 @@ int pair_density(wf_ctx *c)
     c->dens_valid = false;
     return 0;
 }
-int pair_rate_stress(wf_ctx *c)
+int pair_rate_stress(wf_ctx *c, int64_t lo, int64_t hi)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
+    if (hi < 0) hi = c->n_loc;
+    if (hi <= lo) return 0;
+    PairArgs a = make_args(c); a.s0 = lo; a.n = hi; const int g = grid_for(hi - lo, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_RATE_STRESS);
     if (fast_path(c)) WF_LAUNCH_PF(k_rate_stress, true); else WF_LAUNCH_PF(k_rate_stress, false);
     WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
-int pair_accel(wf_ctx *c)
+int pair_accel(wf_ctx *c, int64_t lo, int64_t hi)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
+    if (hi < 0) hi = c->n_loc;
+    if (hi <= lo) return 0;
+    PairArgs a = make_args(c); a.s0 = lo; a.n = hi; const int g = grid_for(hi - lo, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_ACCEL);
     const bool fast = fast_path(c);
     const bool mb3 = (c->prm.tuning & 2) == 0;        // 3 resident blocks per SM (168 registers) by default; bit 1 of wf_params::tuning selects 4 (128 registers, spills)
@@ -873,14 +878,24 @@ int pair_accel(wf_ctx *c)
     return 0;
 }
 // CalcPlasticWorkHeat + ThermalCalcs, then CalcKinEnergyEqn + CalcIntEnergyEqn, then next step's density rate: one walk
-int pair_post(wf_ctx *c, bool skip_dens)
+// the per-particle prologue of the post pass: CalcPlasticWorkHeat, T += dt*dTdt, CalcConvHeat
+int pair_post_pre(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
-    PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
+    PairArgs a = make_args(c);
+    ProfScope ps(c, PK_THERMAL);
+    if (c->prm.thermal_solver != 0 || c->prm.pl_heating) { k_thermal_pre<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
+    return 0;
+}
+// the pair walk of the post pass over slots [lo, hi)
+int pair_post_range(wf_ctx *c, bool skip_dens, int64_t lo, int64_t hi)
+{
+    WF_PAIR_PRECHECK(c);
+    if (hi < 0) hi = c->n_loc;
+    if (hi <= lo) return 0;
+    PairArgs a = make_args(c); a.s0 = lo; a.n = hi; const int g = grid_for(hi - lo, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_THERMAL);
     const bool th = c->prm.thermal_solver != 0;
-    if (th || c->prm.pl_heating) { k_thermal_pre<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
-    WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2));   // x, v, T of the halos after the move / temperature update
     const bool fast = fast_path(c);
     if (skip_dens) {
         // the coming step rebuilds its neighbour lists first (known from the cadence): a density rate and TIR summed over the
@@ -888,7 +903,6 @@ int pair_post(wf_ctx *c, bool skip_dens)
         if (th) { if (fast) WF_LAUNCH_PF(k_post, true, true, true, false); else WF_LAUNCH_PF(k_post, false, true, true, false); }
         else    { if (fast) WF_LAUNCH_PF(k_post, true, false, true, false); else WF_LAUNCH_PF(k_post, false, false, true, false); }
         WF_LAUNCH_CHECK(c); c->launches++;
-        c->dens_valid = false;
         return 0;
     }
     if (th && fast && pf && (c->prm.tuning & (64 | 128))) {      // bits 6 / 7 of wf_params::tuning: 5 / 3 resident blocks per SM for the fused pass (A/B measurements)
@@ -897,7 +911,21 @@ int pair_post(wf_ctx *c, bool skip_dens)
     else if (th) { if (fast) WF_LAUNCH_PF(k_post, true, true, true, true); else WF_LAUNCH_PF(k_post, false, true, true, true); }
     else    { if (fast) WF_LAUNCH_PF(k_post, true, false, true, true); else WF_LAUNCH_PF(k_post, false, false, true, true); }
     WF_LAUNCH_CHECK(c); c->launches++;
-    c->dens_valid = true;
+    return 0;
+}
+// CalcPlasticWorkHeat + ThermalCalcs, then CalcKinEnergyEqn + CalcIntEnergyEqn, then next step's density rate: one walk.
+// Multi-GPU: the halo refresh (x, v, T after the move / temperature update) travels on the communication stream while the
+// interior slots -- whose neighbour lists cannot reach a halo slot -- are evaluated; the two boundary layers follow.
+int pair_post(wf_ctx *c, bool skip_dens)
+{
+    WF_CHECK(pair_post_pre(c));
+    int64_t i0 = 0, i1 = c->n_loc;
+    WF_CHECK(comm_halo_begin(c, HALO_Q0 | HALO_Q1 | HALO_Q2, &i0, &i1));
+    WF_CHECK(pair_post_range(c, skip_dens, i0, i1));
+    WF_CHECK(comm_halo_end(c));
+    WF_CHECK(pair_post_range(c, skip_dens, 0, i0));
+    WF_CHECK(pair_post_range(c, skip_dens, i1, c->n_loc));
+    c->dens_valid = !skip_dens;
     return 0;
 }
 // stand-alone phases of the C ABI (wf_thermal, wf_energy): same kernel, one family of sums each

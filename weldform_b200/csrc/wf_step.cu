@@ -489,10 +489,16 @@ extern "C" int wf_fraser_stage_a(wf_ctx *c)
     WF_CHECK(nb_policy(c));
     if (!c->dens_valid) WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));   // stand-alone density pass gathers x, v, m/rho of the halos
     WF_CHECK(pair_density(c));
-    WF_CHECK(comm_halo_refresh(c, HALO_Q1));                     // m/rho of the halos (rho just advanced)
-    WF_CHECK(pair_rate_stress(c));
-    WF_CHECK(comm_halo_refresh(c, HALO_Q2 | HALO_S));            // m, rho, sigma/rho^2, TIR of the halos
-    WF_CHECK(pair_accel(c));
+    // each halo refresh travels on the communication stream while the interior slots are evaluated; the boundary layers follow
+    int64_t i0 = 0, i1 = c->n_loc;
+    WF_CHECK(comm_halo_begin(c, HALO_Q1, &i0, &i1));             // m/rho of the halos (rho just advanced)
+    WF_CHECK(pair_rate_stress(c, i0, i1));
+    WF_CHECK(comm_halo_end(c));
+    WF_CHECK(pair_rate_stress(c, 0, i0)); WF_CHECK(pair_rate_stress(c, i1, c->n_loc));
+    WF_CHECK(comm_halo_begin(c, HALO_Q2 | HALO_S, &i0, &i1));    // m, rho, sigma/rho^2, TIR of the halos
+    WF_CHECK(pair_accel(c, i0, i1));
+    WF_CHECK(comm_halo_end(c));
+    WF_CHECK(pair_accel(c, 0, i0)); WF_CHECK(pair_accel(c, i1, c->n_loc));
     WF_CHECK(contact_impl(c));
     return 0;
 }

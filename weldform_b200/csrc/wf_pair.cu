@@ -883,7 +883,7 @@ int pair_post_pre(wf_ctx *c)
 {
     WF_PAIR_PRECHECK(c);
     PairArgs a = make_args(c);
-    ProfScope ps(c, PK_THERMAL);
+    ProfScope ps(c, PK_BEGIN);
     if (c->prm.thermal_solver != 0 || c->prm.pl_heating) { k_thermal_pre<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
     return 0;
 }

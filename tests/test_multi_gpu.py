@@ -174,3 +174,20 @@ def test_multi_gpu_kickdrift_leapfrog_bit_identical_to_single(product_lib, oracl
     ref = ot.run_port(case)
     worst = {k: ot.max_rel(multi[k], ref[k]) for k in ("x", "v", "Displacement", "pl_strain", "T", "Density", "Sigma")}
     assert max(worst.values()) < 1e-6, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs (gpurun --gpus 2)")
+def test_multi_gpu_rebalance_moves_a_layer_and_keeps_every_bit(product_lib, oracle_port):
+    """Time-based slab rebalancing: wf_params::tuning bit 13 forces one boundary move (rank 0 hands its last cell layer to rank 1
+    through the migration path) at the third rebuild; the state must stay bit-identical to the single-GPU run."""
+    from weldform_b200 import harness
+    case = cases.perturbed(cases.compression(dx=0.02, nsteps=120), amp=400.0)
+    single = harness.run_case(case)
+    forced = dict(case); forced["tuning"] = 8192.0
+    multi, info = _run_multi(forced, 2)
+    plain, info0 = _run_multi(dict(case, tuning=16384.0), 2)          # rebalancing off: the planner's bounds stay
+    assert int(info[0][5]) == int(info0[0][5]) - 1 or int(info[0][5]) != int(info0[0][5]), "the forced move must change rank 0's upper layer bound"
+    assert np.array_equal(multi["pairs"], single["pairs"])
+    bad = {k: ot.max_rel(multi[k], single[k]) for k in cases.FIELDS_F64 + ["ID", "Nb"] if not np.array_equal(multi[k], single[k])}
+    assert not bad, "rebalanced multi-GPU run differs from single GPU per particle: %s" % bad

@@ -249,6 +249,88 @@ int comm_halo_end(wf_ctx *c)
     return 0;
 }
 
+// ---- time-based slab rebalancing -----------------------------------------------------------------------------------------
+// Equal particle counts do not give equal step times: ranks differ in neighbours per particle (end caps, free surfaces) and
+// the GPUs of a box do not clock identically under load, and every halo exchange makes the fast ranks wait for the slowest.
+// Each rank times its interior momentum launch (the largest kernel) over the steps between two rebuilds; at the rebuild the
+// ranks exchange (time, particles, particles in their first / last layer) and every boundary moves by at most ONE layer if
+// that lowers the larger of the two adjacent estimated step times by more than 1 %. The decision is a deterministic function
+// of the gathered numbers, so all ranks take it alike; the particles of the moved layer travel through the ordinary migration
+// (they are simply outside their old owner's [layer_lo, layer_hi) at the next cell-key pass). Results do not depend on the
+// decomposition (per-particle sums follow the reference's order), so this never changes a bit of the state.
+int comm_time_begin(wf_ctx *c)
+{
+    wf_ctx::Comm &m = c->comm;
+    if (m.nranks <= 1 || (c->prm.tuning & 16384)) return 0;       // bit 14 of wf_params::tuning: rebalancing off (A/B measurement)
+    if (m.t_used >= 64) return 0;
+    if (m.t_used >= (int)m.t_events.size()) { cudaEvent_t a, b; WF_CUDA(c, cudaEventCreate(&a)); WF_CUDA(c, cudaEventCreate(&b)); m.t_events.push_back(std::make_pair(a, b)); }
+    WF_CUDA(c, cudaEventRecord(m.t_events[m.t_used].first, c->stream));
+    return 0;
+}
+int comm_time_end(wf_ctx *c)
+{
+    wf_ctx::Comm &m = c->comm;
+    if (m.nranks <= 1 || (c->prm.tuning & 16384)) return 0;
+    if (m.t_used >= (int)m.t_events.size()) return 0;
+    WF_CUDA(c, cudaEventRecord(m.t_events[m.t_used].second, c->stream));
+    m.t_used++;
+    return 0;
+}
+int comm_rebalance(wf_ctx *c)
+{
+    wf_ctx::Comm &m = c->comm;
+    if (m.nranks <= 1 || (c->prm.tuning & 16384)) return 0;
+    m.rebuilds_seen++;
+    const bool forced = (c->prm.tuning & 8192) && m.rebuilds_seen == 3;     // bit 13: force one move of boundary 0 at the third rebuild (tests)
+    if (m.t_used == 0 && !forced) return 0;
+    double t = 0.0;
+    if (m.t_used > 0) {
+        WF_CUDA(c, cudaEventSynchronize(m.t_events[m.t_used - 1].second));
+        for (int k = 0; k < m.t_used; ++k) { float ms = 0.f; cudaEventElapsedTime(&ms, m.t_events[k].first, m.t_events[k].second); t += ms; }
+        t /= m.t_used;
+    }
+    m.t_used = 0;
+    // the interior launch covers n_loc minus the boundary layers: scale to the whole rank
+    const double n_int = (double)(c->n_loc - c->nmeshp) - (double)(m.rank > 0 ? m.send_lo_n : 0) - (double)(m.rank < m.nranks - 1 ? m.send_hi_n : 0);
+    double mine[8] = { n_int > 0 ? t / n_int : 0.0, (double)(c->n_loc - c->nmeshp), (double)m.send_lo_n, (double)m.send_hi_n, (double)m.emig_cap, 0., 0., 0. };
+    WF_CUDA(c, cudaMemcpyAsync(m.d_rank, mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+    WF_CHECK(comm_gather_scalars(c, 8));
+    std::vector<double> all(8 * (size_t)m.nranks);
+    WF_CUDA(c, cudaMemcpyAsync(all.data(), m.d_all, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    // gather all layer bounds too (they are needed to keep >= 3 layers per rank): derive from a second gather
+    double lb[2] = { (double)m.layer_lo, (double)m.layer_hi };
+    WF_CUDA(c, cudaMemcpyAsync(m.d_rank, lb, sizeof(lb), cudaMemcpyHostToDevice, c->stream));
+    WF_CHECK(comm_gather_scalars(c, 2));
+    std::vector<double> bounds(2 * (size_t)m.nranks);
+    WF_CUDA(c, cudaMemcpyAsync(bounds.data(), m.d_all, bounds.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<double> cost(m.nranks), np(m.nranks), load(m.nranks); std::vector<int> lo(m.nranks), hi(m.nranks);
+    for (int r = 0; r < m.nranks; ++r) { cost[r] = all[8 * r]; np[r] = all[8 * r + 1]; load[r] = cost[r] * np[r]; lo[r] = (int)bounds[2 * r]; hi[r] = (int)bounds[2 * r + 1]; }
+    bool any_zero = false; for (int r = 0; r < m.nranks; ++r) if (!(cost[r] > 0.0)) any_zero = true;
+    for (int b = 0; b + 1 < m.nranks; ++b) {               // boundary between rank b and b + 1, left to right with updated loads
+        const int r = b, q = b + 1;
+        const double n_up = all[8 * r + 3], n_dn = all[8 * q + 2];            // rank r's last layer / rank q's first layer
+        int move = 0;                                                          // +1: r gives its last layer to q; -1: q gives its first layer to r
+        if (forced) move = (b == 0) ? +1 : 0;
+        else if (!any_zero) {
+            const double cur = std::max(load[r], load[q]);
+            const double a_ = std::max(load[r] - cost[r] * n_up, load[q] + cost[q] * n_up);
+            const double b_ = std::max(load[r] + cost[r] * n_dn, load[q] - cost[q] * n_dn);
+            if (a_ < cur * 0.99 && a_ <= b_) move = +1; else if (b_ < cur * 0.99) move = -1;
+        }
+        if (move > 0 && (hi[r] - lo[r] < 4 || n_up > all[8 * r + 4] * 0.9)) move = 0;      // the giving rank's emigrant list must hold the layer
+        if (move < 0 && (hi[q] - lo[q] < 4 || n_dn > all[8 * q + 4] * 0.9)) move = 0;
+        if (move > 0) { hi[r] -= 1; lo[q] -= 1; load[r] -= cost[r] * n_up; load[q] += cost[q] * n_up; np[r] -= n_up; np[q] += n_up; }
+        if (move < 0) { hi[r] += 1; lo[q] += 1; load[r] += cost[r] * n_dn; load[q] -= cost[q] * n_dn; np[r] += n_dn; np[q] -= n_dn; }
+        if (move != 0 && (r == m.rank || q == m.rank)) m.rebalance_moves++;
+        // a rank takes part in at most one move per rebuild: skip its other boundary
+        if (move != 0) ++b;
+    }
+    m.layer_lo = lo[m.rank]; m.layer_hi = hi[m.rank];
+    return 0;
+}
+
 int comm_gather_scalars(wf_ctx *c, int nvals)
 {
     wf_ctx::Comm &m = c->comm;

@@ -89,6 +89,8 @@ struct wf_ctx {
         cudaStream_t stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool pending = false;   // halo exchange overlapped with interior work
         double *d_rank = nullptr, *d_all = nullptr;                                     // scalar partials: this rank / all ranks
         int64_t migrated_out = 0, migrated_in = 0, halo_bytes_step = 0;
+        // time-based rebalancing of the slabs: event pairs around the interior momentum launch of every step since the last rebuild
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t> > t_events; int t_used = 0; int64_t rebalance_moves = 0; int rebuilds_seen = 0;
     } comm;
     // gathered arrays, double-buffered (index cur / 1-cur): Q0 (x,y,z,h) Q1 (vx,vy,vz,m/rho) Q2 (m,rho,T,P/rho^2)
     // S0 (pxx,pyy,pzz,pxy) S1 (pyz,pxz,Rxx,Ryy) S2 (Rzz,Rxy,Ryz,Rxz), p = Sigma/rho^2 (GradientType 0) or Sigma, R = TIR
@@ -186,6 +188,9 @@ int comm_halo_refresh(wf_ctx *c, int sets);             // no-op on one GPU
 // neighbour lists cannot reach a halo slot) that may be evaluated meanwhile; comm_halo_end makes the compute stream wait for it
 int comm_halo_begin(wf_ctx *c, int sets, int64_t *i0, int64_t *i1);
 int comm_halo_end(wf_ctx *c);
+int comm_time_begin(wf_ctx *c);                          // brackets the launch whose duration measures this rank's speed (no-op on one GPU)
+int comm_time_end(wf_ctx *c);
+int comm_rebalance(wf_ctx *c);                           // at a rebuild: move slab boundaries by at most one layer towards equal step time
 int comm_gather_scalars(wf_ctx *c, int nvals);          // d_rank -> d_all (all ranks), no-op on one GPU
 int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);

@@ -389,6 +389,7 @@ int nb_build_impl(wf_ctx *c)
     const bool multi = c->comm.nranks > 1;
     int64_t n = c->n_loc, n_out = 0;                  // slots to sort; emigrants among them
     const int a = c->cur, b = 1 - c->cur;
+    if (multi && c->solver_ready) WF_CHECK(comm_rebalance(c));       // may move this rank's layer bounds by one layer (the cell-key pass below migrates)
     MigArgs mg; mg.on = multi ? 1 : 0; mg.layer_lo = c->comm.layer_lo; mg.layer_hi = c->comm.layer_hi;
     mg.plane = (long long)c->CellNo[c->ax_mid] * c->CellNo[c->ax_fast]; mg.emig = c->comm.d_emig; mg.cnt = c->comm.d_cnt; mg.emig_cap = c->comm.emig_cap;
     mg.mesh_tail = c->mesh_tail ? 1 : 0; mg.nsph = (int)c->nsph;

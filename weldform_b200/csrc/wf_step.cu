@@ -496,7 +496,9 @@ extern "C" int wf_fraser_stage_a(wf_ctx *c)
     WF_CHECK(comm_halo_end(c));
     WF_CHECK(pair_rate_stress(c, 0, i0)); WF_CHECK(pair_rate_stress(c, i1, c->n_loc));
     WF_CHECK(comm_halo_begin(c, HALO_Q2 | HALO_S, &i0, &i1));    // m, rho, sigma/rho^2, TIR of the halos
+    WF_CHECK(comm_time_begin(c));                                // this rank's speed, for the slab rebalancing at the next rebuild
     WF_CHECK(pair_accel(c, i0, i1));
+    WF_CHECK(comm_time_end(c));
     WF_CHECK(comm_halo_end(c));
     WF_CHECK(pair_accel(c, 0, i0)); WF_CHECK(pair_accel(c, i1, c->n_loc));
     WF_CHECK(contact_impl(c));

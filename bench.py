@@ -250,12 +250,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timed region
-    ctx.run(args.warmup)
+    # ---- device-resident timed region. The clock sampler (nvidia-smi every 100 ms) starts with the warm-up steps -- the same load --
+    # so that a short multi-GPU timed region (20 steps of a few ms) still has samples taken under load.
+    clocks = ClockSampler(local); clocks.start()
+    ctx.run(max(args.warmup, 3))
     ctx.sync()
+    if world > 1:
+        for _ in range(40):                          # at least ~0.3 s of load before the timed region at small per-GPU sizes
+            ctx.run(2)
+        ctx.sync()
     ctx.prof_enable(True)
     l0 = ctx.launch_count()
-    clocks = ClockSampler(local); clocks.start()
     barrier()
     ev0.record(ext)
     ctx.run(args.steps)

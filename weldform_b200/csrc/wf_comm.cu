@@ -488,7 +488,9 @@ extern "C" int wf_comm_init(wf_ctx *c, int rank, int nranks, const void *id128)
     ncclComm_t comm;
     WF_NCCL(c, A->CommInitRank(&comm, nranks, id, rank));
     c->comm.nccl = comm;
-    WF_CUDA(c, cudaStreamCreateWithFlags(&c->comm.stream, cudaStreamNonBlocking));
+    {   // highest priority: the exchange kernels must get SM slots while the interior pair kernel still has blocks queued
+        int prio_lo = 0, prio_hi = 0; cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        WF_CUDA(c, cudaStreamCreateWithPriority(&c->comm.stream, cudaStreamNonBlocking, prio_hi)); }
     WF_CUDA(c, cudaEventCreateWithFlags(&c->comm.ev_ready, cudaEventDisableTiming)); WF_CUDA(c, cudaEventCreateWithFlags(&c->comm.ev_done, cudaEventDisableTiming));
     WF_CUDA(c, cudaMalloc(&c->comm.d_cnt, 64 * sizeof(int) + 16 * sizeof(long long)));
     WF_CUDA(c, cudaMemset(c->comm.d_cnt, 0, 64 * sizeof(int) + 16 * sizeof(long long)));

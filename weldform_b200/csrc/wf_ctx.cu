@@ -92,6 +92,9 @@ extern "C" void wf_destroy(wf_ctx *c)
     cudaFree(c->stage); if (c->h_stage) cudaFreeHost(c->h_stage); if (c->h_sc) cudaFreeHost(c->h_sc);
     prof_resolve(c); for (auto &e : c->prof_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    if (c->comm.stream) { cudaStreamSynchronize(c->comm.stream); cudaStreamDestroy(c->comm.stream); }
+    if (c->comm.ev_ready) cudaEventDestroy(c->comm.ev_ready); if (c->comm.ev_done) cudaEventDestroy(c->comm.ev_done);
+    for (auto &e : c->comm.t_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaStreamDestroy(c->stream);
     delete c;
 }

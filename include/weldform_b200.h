@@ -207,6 +207,10 @@ int wf_plan_slabs(const double *x, const double *h, int64_t n, int kernel_type, 
 /* Same with rigid meshes: x, h = the n_sph SPH particles followed by the element particles (centroid, (float)hfac*radius), which
  * shape the cell grid like every particle does (Neighbour.cpp:10-139) but are not distributed: each rank is given ALL meshes
  * (wf_add_mesh) and keeps a replica of their element particles; rank_of = -1 for them. */
+/* Host-only: the slab-boundary moves the library's time-based rebalancing (at every neighbour rebuild; each boundary by at most one
+ * cell layer towards equal step time) would decide from per-rank statistics: 8 doubles per rank = seconds per particle, particles,
+ * particles in the first layer, in the last layer, emigrant-list capacity, 3 unused. bounds (nranks + 1 layer indices) is updated in place. */
+int wf_plan_rebalance(const double *stats, int nranks, int32_t *bounds);
 int wf_plan_slabs_ex(const double *x, const double *h, int64_t n, int64_t n_sph, int kernel_type, const double dom_min[3], const double dom_max[3],
                      int nranks, int32_t *rank_of, int32_t *bounds);
 

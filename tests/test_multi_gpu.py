@@ -67,6 +67,25 @@ def test_slab_planner_properties(product_lib, nranks):
     assert (np.diff(rank_of[order]) >= 0).all()
 
 
+def test_rebalance_decision_moves_one_layer_towards_the_slow_rank(product_lib):
+    """wf_plan_rebalance (host-only, the same code the ranks run at a rebuild): a rank that takes 20 % longer per particle hands one
+    boundary layer to a neighbour; balanced ranks keep their bounds; nobody drops below 3 layers; at most one move per rank."""
+    from weldform_b200 import api
+    n, layer = 1.0e6, 5.0e4
+    def stats(costs):
+        return np.array([[c, n, layer, layer, 1.0e5, 0, 0, 0] for c in costs])
+    b0 = np.array([0, 20, 40, 60, 80], np.int32)
+    assert np.array_equal(api.plan_rebalance(stats([1e-9] * 4), b0), b0)
+    b = api.plan_rebalance(stats([1e-9, 1.2e-9, 1e-9, 1e-9]), b0)
+    assert (b[2] - b[1]) == 19 and b[0] == 0 and b[4] == 80 and np.abs(b - b0).sum() == 1     # the slow rank gives up exactly one layer
+    b = api.plan_rebalance(stats([1.3e-9, 1e-9, 1e-9, 1.3e-9]), b0)
+    assert b[1] == 19 and b[3] == 61                                                        # both ends shed a layer inwards
+    small = np.array([0, 3, 6, 9, 12], np.int32)
+    assert np.array_equal(api.plan_rebalance(stats([2e-9, 1e-9, 1e-9, 1e-9]), small), small)  # < 4 layers: no move
+    tiny_cap = stats([2e-9, 1e-9, 1e-9, 1e-9]); tiny_cap[:, 4] = 1.0e4
+    assert np.array_equal(api.plan_rebalance(tiny_cap, b0), b0)                                 # the layer would not fit the emigrant list
+
+
 def test_planner_rejects_more_ranks_than_layers(product_lib):
     from weldform_b200 import api
     pts = np.array([[0.0, 0.0, 0.0], [0.01, 0.0, 0.0], [0.02, 0.0, 0.0]])

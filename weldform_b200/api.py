@@ -100,6 +100,7 @@ def load_library():
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
         "wf_comm_unique_id": ([vp], C.c_int), "wf_comm_init": ([vp, C.c_int, C.c_int, vp], C.c_int), "wf_comm_info": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "wf_plan_slabs": ([_PD, _PD, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
+        "wf_plan_rebalance": ([_PD, C.c_int, _PI], C.c_int),
         "wf_plan_slabs_ex": ([_PD, _PD, C.c_int64, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
         "wf_get_stream": ([vp], vp), "wf_measure_fp64_peak": ([vp, _PD], C.c_int),
         "wf_prof_name": ([C.c_int], C.c_char_p), "wf_launch_count": ([vp, C.POINTER(C.c_int64)], C.c_int),
@@ -166,6 +167,16 @@ def plan_slabs(x, h, nranks, kernel_type=0, dom_min=None, dom_max=None, n_sph=No
     if rc != 0:
         raise WeldformError("wf_plan_slabs failed (%d): fewer cell layers than ranks, or bad arguments" % rc)
     return rank_of, bounds
+
+
+def plan_rebalance(stats, bounds):
+    """Host-only (wf_plan_rebalance): stats[nranks, 8], bounds[nranks + 1] -> new bounds."""
+    L = load_library()
+    st = np.ascontiguousarray(stats, np.float64).reshape(-1, 8); b = np.ascontiguousarray(bounds, np.int32).copy()
+    rc = L.wf_plan_rebalance(_dp(st), len(st), _ip(b))
+    if rc != 0:
+        raise WeldformError("wf_plan_rebalance failed (%d)" % rc)
+    return b
 
 
 class Context:

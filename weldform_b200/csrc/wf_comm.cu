@@ -258,6 +258,31 @@ int comm_halo_end(wf_ctx *c)
 // of the gathered numbers, so all ranks take it alike; the particles of the moved layer travel through the ordinary migration
 // (they are simply outside their old owner's [layer_lo, layer_hi) at the next cell-key pass). Results do not depend on the
 // decomposition (per-particle sums follow the reference's order), so this never changes a bit of the state.
+// stats: 8 doubles per rank = time per particle, particles, particles in the first layer, in the last layer, emigrant-list capacity, -, -, -
+static void rebalance_decide(int nranks, const double *all, bool forced, std::vector<int> &lo, std::vector<int> &hi)
+{
+    std::vector<double> cost(nranks), load(nranks);
+    bool any_zero = false;
+    for (int r = 0; r < nranks; ++r) { cost[r] = all[8 * r]; load[r] = cost[r] * all[8 * r + 1]; if (!(cost[r] > 0.0)) any_zero = true; }
+    for (int b = 0; b + 1 < nranks; ++b) {               // boundary between rank b and b + 1, left to right with updated loads
+        const int r = b, q = b + 1;
+        const double n_up = all[8 * r + 3], n_dn = all[8 * q + 2];            // rank r's last layer / rank q's first layer
+        int move = 0;                                                          // +1: r gives its last layer to q; -1: q gives its first layer to r
+        if (forced) move = (b == 0) ? +1 : 0;
+        else if (!any_zero) {
+            const double cur = std::max(load[r], load[q]);
+            const double a_ = std::max(load[r] - cost[r] * n_up, load[q] + cost[q] * n_up);
+            const double b_ = std::max(load[r] + cost[r] * n_dn, load[q] - cost[q] * n_dn);
+            if (a_ < cur * 0.99 && a_ <= b_) move = +1; else if (b_ < cur * 0.99) move = -1;
+        }
+        if (move > 0 && (hi[r] - lo[r] < 4 || n_up > all[8 * r + 4] * 0.9)) move = 0;      // the giving rank's emigrant list must hold the layer
+        if (move < 0 && (hi[q] - lo[q] < 4 || n_dn > all[8 * q + 4] * 0.9)) move = 0;
+        if (move > 0) { hi[r] -= 1; lo[q] -= 1; load[r] -= cost[r] * n_up; load[q] += cost[q] * n_up; }
+        if (move < 0) { hi[r] += 1; lo[q] += 1; load[r] += cost[r] * n_dn; load[q] -= cost[q] * n_dn; }
+        if (move != 0) ++b;                              // a rank takes part in at most one move per rebuild: skip its other boundary
+    }
+}
+
 int comm_time_begin(wf_ctx *c)
 {
     wf_ctx::Comm &m = c->comm;
@@ -305,28 +330,11 @@ int comm_rebalance(wf_ctx *c)
     std::vector<double> bounds(2 * (size_t)m.nranks);
     WF_CUDA(c, cudaMemcpyAsync(bounds.data(), m.d_all, bounds.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     WF_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::vector<double> cost(m.nranks), np(m.nranks), load(m.nranks); std::vector<int> lo(m.nranks), hi(m.nranks);
-    for (int r = 0; r < m.nranks; ++r) { cost[r] = all[8 * r]; np[r] = all[8 * r + 1]; load[r] = cost[r] * np[r]; lo[r] = (int)bounds[2 * r]; hi[r] = (int)bounds[2 * r + 1]; }
-    bool any_zero = false; for (int r = 0; r < m.nranks; ++r) if (!(cost[r] > 0.0)) any_zero = true;
-    for (int b = 0; b + 1 < m.nranks; ++b) {               // boundary between rank b and b + 1, left to right with updated loads
-        const int r = b, q = b + 1;
-        const double n_up = all[8 * r + 3], n_dn = all[8 * q + 2];            // rank r's last layer / rank q's first layer
-        int move = 0;                                                          // +1: r gives its last layer to q; -1: q gives its first layer to r
-        if (forced) move = (b == 0) ? +1 : 0;
-        else if (!any_zero) {
-            const double cur = std::max(load[r], load[q]);
-            const double a_ = std::max(load[r] - cost[r] * n_up, load[q] + cost[q] * n_up);
-            const double b_ = std::max(load[r] + cost[r] * n_dn, load[q] - cost[q] * n_dn);
-            if (a_ < cur * 0.99 && a_ <= b_) move = +1; else if (b_ < cur * 0.99) move = -1;
-        }
-        if (move > 0 && (hi[r] - lo[r] < 4 || n_up > all[8 * r + 4] * 0.9)) move = 0;      // the giving rank's emigrant list must hold the layer
-        if (move < 0 && (hi[q] - lo[q] < 4 || n_dn > all[8 * q + 4] * 0.9)) move = 0;
-        if (move > 0) { hi[r] -= 1; lo[q] -= 1; load[r] -= cost[r] * n_up; load[q] += cost[q] * n_up; np[r] -= n_up; np[q] += n_up; }
-        if (move < 0) { hi[r] += 1; lo[q] += 1; load[r] += cost[r] * n_dn; load[q] -= cost[q] * n_dn; np[r] += n_dn; np[q] -= n_dn; }
-        if (move != 0 && (r == m.rank || q == m.rank)) m.rebalance_moves++;
-        // a rank takes part in at most one move per rebuild: skip its other boundary
-        if (move != 0) ++b;
-    }
+    std::vector<int> lo(m.nranks), hi(m.nranks);
+    for (int r = 0; r < m.nranks; ++r) { lo[r] = (int)bounds[2 * r]; hi[r] = (int)bounds[2 * r + 1]; }
+    const int lo_before = lo[m.rank], hi_before = hi[m.rank];
+    rebalance_decide(m.nranks, all.data(), forced, lo, hi);
+    if (lo[m.rank] != lo_before || hi[m.rank] != hi_before) m.rebalance_moves++;
     m.layer_lo = lo[m.rank]; m.layer_hi = hi[m.rank];
     return 0;
 }
@@ -503,6 +511,20 @@ extern "C" int wf_comm_info(wf_ctx *c, int64_t out[8])
     if (!c || !out) return WF_ERR_ARG;
     out[0] = c->n_loc; out[1] = c->n - c->n_loc; out[2] = c->comm.migrated_out; out[3] = c->comm.migrated_in;
     out[4] = c->comm.layer_lo; out[5] = c->comm.layer_hi; out[6] = c->comm.halo_bytes_step; out[7] = c->CellNo[c->ax_slow];
+    return 0;
+}
+
+// Host-only: the boundary moves comm_rebalance would decide from the gathered per-rank statistics (8 doubles per rank: time per
+// particle, particles, particles in the first / last layer, emigrant-list capacity, 3 unused); bounds = nranks + 1 layer indices,
+// updated in place. Same code as the library's collective; exposed for CPU tests and for drivers that want to log the decision.
+extern "C" int wf_plan_rebalance(const double *stats, int nranks, int32_t *bounds)
+{
+    if (!stats || !bounds || nranks < 1) return WF_ERR_ARG;
+    std::vector<int> lo(nranks), hi(nranks);
+    for (int r = 0; r < nranks; ++r) { lo[r] = bounds[r]; hi[r] = bounds[r + 1]; }
+    wf::rebalance_decide(nranks, stats, false, lo, hi);
+    for (int r = 0; r < nranks; ++r) bounds[r] = lo[r];
+    bounds[nranks] = hi[nranks - 1];
     return 0;
 }
 

@@ -119,6 +119,16 @@ __device__ inline double pow4_cr(double r)
 // Domain.cpp:1528-1570: tensile-instability tensor from Sigma and rho
 __device__ inline void tir_of(const S6 &sg, double rho, double TI, double out[6])
 {
+    // No principal stress is positive <=> Sigma is negative semi-definite; then every Val(k,k) below is 0 and TIR = Vec*0*Vec^T = 0
+    // whatever the eigenvectors are. Sylvester's criterion on -Sigma with margins nine orders of magnitude above the Jacobi
+    // iteration's round-off (all leading minors > 1e-6 * scale^k  =>  every eigenvalue < -1e-7 * scale) decides the common
+    // compressive state without the eigen-solve, which costs as much as a third of the pair walk of this pass.
+    {
+        const double sc = fmax(fmax(fabs(sg.xx), fabs(sg.yy)), fmax(fmax(fabs(sg.zz), fabs(sg.xy)), fmax(fabs(sg.yz), fabs(sg.xz))));
+        const double m2 = sg.xx * sg.yy - sg.xy * sg.xy;
+        const double det = sg.xx * (sg.yy * sg.zz - sg.yz * sg.yz) - sg.xy * (sg.xy * sg.zz - sg.yz * sg.xz) + sg.xz * (sg.xy * sg.yz - sg.yy * sg.xz);
+        if (-sg.xx > 1e-6 * sc && m2 > 1e-6 * sc * sc && -det > 1e-6 * sc * sc * sc) { for (int k = 0; k < 6; ++k) out[k] = 0.0; return; }
+    }
     const double rho2 = rho * rho;
     const double pc = TI / (rho2);
     double d[3]; M3 Vec; sym_eig3(m3sym(sg), d, Vec);
@@ -185,9 +195,11 @@ __global__ void __launch_bounds__(128) k_gradcorr(PairArgs a)
     for (int k = 0; k < 9; ++k) OWN(F_GC + k) = Mi[k];
 }
 
-// ---- StartAcceleration's tensile-instability tensor (Domain.cpp:1528-1570) as a stand-alone pass: the KickDrift / LeapFrog step
-// orders evaluate the momentum sums first, with the TIR of the stresses and densities the previous step left behind
-__global__ void k_tir(PairArgs a)
+// ---- StartAcceleration's tensile-instability tensor (Domain.cpp:1528-1570) as a per-particle pass of its own. The eigen-solve is
+// register-hungry and as long as a third of a pair walk: kept out of k_post it runs at full occupancy and leaves k_post its registers.
+// HANDOVER = true (Fraser step): the tensor of the NEXT step, written to F_TN only (the prologue hands it over);
+// HANDOVER = false (KickDrift / LeapFrog: momentum sums first): also written to the gathered arrays
+template <bool HANDOVER> __global__ void __launch_bounds__(128) k_tir(PairArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
@@ -196,8 +208,10 @@ __global__ void k_tir(PairArgs a)
     if (!(TI > 0.0) || (a.is_free && !a.is_free[s])) return;
     S6 sg; sg.xx = OWN(F_SG); sg.yy = OWN(F_SG + 1); sg.zz = OWN(F_SG + 2); sg.xy = OWN(F_SG + 3); sg.yz = OWN(F_SG + 4); sg.xz = OWN(F_SG + 5);
     double t[6]; tir_of(sg, a.Q2[s].y, TI, t);
-    ((double2 *)&a.S1[s])[1] = make_double2(t[0], t[1]);
-    a.S2[s] = make_double4(t[2], t[3], t[4], t[5]);
+    if (!HANDOVER) {            // StartAcceleration proper: the gathered copy is needed by the momentum pass that follows
+        ((double2 *)&a.S1[s])[1] = make_double2(t[0], t[1]);
+        a.S2[s] = make_double4(t[2], t[3], t[4], t[5]);
+    }
     for (int k = 0; k < 6; ++k) OWN(F_TN + k) = t[k];
 }
 
@@ -736,11 +750,6 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __gl
     if (DENS) {
         if (!gc) dd *= di;
         OWN(F_DDN) = dd;
-        if (a.any_ti && cpi.TI > 0.0 && !(a.is_free && !a.is_free[s])) {      // StartAcceleration: TIR for free particles only
-            S6 sg; sg.xx = OWN(F_SG); sg.yy = OWN(F_SG + 1); sg.zz = OWN(F_SG + 2); sg.xy = OWN(F_SG + 3); sg.yz = OWN(F_SG + 4); sg.xz = OWN(F_SG + 5);
-            double t[6]; tir_of(sg, di, cpi.TI, t);
-            for (int k = 0; k < 6; ++k) OWN(F_TN + k) = t[k];
-        }
     }
 }
 
@@ -807,7 +816,7 @@ int pair_tir(wf_ctx *c)
     if (!c->any_ti) return 0;
     PairArgs a = make_args(c);
     ProfScope ps(c, PK_BEGIN);
-    k_tir<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    k_tir<false><<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
 // CheckMinTSVel: this rank's min of CFL*dmin/(Cs+|v|) (blocking read-back)
@@ -835,6 +844,7 @@ int pair_density(wf_ctx *c)
     if (!c->dens_valid) {
         if (fast_path(c)) WF_LAUNCH_PF(k_post, true, false, false, true); else WF_LAUNCH_PF(k_post, false, false, false, true);
         WF_LAUNCH_CHECK(c); c->launches++;
+        if (c->any_ti) { k_tir<true><<<g, 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
     }
     k_prologue<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
     c->dens_valid = false;
@@ -911,6 +921,7 @@ int pair_post_range(wf_ctx *c, bool skip_dens, int64_t lo, int64_t hi)
     else if (th) { if (fast) WF_LAUNCH_PF(k_post, true, true, true, true); else WF_LAUNCH_PF(k_post, false, true, true, true); }
     else    { if (fast) WF_LAUNCH_PF(k_post, true, false, true, true); else WF_LAUNCH_PF(k_post, false, false, true, true); }
     WF_LAUNCH_CHECK(c); c->launches++;
+    if (c->any_ti) { k_tir<true><<<g, 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }      // the next step's TIR, same slot range
     return 0;
 }
 // CalcPlasticWorkHeat + ThermalCalcs, then CalcKinEnergyEqn + CalcIntEnergyEqn, then next step's density rate: one walk.

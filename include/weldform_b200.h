@@ -152,6 +152,13 @@ int wf_download(wf_ctx *ctx, wf_field f, void *host);                 /* blockin
 int wf_upload(wf_ctx *ctx, wf_field f, const void *host);             /* blocking; X,V,A,DENSITY,T,SIGMAY,ID only */
 int wf_download_subset(wf_ctx *ctx, wf_field f, const int32_t *idx, int64_t n, void *host);   /* callback bridge */
 int wf_upload_subset(wf_ctx *ctx, wf_field f, const int32_t *idx, int64_t n, const void *host);
+/* Registered subsets: a GeneralAfter callback touches the same tagged particles every step; their index list (local creation order)
+ * is kept on the device so that the per-step bridge moves field values only. Indices refer to this rank's current particles:
+ * register again after particles migrated between ranks (wf_comm_info). */
+int wf_subset_register(wf_ctx *ctx, const int32_t *idx, int64_t n, int *handle);
+int wf_subset_release(wf_ctx *ctx, int handle);
+int wf_download_registered(wf_ctx *ctx, wf_field f, int handle, void *host);
+int wf_upload_registered(wf_ctx *ctx, wf_field f, int handle, const void *host);
 int wf_mesh_download(wf_ctx *ctx, int mesh, double *nodes, double *normals, double *pplane);
 
 /* ---- hot path, one call per phase of the Fraser step (SolverFraser.cpp:133-505) -------------------------------- */

@@ -73,7 +73,7 @@ def _read_bin(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sync,solver", [("full", 0), ("tagged", 0), ("tagged", 1), ("tagged", 2)])
+@pytest.mark.parametrize("sync,solver", [("full", 0), ("tagged", 0), ("push", 0), ("tagged", 1), ("tagged", 2)])
 def test_host_domain_driver_matches_device_run_and_oracle(host_example, oracle_port, sync, solver):
     """The C++ driver (host GeneralAfter callback between the stages of SolveDiffUpdateFraser / KickDrift / LeapFrog) against the
     device-BC run of the same case and against the oracle."""

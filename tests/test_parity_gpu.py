@@ -258,6 +258,27 @@ def test_subset_bridge_round_trip(harness):
         ctx.close()
 
 
+def test_registered_subset_bridge(harness):
+    """wf_subset_register keeps a callback's index list on the device: registered up/downloads equal the index-list calls."""
+    from weldform_b200 import api
+    case = cases.perturbed(cases.compression(dx=0.03, nsteps=1), amp=60.0)
+    ctx, info = harness.context_from_case(case)
+    try:
+        ctx.solver_init(float(case["dt"])); ctx.run(3)
+        idx = np.array([5, 17, 1200, 3, 999], np.int32)
+        h = ctx.subset_register(idx)
+        a = ctx.download("v", idx); b = ctx.download_registered("v", h, np.empty((len(idx), 3)))
+        assert np.array_equal(a.reshape(-1), b.reshape(-1))
+        new = np.arange(15, dtype=np.float64).reshape(5, 3)
+        ctx.upload_registered("v", h, new)
+        assert np.array_equal(ctx.download("v", idx).reshape(-1), new.reshape(-1))
+        full = ctx.download("v").reshape(-1, 3)
+        assert np.array_equal(full[idx], new)
+        ctx.subset_release(h)
+    finally:
+        ctx.close()
+
+
 def test_phase_api_equals_fused_run(harness):
     """Driving the step phase by phase (what the host Domain::SolveDiffUpdateFraser mirror does around its GeneralAfter
     callbacks) gives the same bits as wf_fraser_run."""

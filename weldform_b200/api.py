@@ -100,6 +100,8 @@ def load_library():
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
         "wf_comm_unique_id": ([vp], C.c_int), "wf_comm_init": ([vp, C.c_int, C.c_int, vp], C.c_int), "wf_comm_info": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "wf_plan_slabs": ([_PD, _PD, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
+        "wf_subset_register": ([vp, _PI, C.c_int64, C.POINTER(C.c_int)], C.c_int), "wf_subset_release": ([vp, C.c_int], C.c_int),
+        "wf_download_registered": ([vp, C.c_int, C.c_int, C.c_void_p], C.c_int), "wf_upload_registered": ([vp, C.c_int, C.c_int, C.c_void_p], C.c_int),
         "wf_plan_rebalance": ([_PD, C.c_int, _PI], C.c_int),
         "wf_plan_slabs_ex": ([_PD, _PD, C.c_int64, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
         "wf_get_stream": ([vp], vp), "wf_measure_fp64_peak": ([vp, _PD], C.c_int),
@@ -299,6 +301,24 @@ class Context:
         else:
             idx = np.ascontiguousarray(idx, np.int32)
             self._ck(self.L.wf_upload_subset(self.h, fid, _ip(idx), len(idx), data.ctypes.data_as(C.c_void_p)), "wf_upload_subset(%s)" % name)
+
+    def subset_register(self, idx):
+        """Keep an index list (local creation order) on the device; returns a handle for download_registered / upload_registered."""
+        idx = np.ascontiguousarray(idx, np.int32); h = C.c_int()
+        self._ck(self.L.wf_subset_register(self.h, _ip(idx), len(idx), C.byref(h)), "wf_subset_register")
+        return int(h.value)
+
+    def subset_release(self, handle):
+        self._ck(self.L.wf_subset_release(self.h, int(handle)), "wf_subset_release")
+
+    def download_registered(self, name, handle, out):
+        fid = FIELDS[name][0]
+        self._ck(self.L.wf_download_registered(self.h, fid, int(handle), out.ctypes.data_as(C.c_void_p)), "wf_download_registered(%s)" % name)
+        return out
+
+    def upload_registered(self, name, handle, data):
+        fid = FIELDS[name][0]
+        self._ck(self.L.wf_upload_registered(self.h, fid, int(handle), data.ctypes.data_as(C.c_void_p)), "wf_upload_registered(%s)" % name)
 
     def mesh_download(self, mesh, n_nodes, n_elems):
         nodes = np.empty((n_nodes, 3)); normals = np.empty((n_elems, 3)); pp = np.empty(n_elems)

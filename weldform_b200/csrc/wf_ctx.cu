@@ -89,6 +89,7 @@ extern "C" void wf_destroy(wf_ctx *c)
     cudaFree(c->dm.enormal); cudaFree(c->dm.ev); cudaFree(c->dm.pplane); cudaFree(c->dm.motion);
     cudaFree(c->comm.d_emig); cudaFree(c->comm.d_cnt); cudaFree(c->comm.d_rank); cudaFree(c->comm.d_all);
     for (int d = 0; d < 2; ++d) { cudaFree(c->comm.stage_send[d]); cudaFree(c->comm.stage_recv[d]); }
+    for (auto &sb : c->subsets) cudaFree(sb.first);
     cudaFree(c->stage); if (c->h_stage) cudaFreeHost(c->h_stage); if (c->h_sc) cudaFreeHost(c->h_sc);
     prof_resolve(c); for (auto &e : c->prof_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -521,20 +522,20 @@ static FieldView view_of(wf_ctx *c)
     v.F = c->F[c->cur]; v.I = c->I[c->cur]; v.cap = c->cap; return v;
 }
 
-static int download_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, void *host)
+static int download_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, void *host, const int *dev_idx = nullptr)
 {
     if (!c || !host) return WF_ERR_ARG;
     if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_download: no particles");
     if (f < 0 || f >= WF_F_COUNT) return fail(c, WF_ERR_ARG, "wf_download: bad field %d", (int)f);
     cudaSetDevice(c->device);
     const int nc = field_ncomp(f); const bool isint = field_is_int(f);
-    const int64_t cnt = idx ? nidx : c->n_loc;
+    const int64_t cnt = (idx || dev_idx) ? nidx : c->n_loc;
     if (cnt == 0) return 0;
     const size_t bytes = (size_t)cnt * nc * (isint ? 4 : 8);
     const size_t idx_bytes = idx ? (((size_t)nidx * 4 + 255) / 256) * 256 : 0;
     WF_CHECK(ensure_stage(c, bytes + idx_bytes));
-    int *d_idx = nullptr;
-    if (idx) { d_idx = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(d_idx, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); }
+    const int *d_idx = dev_idx;
+    if (idx) { int *t_ = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(t_, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); d_idx = t_; }
     k_download<<<grid_for(cnt, 256), 256, 0, c->stream>>>(view_of(c), (int)f, nc, isint ? 1 : 0, c->n_loc, c->Ip(I_LID), c->slot_of, d_idx, nidx, c->stage);
     WF_LAUNCH_CHECK(c);
     WF_CUDA(c, cudaMemcpyAsync(host, c->stage, bytes, cudaMemcpyDeviceToHost, c->stream));
@@ -563,7 +564,7 @@ __global__ void k_upload(double4 *Q0, double4 *Q1, double4 *Q2, double *F, int *
     default: break;
     }
 }
-static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, const void *host)
+static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, const void *host, const int *dev_idx = nullptr)
 {
     if (!c || !host) return WF_ERR_ARG;
     if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_upload: no particles");
@@ -571,13 +572,13 @@ static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, 
         default: return fail(c, WF_ERR_UNSUPPORTED, "wf_upload: field %d is not uploadable", (int)f); }
     cudaSetDevice(c->device);
     const int nc = field_ncomp(f); const bool isint = field_is_int(f);
-    const int64_t cnt = idx ? nidx : c->n_loc;
+    const int64_t cnt = (idx || dev_idx) ? nidx : c->n_loc;
     if (cnt == 0) return 0;
     const size_t bytes = (((size_t)cnt * nc * (isint ? 4 : 8) + 255) / 256) * 256;
     WF_CHECK(ensure_stage(c, bytes + (idx ? (size_t)nidx * 4 : 0)));
     WF_CUDA(c, cudaMemcpyAsync(c->stage, host, (size_t)cnt * nc * (isint ? 4 : 8), cudaMemcpyHostToDevice, c->stream));
-    int *d_idx = nullptr;
-    if (idx) { d_idx = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(d_idx, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); }
+    const int *d_idx = dev_idx;
+    if (idx) { int *t_ = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(t_, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); d_idx = t_; }
     k_upload<<<grid_for(cnt, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->F[c->cur], c->I[c->cur], c->cap, (int)f, c->n_loc, c->slot_of, d_idx, nidx, c->stage);
     WF_LAUNCH_CHECK(c);
     WF_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -587,6 +588,37 @@ static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, 
 extern "C" int wf_upload(wf_ctx *c, wf_field f, const void *host) { return upload_impl(c, f, nullptr, 0, host); }
 extern "C" int wf_upload_subset(wf_ctx *c, wf_field f, const int32_t *idx, int64_t n, const void *host)
 { if (n > 0 && !idx) return WF_ERR_ARG; return upload_impl(c, f, idx, n, host); }
+
+// Registered subsets: the index list of a callback's tagged particles lives on the device, so that the per-step bridge moves field
+// values only (the reference's GeneralAfter callbacks touch the same particles every step)
+extern "C" int wf_subset_register(wf_ctx *c, const int32_t *idx, int64_t n, int *handle)
+{
+    if (!c || !handle || n < 0 || (n > 0 && !idx)) return WF_ERR_ARG;
+    cudaSetDevice(c->device);
+    int *d = nullptr;
+    if (n > 0) { WF_CUDA(c, cudaMalloc(&d, (size_t)n * sizeof(int))); WF_CUDA(c, cudaMemcpy(d, idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice)); }
+    c->subsets.push_back(std::make_pair(d, n));
+    *handle = (int)c->subsets.size() - 1;
+    return 0;
+}
+extern "C" int wf_subset_release(wf_ctx *c, int handle)
+{
+    if (!c || handle < 0 || handle >= (int)c->subsets.size()) return WF_ERR_ARG;
+    cudaFree(c->subsets[handle].first); c->subsets[handle] = std::make_pair((int *)nullptr, (int64_t)0);
+    return 0;
+}
+extern "C" int wf_download_registered(wf_ctx *c, wf_field f, int handle, void *host)
+{
+    if (!c || handle < 0 || handle >= (int)c->subsets.size()) return WF_ERR_ARG;
+    if (c->subsets[handle].second == 0) return 0;
+    return download_impl(c, f, nullptr, c->subsets[handle].second, host, c->subsets[handle].first);
+}
+extern "C" int wf_upload_registered(wf_ctx *c, wf_field f, int handle, const void *host)
+{
+    if (!c || handle < 0 || handle >= (int)c->subsets.size()) return WF_ERR_ARG;
+    if (c->subsets[handle].second == 0) return 0;
+    return upload_impl(c, f, nullptr, c->subsets[handle].second, host, c->subsets[handle].first);
+}
 
 extern "C" int wf_mesh_download(wf_ctx *c, int mesh, double *nodes, double *normals, double *pplane)
 {

@@ -134,6 +134,7 @@ struct wf_ctx {
     double dt = 0.0, time = 0.0; int ts_i = 0; bool isfirst = true, isyielding = false, nb_cleared = true;
     int64_t steps = 0, nb_rebuilds = 0, launches = 0; bool in_step = false;
     double step_max_pl = 0.0;                    // `max` of SolverFraser.cpp:139-149 for the step in flight
+    std::vector<std::pair<int *, int64_t> > subsets;     // registered index lists of the callback bridge (device copies)
     // staging
     void *stage = nullptr; size_t stage_bytes = 0; void *h_stage = nullptr; size_t h_stage_bytes = 0;
     // profiling

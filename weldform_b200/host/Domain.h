@@ -17,6 +17,8 @@
 //           downloaded before the callback; v and a of all particles are uploaded after it;
 //   tagged  only particles whose ID differs from the most common ID (the boundary-condition rows of the usual drivers,
 //           e.g. ID 2/3 in examples/Compression_thermal.cpp:30-66) are mirrored -- O(surface) traffic instead of O(N);
+//   push    like tagged, but nothing is read back before the callback: for callbacks that only ASSIGN whole v and a vectors of their
+//           boundary rows (examples/Compression_thermal.cpp:30-66 does); v and a of the tagged rows are uploaded after it;
 //   none    the callback only sees scalars (time, max_disp, contact_force_sum) and trimesh[m]->SetVel.
 // Rigid-mesh velocities set from the callback (trimesh[m]->SetVel / SetRotAxisVel) are always forwarded.
 #ifndef WF_HOST_DOMAIN_H
@@ -130,7 +132,7 @@ public:
 
 private:
     double Time = 0.0;
-    enum SyncMode { SYNC_FULL = 0, SYNC_TAGGED = 1, SYNC_NONE = 2 } sync_mode = SYNC_FULL;
+    enum SyncMode { SYNC_FULL = 0, SYNC_TAGGED = 1, SYNC_NONE = 2, SYNC_PUSH = 3 } sync_mode = SYNC_FULL;
     std::vector<int32_t> sync_idx;             // creation indices mirrored around callbacks (empty + SYNC_FULL: everything)
     std::vector<double> buf3, buf9, buf1;
     std::vector<Vec3_t> sent_mv, sent_mw;
@@ -229,8 +231,9 @@ inline void Domain::choose_sync()
     sync_mode = SYNC_FULL;
     if (m && std::strcmp(m, "tagged") == 0) sync_mode = SYNC_TAGGED;
     if (m && std::strcmp(m, "none") == 0) sync_mode = SYNC_NONE;
+    if (m && std::strcmp(m, "push") == 0) sync_mode = SYNC_PUSH;
     sync_idx.clear();
-    if (sync_mode == SYNC_TAGGED) {
+    if (sync_mode == SYNC_TAGGED || sync_mode == SYNC_PUSH) {
         std::map<int, size_t> hist;
         for (int i = 0; i < solid_part_count; ++i) hist[Particles[i]->ID]++;
         int bulk = 0; size_t best = 0;
@@ -343,7 +346,7 @@ inline void Domain::put3(wf_field f, Vec3_t Particle::*mem, bool subset)
 inline void Domain::sync_down(bool everything)
 {
     const bool subset = !everything && sync_mode == SYNC_TAGGED;
-    if (!everything && sync_mode == SYNC_NONE) return;
+    if (!everything && (sync_mode == SYNC_NONE || sync_mode == SYNC_PUSH)) return;
     get3(WF_F_X, &Particle::x, subset); get3(WF_F_V, &Particle::v, subset); get3(WF_F_A, &Particle::a, subset);
     get3(WF_F_DISPLACEMENT, &Particle::Displacement, subset); get9(WF_F_SIGMA, &Particle::Sigma, subset);
     get1(WF_F_T, &Particle::T, subset); get1(WF_F_PL_STRAIN, &Particle::pl_strain, subset); get1(WF_F_DENSITY, &Particle::Density, subset);
@@ -366,7 +369,7 @@ inline void Domain::sync_down(bool everything)
 inline void Domain::sync_up()
 {
     if (sync_mode == SYNC_NONE) return;
-    const bool subset = sync_mode == SYNC_TAGGED;
+    const bool subset = sync_mode == SYNC_TAGGED || sync_mode == SYNC_PUSH;
     put3(WF_F_V, &Particle::v, subset); put3(WF_F_A, &Particle::a, subset);
 }
 inline void Domain::forward_mesh_motion()

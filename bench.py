@@ -299,9 +299,10 @@ def run_ours(args):
         # tagged rows grouped by ID so that the callback writes contiguous slices of the pinned buffers (ID 2 rows, then ID 3 rows)
         i2 = np.nonzero(ids == 2)[0]; i3 = np.nonzero(ids == 3)[0]
         tg = np.concatenate([i2, i3]).astype(np.int32)
-        bridge.update(mig=mig, tagged=tg, n2=len(i2), handle=ctx.subset_register(tg),
-                      v=torch.zeros((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)],
-                      a=torch.zeros((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)])
+        # two sets of pinned buffers, one per callback point of the step: the uploads are asynchronous and a set is rewritten only
+        # after the blocking wf_reduce at the start of the next step
+        mk = lambda: torch.zeros((max(len(tg), 1), 3), dtype=torch.float64).pin_memory().numpy()[:len(tg)]
+        bridge.update(mig=mig, tagged=tg, n2=len(i2), handle=ctx.subset_register(tg), sets=[(mk(), mk()), (mk(), mk())], point=0)
 
     def general_after_contact(t_now):
         # examples/Contact_Compression_1010.cpp:18-47: the tool velocity is set from the host (TriMesh::SetVel) and the callback
@@ -326,17 +327,19 @@ def run_ours(args):
         if contact:
             return general_after_contact(t_now)
         refresh_tagged()
-        tagged, n2, v_host, a_host = bridge["tagged"], bridge["n2"], bridge["v"], bridge["a"]
+        tagged, n2 = bridge["tagged"], bridge["n2"]
         if len(tagged) == 0:
             return
+        v_host, a_host = bridge["sets"][bridge["point"]]; bridge["point"] ^= 1
         f = min(t_now / tau, 1.0) if tau > 0 else 1.0
         a_host[:] = 0.0
         v_host[n2:] = vtop * f
         v_host[:n2] = 0.0
-        ctx.upload_registered("v", bridge["handle"], v_host); ctx.upload_registered("a", bridge["handle"], a_host)
+        ctx.upload_registered("v", bridge["handle"], v_host, wait=False); ctx.upload_registered("a", bridge["handle"], a_host, wait=False)
 
     def e2e_step():
-        sc = ctx.reduce()                       # scalars the solver loop reads each step (max pl_strain, max_disp): D2H
+        sc = ctx.reduce()                       # scalars the solver loop reads each step (max pl_strain, max_disp): D2H; blocking, frees the pinned sets
+        bridge["point"] = 0
         ctx.phase("fraser_stage_a")
         general_after(sc.time)
         ctx.phase("fraser_stage_b1"); ctx.phase("fraser_stage_b2")

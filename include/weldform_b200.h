@@ -159,6 +159,9 @@ int wf_subset_register(wf_ctx *ctx, const int32_t *idx, int64_t n, int *handle);
 int wf_subset_release(wf_ctx *ctx, int handle);
 int wf_download_registered(wf_ctx *ctx, wf_field f, int handle, void *host);
 int wf_upload_registered(wf_ctx *ctx, wf_field f, int handle, const void *host);
+/* same without waiting for the copy: `host` (pinned) must stay untouched until the next blocking call on the ctx (wf_sync, wf_reduce,
+ * any download); the upload is ordered before every later phase call on the ctx stream */
+int wf_upload_registered_async(wf_ctx *ctx, wf_field f, int handle, const void *host);
 int wf_mesh_download(wf_ctx *ctx, int mesh, double *nodes, double *normals, double *pplane);
 
 /* ---- hot path, one call per phase of the Fraser step (SolverFraser.cpp:133-505) -------------------------------- */

@@ -102,6 +102,7 @@ def load_library():
         "wf_plan_slabs": ([_PD, _PD, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
         "wf_subset_register": ([vp, _PI, C.c_int64, C.POINTER(C.c_int)], C.c_int), "wf_subset_release": ([vp, C.c_int], C.c_int),
         "wf_download_registered": ([vp, C.c_int, C.c_int, C.c_void_p], C.c_int), "wf_upload_registered": ([vp, C.c_int, C.c_int, C.c_void_p], C.c_int),
+        "wf_upload_registered_async": ([vp, C.c_int, C.c_int, C.c_void_p], C.c_int),
         "wf_plan_rebalance": ([_PD, C.c_int, _PI], C.c_int),
         "wf_plan_slabs_ex": ([_PD, _PD, C.c_int64, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
         "wf_get_stream": ([vp], vp), "wf_measure_fp64_peak": ([vp, _PD], C.c_int),
@@ -316,9 +317,11 @@ class Context:
         self._ck(self.L.wf_download_registered(self.h, fid, int(handle), out.ctypes.data_as(C.c_void_p)), "wf_download_registered(%s)" % name)
         return out
 
-    def upload_registered(self, name, handle, data):
+    def upload_registered(self, name, handle, data, wait=True):
+        """wait=False: wf_upload_registered_async -- `data` (pinned) must stay untouched until the next blocking call (sync, reduce, download)"""
         fid = FIELDS[name][0]
-        self._ck(self.L.wf_upload_registered(self.h, fid, int(handle), data.ctypes.data_as(C.c_void_p)), "wf_upload_registered(%s)" % name)
+        fn = self.L.wf_upload_registered if wait else self.L.wf_upload_registered_async
+        self._ck(fn(self.h, fid, int(handle), data.ctypes.data_as(C.c_void_p)), "wf_upload_registered(%s)" % name)
 
     def mesh_download(self, mesh, n_nodes, n_elems):
         nodes = np.empty((n_nodes, 3)); normals = np.empty((n_elems, 3)); pp = np.empty(n_elems)

@@ -564,7 +564,7 @@ __global__ void k_upload(double4 *Q0, double4 *Q1, double4 *Q2, double *F, int *
     default: break;
     }
 }
-static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, const void *host, const int *dev_idx = nullptr)
+static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, const void *host, const int *dev_idx = nullptr, bool async = false)
 {
     if (!c || !host) return WF_ERR_ARG;
     if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_upload: no particles");
@@ -581,7 +581,7 @@ static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, 
     if (idx) { int *t_ = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(t_, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); d_idx = t_; }
     k_upload<<<grid_for(cnt, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->F[c->cur], c->I[c->cur], c->cap, (int)f, c->n_loc, c->slot_of, d_idx, nidx, c->stage);
     WF_LAUNCH_CHECK(c);
-    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!async) WF_CUDA(c, cudaStreamSynchronize(c->stream));
     if (f == WF_F_X || f == WF_F_V || f == WF_F_DENSITY) c->dens_valid = false;   // the prepared density rate no longer matches the state
     return 0;
 }
@@ -618,6 +618,12 @@ extern "C" int wf_upload_registered(wf_ctx *c, wf_field f, int handle, const voi
     if (!c || handle < 0 || handle >= (int)c->subsets.size()) return WF_ERR_ARG;
     if (c->subsets[handle].second == 0) return 0;
     return upload_impl(c, f, nullptr, c->subsets[handle].second, host, c->subsets[handle].first);
+}
+extern "C" int wf_upload_registered_async(wf_ctx *c, wf_field f, int handle, const void *host)
+{
+    if (!c || handle < 0 || handle >= (int)c->subsets.size()) return WF_ERR_ARG;
+    if (c->subsets[handle].second == 0) return 0;
+    return upload_impl(c, f, nullptr, c->subsets[handle].second, host, c->subsets[handle].first, true);
 }
 
 extern "C" int wf_mesh_download(wf_ctx *c, int mesh, double *nodes, double *normals, double *pplane)

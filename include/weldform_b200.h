@@ -58,7 +58,11 @@ typedef struct wf_params {
                                 * (SolverKickDrift.cpp:21-400), 2 SolveDiffUpdateLeapFrog (SolverLeapfrog.cpp:24-450) */
     int    auto_ts;            /* Domain::auto_ts: CheckMinTSVel + AdaptiveTimeStep (Domain.cpp:205-297); honoured by solvers 1 and 2 only, like the reference */
     double cfl;                /* Domain::CFL (0.7) */
-    int    tuning;             /* bit 0: disable the software-pipelined gathers of the pair kernels (A/B measurements), bit 8: multi-GPU mesh-particle layout on one GPU; default 0 */
+    int    tuning;             /* A/B measurement and test switches, default 0 (never needed for correct results):
+                                *   bit 0 no software-pipelined gathers; bits 1-5 momentum-kernel variants (occupancy, general instead of lean
+                                *   kernel, 2 x LDG.128 instead of LDG.256); bits 6-7 post-pass occupancy; bit 8 the multi-GPU layout of the
+                                *   rigid-mesh element particles on one GPU (tests); bit 9 blocking halo refreshes instead of the overlapped
+                                *   ones; bit 13 force one slab-rebalancing move at the third rebuild (tests); bit 14 slab rebalancing off */
 } wf_params;
 
 /* Material_ subclasses (Source/Material.h:96-224). model: 0 bilinear (no object), 1 Hollomon, 2 Johnson-Cook. */

@@ -58,6 +58,8 @@ typedef struct wf_params {
                                 * (SolverKickDrift.cpp:21-400), 2 SolveDiffUpdateLeapFrog (SolverLeapfrog.cpp:24-450) */
     int    auto_ts;            /* Domain::auto_ts: CheckMinTSVel + AdaptiveTimeStep (Domain.cpp:205-297); honoured by solvers 1 and 2 only, like the reference */
     double cfl;                /* Domain::CFL (0.7) */
+    int    auto_ts_acc;        /* Domain::auto_ts_acc: CheckMinTSAccel, sqrt_h_a*sqrt(h/|a|) with sqrt_h_a = 0.0025 (Domain.cpp:109,302-317); it replaces the
+                                * velocity criterion when both are set, as the reference's call sequence does */
     int    tuning;             /* A/B measurement and test switches, default 0 (never needed for correct results):
                                 *   bit 0 no software-pipelined gathers; bits 1-5 momentum-kernel variants (occupancy, general instead of lean
                                 *   kernel, 2 x LDG.128 instead of LDG.256); bits 6-7 post-pass occupancy; bit 8 the multi-GPU layout of the

@@ -214,6 +214,7 @@ int main(int argc, char ** argv) try
     dom.BC.InOutFlow = 0;
     dom.auto_ts = in.scalar("auto_ts", 0) != 0.0;      // honoured by the KickDrift / LeapFrog solvers only (SolverFraser.cpp:500-502 is commented out)
     dom.CFL = in.scalar("CFL", 0.7);
+    dom.auto_ts_acc = in.scalar("auto_ts_acc", 0) != 0.0;
 
     if (in.has("bc")) {
         const std::vector<double> & b = in.f("bc");

@@ -287,6 +287,7 @@ struct Dom {
     double Cellfac = 2.0, deltat = 0.0, Time = 0.0;
     bool thermal_solver = false, pl_heating = false, contact = false, cont_heat_fric = false, cont_heat_cond = false;
     int solver = 0;                          // 0 SolveDiffUpdateFraser, 1 SolveDiffUpdateKickDrift, 2 SolveDiffUpdateLeapFrog
+    bool auto_ts_acc = false; double sqrt_h_a = 0.0025;   // Domain.cpp:109,127
     bool auto_ts = false; double CFL = 0.7, deltatint = 0.0, deltatmin = 0.0, manual_min_ts = 1.e-10;   // Domain.cpp:126,153,170
     long steps_done = 0;
     bool gradKernelCorr = false;             // Domain::gradKernelCorr: Bonet-Lok corrected gradient; the Fraser solver then sums with locks, in pair order (SolverFraser.cpp:112-115)
@@ -922,6 +923,14 @@ struct Dom {
             if (deltatmin > test) deltatmin = test;
         }
     }
+    // ---- Domain.cpp:302-317 CheckMinTSAccel
+    void CheckMinTSAccel() {
+        deltatmin = deltatint;
+        for (size_t i = 0; i < N; ++i) {
+            double test = sqrt_h_a * std::sqrt(h[i] / norm3(A(i)));
+            if (deltatmin > test) deltatmin = test;
+        }
+    }
     void AdaptiveTimeStep() {
         if (deltatint > deltatmin) {
             if (deltat < deltatmin) deltat = 2.0 * deltat * deltatmin / (deltat + deltatmin);
@@ -998,7 +1007,9 @@ struct Dom {
                     UserBC();
                 }
                 prev_deltat = deltat;
-                if (auto_ts) { CheckMinTSVel(); AdaptiveTimeStep(); }
+                if (auto_ts) CheckMinTSVel();
+                if (auto_ts_acc) CheckMinTSAccel();
+                if (auto_ts || auto_ts_acc) AdaptiveTimeStep();
                 if (solver == 1) for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * 0.5 * prev_deltat * 1.;
                 else for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * 0.5 * (prev_deltat + deltat);
                 UserBC();
@@ -1154,7 +1165,7 @@ void load_case(const wfc::File & in, Dom & d)
     d.cont_heat_fric = in.scalar("cont_heat_fric", 0) != 0.0; d.cont_heat_cond = in.scalar("cont_heat_cond", 0) != 0.0;
     d.ts_nb_inc = (int)in.scalar("ts_nb_inc", 5);
     d.gradKernelCorr = in.scalar("gradKernelCorr", 0) != 0.0;
-    d.solver = (int)in.scalar("solver", 0); d.auto_ts = in.scalar("auto_ts", 0) != 0.0; d.CFL = in.scalar("CFL", 0.7);
+    d.solver = (int)in.scalar("solver", 0); d.auto_ts = in.scalar("auto_ts", 0) != 0.0; d.auto_ts_acc = in.scalar("auto_ts_acc", 0) != 0.0; d.CFL = in.scalar("CFL", 0.7);
     d.thermal_solver = in.scalar("thermal_solver", 0) != 0.0; d.pl_heating = in.scalar("pl_heating", 0) != 0.0;
     d.pl_work_heat_frac = in.scalar("pl_work_heat_frac", 0.9);
     if (in.has("bc")) { const dvec & b = in.f("bc"); for (size_t r = 0; r + 8 <= b.size(); r += 8) { BC s; s.id = (int)b[r]; s.v[0] = b[r + 1]; s.v[1] = b[r + 2]; s.v[2] = b[r + 3]; s.tau = b[r + 4]; s.set_a = (int)b[r + 5]; d.bcs.push_back(s); } }

@@ -47,6 +47,7 @@ def golden_cases():
     out["lf_comp_30"] = sv(base, 2)
     out["kd_auto_ts"] = sv(base, 1, auto_ts=1.0, CFL=0.1, tf=25 * base["dt"])        # CFL 0.1: the velocity criterion shortens the step
     out["lf_auto_ts"] = sv(base, 2, auto_ts=1.0, CFL=0.1, tf=25 * base["dt"])
+    out["kd_auto_ts_acc"] = sv(base, 1, auto_ts_acc=1.0, tf=25 * base["dt"])             # CheckMinTSAccel: the acceleration criterion shortens the step
     out["lf_contact_60"] = sv(cases.contact_compression(dx=0.0032, nsteps=60, vmax=5.0, tau=1e-5, dens=8, cfl=0.3), 2)
     out["kd_gc_20"] = sv(gc(cases.perturbed(cases.compression(dx=0.04, nsteps=20), amp=60.0)), 1)
     # AddBoxLength lattices: examples/Plate-Yield_3d.cpp (cubic and quintic spline kernels) and an examples/FSW.cpp-like set-up

@@ -23,7 +23,7 @@ class wf_params(C.Structure):
                 ("friction_function", C.c_int), ("friction_m", C.c_double), ("friction_b", C.c_double),
                 ("pfac", C.c_double), ("dfac", C.c_double), ("contact_force_factor", C.c_double),
                 ("cont_heat_fric", C.c_int), ("cont_heat_cond", C.c_int), ("contact_hc", C.c_double),
-                ("nb_order_reference", C.c_int), ("grad_kernel_corr", C.c_int), ("solver", C.c_int), ("auto_ts", C.c_int), ("cfl", C.c_double), ("tuning", C.c_int)]
+                ("nb_order_reference", C.c_int), ("grad_kernel_corr", C.c_int), ("solver", C.c_int), ("auto_ts", C.c_int), ("cfl", C.c_double), ("auto_ts_acc", C.c_int), ("tuning", C.c_int)]
 
 
 class wf_material(C.Structure):

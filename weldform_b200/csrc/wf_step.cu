@@ -569,7 +569,7 @@ static int kdlf_stage(wf_ctx *c, int stage, bool device_bcs)
         return 0;
     case 2:
         c->prev_dt = c->dt;
-        if (c->prm.auto_ts) {
+        if (c->prm.auto_ts || c->prm.auto_ts_acc) {
             double t = 0.0;
             WF_CHECK(pair_min_ts(c, &t));
             if (c->comm.nranks > 1) {                                // min over the ranks

@@ -79,7 +79,7 @@ def context_from_case(case, device=0, comm=None):
     p.cont_heat_fric = int(case.get("cont_heat_fric", 0)); p.cont_heat_cond = int(case.get("cont_heat_cond", 0))
     p.tuning = int(case.get("tuning", int(__import__("os").environ.get("WF_TUNING", "0"))))
     p.grad_kernel_corr = int(case.get("gradKernelCorr", 0))
-    p.solver = int(case.get("solver", 0)); p.auto_ts = int(case.get("auto_ts", 0)); p.cfl = float(case.get("CFL", 0.7))
+    p.solver = int(case.get("solver", 0)); p.auto_ts = int(case.get("auto_ts", 0)); p.cfl = float(case.get("CFL", 0.7)); p.auto_ts_acc = int(case.get("auto_ts_acc", 0))
     ctx.set_params(p)
     if "materials" in case:
         mt = np.asarray(case["materials"], float).reshape(-1, 16)

@@ -256,7 +256,7 @@ inline void Domain::backend_begin(double dt)
     p.thermal_solver = thermal_solver; p.pl_heating = pl_heating; p.pl_work_heat_frac = pl_work_heat_frac;
     p.contact = contact; p.friction_sta = friction_sta; p.friction_dyn = friction_dyn; p.pfac = PFAC; p.dfac = DFAC;
     p.cont_heat_fric = cont_heat_fric; p.cont_heat_cond = cont_heat_cond; p.contact_hc = contact_hc;
-    p.solver = solver_kind; p.auto_ts = (solver_kind != 0 && auto_ts) ? 1 : 0; p.cfl = CFL;   // auto_ts is dead code in the Fraser loop (SolverFraser.cpp:500-502)
+    p.solver = solver_kind; p.auto_ts = (solver_kind != 0 && auto_ts) ? 1 : 0; p.auto_ts_acc = (solver_kind != 0 && auto_ts_acc) ? 1 : 0; p.cfl = CFL;   // auto_ts is dead code in the Fraser loop (SolverFraser.cpp:500-502)
     p.grad_kernel_corr = gradKernelCorr ? 1 : 0;     // CalcGradCorrMatrix + the locking summation the reference switches to (SolverFraser.cpp:112-115)
     if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
     p.friction_function = (friction_function == Linear) ? 1 : 0; p.friction_m = friction_m; p.friction_b = friction_b;
@@ -402,7 +402,6 @@ inline void Domain::run_callback(PtDom cb)
 inline void Domain::solve_kick_drift_leap_frog(int solver, double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx)
 {
     std::cout << "\n--------------Solving (weldform_b200, " << (solver == 1 ? "SolveDiffUpdateKickDrift" : "SolveDiffUpdateLeapFrog") << " on the GPU)----------------------------" << std::endl;
-    if (auto_ts_acc) throw new Fatal("Domain::auto_ts_acc (CheckMinTSAccel) is not implemented in weldform_b200");
     solver_kind = solver;
     deltat = dt; deltatmin = dt;
     backend_begin(dt);

@@ -18,7 +18,7 @@
 // ThermalCalcs (CalcConvHeat, CalcTempInc), CalcKinEnergyEqn/CalcIntEnergyEqn, and the Fraser step order with its
 // neighbour-rebuild cadence (Source/SolverFraser.cpp:133-505). Fixed particles (IsFree = false) are routed as the reference
 // does (no SM pairs); their Shepard-smoothed TIR (PrimaryComputeAcceleration, Domain.cpp:1599-1698, read by nothing) is not
-// restated. gradKernelCorr (Domain.cpp:1832-1940 + the locking branches of InteractionAlt.cpp) is restated for all-free particle sets. Not restated: ghost particles, damage, 2-D axisymmetric branches (all "next" or out of scope in SURVEY.md section 8).
+// restated. gradKernelCorr (Domain.cpp:1832-1940 + the locking branches of InteractionAlt.cpp) is restated, including the FSM pairs of fixed particles in CalcGradCorrMatrix. Not restated: ghost particles, damage, 2-D axisymmetric branches (all "next" or out of scope in SURVEY.md section 8).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -307,7 +307,7 @@ struct Dom {
     // cell grid
     double BLPF[3], TRPR[3], CellSize[3], hmax = 0.0; int CellNo[3]; ivec HOC, LL; bool grid_ready = false;
     // pair lists (Nproc = 1 discovery order)
-    std::vector<std::pair<int, int> > SM, RIG, CONT;
+    std::vector<std::pair<int, int> > SM, FSM, RIG, CONT;   // FSM: one particle fixed (Neighbour.cpp:410); read by CalcGradCorrMatrix only
     std::vector<ivec> ipairs, jpairs;   // per particle: pair indices with the particle as min / as max, discovery order
     bool nb_cleared = true;
     // scalars
@@ -390,7 +390,7 @@ struct Dom {
         }
         if (CheckRadius(t1, t2)) {
             if (IsFree[t1] || IsFree[t2]) {
-                if (Material[t1] == Material[t2]) { if (IsFree[t1] && IsFree[t2]) SM.push_back(std::make_pair(t1, t2)); }
+                if (Material[t1] == Material[t2]) { if (IsFree[t1] && IsFree[t2]) SM.push_back(std::make_pair(t1, t2)); else FSM.push_back(std::make_pair(t1, t2)); }
             }
         }
     }
@@ -417,7 +417,7 @@ struct Dom {
         }
         nb_cleared = false;
     }
-    void ClearNbData() { SM.clear(); RIG.clear(); CONT.clear(); CellReset(); ListGenerate(); nb_cleared = true; }   // Neighbour.cpp:479-497
+    void ClearNbData() { SM.clear(); FSM.clear(); RIG.clear(); CONT.clear(); CellReset(); ListGenerate(); nb_cleared = true; }   // Neighbour.cpp:479-497
     // ---- Neighbour.cpp:617-694 CalcPairPosList: per particle, pairs as min (front) and as max (back), discovery order
     void CalcPairPosList() {
         ipairs.assign(N, ivec()); jpairs.assign(N, ivec());
@@ -546,7 +546,7 @@ struct Dom {
     // ================= gradKernelCorr = true: locking summation, pairs as stored (first, second), pair order =================
     // External/matvec.h:836-841 Mult(Mat3,Vec3,Vec3): B = M A
     static V3 mvmul(const M3 & M, const V3 & A) { V3 b; for (int i = 0; i < 3; ++i) b(i) = A(0) * M(i, 0) + A(1) * M(i, 1) + A(2) * M(i, 2); return b; }
-    // ---- Source/Domain.cpp:1832-1940 CalcGradCorrMatrix (SM pairs; this restatement has no FSM pairs: fixed particles unsupported with it)
+    // ---- Source/Domain.cpp:1832-1940 CalcGradCorrMatrix (SM pairs, then the FSM pairs with one fixed particle)
     void CalcGradCorrMatrix() {
         std::vector<M3> temp(N, zero3());
         for (size_t p = 0; p < SM.size(); ++p) {
@@ -557,6 +557,18 @@ struct Dom {
             double di = Density[P1], mi = Mass[P1], dj = Density[P2], mj = Mass[P2];
             V3 gx = vscale(GK, xij);
             M3 m;                                     // Dyad(GK*xij, xij), matvec.h:813-818
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) m(r, c) = gx(r) * xij(c);
+            temp[P1] = msub(temp[P1], smul(mj / dj, m));
+            temp[P2] = msub(temp[P2], smul(mi / di, m));
+        }
+        for (size_t p = 0; p < FSM.size(); ++p) {          // Domain.cpp:1870-1898: the pairs with one fixed particle, same term
+            int P1 = FSM[p].first, P2 = FSM[p].second;
+            V3 xij = vsub(X(P1), X(P2));
+            double hh = (h[P1] + h[P2]) / 2.0;
+            double GK = GradKernel(Dimension, KernelType, norm3(xij) / hh, hh);
+            double di = Density[P1], mi = Mass[P1], dj = Density[P2], mj = Mass[P2];
+            V3 gx = vscale(GK, xij);
+            M3 m;
             for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) m(r, c) = gx(r) * xij(c);
             temp[P1] = msub(temp[P1], smul(mj / dj, m));
             temp[P2] = msub(temp[P2], smul(mi / di, m));

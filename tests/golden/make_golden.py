@@ -55,6 +55,7 @@ def golden_cases():
     out["plate_cubic_40"] = cases.plate_yield(dx=0.0012, nsteps=40, amp=0.3)
     out["plate_quintic_10"] = cases.plate_yield(dx=0.0012, nsteps=10, kernel=2, hfac=0.8, amp=0.3)
     out["fsw_like_80"] = cases.fsw_like(dx=0.0009, nsteps=80, L=0.02, rt=0.004)
+    out["gc_fixed_40"] = gc(cases.fsw_like(dx=0.0009, nsteps=40, L=0.02, rt=0.004))      # gradient correction with fixed walls: FSM pairs in CalcGradCorrMatrix
     return out
 
 

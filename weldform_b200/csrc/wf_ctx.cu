@@ -241,7 +241,6 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     if (multi && !p->global_index) return fail(c, WF_ERR_ARG, "wf_set_particles: global_index is required when nranks > 1");
     c->any_fixed = false;
     if (p->is_free) for (int64_t i = 0; i < nsph; ++i) if (!p->is_free[i]) { c->any_fixed = true; break; }
-    if (c->any_fixed && c->prm.grad_kernel_corr) return fail(c, WF_ERR_UNSUPPORTED, "gradKernelCorr with fixed particles (FSM pairs of CalcGradCorrMatrix, Domain.cpp:1870-1898) is not implemented");
     c->n = n; c->n_loc = n; c->nsph = nsph_global; c->nmeshp = nmeshp;
     c->mesh_tail = nmeshp > 0 && (multi || (c->prm.tuning & 256));   // bit 8 of wf_params::tuning: the multi-GPU mesh-particle layout on one GPU (tests)
     WF_CHECK(alloc_particles(c, multi ? n + n / 4 + 262144 : n));

@@ -172,6 +172,7 @@ int ensure_stage(wf_ctx *c, size_t bytes);
 // wf_neighbour.cu
 int nb_cell_initiate(wf_ctx *c);
 int nb_build_impl(wf_ctx *c);
+int nb_gradcorr_fsm(wf_ctx *c);                         // CalcGradCorrMatrix: contributions of the pairs with one fixed particle
 // wf_pair.cu
 int pair_gradcorr(wf_ctx *c);
 int pair_tir(wf_ctx *c);

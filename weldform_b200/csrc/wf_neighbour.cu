@@ -292,6 +292,50 @@ k_cont_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long
 
 // pairs (i, j > i) of slot s: rows [0, nb_hi) hold them unless the list is in plain discovery order (walk_order), where
 // every front row is tested
+// CalcGradCorrMatrix, second loop (Domain.cpp:1870-1898): the FSM pairs -- one particle fixed -- add the same term as the SM pairs
+// to BOTH members. The neighbour lists hold SM pairs only, so every free particle walks its 27 cells for fixed partners (same
+// filters as AllocateNbPair, Neighbour.cpp:374-417) in the reference's discovery order, after its SM sums (k_gradcorr).
+__global__ void __launch_bounds__(128)
+k_gradcorr_fsm(Grid g, int64_t n, int64_t cap, int nsph, int dim, int kt, const unsigned long long *keys, const int *cell_start, const int *cell_end,
+               const double4 *__restrict__ Q0, const double4 *__restrict__ Q2, const int *__restrict__ orig, const int *__restrict__ ID, const int *__restrict__ cls_of,
+               const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, double *F)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    if (orig[s] >= nsph || !is_free[s]) return;
+    if (contact && is_mesh_id(ID[s], mids)) return;
+    const double4 qi = Q0[s]; const V3 xi = v3(qi.x, qi.y, qi.z);
+    const int mat_i = classes[cls_of[s]].Material;
+    double T[9];
+    for (int k = 0; k < 9; ++k) T[k] = F[(int64_t)(F_GC + k) * cap + s];
+    int c[3]; g.unlin((int)(keys[s] >> 32), c);
+    for (int e = 0; e < 27; ++e) {
+        int d[3] = { c[0] + c_walk[e][0], c[1] + c_walk[e][1], c[2] + c_walk[e][2] };
+        if (d[0] < 0 || d[0] >= g.CellNo[0] || d[1] < 0 || d[1] >= g.CellNo[1] || d[2] < 0 || d[2] >= g.CellNo[2]) continue;
+        const int l = g.lin(d);
+        const int js = cell_start[l], je = cell_end[l], role = c_walk[e][3];
+        for (int j = js; j < je; ++j) {
+            if (j == (int)s || orig[j] >= nsph || is_free[j]) continue;
+            if (contact && is_mesh_id(ID[j], mids)) continue;
+            const double4 qj = Q0[j]; const V3 xj = v3(qj.x, qj.y, qj.z);
+            const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
+            const V3 xij = ifirst ? (xi - xj) : (xj - xi);
+            const double hh = (qi.w + qj.w) / 2;
+            const double rij = norm(xij);
+            if (!((rij / hh) <= g.Cellfac)) continue;                         // CheckRadius
+            if (classes[cls_of[j]].Material != mat_i) continue;
+            const double hg = (qi.w + qj.w) / 2.0, q = rij / hg;
+            const double GK = (kt == 0 && dim == 3) ? cubicGW_c(1.0 / (hg * hg * hg * hg * WF_PI), q, hg) : gradW(dim, kt, q, hg);
+            const double4 q2j = Q2[j];
+            const double f = q2j.x / q2j.y;
+            const V3 gv = GK * xij;
+            const double gx[3] = { gv.x, gv.y, gv.z }, xx[3] = { xij.x, xij.y, xij.z };
+            for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) T[3 * r + cc] = T[3 * r + cc] - (gx[r] * xx[cc]) * f;
+        }
+    }
+    for (int k = 0; k < 9; ++k) F[(int64_t)(F_GC + k) * cap + s] = T[k];
+}
+
 __global__ void k_export_pairs(int64_t n, int64_t cap, int K, const uint32_t *nbr, const int *nb_hi, const int *orig, const int64_t *offs, int64_t *out, int64_t *count)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,6 +422,19 @@ int nb_cell_initiate(wf_ctx *c)
         c->comm.emig_cap = std::max<int64_t>(4096, n / 16);
         cudaFree(c->comm.d_emig); WF_CUDA(c, cudaMalloc(&c->comm.d_emig, 2 * c->comm.emig_cap * sizeof(int)));
     }
+    return 0;
+}
+
+int nb_gradcorr_fsm(wf_ctx *c)
+{
+    if (!c->any_fixed) return 0;
+    Grid g = make_grid(c);
+    int4 mids = make_int4(-2147483647, -2147483647, -2147483647, -2147483647);
+    if (c->mesh_ids.size() > 0) mids.x = c->mesh_ids[0]; if (c->mesh_ids.size() > 1) mids.y = c->mesh_ids[1];
+    if (c->mesh_ids.size() > 2) mids.z = c->mesh_ids[2]; if (c->mesh_ids.size() > 3) mids.w = c->mesh_ids[3];
+    k_gradcorr_fsm<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(g, c->n_loc, c->cap, (int)c->nsph, c->prm.dimension, c->prm.kernel_type, c->keys[1], c->cell_start, c->cell_end,
+        c->Q0[c->cur], c->Q2[c->cur], c->Ip(I_ORIG), c->Ip(I_ID), c->Ip(I_CLS), c->Ip(I_FREE), c->d_classes, c->prm.contact ? 1 : 0, mids, c->F[c->cur]);
+    WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
 

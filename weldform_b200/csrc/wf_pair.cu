@@ -154,7 +154,7 @@ __device__ inline V3 gc_mat_vec(const double M[9], const V3 &g)
 { return v3(g.x * M[0] + g.y * M[1] + g.z * M[2], g.x * M[3] + g.y * M[4] + g.z * M[5], g.x * M[6] + g.y * M[7] + g.z * M[8]); }
 
 // Domain::CalcGradCorrMatrix (Domain.cpp:1832-1940), gather form: M_i = - sum_j (m_j/rho_j) (GK xij) (x) xij over the list in
-// discovery order, then InvLog (matvec.h:673-693); identity when the determinant is below 1e-10. All-free particle sets only.
+// discovery order (k_gradcorr), plus the pairs with a fixed particle (k_gradcorr_fsm, wf_neighbour.cu), then InvLog (k_gradcorr_inv).
 __global__ void __launch_bounds__(128) k_gradcorr(PairArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
@@ -183,14 +183,27 @@ __global__ void __launch_bounds__(128) k_gradcorr(PairArgs a)
 #pragma unroll
             for (int c = 0; c < 3; ++c) T[3 * r + c] = T[3 * r + c] - (gx[r] * xx[c]) * f;
     }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) OWN(F_GC + k) = T[k];        // raw sum; k_gradcorr_fsm (fixed neighbours) may add to it, k_gradcorr_inv inverts
+}
+// InvLog (matvec.h:673-693) of the summed matrix; identity when the determinant is below 1e-10 and for fixed particles (Domain.cpp:1916-1937)
+__global__ void __launch_bounds__(128) k_gradcorr_inv(PairArgs a)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
+    if (s >= a.n) return;
+    if (a.orig[s] >= a.nsph) return;
+    double T[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) T[k] = OWN(F_GC + k);
     const double det = T[0] * (T[4] * T[8] - T[5] * T[7]) - T[1] * (T[3] * T[8] - T[5] * T[6]) + T[2] * (T[3] * T[7] - T[4] * T[6]);
     double Mi[9];
-    if (fabs(det) < 1.0e-10) { for (int k = 0; k < 9; ++k) Mi[k] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0; }
+    if (fabs(det) < 1.0e-10 || (a.is_free && !a.is_free[s])) { for (int k = 0; k < 9; ++k) Mi[k] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0; }
     else {
         Mi[0] = (T[4] * T[8] - T[5] * T[7]) / det; Mi[1] = (T[2] * T[7] - T[1] * T[8]) / det; Mi[2] = (T[1] * T[5] - T[2] * T[4]) / det;
         Mi[3] = (T[5] * T[6] - T[3] * T[8]) / det; Mi[4] = (T[0] * T[8] - T[2] * T[6]) / det; Mi[5] = (T[2] * T[3] - T[0] * T[5]) / det;
         Mi[6] = (T[3] * T[7] - T[4] * T[6]) / det; Mi[7] = (T[1] * T[6] - T[0] * T[7]) / det; Mi[8] = (T[0] * T[4] - T[1] * T[3]) / det;
     }
+#pragma unroll
 #pragma unroll
     for (int k = 0; k < 9; ++k) OWN(F_GC + k) = Mi[k];
 }
@@ -811,6 +824,8 @@ int pair_gradcorr(wf_ctx *c)
     PairArgs a = make_args(c);
     ProfScope ps(c, PK_NB_LIST);
     k_gradcorr<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    if (c->any_fixed) WF_CHECK(nb_gradcorr_fsm(c));           // FSM pairs (one particle fixed): a cell walk of its own, after the SM sums
+    k_gradcorr_inv<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
     c->dens_valid = false;
     return 0;
 }

@@ -4,7 +4,8 @@
 // a cylinder with AddCylinderLength, assign per-particle material fields, install a GeneralAfter callback that drives
 // the top rows and holds the bottom rows, call SolveDiffUpdateFraser. Everything under Solve runs on the GPU.
 //
-//   usage: compression_host_api <dx> <nsteps> <perturb_amp> <out.bin> [solver: 0 Fraser (default), 1 KickDrift, 2 LeapFrog]
+//   usage: compression_host_api <dx> <nsteps> <perturb_amp> <out.bin> [solver: 0 Fraser (default), 1 KickDrift, 2 LeapFrog,
+//          3 ThermalSolve (heat conduction only, time step 0.05 s)]
 // out.bin: int64 n, then n*(x[3], v[3], Displacement[3], pl_strain, T, Density, Sigma[9]) as float64 (creation order).
 #include <cstdio>
 #include "Domain.h"
@@ -54,6 +55,7 @@ int main(int argc, char ** argv) try
     const int solver = argc > 5 ? std::atoi(argv[5]) : 0;
     if (solver == 1) dom.SolveDiffUpdateKickDrift((nsteps - 0.5) * timestep, timestep, 1.e30, NULL, 1000000);
     else if (solver == 2) dom.SolveDiffUpdateLeapFrog((nsteps - 0.5) * timestep, timestep, 1.e30, NULL, 1000000);
+    else if (solver == 3) dom.ThermalSolve((nsteps - 0.5) * 0.05, 0.05, 1.e30, NULL, 1000000);
     else dom.SolveDiffUpdateFraser((nsteps - 0.5) * timestep, timestep, 1.e30, NULL, 1000000);
     FILE * fp = std::fopen(argv[4], "wb");
     const long long n = (long long)dom.Particles.Size();

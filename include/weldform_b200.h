@@ -55,7 +55,8 @@ typedef struct wf_params {
     int    grad_kernel_corr;   /* Domain::gradKernelCorr: Bonet-Lok corrected kernel gradient (Domain.cpp:1832-1940). As in the reference the Fraser
                                 * solver then sums per pair with locks, in pair-discovery order (SolverFraser.cpp:112-115) */
     int    solver;             /* step order run by wf_run: 0 SolveDiffUpdateFraser (SolverFraser.cpp), 1 SolveDiffUpdateKickDrift
-                                * (SolverKickDrift.cpp:21-400), 2 SolveDiffUpdateLeapFrog (SolverLeapfrog.cpp:24-450) */
+                                * (SolverKickDrift.cpp:21-400), 2 SolveDiffUpdateLeapFrog (SolverLeapfrog.cpp:24-450), 3 ThermalSolve (Thermal.cpp:567-719:
+                                * heat conduction only, one neighbour search at wf_solver_init) */
     int    auto_ts;            /* Domain::auto_ts: CheckMinTSVel + AdaptiveTimeStep (Domain.cpp:205-297); honoured by solvers 1 and 2 only, like the reference */
     double cfl;                /* Domain::CFL (0.7) */
     int    auto_ts_acc;        /* Domain::auto_ts_acc: CheckMinTSAccel, sqrt_h_a*sqrt(h/|a|) with sqrt_h_a = 0.0025 (Domain.cpp:109,302-317); it replaces the

@@ -248,6 +248,7 @@ int main(int argc, char ** argv) try
         auto t0 = std::chrono::steady_clock::now();
         if (solver == 1) dom.SolveDiffUpdateKickDrift(tf, dt, 1.0e30, "wfref", 1000000);
         else if (solver == 2) dom.SolveDiffUpdateLeapFrog(tf, dt, 1.0e30, "wfref", 1000000);
+        else if (solver == 3) dom.ThermalSolve(tf, dt, 1.0e30, "wfref", 1000000);     // while (Time < tf): the same nsteps with tf = (nsteps - 0.5) dt
         else dom.SolveDiffUpdateFraser(tf, dt, 1.0e30, "wfref", 1000000);
         solve_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }

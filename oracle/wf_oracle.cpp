@@ -286,7 +286,7 @@ struct Dom {
     int Dimension = 3, KernelType = 0, GradientType = 0, ts_nb_inc = 5;
     double Cellfac = 2.0, deltat = 0.0, Time = 0.0;
     bool thermal_solver = false, pl_heating = false, contact = false, cont_heat_fric = false, cont_heat_cond = false;
-    int solver = 0;                          // 0 SolveDiffUpdateFraser, 1 SolveDiffUpdateKickDrift, 2 SolveDiffUpdateLeapFrog
+    int solver = 0;                          // 0 SolveDiffUpdateFraser, 1 SolveDiffUpdateKickDrift, 2 SolveDiffUpdateLeapFrog, 3 ThermalSolve
     bool auto_ts_acc = false; double sqrt_h_a = 0.0025;   // Domain.cpp:109,127
     bool auto_ts = false; double CFL = 0.7, deltatint = 0.0, deltatmin = 0.0, manual_min_ts = 1.e-10;   // Domain.cpp:126,153,170
     long steps_done = 0;
@@ -953,6 +953,42 @@ struct Dom {
         }
         if (deltat < manual_min_ts) deltat = manual_min_ts;
     }
+    // ---- Source/ThermalTest.cpp:8-49 CalcTempIncPair / CalcTempIncPP: the initial dT/dt of ThermalSolve, per particle over the
+    //      Nishiura lists (pairs as min first, then as max), always from particle i's side
+    void CalcTempIncPP() {
+        for (size_t i = 0; i < N; ++i) dTdt[i] = 0.;
+        for (size_t i = 0; i < N; ++i) {
+            double k = 1. / (Density[i] * cp_T[i]);
+            auto pair = [&](int P1, int P2) {
+                V3 xij = vsub(X(P1), X(P2));
+                double hh = (h[P1] + h[P2]) / 2.0;
+                double GK = GradKernel(Dimension, KernelType, norm3(xij) / hh, hh);
+                double dj = Density[P2], mj = Mass[P2];
+                return mj / dj * 4. * (k_T[P1] * k_T[P2]) / (k_T[P1] + k_T[P2]) * (T[P1] - T[P2]) * dot3(xij, vscale(GK, xij)) / (dot3(xij, xij));
+            };
+            if (i < ipairs.size()) {
+                for (size_t n = 0; n < ipairs[i].size(); ++n) { int p = ipairs[i][n]; dTdt[i] += pair((int)i, std::max(SM[p].first, SM[p].second)); }
+                for (size_t n = 0; n < jpairs[i].size(); ++n) { int p = jpairs[i][n]; dTdt[i] += pair((int)i, std::min(SM[p].first, SM[p].second)); }
+            }
+            dTdt[i] *= k;
+        }
+    }
+    // ---- Source/Thermal.cpp:567-719 ThermalSolve: one neighbour search, then ThermalCalcs + GeneralAfter per step
+    void ThermalSolve(int nsteps, double dt) {
+        deltat = deltatint = deltatmin = dt;
+        for (size_t i = 0; i < N; ++i) Pressure[i] = EOS(PresEq[i], Cs[i], P0[i], Density[i], RefDensity[i]);
+        CellInitiate(); ListGenerate();
+        MainNeighbourSearch(); SaveNeighbourData();
+        if (gradKernelCorr) CalcGradCorrMatrix();
+        CalcPairPosList();
+        CalcTempIncPP();
+        for (int step = 0; step < nsteps; ++step) {
+            ThermalCalcs(dt);
+            UserBC();
+            Time += deltat;
+            steps_done++;
+        }
+    }
     // ---- Source/SolverFraser.cpp:21-513 SolveDiffUpdateFraser, SolverKickDrift.cpp:21-400 SolveDiffUpdateKickDrift,
     //      SolverLeapfrog.cpp:24-450 SolveDiffUpdateLeapFrog: one neighbour policy, three step orders.
     //      nsteps > 0: that many iterations; else while (Time <= tf) as the reference loops.
@@ -1213,7 +1249,8 @@ extern "C" int wfo_run_file(const char * case_path, const char * out_path)
     } else {
         auto t0 = std::chrono::steady_clock::now();
         const double tf = in.scalar("tf", 0.0);          // > 0: loop while (Time <= tf) as the reference does (needed with auto_ts)
-        if (tf > 0.0) d.Solve(0, dt, tf); else d.Solve(nsteps, dt);
+        if (d.solver == 3) d.ThermalSolve(nsteps, dt);
+        else if (tf > 0.0) d.Solve(0, dt, tf); else d.Solve(nsteps, dt);
         solve_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     out.put_scalar("n_particles", (double)d.N); out.put_scalar("solid_part_count", (double)d.solid_part_count);

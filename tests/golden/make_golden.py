@@ -56,6 +56,12 @@ def golden_cases():
     out["plate_quintic_10"] = cases.plate_yield(dx=0.0012, nsteps=10, kernel=2, hfac=0.8, amp=0.3)
     out["fsw_like_80"] = cases.fsw_like(dx=0.0009, nsteps=80, L=0.02, rt=0.004)
     out["gc_fixed_40"] = gc(cases.fsw_like(dx=0.0009, nsteps=40, L=0.02, rt=0.004))      # gradient correction with fixed walls: FSM pairs in CalcGradCorrMatrix
+    # Domain::ThermalSolve (heat conduction only, one neighbour search): convection on every seventh particle, a thermal time step
+    th = cases.compression(dx=0.04, nsteps=25)
+    nth = len(th["T"])
+    th.update(solver=3.0, dt=0.05, Thermal_BC=(np.arange(nth) % 7 == 0).astype(np.int32), h_conv=200.0 * np.ones(nth), T_inf=5.0 * np.ones(nth),
+              th_exp=1e-5 * np.ones(nth))
+    out["thermal_solve_25"] = th
     return out
 
 

@@ -93,3 +93,26 @@ def test_host_domain_driver_matches_device_run_and_oracle(host_example, oracle_p
     assert ref["pl_strain"].max() > 1e-3
     worst = {k: ot.max_rel(got[k], ref[k]) for k in got}
     assert max(worst.values()) < 1e-6, worst
+
+
+@pytest.mark.gpu
+def test_host_domain_thermal_solve_matches_device_run_and_oracle(host_example, oracle_port):
+    """Domain::ThermalSolve of the host mirror (wf_thermal + the GeneralAfter callback + wf_step_end per step, Thermal.cpp:627-717)
+    against wf_run with device-side BCs and against the oracle port of the reference's ThermalSolve."""
+    from weldform_b200 import harness
+    dx, nsteps, amp = 0.03, 30, 60.0
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.bin")
+        r = subprocess.run([host_example, str(dx), str(nsteps), str(amp), out, "3"], capture_output=True, text=True, timeout=600, env=dict(os.environ, WELDFORM_SYNC="tagged"))
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        got = _read_bin(out)
+    case = cases.perturbed(cases.compression(dx=dx, nsteps=nsteps), amp=amp)
+    T0 = np.array(case["T"], dtype=np.float64)
+    case["solver"] = 3.0; case["dt"] = 0.05
+    dev = harness.run_case(case, with_pairs=False)
+    for k in got:
+        assert np.array_equal(got[k], dev[k]), "host-callback run differs from the device-BC run in %s (%.3e)" % (k, ot.max_rel(got[k], dev[k]))
+    ref = ot.run_port(case)
+    assert np.abs(ref["T"] - T0).max() > 0.05 and not ref["Displacement"].any(), "conduction must act, nothing may move"
+    worst = {k: ot.max_rel(got[k], ref[k]) for k in got}
+    assert max(worst.values()) < 1e-9, worst

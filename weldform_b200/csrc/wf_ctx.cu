@@ -148,7 +148,7 @@ extern "C" int wf_set_params(wf_ctx *c, const wf_params *p)
 {
     if (!c || !p) return WF_ERR_ARG;
     if (p->dimension != 3) return fail(c, WF_ERR_UNSUPPORTED, "wf_set_params: Dimension=%d; only the 3-D path is implemented", p->dimension);
-    if (p->solver < 0 || p->solver > 2) return fail(c, WF_ERR_UNSUPPORTED, "wf_set_params: solver=%d; 0 Fraser, 1 KickDrift, 2 LeapFrog are implemented (Verlet is not)", p->solver);
+    if (p->solver < 0 || p->solver > 3) return fail(c, WF_ERR_UNSUPPORTED, "wf_set_params: solver=%d; 0 Fraser, 1 KickDrift, 2 LeapFrog, 3 ThermalSolve are implemented (Verlet is not)", p->solver);
     if (p->kernel_type < 0 || p->kernel_type > 3) return fail(c, WF_ERR_ARG, "wf_set_params: kernel_type %d out of range", p->kernel_type);
     if (p->gradient_type < 0 || p->gradient_type > 2) return fail(c, WF_ERR_ARG, "wf_set_params: gradient_type %d out of range", p->gradient_type);
     if (p->ts_nb_inc < 1) return fail(c, WF_ERR_ARG, "wf_set_params: ts_nb_inc must be >= 1");

@@ -176,6 +176,7 @@ int nb_gradcorr_fsm(wf_ctx *c);                         // CalcGradCorrMatrix: c
 // wf_pair.cu
 int pair_gradcorr(wf_ctx *c);
 int pair_tir(wf_ctx *c);
+int pair_temp_inc_pp(wf_ctx *c);                         // CalcTempIncPP: the initial dT/dt of ThermalSolve
 int pair_min_ts(wf_ctx *c, double *test_min);
 int pair_density(wf_ctx *c);
 int pair_rate_stress(wf_ctx *c, int64_t lo = 0, int64_t hi = -1);   // slots [lo, hi); hi < 0: n_loc

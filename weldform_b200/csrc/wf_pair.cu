@@ -228,6 +228,32 @@ template <bool HANDOVER> __global__ void __launch_bounds__(128) k_tir(PairArgs a
     for (int k = 0; k < 6; ++k) OWN(F_TN + k) = t[k];
 }
 
+// ---- Domain::CalcTempIncPP / CalcTempIncPair (ThermalTest.cpp:8-49): the initial dT/dt of ThermalSolve, every pair from particle
+// i's side over the Nishiura order (the list order), dot(xij, xij) in the denominator, times 1/(rho_i cp_i) at the end
+__global__ void __launch_bounds__(128) k_temp_inc_pp(PairArgs a)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
+    if (s >= a.n) return;
+    double acc = 0.0;
+    const double4 qi = a.Q0[s], q2i = a.Q2[s];
+    const ClassProps cpi = a.cls[a.cls_of[s]];
+    if (a.orig[s] < a.nsph) {
+        const V3 xi = v3(qi.x, qi.y, qi.z);
+        const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
+        for (int n = 0; n < cnt; ++n) {
+            const int j = (int)(a.nbr[(int64_t)nb_row(n, nhi, a.K) * a.cap + s] & 0x7fffffffu);
+            const double4 qj = a.Q0[j], q2j = a.Q2[j];
+            const double kj = a.cls[a.cls_of[j]].k_T;
+            const V3 xij = xi - v3(qj.x, qj.y, qj.z);
+            const double hh = (qi.w + qj.w) / 2.0;
+            const double q = norm(xij) / hh;
+            const double GK = (a.kt == 0 && a.dim == 3) ? cubicGW_c(c4_of(hh), q, hh) : gradW(a.dim, a.kt, q, hh);
+            acc += q2j.x / q2j.y * 4. * (cpi.k_T * kj) / (cpi.k_T + kj) * (q2i.z - q2j.z) * dot(xij, GK * xij) / (dot(xij, xij));
+        }
+    }
+    OWN(F_DTDT) = acc * (1. / (q2i.y * cpi.cp_T));
+}
+
 // ---- Domain::CheckMinTSVel (Domain.cpp:267-297): min over all particles of CFL * (nearest listed neighbour) / (Cs + |v|);
 // the CFL factor and the comparison with deltatint are applied by the caller
 __global__ void __launch_bounds__(128) k_min_ts(PairArgs a, double cfl, int accel_criterion, double *partial)
@@ -836,6 +862,14 @@ int pair_tir(wf_ctx *c)
     PairArgs a = make_args(c);
     ProfScope ps(c, PK_BEGIN);
     k_tir<false><<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
+    return 0;
+}
+int pair_temp_inc_pp(wf_ctx *c)
+{
+    WF_PAIR_PRECHECK(c);
+    PairArgs a = make_args(c);
+    ProfScope ps(c, PK_THERMAL);
+    k_temp_inc_pp<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
 // CheckMinTSVel: this rank's min of CFL*dmin/(Cs+|v|) (blocking read-back)

@@ -387,6 +387,16 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     StepArgs a = make_step_args(c);
     k_init_pressure<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c);       // InitialChecks
     WF_CHECK(nb_cell_initiate(c));                                                               // CellInitiate (+ListGenerate: part of the build)
+    if (c->prm.solver == 3) {
+        // Domain::ThermalSolve (Thermal.cpp:567-626): one neighbour search for the whole run, the correction matrices, the initial dT/dt
+        if (c->prm.contact) return fail(c, WF_ERR_UNSUPPORTED, "ThermalSolve with rigid-mesh contact is not implemented");
+        WF_CHECK(nb_build_impl(c));
+        c->solver_ready = true;
+        WF_CHECK(pair_gradcorr(c));
+        WF_CHECK(pair_temp_inc_pp(c));
+        WF_CHECK(reduce_impl(c, false));
+        return 0;
+    }
     if (c->prm.contact) {
         // SolverFraser.cpp:71-92: ID_orig = ID, MainNeighbourSearch, SaveNeighbourData, CalculateSurface(1)
         WF_CHECK(nb_build_impl(c));
@@ -613,11 +623,23 @@ extern "C" int wf_solver_stage(wf_ctx *c, int stage)
 {
     WF_NEED_READY(c);
     if (c->prm.solver == 0) return fail(c, WF_ERR_ARG, "wf_solver_stage: the Fraser step has its own stages (wf_fraser_stage_a/b1/b2/c)");
+    if (c->prm.solver == 3) return fail(c, WF_ERR_ARG, "wf_solver_stage: ThermalSolve steps are wf_thermal + the callback + wf_step_end; use wf_run");
     return kdlf_stage(c, stage, false);
 }
 
+// One step of Domain::ThermalSolve (Thermal.cpp:627-717): ThermalCalcs (T += dt*dTdt, CalcConvHeat, CalcTempInc, thermal-expansion
+// strain rate), GeneralAfter, Time += dt; the neighbour lists of the initial search are kept
+static int thermal_step(wf_ctx *c)
+{
+    WF_CHECK(pair_thermal(c));
+    WF_CHECK(apply_bcs_impl(c));
+    WF_CHECK(reduce_impl(c, true));
+    c->time += c->dt; c->steps++;
+    return 0;
+}
 static int one_step(wf_ctx *c)
 {
+    if (c->prm.solver == 3) return thermal_step(c);
     if (c->prm.solver != 0) return kdlf_step(c);
     return wf_fraser_run(c, 1);
 }
@@ -625,7 +647,7 @@ extern "C" int wf_run(wf_ctx *c, int64_t nsteps)
 {
     WF_NEED_READY(c);
     if (c->prm.solver == 0) return wf_fraser_run(c, nsteps);
-    for (int64_t k = 0; k < nsteps; ++k) WF_CHECK(kdlf_step(c));
+    for (int64_t k = 0; k < nsteps; ++k) WF_CHECK(one_step(c));
     return 0;
 }
 extern "C" int wf_run_until(wf_ctx *c, double tf, int64_t *steps_done)

@@ -86,7 +86,7 @@ public:
     // the reference's Verlet loop calls its reductions under `#ifdef NONLOCK_SUM`, a macro nothing defines (SolverVerlet.cpp:176-178,
     // 206-208): with the default nonlock_sum = true no pair sum ever reaches the particles there. Not restated.
     void SolveDiffUpdateVerlet(double, double, double, char const *, size_t) { not_implemented("SolveDiffUpdateVerlet"); }
-    void ThermalSolve(double, double, double, char const *, size_t) { not_implemented("ThermalSolve"); }
+    void ThermalSolve(double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx);
     void ThermalStructSolve(double, double, double, char const *, size_t) { not_implemented("ThermalStructSolve"); }
     void Solve(double, double, double, char const *, size_t) { throw new Fatal("Domain::Solve: DEPRECATED (the reference throws here too, Source/Domain.cpp:2130); use SolveDiffUpdateFraser"); }
 
@@ -395,6 +395,33 @@ inline void Domain::run_callback(PtDom cb)
     cb(*this);
     sync_up();
     forward_mesh_motion();
+}
+
+// Source/Thermal.cpp:567-719: heat conduction only; one neighbour search (wf_solver_init with solver 3), then per step ThermalCalcs
+// (wf_thermal), GeneralAfter on the host, Time += dt
+inline void Domain::ThermalSolve(double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx)
+{
+    std::cout << "\n--------------Solving (weldform_b200, ThermalSolve on the GPU)----------------------------" << std::endl;
+    solver_kind = 3;
+    deltat = dt; deltatmin = dt;
+    backend_begin(dt);
+    size_t idx_out = 1; double tout = Time;
+    auto t0 = std::chrono::steady_clock::now();
+    refresh_scalars();
+    while (Time < tf && idx_out <= maxidx) {
+        if (GeneralAfter) { ck(wf_thermal(backend), "wf_thermal"); run_callback(GeneralAfter); ck(wf_step_end(backend), "wf_step_end"); }   // :657-674
+        else ck(wf_run(backend, 1), "wf_run");
+        refresh_scalars();
+        if (Time >= tout) {
+            if (TheFileKey != NULL) { String fn; fn.Printf("%s_%04d", TheFileKey, (int)idx_out); sync_down(true); WriteCSV(fn.CStr()); }
+            idx_out++; tout += dtOut;
+            std::cout << "Output No. " << idx_out << " at " << Time << " has been generated\nMax, Min, Avg temps: " << m_maxT << ", " << m_minT << ", " << (m_maxT + m_minT) / 2. << "\n";
+        }
+    }
+    ck(wf_sync(backend), "wf_sync");
+    wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    sync_down(true);
+    std::cout << "\n--------------Solving is finished: " << steps << " steps, " << wall_seconds << " s" << std::endl;
 }
 
 // Source/SolverKickDrift.cpp:21-400 / Source/SolverLeapfrog.cpp:24-450: the loops' control flow with the GeneralAfter calls at the

@@ -62,6 +62,11 @@ def golden_cases():
     th.update(solver=3.0, dt=0.05, Thermal_BC=(np.arange(nth) % 7 == 0).astype(np.int32), h_conv=200.0 * np.ones(nth), T_inf=5.0 * np.ones(nth),
               th_exp=1e-5 * np.ones(nth))
     out["thermal_solve_25"] = th
+    # the same with corrected gradients (CalcGradCorrMatrix once, Thermal.cpp:607-608; the conduction branch of Thermal.cpp:90-111) and two
+    # conductivities / heat capacities, so that pairs of unlike particles use the 4 k_i k_j / (k_i + k_j) mean
+    thg = gc(th)
+    thg.update(nsteps=20.0, k_T=np.where(np.arange(nth) % 3 == 0, 90.0, 150.0), cp_T=np.where(np.arange(nth) % 5 == 0, 700.0, 960.0))
+    out["thermal_solve_gc_20"] = thg
     return out
 
 

@@ -40,6 +40,12 @@ def test_golden_fixtures_are_nontrivial():
     assert np.abs(ref["TIR"]).max() > 0.0                     # tensile-instability tensor populated
     _, ref = golden_tools.load("contact_100")
     assert (ref["delta_cont"] > 0).sum() > 10 and ref["contact_force_sum"][0] > 0.0 and ref["cont_pairs"].size > 0
+    for name in ("thermal_solve_25", "thermal_solve_gc_20"):   # ThermalSolve: conduction + convection act, nothing moves, the expansion term accumulates
+        case, ref = golden_tools.load(name)
+        assert np.abs(ref["T"] - case["T"]).max() > 0.1 and np.abs(ref["dTdt"]).max() > 0.0 and np.abs(ref["q_conv"]).max() > 0.0
+        assert not ref["Displacement"].any() and np.abs(ref["StrainRate"]).max() > 0.0
+    _, ref = golden_tools.load("thermal_solve_gc_20")
+    assert np.abs(ref["gradCorrM"].reshape(-1, 9)[:, [0, 4, 8]] - 1.0).max() > 1e-3
     _, ref = golden_tools.load("nb_only")
     nb = ref["Nb"]
     assert nb.max() == 56                                      # interior particle of the cubic lattice, h = 1.2 dx
@@ -56,6 +62,9 @@ def test_golden_fixtures_are_nontrivial():
     lambda: dict(cases.perturbed(cases.compression(dx=0.03, nsteps=1), amp=60.0), solver=2.0, auto_ts_acc=1.0, tf=2.0e-5),
     lambda: cases.compression_fast(dx=0.03, nsteps=30, perturb_amp=60.0, contact_planes=True),
     lambda: cases.plate_yield(dx=0.0015, nsteps=15, amp=0.3),
+    # Domain::ThermalSolve at another size, with and without corrected gradients
+    lambda: dict(cases.compression(dx=0.03, nsteps=30), solver=3.0, dt=0.05),
+    lambda: dict(cases.compression(dx=0.03, nsteps=12), solver=3.0, dt=0.02, gradKernelCorr=1.0),
 ])
 def test_port_matches_live_reference(oracle_port, maker):
     case = maker()

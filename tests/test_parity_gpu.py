@@ -67,7 +67,7 @@ def test_golden_one_step_bit_exact_fields(harness, name):
 
 @pytest.mark.parametrize("name", ["comp_yield_40", "contact_100", "comp_hollomon_30", "comp_jc_30", "gc_comp_yield_40", "gc_g2_jc_12", "gc_contact_60",
                                   "kd_comp_30", "lf_comp_30", "kd_auto_ts", "lf_auto_ts", "kd_auto_ts_acc", "lf_contact_60", "kd_gc_20",
-                                  "plate_cubic_40", "plate_quintic_10", "fsw_like_80", "gc_fixed_40", "thermal_solve_25"])
+                                  "plate_cubic_40", "plate_quintic_10", "fsw_like_80", "gc_fixed_40", "thermal_solve_25", "thermal_solve_gc_20"])
 def test_golden_multi_step_tight(harness, name):
     """Tens of steps through yield, rebuilds and contact stay within 1e-7 of the reference on every field (state fields
     x, v, rho, sigma sit at 1e-10 or better; a and d(rho)/dt, differences of large terms, are the noisiest)."""
@@ -315,4 +315,24 @@ def test_large_lattice_properties(harness):
     # sum_i m_i a_i = 0 for the symmetric pair force (every particle here is free; BC particles have a forced to 0 -> use interior)
     again = harness.run_case(c, with_pairs=False)
     for k in ("x", "v", "a", "Sigma", "T"):
+        assert np.array_equal(got[k], again[k]), "non-deterministic %s" % k
+
+
+def test_thermal_solve_large_properties(harness):
+    """Domain::ThermalSolve at 1.0 M particles (no oracle at this size; one material class, so the uniform-property variant of the
+    conduction walk runs): without convection the pair terms are antisymmetric, so the total heat sum(T) is conserved (uniform m,
+    rho, cp); the temperature obeys the maximum principle for a stable step; nothing moves; two runs agree bit for bit."""
+    dx = 0.00362
+    c = cases.compression_fast(dx=dx, nsteps=20); c["solver"] = 3.0; c["dt"] = 0.02        # Fourier number 0.09 per step
+    T0 = np.asarray(c["T"], dtype=np.float64)
+    got = harness.run_case(c, with_pairs=False)
+    n = int(got["solid_part_count"][0])
+    assert n > 900000 and n == T0.size
+    T = got["T"]
+    assert np.isfinite(T).all() and np.isfinite(got["dTdt"]).all()
+    assert abs(T.sum() - T0.sum()) <= 1e-11 * T0.sum(), "total heat drifted by %.3e" % (abs(T.sum() - T0.sum()) / T0.sum())
+    assert T.min() >= T0.min() and T.max() <= T0.max() and np.abs(T - T0).max() > 0.05
+    assert not got["Displacement"].any() and abs(got["Time"][0] - 20 * 0.02) < 1e-12
+    again = harness.run_case(c, with_pairs=False)
+    for k in ("T", "dTdt", "StrainRate"):
         assert np.array_equal(got[k], again[k]), "non-deterministic %s" % k

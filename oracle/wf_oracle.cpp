@@ -18,7 +18,7 @@
 // ThermalCalcs (CalcConvHeat, CalcTempInc), CalcKinEnergyEqn/CalcIntEnergyEqn, and the Fraser step order with its
 // neighbour-rebuild cadence (Source/SolverFraser.cpp:133-505). Fixed particles (IsFree = false) are routed as the reference
 // does (no SM pairs); their Shepard-smoothed TIR (PrimaryComputeAcceleration, Domain.cpp:1599-1698, read by nothing) is not
-// restated. gradKernelCorr (Domain.cpp:1832-1940 + the locking branches of InteractionAlt.cpp) is restated, including the FSM pairs of fixed particles in CalcGradCorrMatrix. Not restated: ghost particles, damage, 2-D axisymmetric branches (all "next" or out of scope in SURVEY.md section 8).
+// restated. gradKernelCorr (Domain.cpp:1832-1940 + the locking branches of InteractionAlt.cpp) is restated, including the FSM pairs of fixed particles in CalcGradCorrMatrix. Ghost particles: the Mirror_XYZ rows of AddCylinderLength(..., ghost = true) with MoveGhost (Domain.cpp:795-826, 1142-1236). Not restated: the Symmetric-plane ghosts of AddCylSliceLength, damage, 2-D axisymmetric branches (all "next" or out of scope in SURVEY.md section 8).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -286,6 +286,7 @@ struct Dom {
     int Dimension = 3, KernelType = 0, GradientType = 0, ts_nb_inc = 5;
     double Cellfac = 2.0, deltat = 0.0, Time = 0.0;
     bool thermal_solver = false, pl_heating = false, contact = false, cont_heat_fric = false, cont_heat_cond = false;
+    std::vector<std::pair<int, int> > GhostPairs;   // Domain.h:473 (inner particle, ghost particle)
     int solver = 0;                          // 0 SolveDiffUpdateFraser, 1 SolveDiffUpdateKickDrift, 2 SolveDiffUpdateLeapFrog, 3 ThermalSolve
     bool auto_ts_acc = false; double sqrt_h_a = 0.0025;   // Domain.cpp:109,127
     bool auto_ts = false; double CFL = 0.7, deltatint = 0.0, deltatmin = 0.0, manual_min_ts = 1.e-10;   // Domain.cpp:126,153,170
@@ -953,6 +954,22 @@ struct Dom {
         }
         if (deltat < manual_min_ts) deltat = manual_min_ts;
     }
+    // ---- Source/Domain.cpp:1142-1236 MoveGhost, ghost_type Mirror_XYZ with ghost_plane_axis = 2 (the rows AddCylinderLength(..., ghost = true)
+    //      creates, Domain.cpp:795-826): the ghost takes v, a (mirrored across the plane), Sigma, Strain, ShearStress, StrainRate, RotationRate
+    //      and Density of its inner particle; va / vb are copied too but nothing on this path reads them
+    void MoveGhost() {
+        const int axis = 2;
+        for (size_t gp = 0; gp < GhostPairs.size(); ++gp) {
+            const size_t i = GhostPairs[gp].first, gi = GhostPairs[gp].second;
+            for (int k = 0; k < 3; ++k) v[3 * gi + k] = v[3 * i + k];
+            v[3 * gi + axis] = -v[3 * i + axis];
+            for (int k = 0; k < 3; ++k) a[3 * gi + k] = a[3 * i + k];
+            a[3 * gi + axis] = -a[3 * i + axis];
+            setM(Sigma, gi, getM(Sigma, i)); setM(Strain, gi, getM(Strain, i)); setM(Shear, gi, getM(Shear, i));
+            setM(SRate, gi, getM(SRate, i)); setM(RRate, gi, getM(RRate, i));
+            Density[gi] = Density[i];
+        }
+    }
     // ---- Source/ThermalTest.cpp:8-49 CalcTempIncPair / CalcTempIncPP: the initial dT/dt of ThermalSolve, per particle over the
     //      Nishiura lists (pairs as min first, then as max), always from particle i's side
     void CalcTempIncPP() {
@@ -1039,11 +1056,13 @@ struct Dom {
                 if (gradKernelCorr) Accel_lock(); else Accel_pass();
                 if (contact) ContactWang();
                 UserBC();
+                MoveGhost();                                   // SolverFraser.cpp:335
                 for (size_t i = 0; i < N; ++i) for (int k = 0; k < 3; ++k) {
                     double du = (v[3 * i + k] + 0.0) * deltat + 0.5 * a[3 * i + k] * deltat * deltat;
                     Disp[3 * i + k] += du; x[3 * i + k] += du;
                 }
                 for (size_t i = 0; i < N; ++i) for (int k = 0; k < 3; ++k) v[3 * i + k] += a[3 * i + k] * deltat;
+                MoveGhost();                                   // :358
                 UserBC();
             } else {
                 // SolverKickDrift.cpp:195-271 / SolverLeapfrog.cpp:213-290
@@ -1052,6 +1071,7 @@ struct Dom {
                 if (contact) ContactWang();
                 if (solver == 2) {
                     if (isfirst) for (size_t i = 0; i < 3 * N; ++i) v[i] -= a[i] * 0.5 * deltat;
+                    MoveGhost();                               // SolverLeapfrog.cpp:253
                     UserBC();
                 }
                 prev_deltat = deltat;
@@ -1060,6 +1080,7 @@ struct Dom {
                 if (auto_ts || auto_ts_acc) AdaptiveTimeStep();
                 if (solver == 1) for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * 0.5 * prev_deltat * 1.;
                 else for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * 0.5 * (prev_deltat + deltat);
+                MoveGhost();                                   // SolverKickDrift.cpp:230, SolverLeapfrog.cpp:272
                 UserBC();
                 if (gradKernelCorr) Density_lock(); else Density_pass();
                 if (solver == 1) for (size_t i = 0; i < N; ++i) Density[i] += deltat * dDensity[i] * 1.;
@@ -1068,7 +1089,7 @@ struct Dom {
                     double du = solver == 1 ? (v[i] + 0.0) * deltat * 1. : (v[i] + 0.0) * deltat;
                     Disp[i] += du; x[i] += du;
                 }
-                if (solver == 1) { for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * deltat / 2. * 1.; UserBC(); }
+                if (solver == 1) { for (size_t i = 0; i < 3 * N; ++i) v[i] += a[i] * deltat / 2. * 1.; MoveGhost(); UserBC(); }   // SolverKickDrift.cpp:266
                 if (gradKernelCorr) RateTensors_lock(); else RateTensors_pass();
                 for (size_t i = 0; i < N; ++i) CalcStressStrain(i, deltat);
             }
@@ -1088,7 +1109,7 @@ struct Dom {
     }
 };
 
-// ---- generators: Source/Domain.cpp:674-689 calcHalfPartCount, :708-860 AddCylinderLength (3-D, no ghost) -------
+// ---- generators: Source/Domain.cpp:674-689 calcHalfPartCount, :708-860 AddCylinderLength (3-D; ghost = the three mirror rows at the bottom) -------
 int calcHalfPartCount(double r, double R, int xinc)
 {
     int ypartcount = -1;
@@ -1101,21 +1122,37 @@ int calcHalfPartCount(double r, double R, int xinc)
     }
     return ypartcount;
 }
-void gen_cylinder(const double * V, double Rxy, double Lz, double r, dvec & pts)
+void gen_cylinder(const double * V, double Rxy, double Lz, double r, dvec & pts, bool ghost = false, std::vector<std::pair<int, int> > * ghost_pairs = nullptr)
 {
     int numpartxy = calcHalfPartCount(r, Rxy, 1);
     double zp = V[2] + r;
+    int part_per_row = 0;
     while (zp <= (V[2] + Lz - r)) {
         double yp = V[1] - r - (2. * r * (numpartxy - 1));
         int numypart = 2 * numpartxy, yinc = numpartxy, yinc_sign = -1;
         for (int j = 0; j < numypart; ++j) {
             int numxpart = calcHalfPartCount(r, Rxy, yinc);
             double xp = V[0] - r - (2. * r * (numxpart - 1));
-            for (int i = 0; i < 2 * numxpart; ++i) { pts.push_back(xp); pts.push_back(yp); pts.push_back(zp); xp += 2. * r; }
+            for (int i = 0; i < 2 * numxpart; ++i) { pts.push_back(xp); pts.push_back(yp); pts.push_back(zp); if (zp == V[2] + r) part_per_row++; xp += 2. * r; }
             yp += 2. * r; yinc += yinc_sign;
             if (yinc < 1) { yinc = 1; yinc_sign = 1; }
         }
         zp += 2. * r;
+    }
+    if (ghost) {
+        // Domain.cpp:795-826: three mirror rows below the bottom plane; ghost particle id_part copies particle part (rows 0..2 from the bottom)
+        const int ghost_rows = 3;
+        zp = V[2] - r;
+        int part = 0, id_part = (int)(pts.size() / 3);
+        for (int zinc = 0; zinc < ghost_rows; ++zinc) {
+            for (int xy = 0; xy < part_per_row; ++xy) {
+                const double xp = pts[3 * part], yp = pts[3 * part + 1];
+                pts.push_back(xp); pts.push_back(yp); pts.push_back(zp);
+                if (ghost_pairs) ghost_pairs->push_back(std::make_pair(part, id_part));
+                id_part++; part++;
+            }
+            zp -= 2.0 * r;
+        }
     }
 }
 // ---- Source/Domain.cpp:326-470 AddBoxLength, 3-D cubic packing (type 1, no random) -----------------------------
@@ -1147,7 +1184,7 @@ void load_case(const wfc::File & in, Dom & d)
     const int gen_kind = (int)in.scalar("gen_kind", 0);
     dvec pts; double gmass = 0.0, grho = 0.0, gh = 0.0; int gtag = 0;
     if (gen_kind == 1) {
-        const dvec & g = in.f("gen_args"); gen_cylinder(&g[1], g[4], g[5], g[6], pts);
+        const dvec & g = in.f("gen_args"); gen_cylinder(&g[1], g[4], g[5], g[6], pts, g.size() > 10 && g[10] != 0.0, &d.GhostPairs);
         gtag = (int)g[0]; grho = g[7]; gh = g[8];
         double Vol = M_PI * g[4] * g[4] * g[5]; gmass = Vol * grho / (pts.size() / 3);   // Domain.cpp:839-841
     } else if (gen_kind == 2) {
@@ -1177,6 +1214,7 @@ void load_case(const wfc::File & in, Dom & d)
     d.resize(ntot); d.solid_part_count = (int)nsph;
     for (size_t i = 0; i < 3 * nsph; ++i) d.x[i] = pts[i];
     if (gen_kind != 0) for (size_t i = 0; i < nsph; ++i) { d.Mass[i] = gmass; d.Density[i] = d.RefDensity[i] = grho; d.h[i] = gh; d.ID[i] = gtag; }
+    for (size_t g = 0; g < d.GhostPairs.size(); ++g) d.nowrite[d.GhostPairs[g].second] = 1;     // Domain.cpp:814 not_write_surf_ID
 #define LD_D(NAME, MEM) if (in.has(NAME)) { const dvec & a_ = in.f(NAME); for (size_t i = 0; i < nsph; ++i) d.MEM[i] = a_[i]; }
 #define LD_I(NAME, MEM) if (in.has(NAME)) { const std::vector<int32_t> & a_ = in.i(NAME); for (size_t i = 0; i < nsph; ++i) d.MEM[i] = a_[i]; }
     LD_D("Mass", Mass) LD_D("h", h) LD_I("ID", ID) LD_I("IsFree", IsFree)

@@ -9,9 +9,10 @@ import numpy as np
 BILINEAR, HOLLOMON, JOHNSON_COOK = 0, 1, 2
 
 
-def cylinder_points(V, Rxy, Lz, r):
-    """numpy restatement of the lattice of Domain::AddCylinderLength (Source/Domain.cpp:708-792); used only to size
-    per-particle arrays in case dicts -- positions themselves always come from the implementation under test."""
+def cylinder_points(V, Rxy, Lz, r, ghost=False):
+    """numpy restatement of the lattice of Domain::AddCylinderLength (Source/Domain.cpp:708-826; ghost: the three mirror rows
+    below the bottom plane); used only to size per-particle arrays in case dicts -- positions themselves always come from
+    the implementation under test."""
     def half(r, R, xinc):
         yp, xp, c = r, r + (xinc - 1) * 2.0 * r, 1
         while np.sqrt(yp * yp + xp * xp) <= R - r:
@@ -35,6 +36,14 @@ def cylinder_points(V, Rxy, Lz, r):
             if yinc < 1:
                 yinc, sign = 1, 1
         zp += 2.0 * r
+    if ghost:
+        row = [p for p in pts if p[2] == V[2] + r]
+        per_row = len(row)
+        zp = V[2] - r
+        for k in range(3):
+            for q in range(per_row):
+                pts.append((pts[k * per_row + q][0], pts[k * per_row + q][1], zp))
+            zp -= 2.0 * r
     return np.array(pts, dtype=np.float64)
 
 
@@ -136,22 +145,25 @@ def fsw_like(dx=0.0012, nsteps=1, wrot=10000.0, vplunge=10.0, vfac=1.0, L=0.05, 
 
 
 def compression(dx=0.03, nsteps=1, thermal=True, pl_heating=True, alpha=1.0, beta=0.0, ti=0.3, gradient_type=0,
-                vmax=10.0, tau=0.005, cfl=0.2, fy=300.0e6, model=BILINEAR, t_field=True, ts_nb_inc=5):
-    """examples/Compression_thermal.cpp:71-169 scaled by dx (shipped dx = 0.015 -> 12 144 particles)."""
+                vmax=10.0, tau=0.005, cfl=0.2, fy=300.0e6, model=BILINEAR, t_field=True, ts_nb_inc=5, ghost=False):
+    """examples/Compression_thermal.cpp:71-169 scaled by dx (shipped dx = 0.015 -> 12 144 particles).
+    ghost: AddCylinderLength(..., ghost = true) -- three mirror rows below the bottom plane driven by MoveGhost; the bottom rows
+    are then left free (no ID 2), the symmetry plane holds the body."""
     rho, K, G = 2700.0, 6.7549e10, 2.5902e10
     R, L = 0.15, 0.56
     h = 1.2 * dx
     Cs = np.sqrt(K / rho)
     V = (0.0, 0.0, -L / 10.0)
-    pts = cylinder_points(V, R, L + 2.0 * L / 10.0, dx / 2.0)
+    pts = cylinder_points(V, R, L + 2.0 * L / 10.0, dx / 2.0, ghost)
     n = len(pts)
     z = pts[:, 2]
     ID = np.full(n, 1, np.int32)
-    ID[z < 0] = 2
+    if not ghost:
+        ID[z < 0] = 2
     ID[z > L] = 3
     ones = np.ones(n)
     case = dict(
-        gen_kind=1.0, gen_args=np.array([1, V[0], V[1], V[2], R, L + 2.0 * L / 10.0, dx / 2.0, rho, h, 0, 0], float),
+        gen_kind=1.0, gen_args=np.array([1, V[0], V[1], V[2], R, L + 2.0 * L / 10.0, dx / 2.0, rho, h, 0, 1 if ghost else 0], float),
         Dimension=3.0, KernelType=0.0, GradientType=float(gradient_type), DomMax=np.array([L, -1e11, -1e11]), DomMin=np.array([-L, 1e11, 1e11]),
         ID=ID, G=G * ones, Cs=Cs * ones, PresEq=np.zeros(n, np.int32), Material=np.full(n, 2, np.int32), Fail=np.ones(n, np.int32),
         Sigmay=fy * ones, Alpha=alpha * ones, Beta=beta * ones, TI=ti * ones, TIInitDist=dx * ones,
@@ -178,7 +190,7 @@ def perturbed(case, amp=5.0, seed=1):
     """Give every particle a smooth non-zero initial velocity so that one step exercises every pair term."""
     c = dict(case)
     g = c["gen_args"]
-    pts = cylinder_points((g[1], g[2], g[3]), g[4], g[5], g[6])
+    pts = cylinder_points((g[1], g[2], g[3]), g[4], g[5], g[6], len(g) > 10 and g[10] != 0)
     x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
     v = np.stack([amp * np.sin(9.0 * y + seed) * np.cos(4.0 * z), amp * np.cos(8.0 * x - seed) * np.sin(3.0 * z), -amp * z * (1.0 + 0.3 * np.sin(11.0 * x * y))], axis=1)
     c["v"] = v.reshape(-1)

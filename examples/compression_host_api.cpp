@@ -5,7 +5,8 @@
 // the top rows and holds the bottom rows, call SolveDiffUpdateFraser. Everything under Solve runs on the GPU.
 //
 //   usage: compression_host_api <dx> <nsteps> <perturb_amp> <out.bin> [solver: 0 Fraser (default), 1 KickDrift, 2 LeapFrog,
-//          3 ThermalSolve (heat conduction only, time step 0.05 s)]
+//          3 ThermalSolve (heat conduction only, time step 0.05 s)] [ghost: 1 = AddCylinderLength(..., ghost = true), the bottom rows are
+//          then left free and the mirror rows below the bottom plane hold the body (Domain::MoveGhost)]
 // out.bin: int64 n, then n*(x[3], v[3], Displacement[3], pl_strain, T, Density, Sigma[9]) as float64 (creation order).
 #include <cstdio>
 #include "Domain.h"
@@ -37,14 +38,15 @@ int main(int argc, char ** argv) try
     const double h = dx * 1.2, Cs = sqrt(K / rho);
     dom.GeneralAfter = &UserAcc;
     dom.DomMax(0) = L; dom.DomMin(0) = -L;
-    dom.AddCylinderLength(1, Vec3_t(0., 0., -L / 10.), R, L + 2. * L / 10., dx / 2., rho, h, false);
+    const bool ghost = argc > 6 && std::atoi(argv[6]) != 0;
+    dom.AddCylinderLength(1, Vec3_t(0., 0., -L / 10.), R, L + 2. * L / 10., dx / 2., rho, h, false, ghost);
     for (size_t a = 0; a < dom.Particles.Size(); a++) {
         SPH::Particle * P = dom.Particles[a];
         P->G = G; P->PresEq = 0; P->k_T = 150.; P->cp_T = 960.; P->Cs = Cs; P->Shepard = false; P->Material = 2; P->Fail = 1; P->Sigmay = Fy;
         P->Alpha = 1.0; P->TI = 0.3; P->TIInitDist = dx; P->th_exp = 0.;
         const double x = P->x(0), y = P->x(1), z = P->x(2);
         P->T = 20.0 + 15.0 * sin(7.0 * x) * cos(5.0 * z);
-        if (z < 0) P->ID = 2;
+        if (z < 0 && !ghost) P->ID = 2;
         if (z > L) P->ID = 3;
         if (amp != 0.0) P->v = Vec3_t(amp * sin(9.0 * y + 1) * cos(4.0 * z), amp * cos(8.0 * x - 1) * sin(3.0 * z), -amp * z * (1.0 + 0.3 * sin(11.0 * x * y)));
     }

@@ -144,6 +144,10 @@ void wf_default_params(wf_params *p);               /* Domain::Domain defaults *
 int wf_set_params(wf_ctx *ctx, const wf_params *p);
 int wf_set_materials(wf_ctx *ctx, const wf_material *m, int n);
 int wf_set_particles(wf_ctx *ctx, const wf_particles *p);
+/* Domain::GhostPairs (Domain.h:473) for Domain::MoveGhost (Domain.cpp:1142-1236), ghost_type Mirror_XYZ: n x (inner, ghost) creation indices,
+ * axis = ghost_plane_axis per pair (NULL: 2, what AddCylinderLength creates). After wf_set_particles, before wf_solver_init; one GPU only.
+ * The Symmetric-plane ghosts of AddCylSliceLength are not implemented. */
+int wf_set_ghost_pairs(wf_ctx *ctx, const int32_t *pairs, const int32_t *axis, int64_t n);
 int wf_add_mesh(wf_ctx *ctx, const wf_mesh *m);                       /* AddTrimeshParticles */
 int wf_mesh_set_motion(wf_ctx *ctx, int mesh, const double v[3], const double w[3]);   /* TriMesh::SetVel / SetRotAxisVel */
 int wf_mesh_set_ramp(wf_ctx *ctx, int mesh, const double vmax[3], double tau);         /* v(t) = vmax*min(t/tau,1), evaluated on device */
@@ -185,6 +189,7 @@ int wf_contact(wf_ctx *ctx);                        /* CalcContactForcesWang (:3
 int wf_apply_bcs(wf_ctx *ctx);                      /* device-side GeneralAfter (:332,:360) */
 int wf_integrate_pos(wf_ctx *ctx);                  /* x_prev, Displacement, x update (:337-343) */
 int wf_integrate_vel(wf_ctx *ctx);                  /* v += a*dt (:352-355) */
+int wf_move_ghost(wf_ctx *ctx);                     /* MoveGhost (:335,:358); part of wf_fraser_stage_b1 / b2 and of wf_solver_stage 1..3; no-op without ghost pairs */
 int wf_thermal(wf_ctx *ctx);                        /* CalcPlasticWorkHeat + ThermalCalcs (:369-370) */
 int wf_energy(wf_ctx *ctx);                         /* CalcKinEnergyEqn + CalcIntEnergyEqn (:375-376) */
 int wf_step_end(wf_ctx *ctx);                       /* Time += dt, TriMesh::Update, UpdateContactParticles, cadence (:384-412) */
@@ -210,6 +215,10 @@ int wf_run_until(wf_ctx *ctx, double tf, int64_t *steps_done);
  * Call with pts = NULL to get the count. Returns particle count or a negative wf_status. ------------------------ */
 int64_t wf_gen_cylinder(const double V[3], double Rxy, double Lz, double r, double *pts, int64_t cap);
 int64_t wf_gen_box(const double V[3], double Lx, double Ly, double Lz, double r, double *pts, int64_t cap, double box_dims[3]);
+/* AddCylinderLength(..., ghost = true), Domain.cpp:795-826: the lattice plus three mirror rows below the bottom plane; pairs = (inner, ghost)
+ * creation indices (Domain::GhostPairs). pts / pairs may be NULL to get the counts. The generator's particle mass divides by the count
+ * including the ghosts (Domain.cpp:839-841). */
+int64_t wf_gen_cylinder_ghost(const double V[3], double Rxy, double Lz, double r, double *pts, int64_t cap, int32_t *pairs, int64_t pair_cap, int64_t *n_pairs);
 
 /* ---- multi-GPU: one process (and one wf_ctx) per GPU, 1-D slab decomposition of the cell grid along its longest axis, NCCL
  * point-to-point halos; the reference is single-process (no counterpart). Rank 0 obtains an id with wf_comm_unique_id and

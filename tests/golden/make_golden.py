@@ -67,6 +67,11 @@ def golden_cases():
     thg = gc(th)
     thg.update(nsteps=20.0, k_T=np.where(np.arange(nth) % 3 == 0, 90.0, 150.0), cp_T=np.where(np.arange(nth) % 5 == 0, 700.0, 960.0))
     out["thermal_solve_gc_20"] = thg
+    # AddCylinderLength(..., ghost = true): three mirror rows below the bottom plane driven by Domain::MoveGhost; bottom rows left free
+    out["ghost_comp_1step"] = cases.perturbed(cases.compression(dx=0.04, nsteps=1, ghost=True), amp=60.0)
+    out["ghost_comp_yield_40"] = cases.perturbed(cases.compression(dx=0.04, nsteps=40, ghost=True), amp=60.0)
+    out["ghost_kd_25"] = dict(cases.perturbed(cases.compression(dx=0.04, nsteps=25, ghost=True), amp=60.0), solver=1.0)
+    out["ghost_lf_25"] = dict(cases.perturbed(cases.compression(dx=0.04, nsteps=25, ghost=True, model=cases.HOLLOMON), amp=60.0), solver=2.0)
     return out
 
 

@@ -68,6 +68,20 @@ def test_cylinder_generator_matches_reference_lattice(product_lib):
     assert pts.shape == ref.shape and np.array_equal(pts, ref)
 
 
+def test_ghost_cylinder_generator_matches_reference_lattice(product_lib):
+    """AddCylinderLength(..., ghost = true), Domain.cpp:795-826: three mirror rows below the bottom plane; ghost k copies particle k."""
+    from weldform_b200 import api
+    V, R, L, r = (0.0, 0.0, -0.056), 0.15, 0.672, 0.02
+    pts, pairs = api.gen_cylinder_ghost(V, R, L, r)
+    ref = cases.cylinder_points(V, R, L, r, ghost=True)      # restatement checked against wf_ref through the ghost_* goldens
+    base = api.gen_cylinder(V, R, L, r)
+    assert pts.shape == ref.shape and np.array_equal(pts, ref) and np.array_equal(pts[:len(base)], base)
+    per_row = int((base[:, 2] == base[0, 2]).sum())
+    assert len(pairs) == 3 * per_row and np.array_equal(pairs[:, 0], np.arange(3 * per_row)) and np.array_equal(pairs[:, 1], len(base) + np.arange(3 * per_row))
+    assert np.array_equal(pts[pairs[:, 1], :2], pts[pairs[:, 0], :2])                      # same x, y
+    assert np.allclose(pts[pairs[:, 1], 2] + pts[pairs[:, 0], 2], 2.0 * V[2], atol=1e-15)   # mirrored across z = V[2]
+
+
 def test_box_generator_counts(product_lib):
     from weldform_b200 import api
     pts, dims = api.gen_box((0.0, 0.0, 0.0), 0.1, 0.05, 0.02, 0.005)

@@ -52,9 +52,18 @@ def test_unsupported_solvers_fail_loudly(product_lib):
 int main() { SPH::Domain d; int hits = 0;
   try { d.Solve(1, 1, 1, "x", 1); } catch (Fatal * f) { ++hits; delete f; }
   try { d.SolveDiffUpdateVerlet(1, 1, 1, "x", 1); } catch (Fatal * f) { ++hits; delete f; }
-  try { d.AddCylinderLength(1, Vec3_t(0, 0, 0), 0.1, 0.1, 0.01, 1000., 0.012, false, true); } catch (Fatal * f) { ++hits; delete f; }
+  try { d.ThermalStructSolve(1, 1, 1, "x", 1); } catch (Fatal * f) { ++hits; delete f; }
   d.AddCylinderLength(1, Vec3_t(0, 0, 0), 0.1, 0.1, 0.01, 1000., 0.012, false);
-  return (hits == 3 && d.Particles.Size() > 100 && d.solid_part_count == (int)d.Particles.Size()) ? 0 : 1; }
+  const size_t plain = d.Particles.Size();
+  SPH::Domain g;                                    // ghost = true: three mirror rows below the bottom plane, GhostPairs (Source/Domain.cpp:795-826)
+  g.AddCylinderLength(1, Vec3_t(0, 0, 0), 0.1, 0.1, 0.01, 1000., 0.012, false, true);
+  const size_t ng = g.GhostPairs.Size();
+  bool ok = ng > 0 && g.Particles.Size() == plain + ng && g.solid_part_count == (int)g.Particles.Size();
+  for (size_t k = 0; k < ng && ok; ++k) {
+    const SPH::Particle * in = g.Particles[g.GhostPairs[k].first], * gh = g.Particles[g.GhostPairs[k].second];
+    ok = gh->not_write_surf_ID && gh->ghost_plane_axis == 2 && gh->x(0) == in->x(0) && gh->x(1) == in->x(1) && gh->x(2) < 0.0 && in->x(2) > 0.0 && gh->Mass == in->Mass;
+  }
+  return (hits == 3 && ok && plain > 100 && d.solid_part_count == (int)plain) ? 0 : 1; }
 '''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.cpp"), "w").write(src)
@@ -116,3 +125,26 @@ def test_host_domain_thermal_solve_matches_device_run_and_oracle(host_example, o
     assert np.abs(ref["T"] - T0).max() > 0.05 and not ref["Displacement"].any(), "conduction must act, nothing may move"
     worst = {k: ot.max_rel(got[k], ref[k]) for k in got}
     assert max(worst.values()) < 1e-9, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", [0, 2])
+def test_host_domain_ghost_rows_match_device_run_and_oracle(host_example, oracle_port, solver):
+    """AddCylinderLength(..., ghost = true) through the host mirror: GhostPairs reach the device (wf_set_ghost_pairs), Domain::MoveGhost runs
+    inside wf_fraser_stage_b1 / b2 (wf_solver_stage 1..3 for LeapFrog) around the host GeneralAfter callback."""
+    from weldform_b200 import harness
+    dx, nsteps, amp = 0.03, 40, 60.0
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.bin")
+        r = subprocess.run([host_example, str(dx), str(nsteps), str(amp), out, str(solver), "1"], capture_output=True, text=True, timeout=600, env=dict(os.environ, WELDFORM_SYNC="tagged"))
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        got = _read_bin(out)
+    case = cases.perturbed(cases.compression(dx=dx, nsteps=nsteps, ghost=True), amp=amp)
+    case["solver"] = float(solver)
+    dev = harness.run_case(case, with_pairs=False)
+    for k in got:
+        assert np.array_equal(got[k], dev[k]), "host-callback run differs from the device-BC run in %s (%.3e)" % (k, ot.max_rel(got[k], dev[k]))
+    ref = ot.run_port(case)
+    assert ref["pl_strain"].max() > 1e-3
+    worst = {k: ot.max_rel(got[k], ref[k]) for k in got}
+    assert max(worst.values()) < 1e-6, worst

@@ -46,6 +46,20 @@ def test_golden_fixtures_are_nontrivial():
         assert not ref["Displacement"].any() and np.abs(ref["StrainRate"]).max() > 0.0
     _, ref = golden_tools.load("thermal_solve_gc_20")
     assert np.abs(ref["gradCorrM"].reshape(-1, 9)[:, [0, 4, 8]] - 1.0).max() > 1e-3
+    for name in ("ghost_comp_1step", "ghost_comp_yield_40", "ghost_kd_25", "ghost_lf_25"):      # MoveGhost: the mirror rows carry their inner particles' state
+        case, ref = golden_tools.load(name)
+        g = case["gen_args"]
+        pts = cases.cylinder_points((g[1], g[2], g[3]), g[4], g[5], g[6], ghost=True)
+        per_row = int((pts[:, 2] == pts[0, 2]).sum()); n0 = len(pts) - 3 * per_row
+        inner, ghost = np.arange(3 * per_row), n0 + np.arange(3 * per_row)
+        v = ref["v"].reshape(-1, 3)
+        assert np.abs(v[inner, 2]).max() > 1.0
+        if name != "ghost_kd_25" and name != "ghost_lf_25":       # those loops update the stresses after their last MoveGhost
+            assert np.array_equal(v[ghost, :2], v[inner, :2]) and np.array_equal(v[ghost, 2], -v[inner, 2])
+            assert np.array_equal(ref["Density"][ghost], ref["Density"][inner]) and np.array_equal(ref["Sigma"].reshape(-1, 9)[ghost], ref["Sigma"].reshape(-1, 9)[inner])
+        assert int(ref["n_particles"][0]) == len(pts)
+    _, ref = golden_tools.load("ghost_comp_yield_40")
+    assert ref["pl_strain"].max() > 1e-3
     _, ref = golden_tools.load("nb_only")
     nb = ref["Nb"]
     assert nb.max() == 56                                      # interior particle of the cubic lattice, h = 1.2 dx
@@ -65,6 +79,9 @@ def test_golden_fixtures_are_nontrivial():
     # Domain::ThermalSolve at another size, with and without corrected gradients
     lambda: dict(cases.compression(dx=0.03, nsteps=30), solver=3.0, dt=0.05),
     lambda: dict(cases.compression(dx=0.03, nsteps=12), solver=3.0, dt=0.02, gradKernelCorr=1.0),
+    # ghost rows (Domain::MoveGhost) at another size: the Fraser loop with corrected gradients, the LeapFrog loop with the adaptive step
+    lambda: dict(cases.perturbed(cases.compression(dx=0.03, nsteps=20, ghost=True, model=cases.JOHNSON_COOK), amp=60.0), gradKernelCorr=1.0),
+    lambda: dict(cases.perturbed(cases.compression(dx=0.03, nsteps=1, ghost=True), amp=60.0), solver=2.0, auto_ts=1.0, CFL=0.15, tf=2.0e-5),
 ])
 def test_port_matches_live_reference(oracle_port, maker):
     case = maker()

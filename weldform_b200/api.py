@@ -97,6 +97,8 @@ def load_library():
         "wf_run": ([vp, C.c_int64], C.c_int), "wf_solver_stage": ([vp, C.c_int], C.c_int), "wf_run_until": ([vp, C.c_double, C.POINTER(C.c_int64)], C.c_int),
         "wf_gen_cylinder": ([_PD, C.c_double, C.c_double, C.c_double, _PD, C.c_int64], C.c_int64),
         "wf_gen_box": ([_PD, C.c_double, C.c_double, C.c_double, C.c_double, _PD, C.c_int64, _PD], C.c_int64),
+        "wf_gen_cylinder_ghost": ([_PD, C.c_double, C.c_double, C.c_double, _PD, C.c_int64, _PI, C.c_int64, C.POINTER(C.c_int64)], C.c_int64),
+        "wf_set_ghost_pairs": ([vp, _PI, _PI, C.c_int64], C.c_int), "wf_move_ghost": ([vp], C.c_int),
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
         "wf_comm_unique_id": ([vp], C.c_int), "wf_comm_init": ([vp, C.c_int, C.c_int, vp], C.c_int), "wf_comm_info": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "wf_plan_slabs": ([_PD, _PD, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
@@ -135,6 +137,20 @@ def gen_cylinder(V, Rxy, Lz, r):
     pts = np.empty((n, 3))
     L.wf_gen_cylinder(Vc, Rxy, Lz, r, _dp(pts), n)
     return pts
+
+
+def gen_cylinder_ghost(V, Rxy, Lz, r):
+    """Domain::AddCylinderLength(..., ghost = true): lattice + three mirror rows, and the (inner, ghost) index pairs."""
+    L = load_library()
+    Vc = (C.c_double * 3)(*V)
+    npairs = C.c_int64(0)
+    n = L.wf_gen_cylinder_ghost(Vc, Rxy, Lz, r, None, 0, None, 0, C.byref(npairs))
+    if n < 0:
+        raise WeldformError("wf_gen_cylinder_ghost: status %d" % n)
+    pts = np.empty((n, 3))
+    pairs = np.empty((npairs.value, 2), np.int32)
+    L.wf_gen_cylinder_ghost(Vc, Rxy, Lz, r, _dp(pts), n, _ip(pairs), npairs.value, C.byref(npairs))
+    return pts, pairs
 
 
 def gen_box(V, Lx, Ly, Lz, r):
@@ -262,6 +278,15 @@ class Context:
         if unknown:
             raise WeldformError("set_particles: unknown arrays %s" % sorted(unknown))
         self._ck(self.L.wf_set_particles(self.h, C.byref(p)), "wf_set_particles")
+
+    def set_ghost_pairs(self, pairs, axis=None):
+        """Domain::GhostPairs for MoveGhost: (inner, ghost) creation indices, Mirror_XYZ across ghost_plane_axis (default 2)"""
+        pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        ax = None if axis is None else np.ascontiguousarray(axis, np.int32)
+        self._ck(self.L.wf_set_ghost_pairs(self.h, _ip(pr), None if ax is None else _ip(ax), len(pr)), "wf_set_ghost_pairs")
+
+    def move_ghost(self):
+        self._ck(self.L.wf_move_ghost(self.h), "wf_move_ghost")
 
     def mesh_set_ramp(self, mesh, vmax, tau):
         self._ck(self.L.wf_mesh_set_ramp(self.h, mesh, (C.c_double * 3)(*vmax), tau), "wf_mesh_set_ramp")

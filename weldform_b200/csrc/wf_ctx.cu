@@ -89,6 +89,7 @@ extern "C" void wf_destroy(wf_ctx *c)
     cudaFree(c->dm.enormal); cudaFree(c->dm.ev); cudaFree(c->dm.pplane); cudaFree(c->dm.motion);
     cudaFree(c->comm.d_emig); cudaFree(c->comm.d_cnt); cudaFree(c->comm.d_rank); cudaFree(c->comm.d_all);
     for (int d = 0; d < 2; ++d) { cudaFree(c->comm.stage_send[d]); cudaFree(c->comm.stage_recv[d]); }
+    cudaFree(c->d_ghost);
     for (auto &sb : c->subsets) cudaFree(sb.first);
     cudaFree(c->stage); if (c->h_stage) cudaFreeHost(c->h_stage); if (c->h_sc) cudaFreeHost(c->h_sc);
     prof_resolve(c); for (auto &e : c->prof_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -695,6 +696,68 @@ extern "C" int64_t wf_gen_cylinder(const double V[3], double Rxy, double Lz, dou
         zp += 2. * r;
     }
     return n;
+}
+// Source/Domain.cpp:795-826: AddCylinderLength(..., ghost = true) appends three mirror rows below the bottom plane (z = V[2] - r, - 3r, - 5r);
+// ghost particle id_part copies particle part, part running over the first three rows of the lattice from the bottom (GhostPairs, ghost_type
+// Mirror_XYZ, ghost_plane_axis 2, not_write_surf_ID). pts / pairs may be NULL to get the counts; pairs holds (inner, ghost) creation indices.
+// The particle mass of that generator divides the cylinder's mass by the count INCLUDING the ghosts (Domain.cpp:839-841).
+extern "C" int64_t wf_gen_cylinder_ghost(const double V[3], double Rxy, double Lz, double r, double *pts, int64_t cap, int32_t *pairs, int64_t pair_cap, int64_t *n_pairs)
+{
+    if (!V || r <= 0.0) return WF_ERR_ARG;
+    const int64_t n0 = wf_gen_cylinder(V, Rxy, Lz, r, pts, cap);
+    if (n0 < 0) return n0;
+    // particles of the first row: those created with zp == V[2] + r
+    int64_t per_row = 0;
+    {   const int numpartxy = half_part_count(r, Rxy, 1);
+        int yinc = numpartxy, yinc_sign = -1;
+        for (int j = 0; j < 2 * numpartxy; ++j) { per_row += 2 * half_part_count(r, Rxy, yinc); yinc += yinc_sign; if (yinc < 1) { yinc = 1; yinc_sign = 1; } }
+        if (n0 == 0) per_row = 0;
+    }
+    const int ghost_rows = 3;
+    if (3 * per_row > n0) return WF_ERR_ARG;                 // fewer than three lattice rows: the reference indexes past the lattice here
+    int64_t n = n0, np = 0;
+    double zp = V[2] - r;
+    int64_t part = 0;
+    for (int zinc = 0; zinc < ghost_rows; ++zinc) {
+        for (int64_t xy = 0; xy < per_row; ++xy) {
+            if (pts) { if (n >= cap) return WF_ERR_ARG; pts[3 * n] = pts[3 * part]; pts[3 * n + 1] = pts[3 * part + 1]; pts[3 * n + 2] = zp; }
+            if (pairs) { if (np >= pair_cap) return WF_ERR_ARG; pairs[2 * np] = (int32_t)part; pairs[2 * np + 1] = (int32_t)n; }
+            ++n; ++np; ++part;
+        }
+        zp -= 2.0 * r;
+    }
+    if (n_pairs) *n_pairs = np;
+    return n;
+}
+// Domain::GhostPairs (Domain.h:473) for Domain::MoveGhost, ghost_type Mirror_XYZ: pairs = n x (inner, ghost) creation indices of SPH particles,
+// axis = ghost_plane_axis per pair (NULL: 2 for all, what AddCylinderLength creates). After wf_set_particles, before wf_solver_init.
+extern "C" int wf_set_ghost_pairs(wf_ctx *c, const int32_t *pairs, const int32_t *axis, int64_t n)
+{
+    if (!c) return WF_ERR_ARG;
+    if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: call wf_set_particles first");
+    if (c->solver_ready) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: the solver is already initialised");
+    if (n < 0 || (n > 0 && !pairs)) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: bad arguments");
+    if (c->comm.nranks > 1 && n > 0) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles on more than one GPU are not implemented");
+    cudaSetDevice(c->device);
+    std::vector<int> rec((size_t)3 * n);
+    std::vector<char> is_ghost((size_t)c->nsph, 0);
+    for (int64_t g = 0; g < n; ++g) {
+        const int32_t i = pairs[2 * g], gi = pairs[2 * g + 1], ax = axis ? axis[g] : 2;
+        if (i < 0 || gi < 0 || i >= c->nsph || gi >= c->nsph || i == gi) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: pair %lld (%d, %d) out of range", (long long)g, i, gi);
+        if (ax < 0 || ax > 2) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: ghost_plane_axis %d", ax);
+        if (is_ghost[gi]) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: particle %d is the ghost of two pairs", gi);
+        is_ghost[gi] = 1;
+        rec[3 * g] = i; rec[3 * g + 1] = gi; rec[3 * g + 2] = ax;
+    }
+    // MoveGhost walks the pairs serially; the parallel copy is the same thing only while no inner particle is itself a ghost
+    for (int64_t g = 0; g < n; ++g) if (is_ghost[pairs[2 * g]]) return fail(c, WF_ERR_UNSUPPORTED, "wf_set_ghost_pairs: inner particle %d is itself a ghost (chained mirrors are not implemented)", pairs[2 * g]);
+    cudaFree(c->d_ghost); c->d_ghost = nullptr; c->n_ghost = 0;
+    if (n > 0) {
+        WF_CUDA(c, cudaMalloc(&c->d_ghost, rec.size() * sizeof(int)));
+        WF_CUDA(c, cudaMemcpy(c->d_ghost, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice));
+        c->n_ghost = n;
+    }
+    return 0;
 }
 // Source/Domain.cpp:326-455 AddBoxLength, 3-D cubic packing (type 1, random = false); box_dims = Max + r - V (mass rule :447-455)
 extern "C" int64_t wf_gen_box(const double V[3], double Lx, double Ly, double Lz, double r, double *pts, int64_t cap, double box_dims[3])

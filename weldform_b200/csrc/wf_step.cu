@@ -56,6 +56,32 @@ __global__ void k_bc_move(StepArgs a, int mode)
     OWN(F_AX) = ax; OWN(F_AY) = ay; OWN(F_AZ) = az;
 }
 
+// Domain::MoveGhost (Domain.cpp:1142-1236), ghost_type Mirror_XYZ: the ghost particle takes v and a of its inner particle, mirrored across the
+// plane normal to ghost_plane_axis, and its Sigma, Strain, ShearStress, StrainRate, RotationRate and Density. One thread per GhostPairs entry
+// (creation indices -> slots through slot_of); inner particles are never ghosts, so the pairs are independent. The gathered caches that
+// derive from the density (m/rho in Q1.w, P/rho^2 in Q2.w, with the ghost's own mass and pressure) follow the copy; Sigma/rho^2 (S0, S1)
+// is rewritten by the ghost's own stress update before any momentum sum reads it.
+__global__ void k_move_ghost(StepArgs a, const int *gp, int64_t npairs, const int *slot_of)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= npairs) return;
+    const int64_t si = slot_of[gp[3 * g]], s = slot_of[gp[3 * g + 1]];
+    const int axis = gp[3 * g + 2];
+#define INNER(f) a.F[(int64_t)(f) * a.cap + si]
+    const double4 wi = a.Q1[si];
+    double v[3] = { wi.x, wi.y, wi.z }, acc[3] = { INNER(F_AX), INNER(F_AY), INNER(F_AZ) };
+    v[axis] = -v[axis]; acc[axis] = -acc[axis];
+    OWN(F_AX) = acc[0]; OWN(F_AY) = acc[1]; OWN(F_AZ) = acc[2];
+    for (int k = 0; k < 6; ++k) { OWN(F_SG + k) = INNER(F_SG + k); OWN(F_ST + k) = INNER(F_ST + k); OWN(F_SH + k) = INNER(F_SH + k); OWN(F_SR + k) = INNER(F_SR + k); }
+    for (int k = 0; k < 3; ++k) OWN(F_RR + k) = INNER(F_RR + k);
+    double4 q2 = a.Q2[s];
+    const double rho = a.Q2[si].y;
+    q2.y = rho; q2.w = OWN(F_PRES) / (rho * rho);
+    a.Q2[s] = q2;
+    a.Q1[s] = make_double4(v[0], v[1], v[2], q2.x / rho);
+#undef INNER
+}
+
 // Velocity kicks and the drift of the KickDrift / LeapFrog step orders, every particle (SolverKickDrift.cpp:225-259, SolverLeapfrog.cpp:241-286):
 //   kind 0  v -= a*0.5*dt             (LeapFrog, first step only)      kind 1  v += a*0.5*prev_dt*factor   (KickDrift, factor = 1.)
 //   kind 2  v += a*0.5*(prev_dt+dt)   (LeapFrog)                       kind 3  v += a*dt/2.*factor          (KickDrift)
@@ -332,6 +358,15 @@ static int bc_move(wf_ctx *c, int mode, int pk)
 int apply_bcs_impl(wf_ctx *c) { if (c->n_bcs == 0 && c->meshes.empty()) return 0; return bc_move(c, 1, PK_BC); }
 int move_pos_impl(wf_ctx *c) { return bc_move(c, 2, PK_MOVE); }
 int move_vel_impl(wf_ctx *c) { return bc_move(c, 4, PK_MOVE); }
+int move_ghost_impl(wf_ctx *c)
+{
+    if (c->n_ghost == 0) return 0;
+    ProfScope ps(c, PK_MOVE);
+    StepArgs a = make_step_args(c);
+    k_move_ghost<<<grid_for(c->n_ghost, 128), 128, 0, c->stream>>>(a, c->d_ghost, c->n_ghost, c->slot_of); WF_LAUNCH_CHECK(c); c->launches++;
+    c->dens_valid = false;
+    return 0;
+}
 
 int reduce_impl(wf_ctx *c, bool accumulate)
 {
@@ -381,6 +416,8 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_solver_init: no particles");
     if (!(dt > 0.0)) return fail(c, WF_ERR_ARG, "wf_solver_init: dt must be > 0");
     cudaSetDevice(c->device);
+    if (c->n_ghost > 0 && c->comm.nranks > 1) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles on more than one GPU are not implemented");
+    if (c->n_ghost > 0 && c->prm.solver == 3) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles in ThermalSolve: the reference's loop never calls MoveGhost; not implemented");
     c->dt_init = c->dt_min = dt;
     c->dt = dt; c->time = 0.0; c->ts_i = 0; c->isfirst = true; c->isyielding = false; c->steps = 0; c->dens_valid = false; c->in_step = false;
     k_set_time<<<1, 1, 0, c->stream>>>(c->d_sc, 0.0, dt); WF_LAUNCH_CHECK(c);
@@ -514,8 +551,9 @@ extern "C" int wf_fraser_stage_a(wf_ctx *c)
     WF_CHECK(contact_impl(c));
     return 0;
 }
-extern "C" int wf_fraser_stage_b1(wf_ctx *c) { WF_NEED_READY(c); return move_pos_impl(c); }
-extern "C" int wf_fraser_stage_b2(wf_ctx *c) { WF_NEED_READY(c); return move_vel_impl(c); }
+extern "C" int wf_fraser_stage_b1(wf_ctx *c) { WF_NEED_READY(c); WF_CHECK(move_ghost_impl(c)); return move_pos_impl(c); }      // MoveGhost (:335), x update
+extern "C" int wf_fraser_stage_b2(wf_ctx *c) { WF_NEED_READY(c); WF_CHECK(move_vel_impl(c)); return move_ghost_impl(c); }      // v update, MoveGhost (:358)
+extern "C" int wf_move_ghost(wf_ctx *c) { WF_NEED_READY(c); return move_ghost_impl(c); }
 extern "C" int wf_fraser_stage_c(wf_ctx *c)
 {
     WF_NEED_READY(c);
@@ -574,6 +612,7 @@ static int kdlf_stage(wf_ctx *c, int stage, bool device_bcs)
         WF_CHECK(contact_impl(c));
         if (solver == 2) {
             if (c->isfirst) WF_CHECK(kick(c, 0, c->dt));
+            WF_CHECK(move_ghost_impl(c));                            // SolverLeapfrog.cpp:253
             if (device_bcs) WF_CHECK(apply_bcs_impl(c));
         }
         return 0;
@@ -595,6 +634,7 @@ static int kdlf_stage(wf_ctx *c, int stage, bool device_bcs)
             adaptive_time_step(c);
         }
         WF_CHECK(kick(c, solver == 1 ? 1 : 2, c->prev_dt));
+        WF_CHECK(move_ghost_impl(c));                                // SolverKickDrift.cpp:230, SolverLeapfrog.cpp:272
         if (device_bcs) WF_CHECK(apply_bcs_impl(c));
         return 0;
     case 3:
@@ -602,7 +642,7 @@ static int kdlf_stage(wf_ctx *c, int stage, bool device_bcs)
         c->dens_valid = false;
         WF_CHECK(pair_density(c));                                   // CalcDensInc + DensReduction, rho += dt*drho
         WF_CHECK(kick(c, 4, c->prev_dt));                            // drift
-        if (solver == 1) { WF_CHECK(kick(c, 3, c->prev_dt)); if (device_bcs) WF_CHECK(apply_bcs_impl(c)); }
+        if (solver == 1) { WF_CHECK(kick(c, 3, c->prev_dt)); WF_CHECK(move_ghost_impl(c)); if (device_bcs) WF_CHECK(apply_bcs_impl(c)); }   // SolverKickDrift.cpp:266
         return 0;
     case 4:
         WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));
@@ -670,7 +710,16 @@ extern "C" int wf_fraser_run(wf_ctx *c, int64_t nsteps)
             ProfScope ps(c, PK_MOVE);
             StepArgs a = make_step_args(c);
             if (!c->meshes.empty()) { k_mesh_ramp<<<1, 32, 0, c->stream>>>(c->dm.motion, (int)c->meshes.size(), c->d_sc); WF_LAUNCH_CHECK(c); c->launches++; }
-            k_bc_move<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a, 15); WF_LAUNCH_CHECK(c); c->launches++;
+            if (c->n_ghost == 0) { k_bc_move<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a, 15); WF_LAUNCH_CHECK(c); c->launches++; }
+            else {
+                // with ghost pairs the pass splits at the two MoveGhost calls (SolverFraser.cpp:335,358)
+                const int g = grid_for(c->n_loc, 256);
+                k_bc_move<<<g, 256, 0, c->stream>>>(a, 1); WF_LAUNCH_CHECK(c); c->launches++;
+                WF_CHECK(move_ghost_impl(c));
+                k_bc_move<<<g, 256, 0, c->stream>>>(a, 2 | 4); WF_LAUNCH_CHECK(c); c->launches++;
+                WF_CHECK(move_ghost_impl(c));
+                k_bc_move<<<g, 256, 0, c->stream>>>(a, 8); WF_LAUNCH_CHECK(c); c->launches++;
+            }
         }
         WF_CHECK(wf_fraser_stage_c(c));
     }

@@ -89,7 +89,13 @@ def context_from_case(case, device=0, comm=None):
     arrays = {}
     if kind == 1:
         g = case["gen_args"]
-        pts = api.gen_cylinder((g[1], g[2], g[3]), g[4], g[5], g[6])
+        ghost_pairs = None
+        if len(g) > 10 and g[10] != 0:                     # AddCylinderLength(..., ghost = true)
+            pts, ghost_pairs = api.gen_cylinder_ghost((g[1], g[2], g[3]), g[4], g[5], g[6])
+            nowrite = np.zeros(len(pts), np.int32); nowrite[ghost_pairs[:, 1]] = 1      # Domain.cpp:814
+            arrays["not_write_surf_id"] = nowrite
+        else:
+            pts = api.gen_cylinder((g[1], g[2], g[3]), g[4], g[5], g[6])
         n = len(pts)
         mass = np.pi * g[4] * g[4] * g[5] * g[7] / n       # Domain.cpp:839-841
         arrays.update(x=pts, mass=np.full(n, mass), density=np.full(n, g[7]), h=np.full(n, g[8]), id=np.full(n, int(g[0]), np.int32))
@@ -150,6 +156,8 @@ def context_from_case(case, device=0, comm=None):
         arrays["global_index"] = sel.astype(np.int64)
         n = len(sel)
     ctx.set_particles(n, n_sph_global=n_global, **arrays)
+    if kind == 1 and ghost_pairs is not None:
+        ctx.set_ghost_pairs(ghost_pairs)
     for m in range(mesh_count):
         if "mesh%d_w" % m in case:                         # TriMesh::SetRotAxisVel
             ctx.mesh_set_motion(m, (0.0, 0.0, 0.0), tuple(float(w) for w in case["mesh%d_w" % m][:3]))

@@ -119,6 +119,7 @@ public:
     std::vector<Vec3_t> m_contact_force;
     int meshcount = 0, first_fem_particle_idx = -1, solid_part_count = 0;
     Array<Particle *> Particles;
+    Array<std::pair<size_t, size_t> > GhostPairs;                  // Domain.h:473 (inner particle, ghost particle)
     double m_scalar_prop = 0.0;
     Vec3_t max_disp;
     double contact_force_sum = 0.0, contact_reaction_sum = 0.0, ext_forces_work = 0.0, plastic_work = 0.0, accum_cont_heat_cond = 0.0,
@@ -167,19 +168,26 @@ inline Domain::~Domain()
     for (size_t i = 0; i < Particles.Size(); ++i) delete Particles[i];       // Domain owns its particles (Source/Domain.cpp:177-181)
 }
 
-// Source/Domain.cpp:708-860 (3-D, no ghost rows). Points come from the library's generator, mass rule :839-841.
+// Source/Domain.cpp:708-860 (3-D). Points come from the library's generator, mass rule :839-841. ghost = true (:795-826): three mirror rows
+// below the bottom plane, GhostPairs (inner, ghost), ghost_plane_axis 2, not_write_surf_ID; Domain::MoveGhost runs on the device.
 inline void Domain::AddCylinderLength(int tag, Vec3_t const & V, double Rxy, double Lz, double r, double Density, double h, bool Fixed, bool ghost)
 {
     if (Dimension != 3) throw new Fatal("AddCylinderLength: only Dimension = 3 is implemented in weldform_b200");
-    if (ghost) throw new Fatal("AddCylinderLength: ghost/symmetry particles are not implemented in weldform_b200 (SURVEY.md section 2 row 11)");
     const double Vd[3] = { V(0), V(1), V(2) };
-    const int64_t n = wf_gen_cylinder(Vd, Rxy, Lz, r, nullptr, 0);
+    int64_t npairs = 0;
+    const int64_t n = ghost ? wf_gen_cylinder_ghost(Vd, Rxy, Lz, r, nullptr, 0, nullptr, 0, &npairs) : wf_gen_cylinder(Vd, Rxy, Lz, r, nullptr, 0);
     if (n < 0) throw new Fatal("AddCylinderLength: bad arguments");
-    std::vector<double> pts(3 * (size_t)n);
-    wf_gen_cylinder(Vd, Rxy, Lz, r, pts.data(), n);
+    std::vector<double> pts(3 * (size_t)n); std::vector<int32_t> pairs(2 * (size_t)npairs);
+    if (ghost) wf_gen_cylinder_ghost(Vd, Rxy, Lz, r, pts.data(), n, pairs.data(), npairs, &npairs); else wf_gen_cylinder(Vd, Rxy, Lz, r, pts.data(), n);
     const size_t first = Particles.Size();
+    if (ghost && first != 0) throw new Fatal("AddCylinderLength: ghost rows need the cylinder to be the first particle set (the reference indexes the first rows from particle 0, Source/Domain.cpp:801-806)");
     std::cout << "\n--------------Generating particles by AddCylinderLength with defined length of particles-----------" << std::endl;
     for (int64_t i = 0; i < n; ++i) Particles.Push(new Particle(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
+    for (int64_t g = 0; g < npairs; ++g) {
+        Particle * P = Particles[pairs[2 * g + 1]];
+        P->inner_mirr_part = pairs[2 * g]; P->ghost_plane_axis = 2; P->not_write_surf_ID = true;
+        GhostPairs.Push(std::make_pair((size_t)pairs[2 * g], (size_t)pairs[2 * g + 1]));
+    }
     const double Vol = M_PI * Rxy * Rxy * Lz;
     const double Mass = Vol * Density / (double)(Particles.Size() - first);
     std::cout << "Total Particle count: " << Particles.Size() << std::endl;
@@ -305,6 +313,11 @@ inline void Domain::backend_begin(double dt)
     wp.pres_eq = preseq.data(); wp.fail = fail.data(); wp.material = matl.data(); wp.material_model = mmodel.data(); wp.mat_id = matid.data(); wp.thermal_bc = thbc.data();
     wp.sigmay = sy.data(); wp.T = T.data();
     ck(wf_set_particles(backend, &wp), "wf_set_particles");
+    if (GhostPairs.Size() > 0) {                                          // Domain::MoveGhost runs on the device (Mirror_XYZ ghosts)
+        std::vector<int32_t> gp(2 * GhostPairs.Size()), ax(GhostPairs.Size());
+        for (size_t g = 0; g < GhostPairs.Size(); ++g) { gp[2 * g] = (int32_t)GhostPairs[g].first; gp[2 * g + 1] = (int32_t)GhostPairs[g].second; ax[g] = Particles[GhostPairs[g].second]->ghost_plane_axis; }
+        ck(wf_set_ghost_pairs(backend, gp.data(), ax.data(), (int64_t)GhostPairs.Size()), "wf_set_ghost_pairs");
+    }
     sent_mv.assign(trimesh.size(), Vec3_t(0.)); sent_mw.assign(trimesh.size(), Vec3_t(0.));
     forward_mesh_motion();
     ck(wf_solver_init(backend, dt), "wf_solver_init");

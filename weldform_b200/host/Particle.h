@@ -21,6 +21,7 @@ public:
     }
     // ---- identity / flags
     int ID = 0, ID_orig = 0, Material = 0, Material_model = BILINEAR, Thermal_BC = TH_BC_NONE, Nb = 0, ContNb = 0, mesh = -1, element = -1;
+    int inner_mirr_part = -1, ghost_plane_axis = 2;       // Particle.h:223-225: the inner particle a ghost mirrors, and the mirror plane's axis
     bool IsFree = true, Shepard = false, NoSlip = false, not_write_surf_ID = false, is_ghost = false, is_fixed = false, print_history = false;
     size_t PresEq = 0, Fail = 0;
     Material_ * mat = nullptr;

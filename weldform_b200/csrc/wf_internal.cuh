@@ -179,7 +179,7 @@ int pair_gradcorr(wf_ctx *c);
 int pair_tir(wf_ctx *c);
 int pair_temp_inc_pp(wf_ctx *c);                         // CalcTempIncPP: the initial dT/dt of ThermalSolve
 int pair_min_ts(wf_ctx *c, double *test_min);
-int pair_density(wf_ctx *c);
+int pair_density(wf_ctx *c, bool with_tir = true);
 int pair_rate_stress(wf_ctx *c, int64_t lo = 0, int64_t hi = -1);   // slots [lo, hi); hi < 0: n_loc
 int pair_accel(wf_ctx *c, int64_t lo = 0, int64_t hi = -1);
 int pair_thermal(wf_ctx *c);

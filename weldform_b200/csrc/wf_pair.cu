@@ -888,8 +888,10 @@ int pair_min_ts(wf_ctx *c, double *test_min)
     return 0;
 }
 // CalcDensInc + DensReduction + rho update. If the previous step's k_post already holds this step's density rate and TIR
-// (nothing moved in between) only the per-particle prologue runs.
-int pair_density(wf_ctx *c)
+// (nothing moved in between) only the per-particle prologue runs. with_tir = false (KickDrift / LeapFrog: StartAcceleration's tensor was
+// evaluated by pair_tir at the top of the step and sits in F_TN and in the gathered arrays already): the tensor is not evaluated again --
+// the same values without ghosts, and with ghosts MoveGhost has changed Sigma and the density of the mirror rows since.
+int pair_density(wf_ctx *c, bool with_tir)
 {
     WF_PAIR_PRECHECK(c);
     PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
@@ -897,7 +899,7 @@ int pair_density(wf_ctx *c)
     if (!c->dens_valid) {
         if (fast_path(c)) WF_LAUNCH_PF(k_post, true, false, false, true); else WF_LAUNCH_PF(k_post, false, false, false, true);
         WF_LAUNCH_CHECK(c); c->launches++;
-        if (c->any_ti) { k_tir<true><<<g, 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
+        if (c->any_ti && with_tir) { k_tir<true><<<g, 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
     }
     k_prologue<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++;
     c->dens_valid = false;

@@ -640,7 +640,7 @@ static int kdlf_stage(wf_ctx *c, int stage, bool device_bcs)
     case 3:
         WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1));
         c->dens_valid = false;
-        WF_CHECK(pair_density(c));                                   // CalcDensInc + DensReduction, rho += dt*drho
+        WF_CHECK(pair_density(c, false));                            // CalcDensInc + DensReduction, rho += dt*drho; the step's TIR stands (pair_tir, stage 0)
         WF_CHECK(kick(c, 4, c->prev_dt));                            // drift
         if (solver == 1) { WF_CHECK(kick(c, 3, c->prev_dt)); WF_CHECK(move_ghost_impl(c)); if (device_bcs) WF_CHECK(apply_bcs_impl(c)); }   // SolverKickDrift.cpp:266
         return 0;

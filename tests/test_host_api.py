@@ -37,6 +37,29 @@ def test_reference_drivers_compile_unchanged(driver):
     assert r.returncode == 0, r.stderr[-3000:]
 
 
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="/root/reference is only present in the build container")
+def test_host_generators_and_materials_match_the_reference_bit_for_bit(product_lib):
+    """tests/host_parity/gen_dump.cpp compiled against the reference's own headers and against the host mirror: every lattice generator of the
+    Domain API (AddCylinderLength with and without ghost rows, AddBoxLength, Add3DCubicBoxParticles + Calculate3DMass, AddTractionProbeLength,
+    AddCylUniformLength full and slice) gives the same positions, masses and GhostPairs, and the Hollomon / Johnson-Cook host evaluations
+    (Material.cpp:6-73) the same values, to the last bit (hex floats)."""
+    src = os.path.join(ROOT, "tests", "host_parity", "gen_dump.cpp")
+    ref_root = os.path.dirname(REF_EXAMPLES)
+    with tempfile.TemporaryDirectory() as d:
+        ref_exe, our_exe = os.path.join(d, "gen_ref"), os.path.join(d, "gen_ours")
+        subprocess.check_call(["g++", "-std=c++14", "-O1", "-fpermissive", "-w", "-fopenmp", "-ffp-contract=off", "-include", "iomanip", "-D_USE_MATH_DEFINES",
+                               "-I" + os.path.join(ROOT, "oracle", "shim"), "-I" + os.path.join(ROOT, "oracle"), "-I" + os.path.join(ref_root, "Source"),
+                               "-I" + os.path.join(ref_root, "External"), src, os.path.join(ref_root, "External", "LSDynaReader", "src", "lsdynaReader.cpp"), "-o", ref_exe])
+        subprocess.check_call(["g++", "-std=c++14", "-O1", "-fpermissive", "-w", "-ffp-contract=off", "-D_USE_MATH_DEFINES", "-I" + HOST, "-I" + os.path.join(ROOT, "include"), src, "-o", our_exe,
+                               "-L" + os.path.join(ROOT, "weldform_b200"), "-lweldform_b200", "-Wl,-rpath," + os.path.join(ROOT, "weldform_b200")])
+        ref = [l for l in subprocess.run([ref_exe], capture_output=True, text=True, timeout=300).stdout.splitlines() if l.startswith("@ ")]
+        our = [l for l in subprocess.run([our_exe], capture_output=True, text=True, timeout=300).stdout.splitlines() if l.startswith("@ ")]
+    assert len(ref) > 12000 and sum(l.startswith("@ Add") for l in ref) == 7
+    assert len(ref) == len(our)
+    bad = [(i, a, b) for i, (a, b) in enumerate(zip(ref, our)) if a != b]
+    assert not bad, "first differences (line, reference, mirror): %s" % bad[:5]
+
+
 def test_example_links_and_refuses_without_gpu(host_example):
     import torch
     if torch.cuda.is_available():

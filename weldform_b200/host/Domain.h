@@ -73,6 +73,12 @@ public:
     void AddBoxLength(int tag, Vec3_t const & V, double Lx, double Ly, double Lz, double r, double Density, double h, int type, int rotation, bool random, bool Fixed);
     void AddCylinderLength(int tag, Vec3_t const & V, double Rxy, double Lz, double r, double Density, double h, bool Fixed, bool ghost = false);
     void AddTrimeshParticles(TriMesh * mesh, const float & hfac, const int & id);
+    void AddSingleParticle(int tag, Vec3_t const & x, double Mass, double Density, double h, bool Fixed);
+    void Add3DCubicBoxParticles(int tag, Vec3_t const & V, double Lx, double Ly, double Lz, double r, double Density, double h);
+    void Calculate3DMass(double Density);
+    void AddTractionProbeLength(int tag, Vec3_t const & V, double Rxy, double Lz_side, double Lz_neckmin, double Lz_necktot, double Rxy_center,
+                                double r, double Density, double h, bool Fixed);
+    void AddCylUniformLength(int tag, double Rxy, double Lz, double r, double Density, double h, double ang = 2 * M_PI, int rows = 1, double r_i = 0.0, bool ghost = true);
     void Kernel_Set(Kernels_Type const & KT) { KernelType = KT; Cellfac = (KT == Quintic_Spline) ? 3.0 : 2.0; }
     void Gradient_Approach_Set(Gradient_Type const & GT) { GradientType = GT; }
     void Viscosity_Eq_Set(Viscosity_Eq_Type const & VQ) { VisEq = VQ; }
@@ -112,6 +118,7 @@ public:
     double pl_work_heat_frac = 0.9;
     bool contact = false, update_contact_surface = true, cont_heat_gen = false, cont_heat_cond = false, cont_heat_fric = false, model_damage = false;
     double PFAC = 0.4, DFAC = 0.0, friction_sta = 0.0, friction_dyn = 0.0, friction_m = 0.0, friction_b = 0.0, contact_hc = 0.0;
+    double friction = 0.0;                     // Domain.h:291: legacy coefficient of the Fraser / Seo contact laws; CalcContactForcesWang reads friction_sta / friction_dyn only
     int friction_function = Constant, fric_type = Fr_Dyn, contact_alg = Wang;
     int id_free_surf = 1;
     std::vector<int> contact_surf_id;
@@ -120,7 +127,8 @@ public:
     int meshcount = 0, first_fem_particle_idx = -1, solid_part_count = 0;
     Array<Particle *> Particles;
     Array<std::pair<size_t, size_t> > GhostPairs;                  // Domain.h:473 (inner particle, ghost particle)
-    double m_scalar_prop = 0.0;
+    double m_scalar_prop = 0.0, Vol = 0.0, R = 0.0;          // Vol: accumulated by Add3DCubicBoxParticles for Calculate3DMass (Domain.h:337); R: particle radius of the last lattice
+    double sqrt_h_a = 0.0025;                                // Domain.cpp:109; the device's CheckMinTSAccel uses this value, anything else is refused in backend_begin
     Vec3_t max_disp;
     double contact_force_sum = 0.0, contact_reaction_sum = 0.0, ext_forces_work = 0.0, plastic_work = 0.0, accum_cont_heat_cond = 0.0,
            contact_friction_work = 0.0, kin_energy_sum = 0.0, int_energy_sum = 0.0, max_contact_force = 0.0, m_maxT = 0.0, m_minT = 0.0;
@@ -196,6 +204,141 @@ inline void Domain::AddCylinderLength(int tag, Vec3_t const & V, double Rxy, dou
     solid_part_count = (int)Particles.Size();
 }
 
+// Source/Domain.cpp:321-324 (solid_part_count is left alone there; the mirror's upload needs it, so it follows the particle count)
+inline void Domain::AddSingleParticle(int tag, Vec3_t const & x, double Mass, double Density, double h, bool Fixed)
+{
+    Particles.Push(new Particle(tag, x, Vec3_t(0, 0, 0), Mass, Density, h, Fixed));
+    solid_part_count = (int)Particles.Size();
+}
+
+// Source/Domain.cpp:601-655: the cubic lattice of AddBoxLength without the mass rule; the box volume accumulates in Vol for Calculate3DMass
+inline void Domain::Add3DCubicBoxParticles(int tag, Vec3_t const & V, double Lx, double Ly, double Lz, double r, double Density, double h)
+{
+    if (Dimension != 3) throw new Fatal("Add3DCubicBoxParticles: only Dimension = 3 is implemented in weldform_b200");
+    const double Vd[3] = { V(0), V(1), V(2) }; double dims[3];
+    const int64_t n = wf_gen_box(Vd, Lx, Ly, Lz, r, nullptr, 0, dims);
+    if (n < 0) throw new Fatal("Add3DCubicBoxParticles: bad arguments");
+    std::vector<double> pts(3 * (size_t)n);
+    wf_gen_box(Vd, Lx, Ly, Lz, r, pts.data(), n, dims);
+    std::cout << "\n--------------Generating particles by AddBoxLength with defined length of particles-----------" << std::endl;
+    for (int64_t i = 0; i < n; ++i) Particles.Push(new Particle(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, false));
+    std::cout << "BoxDimensions: " << dims[0] << ", " << dims[1] << ", " << dims[2] << ", " << std::endl;
+    Vol += dims[0] * dims[1] * dims[2];
+    solid_part_count = (int)Particles.Size();
+}
+// Source/Domain.cpp:658-672
+inline void Domain::Calculate3DMass(double Density)
+{
+    double Mass = Vol * Density / Particles.Size();
+    std::cout << "Particle Mass: " << Mass << std::endl;
+    for (size_t i = 0; i < Particles.Size(); ++i) Particles[i]->Mass = Mass;
+}
+
+namespace detail {
+// Source/Domain.cpp:674-689 calcHalfPartCount
+inline int calc_half_part_count(const double & r, const double & R, const int xinc)
+{
+    int ypartcount = -1;
+    if (xinc > 0) {
+        ypartcount = 1;
+        double yp = r;
+        double xp = r + (double)(xinc - 1) * 2. * r;
+        double rad = sqrt(yp * yp + xp * xp);
+        while (rad <= R - r) { yp += 2. * r; rad = sqrt(yp * yp + xp * xp); ypartcount++; }
+        ypartcount -= 1;
+    }
+    return ypartcount;
+}
+}
+
+// Source/Domain.cpp:1290-1412: tensile probe -- two grip cylinders of radius Rxy, two cones and a neck of radius Rxy_center. The first
+// row sits AT z = V(2), the following ones at V(2) + (2k+1) r, as in the reference; every particle of the domain gets the probe's mass.
+inline void Domain::AddTractionProbeLength(int tag, Vec3_t const & V, double Rxy, double Lz_side, double Lz_neckmin, double Lz_necktot, double Rxy_center,
+                                           double r, double Density, double h, bool Fixed)
+{
+    if (Dimension != 3) throw new Fatal("AddTractionProbeLength: only Dimension = 3 is implemented in weldform_b200");
+    std::cout << "\n--------------Generating particles by CylinderBoxLength with defined length of particles-----------" << std::endl;
+    size_t PrePS = Particles.Size();
+    double xp, yp;
+    double Lz = 2. * Lz_side + Lz_necktot;
+    double z_radiusreduction = (Lz_necktot - Lz_neckmin) / 2.;
+    double tan = (Rxy - Rxy_center) / (z_radiusreduction);
+    double R;
+    double z1 = V(2) + Lz_side - r;
+    double z2 = V(2) + Lz_side + z_radiusreduction - r;
+    double z3 = V(2) + Lz_side + z_radiusreduction + Lz_neckmin - r;
+    double z4 = V(2) + Lz_side + Lz_necktot - r;
+    size_t k = 0;
+    double zp = V(2);
+    while (zp <= (V(2) + Lz - r)) {
+        if (zp <= z1 || zp > z4) R = Rxy;
+        else if (zp > z1 && zp <= z2) R = Rxy - (zp - z1) * tan;
+        else if (zp >= z2 && zp < z3) R = Rxy_center;
+        else if (zp >= z3 && zp < z4) R = Rxy_center + (zp - z3) * tan;
+        int numpartxy = detail::calc_half_part_count(r, R, 1);
+        yp = V(1) - r - (2. * r * (numpartxy - 1));
+        int numypart = 2 * numpartxy, yinc = numpartxy, yinc_sign = -1;
+        for (int j = 0; j < numypart; j++) {
+            int numxpart = detail::calc_half_part_count(r, R, yinc);
+            xp = V(0) - r - (2. * r * (numxpart - 1));
+            for (int i = 0; i < 2 * numxpart; i++) {
+                Particles.Push(new Particle(tag, Vec3_t(xp, yp, zp), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
+                xp += 2. * r;
+            }
+            yp += 2. * r;
+            yinc += yinc_sign;
+            if (yinc < 1) { yinc = 1; yinc_sign = 1; }
+        }
+        k++;
+        zp = V(2) + (2.0 * k + 1) * r;
+    }
+    double L_cone = (Lz_necktot - Lz_neckmin) / 2.;
+    double Vol_ = 2.0 * Lz_side * M_PI * Rxy * Rxy + Lz_neckmin * M_PI * Rxy_center * Rxy_center +
+                  2.0 * L_cone * M_PI * (Rxy_center * Rxy_center + Rxy * Rxy + Rxy * Rxy_center) / 3.0;
+    double Mass = Vol_ * Density / (Particles.Size() - PrePS);
+    std::cout << "Particle mass: " << Mass << std::endl;
+    for (size_t i = 0; i < Particles.Size(); ++i) Particles[i]->Mass = Mass;
+    solid_part_count = (int)Particles.Size();
+    this->R = r;
+}
+
+// Source/Domain.cpp:2605-2720: polar ("uniform") cylinder lattice from z = r upwards, rings every 2r from r_i, ceil(ang * ri / 2r) particles per
+// ring. The slice bookkeeping of the reference (boundary zones, correct_vel_acc) feeds only code the new solvers have commented out
+// (CorrectVelAcc, SolverFraser.cpp:333,357) and is not mirrored; `ghost` is unused there as well.
+inline void Domain::AddCylUniformLength(int tag, double Rxy, double Lz, double r, double Density, double h, double ang, int rows, double r_i, bool ghost)
+{
+    if (Dimension != 3) throw new Fatal("AddCylUniformLength: only Dimension = 3 is implemented in weldform_b200");
+    (void)rows; (void)ghost;
+    std::cout << "\n--------------Generating particles by CylinderBoxLength with defined length of particles-----------" << std::endl;
+    double xp, yp;
+    double z0 = r;
+    int tgcount;
+    double zp = z0;
+    while (zp <= (z0 + Lz - r)) {
+        for (double ri = r_i; ri < Rxy; ri += 2. * r) {
+            double dalpha;
+            if (ri == 0.) { tgcount = 1; dalpha = 0.; }
+            else {
+                tgcount = (ceil)((ang * ri) / (2. * r));
+                dalpha = ang / (tgcount);
+            }
+            for (int alphai = 0; alphai < tgcount; alphai++) {
+                xp = ri * cos(alphai * dalpha);
+                yp = ri * sin(alphai * dalpha);
+                Particles.Push(new Particle(tag, Vec3_t(xp, yp, zp), Vec3_t(0, 0, 0), 0.0, Density, h, false));
+            }
+        }
+        zp += 2.0 * r;
+    }
+    double Vol_ = M_PI * Rxy * Rxy * Lz;
+    double Mass = Vol_ * Density / Particles.Size();
+    std::cout << "Total Particle count: " << Particles.Size() << std::endl;
+    std::cout << "Particle mass: " << Mass << std::endl;
+    solid_part_count = (int)Particles.Size();
+    for (size_t i = 0; i < Particles.Size(); ++i) Particles[i]->Mass = Mass;
+    this->R = r;
+}
+
 // Source/Domain.cpp:326-455 (3-D cubic packing, type 1, rotation 0, random = false); mass rule :447-455
 inline void Domain::AddBoxLength(int tag, Vec3_t const & V, double Lx, double Ly, double Lz, double r, double Density, double h, int type, int rotation, bool random, bool Fixed)
 {
@@ -266,6 +409,8 @@ inline void Domain::backend_begin(double dt)
     p.cont_heat_fric = cont_heat_fric; p.cont_heat_cond = cont_heat_cond; p.contact_hc = contact_hc;
     p.solver = solver_kind; p.auto_ts = (solver_kind != 0 && auto_ts) ? 1 : 0; p.auto_ts_acc = (solver_kind != 0 && auto_ts_acc) ? 1 : 0; p.cfl = CFL;   // auto_ts is dead code in the Fraser loop (SolverFraser.cpp:500-502)
     p.grad_kernel_corr = gradKernelCorr ? 1 : 0;     // CalcGradCorrMatrix + the locking summation the reference switches to (SolverFraser.cpp:112-115)
+    if (auto_ts_acc && sqrt_h_a != 0.0025) throw new Fatal("Domain::sqrt_h_a = %g: the device time-step criterion uses the reference's default 0.0025 only", sqrt_h_a);
+    if (contact && contact_alg != Wang) throw new Fatal("Domain::contact_alg = %d: only CalcContactForcesWang (the default, Source/Domain.cpp:169) is implemented in weldform_b200", contact_alg);
     if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
     p.friction_function = (friction_function == Linear) ? 1 : 0; p.friction_m = friction_m; p.friction_b = friction_b;
     ck(wf_set_params(backend, &p), "wf_set_params");

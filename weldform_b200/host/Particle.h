@@ -35,6 +35,9 @@ public:
     // ---- thermal
     double T = 0., k_T = 0., cp_T = 0., dTdt = 0., q_source = 0., q_conv = 0., T_inf = 0., h_conv = 0., q_plheat = 0., th_exp = 0.;
     double delta_cont = 0.;
+    // ---- members some drivers assign that nothing on this path reads (Particle.h:80,83,167): v_max, hfac (smoothing-length update, never
+    // called by the new solvers), Et_m (written by CalcStressStrain, read only in commented-out contact code, Contact.cpp:415)
+    Vec3_t v_max; double hfac = 0., Et_m = 0., Et = 0.;
 };
 
 } // namespace SPH

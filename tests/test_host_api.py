@@ -38,6 +38,25 @@ def test_reference_drivers_compile_unchanged(driver):
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="/root/reference is only present in the build container")
+def test_wider_driver_set_still_compiles_unchanged():
+    """Beyond the five configurations: every driver listed in tests/host_parity/drivers_compiling.txt (95 of the reference's 144 examples; the
+    rest need fluids, CompactNSearch, 2-D, the implicit solver, or do not compile against the reference either) keeps compiling unchanged."""
+    from concurrent.futures import ThreadPoolExecutor
+    names = [l.strip() for l in open(os.path.join(ROOT, "tests", "host_parity", "drivers_compiling.txt")) if l.strip() and not l.startswith("#")]
+    assert len(names) >= 95 and all(d in names for d in DRIVERS)
+
+    def compile_one(name):
+        cmd = ["g++", "-std=c++14", "-fsyntax-only", "-fpermissive", "-w", "-fopenmp", "-D_USE_MATH_DEFINES", "-I" + HOST, "-I" + os.path.join(ROOT, "include"),
+               os.path.join(REF_EXAMPLES, name)]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        return name, r.returncode, r.stderr[-600:]
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        res = list(ex.map(compile_one, names))
+    bad = [(n, e) for n, rc, e in res if rc != 0]
+    assert not bad, bad[:3]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="/root/reference is only present in the build container")
 def test_host_generators_and_materials_match_the_reference_bit_for_bit(product_lib):
     """tests/host_parity/gen_dump.cpp compiled against the reference's own headers and against the host mirror: every lattice generator of the
     Domain API (AddCylinderLength with and without ghost rows, AddBoxLength, Add3DCubicBoxParticles + Calculate3DMass, AddTractionProbeLength,

@@ -124,7 +124,8 @@ public:
     std::vector<int> contact_surf_id;
     std::vector<TriMesh *> trimesh;
     std::vector<Vec3_t> m_contact_force;
-    int meshcount = 0, first_fem_particle_idx = -1, solid_part_count = 0;
+    int meshcount = 0, solid_part_count = 0;
+    std::vector<int> first_fem_particle_idx;                       // Domain.h:348: first element particle of every rigid mesh (Contact.cpp:12)
     Array<Particle *> Particles;
     Array<std::pair<size_t, size_t> > GhostPairs;                  // Domain.h:473 (inner particle, ghost particle)
     double m_scalar_prop = 0.0, Vol = 0.0, R = 0.0;          // Vol: accumulated by Add3DCubicBoxParticles for Calculate3DMass (Domain.h:337); R: particle radius of the last lattice
@@ -363,7 +364,7 @@ inline void Domain::AddBoxLength(int tag, Vec3_t const & V, double Lx, double Ly
 // Source/Contact.cpp:10-38: one massless particle per element at its centroid, h = hfac * radius, ID = id
 inline void Domain::AddTrimeshParticles(TriMesh * mesh, const float & hfac, const int & id)
 {
-    if (first_fem_particle_idx < 0) first_fem_particle_idx = (int)Particles.Size();
+    first_fem_particle_idx.push_back((int)Particles.Size());
     mesh->id = id;
     for (size_t e = 0; e < mesh->element.Size(); ++e) {
         Particle * p = new Particle(id, mesh->element[e]->centroid, Vec3_t(0, 0, 0), 0.0, 0.0, (double)hfac * mesh->element[e]->radius, false);
@@ -398,7 +399,7 @@ inline void Domain::backend_begin(double dt)
     if (backend) { wf_destroy(backend); backend = nullptr; }
     if (wf_create(device, &backend) != 0) throw new Fatal("weldform_b200: %s", wf_last_error(nullptr));
     const size_t ntot = Particles.Size();
-    const size_t nsph = first_fem_particle_idx >= 0 ? (size_t)first_fem_particle_idx : ntot;
+    const size_t nsph = !first_fem_particle_idx.empty() ? (size_t)first_fem_particle_idx[0] : ntot;
     if (nsph == 0) throw new Fatal("Domain: no particles");
     // ---- parameters
     wf_params p; wf_default_params(&p);

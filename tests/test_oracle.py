@@ -97,3 +97,21 @@ def test_reference_pair_set_is_thread_count_independent():
     c = cases.perturbed(cases.compression(dx=0.03, nsteps=1)); c["mode"] = 1.0
     a, b = ot.run_ref(c, nproc=1), ot.run_ref(c, nproc=4)
     assert np.array_equal(a["pairs"], b["pairs"])
+
+
+@pytest.mark.parametrize("name", ["comp_yield_40", "comp_jc_30", "kd_comp_30"])
+def test_tensile_instability_tensor_against_an_independent_eigen_solver(oracle_port, name):
+    """The one third-party arithmetic on the path is GSL's gsl_eigen_symmv inside Rotation() (Functions.cpp:381-395); the reference build here
+    and the port use a cyclic Jacobi stand-in. TIR = V diag(sigma_k > 0 ? -TI sigma_k / rho^2 : 0) V^T does not depend on the eigen-solver's
+    ordering or signs, so LAPACK (numpy.linalg.eigh) on the stresses of step N-1 must reproduce the reference's TIR of step N to round-off."""
+    case, ref = golden_tools.load(name)
+    prev = dict(case); prev["nsteps"] = float(int(case["nsteps"]) - 1)
+    st = ot.run_port(prev)
+    S = st["Sigma"].reshape(-1, 3, 3); rho = st["Density"]
+    TI = np.broadcast_to(np.asarray(case["TI"], dtype=np.float64), rho.shape)
+    w, V = np.linalg.eigh(S)
+    val = np.where(w > 0, -(TI / rho ** 2)[:, None] * w, 0.0)
+    T = np.einsum("nik,nk,njk->nij", V, val, V)
+    Tref = ref["TIR"].reshape(-1, 3, 3)
+    assert np.abs(Tref).max() > 0.0
+    assert np.abs(T - Tref).max() <= 1e-12 * np.abs(Tref).max()

@@ -427,6 +427,7 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     if (c->prm.solver == 3) {
         // Domain::ThermalSolve (Thermal.cpp:567-626): one neighbour search for the whole run, the correction matrices, the initial dT/dt
         if (c->prm.contact) return fail(c, WF_ERR_UNSUPPORTED, "ThermalSolve with rigid-mesh contact is not implemented");
+        if (c->comm.nranks > 1) return fail(c, WF_ERR_UNSUPPORTED, "ThermalSolve on more than one GPU has not been verified against the reference yet; run it on one GPU");
         WF_CHECK(nb_build_impl(c));
         c->solver_ready = true;
         WF_CHECK(pair_gradcorr(c));

@@ -179,6 +179,7 @@ int wf_mesh_download(wf_ctx *ctx, int mesh, double *nodes, double *normals, doub
 int wf_solver_init(wf_ctx *ctx, double dt);         /* InitialChecks, CellInitiate, ListGenerate, contact prologue (:41-94) */
 int wf_nb_build(wf_ctx *ctx);                       /* ClearNbData+MainNeighbourSearch+CalcPairPosList+SaveNeighbourData(+ContactNbUpdate) */
 int wf_nb_export_pairs(wf_ctx *ctx, int64_t *ij, int64_t cap, int64_t *n_pairs);      /* sorted (i<j), creation numbering */
+int wf_get_grid(wf_ctx *ctx, double blpf[3], double trpr[3], double cell_size[3], int32_t cell_no[3]);   /* Domain::BLPF, TRPR, CellSize, CellNo after CellInitiate (Neighbour.cpp:10-139) */
 int wf_cont_export_pairs(wf_ctx *ctx, int64_t *ij, int64_t cap, int64_t *n_pairs);
 int wf_grad_corr(wf_ctx *ctx);                      /* CalcGradCorrMatrix (Domain.cpp:1832-1940) on the current lists; no-op unless grad_kernel_corr */
 int wf_step_begin(wf_ctx *ctx);                     /* StartAcceleration: resets + TIR (Domain.cpp:1519-1597) */

@@ -99,6 +99,7 @@ def load_library():
         "wf_gen_box": ([_PD, C.c_double, C.c_double, C.c_double, C.c_double, _PD, C.c_int64, _PD], C.c_int64),
         "wf_gen_cylinder_ghost": ([_PD, C.c_double, C.c_double, C.c_double, _PD, C.c_int64, _PI, C.c_int64, C.POINTER(C.c_int64)], C.c_int64),
         "wf_set_ghost_pairs": ([vp, _PI, _PI, C.c_int64], C.c_int), "wf_move_ghost": ([vp], C.c_int),
+        "wf_get_grid": ([vp, _PD, _PD, _PD, _PI], C.c_int),
         "wf_prof_enable": ([vp, C.c_int], C.c_int), "wf_prof_get": ([vp, _PD, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int)], C.c_int),
         "wf_comm_unique_id": ([vp], C.c_int), "wf_comm_init": ([vp, C.c_int, C.c_int, vp], C.c_int), "wf_comm_info": ([vp, C.POINTER(C.c_int64)], C.c_int),
         "wf_plan_slabs": ([_PD, _PD, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
@@ -284,6 +285,12 @@ class Context:
         pr = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         ax = None if axis is None else np.ascontiguousarray(axis, np.int32)
         self._ck(self.L.wf_set_ghost_pairs(self.h, _ip(pr), None if ax is None else _ip(ax), len(pr)), "wf_set_ghost_pairs")
+
+    def get_grid(self):
+        """Domain::BLPF, TRPR, CellSize, CellNo of the cell grid (after solver_init)"""
+        b, t, cs, cn = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros(3, np.int32)
+        self._ck(self.L.wf_get_grid(self.h, _dp(b), _dp(t), _dp(cs), _ip(cn)), "wf_get_grid")
+        return b, t, cs, cn
 
     def move_ghost(self):
         self._ck(self.L.wf_move_ghost(self.h), "wf_move_ghost")

@@ -101,6 +101,20 @@ extern "C" void wf_destroy(wf_ctx *c)
     delete c;
 }
 
+// Domain::BLPF / TRPR / CellSize / CellNo as CellInitiate leaves them (Neighbour.cpp:10-139); valid after wf_solver_init
+extern "C" int wf_get_grid(wf_ctx *c, double blpf[3], double trpr[3], double cell_size[3], int32_t cell_no[3])
+{
+    if (!c) return WF_ERR_ARG;
+    if (!c->solver_ready) return fail(c, WF_ERR_ARG, "wf_get_grid: call wf_solver_init first");
+    for (int k = 0; k < 3; ++k) {
+        if (blpf) blpf[k] = c->BLPF[k];
+        if (trpr) trpr[k] = c->TRPR[k];
+        if (cell_size) cell_size[k] = c->CellSize[k];
+        if (cell_no) cell_no[k] = c->CellNo[k];
+    }
+    return 0;
+}
+
 extern "C" const char *wf_last_error(const wf_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
 
 extern "C" void *wf_get_stream(wf_ctx *c) { return c ? (void *)c->stream : nullptr; }

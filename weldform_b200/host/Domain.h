@@ -96,6 +96,20 @@ public:
     void ThermalStructSolve(double, double, double, char const *, size_t) { not_implemented("ThermalStructSolve"); }
     void Solve(double, double, double, char const *, size_t) { throw new Fatal("Domain::Solve: DEPRECATED (the reference throws here too, Source/Domain.cpp:2130); use SolveDiffUpdateFraser"); }
 
+    // ---- neighbour search as the reference's component drivers call it (examples/Neighbour_Test.cpp:84-118): CellInitiate uploads the
+    // particles and sizes the grid on the device (Neighbour.cpp:10-139), MainNeighbourSearch builds the lists there and exports the pair set
+    // into SMPairs[0] as (i, j) with i < j, sorted -- the reference fills one list per thread in discovery order; the SET is the same
+    // (tests/test_parity_gpu.py::test_pairs_bit_exact_12k). ListGenerate / CellReset are part of the device build.
+    void CellInitiate();
+    void ListGenerate() {}
+    void CellReset() {}
+    void MainNeighbourSearch();
+    void SaveNeighbourData();
+    void ClearNbData() { for (size_t k = 0; k < SMPairs.Size(); ++k) SMPairs[k].Clear(); }
+    int AvgNeighbourCount();
+    Array<Array<std::pair<size_t, size_t> > > SMPairs, NSMPairs, FSMPairs;     // Domain.h:405-407
+    Vec3_t BLPF, TRPR, CellSize; int CellNo[3] = { 0, 0, 0 };                  // Domain.h:323-330, valid after CellInitiate
+
     // ---- output
     void WriteXDMF(char const * FileKey);
     void WriteCSV(char const * FileKey);
@@ -471,6 +485,47 @@ inline void Domain::backend_begin(double dt)
 }
 
 inline void Domain::backend_end() { if (backend) { wf_destroy(backend); backend = nullptr; } }
+
+// Source/Neighbour.cpp:10-139 (+ the upload): the cell grid of the reference, computed by the library
+inline void Domain::CellInitiate()
+{
+    backend_begin(deltat > 0.0 ? deltat : 1.0);
+    double b[3], t[3], cs[3]; int32_t cn[3];
+    ck(wf_get_grid(backend, b, t, cs, cn), "wf_get_grid");
+    for (int k = 0; k < 3; ++k) { BLPF(k) = b[k]; TRPR(k) = t[k]; CellSize(k) = cs[k]; CellNo[k] = cn[k]; }
+    const size_t np = Nproc > 0 ? Nproc : 1;
+    while (SMPairs.Size() < np) { SMPairs.Push(Array<std::pair<size_t, size_t> >()); NSMPairs.Push(Array<std::pair<size_t, size_t> >()); FSMPairs.Push(Array<std::pair<size_t, size_t> >()); }
+}
+// Source/Neighbour.cpp:346-398: the search runs on the device; the same-material pair set comes back sorted, in creation numbering
+inline void Domain::MainNeighbourSearch()
+{
+    if (!backend) CellInitiate();
+    ck(wf_nb_build(backend), "wf_nb_build");
+    int64_t np = 0;
+    ck(wf_nb_export_pairs(backend, nullptr, 0, &np), "wf_nb_export_pairs");
+    std::vector<int64_t> ij(2 * (size_t)np);
+    ck(wf_nb_export_pairs(backend, ij.data(), np, &np), "wf_nb_export_pairs");
+    ClearNbData();
+    for (int64_t p = 0; p < np; ++p) SMPairs[0].Push(std::make_pair((size_t)ij[2 * p], (size_t)ij[2 * p + 1]));
+}
+// Source/Neighbour.cpp:499-532: Particle::Nb
+inline void Domain::SaveNeighbourData()
+{
+    if (!backend) throw new Fatal("Domain::SaveNeighbourData: no neighbour search has run");
+    const size_t n = Particles.Size(); std::vector<int32_t> ib(n);
+    ck(wf_download(backend, WF_F_NB, ib.data()), "wf_download(Nb)");
+    for (size_t i = 0; i < n; ++i) Particles[i]->Nb = ib[i];
+}
+// Source/Neighbour.cpp:553-570
+inline int Domain::AvgNeighbourCount()
+{
+    std::vector<int> nbcount(Particles.Size());
+    for (size_t p = 0; p < SMPairs.Size(); ++p)
+        for (size_t i = 0; i < SMPairs[p].Size(); ++i) { nbcount[SMPairs[p][i].first]++; nbcount[SMPairs[p][i].second]++; }
+    int tot = 0;
+    for (size_t p = 0; p < nbcount.size(); ++p) tot += nbcount[p];
+    return nbcount.empty() ? 0 : tot / (int)nbcount.size();
+}
 
 // ---- field mirrors -------------------------------------------------------------------------------------------------
 inline void Domain::get3(wf_field f, Vec3_t Particle::*mem, bool subset)

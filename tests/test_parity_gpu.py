@@ -337,3 +337,20 @@ def test_thermal_solve_large_properties(harness):
     again = harness.run_case(c, with_pairs=False)
     for k in ("T", "dTdt", "StrainRate"):
         assert np.array_equal(got[k], again[k]), "non-deterministic %s" % k
+
+
+# Combinations that are pinned in the oracle port (bit-identical to the reference build, tests/test_oracle.py) but have not been run on
+# a GPU yet: kept out of the default -m gpu run until they have been seen green once (WF_UNVERIFIED_GPU=1 runs them).
+import os  # noqa: E402
+_unverified = pytest.mark.skipif(os.environ.get("WF_UNVERIFIED_GPU") != "1", reason="not yet run on a GPU; set WF_UNVERIFIED_GPU=1")
+
+
+@_unverified
+@pytest.mark.parametrize("solver", [0, 1, 2])
+def test_ghost_rows_with_gradient_correction(harness, oracle_port, solver):
+    """examples/Compression_half_ghost_vel.cpp's combination: AddCylinderLength(..., ghost = true) + gradKernelCorr (+ LeapFrog there)."""
+    c = cases.perturbed(cases.compression(dx=0.03, nsteps=30, ghost=True, model=cases.JOHNSON_COOK), amp=60.0)
+    c["gradKernelCorr"] = 1.0; c["solver"] = float(solver)
+    got, ref = harness.run_case(c), ot.run_port(c)
+    assert ref["pl_strain"].max() > 1e-3
+    _compare(got, ref, 1e-7, what="ghost + gradKernelCorr, solver %d" % solver)

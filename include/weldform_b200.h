@@ -202,9 +202,9 @@ int wf_fraser_stage_b1(wf_ctx *ctx);
 int wf_fraser_stage_b2(wf_ctx *ctx);
 int wf_fraser_stage_c(wf_ctx *ctx);
 int wf_fraser_run(wf_ctx *ctx, int64_t nsteps);     /* nsteps full steps with device-side BCs, no host callback */
-/* Whole steps of the solver wf_params::solver selects (Fraser / KickDrift / LeapFrog step order), device-side BCs.
+/* Whole steps of the solver wf_params::solver selects (Fraser / KickDrift / LeapFrog step order, ThermalSolve), device-side BCs.
  * wf_run: nsteps steps. wf_run_until: while (Time <= tf) as the reference's loops do (the only stop rule that makes sense
- * with auto_ts); *steps_done receives the number of steps taken. */
+ * with auto_ts; ThermalSolve's loop stops at Time < tf, Thermal.cpp:626); *steps_done receives the number of steps taken. */
 int wf_run(wf_ctx *ctx, int64_t nsteps);
 /* One KickDrift / LeapFrog step in five stages split at the reference loops' GeneralAfter calls (host-callback bridge): 0 rebuild
  * policy + TIR + CalcAccel | 1 contact (+ LeapFrog's first-step half kick) | 2 adaptive time step + velocity kick | 3 density + drift

@@ -695,7 +695,8 @@ extern "C" int wf_run_until(wf_ctx *c, double tf, int64_t *steps_done)
 {
     WF_NEED_READY(c);
     int64_t n = 0;
-    while (c->time <= tf) { WF_CHECK(one_step(c)); ++n; }        // while (Time <= tf), SolverFraser.cpp:133
+    // while (Time <= tf) in the Fraser / KickDrift / LeapFrog loops (SolverFraser.cpp:133); ThermalSolve stops at Time < tf (Thermal.cpp:626)
+    while (c->prm.solver == 3 ? c->time < tf : c->time <= tf) { WF_CHECK(one_step(c)); ++n; }
     if (steps_done) *steps_done = n;
     return 0;
 }

@@ -14,3 +14,5 @@ tail -2 gpurun_out/bench_$tag.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --max-spinup 20 --no-cpu-baseline > gpurun_out/bench_launches_$tag.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_accel|k_rate_stress|k_post|k_nb_list" -s 8 -c 8 -o gpurun_out/prof_$tag python bench.py --steps 3 --warmup 3 --max-spinup 20 --no-cpu-baseline > gpurun_out/bench_ncu_$tag.log 2>&1
 ls -la gpurun_out | tail -10
+# 4. the packed-record micro-benchmark
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 scripts/ubench/rec_layout.cu -o /tmp/rec_layout && /tmp/rec_layout > gpurun_out/rec_layout_$tag.txt 2>&1; cat gpurun_out/rec_layout_$tag.txt

@@ -339,13 +339,8 @@ def test_thermal_solve_large_properties(harness):
         assert np.array_equal(got[k], again[k]), "non-deterministic %s" % k
 
 
-# Combinations that are pinned in the oracle port (bit-identical to the reference build, tests/test_oracle.py) but have not been run on
-# a GPU yet: kept out of the default -m gpu run until they have been seen green once (WF_UNVERIFIED_GPU=1 runs them).
-import os  # noqa: E402
-_unverified = pytest.mark.skipif(os.environ.get("WF_UNVERIFIED_GPU") != "1", reason="not yet run on a GPU; set WF_UNVERIFIED_GPU=1")
-
-
-@_unverified
+# Pinned in the oracle port (bit-identical to the reference build, tests/test_oracle.py); first seen green on a B200 in round 2
+# (profiles/r2_v0_pytest_gpu.log), part of the default -m gpu run since.
 @pytest.mark.parametrize("solver", [0, 1, 2])
 def test_ghost_rows_with_gradient_correction(harness, oracle_port, solver):
     """examples/Compression_half_ghost_vel.cpp's combination: AddCylinderLength(..., ghost = true) + gradKernelCorr (+ LeapFrog there)."""

@@ -76,7 +76,6 @@ def algorithmic_bytes(nb_avg, ti=True, thermal=True):
     return b
 
 
-FLOPS_PER_PAIR = {"rate_stress": 80.0, "accel": 250.0, "post": 45.0 + 40.0 + 45.0, "energy": 40.0}   # thermal + energy + density share k_post
 
 
 class ClockSampler:
@@ -189,7 +188,8 @@ def run_reference_arm(args):
     r = reference_throughput(n_sample, args.steps, args.warmup, log=lambda m: print(m, file=sys.stderr, flush=True))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args.particles, {"reference_sample_particles": r["particles"]}),
+            "data": "synthetic", "config": workload_config(r["particles"], {"sample_of": "the %d-particle workload of the GPU arm: the reference is timed on a %d-particle lattice of the same generator, "
+                                                                                          "physics and spin-free state (particle-steps/s normalises the size)" % (args.particles, r["particles"])}),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -255,10 +255,9 @@ def run_ours(args):
     clocks = ClockSampler(local); clocks.start()
     ctx.run(max(args.warmup, 3))
     ctx.sync()
-    if world > 1:
-        for _ in range(40):                          # at least ~0.3 s of load before the timed region at small per-GPU sizes
-            ctx.run(2)
-        ctx.sync()
+    for _ in range(40):                              # the same 80 steps at every N: >= 0.3 s of load before the timed region at small per-GPU sizes, and
+        ctx.run(2)                                   # the SAME state (step count) under the clock and in config.state_checksum whatever N is
+    ctx.sync()
     ctx.prof_enable(True)
     l0 = ctx.launch_count()
     barrier()
@@ -273,6 +272,17 @@ def run_ours(args):
     prof = ctx.prof_get()
     ctx.prof_enable(False)
     s_after = ctx.reduce()
+    # N-independence of the state, visible in the bench line itself: order-independent checksums (sums of the 32-bit halves of the fp64 bit
+    # patterns, exact in int64 and independent of how particles are split over ranks) of x, pl_strain and T after spin-up + warm-up + timed steps
+    def bit_checksum(field):
+        a = np.ascontiguousarray(ctx.download(field)).view(np.uint64).reshape(-1)
+        lo, hi = int((a & np.uint64(0xFFFFFFFF)).sum(dtype=np.uint64)), int((a >> np.uint64(32)).sum(dtype=np.uint64))
+        t = torch.tensor([lo, hi], device="cuda", dtype=torch.int64)
+        if world > 1:
+            dist.all_reduce(t)
+        return "%016x%016x" % (int(t[1].item()) & (2 ** 64 - 1), int(t[0].item()) & (2 ** 64 - 1))
+    checksum = {"steps": int(s_after.steps), "max_pl_strain_hex": float(s_after.max_pl_strain).hex(),
+                "x": bit_checksum("x"), "pl_strain": bit_checksum("pl_strain"), "T": bit_checksum("T")}
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -384,6 +394,14 @@ def run_ours(args):
     else:
         peak_hbm = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
     alg = algorithmic_bytes(nb_avg)
+    # measured FP64 operation counts per launch (ncu smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on of the 10M workload,
+    # profiles/fp64_ops.json written by scripts/ncu_ops.py): flop = dadd + dmul + 2 dfma, per particle
+    fp64_ops = {}
+    op = os.path.join(ROOT, "profiles", "fp64_ops.json")
+    if os.path.exists(op):
+        for kname, rec in json.load(open(op)).items():
+            if rec.get("particles"):
+                fp64_ops[kname] = {"flop_per_particle": (rec["dadd"] + rec["dmul"] + 2.0 * rec["dfma"]) / rec["particles"], "pipe_fp64_pct": rec.get("pipe_fp64_pct")}
     n_loc_now = ctx.n_sph                    # particles this rank's kernels process (== the domain on one GPU)
     total_prof = sum(v[0] for v in prof.values()) or 1.0
     kernels = {}
@@ -392,11 +410,16 @@ def run_ours(args):
             continue
         ent = {"ms_per_launch": kms / kn, "launches": int(kn), "share_of_step": kms / total_prof}
         if name in alg and alg[name] > 0:
+            # one PASS over this rank's particles = every launch of the family in one step (on several GPUs a pass is an interior launch + a
+            # boundary launch): algorithmic bytes of the rank / time of the pass
+            per_pass = kms / args.steps
+            ent["ms_per_pass"] = per_pass
             ent["alg_bytes_per_particle"] = alg[name]
-            ent["hbm_gbs"] = alg[name] * n_loc_now / (kms / kn * 1e-3) / 1e9
+            ent["hbm_gbs"] = alg[name] * n_loc_now / (per_pass * 1e-3) / 1e9
             ent["hbm_frac"] = ent["hbm_gbs"] / peak_hbm
-        if name in FLOPS_PER_PAIR:
-            ent["fp64_tflops_est"] = FLOPS_PER_PAIR[name] * nb_avg * n_loc_now / (kms / kn * 1e-3) / 1e12
+            if name in fp64_ops:
+                ent["fp64_flop_per_particle_measured"] = fp64_ops[name]["flop_per_particle"]
+                ent["fp64_tflops"] = fp64_ops[name]["flop_per_particle"] * n_loc_now / (per_pass * 1e-3) / 1e12
         kernels[name] = ent
     pair_names = [k for k in ("accel", "rate_stress", "post", "energy") if k in kernels]
     dom = max(pair_names, key=lambda k: kernels[k]["share_of_step"]) if pair_names else None
@@ -410,14 +433,16 @@ def run_ours(args):
                 traffic = tj["dram_bytes_per_launch"]
         k = kernels[dom]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": k["hbm_gbs"], "peak": peak_hbm, "unit": "GB/s", "frac": k["hbm_frac"], "traffic": traffic,
-                    "peak_source": peak_src, "alg_bytes_per_launch": k["alg_bytes_per_particle"] * n_loc_now, "ms_per_launch": k["ms_per_launch"],
-                    "share_of_step": k["share_of_step"],
+                    "peak_source": peak_src, "alg_bytes_per_launch": k["alg_bytes_per_particle"] * n_loc_now, "ms_per_launch": k["ms_per_pass"],
+                    "launches_per_pass": k["launches"] / args.steps, "share_of_step": k["share_of_step"],
                     "note": "fp64 gather pair loop: the FP64 pipe, not HBM, is the binding roof (see fp64); HBM fraction is on unique algorithmic bytes"}
         try:
             fp64_peak = ctx.measure_fp64_peak()
-            roofline["fp64"] = {"achieved_tflops_est": k.get("fp64_tflops_est"), "peak_tflops_measured_dfma": fp64_peak,
-                                "frac": (k.get("fp64_tflops_est") or 0.0) / fp64_peak if fp64_peak else None,
-                                "flops_per_pair_visit": FLOPS_PER_PAIR.get(dom)}
+            roofline["fp64"] = {"achieved_tflops": k.get("fp64_tflops"), "peak_tflops_measured_dfma": fp64_peak,
+                                "frac": (k.get("fp64_tflops") / fp64_peak) if (fp64_peak and k.get("fp64_tflops")) else None,
+                                "flop_per_particle_measured": k.get("fp64_flop_per_particle_measured"),
+                                "ncu_pipe_fp64_pct": fp64_ops.get(dom, {}).get("pipe_fp64_pct"),
+                                "source": "profiles/fp64_ops.json (ncu op counters of this kernel build); flop = dadd + dmul + 2*dfma executed"}
         except Exception as exc:       # noqa: BLE001
             roofline["fp64"] = {"error": str(exc)}
 
@@ -437,7 +462,7 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(n_sph, {"decomposition": ("1 GPU" if world == 1 else "%d slabs along z, NCCL halos (3 refreshes per step), rank 0: %s" % (world, comm_info)),
                                                   "neighbours_avg": nb_avg, "spinup_steps": spin, "nb_rebuilds_in_timed_region": int(prof.get("nb_list", (0, 0))[1]),
-                                                  "max_pl_strain": s_after.max_pl_strain,
+                                                  "max_pl_strain": s_after.max_pl_strain, "state_checksum": checksum,
                                                   **({"contact": "two rigid AxisPlaneMesh planes (%d elements each), Wang penalty contact, friction 0.2; contact force sum %.4g N" % (info["meshes"][0][1], s_after.contact_force_sum)} if contact else {})}),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line), flush=True)

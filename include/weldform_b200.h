@@ -195,6 +195,9 @@ int wf_thermal(wf_ctx *ctx);                        /* CalcPlasticWorkHeat + The
 int wf_energy(wf_ctx *ctx);                         /* CalcKinEnergyEqn + CalcIntEnergyEqn (:375-376) */
 int wf_step_end(wf_ctx *ctx);                       /* Time += dt, TriMesh::Update, UpdateContactParticles, cadence (:384-412) */
 int wf_reduce(wf_ctx *ctx, wf_scalars *out);        /* blocking: scalars */
+/* Domain::m_contact_force (Domain.h:302; summed per rigid mesh in CalcContactForcesWang, Contact_Wang.cpp:312; the History.csv columns of
+ * SolverFraser.cpp:476-482): out[3*m + k] for the first cap_meshes meshes, as of the last completed step. Blocking. At most 6 meshes. */
+int wf_mesh_forces(wf_ctx *ctx, double *out, int cap_meshes);
 
 /* Whole steps. stage_a = begin .. contact; [GeneralAfter]; stage_b = move x, v; [GeneralAfter]; stage_c = thermal .. end. */
 int wf_fraser_stage_a(wf_ctx *ctx);

@@ -64,3 +64,20 @@ def max_rel(a, b):
     if scale == 0.0:
         return float(np.max(np.abs(a))) if a.size else 0.0
     return float(np.max(np.abs(a - b)) / scale)
+
+
+ELEM_FLOOR = 1e-6
+
+
+def max_rel_elem(a, b, floor=ELEM_FLOOR):
+    """ELEMENT-WISE relative error: max_k |a_k - b_k| / max(|b_k|, floor * max|b|). Every entry is judged against its own magnitude; the
+    floor (a fraction of the field's largest entry) only keeps entries that are zero up to round-off -- sums that cancel -- from dividing
+    by nothing. 0 for two all-zero fields."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    if not b.size:
+        return 0.0
+    top = float(np.max(np.abs(b)))
+    if top == 0.0:
+        return float(np.max(np.abs(a)))
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor * top)))

@@ -1,0 +1,175 @@
+"""The reference's OWN example drivers (BASELINE.json's configurations: /root/reference/examples/{Compression,Compression_thermal,
+Contact_Compression_1010,FSW}.cpp), compiled UNCHANGED against the host mirror (weldform_b200/host/bin/ref_*, built by
+weldform_b200/build.py where /root/reference exists), run on the GPU and compared with what the reference itself writes
+(tests/golden/drivers/*.npz, made by tests/golden/drivers/make_driver_goldens.py from the reference binaries oracle/_ref/drv_*).
+
+What the reference's drivers do in this snapshot (oracle/Makefile):
+  Compression_thermal        runs to the end (2 924 steps, 106 tables)                               -> whole run pinned
+  Compression                Gradient_Approach_Set(2) is unstable here; heap corruption near step 34 -> table 1 pinned
+  Contact_Compression_1010   segfaults as shipped (m_contact_force never sized); with the one-line fix it explodes and stops with
+                             "No external particles found" at step 136                              -> table 1 + the Fatal pinned
+  FSW                        segfaults as shipped (same); with the fix it runs (days of CPU time)     -> tables 1-3 (1 845 steps) pinned
+  Plate-Yield_3d             calls Domain::Solve, which throws in the reference                      -> the mirror throws alike (test_host_api.py)
+
+Comparison: the WriteCSV tables carry 6 significant digits. An entry passes when |ours - ref| <= rtol * max(|ref|, floor * max|column|):
+element-wise, with a floor so that entries that are zero up to round-off (vx on the axis ...) are judged against the column's scale.
+"""
+import os
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "weldform_b200", "host", "bin")
+GOLD = os.path.join(ROOT, "tests", "golden", "drivers")
+REFDATA = os.path.join(ROOT, "oracle", "_ref")
+COLS = ["X", "Y", "Z", "ID", "Sigma_eq", "Pl_Strain", "vx", "vy", "vz", "ax", "ay", "az", "CFx", "CFy", "CFz", "p", "Temp"]
+
+
+def read_csv_table(path):
+    with open(path) as f:
+        f.readline()
+        rows = [[float(t) for t in line.replace(",", " ").split()] for line in f if line.strip()]
+    return np.asarray(rows, dtype=np.float64)
+
+
+def read_rows(path):
+    out = []
+    with open(path) as f:
+        for line in f:
+            toks = [t.strip() for t in line.strip().split(",")]
+            try:
+                out.append([float(t) if t else np.nan for t in toks])
+            except ValueError:
+                continue
+    w = max((len(r) for r in out), default=0)
+    return np.asarray([r + [np.nan] * (w - len(r)) for r in out], dtype=np.float64).reshape(len(out), w)
+
+
+def run_mirror_driver(name, sync, max_outputs, needs=(), timeout=1500, extra_env=None):
+    exe = os.path.join(BIN, "ref_" + name)
+    if not os.path.exists(exe):
+        pytest.fail("%s is missing: weldform_b200/build.py builds it where /root/reference exists and it ships with the repo snapshot" % exe)
+    d = tempfile.mkdtemp(prefix="mirror_%s_" % name)
+    for f in needs:
+        shutil.copy(os.path.join(REFDATA, f), os.path.join(d, f))
+    env = dict(os.environ, WELDFORM_SYNC=sync, WELDFORM_MAX_OUTPUTS=str(max_outputs))
+    env.update(extra_env or {})
+    with open(os.path.join(d, "log.txt"), "w") as log:
+        r = subprocess.run([exe], cwd=d, stdout=log, stderr=subprocess.STDOUT, env=env, timeout=timeout)
+    keep = os.environ.get("WF_KEEP_DRIVER_OUT")
+    if keep:
+        dst = os.path.join(keep, "%s_%s" % (name, sync))
+        shutil.rmtree(dst, ignore_errors=True)
+        shutil.copytree(d, dst, ignore=shutil.ignore_patterns("*.nas", "*.xmf", "*.h5"))
+    return d, r.returncode
+
+
+def worst_entries(ours, ref, floor):
+    """max over entries of |ours - ref| / max(|ref|, floor * max|column|), per column"""
+    scale = np.maximum(np.abs(ref), floor * np.max(np.abs(ref), axis=0, keepdims=True))
+    scale[scale == 0.0] = 1.0
+    return np.max(np.abs(ours - ref) / scale, axis=0)
+
+
+def compare_tables(d, gold, key, rtol_of_table, floor=1e-3, what=""):
+    stride = int(gold["stride"])
+    report = {}
+    for idx in gold["kept"].tolist():
+        ref = gold["table_%04d" % idx].astype(np.float64)
+        path = os.path.join(d, "%s_%04d.csv" % (key, idx))
+        assert os.path.exists(path), "%s: the mirror did not write %s" % (what, os.path.basename(path))
+        ours = read_csv_table(path)
+        assert ours.shape[0] == int(gold["rows_%04d" % idx]), "%s table %d: %d rows, the reference wrote %d" % (what, idx, ours.shape[0], int(gold["rows_%04d" % idx]))
+        ours = ours[::stride]
+        assert np.array_equal(ours[:, 3], ref[:, 3]), "%s table %d: particle IDs differ" % (what, idx)
+        w = worst_entries(ours, ref, floor)
+        report[idx] = dict(zip(COLS, w.tolist()))
+        rtol = rtol_of_table(idx)
+        bad = {c: v for c, v in report[idx].items() if v > rtol}
+        assert not bad, "%s table %d (rtol %.1e, element-wise): %s" % (what, idx, rtol, bad)
+    return report
+
+
+def compare_history(d, gold, rtol, what=""):
+    """History.csv / Prop.csv: the mirror writes a row per table; the reference's extra wall-clock rows are skipped by matching time stamps."""
+    for fname, key in (("History.csv", "history"), ("Prop.csv", "prop")):
+        ref = gold[key]
+        if ref.size == 0:
+            continue
+        ours = read_rows(os.path.join(d, fname))
+        assert ours.shape[0] >= 1 and ours.shape[1] == ref.shape[1], "%s %s: %s columns, reference %s" % (what, fname, ours.shape, ref.shape)
+        matched = 0
+        for row in ours:
+            j = np.where(np.abs(ref[:, 0] - row[0]) <= 1e-5 * max(abs(row[0]), 1e-300))[0]
+            if j.size == 0:
+                continue
+            matched += 1
+            r = ref[j[0]]
+            scale = np.maximum(np.abs(r), 1e-3 * np.nanmax(np.abs(ref), axis=0))
+            scale[~(scale > 0)] = 1.0
+            err = np.abs(row - r) / scale
+            assert np.nanmax(err) <= rtol, "%s %s row t=%g: %s vs %s" % (what, fname, row[0], row, r)
+        assert matched >= min(len(ours), int(gold["kept"].size)) - 1, "%s %s: only %d rows matched the reference's time stamps" % (what, fname, matched)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sync", ["full", "tagged"])
+def test_compression_thermal_driver_whole_run(sync):
+    """examples/Compression_thermal.cpp, the configuration BASELINE.json's metric is quoted on (12 144 particles as shipped): the whole run,
+    2 924 steps with the GeneralAfter callback on host Particle objects twice per step, 106 output tables; six of them are pinned, through
+    yield (max plastic strain 0.28 at the end)."""
+    gold = np.load(os.path.join(GOLD, "Compression_thermal.npz"))
+    d, rc = run_mirror_driver("Compression_thermal", sync, int(gold["kept"].max()))
+    assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
+    # printed precision (a unit in the 6th digit is 1e-5 .. 1e-6 relative) for the first 1 000 steps; afterwards the accumulated round-off of the
+    # different (but fixed) summation grouping of the device shows in the accelerations of a body that has yielded through
+    compare_tables(d, gold, "test06", lambda idx: 1e-5 if idx <= 30 else 2e-4, what="Compression_thermal/" + sync)
+    compare_history(d, gold, 1e-5, what="Compression_thermal/" + sync)
+    shutil.rmtree(d, ignore_errors=True)
+
+
+@pytest.mark.gpu
+def test_compression_driver_first_table():
+    """examples/Compression.cpp (Gradient_Approach_Set(2)): the reference is unstable in this configuration and corrupts its heap near step 34
+    (SURVEY.md section 8c); what it writes before -- the table after the first step -- is pinned."""
+    gold = np.load(os.path.join(GOLD, "Compression.npz"))
+    d, rc = run_mirror_driver("Compression", "full", 1)
+    assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
+    compare_tables(d, gold, "test06", lambda idx: 1e-5, what="Compression")
+    shutil.rmtree(d, ignore_errors=True)
+
+
+@pytest.mark.gpu
+def test_contact_compression_1010_driver():
+    """examples/Contact_Compression_1010.cpp (Hollomon, gradKernelCorr, two rigid planes, friction; the callback reads Sigma, a and Mass of the
+    first particle row and steers the meshes with SetVel): table 1 + History row pinned; left to run, the reference (with the m_contact_force
+    fix) explodes and ends with the Fatal "No external particles found" at step 136 -- the mirror must end the same way, not run on."""
+    gold = np.load(os.path.join(GOLD, "Contact_Compression_1010.npz"))
+    d, rc = run_mirror_driver("Contact_Compression_1010", "full", 1)
+    assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
+    compare_tables(d, gold, "test06", lambda idx: 1e-5, what="Contact_Compression_1010")
+    compare_history(d, gold, 1e-5, what="Contact_Compression_1010")
+    shutil.rmtree(d, ignore_errors=True)
+    d, rc = run_mirror_driver("Contact_Compression_1010", "full", 3, timeout=600)
+    log = open(os.path.join(d, "log.txt")).read()
+    assert rc != 0 and "No external particles found" in log, log[-2000:]
+    import re
+    m = re.search(r"at step (\d+), time", log)
+    assert m and 120 <= int(m.group(1)) <= 150, "the mirror's run ended at another point than the reference's (step 136): %s" % (m.group(0) if m else log[-500:])
+    shutil.rmtree(d, ignore_errors=True)
+
+
+@pytest.mark.gpu
+def test_fsw_driver_first_tables():
+    """examples/FSW.cpp: 41 405 particles, Johnson-Cook, convection BC, fixed walls, the rotating + plunging tool read from Tool.nas through
+    NastranReader, friction linear in T with friction heat; tables 1-3 (1 845 steps)."""
+    gold = np.load(os.path.join(GOLD, "FSW.npz"))
+    d, rc = run_mirror_driver("FSW", "full", int(gold["kept"].max()), needs=["Tool.nas"])
+    assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
+    compare_tables(d, gold, "test06", lambda idx: 1e-5, what="FSW")
+    compare_history(d, gold, 1e-5, what="FSW")
+    shutil.rmtree(d, ignore_errors=True)

@@ -75,8 +75,38 @@ def build_host_examples(force=False):
     return out
 
 
+REF_EXAMPLES = "/root/reference/examples"
+REF_DRIVERS = ["Compression", "Compression_thermal", "Contact_Compression_1010", "FSW"]
+
+
+def build_reference_drivers(force=False):
+    """The reference's OWN example drivers (BASELINE.json's configurations), compiled UNCHANGED from /root/reference/examples against the host
+    mirror (weldform_b200/host/) and linked with libweldform_b200.so -> host/bin/ref_<name>. Only where /root/reference exists (the build
+    container); the binaries are git-ignored and travel to the GPU box like the library. No reference source is copied."""
+    if not os.path.isdir(REF_EXAMPLES):
+        return [os.path.join(HOST_BIN, "ref_" + d) for d in REF_DRIVERS if os.path.exists(os.path.join(HOST_BIN, "ref_" + d))]
+    build()
+    os.makedirs(HOST_BIN, exist_ok=True)
+    out, procs = [], []
+    for d in REF_DRIVERS:
+        src = os.path.join(REF_EXAMPLES, d + ".cpp")
+        exe = os.path.join(HOST_BIN, "ref_" + d)
+        deps = [src, LIB] + [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith((".h", ".cpp"))]
+        if force or not os.path.exists(exe) or any(os.path.getmtime(x) > os.path.getmtime(exe) for x in deps):
+            cmd = ["g++", "-std=c++14", "-O2", "-fpermissive", "-w", "-fopenmp", "-D_USE_MATH_DEFINES", "-I" + HOST_DIR, "-I" + os.path.join(os.path.dirname(HERE), "include"),
+                   src, "-o", exe, "-L" + HERE, "-lweldform_b200", "-Wl,-rpath,$ORIGIN/../.."]
+            procs.append((d, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        out.append(exe)
+    for d, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(o)
+            raise RuntimeError("reference driver %s does not compile against the host mirror" % d)
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)
-    for exe in build_host_examples():
+    for exe in build_host_examples() + build_reference_drivers():
         print(exe)

@@ -339,6 +339,15 @@ int comm_rebalance(wf_ctx *c)
     return 0;
 }
 
+// wf_destroy: release the NCCL communicator (collective-free: ncclCommDestroy only tears down this rank's resources)
+void comm_destroy(wf_ctx *c)
+{
+    if (!c->comm.nccl) return;
+    NcclApi *A = nccl_api();
+    if (A && A->CommDestroy) A->CommDestroy((ncclComm_t)c->comm.nccl);
+    c->comm.nccl = nullptr;
+}
+
 int comm_gather_scalars(wf_ctx *c, int nvals)
 {
     wf_ctx::Comm &m = c->comm;

@@ -84,7 +84,7 @@ extern "C" void wf_destroy(wf_ctx *c)
     }
     cudaFree(c->slot_of); cudaFree(c->d_classes); cudaFree(c->d_mats); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->mcell_start); cudaFree(c->mcell_end);
     cudaFree(c->cub_tmp); cudaFree(c->nbr); cudaFree(c->nb_cnt); cudaFree(c->nb_hi); cudaFree(c->d_maxcnt);
-    cudaFree(c->cont); cudaFree(c->cont_cnt); cudaFree(c->d_mesh_ids); cudaFree(c->d_bcs); cudaFree(c->d_sc); cudaFree(c->d_partial);
+    cudaFree(c->cont); cudaFree(c->cont_cnt); cudaFree(c->d_mesh_ids); cudaFree(c->d_bcs); cudaFree(c->d_sc); cudaFree(c->d_partial); cudaFree(c->d_mf_part); cudaFree(c->d_mf_flag);
     cudaFree(c->dm.node); cudaFree(c->dm.node_v); cudaFree(c->dm.en); cudaFree(c->dm.nfar); cudaFree(c->dm.emesh);
     cudaFree(c->dm.enormal); cudaFree(c->dm.ev); cudaFree(c->dm.pplane); cudaFree(c->dm.motion);
     cudaFree(c->comm.d_emig); cudaFree(c->comm.d_cnt); cudaFree(c->comm.d_rank); cudaFree(c->comm.d_all);
@@ -97,6 +97,7 @@ extern "C" void wf_destroy(wf_ctx *c)
     if (c->comm.stream) { cudaStreamSynchronize(c->comm.stream); cudaStreamDestroy(c->comm.stream); }
     if (c->comm.ev_ready) cudaEventDestroy(c->comm.ev_ready); if (c->comm.ev_done) cudaEventDestroy(c->comm.ev_done);
     for (auto &e : c->comm.t_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    comm_destroy(c);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -523,7 +524,7 @@ __global__ void k_download(FieldView v, int f, int ncomp, int is_int, int64_t n,
     int64_t cnt = idx ? nidx : n;
     if (t >= cnt) return;
     int64_t s, o;
-    if (idx) { s = slot_of[idx[t]]; o = t; } else { s = t; o = orig[t]; }
+    if (idx) { const int64_t li = idx[t]; s = slot_of[(li < 0 || li >= n) ? 0 : li]; o = t; } else { s = t; o = orig[t]; }
     double val[9]; int iv = 0;
     field_get(v, f, s, val, iv);
     if (is_int) ((int *)out)[o] = iv;
@@ -534,6 +535,13 @@ static FieldView view_of(wf_ctx *c)
 {
     FieldView v; v.Q0 = c->Q0[c->cur]; v.Q1 = c->Q1[c->cur]; v.Q2 = c->Q2[c->cur]; v.S0 = c->S0[c->cur]; v.S1 = c->S1[c->cur]; v.S2 = c->S2[c->cur];
     v.F = c->F[c->cur]; v.I = c->I[c->cur]; v.cap = c->cap; return v;
+}
+
+// subset indices are local creation indices of THIS rank's current particles (they go stale when particles migrate between ranks)
+static int check_subset(wf_ctx *c, const int32_t *idx, int64_t n, const char *what)
+{
+    for (int64_t k = 0; k < n; ++k) if (idx[k] < 0 || idx[k] >= c->n_loc) return fail(c, WF_ERR_ARG, "%s: index %d at position %lld is outside [0, %lld)", what, (int)idx[k], (long long)k, (long long)c->n_loc);
+    return 0;
 }
 
 static int download_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, void *host, const int *dev_idx = nullptr)
@@ -558,20 +566,34 @@ static int download_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx
 }
 extern "C" int wf_download(wf_ctx *c, wf_field f, void *host) { return download_impl(c, f, nullptr, 0, host); }
 extern "C" int wf_download_subset(wf_ctx *c, wf_field f, const int32_t *idx, int64_t n, void *host)
-{ if (n > 0 && !idx) return WF_ERR_ARG; return download_impl(c, f, idx, n, host); }
+{ if (n > 0 && !idx) return WF_ERR_ARG; if (c && c->have_particles) WF_CHECK(check_subset(c, idx, n, "wf_download_subset")); return download_impl(c, f, idx, n, host); }
 
-__global__ void k_upload(double4 *Q0, double4 *Q1, double4 *Q2, double *F, int *I, int64_t cap, int f, int64_t n, const int *slot_of, const int *idx, int64_t nidx, const void *in)
+__global__ void k_upload(double4 *Q0, double4 *Q1, double4 *Q2, double4 *S0, double4 *S1, int gt, double *F, int *I, int64_t cap, int f, int64_t n, const int *slot_of, const int *idx, int64_t nidx, const void *in)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t cnt = idx ? nidx : n;
     if (t >= cnt) return;
-    int64_t s = slot_of[idx ? idx[t] : t];
+    const int64_t li = idx ? idx[t] : t;
+    if (li < 0 || li >= n) return;               // stale or bad subset index: never scatter outside this rank's particles (the host entry points validate too)
+    int64_t s = slot_of[li];
     const double *d = (const double *)in;
     switch (f) {
     case WF_F_X: { double4 q = Q0[s]; q.x = d[3 * t]; q.y = d[3 * t + 1]; q.z = d[3 * t + 2]; Q0[s] = q; } break;
     case WF_F_V: { double4 q = Q1[s]; q.x = d[3 * t]; q.y = d[3 * t + 1]; q.z = d[3 * t + 2]; Q1[s] = q; } break;
     case WF_F_A: F[(int64_t)F_AX * cap + s] = d[3 * t]; F[(int64_t)F_AY * cap + s] = d[3 * t + 1]; F[(int64_t)F_AZ * cap + s] = d[3 * t + 2]; break;
-    case WF_F_DENSITY: { double4 q = Q2[s]; q.y = d[t]; Q2[s] = q; double4 w = Q1[s]; w.w = q.x / d[t]; Q1[s] = w; } break;
+    case WF_F_DENSITY: {
+        // every gathered cache derived from the density follows it: m/rho (Q1.w), P/rho^2 (Q2.w) and, for GradientType 0, Sigma/rho^2 (S0, S1) --
+        // the reference evaluates all three from the particle's current Density at the point of use (InteractionAlt.cpp:139,455, Domain.cpp:1784)
+        const double rho = d[t];
+        double4 q = Q2[s]; q.y = rho; q.w = F[(int64_t)F_PRES * cap + s] / (rho * rho); Q2[s] = q;
+        double4 w = Q1[s]; w.w = q.x / rho; Q1[s] = w;
+        if (gt == 0) {
+            const double inv_d2 = 1.0 / (rho * rho);
+            const double *sg = F + (int64_t)F_SG * cap + s;
+            S0[s] = make_double4(sg[0] * inv_d2, sg[cap] * inv_d2, sg[2 * cap] * inv_d2, sg[3 * cap] * inv_d2);
+            ((double2 *)&S1[s])[0] = make_double2(sg[4 * cap] * inv_d2, sg[5 * cap] * inv_d2);
+        }
+    } break;
     case WF_F_T: { double4 q = Q2[s]; q.z = d[t]; Q2[s] = q; } break;
     case WF_F_SIGMAY: F[(int64_t)F_SIGY * cap + s] = d[t]; break;
     case WF_F_ID: I[(int64_t)I_ID * cap + s] = ((const int *)in)[t]; break;
@@ -593,7 +615,7 @@ static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, 
     WF_CUDA(c, cudaMemcpyAsync(c->stage, host, (size_t)cnt * nc * (isint ? 4 : 8), cudaMemcpyHostToDevice, c->stream));
     const int *d_idx = dev_idx;
     if (idx) { int *t_ = (int *)((char *)c->stage + bytes); WF_CUDA(c, cudaMemcpyAsync(t_, idx, (size_t)nidx * 4, cudaMemcpyHostToDevice, c->stream)); d_idx = t_; }
-    k_upload<<<grid_for(cnt, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->F[c->cur], c->I[c->cur], c->cap, (int)f, c->n_loc, c->slot_of, d_idx, nidx, c->stage);
+    k_upload<<<grid_for(cnt, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->S0[c->cur], c->S1[c->cur], c->prm.gradient_type, c->F[c->cur], c->I[c->cur], c->cap, (int)f, c->n_loc, c->slot_of, d_idx, nidx, c->stage);
     WF_LAUNCH_CHECK(c);
     if (!async) WF_CUDA(c, cudaStreamSynchronize(c->stream));
     if (f == WF_F_X || f == WF_F_V || f == WF_F_DENSITY) c->dens_valid = false;   // the prepared density rate no longer matches the state
@@ -601,13 +623,15 @@ static int upload_impl(wf_ctx *c, wf_field f, const int32_t *idx, int64_t nidx, 
 }
 extern "C" int wf_upload(wf_ctx *c, wf_field f, const void *host) { return upload_impl(c, f, nullptr, 0, host); }
 extern "C" int wf_upload_subset(wf_ctx *c, wf_field f, const int32_t *idx, int64_t n, const void *host)
-{ if (n > 0 && !idx) return WF_ERR_ARG; return upload_impl(c, f, idx, n, host); }
+{ if (n > 0 && !idx) return WF_ERR_ARG; if (c && c->have_particles) WF_CHECK(check_subset(c, idx, n, "wf_upload_subset")); return upload_impl(c, f, idx, n, host); }
 
 // Registered subsets: the index list of a callback's tagged particles lives on the device, so that the per-step bridge moves field
 // values only (the reference's GeneralAfter callbacks touch the same particles every step)
 extern "C" int wf_subset_register(wf_ctx *c, const int32_t *idx, int64_t n, int *handle)
 {
     if (!c || !handle || n < 0 || (n > 0 && !idx)) return WF_ERR_ARG;
+    if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_subset_register: no particles");
+    WF_CHECK(check_subset(c, idx, n, "wf_subset_register"));
     cudaSetDevice(c->device);
     int *d = nullptr;
     if (n > 0) { WF_CUDA(c, cudaMalloc(&d, (size_t)n * sizeof(int))); WF_CUDA(c, cudaMemcpy(d, idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice)); }

@@ -9,6 +9,8 @@
 #include "../../include/weldform_b200.h"
 #include "wf_math.cuh"
 
+#define WF_MAX_MESH_FORCES 6      // rigid meshes whose summed contact force (Domain::m_contact_force) rides in the 32-double scalar record
+
 namespace wf {
 
 // ---- property classes: distinct tuples of the per-particle constants the drivers assign (Particle.h:53-231) ------
@@ -57,7 +59,7 @@ struct DevScalars {
     double kin_energy_sum, int_energy_sum, plastic_work, contact_force_sum, contact_reaction_sum, ext_forces_work,
            contact_friction_work, accum_cont_heat_cond;
     double max_pl_strain, max_disp2[3], max_disp2_prev[3], max_T, min_T;
-    double mcf[4][3];
+    double mcf[WF_MAX_MESH_FORCES][3];      // Domain::m_contact_force of the last completed step
 };
 
 enum ProfKernel { PK_NB_KEYS = 0, PK_NB_SORT, PK_NB_PERMUTE, PK_NB_CELLS, PK_NB_LIST, PK_NB_SURFACE, PK_NB_CONTACT,
@@ -128,6 +130,7 @@ struct wf_ctx {
     // scalars
     wf::DevScalars *d_sc = nullptr; wf::DevScalars *h_sc = nullptr;   // h_sc pinned
     double *d_partial = nullptr; int partial_blocks = 0;
+    double *d_mf_part = nullptr; int *d_mf_flag = nullptr; int mf_cap = 0, mf_blocks = 0;   // per-block m_contact_force partials of k_contact
     // solver state (SolverFraser.cpp:62-68)
     double prev_dt = 0.0;                        // deltat of the previous step (the kicks of the KickDrift / LeapFrog orders use both)
     double dt_init = 0.0, dt_min = 0.0;          // Domain::deltatint / deltatmin (adaptive time step, Domain.cpp:205-297)
@@ -195,6 +198,7 @@ int comm_halo_end(wf_ctx *c);
 int comm_time_begin(wf_ctx *c);                          // brackets the launch whose duration measures this rank's speed (no-op on one GPU)
 int comm_time_end(wf_ctx *c);
 int comm_rebalance(wf_ctx *c);                           // at a rebuild: move slab boundaries by at most one layer towards equal step time
+void comm_destroy(wf_ctx *c);                           // ncclCommDestroy, no-op on one GPU
 int comm_gather_scalars(wf_ctx *c, int nvals);          // d_rank -> d_all (all ranks), no-op on one GPU
 int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);

@@ -120,15 +120,17 @@ struct ContactArgs {
     int K; const int *cont, *cont_cnt; const double *node, *enormal, *ev, *pplane; const int *en, *emesh;
     double friction_sta, friction_dyn, dfac, contact_hc; int cont_heat_fric, cont_heat_cond;
     int friction_function; double friction_m, friction_b;
+    int n_mesh; double *mf_part; int *mf_flag;      // Domain::m_contact_force (Contact_Wang.cpp:312): per-block sums [block][WF_MAX_MESH_FORCES][3] + "block had a hit"
 };
-__global__ void k_contact(StepArgs a, ContactArgs k)
+__global__ void __launch_bounds__(128) k_contact(StepArgs a, ContactArgs k)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n) return;
     // resets (Contact_Wang.cpp:27-42)
     double cfx = 0., cfy = 0., cfz = 0., dcont = 0., qfric = 0., qcont = 0., csum = 0., creac = 0., cext = 0.;
-    const int cnt = k.cont_cnt[s];
+    double mf[WF_MAX_MESH_FORCES][3]; int hit = 0;
+    const int cnt = s < a.n ? k.cont_cnt[s] : 0;
     if (cnt > 0) {
+        for (int m = 0; m < WF_MAX_MESH_FORCES; ++m) mf[m][0] = mf[m][1] = mf[m][2] = 0.;
         const double4 q = a.Q0[s], w = a.Q1[s], q2 = a.Q2[s];
         const V3 x = v3(q.x, q.y, q.z), v = v3(w.x, w.y, w.z);
         const double h = q.w, Mass = q2.x, dens = q2.y, dt = a.dt;
@@ -178,6 +180,7 @@ __global__ void k_contact(StepArgs a, ContactArgs k)
                         }
                     }
                     cfx = cf.x; cfy = cf.y; cfz = cf.z;
+                    { const int m = k.emesh[e]; if (m < WF_MAX_MESH_FORCES) { mf[m][0] += cf.x; mf[m][1] += cf.y; mf[m][2] += cf.z; hit = 1; } }
                     csum += norm(cf);
                     creac += dot(acc, n2) * Mass;
                     cext += dot(cf, v2);
@@ -187,6 +190,21 @@ __global__ void k_contact(StepArgs a, ContactArgs k)
         }
         OWN(F_AX) = acc.x; OWN(F_AY) = acc.y; OWN(F_AZ) = acc.z;
     }
+    // m_contact_force[m] += contforce, summed block-wise in a fixed order (no atomics: the per-mesh force is the same bits on every run)
+    const int any = __syncthreads_or(hit);
+    if (k.mf_flag) {
+        if (threadIdx.x == 0) k.mf_flag[blockIdx.x] = any;
+        if (any) {
+            typedef cub::BlockReduce<double, 128> BR; __shared__ typename BR::TempStorage tmp;
+            for (int m = 0; m < k.n_mesh && m < WF_MAX_MESH_FORCES; ++m)
+                for (int d = 0; d < 3; ++d) {
+                    const double r = BR(tmp).Sum(hit ? mf[m][d] : 0.);
+                    __syncthreads();
+                    if (threadIdx.x == 0) k.mf_part[((int64_t)blockIdx.x * WF_MAX_MESH_FORCES + m) * 3 + d] = r;
+                }
+        }
+    }
+    if (s >= a.n) return;
     OWN(F_CFX) = cfx; OWN(F_CFY) = cfy; OWN(F_CFZ) = cfz; OWN(F_DCONT) = dcont; OWN(F_QFRIC) = qfric; OWN(F_QCONT) = qcont;
     OWN(F_CSUM) = csum; OWN(F_CREAC) = creac; OWN(F_CEXT) = cext;
 }
@@ -226,7 +244,8 @@ __global__ void k_mesh_elems(int n_elems, int nsph, const double *node, const do
 }
 
 // ---- reductions ---------------------------------------------------------------------------------------------------------
-enum { R_DKIN = 0, R_DINT, R_PLW, R_FRIC, R_COND, R_CSUM, R_CREAC, R_CEXT, R_NSUM, R_MAXPL = R_NSUM, R_MD0, R_MD1, R_MD2, R_TMAX, R_TMIN, R_NTOT };
+enum { R_DKIN = 0, R_DINT, R_PLW, R_FRIC, R_COND, R_CSUM, R_CREAC, R_CEXT, R_NSUM, R_MAXPL = R_NSUM, R_MD0, R_MD1, R_MD2, R_TMAX, R_TMIN, R_NTOT, R_MCF = R_NTOT };   // slots R_MCF .. R_MCF + 3*WF_MAX_MESH_FORCES - 1: m_contact_force
+static_assert(R_MCF + 3 * WF_MAX_MESH_FORCES <= 32, "scalar record is 32 doubles per rank");
 
 __global__ void __launch_bounds__(256) k_reduce_partial(StepArgs a, int first_fem, double *partial)
 {
@@ -261,9 +280,16 @@ __global__ void __launch_bounds__(256) k_reduce_partial(StepArgs a, int first_fe
     }
 }
 // stage 2: block partials -> this rank's totals (32 doubles)
-__global__ void __launch_bounds__(256) k_reduce_rank(const double *partial, int nblocks, double *out)
+__global__ void __launch_bounds__(256) k_reduce_rank(const double *partial, int nblocks, double *out, const double *mf_part, const int *mf_flag, int mf_blocks, int n_mesh)
 {
     typedef cub::BlockReduce<double, 256> BR; __shared__ typename BR::TempStorage tmp;
+    for (int q = 0; q < 3 * WF_MAX_MESH_FORCES; ++q) {          // per-mesh contact force: block partials of k_contact, fixed order
+        double v = 0.;
+        if (q < 3 * n_mesh) for (int b = threadIdx.x; b < mf_blocks; b += blockDim.x) if (mf_flag[b]) v += mf_part[(int64_t)b * 3 * WF_MAX_MESH_FORCES + q];
+        const double r = (q < 3 * n_mesh && mf_blocks > 0) ? BR(tmp).Sum(v) : 0.;
+        __syncthreads();
+        if (threadIdx.x == 0) out[R_MCF + q] = r;
+    }
     for (int k = 0; k < R_NTOT; ++k) {
         double v = (k < R_NSUM) ? 0. : (k == R_TMIN ? 1000. : 0.);
         for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
@@ -301,6 +327,7 @@ __global__ void k_reduce_final(const double *all, int nranks, DevScalars *sc, do
             sc->contact_friction_work += res[R_FRIC] * dt;      // Thermal.cpp:208
             sc->accum_cont_heat_cond += res[R_COND] * dt;       // Thermal.cpp:209
             sc->contact_force_sum = res[R_CSUM]; sc->contact_reaction_sum = res[R_CREAC];
+            for (int q = 0; q < 3 * WF_MAX_MESH_FORCES; ++q) { double v = 0.; for (int r = 0; r < nranks; ++r) v += all[r * 32 + R_MCF + q]; sc->mcf[q / 3][q % 3] = v; }
             sc->ext_forces_work += res[R_CEXT] * dt;            // Contact_Wang.cpp:344
             sc->time += dt;                                     // SolverFraser.cpp:384
         }
@@ -341,6 +368,15 @@ int contact_impl(wf_ctx *c)
     ContactArgs k; k.K = c->cont_k; k.cont = c->cont; k.cont_cnt = c->cont_cnt; k.node = c->dm.node; k.enormal = c->dm.enormal; k.ev = c->dm.ev; k.pplane = c->dm.pplane;
     k.en = c->dm.en; k.emesh = c->dm.emesh; k.friction_sta = c->prm.friction_sta; k.friction_dyn = c->prm.friction_dyn; k.friction_function = c->prm.friction_function; k.friction_m = c->prm.friction_m; k.friction_b = c->prm.friction_b; k.dfac = c->prm.dfac; k.contact_hc = c->prm.contact_hc;
     k.cont_heat_fric = c->prm.cont_heat_fric; k.cont_heat_cond = c->prm.cont_heat_cond;
+    const int nblk = grid_for(c->n_loc, 128);
+    if (nblk > c->mf_cap) {
+        cudaFree(c->d_mf_part); cudaFree(c->d_mf_flag); c->d_mf_part = nullptr; c->d_mf_flag = nullptr; c->mf_cap = 0;
+        const int want = nblk + nblk / 8 + 64;
+        WF_CUDA(c, cudaMalloc(&c->d_mf_part, (size_t)want * 3 * WF_MAX_MESH_FORCES * sizeof(double))); WF_CUDA(c, cudaMalloc(&c->d_mf_flag, (size_t)want * sizeof(int)));
+        c->mf_cap = want;
+    }
+    c->mf_blocks = nblk;
+    k.n_mesh = (int)c->meshes.size(); k.mf_part = c->d_mf_part; k.mf_flag = c->d_mf_flag;
     k_contact<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a, k); WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
@@ -375,7 +411,7 @@ int reduce_impl(wf_ctx *c, bool accumulate)
     int nb = std::min<int64_t>(c->partial_blocks, (c->n_loc + 255) / 256); if (nb < 1) nb = 1;
     const int first_fem = c->meshes.empty() ? 2147483647 : (int)c->meshes[0].first_particle;
     k_reduce_partial<<<nb, 256, 0, c->stream>>>(a, first_fem, c->d_partial); WF_LAUNCH_CHECK(c);
-    k_reduce_rank<<<1, 256, 0, c->stream>>>(c->d_partial, nb, c->comm.d_rank); WF_LAUNCH_CHECK(c);
+    k_reduce_rank<<<1, 256, 0, c->stream>>>(c->d_partial, nb, c->comm.d_rank, c->d_mf_part, c->d_mf_flag, c->mf_blocks, (int)std::min<size_t>(c->meshes.size(), WF_MAX_MESH_FORCES)); WF_LAUNCH_CHECK(c);
     WF_CHECK(comm_gather_scalars(c, 32));
     const bool multi = c->comm.nranks > 1;
     k_reduce_final<<<1, 32, 0, c->stream>>>(multi ? c->comm.d_all : c->comm.d_rank, multi ? c->comm.nranks : 1, c->d_sc, c->dt, accumulate ? 1 : 0); WF_LAUNCH_CHECK(c);
@@ -420,6 +456,7 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     if (c->n_ghost > 0 && c->prm.solver == 3) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles in ThermalSolve: the reference's loop never calls MoveGhost; not implemented");
     c->dt_init = c->dt_min = dt;
     c->dt = dt; c->time = 0.0; c->ts_i = 0; c->isfirst = true; c->isyielding = false; c->steps = 0; c->dens_valid = false; c->in_step = false;
+    WF_CUDA(c, cudaMemsetAsync(c->d_sc, 0, sizeof(DevScalars), c->stream));      // a second wf_solver_init starts from zeroed energy / work accumulators like the first
     k_set_time<<<1, 1, 0, c->stream>>>(c->d_sc, 0.0, dt); WF_LAUNCH_CHECK(c);
     StepArgs a = make_step_args(c);
     k_init_pressure<<<grid_for(c->n_loc, 256), 256, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c);       // InitialChecks
@@ -483,6 +520,16 @@ extern "C" int wf_reduce(wf_ctx *c, wf_scalars *out)
     out->contact_friction_work = d.contact_friction_work; out->accum_cont_heat_cond = d.accum_cont_heat_cond;
     out->max_T = d.max_T; out->min_T = d.min_T; out->steps = c->steps; out->nb_rebuilds = c->nb_rebuilds; out->is_yielding = c->isyielding ? 1 : 0;
     out->deltat = c->dt;
+    return 0;
+}
+
+extern "C" int wf_mesh_forces(wf_ctx *c, double *out, int cap_meshes)
+{
+    WF_NEED_READY(c);
+    if (!out || cap_meshes < 0) return WF_ERR_ARG;
+    if ((int)c->meshes.size() > WF_MAX_MESH_FORCES) return fail(c, WF_ERR_UNSUPPORTED, "wf_mesh_forces: more than %d rigid meshes", WF_MAX_MESH_FORCES);
+    WF_CHECK(fetch_scalars(c));
+    for (int m = 0; m < cap_meshes; ++m) for (int d = 0; d < 3; ++d) out[3 * m + d] = (m < (int)c->meshes.size()) ? c->h_sc->mcf[m][d] : 0.0;
     return 0;
 }
 

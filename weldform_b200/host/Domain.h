@@ -13,14 +13,18 @@
 //
 // Callback bridge. GeneralAfter runs twice per step on host Particle objects (SolverFraser.cpp:332,360). Environment
 // variable WELDFORM_SYNC selects what is mirrored around each call:
-//   full    (default, always correct) x, v, a, Sigma, T, pl_strain, Displacement, Density, Pressure of ALL particles are
-//           downloaded before the callback; v and a of all particles are uploaded after it;
-//   tagged  only particles whose ID differs from the most common ID (the boundary-condition rows of the usual drivers,
-//           e.g. ID 2/3 in examples/Compression_thermal.cpp:30-66) are mirrored -- O(surface) traffic instead of O(N);
+//   full    (default) x, v, a, Sigma, T, pl_strain, Displacement, Density, Pressure, Sigmay, ID of ALL particles are downloaded before the
+//           callback. After it v and a are uploaded, and so is every other member the device accepts (x, T, Density, Sigmay, ID) that the
+//           callback changed (compared with the downloaded values); a change to a member the device cannot take back (Sigma, pl_strain,
+//           Displacement, Pressure) throws a Fatal instead of being dropped silently;
+//   tagged  the same, for the particles whose ID differs from the most common ID only (the boundary-condition rows of the usual drivers,
+//           e.g. ID 2/3 in examples/Compression_thermal.cpp:30-66) -- O(surface) traffic instead of O(N);
 //   push    like tagged, but nothing is read back before the callback: for callbacks that only ASSIGN whole v and a vectors of their
 //           boundary rows (examples/Compression_thermal.cpp:30-66 does); v and a of the tagged rows are uploaded after it;
 //   none    the callback only sees scalars (time, max_disp, contact_force_sum) and trimesh[m]->SetVel.
 // Rigid-mesh velocities set from the callback (trimesh[m]->SetVel / SetRotAxisVel) are always forwarded.
+// Two more environment knobs, for driver tests that cannot afford a driver's full run: WELDFORM_MAX_STEPS=n and WELDFORM_MAX_OUTPUTS=k end
+// the solver loop after n steps / after the k-th output table, as if tf had been reached.
 #ifndef WF_HOST_DOMAIN_H
 #define WF_HOST_DOMAIN_H
 
@@ -83,7 +87,7 @@ public:
     void Gradient_Approach_Set(Gradient_Type const & GT) { GradientType = GT; }
     void Viscosity_Eq_Set(Viscosity_Eq_Type const & VQ) { VisEq = VQ; }
 
-    // ---- solvers (Source/Domain.h:197-210). Only the Fraser loop -- the one all shipped configurations use -- is implemented.
+    // ---- solvers (Source/Domain.h:197-210): the Fraser, KickDrift and LeapFrog loops and ThermalSolve run on the GPU
     void SolveDiffUpdateFraser(double tf, double dt, double dtOut, char const * TheFileKey, size_t maxidx);
     void SolveDiffUpdateKickDrift(double tf, double dt, double dtOut, char const * k, size_t m) { solve_kick_drift_leap_frog(1, tf, dt, dtOut, k, m); }
     void SolveDiffUpdateLeapFrog(double tf, double dt, double dtOut, char const * k, size_t m) { solve_kick_drift_leap_frog(2, tf, dt, dtOut, k, m); }
@@ -159,12 +163,17 @@ private:
     enum SyncMode { SYNC_FULL = 0, SYNC_TAGGED = 1, SYNC_NONE = 2, SYNC_PUSH = 3 } sync_mode = SYNC_FULL;
     std::vector<int32_t> sync_idx;             // creation indices mirrored around callbacks (empty + SYNC_FULL: everything)
     std::vector<double> buf3, buf9, buf1;
+    // values the bridge handed to the last callback (FULL / TAGGED): what sync_up compares against
+    std::vector<double> snap_x, snap_T, snap_dens, snap_sigy, snap_sigma, snap_pls, snap_disp, snap_pres; std::vector<int32_t> snap_id;
+    bool have_snap = false;
+    long long max_steps_env = -1, max_outputs_env = -1;
+    std::ofstream history_of, prop_of;
     std::vector<Vec3_t> sent_mv, sent_mw;
     struct MeshRec { TriMesh * mesh; float hfac; int id; };
     std::vector<MeshRec> mesh_recs;
 
     void not_implemented(const char * what) { throw new Fatal("Domain::%s is not implemented in weldform_b200 (SURVEY.md section 8f, next rows); the shipped configurations use SolveDiffUpdateFraser", what); }
-    void ck(int rc, const char * what) { if (rc != 0) throw new Fatal("%s failed (%d): %s", what, rc, wf_last_error(backend)); }
+    void ck(int rc, const char * what) { if (rc != 0) throw new Fatal("%s failed (%d) at step %d, time %g: %s", what, rc, (int)steps, Time, wf_last_error(backend)); }
     void backend_begin(double dt);
     void backend_end();
     void choose_sync();
@@ -172,6 +181,11 @@ private:
     void get9(wf_field f, Mat3_t Particle::*mem, bool subset);
     void get1(wf_field f, double Particle::*mem, bool subset);
     void put3(wf_field f, Vec3_t Particle::*mem, bool subset);
+    void put1_if_changed(wf_field f, double Particle::*mem, std::vector<double> & snap, bool subset);
+    void refuse_if_changed(const char * what, const std::vector<double> & snap, int nc, bool subset, double (*get)(const Particle *, int));
+    void open_history();
+    void write_history();
+    bool env_stop(size_t idx_out) const { return (max_steps_env >= 0 && (long long)steps >= max_steps_env) || (max_outputs_env >= 0 && (long long)idx_out > max_outputs_env); }
     void sync_down(bool everything);
     void sync_up();
     void forward_mesh_motion();
@@ -398,6 +412,9 @@ inline void Domain::choose_sync()
     if (m && std::strcmp(m, "tagged") == 0) sync_mode = SYNC_TAGGED;
     if (m && std::strcmp(m, "none") == 0) sync_mode = SYNC_NONE;
     if (m && std::strcmp(m, "push") == 0) sync_mode = SYNC_PUSH;
+    const char * ms = std::getenv("WELDFORM_MAX_STEPS"); max_steps_env = ms ? std::atoll(ms) : -1;
+    const char * mo = std::getenv("WELDFORM_MAX_OUTPUTS"); max_outputs_env = mo ? std::atoll(mo) : -1;
+    have_snap = false;
     sync_idx.clear();
     if (sync_mode == SYNC_TAGGED || sync_mode == SYNC_PUSH) {
         std::map<int, size_t> hist;
@@ -564,7 +581,23 @@ inline void Domain::sync_down(bool everything)
     get3(WF_F_X, &Particle::x, subset); get3(WF_F_V, &Particle::v, subset); get3(WF_F_A, &Particle::a, subset);
     get3(WF_F_DISPLACEMENT, &Particle::Displacement, subset); get9(WF_F_SIGMA, &Particle::Sigma, subset);
     get1(WF_F_T, &Particle::T, subset); get1(WF_F_PL_STRAIN, &Particle::pl_strain, subset); get1(WF_F_DENSITY, &Particle::Density, subset);
-    get1(WF_F_PRESSURE, &Particle::Pressure, subset);
+    get1(WF_F_PRESSURE, &Particle::Pressure, subset); get1(WF_F_SIGMAY, &Particle::Sigmay, subset);
+    {
+        const size_t n = subset ? sync_idx.size() : Particles.Size(); std::vector<int32_t> ib(n);
+        if (n) { if (subset) ck(wf_download_subset(backend, WF_F_ID, sync_idx.data(), (int64_t)n, ib.data()), "wf_download_subset(ID)"); else ck(wf_download(backend, WF_F_ID, ib.data()), "wf_download(ID)"); }
+        for (size_t k = 0; k < n; ++k) Particles[subset ? sync_idx[k] : k]->ID = ib[k];
+    }
+    if (!everything) {            // what the callback is about to see: sync_up uploads / refuses what it changed
+        const size_t n = subset ? sync_idx.size() : Particles.Size();
+        snap_x.resize(3 * n); snap_disp.resize(3 * n); snap_sigma.resize(9 * n); snap_T.resize(n); snap_dens.resize(n); snap_sigy.resize(n); snap_pls.resize(n); snap_pres.resize(n); snap_id.resize(n);
+        for (size_t k = 0; k < n; ++k) {
+            const Particle * P = Particles[subset ? sync_idx[k] : k];
+            for (int d = 0; d < 3; ++d) { snap_x[3 * k + d] = P->x(d); snap_disp[3 * k + d] = P->Displacement(d); }
+            for (int d = 0; d < 9; ++d) snap_sigma[9 * k + d] = P->Sigma.d[d];
+            snap_T[k] = P->T; snap_dens[k] = P->Density; snap_sigy[k] = P->Sigmay; snap_pls[k] = P->pl_strain; snap_pres[k] = P->Pressure; snap_id[k] = P->ID;
+        }
+        have_snap = true;
+    }
     if (everything) {
         get3(WF_F_CONTFORCE, &Particle::contforce, false); get3(WF_F_NORMAL, &Particle::normal, false);
         get9(WF_F_SHEARSTRESS, &Particle::ShearStress, false); get9(WF_F_STRAINRATE, &Particle::StrainRate, false); get9(WF_F_ROTATIONRATE, &Particle::RotationRate, false);
@@ -580,10 +613,47 @@ inline void Domain::sync_down(bool everything)
                                                3.0 * (S(0, 1) * S(0, 1) + S(1, 2) * S(1, 2) + S(2, 0) * S(2, 0))); }
     }
 }
+// bitwise comparison: a callback that re-assigns the value it was shown changes nothing
+static inline bool wf_same_bits(double a, double b) { return std::memcmp(&a, &b, sizeof(double)) == 0; }
+inline void Domain::put1_if_changed(wf_field f, double Particle::*mem, std::vector<double> & snap, bool subset)
+{
+    const size_t n = subset ? sync_idx.size() : Particles.Size(); bool changed = false;
+    for (size_t k = 0; k < n && !changed; ++k) changed = !wf_same_bits(Particles[subset ? sync_idx[k] : k]->*mem, snap[k]);
+    if (!changed) return;
+    buf1.resize(n);
+    for (size_t k = 0; k < n; ++k) buf1[k] = Particles[subset ? sync_idx[k] : k]->*mem;
+    if (subset) ck(wf_upload_subset(backend, f, sync_idx.data(), (int64_t)n, buf1.data()), "wf_upload_subset"); else ck(wf_upload(backend, f, buf1.data()), "wf_upload");
+}
+inline void Domain::refuse_if_changed(const char * what, const std::vector<double> & snap, int nc, bool subset, double (*get)(const Particle *, int))
+{
+    const size_t n = subset ? sync_idx.size() : Particles.Size();
+    for (size_t k = 0; k < n; ++k) for (int d = 0; d < nc; ++d)
+        if (!wf_same_bits(get(Particles[subset ? sync_idx[k] : k], d), snap[(size_t)nc * k + d]))
+            throw new Fatal("weldform_b200: the GeneralAfter / GeneralBefore callback assigned Particle::%s of particle %d; the device state takes v, a, x, T, Density, Sigmay and ID "
+                            "back from a callback, %s is computed there", what, (int)(subset ? sync_idx[k] : (int)k), what);
+}
 inline void Domain::sync_up()
 {
     if (sync_mode == SYNC_NONE) return;
     const bool subset = sync_mode == SYNC_TAGGED || sync_mode == SYNC_PUSH;
+    if (have_snap && sync_mode != SYNC_PUSH) {
+        // everything else the device accepts, when the callback touched it (a Dirichlet temperature, a moved or re-tagged particle ...)
+        const size_t n = subset ? sync_idx.size() : Particles.Size(); bool xch = false, idch = false;
+        for (size_t k = 0; k < n && !xch; ++k) { const Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 3; ++d) xch = xch || !wf_same_bits(P->x(d), snap_x[3 * k + d]); }
+        if (xch) put3(WF_F_X, &Particle::x, subset);
+        put1_if_changed(WF_F_T, &Particle::T, snap_T, subset);
+        put1_if_changed(WF_F_DENSITY, &Particle::Density, snap_dens, subset);
+        put1_if_changed(WF_F_SIGMAY, &Particle::Sigmay, snap_sigy, subset);
+        for (size_t k = 0; k < n && !idch; ++k) idch = Particles[subset ? sync_idx[k] : k]->ID != snap_id[k];
+        if (idch) {
+            std::vector<int32_t> ib(n); for (size_t k = 0; k < n; ++k) ib[k] = Particles[subset ? sync_idx[k] : k]->ID;
+            if (subset) ck(wf_upload_subset(backend, WF_F_ID, sync_idx.data(), (int64_t)n, ib.data()), "wf_upload_subset(ID)"); else ck(wf_upload(backend, WF_F_ID, ib.data()), "wf_upload(ID)");
+        }
+        refuse_if_changed("Sigma", snap_sigma, 9, subset, [](const Particle * P, int d) { return P->Sigma.d[d]; });
+        refuse_if_changed("pl_strain", snap_pls, 1, subset, [](const Particle * P, int) { return P->pl_strain; });
+        refuse_if_changed("Displacement", snap_disp, 3, subset, [](const Particle * P, int d) { return P->Displacement(d); });
+        refuse_if_changed("Pressure", snap_pres, 1, subset, [](const Particle * P, int) { return P->Pressure; });
+    }
     put3(WF_F_V, &Particle::v, subset); put3(WF_F_A, &Particle::a, subset);
 }
 inline void Domain::forward_mesh_motion()
@@ -601,6 +671,34 @@ inline void Domain::refresh_scalars()
     contact_force_sum = s.contact_force_sum; contact_reaction_sum = s.contact_reaction_sum; ext_forces_work = s.ext_forces_work; plastic_work = s.plastic_work;
     accum_cont_heat_cond = s.accum_cont_heat_cond; contact_friction_work = s.contact_friction_work; kin_energy_sum = s.kin_energy_sum; int_energy_sum = s.int_energy_sum;
     m_maxT = s.max_T; m_minT = s.min_T; steps = (size_t)s.steps;
+    if (!m_contact_force.empty() && m_contact_force.size() <= 6) {                 // Domain::m_contact_force (Contact_Wang.cpp:312)
+        double mf[18]; ck(wf_mesh_forces(backend, mf, (int)m_contact_force.size()), "wf_mesh_forces");
+        for (size_t m = 0; m < m_contact_force.size(); ++m) m_contact_force[m] = Vec3_t(mf[3 * m], mf[3 * m + 1], mf[3 * m + 2]);
+    }
+}
+// Source/SolverFraser.cpp:48,97-106: Prop.csv and History.csv (header: Time + the contact force of every rigid mesh), a row with every output
+// table (:466,:476-482; the reference also adds a row whenever 60 s of CPU time pass without a table)
+inline void Domain::open_history()
+{
+    prop_of.open("Prop.csv", std::ios::out);
+    history_of.open("History.csv", std::ios::out);
+    history_of << "Time, ";
+    for (size_t cf = 0; cf < m_contact_force.size(); ++cf) {
+        const int sid = contact_surf_id[cf];
+        if (cf > 0) history_of << ", ";
+        history_of << "cf" << sid << "x, " << " cf" << sid << "y, " << " cf" << sid << "z";
+    }
+    history_of << endl;
+}
+inline void Domain::write_history()
+{
+    prop_of << getTime() << ", " << m_scalar_prop << endl;
+    history_of << Time << ", ";
+    for (size_t cf = 0; cf < m_contact_force.size(); ++cf) {
+        if (cf > 0) history_of << ", ";
+        history_of << m_contact_force[cf](0) << ", " << m_contact_force[cf](1) << ", " << m_contact_force[cf](2);
+    }
+    history_of << endl;
 }
 inline void Domain::run_callback(PtDom cb)
 {
@@ -685,7 +783,8 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
     size_t idx_out = 1; double tout = Time; double max_pl = 0.0;
     auto t0 = std::chrono::steady_clock::now();
     refresh_scalars();
-    while (Time <= tf && idx_out <= maxidx) {
+    open_history();
+    while (Time <= tf && idx_out <= maxidx && !env_stop(idx_out)) {
         if (GeneralBefore) run_callback(GeneralBefore);                          // :238
         ck(wf_fraser_stage_a(backend), "wf_fraser_stage_a");                     // :137-312 rebuild policy, density, rates + stress, accel, contact
         if (GeneralAfter) { refresh_scalars(); run_callback(GeneralAfter); }     // :332
@@ -698,6 +797,7 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
             wf_scalars s; ck(wf_reduce(backend, &s), "wf_reduce"); max_pl = s.max_pl_strain;
             if (TheFileKey != NULL) { String fn; fn.Printf("%s_%04d", TheFileKey, (int)idx_out); sync_down(true); WriteCSV(fn.CStr()); }
             idx_out++; tout += dtOut;
+            write_history();
             wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             std::ostringstream o;
             o << "\n---------------------------------------\n Total time: " << wall_seconds << " s (GPU backend)\nstep number: " << steps << "\n";
@@ -723,6 +823,7 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
         for (size_t n = 0; n < nn; ++n) for (int k = 0; k < 3; ++k) (*tm->node[n])(k) = nodes[3 * n + k];
         for (size_t e = 0; e < ne; ++e) { for (int k = 0; k < 3; ++k) tm->element[e]->normal(k) = nrm[3 * e + k]; tm->element[e]->pplane = pp[e]; }
     }
+    history_of.close(); prop_of.close();
     std::cout << "\n--------------Solving is finished: " << steps << " steps, " << wall_seconds << " s, "
               << (double)solid_part_count * (double)steps / (wall_seconds > 0 ? wall_seconds : 1.0) << " particle-steps/s--------------" << std::endl;
     backend_end();

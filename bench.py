@@ -196,6 +196,44 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# e2e through the reference-style C++ API (weldform_b200/host/Domain.h), one process per mode
+# ---------------------------------------------------------------------------------------------------------------------
+def domain_api_e2e(n_particles, steps, warmup, device, log):
+    from weldform_b200 import build as wfbuild
+    exes = wfbuild.build_host_examples()
+    exe = [e for e in exes if e.endswith("bench_domain")][0]
+    threads = max(1, min(32, host_cores()))
+    out = {}
+    # bytes moved per step by the bridge (two callbacks per step), from the mirror's own rules (host/Domain.h): full = every particle,
+    # tagged = the rows with a BC ID; down: x v a Displacement (3) Sigma (9) T pl_strain Density Pressure Sigmay (1) ID (int); up: v a
+    for mode, (k, w) in (("push", (steps, warmup)), ("tagged", (max(3, steps // 4), 2)), ("full", (3, 1))):
+        env = dict(os.environ, WELDFORM_SYNC=mode, WELDFORM_DEVICE=str(device), OMP_NUM_THREADS=str(threads))
+        t0 = time.time()
+        try:
+            r = subprocess.run([exe, str(int(n_particles)), str(k), str(w), str(PERTURB_AMP), str(threads)], capture_output=True, text=True, timeout=1500, env=env)
+        except subprocess.TimeoutExpired:
+            out[mode] = {"error": "timeout"}
+            continue
+        line = [l for l in r.stdout.splitlines() if l.startswith("BENCH ")]
+        if r.returncode != 0 or not line:
+            out[mode] = {"error": (r.stdout + r.stderr)[-400:]}
+            continue
+        kv = dict(t.split("=") for t in line[0].split()[1:])
+        n, sec = int(kv["particles"]), float(kv["seconds"])
+        ntag = None
+        for l in r.stdout.splitlines():
+            if l.startswith("BRIDGE "):
+                ntag = int(l.split("tagged=")[1].split()[0])
+        rows = n if mode == "full" else (ntag or 0)
+        down = 0 if mode == "push" else 2 * rows * (4 * 24 + 72 + 5 * 8 + 4)
+        up = (2 * 2 * 2 * 24) if mode == "push" else 2 * rows * 48
+        out[mode] = {"value": n * k / sec, "ms_per_step": 1e3 * sec / k, "steps": k, "threads": threads, "h2d_bytes_per_step": int(up), "d2h_bytes_per_step": int(down + 3 * 200),
+                     "first_timed_step": int(kv["first_step"]), "max_pl_strain": float(kv["max_pl"]), "wall_s_incl_setup": time.time() - t0}
+        log("e2e Domain API, WELDFORM_SYNC=%s: %.2f ms/step (%d steps), %.3g particle-steps/s" % (mode, out[mode]["ms_per_step"], k, out[mode]["value"]))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -289,7 +327,14 @@ def run_ours(args):
         ms = float(t.item())
     value = n_sph * args.steps / (ms * 1e-3)
 
-    # ---- e2e: phase API + host GeneralAfter callback bridge with pinned host buffers
+    # ---- e2e (N = 1, compression workload): the reference-style C++ API. examples/bench_domain.cpp is a driver written like the reference's
+    # (SPH::Domain::AddCylinderLength, per-particle set-up loop, a GeneralAfter callback looping over Particles[i]->ID twice per step,
+    # SolveDiffUpdateFraser) on the host mirror; it is run as its own process on the same GPU in the three callback-bridge modes.
+    e2e_domain = None
+    if world == 1 and not contact and not args.python_e2e:
+        e2e_domain = domain_api_e2e(n_target, args.steps, max(args.warmup, 3), local, log)
+
+    # ---- e2e, Python form (N > 1 and the contact workload): phase API + host GeneralAfter callback bridge with pinned host buffers
     if contact:
         vtop, tau = np.asarray(case["mesh0_vel"][:3], float).copy(), float(case["mesh0_vel"][3])
     else:
@@ -386,6 +431,13 @@ def run_ours(args):
         path = "wf_fraser_stage_a/b1/b2/c + wf_mesh_set_motion + wf_download_subset (host callback of Contact_Compression_1010: tool velocity, Sigma and a of the first row of %d particles) + wf_reduce" % nt
     e2e = {"value": n_sph * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": ms_e2e / args.steps, "path": path}
+    if e2e_domain and e2e_domain.get("push"):
+        py = e2e
+        hd = e2e_domain["push"]
+        e2e = {"value": hd["value"], "unit": UNIT, "h2d_bytes_per_step": hd["h2d_bytes_per_step"], "d2h_bytes_per_step": hd["d2h_bytes_per_step"], "ms_per_step": hd["ms_per_step"],
+               "path": "C++ SPH::Domain::SolveDiffUpdateFraser of the host mirror (examples/bench_domain.cpp: GeneralAfter loops over Particles[i]->ID on %d host threads, twice per step), "
+                       "WELDFORM_SYNC=push (write-only bridge; uniform v / a of an ID group travel as one vector + a fill kernel), host clock between two wf_sync" % hd["threads"],
+               "modes": e2e_domain, "python_ctypes_push": {"value": py["value"], "ms_per_step": py["ms_per_step"], "h2d_bytes_per_step": py["h2d_bytes_per_step"]}}
 
     # ---- roofline of the dominant kernel, from the CUDA-event pairs recorded on the ctx stream inside the timed region
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -484,6 +536,7 @@ def main():
     ap.add_argument("--workload", choices=["compression", "contact"], default="compression",
                     help="compression: Compression_thermal (velocity-prescribed end rows, BASELINE configs[1] scaled); contact: the same cylinder between two rigid planes (penalty contact)")
     ap.add_argument("--tuning", type=int, default=0, help="wf_params::tuning bit mask (kernel A/B switches)")
+    ap.add_argument("--python-e2e", action="store_true", help="N = 1: time the e2e leg through the Python ctypes phase API only (skip the C++ Domain driver)")
     args = ap.parse_args()
     args.particles = int(args.particles)
     if args.warmup < 3:

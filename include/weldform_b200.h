@@ -173,6 +173,9 @@ int wf_upload_registered(wf_ctx *ctx, wf_field f, int handle, const void *host);
 /* same without waiting for the copy: `host` (pinned) must stay untouched until the next blocking call on the ctx (wf_sync, wf_reduce,
  * any download); the upload is ordered before every later phase call on the ctx stream */
 int wf_upload_registered_async(wf_ctx *ctx, wf_field f, int handle, const void *host);
+/* one value (3 doubles for X, V, A; 1 for T) for every particle of a registered subset: the GeneralAfter callbacks of the reference's drivers
+ * assign the same v and a to a whole ID group (examples/Compression_thermal.cpp:30-66); asynchronous on the ctx stream */
+int wf_fill_registered(wf_ctx *ctx, wf_field f, int handle, const double *value);
 int wf_mesh_download(wf_ctx *ctx, int mesh, double *nodes, double *normals, double *pplane);
 
 /* ---- hot path, one call per phase of the Fraser step (SolverFraser.cpp:133-505) -------------------------------- */

@@ -418,3 +418,24 @@ def test_baseline_scale_digest(harness, name):
         with open(rep, "a") as f:
             f.write(json.dumps({"what": "digest " + name, "tol": tol, "max": {k: v for k, v in report.items() if max(v) > 0}}) + "\n")
     assert not worst, "%s: beyond %.0e (norm) / %.0e (element-wise): %s" % (name, tol, ELEM_FACTOR * tol, worst)
+
+
+# ---- contracted arithmetic (wf_pair_fm.cu, wf_params::tuning bit 10): the pair terms use FMA, one rsqrt per pair and Newton-refined
+# reciprocals instead of the reference's operand-by-operand IEEE sequence. Not bit-identical by construction; held to BASELINE.json's bars.
+FM = 1024.0
+
+
+def test_contracted_arithmetic_one_step_12k(harness, oracle_port):
+    c = cases.perturbed(cases.compression(dx=0.015, nsteps=1), amp=60.0); c["tuning"] = FM
+    got, ref = harness.run_case(c), ot.run_port(c)
+    assert np.array_equal(got["pairs"], ref["pairs"]) and np.array_equal(got["Nb"], ref["Nb"]), "the neighbour search is exact in every mode"
+    assert not np.array_equal(got["a"], ref["a"]), "the contracted momentum kernel did not run (a is bit-identical to the exact path)"
+    _compare(got, ref, TOL_ONE_STEP, what="contracted arithmetic, 12k one step", case=c)
+
+
+@pytest.mark.parametrize("model", [cases.BILINEAR, cases.JOHNSON_COOK])
+def test_contracted_arithmetic_1000_steps(harness, oracle_port, model):
+    c = cases.perturbed(cases.compression(dx=0.03, nsteps=1000, model=model), amp=30.0); c["tuning"] = FM
+    got, ref = harness.run_case(c), ot.run_port(c)
+    assert ref["pl_strain"].max() > 5e-3
+    _compare(got, ref, TOL_LONG, keys=LONG_KEYS + ["Time", "plastic_work", "int_energy_sum", "max_disp"], what="contracted arithmetic, 1000 steps model %d" % model, case=c)

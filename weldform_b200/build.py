@@ -6,7 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libweldform_b200.so")
-SOURCES = ["wf_ctx.cu", "wf_neighbour.cu", "wf_pair.cu", "wf_step.cu", "wf_comm.cu"]
+SOURCES = ["wf_ctx.cu", "wf_neighbour.cu", "wf_pair.cu", "wf_pair_fm.cu", "wf_step.cu", "wf_comm.cu"]
+# wf_pair_fm.cu holds the contracted-arithmetic variants of the pair kernels: the one translation unit compiled with FMA contraction
+FMAD_SOURCES = {"wf_pair_fm.cu"}
 # -fmad=false: the pair terms must round exactly like the reference's x86-64 build (no FMA contraction); see DESIGN.md
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations", "-diag-suppress", "177,550"]
@@ -34,7 +36,8 @@ def build(force=False, verbose=False, extra_flags=()):
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        flags = [("-fmad=true" if (f == "-fmad=false" and src in FMAD_SOURCES) else f) for f in NVCC_FLAGS]
+        cmd = [_nvcc()] + flags + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False
@@ -68,7 +71,7 @@ def build_host_examples(force=False):
         exe = os.path.join(HOST_BIN, src[:-4])
         deps = [os.path.join(EXAMPLES, src), LIB] + [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR) if f.endswith((".h", ".cpp"))]
         if force or not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-            cmd = ["g++", "-std=c++14", "-O2", "-fpermissive", "-w", "-I" + HOST_DIR, "-I" + os.path.join(os.path.dirname(HERE), "include"),
+            cmd = ["g++", "-std=c++14", "-O2", "-fpermissive", "-w", "-fopenmp", "-I" + HOST_DIR, "-I" + os.path.join(os.path.dirname(HERE), "include"),
                    os.path.join(EXAMPLES, src), "-o", exe, "-L" + HERE, "-lweldform_b200", "-Wl,-rpath,$ORIGIN/../.."]
             subprocess.check_call(cmd)
         out.append(exe)

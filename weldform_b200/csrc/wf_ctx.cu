@@ -664,6 +664,37 @@ extern "C" int wf_upload_registered_async(wf_ctx *c, wf_field f, int handle, con
     return upload_impl(c, f, nullptr, c->subsets[handle].second, host, c->subsets[handle].first, true);
 }
 
+// One value for a whole registered subset: what a GeneralAfter callback of the usual kind does (every particle of an ID group gets the same
+// v and a, examples/Compression_thermal.cpp:30-66) without moving a vector per particle over PCIe. X, V, A, T only.
+__global__ void k_fill(double4 *Q0, double4 *Q1, double4 *Q2, double *F, int64_t cap, int f, int64_t n, const int *slot_of, const int *idx, int64_t nidx, double v0, double v1, double v2)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nidx) return;
+    const int64_t li = idx[t];
+    if (li < 0 || li >= n) return;
+    const int64_t s = slot_of[li];
+    switch (f) {
+    case WF_F_X: { double4 q = Q0[s]; q.x = v0; q.y = v1; q.z = v2; Q0[s] = q; } break;
+    case WF_F_V: { double4 q = Q1[s]; q.x = v0; q.y = v1; q.z = v2; Q1[s] = q; } break;
+    case WF_F_A: F[(int64_t)F_AX * cap + s] = v0; F[(int64_t)F_AY * cap + s] = v1; F[(int64_t)F_AZ * cap + s] = v2; break;
+    case WF_F_T: { double4 q = Q2[s]; q.z = v0; Q2[s] = q; } break;
+    default: break;
+    }
+}
+extern "C" int wf_fill_registered(wf_ctx *c, wf_field f, int handle, const double *value)
+{
+    if (!c || !value || handle < 0 || handle >= (int)c->subsets.size()) return WF_ERR_ARG;
+    if (f != WF_F_X && f != WF_F_V && f != WF_F_A && f != WF_F_T) return fail(c, WF_ERR_UNSUPPORTED, "wf_fill_registered: field %d (X, V, A, T only)", (int)f);
+    const int64_t n = c->subsets[handle].second;
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    const double v1 = f == WF_F_T ? 0.0 : value[1], v2 = f == WF_F_T ? 0.0 : value[2];
+    k_fill<<<grid_for(n, 256), 256, 0, c->stream>>>(c->Q0[c->cur], c->Q1[c->cur], c->Q2[c->cur], c->F[c->cur], c->cap, (int)f, c->n_loc, c->slot_of, c->subsets[handle].first, n, value[0], v1, v2);
+    WF_LAUNCH_CHECK(c);
+    if (f == WF_F_X || f == WF_F_V) c->dens_valid = false;
+    return 0;
+}
+
 extern "C" int wf_mesh_download(wf_ctx *c, int mesh, double *nodes, double *normals, double *pplane)
 {
     if (!c || mesh < 0 || mesh >= (int)c->meshes.size()) return fail(c, WF_ERR_ARG, "wf_mesh_download: bad mesh index %d", mesh);

@@ -34,28 +34,12 @@
 #include <cstring>
 #include <cub/cub.cuh>
 #include "wf_internal.cuh"
+#include "wf_pair_args.cuh"
+#include "wf_constitutive.cuh"
 
 using namespace wf;
 
 namespace {
-
-// FAST path (3-D cubic spline, uniform h, one property class): every per-thread constant is uniform over the launch.
-// They are evaluated once on the host with the same expressions (IEEE, no contraction) and travel as kernel parameters,
-// i.e. constant-bank operands: no registers, no per-thread divisions.
-struct FastConsts {
-    double h, C3, C4, inv_h, W0, inv_W0, Alpha, Beta, TI, TIn, TId, Cs, RefDensity, kT, kk, ksum, inv_ksum, cpT, th_exp, q_source;
-    double AlphaAvg, BetaAvg, AlphaCij, h2_001;    // lean momentum kernel: (Alpha+Alpha)/2, (Beta+Beta)/2, AlphaAvg*(0.5*(Cs+Cs)), 0.01*h*h
-    int PresEq, fast_h, fast_W0, fast_k;
-};
-struct PairArgs {
-    FastConsts fc;
-    int64_t n, cap, s0;           // slots [s0, n) of this launch (s0 = 0, n = n_loc unless the launch covers a sub-range)
-    int nsph, K, dim, kt, gt;
-    const uint32_t *nbr; const int *nb_cnt, *nb_hi; const int *orig; const int *cls_of; const int *is_free;   // is_free: NULL when every particle is free
-    double4 *Q0, *Q1, *Q2, *S0, *S1, *S2; double *F; const ClassProps *cls; const MatProps *mats;
-    double dt; int any_ti, thermal, pl_heating, contact, cont_heat_fric; double pl_work_heat_frac;
-    int gc;                       // Domain::gradKernelCorr: corrected gradients, pairs in stored (first, second) roles, lists in plain discovery order
-};
 
 #define OWN(f) a.F[(int64_t)(f) * a.cap + s]
 
@@ -311,17 +295,6 @@ __global__ void k_prologue(PairArgs a)
     }
 }
 
-// Material.cpp:6-25,59-64
-__device__ inline double yield_stress(const MatProps &m, double strain, double strain_rate, double temp)
-{
-    if (m.model == 1) { if (strain + m.eps0 > m.eps1) return m.p[1] * pow(strain + m.eps0, m.p[2]); else return m.p[0]; }
-    const double A = m.p[0], B = m.p[1], n = m.p[2], C = m.p[3], e0 = m.p[4], mm = m.p[5], Tm = m.p[6], Tt = m.p[7];
-    const double T_h = (temp - Tt) / (Tm - Tt);
-    double f = 1.0;
-    if (strain_rate > e0) f = (1.0 + C * log(strain_rate / e0));
-    return (A + B * pow(strain, n)) * f * (1.0 - pow(T_h, mm));
-}
-
 // ---- CalcRateTensors + RateTensorsReduction + CalcStressStrain -------------------------------------------------------
 template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_stress(PairArgs a)
 {
@@ -392,77 +365,7 @@ template <bool FAST, bool PF> __global__ void __launch_bounds__(128, 5) k_rate_s
         r02 = r02 + ((vab.x * xij.z - vab.z * xij.x) * f) * mjdj;
         r12 = r12 + ((vab.y * xij.z - vab.z * xij.y) * f) * mjdj;
     }
-    // ---------------- Particle::CalcStressStrain (Particle.cpp:960-1067) ----------------
-    const int ci = a.cls_of[s]; const ClassProps cp = a.cls[ci];
-    const double dt = a.dt;
-    double4 q2 = a.Q2[s];
-    const double rho = q2.y;
-    const double Pressure = eos(cp.PresEq, cp.Cs, cp.P0, rho, cp.RefDensity);
-    S6 srs; srs.xx = sxx; srs.yy = syy; srs.zz = szz; srs.xy = sxy; srs.yz = syz; srs.xz = sxz;
-    const M3 SR = m3sym(srs);
-    M3 RR = m3zero(); RR(0, 1) = r01; RR(0, 2) = r02; RR(1, 2) = r12; RR(1, 0) = -r01; RR(2, 0) = -r02; RR(2, 1) = -r12;
-    S6 shs; shs.xx = OWN(F_SH); shs.yy = OWN(F_SH + 1); shs.zz = OWN(F_SH + 2); shs.xy = OWN(F_SH + 3); shs.yz = OWN(F_SH + 4); shs.xz = OWN(F_SH + 5);
-    // StartAcceleration zeroes Sigma / ShearStress of fixed particles every step (Domain.cpp:1572-1578)
-    if (a.is_free && !a.is_free[s]) { shs.xx = shs.yy = shs.zz = shs.xy = shs.yz = shs.xz = 0.0; }
-    M3 SS = m3sym(shs);
-    const M3 RRT = mtrans(RR), SRT = mmul(SS, RRT), RS = mmul(RR, SS);
-    M3 I = m3zero(); I(0, 0) = 1.0; I(1, 1) = 1.0; I(2, 2) = 1.0;
-    const double tr = SR(0, 0) + SR(1, 1) + SR(2, 2);
-    const M3 dev = SR - (1.0 / 3.0 * tr) * I;
-    SS = dt * (((2.0 * cp.G) * dev + SRT) + RS) + SS;
-    const double effsr = sqrt(0.5 * ((SR(0, 0) - SR(1, 1)) * (SR(0, 0) - SR(1, 1)) + (SR(1, 1) - SR(2, 2)) * (SR(1, 1) - SR(2, 2)) +
-                                     (SR(2, 2) - SR(0, 0)) * (SR(2, 2) - SR(0, 0))) +
-                              3.0 * (SR(0, 1) * SR(0, 1) + SR(1, 2) * SR(1, 2) + SR(2, 0) * SR(2, 0)));
-    double dep = 0., Sigmay = OWN(F_SIGY);
-    if (cp.Fail == 1) {
-        const double J2 = 0.5 * (SS(0, 0) * SS(0, 0) + 2.0 * SS(0, 1) * SS(1, 0) + 2.0 * SS(0, 2) * SS(2, 0) + SS(1, 1) * SS(1, 1) +
-                                 2.0 * SS(1, 2) * SS(2, 1) + SS(2, 2) * SS(2, 2));
-        const double sig_trial = sqrt(3.0 * J2);
-        const double rs = Sigmay / sig_trial;
-        SS = ((1.0 < rs) ? 1.0 : rs) * SS;            // std::min(Sigmay/sig_trial, 1.0), NaN-propagating like the reference
-        double pl = OWN(F_PLS);
-        if (cp.Material_model == 1) Sigmay = yield_stress(a.mats[cp.mat_id], pl, 0.0, 0.0);
-        else if (cp.Material_model == 2) Sigmay = yield_stress(a.mats[cp.mat_id], pl, effsr, q2.z);
-        if (sig_trial > Sigmay) {
-            double Ep = cp.Ep;
-            if (Ep < 0) Ep = 1. * a.mats[cp.mat_id].E;
-            dep = (sig_trial - Sigmay) / (3. * cp.G + Ep);
-            pl += dep;
-            OWN(F_PLS) = pl; OWN(F_DPLS) = dep;
-            if (cp.Material_model == 0) Sigmay += dep * Ep;
-        }
-        OWN(F_SIGY) = Sigmay;
-    }
-    const M3 Sg = (-Pressure) * I + SS;
-    OWN(F_SH) = SS(0, 0); OWN(F_SH + 1) = SS(1, 1); OWN(F_SH + 2) = SS(2, 2); OWN(F_SH + 3) = SS(0, 1); OWN(F_SH + 4) = SS(1, 2); OWN(F_SH + 5) = SS(0, 2);
-    OWN(F_SG) = Sg(0, 0); OWN(F_SG + 1) = Sg(1, 1); OWN(F_SG + 2) = Sg(2, 2); OWN(F_SG + 3) = Sg(0, 1); OWN(F_SG + 4) = Sg(1, 2); OWN(F_SG + 5) = Sg(0, 2);
-    OWN(F_PRES) = Pressure;
-    // gathered copies for the momentum pass: 1.0/(rho*rho)*Sigma (InteractionAlt.cpp:139) or Sigma (GradientType 1, 2);
-    // and P/(rho*rho) for the kinetic-energy pass (Domain.cpp:1784)
-    const double inv_d2 = 1.0 / (rho * rho);
-    if (a.gt == 0) {
-        a.S0[s] = make_double4(Sg(0, 0) * inv_d2, Sg(1, 1) * inv_d2, Sg(2, 2) * inv_d2, Sg(0, 1) * inv_d2);
-        ((double2 *)&a.S1[s])[0] = make_double2(Sg(1, 2) * inv_d2, Sg(0, 2) * inv_d2);
-    } else {
-        a.S0[s] = make_double4(Sg(0, 0), Sg(1, 1), Sg(2, 2), Sg(0, 1));
-        ((double2 *)&a.S1[s])[0] = make_double2(Sg(1, 2), Sg(0, 2));
-    }
-    ((double *)&a.Q2[s])[3] = Pressure / (rho * rho);
-    if (dep > 0.0) {
-        const double f = dep / Sigmay;
-        const double ixx = f * (Sg(0, 0) - 0.5 * (Sg(1, 1) + Sg(2, 2)));
-        const double iyy = f * (Sg(1, 1) - 0.5 * (Sg(0, 0) + Sg(2, 2)));
-        const double izz = f * (Sg(2, 2) - 0.5 * (Sg(0, 0) + Sg(1, 1)));
-        const double ixy = 1.5 * f * (Sg(0, 1)), ixz = 1.5 * f * (Sg(0, 2)), iyz = 1.5 * f * (Sg(1, 2));
-        OWN(F_SI) = ixx; OWN(F_SI + 1) = iyy; OWN(F_SI + 2) = izz; OWN(F_SI + 3) = ixy; OWN(F_SI + 4) = iyz; OWN(F_SI + 5) = ixz;
-        OWN(F_SP) = OWN(F_SP) + ixx; OWN(F_SP + 1) = OWN(F_SP + 1) + iyy; OWN(F_SP + 2) = OWN(F_SP + 2) + izz;
-        OWN(F_SP + 3) = OWN(F_SP + 3) + ixy; OWN(F_SP + 4) = OWN(F_SP + 4) + iyz; OWN(F_SP + 5) = OWN(F_SP + 5) + ixz;
-    }
-    OWN(F_ST) = dt * sxx + OWN(F_ST); OWN(F_ST + 1) = dt * syy + OWN(F_ST + 1); OWN(F_ST + 2) = dt * szz + OWN(F_ST + 2);
-    OWN(F_ST + 3) = dt * sxy + OWN(F_ST + 3); OWN(F_ST + 4) = dt * syz + OWN(F_ST + 4); OWN(F_ST + 5) = dt * sxz + OWN(F_ST + 5);
-    OWN(F_SR) = sxx; OWN(F_SR + 1) = syy; OWN(F_SR + 2) = szz; OWN(F_SR + 3) = sxy; OWN(F_SR + 4) = syz; OWN(F_SR + 5) = sxz;
-    OWN(F_RR) = r01; OWN(F_RR + 1) = r02; OWN(F_RR + 2) = r12;
-    OWN(F_EFFSR) = effsr;
+    stress_update(a, s, sxx, syy, szz, sxy, syz, sxz, r01, r02, r12);
 }
 
 // ---- CalcAccel + AccelReduction ------------------------------------------------------------------------------------------
@@ -832,6 +735,8 @@ inline bool lean_ok(const wf_ctx *c, const PairArgs &a)
     const FastConsts &f = a.fc;
     return a.dim == 3 && f.PresEq == 0 && f.fast_h && (!c->any_ti || (f.TI > 0.0 && f.TIn == 4.0 && f.fast_W0)) && !c->any_fixed;
 }
+// contracted-arithmetic variants (wf_pair_fm.cu): wf_params::tuning bit 10, on the lean FAST path only
+inline bool use_fm(const wf_ctx *c, const PairArgs &a) { return (c->prm.tuning & 1024) && fast_path(c) && lean_ok(c, a) && a.gt == 0; }
 inline bool use_pf(const wf_ctx *c) { return (c->prm.tuning & 1) == 0; }     // bit 0 of wf_params::tuning switches the software pipeline OFF
 
 } // namespace
@@ -897,7 +802,8 @@ int pair_density(wf_ctx *c, bool with_tir)
     PairArgs a = make_args(c); const int g = grid_for(c->n_loc, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_DENSITY);
     if (!c->dens_valid) {
-        if (fast_path(c)) WF_LAUNCH_PF(k_post, true, false, false, true); else WF_LAUNCH_PF(k_post, false, false, false, true);
+        if (use_fm(c, a) && launch_post_fm(c, a, g, false, false, true) == 0) {}
+        else if (fast_path(c)) WF_LAUNCH_PF(k_post, true, false, false, true); else WF_LAUNCH_PF(k_post, false, false, false, true);
         WF_LAUNCH_CHECK(c); c->launches++;
         if (c->any_ti && with_tir) { k_tir<true><<<g, 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
     }
@@ -912,6 +818,7 @@ int pair_rate_stress(wf_ctx *c, int64_t lo, int64_t hi)
     if (hi <= lo) return 0;
     PairArgs a = make_args(c); a.s0 = lo; a.n = hi; const int g = grid_for(hi - lo, 128); const bool pf = use_pf(c);
     ProfScope ps(c, PK_RATE_STRESS);
+    if (use_fm(c, a)) { WF_CHECK(launch_rate_fm(c, a, g)); WF_LAUNCH_CHECK(c); c->launches++; return 0; }
     if (fast_path(c)) WF_LAUNCH_PF(k_rate_stress, true); else WF_LAUNCH_PF(k_rate_stress, false);
     WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
@@ -928,6 +835,7 @@ int pair_accel(wf_ctx *c, int64_t lo, int64_t hi)
     switch (a.gt) {
     case 0: if (fast && lean_ok(c, a) && !(c->prm.tuning & 8)) {        // bit 3 of wf_params::tuning: the general FAST kernel instead of the lean one
                 const bool w256 = (c->prm.tuning & 32) == 0;           // bit 5: 2 x LDG.128 per gathered record instead of one LDG.256
+                if (use_fm(c, a)) { WF_CHECK(launch_accel_fm(c, a, g, c->any_ti)); WF_LAUNCH_CHECK(c); c->launches++; return 0; }   // bit 10: contracted arithmetic (wf_pair_fm.cu)
                 if (c->any_ti) {
                     if (c->prm.tuning & 16) { if (w256) k_accel_lean<true, 4, true><<<g, 128, 0, c->stream>>>(a); else k_accel_lean<true, 4, false><<<g, 128, 0, c->stream>>>(a); }
                     else { if (w256) k_accel_lean<true, 3, true><<<g, 128, 0, c->stream>>>(a); else k_accel_lean<true, 3, false><<<g, 128, 0, c->stream>>>(a); }
@@ -962,6 +870,11 @@ int pair_post_range(wf_ctx *c, bool skip_dens, int64_t lo, int64_t hi)
     ProfScope ps(c, PK_THERMAL);
     const bool th = c->prm.thermal_solver != 0;
     const bool fast = fast_path(c);
+    if (use_fm(c, a) && launch_post_fm(c, a, g, th, true, !skip_dens) == 0) {
+        WF_LAUNCH_CHECK(c); c->launches++;
+        if (!skip_dens && c->any_ti) { k_tir<true><<<g, 128, 0, c->stream>>>(a); WF_LAUNCH_CHECK(c); c->launches++; }
+        return 0;
+    }
     if (skip_dens) {
         // the coming step rebuilds its neighbour lists first (known from the cadence): a density rate and TIR summed over the
         // current lists would be discarded, so only the conduction and energy sums of this step are evaluated

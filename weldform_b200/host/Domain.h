@@ -49,6 +49,15 @@ using std::cout;
 using std::endl;
 using std::string;
 
+// the AoS <-> SoA loops of the callback bridge run on Domain::Nproc host threads when the driver is compiled with OpenMP (the reference's
+// drivers are: their callbacks carry `#pragma omp parallel for ... num_threads(domi.Nproc)`); plain loops otherwise
+#ifdef _OPENMP
+#define WF_HOST_PRAGMA(x) _Pragma(#x)
+#define WF_HOST_PARALLEL_FOR WF_HOST_PRAGMA(omp parallel for schedule(static) num_threads((int)(Nproc > 0 ? Nproc : 1)))
+#else
+#define WF_HOST_PARALLEL_FOR
+#endif
+
 enum domain_bid_type { PlaneStress = 0, PlaneStrain = 1, AxiSymmetric = 2, AxiSymm_3D = 2 };
 enum Kernels_Type { Qubic_Spline = 0, Quintic = 1, Quintic_Spline = 2, Hyperbolic_Spline = 3 };
 enum Viscosity_Eq_Type { Morris = 0, Shao = 1, Incompressible_Full = 2, Takeda = 3 };
@@ -157,11 +166,17 @@ public:
     wf_ctx * backend = nullptr;                // live between the start and the end of a Solve call
     int device = 0;                            // CUDA device (WELDFORM_DEVICE)
     double wall_seconds = 0.0;                 // wall time of the last Solve's step loop
+    // benchmark hook of the Fraser loop (bench.py's e2e leg, examples/bench_domain.cpp): once the body yields (the rebuild cadence is then the
+    // reference's every-ts_nb_inc-steps one) and at least bench_spin_min steps have run, bench_warmup untimed steps, then bench_steps steps
+    // timed on the host clock between two wf_sync calls -> bench_seconds; the loop ends there. bench_steps = 0: no effect.
+    size_t bench_steps = 0, bench_warmup = 0, bench_spin_min = 20; double bench_seconds = 0.0; size_t bench_first_step = 0; bool isyielding = false;
 
 private:
     double Time = 0.0;
     enum SyncMode { SYNC_FULL = 0, SYNC_TAGGED = 1, SYNC_NONE = 2, SYNC_PUSH = 3 } sync_mode = SYNC_FULL;
     std::vector<int32_t> sync_idx;             // creation indices mirrored around callbacks (empty + SYNC_FULL: everything)
+    struct PushGroup { int id; std::vector<int32_t> idx; int handle; std::vector<double> v, a; };   // SYNC_PUSH: the tagged rows by ID, registered on the device
+    std::vector<PushGroup> push_groups;
     std::vector<double> buf3, buf9, buf1;
     // values the bridge handed to the last callback (FULL / TAGGED): what sync_up compares against
     std::vector<double> snap_x, snap_T, snap_dens, snap_sigy, snap_sigma, snap_pls, snap_disp, snap_pres; std::vector<int32_t> snap_id;
@@ -422,6 +437,17 @@ inline void Domain::choose_sync()
         int bulk = 0; size_t best = 0;
         for (auto & kv : hist) if (kv.second > best) { best = kv.second; bulk = kv.first; }
         for (int i = 0; i < solid_part_count; ++i) if (Particles[i]->ID != bulk) sync_idx.push_back(i);
+        push_groups.clear();
+        if (sync_mode == SYNC_PUSH) {
+            std::map<int, size_t> slot;
+            for (size_t k = 0; k < sync_idx.size(); ++k) {
+                const int id = Particles[sync_idx[k]]->ID;
+                if (!slot.count(id)) { slot[id] = push_groups.size(); PushGroup g; g.id = id; g.handle = -1; push_groups.push_back(g); }
+                push_groups[slot[id]].idx.push_back(sync_idx[k]);
+            }
+            for (auto & g : push_groups) ck(wf_subset_register(backend, g.idx.data(), (int64_t)g.idx.size(), &g.handle), "wf_subset_register");
+        }
+        std::cout << "BRIDGE mode=" << (sync_mode == SYNC_PUSH ? "push" : "tagged") << " tagged=" << sync_idx.size() << " of " << solid_part_count << " particles" << std::endl;
     }
 }
 
@@ -550,6 +576,7 @@ inline void Domain::get3(wf_field f, Vec3_t Particle::*mem, bool subset)
     const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
     buf3.resize(3 * n);
     if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf3.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf3.data()), "wf_download");
+    WF_HOST_PARALLEL_FOR
     for (size_t k = 0; k < n; ++k) { Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 3; ++d) (P->*mem)(d) = buf3[3 * k + d]; }
 }
 inline void Domain::get9(wf_field f, Mat3_t Particle::*mem, bool subset)
@@ -557,6 +584,7 @@ inline void Domain::get9(wf_field f, Mat3_t Particle::*mem, bool subset)
     const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
     buf9.resize(9 * n);
     if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf9.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf9.data()), "wf_download");
+    WF_HOST_PARALLEL_FOR
     for (size_t k = 0; k < n; ++k) { Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 9; ++d) (P->*mem).d[d] = buf9[9 * k + d]; }
 }
 inline void Domain::get1(wf_field f, double Particle::*mem, bool subset)
@@ -564,12 +592,14 @@ inline void Domain::get1(wf_field f, double Particle::*mem, bool subset)
     const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
     buf1.resize(n);
     if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf1.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf1.data()), "wf_download");
+    WF_HOST_PARALLEL_FOR
     for (size_t k = 0; k < n; ++k) Particles[subset ? sync_idx[k] : k]->*mem = buf1[k];
 }
 inline void Domain::put3(wf_field f, Vec3_t Particle::*mem, bool subset)
 {
     const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
     buf3.resize(3 * n);
+    WF_HOST_PARALLEL_FOR
     for (size_t k = 0; k < n; ++k) { const Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 3; ++d) buf3[3 * k + d] = (P->*mem)(d); }
     if (subset) ck(wf_upload_subset(backend, f, sync_idx.data(), (int64_t)n, buf3.data()), "wf_upload_subset"); else ck(wf_upload(backend, f, buf3.data()), "wf_upload");
 }
@@ -590,6 +620,7 @@ inline void Domain::sync_down(bool everything)
     if (!everything) {            // what the callback is about to see: sync_up uploads / refuses what it changed
         const size_t n = subset ? sync_idx.size() : Particles.Size();
         snap_x.resize(3 * n); snap_disp.resize(3 * n); snap_sigma.resize(9 * n); snap_T.resize(n); snap_dens.resize(n); snap_sigy.resize(n); snap_pls.resize(n); snap_pres.resize(n); snap_id.resize(n);
+        WF_HOST_PARALLEL_FOR
         for (size_t k = 0; k < n; ++k) {
             const Particle * P = Particles[subset ? sync_idx[k] : k];
             for (int d = 0; d < 3; ++d) { snap_x[3 * k + d] = P->x(d); snap_disp[3 * k + d] = P->Displacement(d); }
@@ -654,6 +685,33 @@ inline void Domain::sync_up()
         refuse_if_changed("Displacement", snap_disp, 3, subset, [](const Particle * P, int d) { return P->Displacement(d); });
         refuse_if_changed("Pressure", snap_pres, 1, subset, [](const Particle * P, int) { return P->Pressure; });
     }
+    if (sync_mode == SYNC_PUSH) {
+        // write-only bridge: the rows of an ID group usually all get the SAME v and a (examples/Compression_thermal.cpp:30-66): then one
+        // 3-vector and a fill kernel per group and field replace a vector per particle over PCIe (wf_fill_registered); otherwise the
+        // group's values are uploaded through its registered index list
+        for (auto & g : push_groups) {
+            const size_t n = g.idx.size(); if (!n) continue;
+            const Particle * P0 = Particles[g.idx[0]];
+            const Vec3_t v0 = P0->v, a0 = P0->a;
+            int differ = 0;
+            #ifdef _OPENMP
+            #pragma omp parallel for schedule(static) num_threads((int)(Nproc > 0 ? Nproc : 1)) reduction(|:differ)
+            #endif
+            for (size_t k = 0; k < n; ++k) {
+                const Particle * P = Particles[g.idx[k]];
+                for (int d = 0; d < 3; ++d) if (!wf_same_bits(P->v(d), v0(d)) || !wf_same_bits(P->a(d), a0(d))) differ |= 1;
+            }
+            if (!differ) {
+                ck(wf_fill_registered(backend, WF_F_V, g.handle, v0.d), "wf_fill_registered"); ck(wf_fill_registered(backend, WF_F_A, g.handle, a0.d), "wf_fill_registered");
+            } else {
+                g.v.resize(3 * n); g.a.resize(3 * n);
+                WF_HOST_PARALLEL_FOR
+                for (size_t k = 0; k < n; ++k) { const Particle * P = Particles[g.idx[k]]; for (int d = 0; d < 3; ++d) { g.v[3 * k + d] = P->v(d); g.a[3 * k + d] = P->a(d); } }
+                ck(wf_upload_registered(backend, WF_F_V, g.handle, g.v.data()), "wf_upload_registered"); ck(wf_upload_registered(backend, WF_F_A, g.handle, g.a.data()), "wf_upload_registered");
+            }
+        }
+        return;
+    }
     put3(WF_F_V, &Particle::v, subset); put3(WF_F_A, &Particle::a, subset);
 }
 inline void Domain::forward_mesh_motion()
@@ -670,7 +728,7 @@ inline void Domain::refresh_scalars()
     Time = s.time; for (int k = 0; k < 3; ++k) max_disp(k) = s.max_disp[k];
     contact_force_sum = s.contact_force_sum; contact_reaction_sum = s.contact_reaction_sum; ext_forces_work = s.ext_forces_work; plastic_work = s.plastic_work;
     accum_cont_heat_cond = s.accum_cont_heat_cond; contact_friction_work = s.contact_friction_work; kin_energy_sum = s.kin_energy_sum; int_energy_sum = s.int_energy_sum;
-    m_maxT = s.max_T; m_minT = s.min_T; steps = (size_t)s.steps;
+    m_maxT = s.max_T; m_minT = s.min_T; steps = (size_t)s.steps; isyielding = s.is_yielding != 0;
     if (!m_contact_force.empty() && m_contact_force.size() <= 6) {                 // Domain::m_contact_force (Contact_Wang.cpp:312)
         double mf[18]; ck(wf_mesh_forces(backend, mf, (int)m_contact_force.size()), "wf_mesh_forces");
         for (size_t m = 0; m < m_contact_force.size(); ++m) m_contact_force[m] = Vec3_t(mf[3 * m], mf[3 * m + 1], mf[3 * m + 2]);
@@ -784,7 +842,13 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
     auto t0 = std::chrono::steady_clock::now();
     refresh_scalars();
     open_history();
+    int bench_state = 0; size_t bench_mark = 0; std::chrono::steady_clock::time_point bench_t0;
     while (Time <= tf && idx_out <= maxidx && !env_stop(idx_out)) {
+        if (bench_steps > 0) {
+            if (bench_state == 0 && isyielding && steps >= bench_spin_min) { bench_state = 1; bench_mark = steps + bench_warmup; }
+            if (bench_state == 1 && steps == bench_mark) { ck(wf_sync(backend), "wf_sync"); bench_t0 = std::chrono::steady_clock::now(); bench_state = 2; bench_first_step = steps; bench_mark = steps + bench_steps; }
+            else if (bench_state == 2 && steps == bench_mark) { ck(wf_sync(backend), "wf_sync"); bench_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - bench_t0).count(); break; }
+        }
         if (GeneralBefore) run_callback(GeneralBefore);                          // :238
         ck(wf_fraser_stage_a(backend), "wf_fraser_stage_a");                     // :137-312 rebuild policy, density, rates + stress, accel, contact
         if (GeneralAfter) { refresh_scalars(); run_callback(GeneralAfter); }     // :332

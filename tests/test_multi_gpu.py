@@ -210,3 +210,26 @@ def test_multi_gpu_rebalance_moves_a_layer_and_keeps_every_bit(product_lib, orac
     assert np.array_equal(multi["pairs"], single["pairs"])
     bad = {k: ot.max_rel(multi[k], single[k]) for k in cases.FIELDS_F64 + ["ID", "Nb"] if not np.array_equal(multi[k], single[k])}
     assert not bad, "rebalanced multi-GPU run differs from single GPU per particle: %s" % bad
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("sync,amp,nsteps", [("full", 60.0, 40), ("tagged", 400.0, 100), ("push", 400.0, 100)])
+def test_host_mirror_on_two_gpus_bit_identical_to_one(product_lib, sync, amp, nsteps):
+    """The C++ host mirror of SPH::Domain on WELDFORM_GPUS=2 (one process, one host thread and one wf_ctx per GPU, host/Backend.h): the driver's
+    GeneralAfter callback works on the GLOBAL Particles array while the particles live on two slabs and migrate between them at the rebuilds
+    (amp = 400 m/s); every field of the final state is bit-identical to the same driver on one GPU."""
+    from weldform_b200 import build
+    exe = [e for e in build.build_host_examples() if e.endswith("compression_host_api")][0]
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for gpus in (1, 2):
+            out = os.path.join(d, "o%d.bin" % gpus)
+            r = subprocess.run([exe, "0.02", str(nsteps), str(amp), out, "0"], capture_output=True, text=True, timeout=900,
+                               env=dict(os.environ, WELDFORM_SYNC=sync, WELDFORM_GPUS=str(gpus)))
+            assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+            raw = np.fromfile(out, dtype=np.uint8)
+            outs.append(raw)
+    assert outs[0].size == outs[1].size and outs[0].size > 8
+    a, b = outs[0][8:].view(np.float64), outs[1][8:].view(np.float64)
+    assert np.array_equal(a, b), "2-GPU host-mirror run differs from the 1-GPU run: max |diff| %.3e in %d of %d values" % (np.abs(a - b).max(), int((a != b).sum()), a.size)

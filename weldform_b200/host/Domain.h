@@ -41,6 +41,7 @@
 #include <vector>
 
 #include "weldform_b200.h"
+#include "Backend.h"
 #include "matvec.h"
 #include "Particle.h"
 #include "Mesh.h"
@@ -163,8 +164,10 @@ public:
     size_t steps = 0;
 
     // ---- weldform_b200 specifics
-    wf_ctx * backend = nullptr;                // live between the start and the end of a Solve call
-    int device = 0;                            // CUDA device (WELDFORM_DEVICE)
+    wf_ctx * backend = nullptr;                // rank 0's context; live between the start and the end of a Solve call
+    wf_host::Backend bk;                       // all GPUs of the run (host/Backend.h)
+    int device = 0;                            // first CUDA device (WELDFORM_DEVICE)
+    int gpus = 1;                              // GPUs of one node this Domain runs on (WELDFORM_GPUS): slab decomposition, one host thread per GPU
     double wall_seconds = 0.0;                 // wall time of the last Solve's step loop
     // benchmark hook of the Fraser loop (bench.py's e2e leg, examples/bench_domain.cpp): once the body yields (the rebuild cadence is then the
     // reference's every-ts_nb_inc-steps one) and at least bench_spin_min steps have run, bench_warmup untimed steps, then bench_steps steps
@@ -175,7 +178,8 @@ private:
     double Time = 0.0;
     enum SyncMode { SYNC_FULL = 0, SYNC_TAGGED = 1, SYNC_NONE = 2, SYNC_PUSH = 3 } sync_mode = SYNC_FULL;
     std::vector<int32_t> sync_idx;             // creation indices mirrored around callbacks (empty + SYNC_FULL: everything)
-    struct PushGroup { int id; std::vector<int32_t> idx; int handle; std::vector<double> v, a; };   // SYNC_PUSH: the tagged rows by ID, registered on the device
+    struct PushGroup { int id; std::vector<int32_t> idx; int handle; std::vector<double> v, a; };   // SYNC_PUSH: the tagged rows by ID, registered on the device(s)
+    int sync_group = -1;                       // SYNC_TAGGED: sync_idx as a registered group
     std::vector<PushGroup> push_groups;
     std::vector<double> buf3, buf9, buf1;
     // values the bridge handed to the last callback (FULL / TAGGED): what sync_up compares against
@@ -213,10 +217,11 @@ inline Domain::Domain()
 {
     DomMax = Vec3_t(-100000000000.0); DomMin = Vec3_t(100000000000.0);       // Source/Domain.cpp:118-119
     const char * dv = std::getenv("WELDFORM_DEVICE"); if (dv) device = std::atoi(dv);
+    const char * ng = std::getenv("WELDFORM_GPUS"); if (ng && std::atoi(ng) > 0) gpus = std::atoi(ng);
 }
 inline Domain::~Domain()
 {
-    if (backend) { wf_destroy(backend); backend = nullptr; }
+    bk.destroy(); backend = nullptr;
     for (size_t i = 0; i < Particles.Size(); ++i) delete Particles[i];       // Domain owns its particles (Source/Domain.cpp:177-181)
 }
 
@@ -445,16 +450,17 @@ inline void Domain::choose_sync()
                 if (!slot.count(id)) { slot[id] = push_groups.size(); PushGroup g; g.id = id; g.handle = -1; push_groups.push_back(g); }
                 push_groups[slot[id]].idx.push_back(sync_idx[k]);
             }
-            for (auto & g : push_groups) ck(wf_subset_register(backend, g.idx.data(), (int64_t)g.idx.size(), &g.handle), "wf_subset_register");
+            for (auto & g : push_groups) g.handle = bk.add_group(g.idx);
         }
+        else sync_group = bk.add_group(sync_idx);
         std::cout << "BRIDGE mode=" << (sync_mode == SYNC_PUSH ? "push" : "tagged") << " tagged=" << sync_idx.size() << " of " << solid_part_count << " particles" << std::endl;
     }
 }
 
 inline void Domain::backend_begin(double dt)
 {
-    if (backend) { wf_destroy(backend); backend = nullptr; }
-    if (wf_create(device, &backend) != 0) throw new Fatal("weldform_b200: %s", wf_last_error(nullptr));
+    bk.create(device, gpus); backend = bk.c0();
+    if (gpus > 1 && GhostPairs.Size() > 0) throw new Fatal("weldform_b200: ghost (symmetry) rows run on one GPU only (WELDFORM_GPUS = %d)", gpus);
     const size_t ntot = Particles.Size();
     const size_t nsph = !first_fem_particle_idx.empty() ? (size_t)first_fem_particle_idx[0] : ntot;
     if (nsph == 0) throw new Fatal("Domain: no particles");
@@ -471,7 +477,7 @@ inline void Domain::backend_begin(double dt)
     if (contact && contact_alg != Wang) throw new Fatal("Domain::contact_alg = %d: only CalcContactForcesWang (the default, Source/Domain.cpp:169) is implemented in weldform_b200", contact_alg);
     if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
     p.friction_function = (friction_function == Linear) ? 1 : 0; p.friction_m = friction_m; p.friction_b = friction_b;
-    ck(wf_set_params(backend, &p), "wf_set_params");
+    bk.each("wf_set_params", [&](int r) { return wf_set_params(bk.ctx[r], &p); });
     // ---- materials: distinct Material_ objects
     std::map<Material_ *, int> mat_ids; std::vector<wf_material> mats;
     for (size_t i = 0; i < nsph; ++i) {
@@ -483,7 +489,7 @@ inline void Domain::backend_begin(double dt)
             mat_ids[m] = (int)mats.size(); mats.push_back(wm);
         }
     }
-    ck(wf_set_materials(backend, mats.empty() ? nullptr : mats.data(), (int)mats.size()), "wf_set_materials");
+    bk.each("wf_set_materials", [&](int r) { return wf_set_materials(bk.ctx[r], mats.empty() ? nullptr : mats.data(), (int)mats.size()); });
     // ---- rigid meshes
     for (auto & mr : mesh_recs) {
         TriMesh * tm = mr.mesh; const int nn = (int)tm->node.Size(), ne = (int)tm->element.Size();
@@ -493,7 +499,7 @@ inline void Domain::backend_begin(double dt)
                                        nfar[e] = tm->element[e]->nfar; radius[e] = tm->element[e]->radius; }
         wf_mesh wm; wm.n_nodes = nn; wm.n_elems = ne; wm.nodes = nodes.data(); wm.elems = elems.data(); wm.normals = normals.data(); wm.nfar = nfar.data();
         wm.radius = radius.data(); wm.hfac = (double)mr.hfac; wm.id = mr.id;
-        ck(wf_add_mesh(backend, &wm), "wf_add_mesh");
+        bk.each("wf_add_mesh", [&](int r) { return wf_add_mesh(bk.ctx[r], &wm); });      // every rank holds every rigid mesh
     }
     // ---- particles: AoS mirrors -> SoA upload
     std::vector<double> x(3 * nsph), v(3 * nsph), mass(nsph), dens(nsph), hh(nsph), refd(nsph), G(nsph), Cs(nsph), P0(nsph), al(nsph), be(nsph), TI(nsph), TIn(nsph),
@@ -515,7 +521,11 @@ inline void Domain::backend_begin(double dt)
     wp.Ep = Ep.data(); wp.k_T = kT.data(); wp.cp_T = cp.data(); wp.h_conv = hc.data(); wp.T_inf = Tinf.data(); wp.th_exp = thx.data(); wp.q_source = qs.data();
     wp.pres_eq = preseq.data(); wp.fail = fail.data(); wp.material = matl.data(); wp.material_model = mmodel.data(); wp.mat_id = matid.data(); wp.thermal_bc = thbc.data();
     wp.sigmay = sy.data(); wp.T = T.data();
-    ck(wf_set_particles(backend, &wp), "wf_set_particles");
+    {
+        std::vector<double> px(3 * ntot), ph(ntot);          // every particle shapes the cell grid the slabs are cut from, rigid-mesh element particles included
+        for (size_t i = 0; i < ntot; ++i) { for (int k = 0; k < 3; ++k) px[3 * i + k] = Particles[i]->x(k); ph[i] = Particles[i]->h; }
+        bk.set_particles(wp, px.data(), ph.data(), (int64_t)ntot, (int)KernelType, p.dom_min, p.dom_max);
+    }
     if (GhostPairs.Size() > 0) {                                          // Domain::MoveGhost runs on the device (Mirror_XYZ ghosts)
         std::vector<int32_t> gp(2 * GhostPairs.Size()), ax(GhostPairs.Size());
         for (size_t g = 0; g < GhostPairs.Size(); ++g) { gp[2 * g] = (int32_t)GhostPairs[g].first; gp[2 * g + 1] = (int32_t)GhostPairs[g].second; ax[g] = Particles[GhostPairs[g].second]->ghost_plane_axis; }
@@ -523,15 +533,17 @@ inline void Domain::backend_begin(double dt)
     }
     sent_mv.assign(trimesh.size(), Vec3_t(0.)); sent_mw.assign(trimesh.size(), Vec3_t(0.));
     forward_mesh_motion();
-    ck(wf_solver_init(backend, dt), "wf_solver_init");
+    bk.each("wf_solver_init", [&](int r) { return wf_solver_init(bk.ctx[r], dt); });
+    bk.refresh_ownership();
     choose_sync();
 }
 
-inline void Domain::backend_end() { if (backend) { wf_destroy(backend); backend = nullptr; } }
+inline void Domain::backend_end() { bk.destroy(); backend = nullptr; }
 
 // Source/Neighbour.cpp:10-139 (+ the upload): the cell grid of the reference, computed by the library
 inline void Domain::CellInitiate()
 {
+    if (gpus > 1) throw new Fatal("Domain::CellInitiate / MainNeighbourSearch as stand-alone calls run on one GPU (WELDFORM_GPUS = %d)", gpus);
     backend_begin(deltat > 0.0 ? deltat : 1.0);
     double b[3], t[3], cs[3]; int32_t cn[3];
     ck(wf_get_grid(backend, b, t, cs, cn), "wf_get_grid");
@@ -556,7 +568,7 @@ inline void Domain::SaveNeighbourData()
 {
     if (!backend) throw new Fatal("Domain::SaveNeighbourData: no neighbour search has run");
     const size_t n = Particles.Size(); std::vector<int32_t> ib(n);
-    ck(wf_download(backend, WF_F_NB, ib.data()), "wf_download(Nb)");
+    bk.download_all(WF_F_NB, 1, true, ib.data());
     for (size_t i = 0; i < n; ++i) Particles[i]->Nb = ib[i];
 }
 // Source/Neighbour.cpp:553-570
@@ -575,7 +587,7 @@ inline void Domain::get3(wf_field f, Vec3_t Particle::*mem, bool subset)
 {
     const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
     buf3.resize(3 * n);
-    if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf3.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf3.data()), "wf_download");
+    if (subset) bk.download_group(sync_group, f, 3, false, buf3.data()); else bk.download_all(f, 3, false, buf3.data());
     WF_HOST_PARALLEL_FOR
     for (size_t k = 0; k < n; ++k) { Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 3; ++d) (P->*mem)(d) = buf3[3 * k + d]; }
 }
@@ -583,7 +595,7 @@ inline void Domain::get9(wf_field f, Mat3_t Particle::*mem, bool subset)
 {
     const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
     buf9.resize(9 * n);
-    if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf9.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf9.data()), "wf_download");
+    if (subset) bk.download_group(sync_group, f, 9, false, buf9.data()); else bk.download_all(f, 9, false, buf9.data());
     WF_HOST_PARALLEL_FOR
     for (size_t k = 0; k < n; ++k) { Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 9; ++d) (P->*mem).d[d] = buf9[9 * k + d]; }
 }
@@ -591,7 +603,7 @@ inline void Domain::get1(wf_field f, double Particle::*mem, bool subset)
 {
     const size_t n = subset ? sync_idx.size() : Particles.Size(); if (!n) return;
     buf1.resize(n);
-    if (subset) ck(wf_download_subset(backend, f, sync_idx.data(), (int64_t)n, buf1.data()), "wf_download_subset"); else ck(wf_download(backend, f, buf1.data()), "wf_download");
+    if (subset) bk.download_group(sync_group, f, 1, false, buf1.data()); else bk.download_all(f, 1, false, buf1.data());
     WF_HOST_PARALLEL_FOR
     for (size_t k = 0; k < n; ++k) Particles[subset ? sync_idx[k] : k]->*mem = buf1[k];
 }
@@ -601,7 +613,7 @@ inline void Domain::put3(wf_field f, Vec3_t Particle::*mem, bool subset)
     buf3.resize(3 * n);
     WF_HOST_PARALLEL_FOR
     for (size_t k = 0; k < n; ++k) { const Particle * P = Particles[subset ? sync_idx[k] : k]; for (int d = 0; d < 3; ++d) buf3[3 * k + d] = (P->*mem)(d); }
-    if (subset) ck(wf_upload_subset(backend, f, sync_idx.data(), (int64_t)n, buf3.data()), "wf_upload_subset"); else ck(wf_upload(backend, f, buf3.data()), "wf_upload");
+    if (subset) bk.upload_group(sync_group, f, 3, false, buf3.data()); else bk.upload_all(f, 3, false, buf3.data());
 }
 
 inline void Domain::sync_down(bool everything)
@@ -614,7 +626,7 @@ inline void Domain::sync_down(bool everything)
     get1(WF_F_PRESSURE, &Particle::Pressure, subset); get1(WF_F_SIGMAY, &Particle::Sigmay, subset);
     {
         const size_t n = subset ? sync_idx.size() : Particles.Size(); std::vector<int32_t> ib(n);
-        if (n) { if (subset) ck(wf_download_subset(backend, WF_F_ID, sync_idx.data(), (int64_t)n, ib.data()), "wf_download_subset(ID)"); else ck(wf_download(backend, WF_F_ID, ib.data()), "wf_download(ID)"); }
+        if (n) { if (subset) bk.download_group(sync_group, WF_F_ID, 1, true, ib.data()); else bk.download_all(WF_F_ID, 1, true, ib.data()); }
         for (size_t k = 0; k < n; ++k) Particles[subset ? sync_idx[k] : k]->ID = ib[k];
     }
     if (!everything) {            // what the callback is about to see: sync_up uploads / refuses what it changed
@@ -636,8 +648,8 @@ inline void Domain::sync_down(bool everything)
         get1(WF_F_SIGMAY, &Particle::Sigmay, false); get1(WF_F_DDENSITY, &Particle::dDensity, false); get1(WF_F_DTDT, &Particle::dTdt, false);
         get1(WF_F_EFF_STRAIN_RATE, &Particle::eff_strain_rate, false); get1(WF_F_Q_PLHEAT, &Particle::q_plheat, false); get1(WF_F_DELTA_CONT, &Particle::delta_cont, false);
         const size_t n = Particles.Size(); std::vector<int32_t> ib(n);
-        ck(wf_download(backend, WF_F_ID, ib.data()), "wf_download(ID)"); for (size_t i = 0; i < n; ++i) Particles[i]->ID = ib[i];
-        ck(wf_download(backend, WF_F_NB, ib.data()), "wf_download(Nb)"); for (size_t i = 0; i < n; ++i) Particles[i]->Nb = ib[i];
+        bk.download_all(WF_F_ID, 1, true, ib.data()); for (size_t i = 0; i < n; ++i) Particles[i]->ID = ib[i];
+        bk.download_all(WF_F_NB, 1, true, ib.data()); for (size_t i = 0; i < n; ++i) Particles[i]->Nb = ib[i];
         // Particle::CalculateEquivalentStress (Source/Particle.cpp)
         for (size_t i = 0; i < n; ++i) { const Mat3_t & S = Particles[i]->Sigma;
             Particles[i]->Sigma_eq = std::sqrt(0.5 * ((S(0, 0) - S(1, 1)) * (S(0, 0) - S(1, 1)) + (S(1, 1) - S(2, 2)) * (S(1, 1) - S(2, 2)) + (S(2, 2) - S(0, 0)) * (S(2, 2) - S(0, 0))) +
@@ -653,7 +665,7 @@ inline void Domain::put1_if_changed(wf_field f, double Particle::*mem, std::vect
     if (!changed) return;
     buf1.resize(n);
     for (size_t k = 0; k < n; ++k) buf1[k] = Particles[subset ? sync_idx[k] : k]->*mem;
-    if (subset) ck(wf_upload_subset(backend, f, sync_idx.data(), (int64_t)n, buf1.data()), "wf_upload_subset"); else ck(wf_upload(backend, f, buf1.data()), "wf_upload");
+    if (subset) bk.upload_group(sync_group, f, 1, false, buf1.data()); else bk.upload_all(f, 1, false, buf1.data());
 }
 inline void Domain::refuse_if_changed(const char * what, const std::vector<double> & snap, int nc, bool subset, double (*get)(const Particle *, int))
 {
@@ -678,7 +690,7 @@ inline void Domain::sync_up()
         for (size_t k = 0; k < n && !idch; ++k) idch = Particles[subset ? sync_idx[k] : k]->ID != snap_id[k];
         if (idch) {
             std::vector<int32_t> ib(n); for (size_t k = 0; k < n; ++k) ib[k] = Particles[subset ? sync_idx[k] : k]->ID;
-            if (subset) ck(wf_upload_subset(backend, WF_F_ID, sync_idx.data(), (int64_t)n, ib.data()), "wf_upload_subset(ID)"); else ck(wf_upload(backend, WF_F_ID, ib.data()), "wf_upload(ID)");
+            if (subset) bk.upload_group(sync_group, WF_F_ID, 1, true, ib.data()); else bk.upload_all(WF_F_ID, 1, true, ib.data());
         }
         refuse_if_changed("Sigma", snap_sigma, 9, subset, [](const Particle * P, int d) { return P->Sigma.d[d]; });
         refuse_if_changed("pl_strain", snap_pls, 1, subset, [](const Particle * P, int) { return P->pl_strain; });
@@ -702,12 +714,12 @@ inline void Domain::sync_up()
                 for (int d = 0; d < 3; ++d) if (!wf_same_bits(P->v(d), v0(d)) || !wf_same_bits(P->a(d), a0(d))) differ |= 1;
             }
             if (!differ) {
-                ck(wf_fill_registered(backend, WF_F_V, g.handle, v0.d), "wf_fill_registered"); ck(wf_fill_registered(backend, WF_F_A, g.handle, a0.d), "wf_fill_registered");
+                bk.fill_group(g.handle, WF_F_V, v0.d); bk.fill_group(g.handle, WF_F_A, a0.d);
             } else {
                 g.v.resize(3 * n); g.a.resize(3 * n);
                 WF_HOST_PARALLEL_FOR
                 for (size_t k = 0; k < n; ++k) { const Particle * P = Particles[g.idx[k]]; for (int d = 0; d < 3; ++d) { g.v[3 * k + d] = P->v(d); g.a[3 * k + d] = P->a(d); } }
-                ck(wf_upload_registered(backend, WF_F_V, g.handle, g.v.data()), "wf_upload_registered"); ck(wf_upload_registered(backend, WF_F_A, g.handle, g.a.data()), "wf_upload_registered");
+                bk.upload_group(g.handle, WF_F_V, 3, false, g.v.data()); bk.upload_group(g.handle, WF_F_A, 3, false, g.a.data());
             }
         }
         return;
@@ -719,7 +731,7 @@ inline void Domain::forward_mesh_motion()
     for (size_t m = 0; m < trimesh.size(); ++m) {
         const Vec3_t & mv = trimesh[m]->m_v, & mw = trimesh[m]->m_w;
         bool ch = false; for (int k = 0; k < 3; ++k) if (mv(k) != sent_mv[m](k) || mw(k) != sent_mw[m](k)) ch = true;
-        if (ch) { ck(wf_mesh_set_motion(backend, (int)m, mv.d, mw.d), "wf_mesh_set_motion"); sent_mv[m] = mv; sent_mw[m] = mw; }
+        if (ch) { bk.each("wf_mesh_set_motion", [&](int r) { return wf_mesh_set_motion(bk.ctx[r], (int)m, mv.d, mw.d); }); sent_mv[m] = mv; sent_mw[m] = mw; }
     }
 }
 inline void Domain::refresh_scalars()
@@ -729,6 +741,7 @@ inline void Domain::refresh_scalars()
     contact_force_sum = s.contact_force_sum; contact_reaction_sum = s.contact_reaction_sum; ext_forces_work = s.ext_forces_work; plastic_work = s.plastic_work;
     accum_cont_heat_cond = s.accum_cont_heat_cond; contact_friction_work = s.contact_friction_work; kin_energy_sum = s.kin_energy_sum; int_energy_sum = s.int_energy_sum;
     m_maxT = s.max_T; m_minT = s.min_T; steps = (size_t)s.steps; isyielding = s.is_yielding != 0;
+    bk.steps_hint = (int)steps; bk.time_hint = Time;
     if (!m_contact_force.empty() && m_contact_force.size() <= 6) {                 // Domain::m_contact_force (Contact_Wang.cpp:312)
         double mf[18]; ck(wf_mesh_forces(backend, mf, (int)m_contact_force.size()), "wf_mesh_forces");
         for (size_t m = 0; m < m_contact_force.size(); ++m) m_contact_force[m] = Vec3_t(mf[3 * m], mf[3 * m + 1], mf[3 * m + 2]);
@@ -779,8 +792,8 @@ inline void Domain::ThermalSolve(double tf, double dt, double dtOut, char const 
     auto t0 = std::chrono::steady_clock::now();
     refresh_scalars();
     while (Time < tf && idx_out <= maxidx) {
-        if (GeneralAfter) { ck(wf_thermal(backend), "wf_thermal"); run_callback(GeneralAfter); ck(wf_step_end(backend), "wf_step_end"); }   // :657-674
-        else ck(wf_run(backend, 1), "wf_run");
+        if (GeneralAfter) { bk.phase("wf_thermal", wf_thermal); run_callback(GeneralAfter); bk.phase("wf_step_end", wf_step_end); }   // :657-674
+        else bk.each("wf_run", [&](int r) { return wf_run(bk.ctx[r], 1); });
         refresh_scalars();
         if (Time >= tout) {
             if (TheFileKey != NULL) { String fn; fn.Printf("%s_%04d", TheFileKey, (int)idx_out); sync_down(true); WriteCSV(fn.CStr()); }
@@ -788,7 +801,7 @@ inline void Domain::ThermalSolve(double tf, double dt, double dtOut, char const 
             std::cout << "Output No. " << idx_out << " at " << Time << " has been generated\nMax, Min, Avg temps: " << m_maxT << ", " << m_minT << ", " << (m_maxT + m_minT) / 2. << "\n";
         }
     }
-    ck(wf_sync(backend), "wf_sync");
+    bk.phase("wf_sync", wf_sync);
     wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     sync_down(true);
     std::cout << "\n--------------Solving is finished: " << steps << " steps, " << wall_seconds << " s" << std::endl;
@@ -807,15 +820,15 @@ inline void Domain::solve_kick_drift_leap_frog(int solver, double tf, double dt,
     refresh_scalars();
     while (Time <= tf && idx_out <= maxidx) {
         if (GeneralBefore) run_callback(GeneralBefore);
-        ck(wf_solver_stage(backend, 0), "wf_solver_stage 0");
+        bk.phase_i("wf_solver_stage 0", wf_solver_stage, 0);
         if (GeneralAfter) { refresh_scalars(); run_callback(GeneralAfter); }     // fix free accel
-        ck(wf_solver_stage(backend, 1), "wf_solver_stage 1");
+        bk.phase_i("wf_solver_stage 1", wf_solver_stage, 1);
         if (GeneralAfter && solver == 2) run_callback(GeneralAfter);            // SolverLeapfrog.cpp:254
-        ck(wf_solver_stage(backend, 2), "wf_solver_stage 2");
+        bk.phase_i("wf_solver_stage 2", wf_solver_stage, 2);
         if (GeneralAfter) run_callback(GeneralAfter);                            // reinforce BC vel
-        ck(wf_solver_stage(backend, 3), "wf_solver_stage 3");
+        bk.phase_i("wf_solver_stage 3", wf_solver_stage, 3);
         if (GeneralAfter && solver == 1) run_callback(GeneralAfter);            // SolverKickDrift.cpp:260
-        ck(wf_solver_stage(backend, 4), "wf_solver_stage 4");
+        bk.phase_i("wf_solver_stage 4", wf_solver_stage, 4);
         refresh_scalars();
         { wf_scalars s; ck(wf_reduce(backend, &s), "wf_reduce"); deltat = s.deltat; }
         if (Time >= tout) {
@@ -824,7 +837,7 @@ inline void Domain::solve_kick_drift_leap_frog(int solver, double tf, double dt,
             std::cout << "Output No. " << idx_out << " at " << Time << " has been generated\nCurrent Time Step = " << deltat << "\n";
         }
     }
-    ck(wf_sync(backend), "wf_sync");
+    bk.phase("wf_sync", wf_sync);
     wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     sync_down(true);
     for (int k = 0; k < 3; ++k) max_disp(k) = 0.0;       // those loops shadow Domain::max_disp with a local (SolverKickDrift.cpp:122)
@@ -846,16 +859,16 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
     while (Time <= tf && idx_out <= maxidx && !env_stop(idx_out)) {
         if (bench_steps > 0) {
             if (bench_state == 0 && isyielding && steps >= bench_spin_min) { bench_state = 1; bench_mark = steps + bench_warmup; }
-            if (bench_state == 1 && steps == bench_mark) { ck(wf_sync(backend), "wf_sync"); bench_t0 = std::chrono::steady_clock::now(); bench_state = 2; bench_first_step = steps; bench_mark = steps + bench_steps; }
-            else if (bench_state == 2 && steps == bench_mark) { ck(wf_sync(backend), "wf_sync"); bench_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - bench_t0).count(); break; }
+            if (bench_state == 1 && steps == bench_mark) { bk.phase("wf_sync", wf_sync); bench_t0 = std::chrono::steady_clock::now(); bench_state = 2; bench_first_step = steps; bench_mark = steps + bench_steps; }
+            else if (bench_state == 2 && steps == bench_mark) { bk.phase("wf_sync", wf_sync); bench_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - bench_t0).count(); break; }
         }
         if (GeneralBefore) run_callback(GeneralBefore);                          // :238
-        ck(wf_fraser_stage_a(backend), "wf_fraser_stage_a");                     // :137-312 rebuild policy, density, rates + stress, accel, contact
+        bk.phase("wf_fraser_stage_a", wf_fraser_stage_a);                        // :137-312 rebuild policy, density, rates + stress, accel, contact
         if (GeneralAfter) { refresh_scalars(); run_callback(GeneralAfter); }     // :332
-        ck(wf_fraser_stage_b1(backend), "wf_fraser_stage_b1");                   // :337-343 position update
-        ck(wf_fraser_stage_b2(backend), "wf_fraser_stage_b2");                   // :352-355 velocity update
+        bk.phase("wf_fraser_stage_b1", wf_fraser_stage_b1);                      // :337-343 position update
+        bk.phase("wf_fraser_stage_b2", wf_fraser_stage_b2);                      // :352-355 velocity update
         if (GeneralAfter) run_callback(GeneralAfter);                            // :360
-        ck(wf_fraser_stage_c(backend), "wf_fraser_stage_c");                     // :367-412 heat, energies, time, mesh update, cadence
+        bk.phase("wf_fraser_stage_c", wf_fraser_stage_c);                        // :367-412 heat, energies, time, mesh update, cadence
         refresh_scalars();
         if (Time >= tout) {                                                      // :420-499
             wf_scalars s; ck(wf_reduce(backend, &s), "wf_reduce"); max_pl = s.max_pl_strain;
@@ -877,7 +890,7 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
             std::cout << o.str();
         }
     }
-    ck(wf_sync(backend), "wf_sync");
+    bk.phase("wf_sync", wf_sync);
     wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     sync_down(true);
     for (size_t m = 0; m < trimesh.size(); ++m) {                                // rigid-mesh node positions / normals back into the driver's TriMesh

@@ -125,9 +125,9 @@ def test_compression_thermal_driver_whole_run(sync):
     gold = np.load(os.path.join(GOLD, "Compression_thermal.npz"))
     d, rc = run_mirror_driver("Compression_thermal", sync, int(gold["kept"].max()))
     assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
-    # printed precision (a unit in the 6th digit is 1e-5 .. 1e-6 relative) for the first 1 000 steps; afterwards the accumulated round-off of the
-    # different (but fixed) summation grouping of the device shows in the accelerations of a body that has yielded through
-    compare_tables(d, gold, "test06", lambda idx: 1e-5 if idx <= 30 else 2e-4, what="Compression_thermal/" + sync)
+    # printed precision: a unit in the 6th digit is 1e-6 .. 1e-5 relative, and the reference's own 4-thread run differs from its 1-thread run
+    # (the golden) by up to 1e-5 in v and a at table 30 and 2.3e-5 at table 106 (summation order); 2e-5 / 1e-4 element-wise
+    compare_tables(d, gold, "test06", lambda idx: 2e-5 if idx <= 30 else 1e-4, what="Compression_thermal/" + sync)
     compare_history(d, gold, 1e-5, what="Compression_thermal/" + sync)
     shutil.rmtree(d, ignore_errors=True)
 

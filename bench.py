@@ -46,9 +46,16 @@ def dx_for(n_particles):
     return float((vol / n_particles) ** (1.0 / 3.0))
 
 
-def workload_config(n_sph, extra=None):
-    cfg = {"workload": ("Compression_thermal cylinder between two rigid planes (penalty contact), lattice" if extra and extra.get("contact") else "Compression_thermal cylinder lattice") + " (AddCylinderLength R=0.15 L=0.56 h=1.2dx), elastoplastic + thermal + plastic heating, "
-                       "alpha=1 TI=0.3, yielding state, neighbour rebuild every 5 steps",
+WORKLOAD_TEXT = {
+    "plate": "Plate-Yield_3d box lattice (AddBoxLength 0.033 x 0.01 x 0.01, BASELINE configs[3]), bilinear yield, alpha=beta=1 TI=0.3, ends pulled apart, neighbour rebuild every 5 steps once yielding",
+    "fsw": "FSW plate (AddBoxLength 0.055 x 0.003 x 0.055, BASELINE configs[4]): Johnson-Cook, thermal solver + plastic and friction heat, convection on the bottom row, fixed side walls, "
+           "rotating + plunging rigid tool (penalty contact, friction linear in T)",
+}
+
+
+def workload_config(n_sph, extra=None, workload="compression"):
+    cfg = {"workload": WORKLOAD_TEXT.get(workload) or (("Compression_thermal cylinder between two rigid planes (penalty contact), lattice" if extra and extra.get("contact") else "Compression_thermal cylinder lattice") + " (AddCylinderLength R=0.15 L=0.56 h=1.2dx), elastoplastic + thermal + plastic heating, "
+                       "alpha=1 TI=0.3, yielding state, neighbour rebuild every 5 steps"),
            "particles": int(n_sph), "neighbours_per_particle": 56, "solver": "SolveDiffUpdateFraser", "ts_nb_inc": 5,
            "l2": "inputs larger than L2 (>= 1 kB of fp64 state per particle)"}
     if extra:
@@ -255,7 +262,20 @@ def run_ours(args):
     dx = dx_for(n_target)
     t0 = time.time()
     contact = args.workload == "contact"
-    case = cases.compression_fast(dx=dx, nsteps=1, perturb_amp=PERTURB_AMP, contact_planes=contact)
+    if args.workload == "plate":
+        # BASELINE configs[3]: examples/Plate-Yield_3d.cpp:60-119 scaled by dx (AddBoxLength plate 0.033 x 0.01 x 0.01, ends pulled apart, bilinear
+        # yield; slabs along x on several GPUs). The shipped Quintic_Spline with h = 1.3 dx gives 250 neighbours per particle, beyond the
+        # reference's own MAX_NB_PER_PART: --plate-kernel 0 (cubic spline, h = 1.2 dx, the default) or 2 (quintic, h = 0.8 dx)
+        dx = float((0.033 * 0.01 * 0.01 / n_target) ** (1.0 / 3.0))
+        case = cases.plate_yield(dx=dx, nsteps=1, kernel=args.plate_kernel, hfac=(1.2 if args.plate_kernel == 0 else 0.8), amp=1.0)
+    elif args.workload == "fsw":
+        # BASELINE configs[4]: examples/FSW.cpp:60-305 scaled by dx (AddBoxLength plate 0.055 x 0.003 x 0.055, Johnson-Cook, thermal solver, convection
+        # on the bottom row, fixed side walls, friction linear in T with friction heat) with a rotating + plunging rigid tool; here the tool is an
+        # AxisPlaneMesh disc-sized plane (tests/cases.fsw_like), the NASTRAN tool of the driver itself runs in tests/test_drivers_gpu.py
+        dx = float((0.055 * 0.003 * 0.055 / n_target) ** (1.0 / 3.0))
+        case = cases.fsw_like(dx=dx, nsteps=1)
+    else:
+        case = cases.compression_fast(dx=dx, nsteps=1, perturb_amp=PERTURB_AMP, contact_planes=contact)
     case["tuning"] = float(args.tuning)
     comm = None
     if world > 1:
@@ -331,15 +351,17 @@ def run_ours(args):
     # (SPH::Domain::AddCylinderLength, per-particle set-up loop, a GeneralAfter callback looping over Particles[i]->ID twice per step,
     # SolveDiffUpdateFraser) on the host mirror; it is run as its own process on the same GPU in the three callback-bridge modes.
     e2e_domain = None
-    if world == 1 and not contact and not args.python_e2e:
+    if world == 1 and args.workload == "compression" and not args.python_e2e:
         e2e_domain = domain_api_e2e(n_target, args.steps, max(args.warmup, 3), local, log)
 
     # ---- e2e, Python form (N > 1 and the contact workload): phase API + host GeneralAfter callback bridge with pinned host buffers
+    bc_rows = {}
     if contact:
         vtop, tau = np.asarray(case["mesh0_vel"][:3], float).copy(), float(case["mesh0_vel"][3])
     else:
-        bc = np.asarray(case["bc"]).reshape(-1, 8)
-        vtop, tau = bc[0, 1:4].copy(), float(bc[0, 4])
+        for r in np.asarray(case["bc"]).reshape(-1, 8):          # (ID, vx, vy, vz, tau, set_a, ...) per boundary-condition row of the driver's callback
+            bc_rows[int(r[0])] = (r[1:4].copy(), float(r[4]))
+        vtop, tau = bc_rows[3]
     bridge = {"mig": None}
 
     def refresh_tagged():
@@ -386,10 +408,9 @@ def run_ours(args):
         if len(tagged) == 0:
             return
         v_host, a_host = bridge["sets"][bridge["point"]]; bridge["point"] ^= 1
-        f = min(t_now / tau, 1.0) if tau > 0 else 1.0
         a_host[:] = 0.0
-        v_host[n2:] = vtop * f
-        v_host[:n2] = 0.0
+        for (vv, tt), sl in ((bc_rows[2], slice(0, n2)), (bc_rows[3], slice(n2, None))):
+            v_host[sl] = vv * (min(t_now / tt, 1.0) if tt > 0 else 1.0)
         ctx.upload_registered("v", bridge["handle"], v_host, wait=False); ctx.upload_registered("a", bridge["handle"], a_host, wait=False)
 
     def e2e_step():
@@ -512,9 +533,10 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(n_sph, {"decomposition": ("1 GPU" if world == 1 else "%d slabs along z, NCCL halos (3 refreshes per step), rank 0: %s" % (world, comm_info)),
+                "config": workload_config(n_sph, workload=args.workload, extra={"decomposition": ("1 GPU" if world == 1 else "%d slabs along the longest axis of the cell grid (%s), NCCL halos (3 refreshes per step), rank 0: %s" % (world, {"plate": "x", "fsw": "x"}.get(args.workload, "z"), comm_info)),
                                                   "neighbours_avg": nb_avg, "spinup_steps": spin, "nb_rebuilds_in_timed_region": int(prof.get("nb_list", (0, 0))[1]),
                                                   "max_pl_strain": s_after.max_pl_strain, "state_checksum": checksum,
+                                                  "yielding": bool(s_after.is_yielding),
                                                   **({"contact": "two rigid AxisPlaneMesh planes (%d elements each), Wang penalty contact, friction 0.2; contact force sum %.4g N" % (info["meshes"][0][1], s_after.contact_force_sum)} if contact else {})}),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels}
         print(json.dumps(line), flush=True)
@@ -528,17 +550,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--particles", type=float, default=1.0e7)
+    ap.add_argument("--particles", type=float, default=None, help="default 1e7 (2e7 for --workload fsw)")
     ap.add_argument("--max-spinup", type=int, default=400)
     ap.add_argument("--cpu-sample", type=int, default=50000, help="particles of the CPU-baseline sample lattice")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["compression", "contact"], default="compression",
-                    help="compression: Compression_thermal (velocity-prescribed end rows, BASELINE configs[1] scaled); contact: the same cylinder between two rigid planes (penalty contact)")
+    ap.add_argument("--workload", choices=["compression", "contact", "plate", "fsw"], default="compression",
+                    help="compression: Compression_thermal (velocity-prescribed end rows, BASELINE configs[1] scaled); contact: the same cylinder between two rigid planes (penalty contact); "
+                         "plate: Plate-Yield_3d box lattice (BASELINE configs[3]); fsw: FSW plate with fixed walls, Johnson-Cook, thermal coupling and a rotating + plunging tool (configs[4], default 2e7 particles)")
+    ap.add_argument("--plate-kernel", type=int, default=0, choices=[0, 2], help="plate workload: 0 cubic spline (h = 1.2 dx), 2 quintic spline (h = 0.8 dx)")
     ap.add_argument("--tuning", type=int, default=0, help="wf_params::tuning bit mask (kernel A/B switches)")
     ap.add_argument("--python-e2e", action="store_true", help="N = 1: time the e2e leg through the Python ctypes phase API only (skip the C++ Domain driver)")
     args = ap.parse_args()
-    args.particles = int(args.particles)
+    args.particles = int(args.particles if args.particles else (2.0e7 if args.workload == "fsw" else 1.0e7))
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

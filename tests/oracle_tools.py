@@ -67,6 +67,15 @@ def max_rel(a, b):
 
 
 ELEM_FLOOR = 1e-6
+# Fields a particle ACCUMULATES (time integrals, monotone or slowly varying state): every entry is meaningful down to a millionth of the
+# field's largest. Everything else (a, v, rates, stresses ...) is a sum of signed pair terms that cancel: an entry far below the field's top
+# carries the absolute round-off of the terms it was summed from, so such entries are judged against 1 % of the top instead.
+STATE_FIELDS = {"x", "Displacement", "pl_strain", "T", "T-T0", "Density", "Sigmay"}
+DERIVED_FLOOR = 1e-2
+
+
+def elem_floor(field):
+    return ELEM_FLOOR if field.split("/")[-1] in STATE_FIELDS else DERIVED_FLOOR
 
 
 def max_rel_elem(a, b, floor=ELEM_FLOOR):

@@ -233,3 +233,24 @@ def test_host_mirror_on_two_gpus_bit_identical_to_one(product_lib, sync, amp, ns
     assert outs[0].size == outs[1].size and outs[0].size > 8
     a, b = outs[0][8:].view(np.float64), outs[1][8:].view(np.float64)
     assert np.array_equal(a, b), "2-GPU host-mirror run differs from the 1-GPU run: max |diff| %.3e in %d of %d values" % (np.abs(a - b).max(), int((a != b).sum()), a.size)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("name", ["plate_cubic_40", "plate_quintic_10", "fsw_like_80", "thermal_solve_25", "thermal_solve_gc_20"])
+def test_multi_gpu_plate_and_fsw_goldens(product_lib, name):
+    """BASELINE configs 4 and 5 in small: the Plate-Yield_3d lattice (AddBoxLength, slabs along x; cubic and quintic-spline kernels) and the
+    FSW-like set-up (Johnson-Cook, convection BC, FIXED side walls, rotating + plunging tool, friction heat) on two GPUs: bit-identical per
+    particle to one GPU and within the golden bar of the reference's own dump. Domain::ThermalSolve (conduction only, one neighbour search, with
+    and without corrected gradients) rides along: its halo refresh points are those of the post pass."""
+    from tests import golden_tools
+    from weldform_b200 import harness
+    case, ref = golden_tools.load(name)
+    multi, info = _run_multi(case, 2)
+    single = harness.run_case(case)
+    assert all(i[1] > 0 for i in info), "every rank must hold halo particles"
+    assert np.array_equal(multi["pairs"], single["pairs"]) and np.array_equal(multi["pairs"], ref["pairs"])
+    bad = {k: ot.max_rel(multi[k], single[k]) for k in cases.FIELDS_F64 + ["ID", "Nb"] if not np.array_equal(multi[k], single[k])}
+    assert not bad, "multi-GPU differs from single GPU per particle: %s" % bad
+    worst = {k: ot.max_rel(multi[k], ref[k]) for k in ("x", "v", "Displacement", "pl_strain", "T", "Density", "Sigma") if k in ref}
+    assert max(worst.values()) < 1e-7, worst

@@ -348,6 +348,21 @@ void comm_destroy(wf_ctx *c)
     c->comm.nccl = nullptr;
 }
 
+int comm_gather_scalars_on(wf_ctx *c, const double *src, double *dst, int nvals, cudaStream_t st)
+{
+    wf_ctx::Comm &m = c->comm;
+    if (m.nranks <= 1) return 0;
+    NcclApi *A = nccl_api();
+    WF_NCCL(c, A->AllGather(src, dst, (size_t)nvals, ncclDouble, (ncclComm_t)m.nccl, st));
+    return 0;
+}
+int comm_red_wait(wf_ctx *c)
+{
+    wf_ctx::Comm &m = c->comm;
+    for (int p = 0; p < 2; ++p) if (m.red_pending[p]) { WF_CUDA(c, cudaStreamWaitEvent(c->stream, m.ev_red_done[p], 0)); m.red_pending[p] = false; }
+    return 0;
+}
+
 int comm_gather_scalars(wf_ctx *c, int nvals)
 {
     wf_ctx::Comm &m = c->comm;
@@ -512,6 +527,11 @@ extern "C" int wf_comm_init(wf_ctx *c, int rank, int nranks, const void *id128)
     WF_CUDA(c, cudaMalloc(&c->comm.d_cnt, 64 * sizeof(int) + 16 * sizeof(long long)));
     WF_CUDA(c, cudaMemset(c->comm.d_cnt, 0, 64 * sizeof(int) + 16 * sizeof(long long)));
     WF_CUDA(c, cudaMalloc(&c->comm.d_all, (size_t)nranks * 32 * sizeof(double)));
+    WF_CUDA(c, cudaEventCreateWithFlags(&c->comm.ev_red_ready, cudaEventDisableTiming));
+    for (int p = 0; p < 2; ++p) {
+        WF_CUDA(c, cudaMalloc(&c->comm.d_red_rank[p], 32 * sizeof(double))); WF_CUDA(c, cudaMalloc(&c->comm.d_red_all[p], (size_t)nranks * 32 * sizeof(double)));
+        WF_CUDA(c, cudaEventCreateWithFlags(&c->comm.ev_red_done[p], cudaEventDisableTiming));
+    }
     return 0;
 }
 

@@ -96,6 +96,8 @@ extern "C" void wf_destroy(wf_ctx *c)
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     if (c->comm.stream) { cudaStreamSynchronize(c->comm.stream); cudaStreamDestroy(c->comm.stream); }
     if (c->comm.ev_ready) cudaEventDestroy(c->comm.ev_ready); if (c->comm.ev_done) cudaEventDestroy(c->comm.ev_done);
+    if (c->comm.ev_red_ready) cudaEventDestroy(c->comm.ev_red_ready);
+    for (int p = 0; p < 2; ++p) { cudaFree(c->comm.d_red_rank[p]); cudaFree(c->comm.d_red_all[p]); if (c->comm.ev_red_done[p]) cudaEventDestroy(c->comm.ev_red_done[p]); }
     for (auto &e : c->comm.t_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     comm_destroy(c);
     cudaStreamDestroy(c->stream);

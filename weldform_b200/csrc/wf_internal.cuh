@@ -90,6 +90,10 @@ struct wf_ctx {
         int *d_emig = nullptr; int *d_cnt = nullptr; int64_t emig_cap = 0;            // emigrant slot lists (2 x emig_cap), counters
         cudaStream_t stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool pending = false;   // halo exchange overlapped with interior work
         double *d_rank = nullptr, *d_all = nullptr;                                     // scalar partials: this rank / all ranks
+        // end-of-step scalars gathered OFF the compute stream (two buffer sets by step parity): the all-gather and the accumulation kernel run on
+        // the communication stream while the next step's first kernels are already executing
+        double *d_red_rank[2] = { nullptr, nullptr }, *d_red_all[2] = { nullptr, nullptr };
+        cudaEvent_t ev_red_ready = nullptr, ev_red_done[2] = { nullptr, nullptr }; bool red_pending[2] = { false, false }; int red_parity = 0;
         int64_t migrated_out = 0, migrated_in = 0, halo_bytes_step = 0;
         // time-based rebalancing of the slabs: event pairs around the interior momentum launch of every step since the last rebuild
         std::vector<std::pair<cudaEvent_t, cudaEvent_t> > t_events; int t_used = 0; int64_t rebalance_moves = 0; int rebuilds_seen = 0;
@@ -178,6 +182,7 @@ int nb_cell_initiate(wf_ctx *c);
 int nb_build_impl(wf_ctx *c);
 int nb_gradcorr_fsm(wf_ctx *c);                         // CalcGradCorrMatrix: contributions of the pairs with one fixed particle
 // wf_pair.cu
+bool pair_fm_active(const wf_ctx *c);                  // the contracted-arithmetic pair kernels (wf_pair_fm.cu) serve this configuration
 int pair_gradcorr(wf_ctx *c);
 int pair_tir(wf_ctx *c);
 int pair_temp_inc_pp(wf_ctx *c);                         // CalcTempIncPP: the initial dT/dt of ThermalSolve
@@ -200,6 +205,8 @@ int comm_time_end(wf_ctx *c);
 int comm_rebalance(wf_ctx *c);                           // at a rebuild: move slab boundaries by at most one layer towards equal step time
 void comm_destroy(wf_ctx *c);                           // ncclCommDestroy, no-op on one GPU
 int comm_gather_scalars(wf_ctx *c, int nvals);          // d_rank -> d_all (all ranks), no-op on one GPU
+int comm_gather_scalars_on(wf_ctx *c, const double *src, double *dst, int nvals, cudaStream_t st);
+int comm_red_wait(wf_ctx *c);                            // compute stream waits for every end-of-step scalar gather still in flight
 int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);
 int comm_serial_mass_sum(wf_ctx *c, const double *mass, const int64_t *gidx, int64_t n_local, int64_t n_global, double *tot);

@@ -747,6 +747,15 @@ namespace wf {
 // launch KERNEL<targs..., PF> with PF = software pipeline on/off; grid of one thread per slot, 128 threads per block
 #define WF_LAUNCH_PF(KERNEL, ...) do { if (pf) KERNEL<__VA_ARGS__, true><<<g, 128, 0, c->stream>>>(a); else KERNEL<__VA_ARGS__, false><<<g, 128, 0, c->stream>>>(a); } while (0)
 
+bool pair_fm_active(const wf_ctx *c)
+{
+    if (!(c->prm.tuning & 1024) || !fast_path(c) || c->prm.gradient_type != 0) return false;
+    wf_ctx *cc = const_cast<wf_ctx *>(c);
+    const bool had = cc->nbr != nullptr; (void)had;
+    PairArgs a = make_args(cc);
+    return lean_ok(c, a);
+}
+
 // CalcGradCorrMatrix (Domain.cpp:1832-1940) on the current neighbour lists
 int pair_gradcorr(wf_ctx *c)
 {

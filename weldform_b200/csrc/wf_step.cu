@@ -120,6 +120,7 @@ struct ContactArgs {
     int K; const int *cont, *cont_cnt; const double *node, *enormal, *ev, *pplane; const int *en, *emesh;
     double friction_sta, friction_dyn, dfac, contact_hc; int cont_heat_fric, cont_heat_cond;
     int friction_function; double friction_m, friction_b;
+    const int *slot_of; int first_mesh_local;          // element e's particle: slot_of[first_mesh_local + e] (its temperature, Contact_Wang.cpp:325)
     int n_mesh; double *mf_part; int *mf_flag;      // Domain::m_contact_force (Contact_Wang.cpp:312): per-block sums [block][WF_MAX_MESH_FORCES][3] + "block had a hit"
 };
 __global__ void __launch_bounds__(128) k_contact(StepArgs a, ContactArgs k)
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(128) k_contact(StepArgs a, ContactArgs k)
                     csum += norm(cf);
                     creac += dot(acc, n2) * Mass;
                     cext += dot(cf, v2);
-                    if (k.cont_heat_cond) qcont = dens * k.contact_hc * dS2 * (0.0 - q2.z) / Mass;   // mesh particle T stays 0 unless conduction to the tool is modelled
+                    if (k.cont_heat_cond) qcont = dens * k.contact_hc * dS2 * (a.Q2[k.slot_of[k.first_mesh_local + e]].z - q2.z) / Mass;   // Particles[P2]->T: the element particle's temperature (the driver's value; nothing on this path changes it)
                 }
             }
         }
@@ -329,11 +330,12 @@ __global__ void k_reduce_final(const double *all, int nranks, DevScalars *sc, do
             sc->contact_force_sum = res[R_CSUM]; sc->contact_reaction_sum = res[R_CREAC];
             for (int q = 0; q < 3 * WF_MAX_MESH_FORCES; ++q) { double v = 0.; for (int r = 0; r < nranks; ++r) v += all[r * 32 + R_MCF + q]; sc->mcf[q / 3][q % 3] = v; }
             sc->ext_forces_work += res[R_CEXT] * dt;            // Contact_Wang.cpp:344
-            sc->time += dt;                                     // SolverFraser.cpp:384
+            if (accumulate == 1) sc->time += dt;                // SolverFraser.cpp:384 (accumulate == 2: k_advance_time already did, on the compute stream)
         }
     }
 }
 __global__ void k_set_time(DevScalars *sc, double t, double dt) { sc->time = t; sc->dt = dt; }
+__global__ void k_advance_time(DevScalars *sc, double dt) { sc->time += dt; }
 
 // InitialChecks (Domain.cpp:2097-2113): Pressure = EOS(...) for every particle
 __global__ void k_init_pressure(StepArgs a)
@@ -377,6 +379,7 @@ int contact_impl(wf_ctx *c)
     }
     c->mf_blocks = nblk;
     k.n_mesh = (int)c->meshes.size(); k.mf_part = c->d_mf_part; k.mf_flag = c->d_mf_flag;
+    k.slot_of = c->slot_of; k.first_mesh_local = (int)(c->n_loc - c->nmeshp);
     k_contact<<<grid_for(c->n_loc, 128), 128, 0, c->stream>>>(a, k); WF_LAUNCH_CHECK(c); c->launches++;
     return 0;
 }
@@ -410,10 +413,28 @@ int reduce_impl(wf_ctx *c, bool accumulate)
     StepArgs a = make_step_args(c);
     int nb = std::min<int64_t>(c->partial_blocks, (c->n_loc + 255) / 256); if (nb < 1) nb = 1;
     const int first_fem = c->meshes.empty() ? 2147483647 : (int)c->meshes[0].first_particle;
+    const bool multi = c->comm.nranks > 1;
     k_reduce_partial<<<nb, 256, 0, c->stream>>>(a, first_fem, c->d_partial); WF_LAUNCH_CHECK(c);
+    if (multi && accumulate && !(c->prm.tuning & 2048)) {
+        // several GPUs, end of a step: the all-gather of the 32 scalars and the accumulation run on the COMMUNICATION stream; the compute
+        // stream only advances the time (which the boundary-condition ramps of the next step read) and goes on. wf_params::tuning bit 11
+        // keeps everything in stream order (A/B measurement).
+        wf_ctx::Comm &m = c->comm; const int p = m.red_parity; m.red_parity ^= 1;
+        if (m.red_pending[p]) { WF_CUDA(c, cudaStreamWaitEvent(c->stream, m.ev_red_done[p], 0)); m.red_pending[p] = false; }     // buffer set of two steps ago
+        k_reduce_rank<<<1, 256, 0, c->stream>>>(c->d_partial, nb, m.d_red_rank[p], c->d_mf_part, c->d_mf_flag, c->mf_blocks, (int)std::min<size_t>(c->meshes.size(), WF_MAX_MESH_FORCES)); WF_LAUNCH_CHECK(c);
+        k_advance_time<<<1, 1, 0, c->stream>>>(c->d_sc, c->dt); WF_LAUNCH_CHECK(c);
+        WF_CUDA(c, cudaEventRecord(m.ev_red_ready, c->stream));
+        WF_CUDA(c, cudaStreamWaitEvent(m.stream, m.ev_red_ready, 0));
+        WF_CHECK(comm_gather_scalars_on(c, m.d_red_rank[p], m.d_red_all[p], 32, m.stream));
+        k_reduce_final<<<1, 32, 0, m.stream>>>(m.d_red_all[p], m.nranks, c->d_sc, c->dt, 2); WF_LAUNCH_CHECK(c);
+        WF_CUDA(c, cudaEventRecord(m.ev_red_done[p], m.stream));
+        m.red_pending[p] = true;
+        c->launches += 4;
+        return 0;
+    }
+    WF_CHECK(comm_red_wait(c));
     k_reduce_rank<<<1, 256, 0, c->stream>>>(c->d_partial, nb, c->comm.d_rank, c->d_mf_part, c->d_mf_flag, c->mf_blocks, (int)std::min<size_t>(c->meshes.size(), WF_MAX_MESH_FORCES)); WF_LAUNCH_CHECK(c);
     WF_CHECK(comm_gather_scalars(c, 32));
-    const bool multi = c->comm.nranks > 1;
     k_reduce_final<<<1, 32, 0, c->stream>>>(multi ? c->comm.d_all : c->comm.d_rank, multi ? c->comm.nranks : 1, c->d_sc, c->dt, accumulate ? 1 : 0); WF_LAUNCH_CHECK(c);
     c->launches += 3;
     return 0;
@@ -464,9 +485,9 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     if (c->prm.solver == 3) {
         // Domain::ThermalSolve (Thermal.cpp:567-626): one neighbour search for the whole run, the correction matrices, the initial dT/dt
         if (c->prm.contact) return fail(c, WF_ERR_UNSUPPORTED, "ThermalSolve with rigid-mesh contact is not implemented");
-        if (c->comm.nranks > 1) return fail(c, WF_ERR_UNSUPPORTED, "ThermalSolve on more than one GPU has not been verified against the reference yet; run it on one GPU");
         WF_CHECK(nb_build_impl(c));
         c->solver_ready = true;
+        WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2));      // several GPUs: x, m/rho, T of the halo particles for the two walks below
         WF_CHECK(pair_gradcorr(c));
         WF_CHECK(pair_temp_inc_pp(c));
         WF_CHECK(reduce_impl(c, false));
@@ -496,6 +517,7 @@ extern "C" int wf_energy(wf_ctx *c) { WF_NEED_READY(c); return pair_energy(c); }
 
 static int fetch_scalars(wf_ctx *c)
 {
+    WF_CHECK(comm_red_wait(c));
     WF_CUDA(c, cudaMemcpyAsync(c->h_sc, c->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
     WF_CUDA(c, cudaStreamSynchronize(c->stream));
     return 0;

@@ -20,7 +20,10 @@
 //   tagged  the same, for the particles whose ID differs from the most common ID only (the boundary-condition rows of the usual drivers,
 //           e.g. ID 2/3 in examples/Compression_thermal.cpp:30-66) -- O(surface) traffic instead of O(N);
 //   push    like tagged, but nothing is read back before the callback: for callbacks that only ASSIGN whole v and a vectors of their
-//           boundary rows (examples/Compression_thermal.cpp:30-66 does); v and a of the tagged rows are uploaded after it;
+//           boundary rows (examples/Compression_thermal.cpp:30-66 does); v and a of the tagged rows are uploaded after it (one vector and a
+//           fill kernel per ID group when the group's rows all got the same values). The callback does not wait for the device: getTime()
+//           is advanced on the host (Time += deltat, the device's own arithmetic), max_disp / contact_force_sum / the energy sums are
+//           refreshed every 32 steps and before every output, so the callback overlaps the GPU's work on the step;
 //   none    the callback only sees scalars (time, max_disp, contact_force_sum) and trimesh[m]->SetVel.
 // Rigid-mesh velocities set from the callback (trimesh[m]->SetVel / SetRotAxisVel) are always forwarded.
 // Two more environment knobs, for driver tests that cannot afford a driver's full run: WELDFORM_MAX_STEPS=n and WELDFORM_MAX_OUTPUTS=k end
@@ -36,6 +39,8 @@
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <new>
+#include <utility>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -191,6 +196,16 @@ private:
     struct MeshRec { TriMesh * mesh; float hfac; int id; };
     std::vector<MeshRec> mesh_recs;
 
+    // Particles created by the lattice generators live in one arena, contiguous in creation order: a driver's `for (i...) Particles[i]->ID`
+    // loop then walks memory with a constant stride instead of chasing ten million heap pointers
+    std::vector<void *> pool_blocks; size_t pool_used = 0; static const size_t POOL_BLOCK = 16384;
+    template <typename... A> Particle * pool_make(A && ... a)
+    {
+        if (pool_blocks.empty() || pool_used == POOL_BLOCK) { pool_blocks.push_back(::operator new(POOL_BLOCK * sizeof(Particle))); pool_used = 0; }
+        Particle * p = new ((char *)pool_blocks.back() + (pool_used++) * sizeof(Particle)) Particle(std::forward<A>(a)...);
+        p->wf_pooled = true;
+        return p;
+    }
     void not_implemented(const char * what) { throw new Fatal("Domain::%s is not implemented in weldform_b200 (SURVEY.md section 8f, next rows); the shipped configurations use SolveDiffUpdateFraser", what); }
     void ck(int rc, const char * what) { if (rc != 0) throw new Fatal("%s failed (%d) at step %d, time %g: %s", what, rc, (int)steps, Time, wf_last_error(backend)); }
     void backend_begin(double dt);
@@ -202,6 +217,7 @@ private:
     void put3(wf_field f, Vec3_t Particle::*mem, bool subset);
     void put1_if_changed(wf_field f, double Particle::*mem, std::vector<double> & snap, bool subset);
     void refuse_if_changed(const char * what, const std::vector<double> & snap, int nc, bool subset, double (*get)(const Particle *, int));
+    double max_pl_final() { wf_scalars s; ck(wf_reduce(backend, &s), "wf_reduce"); return s.max_pl_strain; }
     void open_history();
     void write_history();
     bool env_stop(size_t idx_out) const { return (max_steps_env >= 0 && (long long)steps >= max_steps_env) || (max_outputs_env >= 0 && (long long)idx_out > max_outputs_env); }
@@ -222,7 +238,8 @@ inline Domain::Domain()
 inline Domain::~Domain()
 {
     bk.destroy(); backend = nullptr;
-    for (size_t i = 0; i < Particles.Size(); ++i) delete Particles[i];       // Domain owns its particles (Source/Domain.cpp:177-181)
+    for (size_t i = 0; i < Particles.Size(); ++i) { if (Particles[i]->wf_pooled) Particles[i]->~Particle(); else delete Particles[i]; }   // Domain owns its particles (Source/Domain.cpp:177-181)
+    for (void * b : pool_blocks) ::operator delete(b);
 }
 
 // Source/Domain.cpp:708-860 (3-D). Points come from the library's generator, mass rule :839-841. ghost = true (:795-826): three mirror rows
@@ -239,7 +256,7 @@ inline void Domain::AddCylinderLength(int tag, Vec3_t const & V, double Rxy, dou
     const size_t first = Particles.Size();
     if (ghost && first != 0) throw new Fatal("AddCylinderLength: ghost rows need the cylinder to be the first particle set (the reference indexes the first rows from particle 0, Source/Domain.cpp:801-806)");
     std::cout << "\n--------------Generating particles by AddCylinderLength with defined length of particles-----------" << std::endl;
-    for (int64_t i = 0; i < n; ++i) Particles.Push(new Particle(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
+    for (int64_t i = 0; i < n; ++i) Particles.Push(pool_make(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
     for (int64_t g = 0; g < npairs; ++g) {
         Particle * P = Particles[pairs[2 * g + 1]];
         P->inner_mirr_part = pairs[2 * g]; P->ghost_plane_axis = 2; P->not_write_surf_ID = true;
@@ -256,7 +273,7 @@ inline void Domain::AddCylinderLength(int tag, Vec3_t const & V, double Rxy, dou
 // Source/Domain.cpp:321-324 (solid_part_count is left alone there; the mirror's upload needs it, so it follows the particle count)
 inline void Domain::AddSingleParticle(int tag, Vec3_t const & x, double Mass, double Density, double h, bool Fixed)
 {
-    Particles.Push(new Particle(tag, x, Vec3_t(0, 0, 0), Mass, Density, h, Fixed));
+    Particles.Push(pool_make(tag, x, Vec3_t(0, 0, 0), Mass, Density, h, Fixed));
     solid_part_count = (int)Particles.Size();
 }
 
@@ -270,7 +287,7 @@ inline void Domain::Add3DCubicBoxParticles(int tag, Vec3_t const & V, double Lx,
     std::vector<double> pts(3 * (size_t)n);
     wf_gen_box(Vd, Lx, Ly, Lz, r, pts.data(), n, dims);
     std::cout << "\n--------------Generating particles by AddBoxLength with defined length of particles-----------" << std::endl;
-    for (int64_t i = 0; i < n; ++i) Particles.Push(new Particle(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, false));
+    for (int64_t i = 0; i < n; ++i) Particles.Push(pool_make(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, false));
     std::cout << "BoxDimensions: " << dims[0] << ", " << dims[1] << ", " << dims[2] << ", " << std::endl;
     Vol += dims[0] * dims[1] * dims[2];
     solid_part_count = (int)Particles.Size();
@@ -331,7 +348,7 @@ inline void Domain::AddTractionProbeLength(int tag, Vec3_t const & V, double Rxy
             int numxpart = detail::calc_half_part_count(r, R, yinc);
             xp = V(0) - r - (2. * r * (numxpart - 1));
             for (int i = 0; i < 2 * numxpart; i++) {
-                Particles.Push(new Particle(tag, Vec3_t(xp, yp, zp), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
+                Particles.Push(pool_make(tag, Vec3_t(xp, yp, zp), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
                 xp += 2. * r;
             }
             yp += 2. * r;
@@ -374,7 +391,7 @@ inline void Domain::AddCylUniformLength(int tag, double Rxy, double Lz, double r
             for (int alphai = 0; alphai < tgcount; alphai++) {
                 xp = ri * cos(alphai * dalpha);
                 yp = ri * sin(alphai * dalpha);
-                Particles.Push(new Particle(tag, Vec3_t(xp, yp, zp), Vec3_t(0, 0, 0), 0.0, Density, h, false));
+                Particles.Push(pool_make(tag, Vec3_t(xp, yp, zp), Vec3_t(0, 0, 0), 0.0, Density, h, false));
             }
         }
         zp += 2.0 * r;
@@ -401,7 +418,7 @@ inline void Domain::AddBoxLength(int tag, Vec3_t const & V, double Lx, double Ly
     wf_gen_box(Vd, Lx, Ly, Lz, r, pts.data(), n, dims);
     const size_t first = Particles.Size();
     std::cout << "\n--------------Generating particles by AddBoxLength with defined length of particles-----------" << std::endl;
-    for (int64_t i = 0; i < n; ++i) Particles.Push(new Particle(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
+    for (int64_t i = 0; i < n; ++i) Particles.Push(pool_make(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
     const double Vol = dims[0] * dims[1] * dims[2];
     const double Mass = Vol * Density / (double)(Particles.Size() - first);
     std::cout << "Total Particle count: " << Particles.Size() << std::endl;
@@ -415,7 +432,7 @@ inline void Domain::AddTrimeshParticles(TriMesh * mesh, const float & hfac, cons
     first_fem_particle_idx.push_back((int)Particles.Size());
     mesh->id = id;
     for (size_t e = 0; e < mesh->element.Size(); ++e) {
-        Particle * p = new Particle(id, mesh->element[e]->centroid, Vec3_t(0, 0, 0), 0.0, 0.0, (double)hfac * mesh->element[e]->radius, false);
+        Particle * p = pool_make(id, mesh->element[e]->centroid, Vec3_t(0, 0, 0), 0.0, 0.0, (double)hfac * mesh->element[e]->radius, false);
         p->normal = mesh->element[e]->normal; p->element = (int)e; p->mesh = meshcount;
         Particles.Push(p);
     }
@@ -525,6 +542,12 @@ inline void Domain::backend_begin(double dt)
         std::vector<double> px(3 * ntot), ph(ntot);          // every particle shapes the cell grid the slabs are cut from, rigid-mesh element particles included
         for (size_t i = 0; i < ntot; ++i) { for (int k = 0; k < 3; ++k) px[3 * i + k] = Particles[i]->x(k); ph[i] = Particles[i]->h; }
         bk.set_particles(wp, px.data(), ph.data(), (int64_t)ntot, (int)KernelType, p.dom_min, p.dom_max);
+    }
+    if (ntot > nsph) {
+        // rigid-mesh element particles: the driver's set-up loop runs over ALL particles (examples/FSW.cpp:180-199 gives the tool's particles
+        // T = 20 like the plate's); the device keeps their temperature for the contact heat conduction term (Contact_Wang.cpp:323-327)
+        std::vector<double> Tall(ntot); for (size_t i = 0; i < ntot; ++i) Tall[i] = Particles[i]->T;
+        bk.upload_all(WF_F_T, 1, false, Tall.data());
     }
     if (GhostPairs.Size() > 0) {                                          // Domain::MoveGhost runs on the device (Mirror_XYZ ghosts)
         std::vector<int32_t> gp(2 * GhostPairs.Size()), ax(GhostPairs.Size());
@@ -864,12 +887,16 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
         }
         if (GeneralBefore) run_callback(GeneralBefore);                          // :238
         bk.phase("wf_fraser_stage_a", wf_fraser_stage_a);                        // :137-312 rebuild policy, density, rates + stress, accel, contact
-        if (GeneralAfter) { refresh_scalars(); run_callback(GeneralAfter); }     // :332
+        // push mode (write-only callbacks): the callback does not wait for the device -- Time is advanced on the host with the device's own
+        // arithmetic (Time += deltat) and the other scalars are as of the last completed step -- so it runs WHILE stage a executes on the GPU
+        if (GeneralAfter) { if (sync_mode != SYNC_PUSH) refresh_scalars(); run_callback(GeneralAfter); }     // :332
         bk.phase("wf_fraser_stage_b1", wf_fraser_stage_b1);                      // :337-343 position update
         bk.phase("wf_fraser_stage_b2", wf_fraser_stage_b2);                      // :352-355 velocity update
         if (GeneralAfter) run_callback(GeneralAfter);                            // :360
         bk.phase("wf_fraser_stage_c", wf_fraser_stage_c);                        // :367-412 heat, energies, time, mesh update, cadence
-        refresh_scalars();
+        // push mode: no device round trip between outputs (the scalars a callback could read are refreshed every 32 steps and before every output)
+        if (sync_mode == SYNC_PUSH && (steps + 1) % 32 != 0 && Time + deltat < tout) { Time += deltat; steps++; bk.steps_hint = (int)steps; }
+        else refresh_scalars();
         if (Time >= tout) {                                                      // :420-499
             wf_scalars s; ck(wf_reduce(backend, &s), "wf_reduce"); max_pl = s.max_pl_strain;
             if (TheFileKey != NULL) { String fn; fn.Printf("%s_%04d", TheFileKey, (int)idx_out); sync_down(true); WriteCSV(fn.CStr()); }
@@ -901,6 +928,8 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
         for (size_t e = 0; e < ne; ++e) { for (int k = 0; k < 3; ++k) tm->element[e]->normal(k) = nrm[3 * e + k]; tm->element[e]->pplane = pp[e]; }
     }
     history_of.close(); prop_of.close();
+    refresh_scalars();
+    std::cout << "Final state: step " << steps << ", time " << Time << ", max displacements " << max_disp << ", max plastic strain " << max_pl_final() << std::endl;
     std::cout << "\n--------------Solving is finished: " << steps << " steps, " << wall_seconds << " s, "
               << (double)solid_part_count * (double)steps / (wall_seconds > 0 ? wall_seconds : 1.0) << " particle-steps/s--------------" << std::endl;
     backend_end();

@@ -38,6 +38,7 @@ public:
     // ---- members some drivers assign that nothing on this path reads (Particle.h:80,83,167): v_max, hfac (smoothing-length update, never
     // called by the new solvers), Et_m (written by CalcStressStrain, read only in commented-out contact code, Contact.cpp:415)
     Vec3_t v_max; double hfac = 0., Et_m = 0., Et = 0.;
+    bool wf_pooled = false;       // allocated from Domain's particle arena (contiguous in creation order) instead of the heap
     double mcp_t = 1.;            // Particle.cpp:149: mass * cp of a rigid-mesh particle; only read where tot_cont_heat_cond is non-zero, which CalcContactForcesWang never makes it (Contact_Wang.cpp:327,347)
 };
 

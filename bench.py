@@ -205,7 +205,7 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------------------------
 # e2e through the reference-style C++ API (weldform_b200/host/Domain.h), one process per mode
 # ---------------------------------------------------------------------------------------------------------------------
-def domain_api_e2e(n_particles, steps, warmup, device, log):
+def domain_api_e2e(n_particles, steps, warmup, device, log, gpus=1, modes=("push", "tagged", "full")):
     from weldform_b200 import build as wfbuild
     exes = wfbuild.build_host_examples()
     exe = [e for e in exes if e.endswith("bench_domain")][0]
@@ -214,7 +214,11 @@ def domain_api_e2e(n_particles, steps, warmup, device, log):
     # bytes moved per step by the bridge (two callbacks per step), from the mirror's own rules (host/Domain.h): full = every particle,
     # tagged = the rows with a BC ID; down: x v a Displacement (3) Sigma (9) T pl_strain Density Pressure Sigmay (1) ID (int); up: v a
     for mode, (k, w) in (("push", (steps, warmup)), ("tagged", (max(3, steps // 4), 2)), ("full", (3, 1))):
-        env = dict(os.environ, WELDFORM_SYNC=mode, WELDFORM_DEVICE=str(device), OMP_NUM_THREADS=str(threads))
+        if mode not in modes:
+            continue
+        env = dict(os.environ, WELDFORM_SYNC=mode, WELDFORM_DEVICE=str(device), WELDFORM_GPUS=str(gpus), OMP_NUM_THREADS=str(threads))
+        for k_ in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k_, None)
         t0 = time.time()
         try:
             r = subprocess.run([exe, str(int(n_particles)), str(k), str(w), str(PERTURB_AMP), str(threads)], capture_output=True, text=True, timeout=1500, env=env)
@@ -234,7 +238,7 @@ def domain_api_e2e(n_particles, steps, warmup, device, log):
         rows = n if mode == "full" else (ntag or 0)
         down = 0 if mode == "push" else 2 * rows * (4 * 24 + 72 + 5 * 8 + 4)
         up = (2 * 2 * 2 * 24) if mode == "push" else 2 * rows * 48
-        out[mode] = {"value": n * k / sec, "ms_per_step": 1e3 * sec / k, "steps": k, "threads": threads, "h2d_bytes_per_step": int(up), "d2h_bytes_per_step": int(down + 3 * 200),
+        out[mode] = {"value": n * k / sec, "ms_per_step": 1e3 * sec / k, "steps": k, "threads": threads, "gpus": gpus, "h2d_bytes_per_step": int(up), "d2h_bytes_per_step": int(down + 3 * 200),
                      "first_timed_step": int(kv["first_step"]), "max_pl_strain": float(kv["max_pl"]), "wall_s_incl_setup": time.time() - t0}
         log("e2e Domain API, WELDFORM_SYNC=%s: %.2f ms/step (%d steps), %.3g particle-steps/s" % (mode, out[mode]["ms_per_step"], k, out[mode]["value"]))
     return out
@@ -341,6 +345,10 @@ def run_ours(args):
         return "%016x%016x" % (int(t[1].item()) & (2 ** 64 - 1), int(t[0].item()) & (2 ** 64 - 1))
     checksum = {"steps": int(s_after.steps), "max_pl_strain_hex": float(s_after.max_pl_strain).hex(),
                 "x": bit_checksum("x"), "pl_strain": bit_checksum("pl_strain"), "T": bit_checksum("T")}
+    if world == 1:
+        tir = np.asarray(ctx.download("TIR")).reshape(-1, 9)[:ctx.n_sph]
+        checksum["tir_nonzero_fraction"] = float(np.count_nonzero(np.abs(tir).max(axis=1) > 0.0)) / max(len(tir), 1)     # particles with a tensile principal stress
+        del tir
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -452,14 +460,6 @@ def run_ours(args):
         path = "wf_fraser_stage_a/b1/b2/c + wf_mesh_set_motion + wf_download_subset (host callback of Contact_Compression_1010: tool velocity, Sigma and a of the first row of %d particles) + wf_reduce" % nt
     e2e = {"value": n_sph * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": ms_e2e / args.steps, "path": path}
-    if e2e_domain and e2e_domain.get("push"):
-        py = e2e
-        hd = e2e_domain["push"]
-        e2e = {"value": hd["value"], "unit": UNIT, "h2d_bytes_per_step": hd["h2d_bytes_per_step"], "d2h_bytes_per_step": hd["d2h_bytes_per_step"], "ms_per_step": hd["ms_per_step"],
-               "path": "C++ SPH::Domain::SolveDiffUpdateFraser of the host mirror (examples/bench_domain.cpp: GeneralAfter loops over Particles[i]->ID on %d host threads, twice per step), "
-                       "WELDFORM_SYNC=push (write-only bridge; uniform v / a of an ID group travel as one vector + a fill kernel), host clock between two wf_sync" % hd["threads"],
-               "modes": e2e_domain, "python_ctypes_push": {"value": py["value"], "ms_per_step": py["ms_per_step"], "h2d_bytes_per_step": py["h2d_bytes_per_step"]}}
-
     # ---- roofline of the dominant kernel, from the CUDA-event pairs recorded on the ctx stream inside the timed region
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -530,6 +530,21 @@ def run_ours(args):
 
     comm_info = ctx.comm_info() if world > 1 else None
     ctx.close()
+    if world > 1 and args.workload == "compression" and not args.python_e2e:
+        # several GPUs: the same C++ driver, ONE process with one host thread and one wf_ctx per GPU (WELDFORM_GPUS, host/Backend.h), started by
+        # rank 0 once every rank of this job has released its GPU; the other ranks wait at the barrier
+        barrier()
+        if rank == 0:
+            e2e_domain = domain_api_e2e(n_target, args.steps, max(args.warmup, 3), 0, log, gpus=world, modes=("push", "tagged"))
+        barrier()
+    if e2e_domain and e2e_domain.get("push") and "value" in e2e_domain["push"]:
+        py = e2e
+        hd = e2e_domain["push"]
+        e2e = {"value": hd["value"], "unit": UNIT, "h2d_bytes_per_step": hd["h2d_bytes_per_step"], "d2h_bytes_per_step": hd["d2h_bytes_per_step"], "ms_per_step": hd["ms_per_step"],
+               "path": "C++ SPH::Domain::SolveDiffUpdateFraser of the host mirror (examples/bench_domain.cpp: GeneralAfter loops over Particles[i]->ID on %d host threads, twice per step), "
+                       "WELDFORM_SYNC=push (write-only bridge; uniform v / a of an ID group travel as one vector + a fill kernel; the callback overlaps the GPU's work), WELDFORM_GPUS=%d, host clock between two wf_sync" % (hd["threads"], hd.get("gpus", 1)),
+               "modes": e2e_domain, "python_ctypes_push": {"value": py["value"], "ms_per_step": py["ms_per_step"], "h2d_bytes_per_step": py["h2d_bytes_per_step"]}}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

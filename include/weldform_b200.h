@@ -65,7 +65,11 @@ typedef struct wf_params {
                                 *   bit 0 no software-pipelined gathers; bits 1-5 momentum-kernel variants (occupancy, general instead of lean
                                 *   kernel, 2 x LDG.128 instead of LDG.256); bits 6-7 post-pass occupancy; bit 8 the multi-GPU layout of the
                                 *   rigid-mesh element particles on one GPU (tests); bit 9 blocking halo refreshes instead of the overlapped
-                                *   ones; bit 13 force one slab-rebalancing move at the third rebuild (tests); bit 14 slab rebalancing off */
+                                *   ones; bit 10 EXACT ARITHMETIC: the pair kernels evaluate every term with the reference's operand order and without FMA
+                                *   contraction everywhere (bit-identical to the reference build; the default uses contracted arithmetic, a few ulp per pair
+                                *   term, on the uniform-h single-class cubic-spline path, wf_pair_fm.cu); bit 11 end-of-step scalar gather in stream order;
+                                *   bit 13 force one slab-rebalancing move at the third rebuild (tests); bit 14 slab rebalancing off; bit 15 keep the
+                                *   Q2 gather in the contracted momentum kernel */
 } wf_params;
 
 /* Material_ subclasses (Source/Material.h:96-224). model: 0 bilinear (no object), 1 Hollomon, 2 Johnson-Cook. */

@@ -11,6 +11,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# The parity suite pins BIT-IDENTITY with the reference wherever it can, so it runs the library in exact-arithmetic mode (wf_params::tuning
+# bit 10) unless a test asks for the default (contracted arithmetic: tests/test_parity_gpu.py::test_contracted_*, tests/test_drivers_gpu.py).
+os.environ.setdefault("WF_TUNING", "1024")          # weldform_b200.harness
+os.environ.setdefault("WELDFORM_TUNING", "1024")    # the C++ host mirror (weldform_b200/host/Domain.h)
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

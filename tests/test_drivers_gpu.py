@@ -56,7 +56,7 @@ def run_mirror_driver(name, sync, max_outputs, needs=(), timeout=1500, extra_env
     d = tempfile.mkdtemp(prefix="mirror_%s_" % name)
     for f in needs:
         shutil.copy(os.path.join(REFDATA, f), os.path.join(d, f))
-    env = dict(os.environ, WELDFORM_SYNC=sync, WELDFORM_MAX_OUTPUTS=str(max_outputs))
+    env = dict(os.environ, WELDFORM_SYNC=sync, WELDFORM_MAX_OUTPUTS=str(max_outputs), WELDFORM_TUNING="0")      # the library's default arithmetic
     env.update(extra_env or {})
     with open(os.path.join(d, "log.txt"), "w") as log:
         r = subprocess.run([exe], cwd=d, stdout=log, stderr=subprocess.STDOUT, env=env, timeout=timeout)
@@ -117,13 +117,13 @@ def compare_history(d, gold, rtol, what=""):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sync", ["full", "tagged"])
-def test_compression_thermal_driver_whole_run(sync):
+@pytest.mark.parametrize("sync,tuning", [("full", "0"), ("tagged", "0"), ("tagged", "1024")])
+def test_compression_thermal_driver_whole_run(sync, tuning):
     """examples/Compression_thermal.cpp, the configuration BASELINE.json's metric is quoted on (12 144 particles as shipped): the whole run,
     2 924 steps with the GeneralAfter callback on host Particle objects twice per step, 106 output tables; six of them are pinned, through
     yield (max plastic strain 0.28 at the end)."""
     gold = np.load(os.path.join(GOLD, "Compression_thermal.npz"))
-    d, rc = run_mirror_driver("Compression_thermal", sync, int(gold["kept"].max()))
+    d, rc = run_mirror_driver("Compression_thermal", sync, int(gold["kept"].max()), extra_env={"WELDFORM_TUNING": tuning})     # 1024: exact arithmetic
     assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
     # printed precision: a unit in the 6th digit is 1e-6 .. 1e-5 relative, and the reference's own 4-thread run differs from its 1-thread run
     # (the golden) by up to 1e-5 in v and a at table 30 and 2.3e-5 at table 106 (summation order); 2e-5 / 1e-4 element-wise

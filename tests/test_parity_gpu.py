@@ -113,7 +113,7 @@ def test_mesh_tail_layout_equals_cell_layout(harness, name):
     matched by k_cont_list_tail) on one GPU: same contact candidate lists in the same order, hence the same bits."""
     case, ref = golden_tools.load(name)
     base = harness.run_case(case)
-    case = dict(case); case["tuning"] = 256.0
+    case = dict(case); case["tuning"] = 256.0 + 1024.0          # + bit 10: exact arithmetic (contact cases never take the contracted kernels, kept explicit)
     tail = harness.run_case(case)
     assert tail["cont_pairs"].size > 0 and np.array_equal(tail["cont_pairs"], base["cont_pairs"])
     bad = [k for k in cases.FIELDS_F64 + ["ID", "Nb", "pairs"] if k in base and not np.array_equal(tail[k], base[k])]
@@ -423,9 +423,10 @@ def test_baseline_scale_digest(harness, name):
     assert not worst, "%s: beyond %.0e (norm) / %.0e (element-wise): %s" % (name, tol, ELEM_FACTOR * tol, worst)
 
 
-# ---- contracted arithmetic (wf_pair_fm.cu, wf_params::tuning bit 10): the pair terms use FMA, one rsqrt per pair and Newton-refined
-# reciprocals instead of the reference's operand-by-operand IEEE sequence. Not bit-identical by construction; held to BASELINE.json's bars.
-FM = 1024.0
+# ---- contracted arithmetic (wf_pair_fm.cu), the library's DEFAULT (wf_params::tuning = 0; the rest of this file runs with bit 10, exact
+# arithmetic, see conftest.py): the pair terms use FMA, one rsqrt per pair and Newton-refined reciprocals instead of the reference's
+# operand-by-operand IEEE sequence. Not bit-identical by construction; held to BASELINE.json's bars.
+FM = 0.0
 
 
 def test_contracted_arithmetic_one_step_12k(harness, oracle_port):

@@ -143,6 +143,21 @@ int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax)
     return 0;
 }
 
+// min / max of a per-rank value over all ranks (e.g. "is the particle mass the same on every rank?")
+int comm_global_minmax(wf_ctx *c, double *mn, double *mx)
+{
+    if (c->comm.nranks <= 1) return 0;
+    NcclApi *A = nccl_api();
+    double h[2] = { -*mn, *mx };
+    WF_CHECK(ensure_stage(c, 256));
+    WF_CUDA(c, cudaMemcpyAsync(c->stage, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    WF_NCCL(c, A->AllReduce(c->stage, c->stage, 2, ncclDouble, ncclMax, (ncclComm_t)c->comm.nccl, c->stream));
+    WF_CUDA(c, cudaMemcpyAsync(h, c->stage, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    *mn = -h[0]; *mx = h[1];
+    return 0;
+}
+
 // CalculateSurface (Domain.cpp:1421-1425) sums the particle masses serially in creation order; with the particles spread over
 // ranks every rank scatters its masses into a zeroed creation-ordered array, the arrays are summed (exact: one non-zero
 // contributor per entry) and each rank repeats the reference's serial sum over the result.

@@ -372,6 +372,9 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         if (i < nsph && p->h[i] != p->h[0]) uni_h = false;
     }
     c->h_uniform = p->h[0];
+    c->mass_min = c->mass_max = nsph > 0 ? p->mass[0] : 0.0;
+    for (int64_t i = 0; i < nsph; ++i) { if (p->mass[i] < c->mass_min) c->mass_min = p->mass[i]; if (p->mass[i] > c->mass_max) c->mass_max = p->mass[i]; }
+    c->uniform_mass = nsph > 0 && c->mass_min == c->mass_max;        // this rank's particles; wf_solver_init completes the check over all ranks
     c->uniform_h = uni_h;                        // over the SPH particles; rigid-mesh particles never enter an SM pair
     WF_CUDA(c, cudaMemcpy(c->Q0[0], q.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
     for (int64_t i = 0; i < n; ++i) {

@@ -110,6 +110,7 @@ struct wf_ctx {
     std::vector<wf::ClassProps> h_classes; wf::ClassProps *d_classes = nullptr; int n_classes = 0;
     std::vector<wf::MatProps> h_mats; wf::MatProps *d_mats = nullptr;
     bool any_ti = false, uniform_h = false, single_class = false, any_fixed = false; double h_uniform = 0.0;
+    bool uniform_mass = false; double mass_min = 0.0, mass_max = 0.0;       // every SPH particle of the DOMAIN has the same mass (lattice generators): the contracted momentum kernel then skips the Q2 gather
     bool dens_valid = false;                     // F_DDN / F_TN hold the coming step's density rate and TIR (set by k_post)
     double totmass_mean = 0.0;                   // CalculateSurface's serial mean mass (Domain.cpp:1421-1425)
     // cell grid (Neighbour.cpp:10-139)
@@ -182,7 +183,6 @@ int nb_cell_initiate(wf_ctx *c);
 int nb_build_impl(wf_ctx *c);
 int nb_gradcorr_fsm(wf_ctx *c);                         // CalcGradCorrMatrix: contributions of the pairs with one fixed particle
 // wf_pair.cu
-bool pair_fm_active(const wf_ctx *c);                  // the contracted-arithmetic pair kernels (wf_pair_fm.cu) serve this configuration
 int pair_gradcorr(wf_ctx *c);
 int pair_tir(wf_ctx *c);
 int pair_temp_inc_pp(wf_ctx *c);                         // CalcTempIncPP: the initial dT/dt of ThermalSolve
@@ -209,6 +209,7 @@ int comm_gather_scalars_on(wf_ctx *c, const double *src, double *dst, int nvals,
 int comm_red_wait(wf_ctx *c);                            // compute stream waits for every end-of-step scalar gather still in flight
 int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);
+int comm_global_minmax(wf_ctx *c, double *mn, double *mx);
 int comm_serial_mass_sum(wf_ctx *c, const double *mass, const int64_t *gidx, int64_t n_local, int64_t n_global, double *tot);
 int comm_plan_layers(wf_ctx *c, const std::vector<long long> &hist);
 int comm_migrate(wf_ctx *c, int64_t *n_sort, int64_t *n_out);

@@ -127,19 +127,13 @@ __constant__ signed char c_walk[27][4] = {
     { 1,-1,-1,0}, { 1, 0,-1,0}, { 1, 1,-1,0}, { 1,-1, 0,0}                     // owner cells with larger q1
 };
 
-// walk_order 2 (contracted-arithmetic pair kernels): the 27 cells in ASCENDING storage order, so that every list comes out sorted by slot.
-// Lanes of a warp are consecutive slots with nearly the same neighbourhood: with sorted lists their n-th entries point into the same few
-// 128-byte lines, and one gathered record per lane costs the L1 about half the wavefronts of the reference's discovery order
-// (profiles/README.md, round 2). The pair SET is the same (same exact cutoff test); only the order of the sums changes.
-struct WalkPerm { signed char e[27]; };
-
 __device__ inline bool is_mesh_id(int id, int4 mids) { return id == mids.x || id == mids.y || id == mids.z || id == mids.w; }
 
 // One thread per particle. Neighbour.cpp:374-417 AllocateNbPair + :361-372 CheckRadius, gather form.
 __global__ void __launch_bounds__(128)
 k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long long *keys, const int *cell_start, const int *cell_end,
           const double4 *__restrict__ Q0, const double4 *__restrict__ Q2, const int *__restrict__ orig, const int *__restrict__ ID,
-          const int *__restrict__ cls_of, const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material, int uniform_h, int walk_order, WalkPerm perm,
+          const int *__restrict__ cls_of, const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material, int uniform_h, int walk_order,
           uint32_t *nbr, int *nb_cnt, int *nb_hi, int *nbI, double *normal_x, double *normal_y, double *normal_z, int *d_maxcnt)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,8 +164,7 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
                 glo[k] = fmax(xi3[k] - lo - eps, 0.0); ghi[k] = fmax(lo + g.CellSize[k] - xi3[k] - eps, 0.0);
             }
             const double lim_c = g.Cellfac * ((qi.w + g.hmax) / 2), thr_c = (lim_c * lim_c) * (1.0 + 1e-9);
-            for (int ee = 0; ee < 27; ++ee) {
-                const int e = (walk_order == 2) ? perm.e[ee] : ee;
+            for (int e = 0; e < 27; ++e) {
                 int d[3] = { c[0] + c_walk[e][0], c[1] + c_walk[e][1], c[2] + c_walk[e][2] };
                 if (d[0] < 0 || d[0] >= g.CellNo[0] || d[1] < 0 || d[1] >= g.CellNo[1] || d[2] < 0 || d[2] >= g.CellNo[2]) continue;
                 double gap2 = 0.0;
@@ -510,17 +503,8 @@ int nb_build_impl(wf_ctx *c)
         const int K = c->nbr_k;
         if ((int64_t)K * cap > c->nbr_alloc) { cudaFree(c->nbr); c->nbr = nullptr; WF_CUDA(c, cudaMalloc(&c->nbr, (size_t)K * cap * sizeof(uint32_t))); c->nbr_alloc = (int64_t)K * cap; }
         WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt, 0, 4 * sizeof(int), st));
-        const int walk = c->prm.grad_kernel_corr ? 1 : ((pair_fm_active(c) && !(c->prm.tuning & 4096)) ? 2 : 0);   // bit 12 of wf_params::tuning: reference order under the contracted kernels too (A/B)
-        WalkPerm perm;
-        {   // the 27 cell offsets of c_walk sorted by storage order (slowest axis first)
-            static const signed char W[27][3] = { {-1,-1,-1}, {-1,0,-1}, {-1,1,-1}, {-1,-1,0}, {-1,0,0}, {0,-1,-1}, {0,0,-1}, {0,1,-1}, {0,-1,0}, {0,0,0}, {1,0,0}, {-1,1,0}, {0,1,0}, {1,1,0},
-                                                  {-1,-1,1}, {0,-1,1}, {1,-1,1}, {-1,0,1}, {0,0,1}, {1,0,1}, {-1,1,1}, {0,1,1}, {1,1,1}, {1,-1,-1}, {1,0,-1}, {1,1,-1}, {1,-1,0} };
-            int key[27];
-            for (int e = 0; e < 27; ++e) { perm.e[e] = (signed char)e; key[e] = (W[e][g.ax[2]] * 3 + W[e][g.ax[1]]) * 3 + W[e][g.ax[0]]; }
-            for (int a_ = 1; a_ < 27; ++a_) for (int b_ = a_; b_ > 0 && key[(int)perm.e[b_ - 1]] > key[(int)perm.e[b_]]; --b_) { const signed char t_ = perm.e[b_]; perm.e[b_] = perm.e[b_ - 1]; perm.e[b_ - 1] = t_; }
-        }
         k_nb_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->cell_start, c->cell_end, c->Q0[c->cur], c->Q2[c->cur], c->Ip(I_ORIG), c->Ip(I_ID),
-            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->uniform_h ? 1 : 0, walk, perm, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
+            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->uniform_h ? 1 : 0, c->prm.grad_kernel_corr ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
         WF_LAUNCH_CHECK(c); c->launches++;
         int mx = 0; WF_CUDA(c, cudaMemcpyAsync(&mx, c->d_maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));
         if (mx <= K) break;

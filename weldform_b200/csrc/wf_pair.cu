@@ -719,6 +719,7 @@ PairArgs make_args(wf_ctx *c)
         f.cpT = cp.cp_T; f.th_exp = cp.th_exp; f.q_source = cp.q_source;
         f.AlphaAvg = (cp.Alpha + cp.Alpha) / 2.0; f.BetaAvg = (cp.Beta + cp.Beta) / 2.0;
         f.AlphaCij = f.AlphaAvg * (0.5 * (cp.Cs + cp.Cs)); f.h2_001 = 0.01 * f.h * f.h;
+        f.mass = c->mass_min; f.uniform_mass = (c->uniform_mass && !(c->prm.tuning & 8192 * 4)) ? 1 : 0;     // tuning bit 15: keep the Q2 gather (A/B)
     }
     a.n = c->n_loc; a.s0 = 0; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
     a.nbr = c->nbr; a.nb_cnt = c->nb_cnt; a.nb_hi = c->nb_hi; a.orig = c->Ip(I_ORIG); a.cls_of = c->Ip(I_CLS); a.is_free = c->any_fixed ? c->Ip(I_FREE) : nullptr;
@@ -735,8 +736,9 @@ inline bool lean_ok(const wf_ctx *c, const PairArgs &a)
     const FastConsts &f = a.fc;
     return a.dim == 3 && f.PresEq == 0 && f.fast_h && (!c->any_ti || (f.TI > 0.0 && f.TIn == 4.0 && f.fast_W0)) && !c->any_fixed;
 }
-// contracted-arithmetic variants (wf_pair_fm.cu): wf_params::tuning bit 10, on the lean FAST path only
-inline bool use_fm(const wf_ctx *c, const PairArgs &a) { return (c->prm.tuning & 1024) && fast_path(c) && lean_ok(c, a) && a.gt == 0; }
+// contracted-arithmetic variants (wf_pair_fm.cu): the default on the lean FAST path; wf_params::tuning bit 10 selects the exact kernels
+// (bit-identical to the reference's arithmetic) there too
+inline bool use_fm(const wf_ctx *c, const PairArgs &a) { return !(c->prm.tuning & 1024) && fast_path(c) && lean_ok(c, a) && a.gt == 0; }
 inline bool use_pf(const wf_ctx *c) { return (c->prm.tuning & 1) == 0; }     // bit 0 of wf_params::tuning switches the software pipeline OFF
 
 } // namespace
@@ -746,15 +748,6 @@ namespace wf {
 #define WF_PAIR_PRECHECK(c) if (!(c)->nbr) return fail((c), WF_ERR_ARG, "pair kernel called before the first neighbour build")
 // launch KERNEL<targs..., PF> with PF = software pipeline on/off; grid of one thread per slot, 128 threads per block
 #define WF_LAUNCH_PF(KERNEL, ...) do { if (pf) KERNEL<__VA_ARGS__, true><<<g, 128, 0, c->stream>>>(a); else KERNEL<__VA_ARGS__, false><<<g, 128, 0, c->stream>>>(a); } while (0)
-
-bool pair_fm_active(const wf_ctx *c)
-{
-    if (!(c->prm.tuning & 1024) || !fast_path(c) || c->prm.gradient_type != 0) return false;
-    wf_ctx *cc = const_cast<wf_ctx *>(c);
-    const bool had = cc->nbr != nullptr; (void)had;
-    PairArgs a = make_args(cc);
-    return lean_ok(c, a);
-}
 
 // CalcGradCorrMatrix (Domain.cpp:1832-1940) on the current neighbour lists
 int pair_gradcorr(wf_ctx *c)

@@ -49,12 +49,16 @@ __device__ __forceinline__ double rsqrt_fm(double x)
 struct NbBuf { double4 q, w; int j; };
 
 // one neighbour of the momentum sum (InteractionAlt.cpp:12-235 for GradientType 0, 3-D cubic spline, uniform h and class, TIn = 4, PresEq 0)
-template <bool TI_ON> __device__ __forceinline__ void accel_term_fm(const PairArgs &a, const NbBuf &nb, const V3 &xi, const V3 &vi, double di,
+// UM: every particle has the mass fc.mass -- m_j is a constant and rho_j = m / (m/rho)_j comes from Q1.w, which is gathered anyway: the Q2
+// record is not read at all (five gathered sectors per neighbour instead of six; the kernel is bound by L1 wavefronts, profiles/README.md)
+template <bool TI_ON, bool UM> __device__ __forceinline__ void accel_term_fm(const PairArgs &a, const NbBuf &nb, const V3 &xi, const V3 &vi, double di,
                                                                      const double4 &s0i, const double4 &s1i, const double4 &s2i, double c4h, double rW,
                                                                      double &ax, double &ay, double &az)
 {
     const int j = nb.j;
-    const double4 q2j = ld256(a.Q2 + j), s0j = ld256(a.S0 + j), s1j = ld256(a.S1 + j);
+    double4 q2j = make_double4(0., 0., 0., 0.);
+    if (!UM) q2j = ld256(a.Q2 + j);
+    const double4 s0j = ld256(a.S0 + j), s1j = ld256(a.S1 + j);
     double4 t2j = make_double4(0., 0., 0., 0.);
     if (TI_ON) t2j = ld256(a.S2 + j);
     const double xx = xi.x - nb.q.x, xy = xi.y - nb.q.y, xz = xi.z - nb.q.z;
@@ -69,14 +73,24 @@ template <bool TI_ON> __device__ __forceinline__ void accel_term_fm(const PairAr
     const double gk1 = fma(2.25, q, -3.0);
     const double gk2 = (-0.75 * t) * (t * (h * inv_r));
     const double gk = (q < 1.0) ? gk1 : ((q < 2.0) ? gk2 : 0.0);
-    const double mj = q2j.x, dj = q2j.y;
+    const double mj = UM ? a.fc.mass : q2j.x;
     // artificial viscosity (InteractionAlt.cpp:72-94): one reciprocal serves MUij = h vx / (r^2 + 0.01 h^2) and the division by the mean density
     double pi = 0.0;
     if (a.fc.AlphaAvg != 0.0 || a.fc.BetaAvg != 0.0) {          // uniform over the launch
-        const double D = r2 + a.fc.h2_001, S = di + dj;
-        const double ip = rcp_fm(D * S);
-        const double MU = (h * vx) * (ip * S);
-        const double p = (MU * fma(a.fc.BetaAvg, MU, a.fc.AlphaCij)) * ((2.0 * ip) * D);
+        const double D = r2 + a.fc.h2_001;
+        double p;
+        if (UM) {
+            // rho_j = m / r_j with r_j = (m/rho)_j: rho_i + rho_j = (rho_i r_j + m) / r_j, so 1 / (D (rho_i r_j + m)) gives both quotients
+            const double rj = nb.w.w, t2 = fma(di, rj, a.fc.mass);
+            const double ip = rcp_fm(D * t2);
+            const double MU = (h * vx) * (ip * t2);
+            p = (MU * fma(a.fc.BetaAvg, MU, a.fc.AlphaCij)) * ((2.0 * rj) * (ip * D));
+        } else {
+            const double S = di + q2j.y;
+            const double ip = rcp_fm(D * S);
+            const double MU = (h * vx) * (ip * S);
+            p = (MU * fma(a.fc.BetaAvg, MU, a.fc.AlphaCij)) * ((2.0 * ip) * D);
+        }
         pi = (vx < 0.0) ? p : 0.0;
     }
     // momentum tensor, GradientType 0 (InteractionAlt.cpp:139): S holds Sigma / rho^2
@@ -100,7 +114,7 @@ template <bool TI_ON> __device__ __forceinline__ void accel_term_fm(const PairAr
     az = fma(gx, mxz, fma(gy, myz, fma(gz, mzz, az)));
 }
 
-template <bool TI_ON, int MB> __global__ void __launch_bounds__(128, MB) k_accel_fm(PairArgs a)
+template <bool TI_ON, int MB, bool UM> __global__ void __launch_bounds__(128, MB) k_accel_fm(PairArgs a)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     if (s >= a.n) return;
@@ -120,11 +134,11 @@ template <bool TI_ON, int MB> __global__ void __launch_bounds__(128, MB) k_accel
     for (int n = 0; n < cnt; n += 2) {
         if (n + 1 < cnt) { B.j = (int)(e & 0x7fffffffu); B.q = ld256(a.Q0 + B.j); B.w = ld256(a.Q1 + B.j); }
         if (n + 2 < cnt) e = row[(int64_t)nb_row(n + 2, nhi, a.K) * a.cap];
-        accel_term_fm<TI_ON>(a, A, xi, vi, di, s0i, s1i, s2i, c4h, rW, ax, ay, az);
+        accel_term_fm<TI_ON, UM>(a, A, xi, vi, di, s0i, s1i, s2i, c4h, rW, ax, ay, az);
         if (n + 1 >= cnt) break;
         if (n + 2 < cnt) { A.j = (int)(e & 0x7fffffffu); A.q = ld256(a.Q0 + A.j); A.w = ld256(a.Q1 + A.j); }
         if (n + 3 < cnt) e = row[(int64_t)nb_row(n + 3, nhi, a.K) * a.cap];
-        accel_term_fm<TI_ON>(a, B, xi, vi, di, s0i, s1i, s2i, c4h, rW, ax, ay, az);
+        accel_term_fm<TI_ON, UM>(a, B, xi, vi, di, s0i, s1i, s2i, c4h, rW, ax, ay, az);
     }
     OWN(F_AX) = ax; OWN(F_AY) = ay; OWN(F_AZ) = az;
 }
@@ -234,8 +248,13 @@ namespace wf {
 int launch_accel_fm(wf_ctx *c, const PairArgs &a, int grid, bool ti_on)
 {
     const bool mb4 = (c->prm.tuning & 16) != 0;
-    if (ti_on) { if (mb4) k_accel_fm<true, 4><<<grid, 128, 0, c->stream>>>(a); else k_accel_fm<true, 3><<<grid, 128, 0, c->stream>>>(a); }
-    else k_accel_fm<false, 4><<<grid, 128, 0, c->stream>>>(a);
+    if (a.fc.uniform_mass) {
+        if (ti_on) { if (mb4) k_accel_fm<true, 4, true><<<grid, 128, 0, c->stream>>>(a); else k_accel_fm<true, 3, true><<<grid, 128, 0, c->stream>>>(a); }
+        else k_accel_fm<false, 4, true><<<grid, 128, 0, c->stream>>>(a);
+    } else {
+        if (ti_on) { if (mb4) k_accel_fm<true, 4, false><<<grid, 128, 0, c->stream>>>(a); else k_accel_fm<true, 3, false><<<grid, 128, 0, c->stream>>>(a); }
+        else k_accel_fm<false, 4, false><<<grid, 128, 0, c->stream>>>(a);
+    }
     return 0;
 }
 

@@ -40,6 +40,7 @@
 #include <iostream>
 #include <map>
 #include <new>
+#include <sys/mman.h>
 #include <utility>
 #include <sstream>
 #include <string>
@@ -198,10 +199,22 @@ private:
 
     // Particles created by the lattice generators live in one arena, contiguous in creation order: a driver's `for (i...) Particles[i]->ID`
     // loop then walks memory with a constant stride instead of chasing ten million heap pointers
+    // (2 MB-aligned blocks advised as transparent huge pages: ten million particles are 11 GB, and with 4 kB pages a stride-1.1-kB walk over them
+    // pays a TLB miss every fourth particle)
     std::vector<void *> pool_blocks; size_t pool_used = 0; static const size_t POOL_BLOCK = 16384;
+    static void * pool_block_alloc()
+    {
+        const size_t huge = (size_t)2 << 20, bytes = ((POOL_BLOCK * sizeof(Particle) + huge - 1) / huge) * huge;
+        void * p = nullptr;
+        if (posix_memalign(&p, huge, bytes) != 0 || !p) throw std::bad_alloc();
+#ifdef MADV_HUGEPAGE
+        madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+        return p;
+    }
     template <typename... A> Particle * pool_make(A && ... a)
     {
-        if (pool_blocks.empty() || pool_used == POOL_BLOCK) { pool_blocks.push_back(::operator new(POOL_BLOCK * sizeof(Particle))); pool_used = 0; }
+        if (pool_blocks.empty() || pool_used == POOL_BLOCK) { pool_blocks.push_back(pool_block_alloc()); pool_used = 0; }
         Particle * p = new ((char *)pool_blocks.back() + (pool_used++) * sizeof(Particle)) Particle(std::forward<A>(a)...);
         p->wf_pooled = true;
         return p;
@@ -239,7 +252,7 @@ inline Domain::~Domain()
 {
     bk.destroy(); backend = nullptr;
     for (size_t i = 0; i < Particles.Size(); ++i) { if (Particles[i]->wf_pooled) Particles[i]->~Particle(); else delete Particles[i]; }   // Domain owns its particles (Source/Domain.cpp:177-181)
-    for (void * b : pool_blocks) ::operator delete(b);
+    for (void * b : pool_blocks) std::free(b);
 }
 
 // Source/Domain.cpp:708-860 (3-D). Points come from the library's generator, mass rule :839-841. ghost = true (:795-826): three mirror rows
@@ -493,6 +506,7 @@ inline void Domain::backend_begin(double dt)
     if (auto_ts_acc && sqrt_h_a != 0.0025) throw new Fatal("Domain::sqrt_h_a = %g: the device time-step criterion uses the reference's default 0.0025 only", sqrt_h_a);
     if (contact && contact_alg != Wang) throw new Fatal("Domain::contact_alg = %d: only CalcContactForcesWang (the default, Source/Domain.cpp:169) is implemented in weldform_b200", contact_alg);
     if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
+    { const char * tn = std::getenv("WELDFORM_TUNING"); if (tn) p.tuning = std::atoi(tn); }      // wf_params::tuning (A/B and test switches of the library)
     p.friction_function = (friction_function == Linear) ? 1 : 0; p.friction_m = friction_m; p.friction_b = friction_b;
     bk.each("wf_set_params", [&](int r) { return wf_set_params(bk.ctx[r], &p); });
     // ---- materials: distinct Material_ objects

@@ -533,10 +533,12 @@ def run_ours(args):
     if world > 1 and args.workload == "compression" and not args.python_e2e:
         # several GPUs: the same C++ driver, ONE process with one host thread and one wf_ctx per GPU (WELDFORM_GPUS, host/Backend.h), started by
         # rank 0 once every rank of this job has released its GPU; the other ranks wait at the barrier
+        # (a CPU-side gloo barrier: an NCCL barrier would keep a spinning kernel on every waiting rank's GPU -- the GPUs the driver is being timed on)
         barrier()
+        cpu_group = dist.new_group(backend="gloo")
         if rank == 0:
             e2e_domain = domain_api_e2e(n_target, args.steps, max(args.warmup, 3), 0, log, gpus=world, modes=("push", "tagged"))
-        barrier()
+        dist.barrier(group=cpu_group)
     if e2e_domain and e2e_domain.get("push") and "value" in e2e_domain["push"]:
         py = e2e
         hd = e2e_domain["push"]

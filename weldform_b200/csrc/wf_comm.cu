@@ -143,6 +143,43 @@ int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax)
     return 0;
 }
 
+// Property classes are deduplicated per rank from that rank's particles, so the same tuple can get different indices on different ranks --
+// and the class index of a HALO particle is read by its neighbours (k_T, Alpha, TI ... of the other particle of a pair). Every rank therefore
+// adopts one table: the union of all ranks' classes in rank order; remap[old local index] = index in the union.
+int comm_unify_classes(wf_ctx *c, std::vector<ClassProps> &cls, std::vector<int> &remap)
+{
+    wf_ctx::Comm &m = c->comm;
+    remap.resize(cls.size()); for (size_t k = 0; k < cls.size(); ++k) remap[k] = (int)k;
+    if (m.nranks <= 1) return 0;
+    static_assert(sizeof(ClassProps) % sizeof(double) == 0, "ClassProps travels as doubles");
+    const int MAXC = 256, per = (int)(sizeof(ClassProps) / sizeof(double)), rec = 1 + MAXC * per;
+    if ((int)cls.size() > MAXC) return fail(c, WF_ERR_UNSUPPORTED, "more than %d distinct per-particle property tuples on one rank of a multi-GPU run", MAXC);
+    NcclApi *A = nccl_api();
+    std::vector<double> snd((size_t)rec, 0.0), all((size_t)rec * m.nranks);
+    snd[0] = (double)cls.size();
+    if (!cls.empty()) std::memcpy(&snd[1], cls.data(), cls.size() * sizeof(ClassProps));
+    double *d_s = nullptr, *d_r = nullptr;
+    WF_CUDA(c, cudaMalloc(&d_s, snd.size() * sizeof(double))); WF_CUDA(c, cudaMalloc(&d_r, all.size() * sizeof(double)));
+    WF_CUDA(c, cudaMemcpyAsync(d_s, snd.data(), snd.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    WF_NCCL(c, A->AllGather(d_s, d_r, (size_t)rec, ncclDouble, (ncclComm_t)m.nccl, c->stream));
+    WF_CUDA(c, cudaMemcpyAsync(all.data(), d_r, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d_s); cudaFree(d_r);
+    std::vector<ClassProps> uni;
+    for (int r = 0; r < m.nranks; ++r) {
+        const double *b = &all[(size_t)r * rec]; const int nr = (int)b[0];
+        for (int k = 0; k < nr; ++k) {
+            ClassProps cp; std::memcpy(&cp, b + 1 + (size_t)k * per, sizeof(cp));
+            int found = -1;
+            for (size_t u = 0; u < uni.size() && found < 0; ++u) if (std::memcmp(&uni[u], &cp, sizeof(cp)) == 0) found = (int)u;
+            if (found < 0) { found = (int)uni.size(); uni.push_back(cp); }
+            if (r == m.rank) remap[(size_t)k] = found;
+        }
+    }
+    cls.swap(uni);
+    return 0;
+}
+
 // min / max of a per-rank value over all ranks (e.g. "is the particle mass the same on every rank?")
 int comm_global_minmax(wf_ctx *c, double *mn, double *mx)
 {

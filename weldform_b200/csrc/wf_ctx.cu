@@ -301,6 +301,12 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
         }
         cls_of[i] = id;
     }
+    if (multi) {          // several GPUs: the union of all ranks' classes, same indices everywhere
+        std::vector<int> remap;
+        WF_CHECK(comm_unify_classes(c, c->h_classes, remap));
+        for (int64_t i = 0; i < nsph; ++i) cls_of[i] = remap[cls_of[i]];
+        c->any_ti = false; for (const ClassProps &cp : c->h_classes) if (cp.TI > 0.0) c->any_ti = true;
+    }
     int mesh_class = -1;
     if (nmeshp > 0) {     // rigid-mesh particles: Particle ctor defaults with Density = 0 (Contact.cpp:15-27)
         ClassProps cp; std::memset(&cp, 0, sizeof(cp)); cp.TIn = 4.0; cp.mat_id = -1; cp.IsMesh = 1;

@@ -475,7 +475,10 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     cudaSetDevice(c->device);
     if (c->n_ghost > 0 && c->comm.nranks > 1) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles on more than one GPU are not implemented");
     if (c->n_ghost > 0 && c->prm.solver == 3) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles in ThermalSolve: the reference's loop never calls MoveGhost; not implemented");
-    if (c->comm.nranks > 1) { double mn = c->mass_min, mx = c->mass_max; WF_CHECK(comm_global_minmax(c, &mn, &mx)); c->uniform_mass = (mn == mx); c->mass_min = mn; c->mass_max = mx; }
+    if (c->comm.nranks > 1) {         // "uniform over the particles" must mean over the DOMAIN: halo neighbours come from other ranks
+        double mn = c->mass_min, mx = c->mass_max; WF_CHECK(comm_global_minmax(c, &mn, &mx)); c->uniform_mass = (mn == mx); c->mass_min = mn; c->mass_max = mx;
+        double hn = c->uniform_h ? c->h_uniform : 0.0, hx = c->uniform_h ? c->h_uniform : 1.0e300; WF_CHECK(comm_global_minmax(c, &hn, &hx)); c->uniform_h = (hn == hx);
+    }
     c->dt_init = c->dt_min = dt;
     c->dt = dt; c->time = 0.0; c->ts_i = 0; c->isfirst = true; c->isyielding = false; c->steps = 0; c->dens_valid = false; c->in_step = false;
     WF_CUDA(c, cudaMemsetAsync(c->d_sc, 0, sizeof(DevScalars), c->stream));      // a second wf_solver_init starts from zeroed energy / work accumulators like the first

@@ -12,7 +12,7 @@ import json
 import subprocess
 import sys
 
-FAMILY = {"k_accel": "accel", "k_rate_stress": "rate_stress", "k_post": "post"}
+FAMILY = {"k_accel": "accel", "k_rate": "rate_stress", "k_post": "post"}
 
 
 def main():
@@ -34,8 +34,13 @@ def main():
             rec[op] = float(r[idx["smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op]].replace(",", "")) * cyc
         rec["pipe_fp64_pct"] = float(r[idx["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]].replace(",", ""))
         rec["ms"] = float(r[idx["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(rows[1][idx["gpu__time_duration.sum"]], 1.0)
+        rec["dram_bytes_per_launch"] = (float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(rows[1][idx["dram__bytes_read.sum"]], 1.0) +
+                                        float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(rows[1][idx["dram__bytes_write.sum"]], 1.0))
         out[fam] = rec                      # last captured launch of the family
     json.dump(out, open(out_path, "w"), indent=1)
+    if len(sys.argv) > 4:                   # profiles/traffic.json: measured DRAM bytes per launch, the `traffic` key of bench.py's roofline
+        json.dump({fam: {"particles": particles, "dram_bytes_per_launch": rec["dram_bytes_per_launch"], "source": "%s %s: dram__bytes_read.sum + dram__bytes_write.sum" % (rec["report"], rec["kernel"])}
+                   for fam, rec in out.items()}, open(sys.argv[4], "w"), indent=1)
     for fam, rec in out.items():
         print("%-12s %s: dadd %.3g dmul %.3g dfma %.3g -> %.0f flop/particle, FP64 pipe %.1f %%, %.2f ms" %
               (fam, rec["kernel"], rec["dadd"], rec["dmul"], rec["dfma"], (rec["dadd"] + rec["dmul"] + 2 * rec["dfma"]) / particles, rec["pipe_fp64_pct"], rec["ms"]))

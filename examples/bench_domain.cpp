@@ -4,7 +4,7 @@
 // domi.Particles[i]->ID exactly like the reference's drivers do (examples/Compression_thermal.cpp:30-66), twice per step, on host Particle
 // objects; the callback bridge (WELDFORM_SYNC = full | tagged | push) moves the particle data between host and device inside the timed region.
 //
-//   usage: bench_domain <particles> <steps> <warmup> [perturb_amp = 30] [callback threads = 16]
+//   usage: bench_domain <particles> <steps> <warmup> [perturb_amp = 30] [callback threads = 16] [spin-up: 1 (default) wait until the body yields, 0 time from step 2]
 // prints one line:  BENCH particles=<n> steps=<k> seconds=<s> first_step=<i> sync=<mode> max_pl=<..>
 #include <cstdio>
 #include <omp.h>
@@ -61,6 +61,7 @@ int main(int argc, char ** argv) try
     dom.thermal_solver = true; dom.pl_heating = true; dom.pl_work_heat_frac = 0.9; dom.auto_ts = false;
     const double timestep = 0.2 * h / Cs;
     dom.bench_steps = steps; dom.bench_warmup = warmup;
+    if (argc > 6 && std::atoi(argv[6]) == 0) { dom.bench_spin_min = 2; dom.bench_wait_yield = false; }
     dom.SolveDiffUpdateFraser(1.0e30, timestep, 1.e30, NULL, 1000000);
     double max_pl = 0.0; for (size_t i = 0; i < dom.Particles.Size(); ++i) if (dom.Particles[i]->pl_strain > max_pl) max_pl = dom.Particles[i]->pl_strain;
     const char * m = std::getenv("WELDFORM_SYNC");

@@ -529,7 +529,12 @@ int nb_build_impl(wf_ctx *c)
                 1, c->solver_ready ? 1 : 0, c->cont, c->cont_cnt, c->d_maxcnt + 2);
             WF_LAUNCH_CHECK(c); c->launches++;
             int mx[2] = { 0, 0 }; WF_CUDA(c, cudaMemcpyAsync(mx, c->d_maxcnt + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));
-            if (mx[0] == 0) return fail(c, WF_ERR_ARG, "ERROR: No external particles found. Please check particle masses (Domain.cpp:1489)");
+            if (attempt == 0) {   // the reference counts the surface particles of the whole domain (Domain.cpp:1489); a slab may well own none. Every
+                // rank takes the same decision (once per build: the retries below are rank-local), so that none is left waiting in the next collective.
+                double lo = (double)mx[0], hi = (double)mx[0];
+                WF_CHECK(comm_global_minmax(c, &lo, &hi));
+                if (hi == 0.0) return fail(c, WF_ERR_ARG, "ERROR: No external particles found. Please check particle masses (Domain.cpp:1489)");
+            }
             if (mx[1] <= K) break;
             c->cont_k = ((mx[1] + 7) / 8) * 8;
             if (attempt == 3) return fail(c, WF_ERR_NOMEM, "contact candidate list did not fit after regrowing (max count %d)", mx[1]);

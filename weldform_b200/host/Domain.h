@@ -178,7 +178,7 @@ public:
     // benchmark hook of the Fraser loop (bench.py's e2e leg, examples/bench_domain.cpp): once the body yields (the rebuild cadence is then the
     // reference's every-ts_nb_inc-steps one) and at least bench_spin_min steps have run, bench_warmup untimed steps, then bench_steps steps
     // timed on the host clock between two wf_sync calls -> bench_seconds; the loop ends there. bench_steps = 0: no effect.
-    size_t bench_steps = 0, bench_warmup = 0, bench_spin_min = 20; double bench_seconds = 0.0; size_t bench_first_step = 0; bool isyielding = false;
+    size_t bench_steps = 0, bench_warmup = 0, bench_spin_min = 20; double bench_seconds = 0.0; size_t bench_first_step = 0; bool isyielding = false, bench_wait_yield = true;
 
 private:
     double Time = 0.0;
@@ -895,7 +895,7 @@ inline void Domain::SolveDiffUpdateFraser(double tf, double dt, double dtOut, ch
     int bench_state = 0; size_t bench_mark = 0; std::chrono::steady_clock::time_point bench_t0;
     while (Time <= tf && idx_out <= maxidx && !env_stop(idx_out)) {
         if (bench_steps > 0) {
-            if (bench_state == 0 && isyielding && steps >= bench_spin_min) { bench_state = 1; bench_mark = steps + bench_warmup; }
+            if (bench_state == 0 && (isyielding || !bench_wait_yield) && steps >= bench_spin_min) { bench_state = 1; bench_mark = steps + bench_warmup; }
             if (bench_state == 1 && steps == bench_mark) { bk.phase("wf_sync", wf_sync); bench_t0 = std::chrono::steady_clock::now(); bench_state = 2; bench_first_step = steps; bench_mark = steps + bench_steps; }
             else if (bench_state == 2 && steps == bench_mark) { bk.phase("wf_sync", wf_sync); bench_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - bench_t0).count(); break; }
         }

@@ -315,6 +315,13 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     }
     c->n_classes = (int)c->h_classes.size();
     c->single_class = (c->n_classes - (nmeshp > 0 ? 1 : 0)) == 1;
+    c->pair_uniform = c->n_classes > (nmeshp > 0 ? 1 : 0);
+    for (int k = 1; k < c->n_classes && c->pair_uniform; ++k) {
+        const ClassProps &a0 = c->h_classes[0], &b = c->h_classes[k];
+        if (b.IsMesh) continue;
+        if (b.Cs != a0.Cs || b.PresEq != a0.PresEq || b.RefDensity != a0.RefDensity || b.Alpha != a0.Alpha || b.Beta != a0.Beta || b.TI != a0.TI || b.TIn != a0.TIn ||
+            b.TIInitDist != a0.TIInitDist || b.k_T != a0.k_T || b.Material != a0.Material) c->pair_uniform = false;
+    }
     WF_CUDA(c, cudaMalloc(&c->d_classes, c->n_classes * sizeof(ClassProps)));
     WF_CUDA(c, cudaMemcpy(c->d_classes, c->h_classes.data(), c->n_classes * sizeof(ClassProps), cudaMemcpyHostToDevice));
 

@@ -110,6 +110,8 @@ struct wf_ctx {
     std::vector<wf::ClassProps> h_classes; wf::ClassProps *d_classes = nullptr; int n_classes = 0;
     std::vector<wf::MatProps> h_mats; wf::MatProps *d_mats = nullptr;
     bool any_ti = false, uniform_h = false, single_class = false, any_fixed = false; double h_uniform = 0.0;
+    bool pair_uniform = false;                   // every SPH class has the same PAIR-relevant constants (Cs, PresEq, RefDensity, Alpha, Beta, TI, TIn, TIInitDist, k_T, Material):
+                                                 // classes then differ in own-particle properties only (cp_T, h_conv, T_inf, Thermal_BC, G, hardening ...), e.g. FSW's convection rows
     bool uniform_mass = false; double mass_min = 0.0, mass_max = 0.0;       // every SPH particle of the DOMAIN has the same mass (lattice generators): the contracted momentum kernel then skips the Q2 gather
     bool dens_valid = false;                     // F_DDN / F_TN hold the coming step's density rate and TIR (set by k_post)
     double totmass_mean = 0.0;                   // CalculateSurface's serial mean mass (Domain.cpp:1421-1425)

@@ -606,7 +606,8 @@ template <bool FAST, bool THERM, bool EKIN, bool DENS, bool PF, int MB = 4> __gl
     const double hi = FAST ? a.fc.h : qi.w, C4i = FAST ? a.fc.C4 : c4_of(hi), di = q2i.y, Ti = q2i.z, mi = q2i.x, Pi2 = q2i.w, midi = wi.w;
     const int ci = FAST ? 0 : a.cls_of[s];
     struct { double k_T, cp_T, th_exp, q_source, TI; } cpi;
-    if (FAST) { cpi.k_T = a.fc.kT; cpi.cp_T = a.fc.cpT; cpi.th_exp = a.fc.th_exp; cpi.q_source = a.fc.q_source; cpi.TI = a.fc.TI; }
+    if (FAST) { cpi.k_T = a.fc.kT; cpi.cp_T = a.fc.cpT; cpi.th_exp = a.fc.th_exp; cpi.q_source = a.fc.q_source; cpi.TI = a.fc.TI;
+                if (!a.fc.own_uniform) { const ClassProps cp0 = a.cls[a.cls_of[s]]; cpi.cp_T = cp0.cp_T; cpi.th_exp = cp0.th_exp; cpi.q_source = cp0.q_source; } }
     else { const ClassProps cp0 = a.cls[ci]; cpi.k_T = cp0.k_T; cpi.cp_T = cp0.cp_T; cpi.th_exp = cp0.th_exp; cpi.q_source = cp0.q_source; cpi.TI = cp0.TI; }
     const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
     const DivC dh = FAST ? divc_from(a.fc.h, a.fc.inv_h, a.fc.fast_h) : divc_make(hi), dkk = FAST ? divc_from(a.fc.ksum, a.fc.inv_ksum, a.fc.fast_k) : divc_make(cpi.k_T + cpi.k_T);
@@ -705,7 +706,8 @@ inline int divc_ok(double b)
     const unsigned ex = (unsigned)((bits >> 52) & 0x7ff);
     return ((bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull) && ex > 200 && ex < 1800;
 }
-inline bool fast_path(const wf_ctx *c) { return c->prm.kernel_type == 0 && c->prm.dimension == 3 && c->uniform_h && c->single_class && !c->prm.grad_kernel_corr; }
+// FAST path: 3-D cubic spline, uniform h, and classes that agree in every constant a PAIR term reads (own-particle properties may differ)
+inline bool fast_path(const wf_ctx *c) { return c->prm.kernel_type == 0 && c->prm.dimension == 3 && c->uniform_h && c->pair_uniform && !c->prm.grad_kernel_corr; }
 
 PairArgs make_args(wf_ctx *c)
 {
@@ -719,6 +721,7 @@ PairArgs make_args(wf_ctx *c)
         f.cpT = cp.cp_T; f.th_exp = cp.th_exp; f.q_source = cp.q_source;
         f.AlphaAvg = (cp.Alpha + cp.Alpha) / 2.0; f.BetaAvg = (cp.Beta + cp.Beta) / 2.0;
         f.AlphaCij = f.AlphaAvg * (0.5 * (cp.Cs + cp.Cs)); f.h2_001 = 0.01 * f.h * f.h;
+        f.own_uniform = c->single_class ? 1 : 0;
         f.mass = c->mass_min; f.uniform_mass = (c->uniform_mass && !(c->prm.tuning & 8192 * 4)) ? 1 : 0;     // tuning bit 15: keep the Q2 gather (A/B)
     }
     a.n = c->n_loc; a.s0 = 0; a.cap = c->cap; a.nsph = (int)c->nsph; a.K = c->nbr_k; a.dim = c->prm.dimension; a.kt = c->prm.kernel_type; a.gt = c->prm.gradient_type;
@@ -734,7 +737,8 @@ PairArgs make_args(wf_ctx *c)
 inline bool lean_ok(const wf_ctx *c, const PairArgs &a)
 {
     const FastConsts &f = a.fc;
-    return a.dim == 3 && f.PresEq == 0 && f.fast_h && (!c->any_ti || (f.TI > 0.0 && f.TIn == 4.0 && f.fast_W0)) && !c->any_fixed;
+    // fixed particles keep an empty list and are in nobody's (wf_neighbour.cu): the pair walk needs no special case for them
+    return a.dim == 3 && f.PresEq == 0 && f.fast_h && (!c->any_ti || (f.TI > 0.0 && f.TIn == 4.0 && f.fast_W0));
 }
 // contracted-arithmetic variants (wf_pair_fm.cu): the default on the lean FAST path; wf_params::tuning bit 10 selects the exact kernels
 // (bit-identical to the reference's arithmetic) there too

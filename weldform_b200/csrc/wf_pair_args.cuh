@@ -11,6 +11,7 @@ struct FastConsts {
     double h, C3, C4, inv_h, W0, inv_W0, Alpha, Beta, TI, TIn, TId, Cs, RefDensity, kT, kk, ksum, inv_ksum, cpT, th_exp, q_source;
     double AlphaAvg, BetaAvg, AlphaCij, h2_001;    // lean momentum kernel: (Alpha+Alpha)/2, (Beta+Beta)/2, AlphaAvg*(0.5*(Cs+Cs)), 0.01*h*h
     int PresEq, fast_h, fast_W0, fast_k;
+    int own_uniform;                                // one class: cp_T, th_exp, q_source of the particle itself are fc's; 0: read them from the particle's class
     double mass; int uniform_mass;                  // every particle of the domain has this mass (0: read m_j from Q2)
 };
 struct PairArgs {

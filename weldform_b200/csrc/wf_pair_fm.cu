@@ -226,11 +226,13 @@ template <bool THERM, bool EKIN, bool DENS> __global__ void __launch_bounds__(12
         if (EKIN) dk = fma((ifirst ? (0.5 * q2j.x) : (-0.5 * mi)) * (Pi2 + q2j.w), gvx, dk);
     }
     if (THERM) {
-        const double f = 1. / (di * a.fc.cpT);
-        double dTdt = f * (temp + OWN(F_QCONV) + a.fc.q_source + OWN(F_QPL) * a.pl_work_heat_frac + OWN(F_QCONT));
+        double cpT = a.fc.cpT, th_exp = a.fc.th_exp, q_source = a.fc.q_source;
+        if (!a.fc.own_uniform) { const ClassProps cp0 = a.cls[a.cls_of[s]]; cpT = cp0.cp_T; th_exp = cp0.th_exp; q_source = cp0.q_source; }
+        const double f = 1. / (di * cpT);
+        double dTdt = f * (temp + OWN(F_QCONV) + q_source + OWN(F_QPL) * a.pl_work_heat_frac + OWN(F_QCONT));
         if (a.contact && a.cont_heat_fric) dTdt += f * OWN(F_QFRIC);
         OWN(F_DTDT) = dTdt;
-        const double te = a.fc.th_exp * dTdt;                  // CalcThermalExpStrainRate (Particle.cpp:953-957)
+        const double te = th_exp * dTdt;                       // CalcThermalExpStrainRate (Particle.cpp:953-957)
         OWN(F_SR) = OWN(F_SR) + te; OWN(F_SR + 1) = OWN(F_SR + 1) + te; OWN(F_SR + 2) = OWN(F_SR + 2) + te;
     }
     if (EKIN) {

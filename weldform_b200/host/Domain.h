@@ -212,13 +212,36 @@ private:
 #endif
         return p;
     }
+    // one arena for a whole lattice whose size the generator knows, FIRST TOUCHED IN PARALLEL with the static partition the callbacks' own
+    // `omp parallel for schedule(static)` loops use: on a two-socket host each thread's share of the particles then sits in its own socket's memory
+    char * pool_arena = nullptr; size_t pool_arena_cap = 0, pool_arena_used = 0;
+    void pool_reserve(size_t n)
+    {
+        if (n < 65536 || pool_arena_cap - pool_arena_used >= n) return;
+        const size_t huge = (size_t)2 << 20, bytes = ((n * sizeof(Particle) + huge - 1) / huge) * huge;
+        void * p = nullptr;
+        if (posix_memalign(&p, huge, bytes) != 0 || !p) return;
+#ifdef MADV_HUGEPAGE
+        madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+        char * base = (char *)p;
+        WF_HOST_PARALLEL_FOR
+        for (size_t k = 0; k < n; ++k) std::memset(base + k * sizeof(Particle), 0, sizeof(Particle));
+        pool_blocks.push_back(p); pool_arena = base; pool_arena_cap = n; pool_arena_used = 0;
+    }
     template <typename... A> Particle * pool_make(A && ... a)
     {
-        if (pool_blocks.empty() || pool_used == POOL_BLOCK) { pool_blocks.push_back(pool_block_alloc()); pool_used = 0; }
-        Particle * p = new ((char *)pool_blocks.back() + (pool_used++) * sizeof(Particle)) Particle(std::forward<A>(a)...);
+        void * at;
+        if (pool_arena_used < pool_arena_cap) at = pool_arena + (pool_arena_used++) * sizeof(Particle);
+        else {
+            if (pool_small == nullptr || pool_used == POOL_BLOCK) { pool_small = (char *)pool_block_alloc(); pool_blocks.push_back(pool_small); pool_used = 0; }
+            at = pool_small + (pool_used++) * sizeof(Particle);
+        }
+        Particle * p = new (at) Particle(std::forward<A>(a)...);
         p->wf_pooled = true;
         return p;
     }
+    char * pool_small = nullptr;
     void not_implemented(const char * what) { throw new Fatal("Domain::%s is not implemented in weldform_b200 (SURVEY.md section 8f, next rows); the shipped configurations use SolveDiffUpdateFraser", what); }
     void ck(int rc, const char * what) { if (rc != 0) throw new Fatal("%s failed (%d) at step %d, time %g: %s", what, rc, (int)steps, Time, wf_last_error(backend)); }
     void backend_begin(double dt);
@@ -269,6 +292,7 @@ inline void Domain::AddCylinderLength(int tag, Vec3_t const & V, double Rxy, dou
     const size_t first = Particles.Size();
     if (ghost && first != 0) throw new Fatal("AddCylinderLength: ghost rows need the cylinder to be the first particle set (the reference indexes the first rows from particle 0, Source/Domain.cpp:801-806)");
     std::cout << "\n--------------Generating particles by AddCylinderLength with defined length of particles-----------" << std::endl;
+    pool_reserve((size_t)n);
     for (int64_t i = 0; i < n; ++i) Particles.Push(pool_make(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
     for (int64_t g = 0; g < npairs; ++g) {
         Particle * P = Particles[pairs[2 * g + 1]];
@@ -431,6 +455,7 @@ inline void Domain::AddBoxLength(int tag, Vec3_t const & V, double Lx, double Ly
     wf_gen_box(Vd, Lx, Ly, Lz, r, pts.data(), n, dims);
     const size_t first = Particles.Size();
     std::cout << "\n--------------Generating particles by AddBoxLength with defined length of particles-----------" << std::endl;
+    pool_reserve((size_t)n);
     for (int64_t i = 0; i < n; ++i) Particles.Push(pool_make(tag, Vec3_t(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
     const double Vol = dims[0] * dims[1] * dims[2];
     const double Mass = Vol * Density / (double)(Particles.Size() - first);

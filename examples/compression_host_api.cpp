@@ -6,7 +6,7 @@
 //
 //   usage: compression_host_api <dx> <nsteps> <perturb_amp> <out.bin> [solver: 0 Fraser (default), 1 KickDrift, 2 LeapFrog,
 //          3 ThermalSolve (heat conduction only, time step 0.05 s)] [ghost: 1 = AddCylinderLength(..., ghost = true), the bottom rows are
-//          then left free and the mirror rows below the bottom plane hold the body (Domain::MoveGhost)]
+//          then left free and the mirror rows below the bottom plane hold the body (Domain::MoveGhost)] [pin_T: 1 = the callback also assigns T = 100 to the top rows]
 // out.bin: int64 n, then n*(x[3], v[3], Displacement[3], pl_strain, T, Density, Sigma[9]) as float64 (creation order).
 #include <cstdio>
 #include "Domain.h"
@@ -18,12 +18,14 @@
 #define TAU  0.005
 #define VMAX 10.0
 
+static bool pin_T = false;        // argv[7] = 1: the callback also holds the top rows at 100 degrees (a Dirichlet temperature through the bridge)
+
 void UserAcc(SPH::Domain & domi)
 {
     const double t = domi.getTime();
     const double f = t < TAU ? t / TAU : 1.0;
     for (size_t i = 0; i < domi.Particles.Size(); i++) {
-        if (domi.Particles[i]->ID == 3) { domi.Particles[i]->a = Vec3_t(0.0, 0.0, 0.0); domi.Particles[i]->v = Vec3_t(0.0 * f, 0.0 * f, -VMAX * f); }
+        if (domi.Particles[i]->ID == 3) { domi.Particles[i]->a = Vec3_t(0.0, 0.0, 0.0); domi.Particles[i]->v = Vec3_t(0.0 * f, 0.0 * f, -VMAX * f); if (pin_T) domi.Particles[i]->T = 100.0; }
         if (domi.Particles[i]->ID == 2) { domi.Particles[i]->a = Vec3_t(0.0, 0.0, 0.0); domi.Particles[i]->v = Vec3_t(0.0, 0.0, 0.0); }
     }
 }
@@ -39,6 +41,7 @@ int main(int argc, char ** argv) try
     dom.GeneralAfter = &UserAcc;
     dom.DomMax(0) = L; dom.DomMin(0) = -L;
     const bool ghost = argc > 6 && std::atoi(argv[6]) != 0;
+    pin_T = argc > 7 && std::atoi(argv[7]) != 0;
     dom.AddCylinderLength(1, Vec3_t(0., 0., -L / 10.), R, L + 2. * L / 10., dx / 2., rho, h, false, ghost);
     for (size_t a = 0; a < dom.Particles.Size(); a++) {
         SPH::Particle * P = dom.Particles[a];

@@ -190,3 +190,24 @@ def test_host_domain_ghost_rows_match_device_run_and_oracle(host_example, oracle
     assert ref["pl_strain"].max() > 1e-3
     worst = {k: ot.max_rel(got[k], ref[k]) for k in got}
     assert max(worst.values()) < 1e-6, worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sync", ["full", "tagged"])
+def test_callback_that_pins_temperature_reaches_the_device(host_example, sync):
+    """A GeneralAfter callback may assign more than v and a: a Dirichlet temperature (T = 100 on the top rows, every call). The bridge uploads
+    every member the device accepts when the callback changed it (host/Domain.h sync_up), so the rows stay hot and heat their neighbours;
+    before round 2 only v and a went back and the assignment was dropped silently."""
+    dx, nsteps, amp = 0.03, 60, 0.0
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "o.bin")
+        r = subprocess.run([host_example, str(dx), str(nsteps), str(amp), out, "0", "0", "1"], capture_output=True, text=True, timeout=600, env=dict(os.environ, WELDFORM_SYNC=sync))
+        assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+        got = _read_bin(out)
+    z = got["x"].reshape(-1, 3)[:, 2]
+    T = got["T"]
+    top = z > 0.56
+    assert top.sum() > 50
+    assert np.abs(T[top] - 100.0).max() < 1.0, "the pinned rows are at %.2f .. %.2f" % (T[top].min(), T[top].max())
+    below = (z > 0.56 - 0.07) & ~top
+    assert (T[below] - (20.0 + 15.0 * np.sin(7.0 * got["x"].reshape(-1, 3)[below, 0]) * np.cos(5.0 * z[below]))).max() > 1e-3, "conduction from the pinned rows must heat the rows below"

@@ -83,7 +83,7 @@ extern "C" void wf_destroy(wf_ctx *c)
         cudaFree(c->F[b]); cudaFree(c->I[b]); cudaFree(c->keys[b]); cudaFree(c->vals[b]);
     }
     cudaFree(c->slot_of); cudaFree(c->d_classes); cudaFree(c->d_mats); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->mcell_start); cudaFree(c->mcell_end);
-    cudaFree(c->cub_tmp); cudaFree(c->nbr); cudaFree(c->nbr_tent); cudaFree(c->nb_cnt); cudaFree(c->nb_hi); cudaFree(c->d_maxcnt);
+    cudaFree(c->cub_tmp); cudaFree(c->nbr); cudaFree(c->nb_cnt); cudaFree(c->nb_hi); cudaFree(c->d_maxcnt);
     cudaFree(c->cont); cudaFree(c->cont_cnt); cudaFree(c->d_mesh_ids); cudaFree(c->d_bcs); cudaFree(c->d_sc); cudaFree(c->d_partial); cudaFree(c->d_mf_part); cudaFree(c->d_mf_flag);
     cudaFree(c->dm.node); cudaFree(c->dm.node_v); cudaFree(c->dm.en); cudaFree(c->dm.nfar); cudaFree(c->dm.emesh);
     cudaFree(c->dm.enormal); cudaFree(c->dm.ev); cudaFree(c->dm.pplane); cudaFree(c->dm.motion);

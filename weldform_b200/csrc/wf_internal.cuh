@@ -124,7 +124,6 @@ struct wf_ctx {
     void *cub_tmp = nullptr; size_t cub_tmp_bytes = 0;
     // neighbour lists (ELL, transposed): nbr[k*cap + slot]; bit31 = "slot is temp1 (first) of the reference pair"
     uint32_t *nbr = nullptr; int nbr_k = 0; int64_t nbr_alloc = 0;
-    uint32_t *nbr_tent = nullptr;               // tentative lists of the build (same shape): survivors of the squared-distance sweep, before the exact test
     int *nb_cnt = nullptr, *nb_hi = nullptr, *d_maxcnt = nullptr;
     // contact candidate lists: cont[k*cap + slot] = global element index
     int *cont = nullptr; int cont_k = 0; int64_t cont_alloc = 0; int *cont_cnt = nullptr;

@@ -134,13 +134,13 @@ __global__ void __launch_bounds__(128)
 k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long long *keys, const int *cell_start, const int *cell_end,
           const double4 *__restrict__ Q0, const double4 *__restrict__ Q2, const int *__restrict__ orig, const int *__restrict__ ID,
           const int *__restrict__ cls_of, const int *__restrict__ is_free, const ClassProps *__restrict__ classes, int contact, int4 mids, int check_material, int uniform_h, int walk_order,
-          uint32_t *nbr, uint32_t *tent, int *nb_cnt, int *nb_hi, int *nbI, double *normal_x, double *normal_y, double *normal_z, int *d_maxcnt)
+          uint32_t *nbr, int *nb_cnt, int *nb_hi, int *nbI, double *normal_x, double *normal_y, double *normal_z, int *d_maxcnt)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int total = 0;
     if (s < n) {
         const int oi = orig[s];
-        int nhi = 0, nlo = 0, ntent = 0;
+        int nhi = 0, nlo = 0;
         double nx = 0.0, ny = 0.0, nz = 0.0;
         bool active = oi < nsph;
         if (active && contact && is_mesh_id(ID[s], mids)) active = false;
@@ -189,27 +189,16 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
                         if (!uniform_h) { const double hh = (qi.w + qj.w) / 2, lim = g.Cellfac * hh; thr = (lim * lim) * (1.0 + 8e-15); }
                         if (!(d2 > thr)) mask |= 1u << k;
                     }
-                    // survivors go to a tentative list (slot index + the pair role of their cell, in discovery order); the exact test and the
-                    // list update run afterwards over that list, where every lane of the warp has about the same number of entries. Doing them
-                    // here costs popcount(mask) iterations per cell PER LANE: 147 iterations per warp with 12 of 32 lanes active (ncu, round 2).
                     while (mask) {
                         const int j = base + (__ffs(mask) - 1); mask &= mask - 1u;
                         if (j == (int)s) continue;
-                        const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;      // own cell: particles stored before s have a larger creation index and act as temp1
-                        if (ntent < K) tent[(int64_t)ntent * cap + s] = (uint32_t)j | (ifirst ? 0x80000000u : 0u);
-                        ++ntent;
-                    }
-                }
-            }
-            const int nt = min(ntent, K);
-            for (int t = 0; t < nt; ++t) {
-                        const uint32_t te = tent[(int64_t)t * cap + s];
-                        const int j = (int)(te & 0x7fffffffu), ifirst = (int)(te >> 31);
                         const int oj = orig[j];
                         if (oj >= nsph) continue;                               // rigid-mesh particle: never an SM pair
                         if (contact && is_mesh_id(ID[j], mids)) continue;
                         if (is_free && !is_free[j]) continue;
                         const double4 qj = Q0[j];
+                        // own cell: particles stored before s have a larger creation index and act as temp1
+                        const int ifirst = (role == 2) ? (j > (int)s ? 1 : 0) : role;
                         const double hh = (qi.w + qj.w) / 2;
                         const V3 xj = v3(qj.x, qj.y, qj.z);
                         const V3 xij = ifirst ? (xi - xj) : (xj - xi);
@@ -231,8 +220,9 @@ k_nb_list(Grid g, int64_t n, int64_t cap, int nsph, int K, const unsigned long l
                             if (ifirst) { nx += mj * xij.x; ny += mj * xij.y; nz += mj * xij.z; }
                             else        { nx -= mj * xij.x; ny -= mj * xij.y; nz -= mj * xij.z; }
                         }
+                    }
+                }
             }
-            if (ntent > K) { nhi = ntent; nlo = 0; }      // the tentative list overflowed: report its size so that the host regrows K and repeats the build
         }
         total = nhi + nlo;
         nb_cnt[s] = total; nb_hi[s] = nhi; nbI[s] = total;
@@ -511,11 +501,10 @@ int nb_build_impl(wf_ctx *c)
     for (int attempt = 0; attempt < 4; ++attempt) {
         ProfScope ps(c, PK_NB_LIST);
         const int K = c->nbr_k;
-        if ((int64_t)K * cap > c->nbr_alloc) { cudaFree(c->nbr); cudaFree(c->nbr_tent); c->nbr = nullptr; c->nbr_tent = nullptr; WF_CUDA(c, cudaMalloc(&c->nbr, (size_t)K * cap * sizeof(uint32_t)));
-                                                WF_CUDA(c, cudaMalloc(&c->nbr_tent, (size_t)K * cap * sizeof(uint32_t))); c->nbr_alloc = (int64_t)K * cap; }
+        if ((int64_t)K * cap > c->nbr_alloc) { cudaFree(c->nbr); c->nbr = nullptr; WF_CUDA(c, cudaMalloc(&c->nbr, (size_t)K * cap * sizeof(uint32_t))); c->nbr_alloc = (int64_t)K * cap; }
         WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt, 0, 4 * sizeof(int), st));
         k_nb_list<<<grid_for(n, 128), 128, 0, st>>>(g, n, cap, (int)c->nsph, K, c->keys[1], c->cell_start, c->cell_end, c->Q0[c->cur], c->Q2[c->cur], c->Ip(I_ORIG), c->Ip(I_ID),
-            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->uniform_h ? 1 : 0, c->prm.grad_kernel_corr ? 1 : 0, c->nbr, c->nbr_tent, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
+            c->Ip(I_CLS), c->any_fixed ? c->Ip(I_FREE) : nullptr, c->d_classes, c->prm.contact ? 1 : 0, mids, check_material ? 1 : 0, c->uniform_h ? 1 : 0, c->prm.grad_kernel_corr ? 1 : 0, c->nbr, c->nb_cnt, c->nb_hi, c->Ip(I_NB), c->Fp(F_NX), c->Fp(F_NY), c->Fp(F_NZ), c->d_maxcnt);
         WF_LAUNCH_CHECK(c); c->launches++;
         int mx = 0; WF_CUDA(c, cudaMemcpyAsync(&mx, c->d_maxcnt, sizeof(int), cudaMemcpyDeviceToHost, st)); WF_CUDA(c, cudaStreamSynchronize(st));
         if (mx <= K) break;

@@ -257,6 +257,12 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
     const int64_t nsph_global = (multi && p->n_sph_global > 0) ? p->n_sph_global : nsph;
     if (nsph_global + nmeshp >= (int64_t)1 << 31) return fail(c, WF_ERR_UNSUPPORTED, "more than 2^31-1 particles per domain");
     if (multi && !p->global_index) return fail(c, WF_ERR_ARG, "wf_set_particles: global_index is required when nranks > 1");
+    if (multi) {          // validate before anything is allocated or recorded in the context: a failed call leaves it as it was and can be repeated
+        for (int64_t i = 0; i < nsph; ++i) {
+            if (p->global_index[i] < 0 || p->global_index[i] >= nsph_global) return fail(c, WF_ERR_ARG, "global_index[%lld] out of range", (long long)i);
+            if (i > 0 && p->global_index[i] <= p->global_index[i - 1]) return fail(c, WF_ERR_ARG, "global_index must be strictly ascending");
+        }
+    }
     c->any_fixed = false;
     if (p->is_free) for (int64_t i = 0; i < nsph; ++i) if (!p->is_free[i]) { c->any_fixed = true; break; }
     c->n = n; c->n_loc = n; c->nsph = nsph_global; c->nmeshp = nmeshp;

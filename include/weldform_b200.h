@@ -149,8 +149,9 @@ int wf_set_params(wf_ctx *ctx, const wf_params *p);
 int wf_set_materials(wf_ctx *ctx, const wf_material *m, int n);
 int wf_set_particles(wf_ctx *ctx, const wf_particles *p);
 /* Domain::GhostPairs (Domain.h:473) for Domain::MoveGhost (Domain.cpp:1142-1236), ghost_type Mirror_XYZ: n x (inner, ghost) creation indices,
- * axis = ghost_plane_axis per pair (NULL: 2, what AddCylinderLength creates). After wf_set_particles, before wf_solver_init; one GPU only.
- * The Symmetric-plane ghosts of AddCylSliceLength are not implemented. */
+ * axis = ghost_plane_axis per pair (NULL: 2, what AddCylinderLength creates). After wf_set_particles, before wf_solver_init. On several GPUs every
+ * rank is given ALL pairs (creation indices of the whole domain); a ghost and the particle it mirrors must end up on the same rank (they do unless the
+ * mirror plane crosses a slab boundary), otherwise the neighbour build fails on every rank. The Symmetric-plane ghosts of AddCylSliceLength are not implemented. */
 int wf_set_ghost_pairs(wf_ctx *ctx, const int32_t *pairs, const int32_t *axis, int64_t n);
 int wf_add_mesh(wf_ctx *ctx, const wf_mesh *m);                       /* AddTrimeshParticles */
 int wf_mesh_set_motion(wf_ctx *ctx, int mesh, const double v[3], const double w[3]);   /* TriMesh::SetVel / SetRotAxisVel */

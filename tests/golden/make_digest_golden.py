@@ -3,6 +3,7 @@ BASELINE.json's configurations are stated on -- too large to commit as full dump
 
     compression_50k_40     examples/Compression.cpp's scale (dx = 0.0094 -> ~49 k particles), 40 Fraser steps through yield
     compression_1m_3       Compression_thermal at 1 M particles (dx = 0.00362), 3 steps
+    contact_2m_5           the cylinder between two rigid planes at 2 M particles (Contact_Compression_1010's scale), 5 steps with contact forces
 
 Run in the build container only:   python tests/golden/make_digest_golden.py [name ...]
 
@@ -22,10 +23,13 @@ from tests import cases, oracle_tools as ot  # noqa: E402
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "digest")
 SAMPLE_ROWS = 10000
-SAMPLE_FIELDS = ["x", "v", "a", "Displacement", "Density", "Pressure", "pl_strain", "T", "Sigmay", "dTdt", "Sigma", "StrainRate"]
+SAMPLE_FIELDS = ["x", "v", "a", "Displacement", "Density", "Pressure", "pl_strain", "T", "Sigmay", "dTdt", "Sigma", "StrainRate", "contforce", "delta_cont", "normal"]
 SPECS = {
     "compression_50k_40": dict(dx=0.0094, nsteps=40, perturb_amp=150.0),
     "compression_1m_3": dict(dx=0.00362, nsteps=3, perturb_amp=60.0),
+    # BASELINE configs[2] at its stated scale: 2 M particles between two rigid planes (penalty contact, friction 0.2); the velocity field drives the
+    # end rows INTO the planes so that contact forces act from the second step on
+    "contact_2m_5": dict(dx=0.0028744663089468095, nsteps=5, perturb_amp=-60.0, contact_planes=1.0),
 }
 
 
@@ -50,6 +54,7 @@ def digest_of(dump, n):
     out["Nb_rows"] = np.asarray(dump["Nb"])[:n][idx].astype(np.int32)
     out["ID_rows"] = np.asarray(dump["ID"])[:n][idx].astype(np.int32)
     out["pairs"] = np.array(dump["pairs"].size // 2 if "pairs" in dump else -1)
+    out["cont_pairs"] = np.array(dump["cont_pairs"].size // 2 if "cont_pairs" in dump else 0)
     for k in cases.SCALARS:
         if k in dump:
             out["scalar/" + k] = np.asarray(dump[k], dtype=np.float64)
@@ -65,7 +70,7 @@ def main():
         if only and name not in only:
             continue
         t0 = time.time()
-        case = cases.compression_fast(**spec)
+        case = cases.compression_fast(**{k: (bool(v) if k == "contact_planes" else v) for k, v in spec.items()})
         ref = ot.run_ref(case, nproc=1, timeout=6 * 3600)
         n = int(ref["solid_part_count"][0])
         dg = digest_of(ref, n)

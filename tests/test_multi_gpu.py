@@ -214,8 +214,8 @@ def test_multi_gpu_rebalance_moves_a_layer_and_keeps_every_bit(product_lib, orac
 
 @pytest.mark.gpu
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("sync,amp,nsteps", [("full", 60.0, 40), ("tagged", 400.0, 100), ("push", 400.0, 100)])
-def test_host_mirror_on_two_gpus_bit_identical_to_one(product_lib, sync, amp, nsteps):
+@pytest.mark.parametrize("sync,amp,nsteps,ghost", [("full", 60.0, 40, 0), ("tagged", 400.0, 100, 0), ("push", 400.0, 100, 0), ("tagged", 60.0, 40, 1)])
+def test_host_mirror_on_two_gpus_bit_identical_to_one(product_lib, sync, amp, nsteps, ghost):
     """The C++ host mirror of SPH::Domain on WELDFORM_GPUS=2 (one process, one host thread and one wf_ctx per GPU, host/Backend.h): the driver's
     GeneralAfter callback works on the GLOBAL Particles array while the particles live on two slabs and migrate between them at the rebuilds
     (amp = 400 m/s); every field of the final state is bit-identical to the same driver on one GPU."""
@@ -225,7 +225,7 @@ def test_host_mirror_on_two_gpus_bit_identical_to_one(product_lib, sync, amp, ns
     with tempfile.TemporaryDirectory() as d:
         for gpus in (1, 2):
             out = os.path.join(d, "o%d.bin" % gpus)
-            r = subprocess.run([exe, "0.02", str(nsteps), str(amp), out, "0"], capture_output=True, text=True, timeout=900,
+            r = subprocess.run([exe, "0.02", str(nsteps), str(amp), out, "0", str(ghost)], capture_output=True, text=True, timeout=900,
                                env=dict(os.environ, WELDFORM_SYNC=sync, WELDFORM_GPUS=str(gpus)))
             assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
             raw = np.fromfile(out, dtype=np.uint8)
@@ -237,12 +237,14 @@ def test_host_mirror_on_two_gpus_bit_identical_to_one(product_lib, sync, amp, ns
 
 @pytest.mark.gpu
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("name", ["plate_cubic_40", "plate_quintic_10", "fsw_like_80", "thermal_solve_25", "thermal_solve_gc_20"])
+@pytest.mark.parametrize("name", ["plate_cubic_40", "plate_quintic_10", "fsw_like_80", "thermal_solve_25", "thermal_solve_gc_20", "ghost_comp_yield_40", "ghost_lf_25"])
 def test_multi_gpu_plate_and_fsw_goldens(product_lib, name):
     """BASELINE configs 4 and 5 in small: the Plate-Yield_3d lattice (AddBoxLength, slabs along x; cubic and quintic-spline kernels) and the
     FSW-like set-up (Johnson-Cook, convection BC, FIXED side walls, rotating + plunging tool, friction heat) on two GPUs: bit-identical per
     particle to one GPU and within the golden bar of the reference's own dump. Domain::ThermalSolve (conduction only, one neighbour search, with
-    and without corrected gradients) rides along: its halo refresh points are those of the post pass."""
+    and without corrected gradients) rides along: its halo refresh points are those of the post pass. So do the ghost (symmetry) rows of
+    AddCylinderLength(..., ghost = true) with Domain::MoveGhost in the Fraser and LeapFrog loops: every rank holds all GhostPairs and serves
+    the pairs whose ghost it owns (wf_step.cu ghost_localize)."""
     from tests import golden_tools
     from weldform_b200 import harness
     case, ref = golden_tools.load(name)

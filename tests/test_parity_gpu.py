@@ -382,7 +382,7 @@ def test_ghost_rows_with_gradient_correction(harness, oracle_port, solver):
     _compare(got, ref, 1e-7, what="ghost + gradKernelCorr, solver %d" % solver)
 
 
-@pytest.mark.parametrize("name", ["compression_50k_40", "compression_1m_3"])
+@pytest.mark.parametrize("name", ["compression_50k_40", "compression_1m_3", "contact_2m_5"])
 def test_baseline_scale_digest(harness, name):
     """Parity at the sizes BASELINE.json's configurations are stated on: digests of the UNMODIFIED reference solver's own runs
     (tests/golden/make_digest_golden.py: ~49 k particles x 40 steps through yield, 1.0 M particles x 3 steps) against the CUDA path on the
@@ -391,15 +391,21 @@ def test_baseline_scale_digest(harness, name):
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "digest", name + ".npz"))
     spec = {k: float(v) for k, v in zip(z["spec_keys"].tolist(), z["spec_vals"].tolist())}
     spec["nsteps"] = int(spec["nsteps"])
+    if "contact_planes" in spec:
+        spec["contact_planes"] = bool(spec["contact_planes"])
     case = cases.compression_fast(**spec)
     got = harness.run_case(case)
     n = int(z["n"])
     assert int(got["solid_part_count"][0]) == n
     dg = mdg.digest_of(got, n)
     assert int(dg["pairs"]) == int(z["pairs"]) and int(dg["Nb_sum"]) == int(z["Nb_sum"])
+    if "cont_pairs" in z.files:
+        assert int(dg["cont_pairs"]) == int(z["cont_pairs"]), "contact candidate pairs: %d, the reference has %d" % (int(dg["cont_pairs"]), int(z["cont_pairs"]))
     assert np.array_equal(dg["Nb_rows"], z["Nb_rows"]) and np.array_equal(dg["ID_rows"], z["ID_rows"])
     # measured on a B200 (profiles/r2_v1_parity_report.jsonl): 1.0e-16 (1 M x 3 steps) and 3.3e-14 (49 k x 40 steps through yield) in the field norm
     tol = 1e-14 if spec["nsteps"] <= 3 else 1e-12
+    if "contact_planes" in spec:
+        tol = 1e-12
     worst, report = {}, {}
     for k in z.files:
         if k.startswith("rows/"):

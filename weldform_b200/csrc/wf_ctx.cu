@@ -89,7 +89,7 @@ extern "C" void wf_destroy(wf_ctx *c)
     cudaFree(c->dm.enormal); cudaFree(c->dm.ev); cudaFree(c->dm.pplane); cudaFree(c->dm.motion);
     cudaFree(c->comm.d_emig); cudaFree(c->comm.d_cnt); cudaFree(c->comm.d_rank); cudaFree(c->comm.d_all);
     for (int d = 0; d < 2; ++d) { cudaFree(c->comm.stage_send[d]); cudaFree(c->comm.stage_recv[d]); }
-    cudaFree(c->d_ghost);
+    cudaFree(c->d_ghost); cudaFree(c->d_ghost_loc);
     for (auto &sb : c->subsets) cudaFree(sb.first);
     cudaFree(c->stage); if (c->h_stage) cudaFreeHost(c->h_stage); if (c->h_sc) cudaFreeHost(c->h_sc);
     prof_resolve(c); for (auto &e : c->prof_free) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -830,7 +830,6 @@ extern "C" int wf_set_ghost_pairs(wf_ctx *c, const int32_t *pairs, const int32_t
     if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: call wf_set_particles first");
     if (c->solver_ready) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: the solver is already initialised");
     if (n < 0 || (n > 0 && !pairs)) return fail(c, WF_ERR_ARG, "wf_set_ghost_pairs: bad arguments");
-    if (c->comm.nranks > 1 && n > 0) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles on more than one GPU are not implemented");
     cudaSetDevice(c->device);
     std::vector<int> rec((size_t)3 * n);
     std::vector<char> is_ghost((size_t)c->nsph, 0);

@@ -144,6 +144,7 @@ struct wf_ctx {
     double dt = 0.0, time = 0.0; int ts_i = 0; bool isfirst = true, isyielding = false, nb_cleared = true;
     int64_t steps = 0, nb_rebuilds = 0, launches = 0; bool in_step = false;
     double step_max_pl = 0.0;                    // `max` of SolverFraser.cpp:139-149 for the step in flight
+    int *d_ghost_loc = nullptr; bool ghost_loc_valid = false;   // several GPUs: the pairs as LOCAL indices of this rank (-1: not here), refreshed at every neighbour build
     int *d_ghost = nullptr; int64_t n_ghost = 0;         // Domain::GhostPairs (Domain.h:473) as (inner, ghost, ghost_plane_axis) creation indices, Mirror_XYZ ghosts
     std::vector<std::pair<int *, int64_t> > subsets;     // registered index lists of the callback bridge (device copies)
     // staging
@@ -223,6 +224,7 @@ int step_begin_impl(wf_ctx *c);
 int contact_impl(wf_ctx *c);
 int apply_bcs_impl(wf_ctx *c);
 int move_ghost_impl(wf_ctx *c);                          // Domain::MoveGhost; no-op without ghost pairs
+int ghost_localize(wf_ctx *c);                           // several GPUs: ghost pairs -> this rank's local indices (after comm_local_index)
 int move_pos_impl(wf_ctx *c);
 int move_vel_impl(wf_ctx *c);
 int step_end_impl(wf_ctx *c);

@@ -486,6 +486,7 @@ int nb_build_impl(wf_ctx *c)
         if (c->n > c->n_loc) { MigArgs off = mg; off.on = 0; off.mesh_tail = 0;
             k_cell_keys<<<grid_for(c->n - c->n_loc, B), B, 0, st>>>(g, c->Q0[c->cur], c->Ip(I_ORIG), c->n - c->n_loc, c->n_loc, c->keys[1], c->vals[0], off); WF_LAUNCH_CHECK(c); c->launches++; }
         WF_CHECK(comm_local_index(c));
+        WF_CHECK(ghost_localize(c));                  // ghost pairs as local indices of the particles this rank holds now
     }
     {   ProfScope ps(c, PK_NB_CELLS);
         WF_CUDA(c, cudaMemsetAsync(c->cell_start, 0, c->ncells * sizeof(int), st)); WF_CUDA(c, cudaMemsetAsync(c->cell_end, 0, c->ncells * sizeof(int), st));

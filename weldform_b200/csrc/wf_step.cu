@@ -61,10 +61,29 @@ __global__ void k_bc_move(StepArgs a, int mode)
 // (creation indices -> slots through slot_of); inner particles are never ghosts, so the pairs are independent. The gathered caches that
 // derive from the density (m/rho in Q1.w, P/rho^2 in Q2.w, with the ghost's own mass and pressure) follow the copy; Sigma/rho^2 (S0, S1)
 // is rewritten by the ghost's own stress update before any momentum sum reads it.
+// Several GPUs: a pair is handled by the rank that owns the GHOST; its inner particle must live on the same rank (the mirror rows and their partners
+// sit within three rows of a plane, i.e. inside one slab unless the plane runs along the slab axis through a slab boundary). gp holds creation indices;
+// out receives local indices (position in the rank's ascending creation-index order = the index space of slot_of), -1 where the particle is not local.
+__global__ void k_ghost_localize(const int *gp, int64_t npairs, int64_t n_loc, const int *slot_of, const int *orig, int *out, int *flag)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= npairs) return;
+    int lid[2];
+    for (int m = 0; m < 2; ++m) {
+        const int target = gp[3 * g + m];
+        int64_t lo = 0, hi = n_loc;
+        while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (orig[slot_of[mid]] < target) lo = mid + 1; else hi = mid; }
+        lid[m] = (lo < n_loc && orig[slot_of[lo]] == target) ? (int)lo : -1;
+    }
+    out[3 * g] = lid[0]; out[3 * g + 1] = lid[1]; out[3 * g + 2] = gp[3 * g + 2];
+    if (lid[1] >= 0 && lid[0] < 0) atomicExch(flag, 1);
+}
+
 __global__ void k_move_ghost(StepArgs a, const int *gp, int64_t npairs, const int *slot_of)
 {
     int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= npairs) return;
+    if (gp[3 * g + 1] < 0) return;                   // several GPUs: the ghost of this pair lives on another rank
     const int64_t si = slot_of[gp[3 * g]], s = slot_of[gp[3 * g + 1]];
     const int axis = gp[3 * g + 2];
 #define INNER(f) a.F[(int64_t)(f) * a.cap + si]
@@ -402,8 +421,23 @@ int move_ghost_impl(wf_ctx *c)
     if (c->n_ghost == 0) return 0;
     ProfScope ps(c, PK_MOVE);
     StepArgs a = make_step_args(c);
-    k_move_ghost<<<grid_for(c->n_ghost, 128), 128, 0, c->stream>>>(a, c->d_ghost, c->n_ghost, c->slot_of); WF_LAUNCH_CHECK(c); c->launches++;
+    const int *pairs = c->d_ghost;
+    if (c->comm.nranks > 1) { if (!c->ghost_loc_valid) WF_CHECK(ghost_localize(c)); pairs = c->d_ghost_loc; }
+    k_move_ghost<<<grid_for(c->n_ghost, 128), 128, 0, c->stream>>>(a, pairs, c->n_ghost, c->slot_of); WF_LAUNCH_CHECK(c); c->launches++;
     c->dens_valid = false;
+    return 0;
+}
+int ghost_localize(wf_ctx *c)
+{
+    if (c->n_ghost == 0 || c->comm.nranks <= 1) return 0;
+    if (!c->d_ghost_loc) WF_CUDA(c, cudaMalloc(&c->d_ghost_loc, (size_t)3 * c->n_ghost * sizeof(int)));
+    WF_CUDA(c, cudaMemsetAsync(c->d_maxcnt + 3, 0, sizeof(int), c->stream));
+    k_ghost_localize<<<grid_for(c->n_ghost, 128), 128, 0, c->stream>>>(c->d_ghost, c->n_ghost, c->n_loc, c->slot_of, c->Ip(I_ORIG), c->d_ghost_loc, c->d_maxcnt + 3); WF_LAUNCH_CHECK(c); c->launches++;
+    int bad = 0; WF_CUDA(c, cudaMemcpyAsync(&bad, c->d_maxcnt + 3, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); WF_CUDA(c, cudaStreamSynchronize(c->stream));
+    // every rank takes the same decision (a rank that stopped alone would leave the others waiting in the next halo exchange)
+    double lo = (double)bad, hi = (double)bad; WF_CHECK(comm_global_minmax(c, &lo, &hi));
+    if (hi != 0.0) return fail(c, WF_ERR_UNSUPPORTED, "a ghost (symmetry) particle and the inner particle it mirrors live on different GPUs: the mirror plane crosses a slab boundary");
+    c->ghost_loc_valid = true;
     return 0;
 }
 
@@ -473,7 +507,6 @@ extern "C" int wf_solver_init(wf_ctx *c, double dt)
     if (!c->have_particles) return fail(c, WF_ERR_ARG, "wf_solver_init: no particles");
     if (!(dt > 0.0)) return fail(c, WF_ERR_ARG, "wf_solver_init: dt must be > 0");
     cudaSetDevice(c->device);
-    if (c->n_ghost > 0 && c->comm.nranks > 1) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles on more than one GPU are not implemented");
     if (c->n_ghost > 0 && c->prm.solver == 3) return fail(c, WF_ERR_UNSUPPORTED, "ghost (symmetry) particles in ThermalSolve: the reference's loop never calls MoveGhost; not implemented");
     if (c->comm.nranks > 1) {         // "uniform over the particles" must mean over the DOMAIN: halo neighbours come from other ranks
         double mn = c->mass_min, mx = c->mass_max; WF_CHECK(comm_global_minmax(c, &mn, &mx)); c->uniform_mass = (mn == mx); c->mass_min = mn; c->mass_max = mx;

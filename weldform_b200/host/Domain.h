@@ -515,7 +515,6 @@ inline void Domain::choose_sync()
 inline void Domain::backend_begin(double dt)
 {
     bk.create(device, gpus); backend = bk.c0();
-    if (gpus > 1 && GhostPairs.Size() > 0) throw new Fatal("weldform_b200: ghost (symmetry) rows run on one GPU only (WELDFORM_GPUS = %d)", gpus);
     const size_t ntot = Particles.Size();
     const size_t nsph = !first_fem_particle_idx.empty() ? (size_t)first_fem_particle_idx[0] : ntot;
     if (nsph == 0) throw new Fatal("Domain: no particles");
@@ -591,7 +590,7 @@ inline void Domain::backend_begin(double dt)
     if (GhostPairs.Size() > 0) {                                          // Domain::MoveGhost runs on the device (Mirror_XYZ ghosts)
         std::vector<int32_t> gp(2 * GhostPairs.Size()), ax(GhostPairs.Size());
         for (size_t g = 0; g < GhostPairs.Size(); ++g) { gp[2 * g] = (int32_t)GhostPairs[g].first; gp[2 * g + 1] = (int32_t)GhostPairs[g].second; ax[g] = Particles[GhostPairs[g].second]->ghost_plane_axis; }
-        ck(wf_set_ghost_pairs(backend, gp.data(), ax.data(), (int64_t)GhostPairs.Size()), "wf_set_ghost_pairs");
+        bk.each("wf_set_ghost_pairs", [&](int r) { return wf_set_ghost_pairs(bk.ctx[r], gp.data(), ax.data(), (int64_t)GhostPairs.Size()); });    // every rank gets every pair
     }
     sent_mv.assign(trimesh.size(), Vec3_t(0.)); sent_mw.assign(trimesh.size(), Vec3_t(0.));
     forward_mesh_motion();

@@ -72,11 +72,12 @@ typedef struct wf_params {
                                 *   Q2 gather in the contracted momentum kernel */
 } wf_params;
 
-/* Material_ subclasses (Source/Material.h:96-224). model: 0 bilinear (no object), 1 Hollomon, 2 Johnson-Cook. */
+/* Material_ subclasses (Source/Material.h:96-224). model: 0 bilinear (no object), 1 Hollomon, 2 Johnson-Cook, 3 GMT (Material.cpp:96-161). */
 typedef struct wf_material {
     int    model;
     double E, nu;
-    double p[13];              /* Hollomon: sy0, K, m.  Johnson-Cook: A, B, n, C, eps_0, m, T_m, T_t */
+    double p[16];              /* Hollomon: sy0, K, m.  Johnson-Cook: A, B, n, C, eps_0, m, T_m, T_t.
+                                * GMT: n1, n2, C1, C2, m1, m2, I1, I2, e_min, e_max, er_min, er_max, T_min, T_max (the constructor's argument order) */
 } wf_material;
 
 /* Initial particle set, creation order, n = n_sph + total mesh particles. NULL pointers take the value the reference's

@@ -157,6 +157,10 @@ int main(int argc, char ** argv) try
             int model = (int)mt[r];
             if (model == HOLLOMON) mats.push_back(new Hollomon(*el, mt[r + 3], mt[r + 4], mt[r + 5]));
             else if (model == JOHNSON_COOK) mats.push_back(new JohnsonCook(*el, mt[r + 3], mt[r + 4], mt[r + 5], mt[r + 6], mt[r + 7], mt[r + 8], mt[r + 9], mt[r + 10]));
+            else if (model == _GMT_) {       // GMT(el, n1, n2, C1, C2, m1, m2, I1, I2, e_min, e_max, er_min, er_max, T_min, T_max): p0..p12 + materials_ext (p13)
+                const double tmax = in.has("materials_ext") ? in.f("materials_ext")[(r / 16) * 3] : 1.0e10;
+                mats.push_back(new GMT(*el, mt[r + 3], mt[r + 4], mt[r + 5], mt[r + 6], mt[r + 7], mt[r + 8], mt[r + 9], mt[r + 10], mt[r + 11], mt[r + 12], mt[r + 13], mt[r + 14], mt[r + 15], tmax));
+            }
             else mats.push_back(new Material_(*el));
         }
     }

@@ -184,8 +184,8 @@ void sym_eig3(M3 a, double d[3], M3 & v)
 }
 
 // ---- materials (Source/Material.cpp:6-73) ---------------------------------------------------------------------
-struct Mat { int model; double E, nu; double p[13]; double eps0, eps1; };
-enum { BILINEAR = 0, HOLLOMON = 1, JOHNSON_COOK = 2 };
+struct Mat { int model; double E, nu; double p[16]; double eps0, eps1; };
+enum { BILINEAR = 0, HOLLOMON = 1, JOHNSON_COOK = 2, GMT_MODEL = 3 };
 
 double mat_yield(const Mat & m, double strain, double strain_rate, double temp)
 {
@@ -194,6 +194,14 @@ double mat_yield(const Mat & m, double strain, double strain_rate, double temp)
         if (strain + m.eps0 > m.eps1) sy = m.p[1] * std::pow(strain + m.eps0, m.p[2]);
         else sy = m.p[0];
         return sy;
+    }
+    if (m.model == GMT_MODEL) {                        // GMT::CalcYieldStress Material.cpp:96-134; p = n1,n2,C1,C2,m1,m2,I1,I2,e_min,e_max,er_min,er_max,T_min,T_max
+        double n1 = m.p[0], n2 = m.p[1], C1 = m.p[2], C2 = m.p[3], m1 = m.p[4], m2 = m.p[5], I1 = m.p[6], I2 = m.p[7];
+        double e = strain, er = strain_rate, T = temp;
+        if (e < m.p[8]) e = m.p[8]; else if (e > m.p[9]) e = m.p[9];
+        if (er < m.p[10]) er = m.p[10]; else if (er > m.p[11]) er = m.p[11];
+        if (T < m.p[12]) T = m.p[12]; else if (T > m.p[13]) T = m.p[13];
+        return C1 * std::exp(C2 * T) * std::pow(e, n1 * T + n2) * std::exp((I1 * T + I2) / e) * std::pow(er, m1 * T + m2);
     }
     // JohnsonCook::CalcYieldStress Material.cpp:6-25; p = A,B,n,C,eps_0,m,T_m,T_t
     double A = m.p[0], B = m.p[1], n = m.p[2], C = m.p[3], e0 = m.p[4], mm = m.p[5], Tm = m.p[6], Tt = m.p[7];
@@ -682,7 +690,7 @@ struct Dom {
             sig_trial = std::sqrt(3.0 * J2);
             SS = smul(std::min((Sigmay[i] / sig_trial), 1.0), SS);
             if (Material_model[i] == HOLLOMON) Sigmay[i] = mat_yield(mats[mat_id[i]], pl_strain[i], 0.0, 0.0);
-            else if (Material_model[i] == JOHNSON_COOK) Sigmay[i] = mat_yield(mats[mat_id[i]], pl_strain[i], eff_strain_rate[i], T[i]);
+            else if (Material_model[i] == JOHNSON_COOK || Material_model[i] == GMT_MODEL) Sigmay[i] = mat_yield(mats[mat_id[i]], pl_strain[i], eff_strain_rate[i], T[i]);
             if (sig_trial > Sigmay[i]) {
                 // Et is computed and discarded for Hollomon/JC; Ep keeps its initial value
                 if (Ep[i] < 0) Ep[i] = 1. * mats[mat_id[i]].E;
@@ -1227,7 +1235,8 @@ void load_case(const wfc::File & in, Dom & d)
     if (in.has("materials")) {
         const dvec & mt = in.f("materials");
         for (size_t r = 0; r + 16 <= mt.size(); r += 16) {
-            Mat m; m.model = (int)mt[r]; m.E = mt[r + 1]; m.nu = mt[r + 2]; for (int k = 0; k < 13; ++k) m.p[k] = mt[r + 3 + k];
+            Mat m; m.model = (int)mt[r]; m.E = mt[r + 1]; m.nu = mt[r + 2]; for (int k = 0; k < 16; ++k) m.p[k] = 0.0; for (int k = 0; k < 13; ++k) m.p[k] = mt[r + 3 + k];
+            if (in.has("materials_ext")) { const dvec & me = in.f("materials_ext"); const size_t q = (r / 16) * 3; for (int k = 0; k < 3 && q + k < me.size(); ++k) m.p[13 + k] = me[q + k]; }
             m.eps0 = m.eps1 = 0.0;
             if (m.model == HOLLOMON) { m.eps0 = m.p[0] / m.E; m.eps1 = std::pow(m.p[0] / m.p[1], 1. / m.p[2]); }   // Material.cpp:48-57
             d.mats.push_back(m);

@@ -6,7 +6,7 @@ from the reference's example drivers plus per-particle property arrays, exactly 
 """
 import numpy as np
 
-BILINEAR, HOLLOMON, JOHNSON_COOK = 0, 1, 2
+BILINEAR, HOLLOMON, JOHNSON_COOK, GMT = 0, 1, 2, 3
 
 
 def cylinder_points(V, Rxy, Lz, r, ghost=False):
@@ -183,6 +183,13 @@ def compression(dx=0.03, nsteps=1, thermal=True, pl_heating=True, alpha=1.0, bet
         case["mat_id"] = np.zeros(n, np.int32)
         # A, B, n, C, eps_0, m, T_m, T_t  (6061-T6-like numbers as in examples/FSW.cpp:113-115 semantics)
         case["materials"] = np.array([JOHNSON_COOK, 70.0e9, 0.3, fy, 114.0e6, 0.42, 0.002, 1.0, 1.34, 925.0, 0.0] + [0.0] * 5)
+    elif model == GMT:
+        case["Material_model"] = np.full(n, GMT, np.int32)
+        case["mat_id"] = np.zeros(n, np.int32)
+        # GMT(el, n1, n2, C1, C2, m1, m2, I1, I2, e_min, e_max, er_min, er_max, T_min, T_max) (Source/Material.h:168-175): the record carries the
+        # first 13 parameters, materials_ext the 14th; sy = C1 exp(C2 T) e^(n1 T + n2) exp((I1 T + I2)/e) er^(m1 T + m2), ~170 MPa at the start
+        case["materials"] = np.array([GMT, 70.0e9, 0.3, 1.0e-4, 0.15, 4.0e8, -0.002, 1.0e-5, 0.02, 1.0e-6, -0.002, 0.01, 3.0, 0.1, 1.0e5, 0.0])
+        case["materials_ext"] = np.array([500.0, 0.0, 0.0])
     return case
 
 

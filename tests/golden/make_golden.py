@@ -28,6 +28,7 @@ def golden_cases():
     out["comp_g1_beta_8"] = cases.perturbed(cases.compression(dx=0.04, nsteps=8, gradient_type=1, beta=1.0), amp=20.0)
     out["comp_hollomon_30"] = cases.perturbed(cases.compression(dx=0.04, nsteps=30, model=cases.HOLLOMON), amp=60.0)
     out["comp_jc_30"] = cases.perturbed(cases.compression(dx=0.04, nsteps=30, model=cases.JOHNSON_COOK), amp=60.0)
+    out["comp_gmt_30"] = cases.perturbed(cases.compression(dx=0.04, nsteps=30, model=cases.GMT), amp=60.0)       # GMT hardening law (Material.cpp:96-134)
     out["contact_1step"] = cases.contact_compression(dx=0.0032, nsteps=1, vmax=5.0, tau=1e-5, dens=8, cfl=0.3)
     out["contact_100"] = cases.contact_compression(dx=0.0032, nsteps=100, vmax=5.0, tau=1e-5, dens=8, cfl=0.3)   # friction stick+slide, yields
     # Domain::gradKernelCorr = true (examples/Contact_Compression_1010.cpp:125 as shipped): corrected gradients + locking summation

@@ -37,6 +37,9 @@ int main() try
         for (double e : eps) std::printf("@ hollomon %a %a\n", ho.CalcYieldStress(e), ho.CalcTangentModulus(e));
         for (double e : eps) for (double sr : { 0., 0.5, 10., 1.e4 }) for (double T : { 294., 400., 800. })
             std::printf("@ jc %a %a %a\n", jc.CalcYieldStress(e, sr, T), jc.CalcTangentModulus(e, sr, T), jc.CalcYieldStress(e));
+        GMT gm(el, 1.0e-4, 0.15, 4.0e8, -0.002, 1.0e-5, 0.02, 1.0e-6, -0.002, 0.01, 3.0, 0.1, 1.0e5, 0.0, 500.0);          // Source/Material.cpp:96-161
+        for (double e : eps) for (double sr : { 0., 0.5, 10., 1.e4 }) for (double T : { 20., 300., 800. })
+            std::printf("@ gmt %a %a\n", gm.CalcYieldStress(e, sr, T), gm.CalcTangentModulus(e, sr, T));
         Material_ * base = &jc;
         std::printf("@ virtual %a %a\n", base->CalcYieldStress(0.01, 2.0, 350.), base->CalcTangentModulus(0.01, 2.0, 350.));
     }

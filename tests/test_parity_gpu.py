@@ -96,7 +96,7 @@ def test_golden_one_step_bit_exact_fields(harness, name):
         assert "gradCorrM" in got and np.abs(got["gradCorrM"].reshape(-1, 9)[:, [0, 4, 8]] - 1.0).max() > 1e-3, "correction matrices must be non-trivial"
 
 
-@pytest.mark.parametrize("name", ["comp_yield_40", "contact_100", "comp_hollomon_30", "comp_jc_30", "gc_comp_yield_40", "gc_g2_jc_12", "gc_contact_60",
+@pytest.mark.parametrize("name", ["comp_yield_40", "contact_100", "comp_hollomon_30", "comp_jc_30", "comp_gmt_30", "gc_comp_yield_40", "gc_g2_jc_12", "gc_contact_60",
                                   "kd_comp_30", "lf_comp_30", "kd_auto_ts", "lf_auto_ts", "kd_auto_ts_acc", "lf_contact_60", "kd_gc_20",
                                   "plate_cubic_40", "plate_quintic_10", "fsw_like_80", "gc_fixed_40", "thermal_solve_25", "thermal_solve_gc_20",
                                   "ghost_comp_yield_40", "ghost_kd_25", "ghost_lf_25"])

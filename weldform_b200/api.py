@@ -27,7 +27,7 @@ class wf_params(C.Structure):
 
 
 class wf_material(C.Structure):
-    _fields_ = [("model", C.c_int), ("E", C.c_double), ("nu", C.c_double), ("p", C.c_double * 13)]
+    _fields_ = [("model", C.c_int), ("E", C.c_double), ("nu", C.c_double), ("p", C.c_double * 16)]
 
 
 _PD = C.POINTER(C.c_double)
@@ -240,8 +240,8 @@ class Context:
         arr = (wf_material * max(len(mats), 1))()
         for k, m in enumerate(mats):
             arr[k].model = int(m[0]); arr[k].E = m[1]; arr[k].nu = m[2]
-            for q in range(13):
-                arr[k].p[q] = m[3 + q]
+            for q in range(16):
+                arr[k].p[q] = m[3 + q] if 3 + q < len(m) else 0.0
         self._ck(self.L.wf_set_materials(self.h, arr, len(mats)), "wf_set_materials")
 
     def add_mesh(self, nodes, elems, normals, nfar, radius, hfac, mesh_id):

@@ -11,6 +11,14 @@ namespace wf {
 __device__ __forceinline__ double yield_stress(const MatProps &m, double strain, double strain_rate, double temp)
 {
     if (m.model == 1) { if (strain + m.eps0 > m.eps1) return m.p[1] * pow(strain + m.eps0, m.p[2]); else return m.p[0]; }
+    if (m.model == 3) {        // GMT::CalcYieldStress (Material.cpp:96-134): clamped strain, strain rate and temperature; p = n1, n2, C1, C2, m1, m2, I1, I2, limits
+        const double n1 = m.p[0], n2 = m.p[1], C1 = m.p[2], C2 = m.p[3], m1 = m.p[4], m2 = m.p[5], I1 = m.p[6], I2 = m.p[7];
+        double e = strain, er = strain_rate, T = temp;
+        if (e < m.p[8]) e = m.p[8]; else if (e > m.p[9]) e = m.p[9];
+        if (er < m.p[10]) er = m.p[10]; else if (er > m.p[11]) er = m.p[11];
+        if (T < m.p[12]) T = m.p[12]; else if (T > m.p[13]) T = m.p[13];
+        return C1 * exp(C2 * T) * pow(e, n1 * T + n2) * exp((I1 * T + I2) / e) * pow(er, m1 * T + m2);
+    }
     const double A = m.p[0], B = m.p[1], n = m.p[2], C = m.p[3], e0 = m.p[4], mm = m.p[5], Tm = m.p[6], Tt = m.p[7];
     const double T_h = (temp - Tt) / (Tm - Tt);
     double f = 1.0;
@@ -53,7 +61,7 @@ __device__ __forceinline__ void stress_update(const PairArgs &a, int64_t s, doub
         SS = ((1.0 < rs) ? 1.0 : rs) * SS;            // std::min(Sigmay/sig_trial, 1.0), NaN-propagating like the reference
         double pl = WF_OWN(F_PLS);
         if (cp.Material_model == 1) Sigmay = yield_stress(a.mats[cp.mat_id], pl, 0.0, 0.0);
-        else if (cp.Material_model == 2) Sigmay = yield_stress(a.mats[cp.mat_id], pl, effsr, q2.z);
+        else if (cp.Material_model == 2 || cp.Material_model == 3) Sigmay = yield_stress(a.mats[cp.mat_id], pl, effsr, q2.z);     // JOHNSON_COOK || _GMT_ (Particle.cpp:999)
         if (sig_trial > Sigmay) {
             double Ep = cp.Ep;
             if (Ep < 0) Ep = 1. * a.mats[cp.mat_id].E;

@@ -181,11 +181,11 @@ extern "C" int wf_set_materials(wf_ctx *c, const wf_material *m, int n)
     c->h_mats.clear();
     for (int k = 0; k < n; ++k) {
         MatProps mp; std::memset(&mp, 0, sizeof(mp));
-        mp.model = m[k].model; mp.E = m[k].E; mp.nu = m[k].nu; for (int q = 0; q < 13; ++q) mp.p[q] = m[k].p[q];
+        mp.model = m[k].model; mp.E = m[k].E; mp.nu = m[k].nu; for (int q = 0; q < 16; ++q) mp.p[q] = m[k].p[q];
         if (mp.model == 1) {       // Hollomon ctor (Source/Material.cpp:48-57)
             mp.eps0 = mp.p[0] / mp.E; mp.eps1 = std::pow(mp.p[0] / mp.p[1], 1. / mp.p[2]);
             if (mp.eps0 > mp.eps1) return fail(c, WF_ERR_ARG, "Hollomon material bad definition (eps0 > eps1), Material.cpp:54");
-        } else if (mp.model != 2 && mp.model != 0) return fail(c, WF_ERR_UNSUPPORTED, "material model %d not implemented (0 bilinear, 1 Hollomon, 2 Johnson-Cook)", mp.model);
+        } else if (mp.model != 2 && mp.model != 3 && mp.model != 0) return fail(c, WF_ERR_UNSUPPORTED, "material model %d not implemented (0 bilinear, 1 Hollomon, 2 Johnson-Cook, 3 GMT)", mp.model);
         c->h_mats.push_back(mp);
     }
     cudaFree(c->d_mats); c->d_mats = nullptr;
@@ -297,9 +297,9 @@ extern "C" int wf_set_particles(wf_ctx *c, const wf_particles *p)
                 cp.TIInitDist = k.d[8]; cp.Ep = k.d[9]; cp.k_T = k.d[10]; cp.cp_T = k.d[11]; cp.h_conv = k.d[12]; cp.T_inf = k.d[13]; cp.th_exp = k.d[14]; cp.q_source = k.d[15];
                 cp.PresEq = k.i[0]; cp.Fail = k.i[1]; cp.Material = k.i[2]; cp.Material_model = k.i[3]; cp.mat_id = k.i[4]; cp.Thermal_BC = k.i[5]; cp.IsMesh = 0;
                 if (cp.Fail > 1) return fail(c, WF_ERR_ARG, "Undefined failure criteria for solids (Fail=%d), Particle.cpp:1062", cp.Fail);
-                if (cp.Fail == 1 && (cp.Material_model == 1 || cp.Material_model == 2) && (cp.mat_id < 0 || cp.mat_id >= (int)c->h_mats.size()))
+                if (cp.Fail == 1 && (cp.Material_model >= 1 && cp.Material_model <= 3) && (cp.mat_id < 0 || cp.mat_id >= (int)c->h_mats.size()))
                     return fail(c, WF_ERR_ARG, "particle %lld uses Material_model %d but mat_id %d is not in the material table", (long long)i, cp.Material_model, cp.mat_id);
-                if (cp.Material_model > 2 || cp.Material_model < 0) return fail(c, WF_ERR_UNSUPPORTED, "Material_model %d not implemented", cp.Material_model);
+                if (cp.Material_model > 3 || cp.Material_model < 0) return fail(c, WF_ERR_UNSUPPORTED, "Material_model %d not implemented", cp.Material_model);
                 if (cp.TI > 0.0) c->any_ti = true;
                 c->h_classes.push_back(cp); table[k] = id;
             } else id = it->second;

@@ -18,7 +18,7 @@ struct ClassProps {
     double G, Cs, P0, RefDensity, Alpha, Beta, TI, TIn, TIInitDist, Ep, k_T, cp_T, h_conv, T_inf, th_exp, q_source;
     int PresEq, Fail, Material, Material_model, mat_id, Thermal_BC, IsMesh, pad;
 };
-struct MatProps { int model, pad; double E, nu, p[13], eps0, eps1; };
+struct MatProps { int model, pad; double E, nu, p[16], eps0, eps1; };
 
 // ---- own (non-gathered) per-particle doubles, structure of arrays: field f of slot s is F[f*cap + s] -------------
 enum OwnField {

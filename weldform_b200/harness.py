@@ -82,7 +82,9 @@ def context_from_case(case, device=0, comm=None):
     p.solver = int(case.get("solver", 0)); p.auto_ts = int(case.get("auto_ts", 0)); p.cfl = float(case.get("CFL", 0.7)); p.auto_ts_acc = int(case.get("auto_ts_acc", 0))
     ctx.set_params(p)
     if "materials" in case:
-        mt = np.asarray(case["materials"], float).reshape(-1, 16)
+        mt = np.asarray(case["materials"], float).reshape(-1, 16)           # [model, E, nu, p0..p12] per material
+        if "materials_ext" in case:                                           # p13..p15 (GMT has 14 parameters)
+            mt = np.concatenate([mt, np.asarray(case["materials_ext"], float).reshape(-1, 3)], axis=1)
         ctx.set_materials([tuple(r) for r in mt])
     # lattice
     kind = int(case.get("gen_kind", 0))

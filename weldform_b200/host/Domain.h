@@ -540,7 +540,7 @@ inline void Domain::backend_begin(double dt)
         if (m && !mat_ids.count(m)) {
             wf_material wm; std::memset(&wm, 0, sizeof(wm));
             wm.model = m->Material_model; wm.E = m->Elastic().E(); wm.nu = m->Elastic().Poisson();
-            for (int k = 0; k < 13; ++k) wm.p[k] = m->params[k];
+            for (int k = 0; k < 16; ++k) wm.p[k] = m->params[k];
             mat_ids[m] = (int)mats.size(); mats.push_back(wm);
         }
     }

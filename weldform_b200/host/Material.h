@@ -10,6 +10,7 @@ using namespace std;      // Source/Material.h:10 -- the reference drivers rely 
 #define BILINEAR      0
 #define HOLLOMON      1
 #define JOHNSON_COOK  2
+#define _GMT_          3
 
 class Elastic_ {
     double E_m = 0.0, nu_m = 0.0;
@@ -26,7 +27,7 @@ protected:
     double T_t = 0.0, T_m = 0.0;
 public:
     int Material_model = BILINEAR;        // which of the subclasses this is (the device needs a plain tag, not a vtable)
-    double params[13] = { 0 };            // Hollomon: sy0, K, m.  Johnson-Cook: A, B, n, C, eps_0, m, T_m, T_t  (wf_material::p)
+    double params[16] = { 0 };            // Hollomon: sy0, K, m.  Johnson-Cook: A, B, n, C, eps_0, m, T_m, T_t.  GMT: n1, n2, C1, C2, m1, m2, I1, I2 + six limits  (wf_material::p)
     Material_() {}
     Material_(const Elastic_ el) : elastic_m(el) {}
     virtual ~Material_() {}
@@ -117,6 +118,41 @@ public:
     }
 private:
     double eps0_m = 0.0, eps1_m = 0.0;
+};
+
+// Source/Material.h:154-222, Material.cpp:96-161: GMT(el, n1, n2, C1, C2, m1, m2, I1, I2, e_min, e_max, er_min, er_max, T_min, T_max):
+// sy = C1 exp(C2 T) e^(n1 T + n2) exp((I1 T + I2) / e) er^(m1 T + m2) with strain, strain rate and temperature clamped to their limits
+class GMT : public Material_ {
+public:
+    GMT() {}
+    GMT(const Elastic_ & el, const double & n1_, const double & n2_, const double & C1_, const double & C2_, const double & m1_, const double & m2_,
+        const double & I1_, const double & I2_, const double & e_min_ = 0.0, const double & e_max_ = 1.0e10, const double & er_min_ = 0.0, const double & er_max_ = 1.0e10,
+        const double & T_min_ = 0.0, const double & T_max_ = 1.0e10) : Material_(el)
+    {
+        Material_model = _GMT_;
+        params[0] = n1_; params[1] = n2_; params[2] = C1_; params[3] = C2_; params[4] = m1_; params[5] = m2_; params[6] = I1_; params[7] = I2_;
+        params[8] = e_min_; params[9] = e_max_; params[10] = er_min_; params[11] = er_max_; params[12] = T_min_; params[13] = T_max_;
+    }
+    double CalcYieldStress() { return 0.0; }
+    double CalcYieldStress(const double &) { return 0.0; }
+    double CalcYieldStress(const double & strain, const double & strain_rate, const double & temp)      // Material.cpp:96-134, same operand order
+    {
+        const double n1 = params[0], n2 = params[1], C1 = params[2], C2 = params[3], m1 = params[4], m2 = params[5], I1 = params[6], I2 = params[7];
+        double e = strain, er = strain_rate, T = temp;
+        if (e < params[8]) e = params[8]; else if (e > params[9]) e = params[9];
+        if (er < params[10]) er = params[10]; else if (er > params[11]) er = params[11];
+        if (T < params[12]) T = params[12]; else if (T > params[13]) T = params[13];
+        return C1 * exp(C2 * T) * pow(e, n1 * T + n2) * exp((I1 * T + I2) / e) * pow(er, m1 * T + m2);
+    }
+    double CalcTangentModulus(const double & plstrain, const double & strain_rate, const double & temp)  // Material.cpp:136-161
+    {
+        const double n1 = params[0], n2 = params[1], C1 = params[2], C2 = params[3], m1 = params[4], m2 = params[5], I1 = params[6], I2 = params[7];
+        double e = plstrain, er = strain_rate, T = temp;
+        if (plstrain < params[8]) e = params[8]; else if (plstrain > params[9]) e = params[9];
+        if (strain_rate < params[10]) er = params[10]; else if (strain_rate > params[11]) er = params[11];
+        if (temp < params[12]) T = params[12]; else if (temp > params[13]) T = params[13];
+        return C1 * exp(C2 * T) * pow(er, m1 * T + m2) * pow(e, T * n1 + n2 - 2.0) * (-I1 * T - I2 + e * (n1 * T + n2)) * exp((I1 * T + I2) / e);
+    }
 };
 
 #endif

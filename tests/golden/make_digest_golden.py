@@ -3,7 +3,7 @@ BASELINE.json's configurations are stated on -- too large to commit as full dump
 
     compression_50k_40     examples/Compression.cpp's scale (dx = 0.0094 -> ~49 k particles), 40 Fraser steps through yield
     compression_1m_3       Compression_thermal at 1 M particles (dx = 0.00362), 3 steps
-    contact_2m_5           the cylinder between two rigid planes at 2 M particles (Contact_Compression_1010's scale), 5 steps with contact forces
+    contact_1m_10 / 2m_10  the cylinder between two rigid planes at 1 M / 2 M particles (Contact_Compression_1010's scale), 10 steps with contact forces
 
 Run in the build container only:   python tests/golden/make_digest_golden.py [name ...]
 
@@ -27,9 +27,10 @@ SAMPLE_FIELDS = ["x", "v", "a", "Displacement", "Density", "Pressure", "pl_strai
 SPECS = {
     "compression_50k_40": dict(dx=0.0094, nsteps=40, perturb_amp=150.0),
     "compression_1m_3": dict(dx=0.00362, nsteps=3, perturb_amp=60.0),
-    # BASELINE configs[2] at its stated scale: 2 M particles between two rigid planes (penalty contact, friction 0.2); the velocity field drives the
-    # end rows INTO the planes so that contact forces act from the second step on
-    "contact_2m_5": dict(dx=0.0028744663089468095, nsteps=5, perturb_amp=-60.0, contact_planes=1.0),
+    # BASELINE configs[2] (contact against rigid planes): the cylinder between two rigid planes (penalty contact, friction 0.2), the upper one driven
+    # down fast enough that a few hundred surface particles are in contact within the ten steps (1 M and 2 M particles)
+    "contact_1m_10": dict(dx=0.00362, nsteps=10, perturb_amp=60.0, contact_planes=1.0, vmax=500.0, tau=1.0e-9),
+    "contact_2m_10": dict(dx=0.0028744663089468095, nsteps=10, perturb_amp=60.0, contact_planes=1.0, vmax=500.0, tau=1.0e-9),
 }
 
 

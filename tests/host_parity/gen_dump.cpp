@@ -21,6 +21,11 @@ int main() try
     { SPH::Domain d; d.Dimension = 3; d.AddCylinderLength(1, Vec3_t(0., 0., -0.056), 0.15, 0.672, 0.02, 2700., 0.048, false, true); dump("AddCylinderLength ghost", d);
       std::printf("@ GhostPairs %zu\n", (size_t)d.GhostPairs.Size());
       for (size_t g = 0; g < d.GhostPairs.Size(); ++g) std::printf("@ %zu %zu %d\n", (size_t)d.GhostPairs[g].first, (size_t)d.GhostPairs[g].second, (int)d.Particles[d.GhostPairs[g].second]->not_write_surf_ID); }
+    for (int symz = 0; symz < 2; ++symz) {
+      SPH::Domain d; d.Dimension = 3; d.AddXYSymCylinderLength(0, 0.0127, 0.015, 0.0006, 7850., 0.00144, false, symz != 0); dump(symz ? "AddXYSymCylinderLength symlength" : "AddXYSymCylinderLength", d);
+      std::printf("@ GhostPairs %zu\n", (size_t)d.GhostPairs.Size());
+      for (size_t g = 0; g < d.GhostPairs.Size(); ++g) { const SPH::Particle * P = d.Particles[d.GhostPairs[g].second];
+          std::printf("@ %zu %zu %d %d %d\n", (size_t)d.GhostPairs[g].first, (size_t)d.GhostPairs[g].second, (int)P->not_write_surf_ID, P->ghost_plane_axis, P->inner_mirr_part); } }
     { SPH::Domain d; d.Dimension = 3; d.AddBoxLength(1, Vec3_t(-0.0155, -0.005, -0.005), 0.0331, 0.0101, 0.0101, 0.0005, 1000., 0.0013, 1, 0, false, false); dump("AddBoxLength", d); }
     { SPH::Domain d; d.Dimension = 3; d.Vol = 0.;
       d.Add3DCubicBoxParticles(1, Vec3_t(0., 0., 0.), 0.1, 0.05, 0.02, 0.005, 1000., 0.012);

@@ -60,7 +60,7 @@ def test_wider_driver_set_still_compiles_unchanged():
 def test_host_generators_and_materials_match_the_reference_bit_for_bit(product_lib):
     """tests/host_parity/gen_dump.cpp compiled against the reference's own headers and against the host mirror: every lattice generator of the
     Domain API (AddCylinderLength with and without ghost rows, AddBoxLength, Add3DCubicBoxParticles + Calculate3DMass, AddTractionProbeLength,
-    AddCylUniformLength full and slice) gives the same positions, masses and GhostPairs, and the Hollomon / Johnson-Cook host evaluations
+    AddCylUniformLength full and slice, AddXYSymCylinderLength with and without the z mirror rows) gives the same positions, masses and GhostPairs, and the Hollomon / Johnson-Cook host evaluations
     (Material.cpp:6-73) the same values, to the last bit (hex floats)."""
     src = os.path.join(ROOT, "tests", "host_parity", "gen_dump.cpp")
     ref_root = os.path.dirname(REF_EXAMPLES)
@@ -73,7 +73,7 @@ def test_host_generators_and_materials_match_the_reference_bit_for_bit(product_l
                                "-L" + os.path.join(ROOT, "weldform_b200"), "-lweldform_b200", "-Wl,-rpath," + os.path.join(ROOT, "weldform_b200")])
         ref = [l for l in subprocess.run([ref_exe], capture_output=True, text=True, timeout=300).stdout.splitlines() if l.startswith("@ ")]
         our = [l for l in subprocess.run([our_exe], capture_output=True, text=True, timeout=300).stdout.splitlines() if l.startswith("@ ")]
-    assert len(ref) > 12000 and sum(l.startswith("@ Add") for l in ref) == 7
+    assert len(ref) > 12000 and sum(l.startswith("@ Add") for l in ref) == 9
     assert len(ref) == len(our)
     bad = [(i, a, b) for i, (a, b) in enumerate(zip(ref, our)) if a != b]
     assert not bad, "first differences (line, reference, mirror): %s" % bad[:5]

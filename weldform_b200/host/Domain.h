@@ -99,6 +99,7 @@ public:
     void AddTractionProbeLength(int tag, Vec3_t const & V, double Rxy, double Lz_side, double Lz_neckmin, double Lz_necktot, double Rxy_center,
                                 double r, double Density, double h, bool Fixed);
     void AddCylUniformLength(int tag, double Rxy, double Lz, double r, double Density, double h, double ang = 2 * M_PI, int rows = 1, double r_i = 0.0, bool ghost = true);
+    void AddXYSymCylinderLength(int tag, double Rxy, double Lz, double r, double Density, double h, bool Fixed, bool symlength = false);
     void Kernel_Set(Kernels_Type const & KT) { KernelType = KT; Cellfac = (KT == Quintic_Spline) ? 3.0 : 2.0; }
     void Gradient_Approach_Set(Gradient_Type const & GT) { GradientType = GT; }
     void Viscosity_Eq_Set(Viscosity_Eq_Type const & VQ) { VisEq = VQ; }
@@ -440,6 +441,74 @@ inline void Domain::AddCylUniformLength(int tag, double Rxy, double Lz, double r
     solid_part_count = (int)Particles.Size();
     for (size_t i = 0; i < Particles.Size(); ++i) Particles[i]->Mass = Mass;
     this->R = r;
+}
+
+// Source/Domain.cpp:880-1140 (3-D): a QUARTER cylinder in x, y > 0 with three mirror rows behind the x = 0 and y = 0 planes (Mirror_XYZ ghosts, axes 0 and 1)
+// and, with symlength, three mirror rows below z = 0 (axis 2). The creation order is the API (GhostPairs index particles): first the body row by row
+// (z, then y, then x), then per z row the y-plane ghost and its transposed x-plane twin alternately, then the z ghosts. Domain::MoveGhost runs on the device.
+inline void Domain::AddXYSymCylinderLength(int tag, double Rxy, double Lz, double r, double Density, double h, bool Fixed, bool symlength)
+{
+    if (Dimension != 3) throw new Fatal("AddXYSymCylinderLength: only Dimension = 3 is implemented in weldform_b200");
+    if (Particles.Size() != 0) throw new Fatal("AddXYSymCylinderLength: the quarter cylinder must be the first particle set (its GhostPairs count particles from 0, Source/Domain.cpp:899)");
+    std::cout << "\n--------------Generating particles by CylinderBoxLength with XY SYMM AND GHOST part defined length of particles-----------" << std::endl;
+    const int ghost_rows = 3;
+    const int edge = detail::calc_half_part_count(r, Rxy, 1);
+    const double z0 = symlength ? r : -Lz / 2. + r;
+    std::vector<int> mirror_x, mirror_y;                 // body particles within three columns of x = 0 / three rows of y = 0, in creation order
+    int per_layer = 0, x_cols_first_layer = 0, made = 0;
+    size_t layer = 0;
+    for (double zp = z0; zp <= (z0 + Lz - r); zp += 2.0 * r, ++layer) {
+        double yp = r;
+        for (int row = 0; row < edge; ++row, yp += 2. * r) {
+            const int cols = detail::calc_half_part_count(r, Rxy, row + 1);
+            double xp = r;
+            for (int col = 0; col < cols; ++col, xp += 2. * r) {
+                Particles.Push(pool_make(tag, Vec3_t(xp, yp, zp), Vec3_t(0, 0, 0), 0.0, Density, h, Fixed));
+                if (col < ghost_rows) { mirror_x.push_back(made); if (layer == 0) x_cols_first_layer++; }
+                if (row < ghost_rows) mirror_y.push_back(made);
+                if (zp == z0) per_layer++;
+                made++;
+            }
+        }
+    }
+    std::cout << "Particles per row: " << per_layer << std::endl;
+    std::cout << " symmetric particles x, y :" << mirror_x.size() << ", " << mirror_y.size() << std::endl;
+    std::cout << "Creating ghost particles" << std::endl;
+    auto make_ghost = [&](const Vec3_t & x, int inner, int axis) {
+        Particle * P = pool_make(tag, x, Vec3_t(0, 0, 0), 0.0, Density, h, Fixed);
+        P->inner_mirr_part = inner; P->ghost_plane_axis = axis; P->is_ghost = true; P->not_write_surf_ID = true;
+        Particles.Push(P);
+        GhostPairs.Push(std::make_pair((size_t)inner, Particles.Size() - 1));
+    };
+    int next_y = 0;
+    layer = 0;
+    for (double zp = z0; zp <= (z0 + Lz - r); zp += 2.0 * r, ++layer) {
+        for (int row = 0; row < ghost_rows; ++row) {
+            const double yp = -r - 2 * r * row;
+            const int cols = detail::calc_half_part_count(r, Rxy, row + 1);
+            int next_x = x_cols_first_layer * (int)layer + row;
+            double xp = r;
+            for (int col = 0; col < cols; ++col, xp += 2. * r) {
+                make_ghost(Vec3_t(xp, yp, zp), mirror_y[next_y], 1);          // behind the y = 0 plane
+                make_ghost(Vec3_t(yp, xp, zp), mirror_x[next_x], 0);          // its transpose behind the x = 0 plane
+                next_y++; next_x += ghost_rows;
+            }
+        }
+    }
+    std::cout << "inserting z particles" << std::endl;
+    if (symlength) {
+        std::cout << "Inserting z ghost particles at z bottom..." << std::endl;
+        double zp = z0 - 2.0 * r; int inner = 0;
+        for (int zr = 0; zr < ghost_rows; ++zr, zp -= 2.0 * r)
+            for (int k = 0; k < per_layer; ++k, ++inner) make_ghost(Vec3_t(Particles[inner]->x(0), Particles[inner]->x(1), zp), inner, 2);
+    }
+    const double Vol_ = M_PI * Rxy * Rxy * Lz;                                  // the FULL cylinder's volume over every particle made, ghosts included (:1121-1122)
+    const double Mass = Vol_ * Density / Particles.Size();
+    std::cout << "Total Particle count: " << Particles.Size() << std::endl;
+    std::cout << "Particle mass: " << Mass << std::endl;
+    for (size_t i = 0; i < Particles.Size(); ++i) Particles[i]->Mass = Mass;
+    solid_part_count = (int)Particles.Size();
+    R = r;
 }
 
 // Source/Domain.cpp:326-455 (3-D cubic packing, type 1, rotation 0, random = false); mass rule :447-455

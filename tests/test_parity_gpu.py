@@ -459,3 +459,44 @@ def test_contracted_arithmetic_1000_steps(harness, oracle_port, model):
     got, ref = harness.run_case(c), ot.run_port(c)
     assert ref["pl_strain"].max() > 5e-3
     _compare(got, ref, TOL_LONG, keys=LONG_KEYS + ["Time", "plastic_work", "int_energy_sum", "max_disp"], what="contracted arithmetic, 1000 steps model %d" % model, case=c)
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+def test_mirror_ghosts_behind_x_and_y_planes(harness, axis):
+    """Domain::MoveGhost for ghost_plane_axis 0 and 1 (the x = 0 / y = 0 mirror rows of AddXYSymCylinderLength, Domain.cpp:880-1140; the generator
+    is pinned bit for bit on the host, tests/test_host_api.py). No reference run exists for these planes (examples/Compression_1010_qt.cpp segfaults
+    in the reference), so the device copy is checked against its definition (Domain.cpp:1183-1207): after every step each ghost carries its inner
+    particle's v and a with the normal component negated, and its Sigma, Strain, ShearStress, StrainRate, RotationRate and Density, exactly."""
+    dx = 0.0012
+    H, L = 0.01, 0.02
+    V = [-H / 2.0, -H / 2.0, -H / 2.0]; dims = [L, H, H]
+    V[axis] = -3.0 * dx; dims[axis] = L + 3.0 * dx                    # three lattice rows behind the plane
+    pts = cases.box_points(tuple(V), dims[0] + dx / 10.0, dims[1] + dx / 10.0, dims[2] + dx / 10.0, dx / 2.0)
+    n = len(pts)
+    key = lambda p: tuple(np.round(p / (dx / 2.0)).astype(np.int64))
+    index = {key(p): i for i, p in enumerate(pts)}
+    pairs = []
+    for g in np.nonzero(pts[:, axis] < 0.0)[0]:
+        q = pts[g].copy(); q[axis] = -q[axis]
+        pairs.append((index[key(q)], int(g)))
+    assert len(pairs) > 100
+    rho, K, G, Fy = 1000.0, 3.25e6, 7.15e5, 4000.0
+    h = 1.2 * dx; Cs = np.sqrt(K / rho); ones = np.ones(n)
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    case = dict(gen_kind=2.0, gen_args=np.array([1, V[0], V[1], V[2], dims[0] + dx / 10.0, dims[1] + dx / 10.0, dims[2] + dx / 10.0, dx / 2.0, rho, h, 1, 0, 0, 0], float),
+                Dimension=3.0, KernelType=0.0, GradientType=0.0, G=G * ones, Cs=Cs * ones, PresEq=np.zeros(n, np.int32), Material=np.full(n, 2, np.int32),
+                Fail=np.ones(n, np.int32), Sigmay=Fy * ones, Alpha=1.0 * ones, Beta=1.0 * ones, TI=0.3 * ones, TIInitDist=dx * ones, ts_nb_inc=5.0,
+                dt=0.2 * h / Cs, nsteps=25.0, mode=0.0, ghost_pairs=np.array(pairs, np.int32).reshape(-1), ghost_axis=np.full(len(pairs), axis, np.int32),
+                v=np.stack([0.3 * np.sin(300.0 * y) * np.cos(200.0 * z) + 12.0 * x, 0.3 * np.cos(250.0 * x) * np.sin(300.0 * z) + 9.0 * y, 0.3 * np.sin(400.0 * x) * np.cos(150.0 * y)], axis=1).reshape(-1))
+    got = harness.run_case(case, with_pairs=False)
+    assert int(got["n_particles"][0]) == n and np.isfinite(got["x"]).all()
+    inner, ghost = np.array(pairs)[:, 0], np.array(pairs)[:, 1]
+    sign = np.ones(3); sign[axis] = -1.0
+    for k in ("v", "a"):
+        f = got[k].reshape(-1, 3)
+        assert np.array_equal(f[ghost], f[inner] * sign), k
+        assert np.abs(f[inner][:, axis]).max() > 0.0
+    for k in ("Sigma", "Strain", "ShearStress", "StrainRate", "RotationRate"):
+        f = got[k].reshape(-1, 9)
+        assert np.array_equal(f[ghost], f[inner]), k
+    assert np.array_equal(got["Density"][ghost], got["Density"][inner])

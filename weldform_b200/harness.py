@@ -160,6 +160,8 @@ def context_from_case(case, device=0, comm=None):
     ctx.set_particles(n, n_sph_global=n_global, **arrays)
     if kind == 1 and ghost_pairs is not None:
         ctx.set_ghost_pairs(ghost_pairs)
+    if "ghost_pairs" in case:                               # explicit Domain::GhostPairs (inner, ghost) + ghost_plane_axis per pair, e.g. mirrors behind x = 0 / y = 0
+        ctx.set_ghost_pairs(np.asarray(case["ghost_pairs"], np.int32).reshape(-1, 2), np.asarray(case["ghost_axis"], np.int32) if "ghost_axis" in case else None)
     for m in range(mesh_count):
         if "mesh%d_w" % m in case:                         # TriMesh::SetRotAxisVel
             ctx.mesh_set_motion(m, (0.0, 0.0, 0.0), tuple(float(w) for w in case["mesh%d_w" % m][:3]))

@@ -213,9 +213,12 @@ def domain_api_e2e(n_particles, steps, warmup, device, log, gpus=1, modes=("push
     out = {}
     # bytes moved per step by the bridge (two callbacks per step), from the mirror's own rules (host/Domain.h): full = every particle,
     # tagged = the rows with a BC ID; down: x v a Displacement (3) Sigma (9) T pl_strain Density Pressure Sigmay (1) ID (int); up: v a
-    for mode, (k, w) in (("push", (steps, warmup)), ("tagged", (max(3, steps // 4), 2)), ("full", (3, 1))):
-        if mode not in modes:
+    for mode, (k, w) in (("push", (steps, warmup)), ("push_indexed", (steps, warmup)), ("tagged", (max(3, steps // 4), 2)), ("full", (3, 1))):
+        if mode not in modes and not (mode == "push_indexed" and "full" in modes):
             continue
+        indexed = mode == "push_indexed"          # the same driver with a callback that visits its rows through index lists instead of testing every particle's ID
+        if indexed:
+            mode = "push"
         env = dict(os.environ, WELDFORM_SYNC=mode, WELDFORM_DEVICE=str(device), WELDFORM_GPUS=str(gpus), OMP_NUM_THREADS=str(threads))
         for k_ in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
             env.pop(k_, None)
@@ -223,11 +226,13 @@ def domain_api_e2e(n_particles, steps, warmup, device, log, gpus=1, modes=("push
         try:
             # full mode moves every particle's mirrored members both ways at both callbacks (seconds per step): it is timed from step 3 on
             # instead of after the 20+ steps of spin-up to the yielding state (the bridge's traffic does not depend on the state)
-            r = subprocess.run([exe, str(int(n_particles)), str(k), str(w), str(PERTURB_AMP), str(threads), "0" if mode == "full" else "1"], capture_output=True, text=True, timeout=1500, env=env)
+            r = subprocess.run([exe, str(int(n_particles)), str(k), str(w), str(PERTURB_AMP), str(threads), "0" if mode == "full" else "1", "1" if indexed else "0"], capture_output=True, text=True, timeout=1500, env=env)
         except subprocess.TimeoutExpired:
             out[mode] = {"error": "timeout"}
             continue
         line = [l for l in r.stdout.splitlines() if l.startswith("BENCH ")]
+        if indexed:
+            mode = "push_indexed"
         if r.returncode != 0 or not line:
             out[mode] = {"error": (r.stdout + r.stderr)[-400:]}
             continue
@@ -238,8 +243,8 @@ def domain_api_e2e(n_particles, steps, warmup, device, log, gpus=1, modes=("push
             if l.startswith("BRIDGE "):
                 ntag = int(l.split("tagged=")[1].split()[0])
         rows = n if mode == "full" else (ntag or 0)
-        down = 0 if mode == "push" else 2 * rows * (4 * 24 + 72 + 5 * 8 + 4)
-        up = (2 * 2 * 2 * 24) if mode == "push" else 2 * rows * 48
+        down = 0 if mode.startswith("push") else 2 * rows * (4 * 24 + 72 + 5 * 8 + 4)
+        up = (2 * 2 * 2 * 24) if mode.startswith("push") else 2 * rows * 48
         out[mode] = {"value": n * k / sec, "ms_per_step": 1e3 * sec / k, "steps": k, "threads": threads, "gpus": gpus, "h2d_bytes_per_step": int(up), "d2h_bytes_per_step": int(down + 3 * 200),
                      "first_timed_step": int(kv["first_step"]), "max_pl_strain": float(kv["max_pl"]), "wall_s_incl_setup": time.time() - t0}
         log("e2e Domain API, WELDFORM_SYNC=%s: %.2f ms/step (%d steps), %.3g particle-steps/s" % (mode, out[mode]["ms_per_step"], k, out[mode]["value"]))

@@ -4,9 +4,10 @@
 // domi.Particles[i]->ID exactly like the reference's drivers do (examples/Compression_thermal.cpp:30-66), twice per step, on host Particle
 // objects; the callback bridge (WELDFORM_SYNC = full | tagged | push) moves the particle data between host and device inside the timed region.
 //
-//   usage: bench_domain <particles> <steps> <warmup> [perturb_amp = 30] [callback threads = 16] [spin-up: 1 (default) wait until the body yields, 0 time from step 2]
+//   usage: bench_domain <particles> <steps> <warmup> [perturb_amp = 30] [callback threads = 16] [spin-up: 1 (default) wait until the body yields, 0 time from step 2] [callback: 0 (default) tests every particle's ID like the reference's examples, 1 visits index lists built at set-up]
 // prints one line:  BENCH particles=<n> steps=<k> seconds=<s> first_step=<i> sync=<mode> max_pl=<..>
 #include <cstdio>
+#include <vector>
 #include <omp.h>
 #include "Domain.h"
 #include "InteractionAlt.cpp"
@@ -14,6 +15,20 @@
 
 #define TAU  0.005
 #define VMAX 10.0
+
+// argv[7] = 1: the callback visits the rows it drives through index lists built once at set-up (what a driver written for ten million particles would
+// do) instead of testing Particles[i]->ID of every particle like the reference's examples: shows how much of the e2e time is the walk itself
+static std::vector<int> rows_top, rows_bottom;
+void UserAccIndexed(SPH::Domain & domi)
+{
+    double vcompress;
+    if (domi.getTime() < TAU) vcompress = VMAX / TAU * domi.getTime();
+    else vcompress = VMAX;
+    #pragma omp parallel for schedule (static) num_threads(domi.Nproc)
+    for (size_t k = 0; k < rows_top.size(); k++) { SPH::Particle * P = domi.Particles[rows_top[k]]; P->a = Vec3_t(0.0, 0.0, 0.0); P->v = Vec3_t(0.0, 0.0, -vcompress); }
+    #pragma omp parallel for schedule (static) num_threads(domi.Nproc)
+    for (size_t k = 0; k < rows_bottom.size(); k++) { SPH::Particle * P = domi.Particles[rows_bottom[k]]; P->a = Vec3_t(0.0, 0.0, 0.0); P->v = Vec3_t(0.0, 0.0, 0.0); }
+}
 
 void UserAcc(SPH::Domain & domi)
 {
@@ -52,14 +67,15 @@ int main(int argc, char ** argv) try
         P->Alpha = 1.0; P->TI = 0.3; P->TIInitDist = dx; P->th_exp = 0.;
         const double x = P->x(0), y = P->x(1), z = P->x(2);
         P->T = 20.0 + 15.0 * sin(7.0 * x) * cos(5.0 * z);
-        if (z < 0) P->ID = 2;
-        if (z > L) P->ID = 3;
+        if (z < 0) { P->ID = 2; rows_bottom.push_back((int)a); }
+        if (z > L) { P->ID = 3; rows_top.push_back((int)a); }
         if (amp != 0.0) P->v = Vec3_t(amp * sin(9.0 * y + 1) * cos(4.0 * z), amp * cos(8.0 * x - 1) * sin(3.0 * z), -amp * z * (1.0 + 0.3 * sin(11.0 * x * y)));
     }
     dom.m_kernel = SPH::iKernel(dom.Dimension, h);
     dom.BC.InOutFlow = 0;
     dom.thermal_solver = true; dom.pl_heating = true; dom.pl_work_heat_frac = 0.9; dom.auto_ts = false;
     const double timestep = 0.2 * h / Cs;
+    if (argc > 7 && std::atoi(argv[7]) != 0) dom.GeneralAfter = &UserAccIndexed;
     dom.bench_steps = steps; dom.bench_warmup = warmup;
     if (argc > 6 && std::atoi(argv[6]) == 0) { dom.bench_spin_min = 2; dom.bench_wait_yield = false; }
     dom.SolveDiffUpdateFraser(1.0e30, timestep, 1.e30, NULL, 1000000);

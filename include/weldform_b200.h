@@ -59,7 +59,7 @@ typedef struct wf_params {
                                 * heat conduction only, one neighbour search at wf_solver_init) */
     int    auto_ts;            /* Domain::auto_ts: CheckMinTSVel + AdaptiveTimeStep (Domain.cpp:205-297); honoured by solvers 1 and 2 only, like the reference */
     double cfl;                /* Domain::CFL (0.7) */
-    int    auto_ts_acc;        /* Domain::auto_ts_acc: CheckMinTSAccel, sqrt_h_a*sqrt(h/|a|) with sqrt_h_a = 0.0025 (Domain.cpp:109,302-317); it replaces the
+    int    auto_ts_acc;        /* Domain::auto_ts_acc: CheckMinTSAccel, sqrt_h_a*sqrt(h/|a|) (Domain.cpp:302-317, sqrt_h_a below); it replaces the
                                 * velocity criterion when both are set, as the reference's call sequence does */
     int    tuning;             /* A/B measurement and test switches, default 0 (never needed for correct results):
                                 *   bit 0 no software-pipelined gathers; bits 1-5 momentum-kernel variants (occupancy, general instead of lean
@@ -70,6 +70,7 @@ typedef struct wf_params {
                                 *   term, on the uniform-h single-class cubic-spline path, wf_pair_fm.cu); bit 11 end-of-step scalar gather in stream order;
                                 *   bit 13 force one slab-rebalancing move at the third rebuild (tests); bit 14 slab rebalancing off; bit 15 keep the
                                 *   Q2 gather in the contracted momentum kernel */
+    double sqrt_h_a;           /* Domain::sqrt_h_a of CheckMinTSAccel; 0 = the reference's default 0.0025 (Domain.cpp:109) */
 } wf_params;
 
 /* Material_ subclasses (Source/Material.h:96-224). model: 0 bilinear (no object), 1 Hollomon, 2 Johnson-Cook, 3 GMT (Material.cpp:96-161). */
@@ -142,6 +143,9 @@ typedef enum wf_field {
 int  wf_create(int device, wf_ctx **out);
 void wf_destroy(wf_ctx *ctx);
 const char *wf_last_error(const wf_ctx *ctx);      /* ctx may be NULL: last error of wf_create */
+/* sizeof of the structures that cross this boundary, in the order wf_params, wf_material, wf_particles, wf_mesh, wf_scalars: a binding in another
+ * language (ctypes, cgo ...) checks its own declarations against the library it loaded. No device needed. */
+int wf_abi_sizes(int64_t out[5]);
 int  wf_sync(wf_ctx *ctx);
 void wf_default_params(wf_params *p);               /* Domain::Domain defaults */
 

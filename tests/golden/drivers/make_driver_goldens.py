@@ -33,6 +33,11 @@ PLAN = {
     "Compression": ("test06", [1], 1),                                      # Gradient_Approach_Set(2): unstable in this snapshot, heap corruption after ~34 steps
     "Contact_Compression_1010": ("test06", [1, 2, 3, 5, 8], 1),             # 457 steps per table
     "FSW": ("test06", [1, 2, 3], 2),                                        # 922 steps per table
+    "Compression_1010": ("test06", [1, 2, 3], 1),                           # Fraser, Hollomon, gradKernelCorr; 92 steps per table
+    "Compression_1010_half_ghost": ("test06", [1, 2, 3], 1),                # Fraser, ghosts
+    "CompressionVel": ("test06", [1, 2, 3, 4], 1),                          # KickDrift, 70 steps per table
+    "Compression_TRIP_vel": ("test06", [1, 2, 3], 1),                       # KickDrift, gradKernelCorr
+    "Contact_Compression_half_ghost": ("test06", [1, 20, 40, 60], 1),      # KickDrift, adaptive time step, ghosts, one rigid plane
 }
 NEEDS = {"FSW": ["Tool.nas"]}
 
@@ -93,17 +98,17 @@ def run_driver(name, exe, key, wanted, timeout_s, env_extra=None, workdir=None):
 
 def table_blocks(logpath):
     """The reference prints `step number: N` ... `Output No. K at T has been generated` in the block it writes with every table
-    (SolverFraser.cpp:418-452) -- and also whenever 60 s of CPU time passed without one, so only the first block of each K counts.
+    (SolverFraser.cpp:418-452, SolverKickDrift.cpp:332-361) -- and also whenever 60 s of CPU time passed without one, so only the first block of each K counts.
     K is printed after the increment: the block of table file idx shows K = idx + 1. Returns {idx: (steps, time)}."""
     out, step = {}, None
     with open(logpath, errors="replace") as f:
         for line in f:
             if line.startswith("step number:"):
                 step = int(line.split(":")[1])
-            elif line.startswith("Output No.") and step is not None:
+            elif line.startswith("Output No."):
                 toks = line.split()
                 k, t = int(toks[2]), float(toks[4])
-                out.setdefault(k - 1, (step, t))
+                out.setdefault(k - 1, (-1 if step is None else step, t))   # the KickDrift / LeapFrog loops do not print the step number
     return out
 
 

@@ -38,6 +38,16 @@ def test_python_binding_covers_the_header(product_lib):
     api.load_library()       # raises if a bound symbol is absent
 
 
+def test_structure_sizes_agree_with_the_library(product_lib):
+    """wf_abi_sizes: the ctypes declarations (weldform_b200/api.py) and the library were built from the same header; a stale build is refused at load."""
+    from weldform_b200 import api
+    L = api.load_library()
+    sizes = (ctypes.c_int64 * 5)()
+    assert L.wf_abi_sizes(sizes) == 0
+    assert list(sizes) == [ctypes.sizeof(t) for t in (api.wf_params, api.wf_material, api.wf_particles, api.wf_mesh, api.wf_scalars)]
+    assert L.wf_abi_sizes(None) != 0
+
+
 def test_no_cpu_fallback(product_lib):
     """Without a CUDA device wf_create must fail loudly; with one this test is vacuous (covered by the gpu tests)."""
     import torch

@@ -10,6 +10,14 @@ What the reference's drivers do in this snapshot (oracle/Makefile, DESIGN.md sec
                              "No external particles found" at step 136                              -> table 1 + the Fatal pinned
   FSW                        segfaults as shipped (same); with the fix it runs (days of CPU time)     -> tables 1-3 (1 845 steps) pinned
   Plate-Yield_3d             calls Domain::Solve, which throws in the reference                      -> the mirror throws alike (test_host_api.py)
+and five more of the reference's examples, unmodified drivers, for the other step orders and set-ups (first tables of each):
+  Compression_1010           Fraser, Hollomon, gradKernelCorr; the callback sums Sigma(2,2) over a particle row
+  Compression_1010_half_ghost  Fraser, Hollomon, half a cylinder with symmetry ghosts (MoveGhost)
+  CompressionVel             SolveDiffUpdateKickDrift with velocity boundary conditions from the callback
+  Compression_TRIP_vel       SolveDiffUpdateKickDrift, gradKernelCorr, bilinear hardening (Ep), a print_history particle
+  Contact_Compression_half_ghost  SolveDiffUpdateKickDrift, adaptive time step, ghosts, gradKernelCorr, a rigid plane steered with SetVel
+Of the reference's 144 example sources 116 compile against the reference's own headers in this snapshot and 98 of them unchanged against the mirror
+(fluids, 2-D, the implicit solver, XDMF restart and the CompactNSearch variants are the rest).
 
 Comparison: the WriteCSV tables carry 6 significant digits. An entry passes when |ours - ref| <= rtol * max(|ref|, floor * max|column|):
 element-wise, with a floor so that entries that are zero up to round-off (vx on the axis ...) are judged against the column's scale.
@@ -75,7 +83,8 @@ def worst_entries(ours, ref, floor):
     return np.max(np.abs(ours - ref) / scale, axis=0)
 
 
-def compare_tables(d, gold, key, rtol_of_table, floor=1e-3, what=""):
+def compare_tables(d, gold, key, rtol_of_table, floor=1e-3, what="", ignore=None):
+    """ignore = (row predicate on the reference table, [column names]): entries the reference itself leaves undefined (uninitialised members)"""
     stride = int(gold["stride"])
     report = {}
     for idx in gold["kept"].tolist():
@@ -86,6 +95,12 @@ def compare_tables(d, gold, key, rtol_of_table, floor=1e-3, what=""):
         assert ours.shape[0] == int(gold["rows_%04d" % idx]), "%s table %d: %d rows, the reference wrote %d" % (what, idx, ours.shape[0], int(gold["rows_%04d" % idx]))
         ours = ours[::stride]
         assert np.array_equal(ours[:, 3], ref[:, 3]), "%s table %d: particle IDs differ" % (what, idx)
+        if ignore is not None:
+            rows = ignore[0](ref)
+            for c in ignore[1]:
+                ref[rows, COLS.index(c)] = 0.0
+                ours[rows, COLS.index(c)] = 0.0
+        assert np.isfinite(ref).all() and np.isfinite(ours).all(), "%s table %d: non-finite entries" % (what, idx)
         w = worst_entries(ours, ref, floor)
         report[idx] = dict(zip(COLS, w.tolist()))
         rtol = rtol_of_table(idx)
@@ -179,4 +194,33 @@ def test_fsw_driver_first_tables():
     assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
     compare_tables(d, gold, "test06", lambda idx: 1e-5, what="FSW")
     compare_history(d, gold, 1e-5, what="FSW")
+    shutil.rmtree(d, ignore_errors=True)
+
+
+MORE = {
+    # driver: (sync modes, rtol of the tables, entries the reference leaves undefined)
+    "Compression_1010": (["full", "tagged"], 2e-5, None),
+    "Compression_1010_half_ghost": (["full", "tagged"], 2e-5, None),
+    "CompressionVel": (["full", "tagged"], 2e-5, None),
+    "Compression_TRIP_vel": (["full"], 2e-5, None),
+    # AddTrimeshParticles leaves Particle::T of the element particles (ID 10) uninitialised in the reference (garbage up to inf in its tables); no thermal solver here
+    # tables 40 and 60 are in contact (from ~step 2 700) and through yield (max plastic strain 0.049 at table 60)
+    "Contact_Compression_half_ghost": (["full"], lambda idx: 2e-5 if idx <= 20 else 1e-3, (lambda ref: ref[:, 3] == 10, ["Temp"])),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,sync", [(n, m) for n, v in MORE.items() for m in v[0]])
+def test_more_reference_drivers_first_tables(name, sync):
+    """Unmodified examples of the reference for the other step orders (KickDrift), symmetry ghosts, the kernel gradient correction and Hollomon /
+    bilinear hardening: the first output tables (a few hundred steps), element-wise against what the reference wrote."""
+    path = os.path.join(GOLD, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("no golden for %s" % name)
+    gold = np.load(path)
+    _, rtol, ignore = MORE[name]
+    d, rc = run_mirror_driver(name, sync, int(gold["kept"].max()), timeout=900)
+    assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
+    compare_tables(d, gold, "test06", rtol if callable(rtol) else (lambda idx: rtol), what="%s/%s" % (name, sync), ignore=ignore)
+    compare_history(d, gold, 1e-5, what="%s/%s" % (name, sync))
     shutil.rmtree(d, ignore_errors=True)

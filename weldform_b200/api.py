@@ -23,7 +23,7 @@ class wf_params(C.Structure):
                 ("friction_function", C.c_int), ("friction_m", C.c_double), ("friction_b", C.c_double),
                 ("pfac", C.c_double), ("dfac", C.c_double), ("contact_force_factor", C.c_double),
                 ("cont_heat_fric", C.c_int), ("cont_heat_cond", C.c_int), ("contact_hc", C.c_double),
-                ("nb_order_reference", C.c_int), ("grad_kernel_corr", C.c_int), ("solver", C.c_int), ("auto_ts", C.c_int), ("cfl", C.c_double), ("auto_ts_acc", C.c_int), ("tuning", C.c_int)]
+                ("nb_order_reference", C.c_int), ("grad_kernel_corr", C.c_int), ("solver", C.c_int), ("auto_ts", C.c_int), ("cfl", C.c_double), ("auto_ts_acc", C.c_int), ("tuning", C.c_int), ("sqrt_h_a", C.c_double)]
 
 
 class wf_material(C.Structure):
@@ -110,6 +110,7 @@ def load_library():
         "wf_plan_slabs_ex": ([_PD, _PD, C.c_int64, C.c_int64, C.c_int, _PD, _PD, C.c_int, _PI, _PI], C.c_int),
         "wf_get_stream": ([vp], vp), "wf_measure_fp64_peak": ([vp, _PD], C.c_int),
         "wf_prof_name": ([C.c_int], C.c_char_p), "wf_launch_count": ([vp, C.POINTER(C.c_int64)], C.c_int),
+        "wf_abi_sizes": ([C.POINTER(C.c_int64)], C.c_int),
     }
     for name in ["wf_step_begin", "wf_density", "wf_rate_stress", "wf_accel", "wf_contact", "wf_apply_bcs", "wf_integrate_pos", "wf_integrate_vel",
                  "wf_thermal", "wf_energy", "wf_step_end", "wf_fraser_stage_a", "wf_fraser_stage_b1", "wf_fraser_stage_b2", "wf_fraser_stage_c"]:
@@ -118,6 +119,12 @@ def load_library():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = res
+    sizes = (C.c_int64 * 5)()
+    L.wf_abi_sizes(sizes)
+    mine = [C.sizeof(t) for t in (wf_params, wf_material, wf_particles, wf_mesh, wf_scalars)]
+    if list(sizes) != mine:
+        raise WeldformError("%s was built from another include/weldform_b200.h: structure sizes %s, this binding declares %s (rebuild: python -m weldform_b200.build)"
+                            % (path, list(sizes), mine))
     _lib = L
     return L
 

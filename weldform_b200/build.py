@@ -79,7 +79,8 @@ def build_host_examples(force=False):
 
 
 REF_EXAMPLES = "/root/reference/examples"
-REF_DRIVERS = ["Compression", "Compression_thermal", "Contact_Compression_1010", "FSW"]
+REF_DRIVERS = ["Compression", "Compression_thermal", "Contact_Compression_1010", "FSW",
+               "Compression_1010", "Compression_1010_half_ghost", "CompressionVel", "Compression_TRIP_vel", "Contact_Compression_half_ghost"]
 
 
 def build_reference_drivers(force=False):

@@ -119,6 +119,12 @@ extern "C" int wf_get_grid(wf_ctx *c, double blpf[3], double trpr[3], double cel
 }
 
 extern "C" const char *wf_last_error(const wf_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+extern "C" int wf_abi_sizes(int64_t out[5])
+{
+    if (!out) return WF_ERR_ARG;
+    out[0] = sizeof(wf_params); out[1] = sizeof(wf_material); out[2] = sizeof(wf_particles); out[3] = sizeof(wf_mesh); out[4] = sizeof(wf_scalars);
+    return 0;
+}
 
 extern "C" void *wf_get_stream(wf_ctx *c) { return c ? (void *)c->stream : nullptr; }
 

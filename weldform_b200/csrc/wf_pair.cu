@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128) k_temp_inc_pp(PairArgs a)
 
 // ---- Domain::CheckMinTSVel (Domain.cpp:267-297): min over all particles of CFL * (nearest listed neighbour) / (Cs + |v|);
 // the CFL factor and the comparison with deltatint are applied by the caller
-__global__ void __launch_bounds__(128) k_min_ts(PairArgs a, double cfl, int accel_criterion, double *partial)
+__global__ void __launch_bounds__(128) k_min_ts(PairArgs a, double cfl, double sqrt_h_a, double *partial)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + a.s0;
     double test = 1.0e300;
@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(128) k_min_ts(PairArgs a, double cfl, int acce
         const double4 qi = a.Q0[s], wi = a.Q1[s];
         const V3 xi = v3(qi.x, qi.y, qi.z);
         double mn = 1000.;
-        if (accel_criterion) {      // Domain::CheckMinTSAccel (Domain.cpp:302-317): sqrt_h_a * sqrt(h / |a|), sqrt_h_a = 0.0025 (Domain.cpp:109)
-            test = 0.0025 * sqrt(qi.w / norm(v3(OWN(F_AX), OWN(F_AY), OWN(F_AZ))));
+        if (sqrt_h_a != 0.0) {      // Domain::CheckMinTSAccel (Domain.cpp:302-317): sqrt_h_a * sqrt(h / |a|); 0 selects the velocity criterion
+            test = sqrt_h_a * sqrt(qi.w / norm(v3(OWN(F_AX), OWN(F_AY), OWN(F_AZ))));
         } else {
         if (a.orig[s] < a.nsph) {
             const int cnt = a.nb_cnt[s], nhi = a.nb_hi[s];
@@ -792,7 +792,7 @@ int pair_min_ts(wf_ctx *c, double *test_min)
     WF_CHECK(ensure_stage(c, (size_t)(g + 8) * sizeof(double)));
     double *partial = (double *)c->stage;
     {   ProfScope ps(c, PK_REDUCE);
-        k_min_ts<<<g, 128, 0, c->stream>>>(a, c->prm.cfl, c->prm.auto_ts_acc ? 1 : 0, partial + 8); WF_LAUNCH_CHECK(c);
+        k_min_ts<<<g, 128, 0, c->stream>>>(a, c->prm.cfl, c->prm.auto_ts_acc ? (c->prm.sqrt_h_a != 0.0 ? c->prm.sqrt_h_a : 0.0025) : 0.0, partial + 8); WF_LAUNCH_CHECK(c);
         k_min_final<<<1, 256, 0, c->stream>>>(partial + 8, g, partial); WF_LAUNCH_CHECK(c); c->launches += 2; }
     WF_CUDA(c, cudaMemcpyAsync(test_min, partial, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     WF_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -89,6 +89,9 @@ public:
     {
         destroy();
         if (ngpus < 1) ngpus = 1;
+        int64_t sz[5] = {0, 0, 0, 0, 0}; wf_abi_sizes(sz);
+        if (sz[0] != (int64_t)sizeof(wf_params) || sz[1] != (int64_t)sizeof(wf_material) || sz[2] != (int64_t)sizeof(wf_particles) || sz[3] != (int64_t)sizeof(wf_mesh) || sz[4] != (int64_t)sizeof(wf_scalars))
+            throw new Fatal("weldform_b200: libweldform_b200.so was built from another include/weldform_b200.h than this program (structure sizes differ): rebuild both");
         ctx.assign((size_t)ngpus, nullptr);
         for (int r = 0; r < ngpus; ++r)
             if (wf_create(device0 + r, &ctx[(size_t)r]) != 0) { std::string e = wf_last_error(nullptr); destroy_ctxs(); throw new Fatal("weldform_b200: GPU %d: %s", device0 + r, e.c_str()); }
@@ -257,7 +260,6 @@ private:
     void register_group(Group & g)
     {
         // owner rank and local index of every member: local index = position in the rank's ascending creation-index list
-        std::vector<int32_t> where(g.idx.size(), -1);
         for (int r = 0; r < n; ++r) {
             if (g.handle[(size_t)r] >= 0) { wf_subset_release(ctx[(size_t)r], g.handle[(size_t)r]); g.handle[(size_t)r] = -1; }
             g.pos[(size_t)r].clear();

@@ -164,7 +164,7 @@ public:
     Array<Particle *> Particles;
     Array<std::pair<size_t, size_t> > GhostPairs;                  // Domain.h:473 (inner particle, ghost particle)
     double m_scalar_prop = 0.0, Vol = 0.0, R = 0.0;          // Vol: accumulated by Add3DCubicBoxParticles for Calculate3DMass (Domain.h:337); R: particle radius of the last lattice
-    double sqrt_h_a = 0.0025;                                // Domain.cpp:109; the device's CheckMinTSAccel uses this value, anything else is refused in backend_begin
+    double sqrt_h_a = 0.0025;                                // Domain.cpp:109 (CheckMinTSAccel)
     Vec3_t max_disp;
     double contact_force_sum = 0.0, contact_reaction_sum = 0.0, ext_forces_work = 0.0, plastic_work = 0.0, accum_cont_heat_cond = 0.0,
            contact_friction_work = 0.0, kin_energy_sum = 0.0, int_energy_sum = 0.0, max_contact_force = 0.0, m_maxT = 0.0, m_minT = 0.0;
@@ -596,7 +596,7 @@ inline void Domain::backend_begin(double dt)
     p.cont_heat_fric = cont_heat_fric; p.cont_heat_cond = cont_heat_cond; p.contact_hc = contact_hc;
     p.solver = solver_kind; p.auto_ts = (solver_kind != 0 && auto_ts) ? 1 : 0; p.auto_ts_acc = (solver_kind != 0 && auto_ts_acc) ? 1 : 0; p.cfl = CFL;   // auto_ts is dead code in the Fraser loop (SolverFraser.cpp:500-502)
     p.grad_kernel_corr = gradKernelCorr ? 1 : 0;     // CalcGradCorrMatrix + the locking summation the reference switches to (SolverFraser.cpp:112-115)
-    if (auto_ts_acc && sqrt_h_a != 0.0025) throw new Fatal("Domain::sqrt_h_a = %g: the device time-step criterion uses the reference's default 0.0025 only", sqrt_h_a);
+    p.sqrt_h_a = sqrt_h_a;
     if (contact && contact_alg != Wang) throw new Fatal("Domain::contact_alg = %d: only CalcContactForcesWang (the default, Source/Domain.cpp:169) is implemented in weldform_b200", contact_alg);
     if (XSPH != 0.0) throw new Fatal("Domain::XSPH != 0 is not implemented in weldform_b200 (the reference's new solvers never compute VXSPH either)");
     { const char * tn = std::getenv("WELDFORM_TUNING"); if (tn) p.tuning = std::atoi(tn); }      // wf_params::tuning (A/B and test switches of the library)
@@ -946,9 +946,13 @@ inline void Domain::solve_kick_drift_leap_frog(int solver, double tf, double dt,
     deltat = dt; deltatmin = dt;
     backend_begin(dt);
     size_t idx_out = 1; double tout = Time;
+    // SolverKickDrift.cpp:50,100-101 / SolverLeapfrog.cpp: Prop.csv gets (time, m_scalar_prop) and History.csv a row per print_history particle with every table
+    prop_of.open("Prop.csv", std::ios::out);
+    history_of.open("History.csv", std::ios::out);
+    history_of << "Displacement, pl_strain, eff_strain_rate, sigma_eq, sigmay, contforcesum" << endl;
     auto t0 = std::chrono::steady_clock::now();
     refresh_scalars();
-    while (Time <= tf && idx_out <= maxidx) {
+    while (Time <= tf && idx_out <= maxidx && !env_stop(idx_out)) {
         if (GeneralBefore) run_callback(GeneralBefore);
         bk.phase_i("wf_solver_stage 0", wf_solver_stage, 0);
         if (GeneralAfter) { refresh_scalars(); run_callback(GeneralAfter); }     // fix free accel
@@ -965,8 +969,16 @@ inline void Domain::solve_kick_drift_leap_frog(int solver, double tf, double dt,
             if (TheFileKey != NULL) { String fn; fn.Printf("%s_%04d", TheFileKey, (int)idx_out); sync_down(true); WriteCSV(fn.CStr()); }
             idx_out++; tout += dtOut;
             std::cout << "Output No. " << idx_out << " at " << Time << " has been generated\nCurrent Time Step = " << deltat << "\n";
+            prop_of << getTime() << ", " << m_scalar_prop << endl;                    // SolverKickDrift.cpp:379-387
+            for (size_t p = 0; p < Particles.Size(); p++)
+                if (Particles[p]->print_history) {
+                    if (TheFileKey == NULL) sync_down(true);
+                    history_of << Particles[p]->Displacement << ", " << Particles[p]->pl_strain << ", " << Particles[p]->eff_strain_rate << ", "
+                               << Particles[p]->Sigma_eq << ", " << Particles[p]->Sigmay << ", " << contact_force_sum << endl;
+                }
         }
     }
+    history_of.close(); prop_of.close();
     bk.phase("wf_sync", wf_sync);
     wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     sync_down(true);

@@ -202,10 +202,10 @@ MORE = {
     "Compression_1010": (["full", "tagged"], 2e-5, None),
     "Compression_1010_half_ghost": (["full", "tagged"], 2e-5, None),
     "CompressionVel": (["full", "tagged"], 2e-5, None),
-    "Compression_TRIP_vel": (["full"], 2e-5, None),
+    "Compression_TRIP_vel": (["full"], 5e-5, None),                 # measured worst entry 1.2e-5 (ay at table 3, 2 400 steps with gradKernelCorr)
     # AddTrimeshParticles leaves Particle::T of the element particles (ID 10) uninitialised in the reference (garbage up to inf in its tables); no thermal solver here
-    # tables 40 and 60 are in contact (from ~step 2 700) and through yield (max plastic strain 0.049 at table 60)
-    "Contact_Compression_half_ghost": (["full"], lambda idx: 2e-5 if idx <= 20 else 1e-3, (lambda ref: ref[:, 3] == 10, ["Temp"])),
+    # tables 40 and 60 are in contact (from ~step 2 700) and through yield (max plastic strain 0.049 at table 60); measured worst entry 1.7e-6
+    "Contact_Compression_half_ghost": (["full"], 2e-5, (lambda ref: ref[:, 3] == 10, ["Temp"])),
 }
 
 

@@ -2,11 +2,12 @@
 # the indexed-callback variant of the e2e driver
 tag=${1:-r2_v7}
 mkdir -p gpurun_out/drv_$tag
-WF_KEEP_DRIVER_OUT=gpurun_out/drv_$tag timeout 1500 python -m pytest tests/test_drivers_gpu.py -m gpu -q -k more 2>&1 | tail -60 > gpurun_out/pytest_drivers_$tag.log
-tail -25 gpurun_out/pytest_drivers_$tag.log
-find gpurun_out/drv_$tag -name "test06_*.csv" | grep -v -E "_(0001|0002|0003|0004|0020|0040|0060).csv" | xargs -r rm -f
-find gpurun_out/drv_$tag -name "*.csv" -size +3M -delete
-python -m pytest tests/test_abi.py tests/test_host_api.py -q -m gpu 2>&1 | tail -3
+WF_KEEP_DRIVER_OUT=$PWD/gpurun_out/drv_$tag timeout 1500 python -m pytest tests/test_drivers_gpu.py -m gpu -q -k "${3:-more}" 2>&1 | grep -v "^  \|^$" | cut -c1-400 | tail -120 > gpurun_out/pytest_drivers_$tag.log
+tail -60 gpurun_out/pytest_drivers_$tag.log
+for d in gpurun_out/drv_$tag/*/; do echo "== $d"; tail -4 $d/log.txt | cut -c1-300; done 2>/dev/null | tail -120
+find gpurun_out/drv_$tag -name "*.csv" -size +100k | grep -v -E "Contact_Compression_2surf_short_full/test06_(0005|0010|0015).csv" | xargs -r rm -f      # the per-table worst entries are in report.jsonl
+python -m pytest tests/test_parity_gpu.py -m gpu -q -k digest 2>&1 | tail -5
+[ "$2" = "nobench" ] && exit 0
 python bench.py > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err
 tail -4 gpurun_out/bench_${tag}.err
 python - <<PY

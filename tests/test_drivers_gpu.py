@@ -103,9 +103,26 @@ def compare_tables(d, gold, key, rtol_of_table, floor=1e-3, what="", ignore=None
         assert np.isfinite(ref).all() and np.isfinite(ours).all(), "%s table %d: non-finite entries" % (what, idx)
         w = worst_entries(ours, ref, floor)
         report[idx] = dict(zip(COLS, w.tolist()))
+        if os.environ.get("WF_KEEP_DRIVER_OUT"):
+            import json
+            with open(os.path.join(os.environ["WF_KEEP_DRIVER_OUT"], "report.jsonl"), "a") as f:
+                sd = worst_entries(gold["alt_%04d" % idx].astype(np.float64), ref, floor).tolist() if "alt_%04d" % idx in gold else None
+                f.write(json.dumps({"what": what, "table": idx, "worst": float(w.max()), "column": COLS[int(np.argmax(w))], "per_column": report[idx],
+                                    "reference_4_threads_vs_1": dict(zip(COLS, sd)) if sd else None}) + "\n")
         rtol = rtol_of_table(idx)
-        bad = {c: v for c, v in report[idx].items() if v > rtol}
-        assert not bad, "%s table %d (rtol %.1e, element-wise): %s" % (what, idx, rtol, bad)
+        tol = {c: rtol for c in COLS}
+        if "alt_%04d" % idx in gold:
+            # the reference's own reproducibility: its 4-thread run against its 1-thread run (the golden), same metric; an entry may differ from the golden
+            # by ten times what the reference differs from itself in that column (one alternative run is a coarse estimate of the spread), and by 3 % of the
+            # largest such difference of the table (x, v and p integrate a: where a is reproducible to 7e-3, v is not reproducible to 2e-5)
+            alt = gold["alt_%04d" % idx].astype(np.float64)
+            if ignore is not None:
+                for c in ignore[1]:
+                    alt[rows, COLS.index(c)] = 0.0
+            selfdiff = worst_entries(alt, ref, floor)
+            tol = {c: max(rtol, 10.0 * float(sd), 0.03 * float(selfdiff.max())) for c, sd in zip(COLS, selfdiff)}
+        bad = {c: (v, tol[c]) for c, v in report[idx].items() if v > tol[c]}
+        assert not bad, "%s table %d (element-wise; column: (error, tolerance)): %s" % (what, idx, bad)
     return report
 
 
@@ -124,7 +141,12 @@ def compare_history(d, gold, rtol, what=""):
                 continue
             matched += 1
             r = ref[j[0]]
-            scale = np.maximum(np.abs(r), 1e-3 * np.nanmax(np.abs(ref), axis=0))
+            with np.errstate(all="ignore"):
+                scale = np.maximum(np.abs(r), 1e-3 * np.nanmax(np.abs(ref), axis=0))
+            # the columns after the time stamp are components of force vectors: one that vanishes by symmetry is a sum of
+            # cancelling per-particle terms, each as large as those of the dominant component and each reproducible to the tables' 1e-5 only: it is
+            # compared against 10 % of the row's largest component (an absolute tolerance of 1e-6 of the resultant)
+            scale = np.fmax(scale, 0.1 * np.nanmax(np.abs(r[1:])) if r.size > 1 and np.isfinite(r[1:]).any() else 0.0)
             scale[~(scale > 0)] = 1.0
             err = np.abs(row - r) / scale
             assert np.nanmax(err) <= rtol, "%s %s row t=%g: %s vs %s" % (what, fname, row[0], row, r)
@@ -197,16 +219,44 @@ def test_fsw_driver_first_tables():
     shutil.rmtree(d, ignore_errors=True)
 
 
+# AddTrimeshParticles leaves Particle::T of the element particles (IDs 10 and 11 in these drivers) uninitialised in the reference unless the driver
+# assigns it (heap garbage, up to inf, in its tables): not compared where no thermal solver runs. Twisting's own particles carry such garbage too.
+MESH_T = (lambda ref: np.isin(ref[:, 3], (10.0, 11.0)), ["Temp"])
+ALL_T = (lambda ref: np.ones(ref.shape[0], dtype=bool), ["Temp"])
+
+# driver: (sync modes, rtol of the tables, entries the reference leaves undefined, WELDFORM_TUNING: "0" = the library's default arithmetic)
+# The drivers of the last block step at the stability limit (Traction*: dt = h / (Cs + v), "standard modified Verlet do not accept such step" in the
+# driver's own words) or sit at a contact onset: the reference's OWN round-off is amplified there -- its 4-thread run differs from its 1-thread run by
+# up to O(1) in a and v within a few hundred steps (Traction_Hollomon table 10: vx 0.11, ay 25, p 4e-4, while x and pl_strain agree to 1e-5), and so does
+# any other arithmetic (the exact mode included: pow() of libm and of CUDA differ in the last bit). Their goldens carry that second reference run
+# (alt_<idx>, make_driver_goldens.py --alt) and an entry may differ from the golden by max(rtol, 10 x the reference's own difference in that column).
 MORE = {
-    # driver: (sync modes, rtol of the tables, entries the reference leaves undefined)
-    "Compression_1010": (["full", "tagged"], 2e-5, None),
-    "Compression_1010_half_ghost": (["full", "tagged"], 2e-5, None),
-    "CompressionVel": (["full", "tagged"], 2e-5, None),
-    "Compression_TRIP_vel": (["full"], 5e-5, None),                 # measured worst entry 1.2e-5 (ay at table 3, 2 400 steps with gradKernelCorr)
-    # AddTrimeshParticles leaves Particle::T of the element particles (ID 10) uninitialised in the reference (garbage up to inf in its tables); no thermal solver here
+    "Compression_1010": (["full", "tagged"], 2e-5, None, "0"),
+    "Compression_1010_half_ghost": (["full", "tagged"], 2e-5, None, "0"),
+    "CompressionVel": (["full", "tagged"], 2e-5, None, "0"),
+    "Compression_TRIP_vel": (["full"], 5e-5, None, "0"),                 # measured worst entry 1.2e-5 (ay at table 3, 2 400 steps with gradKernelCorr)
     # tables 40 and 60 are in contact (from ~step 2 700) and through yield (max plastic strain 0.049 at table 60); measured worst entry 1.7e-6
-    "Contact_Compression_half_ghost": (["full"], 2e-5, (lambda ref: ref[:, 3] == 10, ["Temp"])),
+    "Contact_Compression_half_ghost": (["full"], 2e-5, MESH_T, "0"),
+    # third set (oracle/Makefile MORE_DRIVERS): contact with one and two rigid surfaces in the KickDrift and Fraser loops, thermal contact, a rotating
+    # surface, the thin-plate FSW set-up (194 262 particles, tool mesh from Tool.nas), traction probes with three hardening laws, the LeapFrog loop
+    "Contact_Compression_TRIP_2surf": (["full"], 2e-5, MESH_T, "0"),    # table 1 only: the reference explodes right after
+    "Contact_Compression_1010_1side": (["full"], 2e-5, MESH_T, "0"),
+    "Contact_Compression_vel": (["full"], 2e-5, MESH_T, "0"),
+    "FSW_thin": (["full"], 2e-5, None, "0"),
+    "slice_test": (["full"], 2e-5, None, "0"),
+    "Twisting": (["full"], 2e-5, ALL_T, "0"),
+    # one particle of this driver lies exactly on the diagonal shared by two mesh triangles (x = -y): whether the inside test (crit < 0, Contact_Wang.cpp:158-168)
+    # admits one triangle or both is decided by the last bit of x, and a second hit overwrites contforce with a tiny value (x_pred already carries the first
+    # hit's acceleration, :139) -- its CF entry is a coin flip for any arithmetic but the reference's own, so this one runs with the exact arithmetic (1024)
+    "Contact_Compression_2surf_short": (["full"], 2e-5, MESH_T, "1024"),
+    "Contact_Compression_1010_unif": (["full"], 2e-5, MESH_T, "0"),
+    "Contact_Compression_thermal": (["full"], 2e-5, None, "0"),
+    "Contact_Compression_Rot": (["full"], 2e-5, None, "0"),
+    "Traction": (["full"], 2e-5, None, "0"),
+    "Traction_JC": (["full"], 2e-5, None, "0"),
+    "Traction_Hollomon": (["full"], 2e-5, None, "0"),
 }
+NEEDS = {"FSW_thin": ["Tool.nas"]}
 
 
 @pytest.mark.gpu
@@ -218,8 +268,8 @@ def test_more_reference_drivers_first_tables(name, sync):
     if not os.path.exists(path):
         pytest.skip("no golden for %s" % name)
     gold = np.load(path)
-    _, rtol, ignore = MORE[name]
-    d, rc = run_mirror_driver(name, sync, int(gold["kept"].max()), timeout=900)
+    _, rtol, ignore, tuning = MORE[name]
+    d, rc = run_mirror_driver(name, sync, int(gold["kept"].max()), needs=NEEDS.get(name, ()), timeout=900, extra_env={"WELDFORM_TUNING": tuning})
     assert rc == 0, open(os.path.join(d, "log.txt")).read()[-3000:]
     compare_tables(d, gold, "test06", rtol if callable(rtol) else (lambda idx: rtol), what="%s/%s" % (name, sync), ignore=ignore)
     compare_history(d, gold, 1e-5, what="%s/%s" % (name, sync))

@@ -80,7 +80,10 @@ def build_host_examples(force=False):
 
 REF_EXAMPLES = "/root/reference/examples"
 REF_DRIVERS = ["Compression", "Compression_thermal", "Contact_Compression_1010", "FSW",
-               "Compression_1010", "Compression_1010_half_ghost", "CompressionVel", "Compression_TRIP_vel", "Contact_Compression_half_ghost"]
+               "Compression_1010", "Compression_1010_half_ghost", "CompressionVel", "Compression_TRIP_vel", "Contact_Compression_half_ghost",
+               "Contact_Compression_TRIP_2surf", "Contact_Compression_1010_1side", "Contact_Compression_2surf_short", "Contact_Compression_vel",
+               "Contact_Compression_1010_unif", "Contact_Compression_thermal", "Contact_Compression_Rot", "FSW_thin",
+               "slice_test", "Traction", "Traction_JC", "Traction_Hollomon", "Twisting"]
 
 
 def build_reference_drivers(force=False):

@@ -10,7 +10,7 @@ What the reference's drivers do in this snapshot (oracle/Makefile, DESIGN.md sec
                              "No external particles found" at step 136                              -> table 1 + the Fatal pinned
   FSW                        segfaults as shipped (same); with the fix it runs (days of CPU time)     -> tables 1-3 (1 845 steps) pinned
   Plate-Yield_3d             calls Domain::Solve, which throws in the reference                      -> the mirror throws alike (test_host_api.py)
-and five more of the reference's examples, unmodified drivers, for the other step orders and set-ups (first tables of each):
+and nineteen more of the reference's examples, unmodified drivers, for the other step orders and set-ups (first tables of each; MORE below lists all):
   Compression_1010           Fraser, Hollomon, gradKernelCorr; the callback sums Sigma(2,2) over a particle row
   Compression_1010_half_ghost  Fraser, Hollomon, half a cylinder with symmetry ghosts (MoveGhost)
   CompressionVel             SolveDiffUpdateKickDrift with velocity boundary conditions from the callback

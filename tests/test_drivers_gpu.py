@@ -274,3 +274,34 @@ def test_more_reference_drivers_first_tables(name, sync):
     compare_tables(d, gold, "test06", rtol if callable(rtol) else (lambda idx: rtol), what="%s/%s" % (name, sync), ignore=ignore)
     compare_history(d, gold, 1e-5, what="%s/%s" % (name, sync))
     shutil.rmtree(d, ignore_errors=True)
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("name", ["Compression_thermal", "CompressionVel", "Contact_Compression_half_ghost", "Contact_Compression_1010_1side", "Traction", "Twisting"])
+def test_reference_drivers_on_two_gpus(name):
+    """The same unmodified drivers with WELDFORM_GPUS=2 (host/Backend.h: one process, two wf_ctx, slab decomposition, NCCL halos; Domain::Particles stays
+    global): Fraser with the callback bridge, KickDrift, KickDrift + ghosts + a rigid plane, contact, a traction probe, LeapFrog -- against the same goldens
+    of the reference and the same tolerances as on one GPU."""
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    if name == "Compression_thermal":
+        sync, rtol, ignore, tuning, last = "tagged", (lambda idx: 2e-5 if idx <= 30 else 1e-4), None, "0", 30
+    else:
+        syncs, rtol, ignore, tuning = MORE[name]
+        sync, last = syncs[0], int(gold["kept"].max())
+    d, rc = run_mirror_driver(name, sync, last, needs=NEEDS.get(name, ()), timeout=900, extra_env={"WELDFORM_TUNING": tuning, "WELDFORM_GPUS": "2"})
+    log = open(os.path.join(d, "log.txt")).read()
+    assert rc == 0, log[-3000:]
+    assert "weldform_b200: 2 GPU(s)" in log, log[:2000]
+    sub = {k: gold[k] for k in gold.files}
+    sub["kept"] = gold["kept"][gold["kept"] <= last]
+    compare_tables(d, sub, "test06", rtol if callable(rtol) else (lambda idx: rtol), what="%s/2gpu" % name, ignore=ignore)
+    shutil.rmtree(d, ignore_errors=True)

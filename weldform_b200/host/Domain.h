@@ -584,6 +584,7 @@ inline void Domain::choose_sync()
 inline void Domain::backend_begin(double dt)
 {
     bk.create(device, gpus); backend = bk.c0();
+    std::cout << "weldform_b200: " << gpus << " GPU(s), first device " << device << std::endl;
     const size_t ntot = Particles.Size();
     const size_t nsph = !first_fem_particle_idx.empty() ? (size_t)first_fem_particle_idx[0] : ntot;
     if (nsph == 0) throw new Fatal("Domain: no particles");

@@ -195,6 +195,19 @@ int comm_global_minmax(wf_ctx *c, double *mn, double *mx)
     return 0;
 }
 
+// A rank-local failure inside a collective section (capacity checks of the migration and the halo set-up) must become every rank's failure: a rank
+// that simply returned would leave its peers blocked in the next send / receive. All ranks call this with their local status (0 or a negative
+// wf_status, message already recorded by fail()); all return the same: 0, or the failing rank's status on that rank and WF_ERR_ARG elsewhere.
+int comm_agree(wf_ctx *c, int local_status, const char *what)
+{
+    if (c->comm.nranks <= 1) return local_status;
+    double lo = (double)local_status, hi = (double)local_status;
+    WF_CHECK(comm_global_minmax(c, &lo, &hi));
+    if (lo == 0.0) return 0;
+    if (local_status != 0) return local_status;
+    return fail(c, WF_ERR_ARG, "%s failed on another GPU rank (status %d); this rank stops with it", what, (int)lo);
+}
+
 // CalculateSurface (Domain.cpp:1421-1425) sums the particle masses serially in creation order; with the particles spread over
 // ranks every rank scatters its masses into a zeroed creation-ordered array, the arrays are summed (exact: one non-zero
 // contributor per entry) and each rank repeats the reference's serial sum over the result.
@@ -449,13 +462,17 @@ int comm_migrate(wf_ctx *c, int64_t *n_sort, int64_t *n_out)
     int out[2] = { 0, 0 }, in[2] = { 0, 0 };
     WF_CUDA(c, cudaMemcpyAsync(out, m.d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     WF_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (out[0] > m.emig_cap || out[1] > m.emig_cap) return fail(c, WF_ERR_NOMEM, "migration: %d/%d particles leave the slab at once (capacity %lld)", out[0], out[1], (long long)m.emig_cap);
-    if (m.rank == 0 && out[0]) return fail(c, WF_ERR_ARG, "migration: %d particles left the cell grid below rank 0", out[0]);
-    if (m.rank == m.nranks - 1 && out[1]) return fail(c, WF_ERR_ARG, "migration: %d particles left the cell grid above the last rank", out[1]);
+    int st = 0;
+    if (out[0] > m.emig_cap || out[1] > m.emig_cap) st = fail(c, WF_ERR_NOMEM, "migration: %d/%d particles leave the slab at once (capacity %lld)", out[0], out[1], (long long)m.emig_cap);
+    else if (m.rank == 0 && out[0]) st = fail(c, WF_ERR_ARG, "migration: %d particles left the cell grid below rank 0", out[0]);
+    else if (m.rank == m.nranks - 1 && out[1]) st = fail(c, WF_ERR_ARG, "migration: %d particles left the cell grid above the last rank", out[1]);
+    WF_CHECK(comm_agree(c, st, "particle migration"));
     WF_CHECK(exchange_counts(c, out, in));
     const int NF = 24 + F_COUNT + I_COUNT;
     const int64_t total_in = (int64_t)in[0] + in[1];
-    if (c->n_loc + total_in > c->cap) return fail(c, WF_ERR_NOMEM, "migration: %lld local + %lld incoming particles exceed the %lld allocated slots", (long long)c->n_loc, (long long)total_in, (long long)c->cap);
+    st = 0;
+    if (c->n_loc + total_in > c->cap) st = fail(c, WF_ERR_NOMEM, "migration: %lld local + %lld incoming particles exceed the %lld allocated slots", (long long)c->n_loc, (long long)total_in, (long long)c->cap);
+    WF_CHECK(comm_agree(c, st, "particle migration"));
     const size_t need = (size_t)NF * std::max(std::max(out[0], out[1]), std::max(in[0], in[1])) * sizeof(double);
     if (need > m.stage_cap) {
         for (int d = 0; d < 2; ++d) { cudaFree(m.stage_send[d]); cudaFree(m.stage_recv[d]); m.stage_send[d] = m.stage_recv[d] = nullptr; }
@@ -508,7 +525,9 @@ int comm_halo_setup(wf_ctx *c, const unsigned long long *sorted_keys)
     m.halo_lo_start = c->n_loc; m.halo_lo_n = rcv[0];
     m.halo_hi_start = c->n_loc + rcv[0]; m.halo_hi_n = rcv[1];
     c->n = c->n_loc + rcv[0] + rcv[1];
-    if (c->n > c->cap) return fail(c, WF_ERR_NOMEM, "halo: %lld local + %d + %d halo particles exceed the %lld allocated slots", (long long)c->n_loc, rcv[0], rcv[1], (long long)c->cap);
+    { int st = 0;
+      if (c->n > c->cap) st = fail(c, WF_ERR_NOMEM, "halo: %lld local + %d + %d halo particles exceed the %lld allocated slots", (long long)c->n_loc, rcv[0], rcv[1], (long long)c->cap);
+      WF_CHECK(comm_agree(c, st, "halo set-up")); }
     m.halo_bytes_step = 8LL * 32 * (m.send_lo_n + m.send_hi_n);
     WF_CHECK(comm_halo_refresh(c, HALO_Q0 | HALO_Q1 | HALO_Q2 | HALO_S));
     const int ifields[4] = { I_ORIG, I_ID, I_CLS, I_FREE };

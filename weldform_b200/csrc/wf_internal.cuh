@@ -213,6 +213,7 @@ int comm_red_wait(wf_ctx *c);                            // compute stream waits
 int comm_nb_exchange(wf_ctx *c);                        // migration + halo set-up inside the neighbour build
 int comm_global_grid(wf_ctx *c, double BL[3], double TR[3], double *hmax);
 int comm_global_minmax(wf_ctx *c, double *mn, double *mx);
+int comm_agree(wf_ctx *c, int local_status, const char *what);
 int comm_unify_classes(wf_ctx *c, std::vector<wf::ClassProps> &cls, std::vector<int> &remap);   // one class table for all ranks (halo neighbours carry class indices)
 int comm_serial_mass_sum(wf_ctx *c, const double *mass, const int64_t *gidx, int64_t n_local, int64_t n_global, double *tot);
 int comm_plan_layers(wf_ctx *c, const std::vector<long long> &hist);

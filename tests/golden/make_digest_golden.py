@@ -3,6 +3,7 @@ BASELINE.json's configurations are stated on -- too large to commit as full dump
 
     compression_50k_40     examples/Compression.cpp's scale (dx = 0.0094 -> ~49 k particles), 40 Fraser steps through yield
     compression_1m_3       Compression_thermal at 1 M particles (dx = 0.00362), 3 steps
+    compression_4m_2       Compression_thermal at 4 M particles (dx = 0.00228), 2 steps: the largest the reference runs in this container's memory
     contact_1m_10 / 2m_10  the cylinder between two rigid planes at 1 M / 2 M particles (Contact_Compression_1010's scale), 10 steps with contact forces
 
 Run in the build container only:   python tests/golden/make_digest_golden.py [name ...]
@@ -27,6 +28,8 @@ SAMPLE_FIELDS = ["x", "v", "a", "Displacement", "Density", "Pressure", "pl_strai
 SPECS = {
     "compression_50k_40": dict(dx=0.0094, nsteps=40, perturb_amp=150.0),
     "compression_1m_3": dict(dx=0.00362, nsteps=3, perturb_amp=60.0),
+    # 4 M of BASELINE's ten million particles: the largest the reference runs in the build container's 62 GB (5 M ends in std::bad_alloc: per-pair tables)
+    "compression_4m_2": dict(dx=0.00228, nsteps=2, perturb_amp=60.0),
     # BASELINE configs[2] (contact against rigid planes): the cylinder between two rigid planes (penalty contact, friction 0.2), the upper one driven
     # down fast enough that a few hundred surface particles are in contact within the ten steps (1 M and 2 M particles)
     "contact_1m_10": dict(dx=0.00362, nsteps=10, perturb_amp=60.0, contact_planes=1.0, vmax=500.0, tau=1.0e-9),

@@ -7,6 +7,8 @@ BASELINE.json's configurations are stated on -- too large to commit as full dump
     contact_1m_10 / 2m_10  the cylinder between two rigid planes at 1 M / 2 M particles (Contact_Compression_1010's scale), 10 steps with contact forces
 
 Run in the build container only:   python tests/golden/make_digest_golden.py [name ...]
+(At millions of particles the reference spends far longer tearing its Domain down than running: compression_4m_2 wrote its dump after 11 minutes and was
+still freeing memory 85 minutes later; its digest was built from the finished dump with digest_of() and the process stopped.)
 
 A digest holds: the arguments that regenerate the case (tests/cases.compression_fast), the pair count, sum(Nb), for every fp64 field of the
 dump its sum / min / max / sum of squares over all particles, and the full rows of SAMPLE_ROWS particles (fixed seed) for the fields in

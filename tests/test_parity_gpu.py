@@ -382,10 +382,11 @@ def test_ghost_rows_with_gradient_correction(harness, oracle_port, solver):
     _compare(got, ref, 1e-7, what="ghost + gradKernelCorr, solver %d" % solver)
 
 
-@pytest.mark.parametrize("name", [n for n in ("compression_50k_40", "compression_1m_3", "contact_1m_10", "contact_2m_10") if os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "digest", n + ".npz"))])
+@pytest.mark.parametrize("name", [n for n in ("compression_50k_40", "compression_1m_3", "compression_4m_2", "contact_1m_10", "contact_2m_10") if os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "digest", n + ".npz"))])
 def test_baseline_scale_digest(harness, name):
     """Parity at the sizes BASELINE.json's configurations are stated on: digests of the UNMODIFIED reference solver's own runs
-    (tests/golden/make_digest_golden.py: ~49 k particles x 40 steps through yield, 1.0 M particles x 3 steps) against the CUDA path on the
+    (tests/golden/make_digest_golden.py: ~49 k particles x 40 steps through yield, 1.0 M particles x 3 steps, 3.9 M particles x 2 steps -- the largest the
+    reference runs in the build container's memory --, 1 M and 2 M particles x 10 steps with rigid-plane contact) against the CUDA path on the
     regenerated case: pair count and sum(Nb) exact, 10 000 sampled particle rows ELEMENT-WISE, and whole-field sums / extrema."""
     from tests.golden import make_digest_golden as mdg
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "digest", name + ".npz"))

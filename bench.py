@@ -544,7 +544,7 @@ def run_ours(args):
         barrier()
         cpu_group = dist.new_group(backend="gloo")
         if rank == 0:
-            e2e_domain = domain_api_e2e(n_target, args.steps, max(args.warmup, 3), 0, log, gpus=world, modes=("push",))
+            e2e_domain = domain_api_e2e(n_target, args.steps, max(args.warmup, 3), 0, log, gpus=world, modes=("push", "push_indexed"))
         dist.barrier(group=cpu_group)
     if e2e_domain and e2e_domain.get("push") and "value" in e2e_domain["push"]:
         py = e2e

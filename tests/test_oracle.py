@@ -131,3 +131,21 @@ def test_reference_is_reproducible_across_thread_counts_only_in_its_mechanical_f
         assert ot.max_rel(b[k], a[k]) <= 1e-11, k
     racy = {k: ot.max_rel(b[k], a[k]) for k in ("T", "dTdt", "dkin_energy_dt")}
     print("reference Nproc=4 vs Nproc=1 (racy sums):", {k: "%.1e" % v for k, v in racy.items()})
+
+
+def _random_case(seed):
+    """A seeded draw over the switches of the Fraser loop the fixtures fix one at a time: artificial viscosity, tensile-instability factor, gradient
+    form, hardening law, thermal coupling, rebuild cadence, perturbation amplitude (large enough to yield within the run)."""
+    rng = np.random.default_rng(1000 + seed)
+    model = [cases.BILINEAR, cases.HOLLOMON, cases.JOHNSON_COOK, cases.GMT][seed % 4]
+    c = cases.compression(dx=float(rng.choice([0.03, 0.0275])), nsteps=14, thermal=bool(rng.integers(0, 2)), pl_heating=bool(rng.integers(0, 2)),
+                          alpha=float(rng.uniform(0.5, 2.5)), beta=float(rng.choice([0.0, 1.5])), ti=float(rng.choice([0.0, 0.3])),
+                          gradient_type=int(rng.integers(0, 3)), model=model, ts_nb_inc=int(rng.choice([1, 5])))
+    return cases.perturbed(c, amp=float(rng.uniform(40.0, 90.0)), seed=seed)
+
+
+@pytest.mark.skipif(not ot.have_ref(), reason="oracle/_ref/wf_ref not built here (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(8))
+def test_port_matches_live_reference_on_random_switch_combinations(oracle_port, seed):
+    case = _random_case(seed)
+    _assert_same(ot.run_port(case), ot.run_ref(case, nproc=1), "random case %d" % seed)

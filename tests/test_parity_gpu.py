@@ -462,6 +462,23 @@ def test_contracted_arithmetic_1000_steps(harness, oracle_port, model):
     _compare(got, ref, TOL_LONG, keys=LONG_KEYS + ["Time", "plastic_work", "int_energy_sum", "max_disp"], what="contracted arithmetic, 1000 steps model %d" % model, case=c)
 
 
+@pytest.mark.parametrize("mode", ["exact", "default"])
+@pytest.mark.parametrize("seed", range(8))
+def test_random_switch_combinations(harness, oracle_port, seed, mode):
+    """Seeded draws over the switches of the Fraser loop (artificial viscosity alpha / beta, tensile-instability factor, the three gradient forms, the four
+    hardening laws, thermal coupling and plastic heating on / off, rebuild cadence), 14 steps through yield: the oracle port is bit-identical to the
+    unmodified reference on exactly these cases (tests/test_oracle.py::test_port_matches_live_reference_on_random_switch_combinations, CPU); here the CUDA
+    path against the port in both arithmetic modes."""
+    from tests.test_oracle import _random_case
+    c = _random_case(seed)
+    if mode == "default":
+        c["tuning"] = FM
+    got, ref = harness.run_case(c), ot.run_port(c)
+    assert ref["pl_strain"].max() > 1e-3
+    keys = None if mode == "exact" else LONG_KEYS + ["Time", "plastic_work", "int_energy_sum", "max_disp"]
+    _compare(got, ref, TOL_LONG, keys=keys, what="random case %d, %s arithmetic" % (seed, mode), case=c)
+
+
 @pytest.mark.parametrize("axis", [0, 1])
 def test_mirror_ghosts_behind_x_and_y_planes(harness, axis):
     """Domain::MoveGhost for ghost_plane_axis 0 and 1 (the x = 0 / y = 0 mirror rows of AddXYSymCylinderLength, Domain.cpp:880-1140; the generator
